@@ -1,0 +1,1303 @@
+/* bn254_oracle.c -- CPU restatement of the bls-bn254 hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product (libbls_bn254_b200.so) never links, loads or calls it.
+ *
+ * PARITY PINNING: pinned.  Checked by tests/test_oracle.py against every golden vector the
+ * reference carries for this path (tests/golden/reference_kats.json, extracted from
+ * /root/reference/src/inner_types/g1.rs:980-1141, g2.rs:1038-1313, pairings.rs:387-479) and
+ * cross-checked against the independent big-integer model oracle/pymodel.py.  The reference
+ * itself cannot be compiled here (Rust; no cargo/rustc in the image), so there is no
+ * oracle/_ref.
+ *
+ * What it follows (file:line under /root/reference/src/inner_types):
+ *   Fp         fp.rs:115-122 (from_okm), 207-243 (invert, sqrt), 246-260 (repr), 388-431
+ *              (the crate reduces with crypto-bigint 0.5.5 const_rem_wide; here: 4x64-bit
+ *              Montgomery -- same residues, canonical on every boundary)
+ *   Fp2        fp2.rs:95-99 (sgn0), 161-218 (invert, sqrt Alg.9 2012/685), 377-452
+ *   SvdW       fp.rs:284-371 (G1), fp2.rs:221-287 (G2)
+ *   XMD        elliptic-curve 0.13.8 hash2curve::ExpandMsgXmd<Sha256> (NOT in the reference tree;
+ *              RFC 9380 5.3.1 restated; call sites fp.rs:433-458, fp2.rs:463-488)
+ *   G1/G2      orc_curve_tmpl.h; g2.rs:685-693 (clear_cofactor), 938-954 (psi); codecs
+ *              g1.rs:283-360, g2.rs:274-388
+ *   Pairing    pairings.rs:888-962 (ell / doubling_step / addition_step, verbatim formulas),
+ *              52-115 (fp4_square / cyclotomic_square structure), 499-514 (Gt::to_repr) with the
+ *              "Tier B" corrections of SURVEY.md 0.5: xi = 9+u, D-twist placement 0/3/4, loop over
+ *              NAF(6x+2) + two Frobenius additions, Fuentes-Castaneda hard part, correct
+ *              Frobenius constants.  That is the function the reference's own known-answer
+ *              test (pairings.rs:970-980, Gt::generator()) demands.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "orc_constants.h"
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fp;
+typedef struct { fp c0, c1; } fp2;
+typedef struct { fp2 c0, c1, c2; } fp6;
+typedef struct { fp6 c0, c1; } fp12;
+
+static __thread uint64_t g_mul_count; /* Fp multiplications + squarings (work unit "M") */
+
+/* ------------------------------------------------------------------ Fp (Montgomery, R = 2^256) */
+static fp FP_ONE, FP_R2;
+static const fp FP_ZERO = {{0, 0, 0, 0}};
+
+static int fp_is_zero(const fp *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static int fp_eq(const fp *a, const fp *b) {
+    return ((a->l[0] ^ b->l[0]) | (a->l[1] ^ b->l[1]) | (a->l[2] ^ b->l[2]) | (a->l[3] ^ b->l[3])) == 0;
+}
+static void fp_set_zero(fp *a) { *a = FP_ZERO; }
+static void fp_set_one(fp *a) { *a = FP_ONE; }
+
+static int ge_p(const uint64_t *t) {
+    for (int i = 3; i >= 0; i--) {
+        if (t[i] > ORC_P[i]) return 1;
+        if (t[i] < ORC_P[i]) return 0;
+    }
+    return 1;
+}
+static void sub_p(uint64_t *t) {
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)t[i] - ORC_P[i] - (uint64_t)br;
+        t[i] = (uint64_t)d;
+        br = (d >> 64) & 1;
+    }
+}
+static void fp_add(fp *r, const fp *a, const fp *b) { /* fp.rs:388-390 */
+    u128 c = 0;
+    uint64_t t[4];
+    for (int i = 0; i < 4; i++) { c += (u128)a->l[i] + b->l[i]; t[i] = (uint64_t)c; c >>= 64; }
+    if (c || ge_p(t)) sub_p(t);
+    memcpy(r->l, t, 32);
+}
+static void fp_sub(fp *r, const fp *a, const fp *b) { /* fp.rs:396-398 */
+    uint64_t t[4];
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a->l[i] - b->l[i] - (uint64_t)br;
+        t[i] = (uint64_t)d;
+        br = (d >> 64) & 1;
+    }
+    if (br) {
+        u128 c = 0;
+        for (int i = 0; i < 4; i++) { c += (u128)t[i] + ORC_P[i]; t[i] = (uint64_t)c; c >>= 64; }
+    }
+    memcpy(r->l, t, 32);
+}
+static void fp_neg(fp *r, const fp *a) { fp_sub(r, &FP_ZERO, a); } /* fp.rs:400-402 */
+static void fp_dbl(fp *r, const fp *a) { fp_add(r, a, a); }
+
+static void fp_mul(fp *r, const fp *a, const fp *b) { /* fp.rs:404-407, as Montgomery CIOS */
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    g_mul_count++;
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a->l[j] * b->l[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * ORC_INV64;
+        c = (u128)m * ORC_P[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * ORC_P[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    if (t[4] || ge_p(t)) sub_p(t);
+    memcpy(r->l, t, 32);
+}
+static void fp_sqr(fp *r, const fp *a) { fp_mul(r, a, a); } /* fp.rs:409-412 */
+
+static void fp_from_canon(fp *r, const uint64_t w[4]) { fp t; memcpy(t.l, w, 32); fp_mul(r, &t, &FP_R2); }
+static void fp_to_canon(uint64_t w[4], const fp *a) { fp one = {{1, 0, 0, 0}}, t; fp_mul(&t, a, &one); memcpy(w, t.l, 32); }
+
+/* a^e, e little-endian 64-bit limbs (ff::Field::pow; call sites fp.rs:228,429) */
+static void fp_pow(fp *r, const fp *a, const uint64_t e[4]) {
+    fp acc = FP_ONE, base = *a;
+    for (int i = 255; i >= 0; i--) {
+        fp_sqr(&acc, &acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(&acc, &acc, &base);
+    }
+    *r = acc;
+}
+static void fp_inv(fp *r, const fp *a) { fp_pow(r, a, ORC_P_MINUS_2); } /* fp.rs:207-210; 0 -> 0 */
+static int fp_is_square(const fp *a) { /* fp.rs:428-431 */
+    fp t;
+    fp_pow(&t, a, ORC_P_MINUS_1_DIV_2);
+    return fp_is_zero(&t) || fp_eq(&t, &FP_ONE);
+}
+static int fp_sqrt(fp *r, const fp *a) { /* fp.rs:212-243 with v = 1: a^((p+1)/4), checked */
+    fp y, t;
+    fp_pow(&y, a, ORC_P_PLUS_1_DIV_4);
+    fp_sqr(&t, &y);
+    *r = y;
+    return fp_eq(&t, a);
+}
+static int fp_parity(const fp *a) { uint64_t w[4]; fp_to_canon(w, a); return (int)(w[0] & 1); } /* sgn0, fp.rs:164-168 */
+
+/* 32 BE bytes -> fp; returns 0 if >= p (fp.rs:249-254) */
+static int fp_from_be(fp *r, const uint8_t b[32]) {
+    uint64_t w[4];
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = 0;
+        for (int j = 0; j < 8; j++) v = (v << 8) | b[(3 - i) * 8 + j];
+        w[i] = v;
+    }
+    if (ge_p(w)) return 0;
+    fp_from_canon(r, w);
+    return 1;
+}
+static void fp_to_be(uint8_t b[32], const fp *a) { /* fp.rs:256-260 */
+    uint64_t w[4];
+    fp_to_canon(w, a);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 8; j++) b[(3 - i) * 8 + j] = (uint8_t)(w[i] >> (56 - 8 * j));
+}
+/* 48 BE bytes mod p (fp.rs:115-122): value = hi(16 B) * 2^256 + lo(32 B) */
+static void fp_from_okm(fp *r, const uint8_t b[48]) {
+    fp hi, lo, t;
+    uint64_t w[4] = {0, 0, 0, 0};
+    for (int j = 0; j < 8; j++) w[1] = (w[1] << 8) | b[j];
+    for (int j = 0; j < 8; j++) w[0] = (w[0] << 8) | b[8 + j];
+    memcpy(hi.l, w, 32);
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = 0;
+        for (int j = 0; j < 8; j++) v = (v << 8) | b[16 + (3 - i) * 8 + j];
+        w[i] = v;
+    }
+    memcpy(lo.l, w, 32);
+    /* mont(hi*2^256 + lo) = hi*R*R + lo*R = montmul(montmul(hi,R2),R2) + montmul(lo,R2) */
+    fp_mul(&hi, &hi, &FP_R2);
+    fp_mul(&hi, &hi, &FP_R2);
+    fp_mul(&t, &lo, &FP_R2); /* lo may be >= p: montmul handles any input < 2^256 */
+    fp_add(r, &hi, &t);
+}
+
+/* ------------------------------------------------------------------ Fp2 = Fp[u]/(u^2+1) */
+static fp2 F2_B, F2_B3, F2_ENDO_U, F2_ENDO_V, F2_SVDW_C1, F2_SVDW_C2, F2_SVDW_C3, F2_SVDW_C4;
+static fp2 F2_GAMMA[3][5];
+static fp F_SVDW_C2, F_SVDW_C3, F_SVDW_C4, F_THREE, F_FOUR;
+
+static void fp2_set_zero(fp2 *a) { a->c0 = FP_ZERO; a->c1 = FP_ZERO; }
+static void fp2_set_one(fp2 *a) { a->c0 = FP_ONE; a->c1 = FP_ZERO; }
+static int fp2_is_zero(const fp2 *a) { return fp_is_zero(&a->c0) && fp_is_zero(&a->c1); }
+static int fp2_eq(const fp2 *a, const fp2 *b) { return fp_eq(&a->c0, &b->c0) && fp_eq(&a->c1, &b->c1); }
+static void fp2_add(fp2 *r, const fp2 *a, const fp2 *b) { fp_add(&r->c0, &a->c0, &b->c0); fp_add(&r->c1, &a->c1, &b->c1); }
+static void fp2_sub(fp2 *r, const fp2 *a, const fp2 *b) { fp_sub(&r->c0, &a->c0, &b->c0); fp_sub(&r->c1, &a->c1, &b->c1); }
+static void fp2_neg(fp2 *r, const fp2 *a) { fp_neg(&r->c0, &a->c0); fp_neg(&r->c1, &a->c1); }
+static void fp2_dbl(fp2 *r, const fp2 *a) { fp2_add(r, a, a); }
+static void fp2_conj(fp2 *r, const fp2 *a) { r->c0 = a->c0; fp_neg(&r->c1, &a->c1); }
+static void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) { /* fp2.rs:377-390 (schoolbook) */
+    fp t0, t1, t2, t3;
+    fp_mul(&t0, &a->c0, &b->c0);
+    fp_mul(&t1, &a->c1, &b->c1);
+    fp_mul(&t2, &a->c0, &b->c1);
+    fp_mul(&t3, &a->c1, &b->c0);
+    fp_sub(&r->c0, &t0, &t1);
+    fp_add(&r->c1, &t2, &t3);
+}
+static void fp2_sqr(fp2 *r, const fp2 *a) { /* fp2.rs:392-402 */
+    fp s, d, m;
+    fp_add(&s, &a->c0, &a->c1);
+    fp_sub(&d, &a->c0, &a->c1);
+    fp_mul(&m, &a->c0, &a->c1);
+    fp_mul(&r->c0, &s, &d);
+    fp_dbl(&r->c1, &m);
+}
+static void fp2_mul_fp(fp2 *r, const fp2 *a, const fp *s) { fp_mul(&r->c0, &a->c0, s); fp_mul(&r->c1, &a->c1, s); }
+static void fp2_mul_xi(fp2 *r, const fp2 *a) { /* (9+u)(a0+a1 u) = (9a0-a1) + (a0+9a1)u */
+    fp t0, t1, n0, n1;
+    fp_dbl(&t0, &a->c0); fp_dbl(&t0, &t0); fp_dbl(&t0, &t0); fp_add(&t0, &t0, &a->c0); /* 9 a0 */
+    fp_dbl(&t1, &a->c1); fp_dbl(&t1, &t1); fp_dbl(&t1, &t1); fp_add(&t1, &t1, &a->c1); /* 9 a1 */
+    fp_sub(&n0, &t0, &a->c1);
+    fp_add(&n1, &t1, &a->c0);
+    r->c0 = n0; r->c1 = n1;
+}
+static void fp2_inv(fp2 *r, const fp2 *a) { /* fp2.rs:161-166 */
+    fp t0, t1;
+    fp_sqr(&t0, &a->c0);
+    fp_sqr(&t1, &a->c1);
+    fp_add(&t0, &t0, &t1);
+    fp_inv(&t0, &t0);
+    fp_mul(&r->c0, &a->c0, &t0);
+    fp_neg(&t0, &t0);
+    fp_mul(&r->c1, &a->c1, &t0);
+}
+static int fp2_sgn0(const fp2 *a) { /* fp2.rs:95-99 */
+    return fp_parity(&a->c0) | (fp_is_zero(&a->c0) & fp_parity(&a->c1));
+}
+static int fp2_is_square(const fp2 *a) { /* fp2.rs:441-452 */
+    fp t0, t1;
+    fp_sqr(&t0, &a->c0);
+    fp_sqr(&t1, &a->c1);
+    fp_add(&t0, &t0, &t1);
+    return fp_is_square(&t0);
+}
+static void fp2_pow(fp2 *r, const fp2 *a, const uint64_t e[4]) {
+    fp2 acc, base = *a;
+    int started = 0;
+    fp2_set_one(&acc);
+    for (int i = 255; i >= 0; i--) {
+        if (started) fp2_sqr(&acc, &acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) { fp2_mul(&acc, &acc, &base); started = 1; }
+    }
+    *r = acc;
+}
+static int fp2_sqrt(fp2 *r, const fp2 *a) { /* fp2.rs:172-218 */
+    fp2 a1, alpha, x0, s, t, m1;
+    if (fp2_is_zero(a)) { fp2_set_zero(r); return 1; }
+    fp2_pow(&a1, a, ORC_P_MINUS_3_DIV_4);
+    fp2_sqr(&alpha, &a1);
+    fp2_mul(&alpha, &alpha, a);
+    fp2_mul(&x0, &a1, a);
+    fp2_set_one(&m1);
+    fp2_neg(&m1, &m1);
+    if (fp2_eq(&alpha, &m1)) {
+        fp_neg(&s.c0, &x0.c1);
+        s.c1 = x0.c0;
+    } else {
+        fp2_set_one(&t);
+        fp2_add(&t, &t, &alpha);
+        fp2_pow(&t, &t, ORC_P_MINUS_1_DIV_2);
+        fp2_mul(&s, &t, &x0);
+    }
+    fp2_sqr(&t, &s);
+    *r = s;
+    return fp2_eq(&t, a);
+}
+static void fp2_from_canon(fp2 *r, const uint64_t w[2][4]) { fp_from_canon(&r->c0, w[0]); fp_from_canon(&r->c1, w[1]); }
+
+/* ------------------------------------------------------------------ Fp6 = Fp2[v]/(v^3 - xi) */
+static void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) { fp2_add(&r->c0, &a->c0, &b->c0); fp2_add(&r->c1, &a->c1, &b->c1); fp2_add(&r->c2, &a->c2, &b->c2); }
+static void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) { fp2_sub(&r->c0, &a->c0, &b->c0); fp2_sub(&r->c1, &a->c1, &b->c1); fp2_sub(&r->c2, &a->c2, &b->c2); }
+static void fp6_neg(fp6 *r, const fp6 *a) { fp2_neg(&r->c0, &a->c0); fp2_neg(&r->c1, &a->c1); fp2_neg(&r->c2, &a->c2); }
+static void fp6_mul(fp6 *r, const fp6 *a, const fp6 *b) { /* Karatsuba, 6 Fp2 mul (role of fp6.rs:225-242) */
+    fp2 v0, v1, v2, t0, t1, t2, c0, c1, c2;
+    fp2_mul(&v0, &a->c0, &b->c0);
+    fp2_mul(&v1, &a->c1, &b->c1);
+    fp2_mul(&v2, &a->c2, &b->c2);
+    fp2_add(&t0, &a->c1, &a->c2); fp2_add(&t1, &b->c1, &b->c2); fp2_mul(&t2, &t0, &t1);
+    fp2_sub(&t2, &t2, &v1); fp2_sub(&t2, &t2, &v2); fp2_mul_xi(&t2, &t2); fp2_add(&c0, &t2, &v0);
+    fp2_add(&t0, &a->c0, &a->c1); fp2_add(&t1, &b->c0, &b->c1); fp2_mul(&t2, &t0, &t1);
+    fp2_sub(&t2, &t2, &v0); fp2_sub(&t2, &t2, &v1); fp2_mul_xi(&t0, &v2); fp2_add(&c1, &t2, &t0);
+    fp2_add(&t0, &a->c0, &a->c2); fp2_add(&t1, &b->c0, &b->c2); fp2_mul(&t2, &t0, &t1);
+    fp2_sub(&t2, &t2, &v0); fp2_sub(&t2, &t2, &v2); fp2_add(&c2, &t2, &v1);
+    r->c0 = c0; r->c1 = c1; r->c2 = c2;
+}
+static void fp6_mul_v(fp6 *r, const fp6 *a) { /* fp6.rs:146-152 with xi = 9+u */
+    fp2 t;
+    fp2_mul_xi(&t, &a->c2);
+    r->c2 = a->c1; r->c1 = a->c0; r->c0 = t;
+}
+static void fp6_inv(fp6 *r, const fp6 *a) { /* fp6.rs:261-287 */
+    fp2 t0, t1, t2, d, s;
+    fp2_sqr(&t0, &a->c0); fp2_mul(&s, &a->c1, &a->c2); fp2_mul_xi(&s, &s); fp2_sub(&t0, &t0, &s);
+    fp2_sqr(&t1, &a->c2); fp2_mul_xi(&t1, &t1); fp2_mul(&s, &a->c0, &a->c1); fp2_sub(&t1, &t1, &s);
+    fp2_sqr(&t2, &a->c1); fp2_mul(&s, &a->c0, &a->c2); fp2_sub(&t2, &t2, &s);
+    fp2_mul(&d, &a->c2, &t1); fp2_mul(&s, &a->c1, &t2); fp2_add(&d, &d, &s); fp2_mul_xi(&d, &d);
+    fp2_mul(&s, &a->c0, &t0); fp2_add(&d, &d, &s);
+    fp2_inv(&d, &d);
+    fp2_mul(&r->c0, &t0, &d); fp2_mul(&r->c1, &t1, &d); fp2_mul(&r->c2, &t2, &d);
+}
+
+/* ------------------------------------------------------------------ Fp12 = Fp6[w]/(w^2 - v) */
+static fp12 F12_ONE;
+static void fp12_mul(fp12 *r, const fp12 *a, const fp12 *b) { /* fp12.rs:203-210 */
+    fp6 aa, bb, s, t, o;
+    fp6_mul(&aa, &a->c0, &b->c0);
+    fp6_mul(&bb, &a->c1, &b->c1);
+    fp6_add(&s, &a->c0, &a->c1);
+    fp6_add(&t, &b->c0, &b->c1);
+    fp6_mul(&o, &s, &t);
+    fp6_sub(&o, &o, &aa);
+    fp6_sub(&o, &o, &bb);
+    fp6_mul_v(&bb, &bb);
+    fp6_add(&r->c0, &aa, &bb);
+    r->c1 = o;
+}
+static void fp12_sqr(fp12 *r, const fp12 *a) { /* fp12.rs:170-180 */
+    fp6 ab, s, t, c0;
+    fp6_mul(&ab, &a->c0, &a->c1);
+    fp6_add(&s, &a->c0, &a->c1);
+    fp6_mul_v(&t, &a->c1);
+    fp6_add(&t, &t, &a->c0);
+    fp6_mul(&c0, &s, &t);
+    fp6_sub(&c0, &c0, &ab);
+    fp6_mul_v(&t, &ab);
+    fp6_sub(&c0, &c0, &t);
+    r->c0 = c0;
+    fp6_add(&r->c1, &ab, &ab);
+}
+static void fp12_conj(fp12 *r, const fp12 *a) { r->c0 = a->c0; fp6_neg(&r->c1, &a->c1); } /* fp12.rs:131-136 */
+static void fp12_inv(fp12 *r, const fp12 *a) { /* fp12.rs:212-219 */
+    fp6 t0, t1;
+    fp6_mul(&t0, &a->c0, &a->c0);
+    fp6_mul(&t1, &a->c1, &a->c1);
+    fp6_mul_v(&t1, &t1);
+    fp6_sub(&t0, &t0, &t1);
+    fp6_inv(&t0, &t0);
+    fp6_mul(&r->c0, &a->c0, &t0);
+    fp6_mul(&t1, &a->c1, &t0);
+    fp6_neg(&r->c1, &t1);
+}
+static int fp12_eq(const fp12 *a, const fp12 *b) {
+    const fp *x = (const fp *)a, *y = (const fp *)b;
+    for (int i = 0; i < 12; i++) if (!fp_eq(&x[i], &y[i])) return 0;
+    return 1;
+}
+/* coefficient of w^i lives at: i even -> c0.c(i/2), i odd -> c1.c((i-1)/2) */
+static fp2 *fp12_coeff(fp12 *a, int i) { fp6 *h = (i & 1) ? &a->c1 : &a->c0; return &(&h->c0)[i >> 1]; }
+static void fp12_frob(fp12 *r, const fp12 *a, int k) { /* role of fp12.rs:139-168, correct constants */
+    fp12 t = *a;
+    for (int i = 0; i < 6; i++) {
+        fp2 *c = fp12_coeff(&t, i);
+        if (k & 1) fp2_conj(c, c);
+        if (i) fp2_mul(c, c, &F2_GAMMA[k - 1][i - 1]);
+    }
+    *r = t;
+}
+/* f * (c0 + c3 w + c4 w^3): the D-twist line placement (role of fp12.rs:120-129 mul_by_014) */
+static void fp12_mul_by_034(fp12 *r, const fp12 *f, const fp2 *c0, const fp2 *c3, const fp2 *c4) {
+    fp12 l;
+    memset(&l, 0, sizeof l);
+    l.c0.c0 = *c0; l.c1.c0 = *c3; l.c1.c1 = *c4;
+    fp12_mul(r, f, &l);
+}
+static void fp12_to_bytes(uint8_t out[384], const fp12 *a) { /* pairings.rs:499-514 */
+    const fp *x = (const fp *)a;
+    for (int i = 0; i < 12; i++) fp_to_be(out + 32 * i, &x[i]);
+}
+static int fp12_from_bytes(fp12 *a, const uint8_t in[384]) { /* pairings.rs:516-579 */
+    fp *x = (fp *)a;
+    for (int i = 0; i < 12; i++) if (!fp_from_be(&x[i], in + 32 * i)) return 0;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ groups */
+typedef struct { fp x, y, z; } g1p;
+typedef struct { fp2 x, y, z; } g2p;
+typedef struct { fp x, y; int inf; } g1a;
+typedef struct { fp2 x, y; int inf; } g2a;
+
+static void fp_mul_by_3b(fp *r, const fp *a) { fp t; fp_dbl(&t, a); fp_dbl(&t, &t); fp_dbl(&t, &t); fp_add(r, &t, a); } /* fp.rs:414-416 */
+static void fp2_mul_by_3b(fp2 *r, const fp2 *a) { fp2_mul(r, a, &F2_B3); } /* fp2.rs:411-413 */
+
+#define FE fp
+#define FN(x) fp_##x
+#define PT g1p
+#define PN(x) g1_##x
+#define MUL_BY_3B fp_mul_by_3b
+#include "orc_curve_tmpl.h"
+#undef FE
+#undef FN
+#undef PT
+#undef PN
+#undef MUL_BY_3B
+#define FE fp2
+#define FN(x) fp2_##x
+#define PT g2p
+#define PN(x) g2_##x
+#define MUL_BY_3B fp2_mul_by_3b
+#include "orc_curve_tmpl.h"
+#undef FE
+#undef FN
+#undef PT
+#undef PN
+#undef MUL_BY_3B
+
+static void g2_psi(g2p *r, const g2p *a) { /* g2.rs:938-954 */
+    fp2 t;
+    fp2_conj(&t, &a->x); fp2_mul(&r->x, &t, &F2_ENDO_U);
+    fp2_conj(&t, &a->y); fp2_mul(&r->y, &t, &F2_ENDO_V);
+    fp2_conj(&r->z, &a->z);
+}
+static void g2_clear_cofactor(g2p *r, const g2p *a) { /* g2.rs:685-693 */
+    g2p p0, p1, p2, p3, t;
+    uint64_t k[1] = {ORC_X};
+    g2_mul_limbs(&p0, a, k, 63);
+    g2_dbl(&t, &p0); g2_add(&t, &t, &p0); g2_psi(&p1, &t);
+    g2_psi(&t, &p0); g2_psi(&p2, &t);
+    g2_psi(&t, a); g2_psi(&t, &t); g2_psi(&p3, &t);
+    /* points.iter().sum(): IDENTITY + p0 + p1 + p2 + p3 */
+    g2_add(&t, &p0, &p1); g2_add(&t, &t, &p2); g2_add(r, &t, &p3);
+}
+
+/* ---- wire formats.  G1 uncompressed: x || y (g1.rs:296-302); decode g1.rs:336-358 (top bit of
+ * both coordinates masked, x == 0 -> identity, y == 1 -> infinity flag).  Returns 0 if invalid. */
+static void g1a_to_bytes(uint8_t out[64], const g1a *a) { fp_to_be(out, &a->x); fp_to_be(out + 32, &a->y); }
+static int g1a_from_bytes(g1a *a, const uint8_t in[64]) {
+    uint8_t xb[32], yb[32];
+    memcpy(xb, in, 32); memcpy(yb, in + 32, 32);
+    xb[0] &= 0x7f; yb[0] &= 0x7f;
+    if (!fp_from_be(&a->x, xb)) return 0;
+    if (fp_is_zero(&a->x)) { a->y = FP_ONE; a->inf = 1; return 1; }
+    if (!fp_from_be(&a->y, yb)) return 0;
+    a->inf = fp_eq(&a->y, &FP_ONE);
+    return 1;
+}
+/* G2 uncompressed: x.c1 || x.c0 || y.c1 || y.c0 (g2.rs:290-300); decode g2.rs:346-388 */
+static void g2a_to_bytes(uint8_t out[128], const g2a *a) {
+    fp_to_be(out, &a->x.c1); fp_to_be(out + 32, &a->x.c0); fp_to_be(out + 64, &a->y.c1); fp_to_be(out + 96, &a->y.c0);
+}
+static int g2a_from_bytes(g2a *a, const uint8_t in[128]) {
+    if (!fp_from_be(&a->x.c1, in) || !fp_from_be(&a->x.c0, in + 32)) return 0;
+    if (fp2_is_zero(&a->x)) { fp2_set_one(&a->y); a->inf = 1; return 1; }
+    if (!fp_from_be(&a->y.c1, in + 64) || !fp_from_be(&a->y.c0, in + 96)) return 0;
+    fp2 one; fp2_set_one(&one);
+    a->inf = fp2_eq(&a->y, &one);
+    return 1;
+}
+static int g1a_on_curve(const g1a *a) { /* g1.rs:383-391 */
+    fp l, r;
+    if (a->inf) return fp_is_zero(&a->x); /* z = 0: 0 == x^3 */
+    fp_sqr(&l, &a->y); fp_sqr(&r, &a->x); fp_mul(&r, &r, &a->x); fp_add(&r, &r, &F_THREE);
+    return fp_eq(&l, &r);
+}
+static int g2a_on_curve(const g2a *a) { /* g2.rs:409-414 */
+    fp2 l, r;
+    if (a->inf) return 1;
+    fp2_sqr(&l, &a->y); fp2_sqr(&r, &a->x); fp2_mul(&r, &r, &a->x); fp2_add(&r, &r, &F2_B);
+    return fp2_eq(&l, &r);
+}
+
+/* ------------------------------------------------------------------ SHA-256 + expand_message_xmd */
+typedef struct { uint32_t h[8]; uint8_t buf[64]; uint64_t len; } sha256_ctx;
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+#define ROR(x, n) (((x) >> (n)) | ((x) << (32 - (n))))
+static void sha256_block(uint32_t h[8], const uint8_t *p) {
+    uint32_t w[64], a, b, c, d, e, f, g, hh;
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = ROR(w[i - 15], 7) ^ ROR(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = ROR(w[i - 2], 17) ^ ROR(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    a = h[0]; b = h[1]; c = h[2]; d = h[3]; e = h[4]; f = h[5]; g = h[6]; hh = h[7];
+    for (int i = 0; i < 64; i++) {
+        uint32_t t1 = hh + (ROR(e, 6) ^ ROR(e, 11) ^ ROR(e, 25)) + ((e & f) ^ (~e & g)) + K256[i] + w[i];
+        uint32_t t2 = (ROR(a, 2) ^ ROR(a, 13) ^ ROR(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+static void sha256_init(sha256_ctx *c) {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    memcpy(c->h, iv, 32);
+    c->len = 0;
+}
+static void sha256_update(sha256_ctx *c, const uint8_t *d, size_t n) {
+    size_t fill = c->len & 63;
+    c->len += n;
+    if (fill) {
+        size_t take = 64 - fill < n ? 64 - fill : n;
+        memcpy(c->buf + fill, d, take);
+        d += take; n -= take;
+        if (fill + take < 64) return;
+        sha256_block(c->h, c->buf);
+    }
+    while (n >= 64) { sha256_block(c->h, d); d += 64; n -= 64; }
+    if (n) memcpy(c->buf, d, n);
+}
+static void sha256_final(sha256_ctx *c, uint8_t out[32]) {
+    uint64_t bits = c->len * 8;
+    uint8_t pad[72] = {0x80};
+    size_t fill = c->len & 63, padlen = (fill < 56 ? 56 - fill : 120 - fill);
+    for (int i = 0; i < 8; i++) pad[padlen + i] = (uint8_t)(bits >> (56 - 8 * i));
+    sha256_update(c, pad, padlen + 8);
+    for (int i = 0; i < 8; i++) { out[4 * i] = c->h[i] >> 24; out[4 * i + 1] = c->h[i] >> 16; out[4 * i + 2] = c->h[i] >> 8; out[4 * i + 3] = c->h[i]; }
+}
+/* RFC 9380 5.3.1; n <= 255*32.  Returns 0 on bad parameters. */
+static int expand_message_xmd(uint8_t *out, size_t n, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len) {
+    uint8_t dst_buf[32], b0[32], bi[32], tmp[32], zpad[64] = {0}, hdr[3];
+    sha256_ctx c;
+    size_t ell = (n + 31) / 32;
+    if (ell > 255 || n > 65535) return 0;
+    if (dst_len > 255) {
+        sha256_init(&c);
+        sha256_update(&c, (const uint8_t *)"H2C-OVERSIZE-DST-", 17);
+        sha256_update(&c, dst, dst_len);
+        sha256_final(&c, dst_buf);
+        dst = dst_buf; dst_len = 32;
+    }
+    uint8_t dl = (uint8_t)dst_len;
+    sha256_init(&c);
+    sha256_update(&c, zpad, 64);
+    sha256_update(&c, msg, msg_len);
+    hdr[0] = (uint8_t)(n >> 8); hdr[1] = (uint8_t)n; hdr[2] = 0;
+    sha256_update(&c, hdr, 3);
+    sha256_update(&c, dst, dst_len);
+    sha256_update(&c, &dl, 1);
+    sha256_final(&c, b0);
+    memset(bi, 0, 32);
+    for (size_t i = 1; i <= ell; i++) {
+        uint8_t idx = (uint8_t)i;
+        for (int j = 0; j < 32; j++) tmp[j] = b0[j] ^ bi[j];
+        sha256_init(&c);
+        sha256_update(&c, tmp, 32);
+        sha256_update(&c, &idx, 1);
+        sha256_update(&c, dst, dst_len);
+        sha256_update(&c, &dl, 1);
+        sha256_final(&c, bi);
+        size_t off = (i - 1) * 32, take = n - off < 32 ? n - off : 32;
+        memcpy(out + off, bi, take);
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------ SvdW maps */
+/* fp.rs:284-371.  Returns 0 where the reference panics (tv1*tv2 == 0, i.e. u = +-1/2). */
+static int svdw_g1(g1a *out, const fp *u) {
+    fp tv1, tv2, tv3, tv4, x1, x2, x3, gx1, gx2, gx, x, y;
+    fp_sqr(&tv1, u);
+    fp_mul(&tv1, &tv1, &F_FOUR);
+    fp_add(&tv2, &FP_ONE, &tv1);
+    fp_sub(&tv1, &FP_ONE, &tv1);
+    fp_mul(&tv3, &tv1, &tv2);
+    if (fp_is_zero(&tv3)) return 0;
+    fp_inv(&tv3, &tv3);
+    fp_mul(&tv4, u, &tv1);
+    fp_mul(&tv4, &tv4, &tv3);
+    fp_mul(&tv4, &tv4, &F_SVDW_C3);
+    fp_sub(&x1, &F_SVDW_C2, &tv4);
+    fp_sqr(&gx1, &x1); fp_mul(&gx1, &gx1, &x1); fp_add(&gx1, &gx1, &F_THREE);
+    fp_add(&x2, &F_SVDW_C2, &tv4);
+    fp_sqr(&gx2, &x2); fp_mul(&gx2, &gx2, &x2); fp_add(&gx2, &gx2, &F_THREE);
+    fp_sqr(&x3, &tv2); fp_mul(&x3, &x3, &tv3); fp_sqr(&x3, &x3); fp_mul(&x3, &x3, &F_SVDW_C4);
+    fp_add(&x3, &x3, &FP_ONE);
+    int e1 = fp_is_square(&gx1);
+    int e2 = fp_is_square(&gx2) & !e1;
+    x = e1 ? x1 : x3;
+    if (e2) x = x2;
+    fp_sqr(&gx, &x); fp_mul(&gx, &gx, &x); fp_add(&gx, &gx, &F_THREE);
+    if (!fp_sqrt(&y, &gx)) return 0;
+    if (fp_parity(u) ^ fp_parity(&y)) fp_neg(&y, &y);
+    out->x = x; out->y = y; out->inf = 0;
+    return 1;
+}
+/* fp2.rs:221-287 */
+static int svdw_g2(g2a *out, const fp2 *u) {
+    fp2 tv1, tv2, tv3, tv4, x1, x2, x3, gx1, gx2, gx, x, y, one;
+    fp2_set_one(&one);
+    fp2_sqr(&tv1, u);
+    fp2_mul(&tv1, &tv1, &F2_SVDW_C1);
+    fp2_add(&tv2, &one, &tv1);
+    fp2_sub(&tv1, &one, &tv1);
+    fp2_mul(&tv3, &tv1, &tv2);
+    if (fp2_is_zero(&tv3)) return 0;
+    fp2_inv(&tv3, &tv3);
+    fp2_mul(&tv4, u, &tv1);
+    fp2_mul(&tv4, &tv4, &tv3);
+    fp2_mul(&tv4, &tv4, &F2_SVDW_C3);
+    fp2_sub(&x1, &F2_SVDW_C2, &tv4);
+    fp2_sqr(&gx1, &x1); fp2_mul(&gx1, &gx1, &x1); fp2_add(&gx1, &gx1, &F2_B);
+    fp2_add(&x2, &F2_SVDW_C2, &tv4);
+    fp2_sqr(&gx2, &x2); fp2_mul(&gx2, &gx2, &x2); fp2_add(&gx2, &gx2, &F2_B);
+    fp2_sqr(&x3, &tv2); fp2_mul(&x3, &x3, &tv3); fp2_sqr(&x3, &x3); fp2_mul(&x3, &x3, &F2_SVDW_C4);
+    fp2_add(&x3, &x3, &one);
+    int e1 = fp2_is_square(&gx1);
+    int e2 = fp2_is_square(&gx2) & !e1;
+    x = e1 ? x1 : x3;
+    if (e2) x = x2;
+    fp2_sqr(&gx, &x); fp2_mul(&gx, &gx, &x); fp2_add(&gx, &gx, &F2_B);
+    if (!fp2_sqrt(&y, &gx)) return 0;
+    if (fp2_sgn0(u) ^ fp2_sgn0(&y)) fp2_neg(&y, &y);
+    out->x = x; out->y = y; out->inf = 0;
+    return 1;
+}
+
+/* hash (count = 2) / encode (count = 1) to G1: g1.rs:910-928.  Returns 0 on the SvdW exception. */
+static int hash_to_g1_one(g1a *out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, int count) {
+    uint8_t okm[96];
+    fp u;
+    g1a q[2];
+    if (!expand_message_xmd(okm, 48 * (size_t)count, msg, msg_len, dst, dst_len)) return 0;
+    for (int i = 0; i < count; i++) {
+        fp_from_okm(&u, okm + 48 * i);
+        if (!svdw_g1(&q[i], &u)) return 0;
+    }
+    if (count == 1) { *out = q[0]; return 1; }
+    g1p a, b;
+    g1_from_affine(&a, &q[0].x, &q[0].y, 0);
+    g1_from_affine(&b, &q[1].x, &q[1].y, 0);
+    g1_add(&a, &a, &b);
+    g1_to_affine(&out->x, &out->y, &out->inf, &a);
+    return 1;
+}
+/* g2.rs:919-936 */
+static int hash_to_g2_one(g2a *out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, int count) {
+    uint8_t okm[192];
+    fp2 u;
+    g2a q[2];
+    g2p a, b;
+    if (!expand_message_xmd(okm, 96 * (size_t)count, msg, msg_len, dst, dst_len)) return 0;
+    for (int i = 0; i < count; i++) {
+        fp_from_okm(&u.c0, okm + 96 * i);
+        fp_from_okm(&u.c1, okm + 96 * i + 48);
+        if (!svdw_g2(&q[i], &u)) return 0;
+    }
+    g2_from_affine(&a, &q[0].x, &q[0].y, 0);
+    if (count == 2) {
+        g2_from_affine(&b, &q[1].x, &q[1].y, 0);
+        g2_add(&a, &a, &b);
+    }
+    g2_clear_cofactor(&a, &a);
+    g2_to_affine(&out->x, &out->y, &out->inf, &a);
+    return 1;
+}
+
+/* ------------------------------------------------------------------ pairing */
+typedef struct { fp2 a, b, c; } line_t;
+
+static void doubling_step(line_t *l, g2p *r) { /* pairings.rs:901-930, verbatim formulas */
+    fp2 tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, zsq, t;
+    fp2_sqr(&tmp0, &r->x);
+    fp2_sqr(&tmp1, &r->y);
+    fp2_sqr(&tmp2, &tmp1);
+    fp2_add(&tmp3, &tmp1, &r->x); fp2_sqr(&tmp3, &tmp3); fp2_sub(&tmp3, &tmp3, &tmp0); fp2_sub(&tmp3, &tmp3, &tmp2);
+    fp2_dbl(&tmp3, &tmp3);
+    fp2_dbl(&tmp4, &tmp0); fp2_add(&tmp4, &tmp4, &tmp0);
+    fp2_add(&tmp6, &r->x, &tmp4);
+    fp2_sqr(&tmp5, &tmp4);
+    fp2_sqr(&zsq, &r->z);
+    fp2_sub(&r->x, &tmp5, &tmp3); fp2_sub(&r->x, &r->x, &tmp3);
+    fp2_add(&t, &r->z, &r->y); fp2_sqr(&t, &t); fp2_sub(&t, &t, &tmp1); fp2_sub(&r->z, &t, &zsq);
+    fp2_sub(&t, &tmp3, &r->x); fp2_mul(&r->y, &t, &tmp4);
+    fp2_dbl(&tmp2, &tmp2); fp2_dbl(&tmp2, &tmp2); fp2_dbl(&tmp2, &tmp2);
+    fp2_sub(&r->y, &r->y, &tmp2);
+    fp2_mul(&tmp3, &tmp4, &zsq); fp2_dbl(&tmp3, &tmp3); fp2_neg(&tmp3, &tmp3);
+    fp2_sqr(&tmp6, &tmp6); fp2_sub(&tmp6, &tmp6, &tmp0); fp2_sub(&tmp6, &tmp6, &tmp5);
+    fp2_dbl(&tmp1, &tmp1); fp2_dbl(&tmp1, &tmp1);
+    fp2_sub(&tmp6, &tmp6, &tmp1);
+    fp2_mul(&tmp0, &r->z, &zsq); fp2_dbl(&tmp0, &tmp0);
+    l->a = tmp0; l->b = tmp3; l->c = tmp6;
+}
+static void addition_step(line_t *l, g2p *r, const fp2 *qx, const fp2 *qy) { /* pairings.rs:932-962 */
+    fp2 zsq, ysq, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, zt;
+    fp2_sqr(&zsq, &r->z);
+    fp2_sqr(&ysq, qy);
+    fp2_mul(&t0, &zsq, qx);
+    fp2_add(&t1, qy, &r->z); fp2_sqr(&t1, &t1); fp2_sub(&t1, &t1, &ysq); fp2_sub(&t1, &t1, &zsq); fp2_mul(&t1, &t1, &zsq);
+    fp2_sub(&t2, &t0, &r->x);
+    fp2_sqr(&t3, &t2);
+    fp2_dbl(&t4, &t3); fp2_dbl(&t4, &t4);
+    fp2_mul(&t5, &t4, &t2);
+    fp2_sub(&t6, &t1, &r->y); fp2_sub(&t6, &t6, &r->y);
+    fp2_mul(&t9, &t6, qx);
+    fp2_mul(&t7, &t4, &r->x);
+    fp2_sqr(&r->x, &t6); fp2_sub(&r->x, &r->x, &t5); fp2_sub(&r->x, &r->x, &t7); fp2_sub(&r->x, &r->x, &t7);
+    fp2_add(&r->z, &r->z, &t2); fp2_sqr(&r->z, &r->z); fp2_sub(&r->z, &r->z, &zsq); fp2_sub(&r->z, &r->z, &t3);
+    fp2_add(&t10, qy, &r->z);
+    fp2_sub(&t8, &t7, &r->x); fp2_mul(&t8, &t8, &t6);
+    fp2_mul(&t0, &r->y, &t5); fp2_dbl(&t0, &t0);
+    fp2_sub(&r->y, &t8, &t0);
+    fp2_sqr(&t10, &t10); fp2_sub(&t10, &t10, &ysq);
+    fp2_sqr(&zt, &r->z);
+    fp2_sub(&t10, &t10, &zt);
+    fp2_dbl(&t9, &t9); fp2_sub(&t9, &t9, &t10);
+    fp2_dbl(&t10, &r->z);
+    fp2_neg(&t6, &t6);
+    fp2_dbl(&t1, &t6);
+    l->a = t10; l->b = t1; l->c = t9;
+}
+static void ell(fp12 *f, const line_t *l, const g1a *p) { /* pairings.rs:888-899, placement 0/3/4 */
+    fp2 c0, c1;
+    fp2_mul_fp(&c0, &l->a, &p->y);
+    fp2_mul_fp(&c1, &l->b, &p->x);
+    fp12_mul_by_034(f, f, &c0, &c1, &l->c);
+}
+
+#define NUM_LINES 88
+/* The 88 line triples of one G2 point, in consumption order (what G2Prepared, pairings.rs:609-660,
+ * is meant to hold). */
+static void prepare_lines(line_t *out, const g2a *q) {
+    g2p r, t, q1, q2;
+    fp2 nqy;
+    int n = 0;
+    r.x = q->x; r.y = q->y; fp2_set_one(&r.z);
+    fp2_neg(&nqy, &q->y);
+    for (int i = 0; i < ORC_ATE_NAF_LEN; i++) {
+        doubling_step(&out[n++], &r);
+        if (ORC_ATE_NAF[i]) addition_step(&out[n++], &r, &q->x, ORC_ATE_NAF[i] > 0 ? &q->y : &nqy);
+    }
+    t.x = q->x; t.y = q->y; fp2_set_one(&t.z);
+    g2_psi(&q1, &t);
+    g2_psi(&q2, &q1);
+    addition_step(&out[n++], &r, &q1.x, &q1.y);
+    fp2_neg(&q2.y, &q2.y);
+    addition_step(&out[n++], &r, &q2.x, &q2.y);
+    (void)n;
+}
+/* Product of Miller loops with one shared squaring per step (pairings.rs:808-857); identity
+ * terms contribute 1 (pairings.rs:820-835). */
+static void multi_miller(fp12 *out, const g1a *ps, const g2a *qs, size_t n) {
+    size_t live = 0;
+    line_t *lines = (line_t *)malloc(sizeof(line_t) * NUM_LINES * (n ? n : 1));
+    const g1a **lp = (const g1a **)malloc(sizeof(void *) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        if (ps[i].inf || qs[i].inf) continue;
+        prepare_lines(lines + NUM_LINES * live, &qs[i]);
+        lp[live++] = &ps[i];
+    }
+    fp12 f = F12_ONE;
+    int idx = 0;
+    for (int i = 0; i < ORC_ATE_NAF_LEN; i++) {
+        fp12_sqr(&f, &f);
+        for (size_t k = 0; k < live; k++) ell(&f, &lines[NUM_LINES * k + idx], lp[k]);
+        idx++;
+        if (ORC_ATE_NAF[i]) {
+            for (size_t k = 0; k < live; k++) ell(&f, &lines[NUM_LINES * k + idx], lp[k]);
+            idx++;
+        }
+    }
+    for (int s = 0; s < 2; s++) {
+        for (size_t k = 0; k < live; k++) ell(&f, &lines[NUM_LINES * k + idx], lp[k]);
+        idx++;
+    }
+    free(lines);
+    free(lp);
+    *out = f;
+}
+
+static void fp4_square(fp2 *c0, fp2 *c1, const fp2 *a, const fp2 *b) { /* pairings.rs:52-63 */
+    fp2 t0, t1, t2;
+    fp2_sqr(&t0, a);
+    fp2_sqr(&t1, b);
+    fp2_mul_xi(&t2, &t1);
+    fp2_add(c0, &t2, &t0);
+    fp2_add(&t2, a, b);
+    fp2_sqr(&t2, &t2);
+    fp2_sub(&t2, &t2, &t0);
+    fp2_sub(c1, &t2, &t1);
+}
+static void cyclotomic_square(fp12 *r, const fp12 *f) { /* pairings.rs:68-115 */
+    fp2 z0 = f->c0.c0, z4 = f->c0.c1, z3 = f->c0.c2, z2 = f->c1.c0, z1 = f->c1.c1, z5 = f->c1.c2;
+    fp2 t0, t1, t2, t3;
+    fp4_square(&t0, &t1, &z0, &z1);
+    fp2_sub(&z0, &t0, &z0); fp2_dbl(&z0, &z0); fp2_add(&z0, &z0, &t0);
+    fp2_add(&z1, &t1, &z1); fp2_dbl(&z1, &z1); fp2_add(&z1, &z1, &t1);
+    fp4_square(&t0, &t1, &z2, &z3);
+    fp4_square(&t2, &t3, &z4, &z5);
+    fp2_sub(&z4, &t0, &z4); fp2_dbl(&z4, &z4); fp2_add(&z4, &z4, &t0);
+    fp2_add(&z5, &t1, &z5); fp2_dbl(&z5, &z5); fp2_add(&z5, &z5, &t1);
+    fp2_mul_xi(&t0, &t3);
+    fp2_add(&z2, &t0, &z2); fp2_dbl(&z2, &z2); fp2_add(&z2, &z2, &t0);
+    fp2_sub(&z3, &t2, &z3); fp2_dbl(&z3, &z3); fp2_add(&z3, &z3, &t2);
+    r->c0.c0 = z0; r->c0.c1 = z4; r->c0.c2 = z3;
+    r->c1.c0 = z2; r->c1.c1 = z1; r->c1.c2 = z5;
+}
+static void cyclotomic_exp_neg_x(fp12 *r, const fp12 *f) { /* pairings.rs:117-134: f^x then conjugate */
+    fp12 t = *f, base = *f;
+    for (int i = 61; i >= 0; i--) { /* x has 63 bits; top bit consumed by t = f */
+        cyclotomic_square(&t, &t);
+        if ((ORC_X >> i) & 1) fp12_mul(&t, &t, &base);
+    }
+    fp12_conj(r, &t);
+}
+/* pairings.rs:50-178 role, Tier B: easy part, then Fuentes-Castaneda hard part */
+static void final_exponentiation(fp12 *out, const fp12 *f) {
+    fp12 f1, r, t, y0, y1, y2, y3, y4, y5, y6, y7, y8, y9, y10, y11, y12, y13, y14, y15;
+    fp12_conj(&f1, f);
+    fp12_inv(&t, f);
+    fp12_mul(&f1, &f1, &t);
+    fp12_frob(&r, &f1, 2);
+    fp12_mul(&r, &r, &f1);
+    cyclotomic_exp_neg_x(&y0, &r);
+    cyclotomic_square(&y1, &y0);
+    cyclotomic_square(&y2, &y1);
+    fp12_mul(&y3, &y2, &y1);
+    cyclotomic_exp_neg_x(&y4, &y3);
+    cyclotomic_square(&y5, &y4);
+    cyclotomic_exp_neg_x(&y6, &y5);
+    fp12_conj(&y3, &y3);
+    fp12_conj(&y6, &y6);
+    fp12_mul(&y7, &y6, &y4);
+    fp12_mul(&y8, &y7, &y3);
+    fp12_mul(&y9, &y8, &y1);
+    fp12_mul(&y10, &y8, &y4);
+    fp12_mul(&y11, &y10, &r);
+    fp12_frob(&y12, &y9, 1);
+    fp12_mul(&y13, &y12, &y11);
+    fp12_frob(&y8, &y8, 2);
+    fp12_mul(&y14, &y8, &y13);
+    fp12_conj(&t, &r);
+    fp12_mul(&y15, &t, &y9);
+    fp12_frob(&y15, &y15, 3);
+    fp12_mul(out, &y15, &y14);
+}
+
+/* ------------------------------------------------------------------ init */
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static g2a G2_GEN_A, NEG_G2_GEN_A;
+static g1a G1_GEN_A, NEG_G1_GEN_A;
+static void init_impl(void) {
+    fp one = {{1, 0, 0, 0}};
+    memcpy(FP_R2.l, ORC_R2, 32);
+    fp_mul(&FP_ONE, &one, &FP_R2);
+    uint64_t w3[4] = {3, 0, 0, 0}, w4[4] = {4, 0, 0, 0}, w2[4] = {2, 0, 0, 0};
+    fp_from_canon(&F_THREE, w3);
+    fp_from_canon(&F_FOUR, w4);
+    fp_from_canon(&F_SVDW_C2, ORC_SVDW1_C2);
+    fp_from_canon(&F_SVDW_C3, ORC_SVDW1_C3);
+    fp_from_canon(&F_SVDW_C4, ORC_SVDW1_C4);
+    fp2_from_canon(&F2_B, ORC_B2);
+    fp2_add(&F2_B3, &F2_B, &F2_B); fp2_add(&F2_B3, &F2_B3, &F2_B); /* fp2.rs:350 */
+    fp2_from_canon(&F2_ENDO_U, ORC_ENDO_U);
+    fp2_from_canon(&F2_ENDO_V, ORC_ENDO_V);
+    fp2_from_canon(&F2_SVDW_C1, ORC_SVDW2_C1);
+    fp2_from_canon(&F2_SVDW_C2, ORC_SVDW2_C2);
+    fp2_from_canon(&F2_SVDW_C3, ORC_SVDW2_C3);
+    fp2_from_canon(&F2_SVDW_C4, ORC_SVDW2_C4);
+    for (int k = 0; k < 3; k++) for (int i = 0; i < 5; i++) fp2_from_canon(&F2_GAMMA[k][i], ORC_GAMMA[k][i]);
+    memset(&F12_ONE, 0, sizeof F12_ONE);
+    F12_ONE.c0.c0.c0 = FP_ONE;
+    fp2_from_canon(&G2_GEN_A.x, ORC_G2_GEN_X);
+    fp2_from_canon(&G2_GEN_A.y, ORC_G2_GEN_Y);
+    G2_GEN_A.inf = 0;
+    NEG_G2_GEN_A = G2_GEN_A;
+    fp2_neg(&NEG_G2_GEN_A.y, &NEG_G2_GEN_A.y);
+    G1_GEN_A.x = FP_ONE; fp_from_canon(&G1_GEN_A.y, w2); G1_GEN_A.inf = 0;
+    NEG_G1_GEN_A = G1_GEN_A;
+    fp_neg(&NEG_G1_GEN_A.y, &NEG_G1_GEN_A.y);
+}
+static void orc_init(void) { pthread_once(&g_once, init_impl); }
+
+/* ------------------------------------------------------------------ threading helper */
+typedef void (*range_fn)(void *arg, size_t lo, size_t hi);
+typedef struct { range_fn fn; void *arg; size_t lo, hi; } job_t;
+static void *job_main(void *p) { job_t *j = (job_t *)p; j->fn(j->arg, j->lo, j->hi); return NULL; }
+static void parallel_for(size_t n, int nthreads, range_fn fn, void *arg) {
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+    if (nthreads == 1) { fn(arg, 0, n); return; }
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    job_t *jobs = (job_t *)malloc(sizeof(job_t) * nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t].fn = fn; jobs[t].arg = arg;
+        jobs[t].lo = n * (size_t)t / nthreads; jobs[t].hi = n * (size_t)(t + 1) / nthreads;
+        pthread_create(&th[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
+
+/* ================================================================== exported API (orc_*) */
+#define EXPORT __attribute__((visibility("default")))
+
+EXPORT uint64_t orc_mul_count(void) { return g_mul_count; }
+EXPORT void orc_mul_count_reset(void) { g_mul_count = 0; }
+
+typedef struct {
+    const uint8_t *msgs; const uint64_t *off; const uint8_t *dst; size_t dst_len; int count;
+    uint8_t *out; uint8_t *status;
+} hash_args;
+static void hash_g1_range(void *p, size_t lo, size_t hi) {
+    hash_args *a = (hash_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        g1a q;
+        int ok = hash_to_g1_one(&q, a->msgs + a->off[i], a->off[i + 1] - a->off[i], a->dst, a->dst_len, a->count);
+        if (ok) g1a_to_bytes(a->out + 64 * i, &q); else memset(a->out + 64 * i, 0, 64);
+        if (a->status) a->status[i] = (uint8_t)ok;
+    }
+}
+static void hash_g2_range(void *p, size_t lo, size_t hi) {
+    hash_args *a = (hash_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        g2a q;
+        int ok = hash_to_g2_one(&q, a->msgs + a->off[i], a->off[i + 1] - a->off[i], a->dst, a->dst_len, a->count);
+        if (ok) g2a_to_bytes(a->out + 128 * i, &q); else memset(a->out + 128 * i, 0, 128);
+        if (a->status) a->status[i] = (uint8_t)ok;
+    }
+}
+/* count: 2 = hash (random oracle), 1 = encode (non-uniform).  out: n x 64 (G1) / n x 128 (G2)
+ * uncompressed; status (optional): 1 ok / 0 SvdW exception. */
+EXPORT int orc_hash_to_g1(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count, uint8_t *out, uint8_t *status, int nthreads) {
+    orc_init();
+    hash_args a = {msgs, off, dst, dst_len, count, out, status};
+    parallel_for(n, nthreads, hash_g1_range, &a);
+    return 0;
+}
+EXPORT int orc_hash_to_g2(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count, uint8_t *out, uint8_t *status, int nthreads) {
+    orc_init();
+    hash_args a = {msgs, off, dst, dst_len, count, out, status};
+    parallel_for(n, nthreads, hash_g2_range, &a);
+    return 0;
+}
+/* hash_to_field over Fp: out = n x count x 32 BE (fp.rs:433-458) */
+EXPORT int orc_hash_to_field_fp(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count, uint8_t *out) {
+    orc_init();
+    uint8_t *okm = (uint8_t *)malloc(48 * (size_t)count);
+    for (size_t i = 0; i < n; i++) {
+        expand_message_xmd(okm, 48 * (size_t)count, msgs + off[i], off[i + 1] - off[i], dst, dst_len);
+        for (int k = 0; k < count; k++) { fp u; fp_from_okm(&u, okm + 48 * k); fp_to_be(out + 32 * (i * count + k), &u); }
+    }
+    free(okm);
+    return 0;
+}
+EXPORT int orc_expand_message_xmd(const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, uint8_t *out, size_t n) {
+    return expand_message_xmd(out, n, msg, msg_len, dst, dst_len) ? 0 : -1;
+}
+/* SvdW on given field elements: u = n x 32 BE -> n x 64 (fp.rs:284-371) */
+EXPORT int orc_svdw_g1(const uint8_t *u, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        fp x; g1a q;
+        if (!fp_from_be(&x, u + 32 * i) || !svdw_g1(&q, &x)) { memset(out + 64 * i, 0, 64); continue; }
+        g1a_to_bytes(out + 64 * i, &q);
+    }
+    return 0;
+}
+/* u = n x 64 (c0 || c1 BE) -> n x 128, no cofactor clearing (fp2.rs:221-287) */
+EXPORT int orc_svdw_g2(const uint8_t *u, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        fp2 x; g2a q;
+        if (!fp_from_be(&x.c0, u + 64 * i) || !fp_from_be(&x.c1, u + 64 * i + 32) || !svdw_g2(&q, &x)) { memset(out + 128 * i, 0, 128); continue; }
+        g2a_to_bytes(out + 128 * i, &q);
+    }
+    return 0;
+}
+
+typedef struct { const uint8_t *g1; const uint8_t *g2; uint8_t *out; uint8_t *status; int mode; } pair_args;
+static void pairing_range(void *p, size_t lo, size_t hi) {
+    pair_args *a = (pair_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        g1a P; g2a Q; fp12 f;
+        int ok = g1a_from_bytes(&P, a->g1 + 64 * i) && g2a_from_bytes(&Q, a->g2 + 128 * i);
+        if (a->status) a->status[i] = (uint8_t)ok;
+        if (!ok) { memset(a->out + 384 * i, 0, 384); continue; }
+        multi_miller(&f, &P, &Q, 1);
+        if (a->mode == 0) final_exponentiation(&f, &f);
+        fp12_to_bytes(a->out + 384 * i, &f);
+    }
+}
+/* pairing() per item (pairings.rs:760-802) + Gt::to_repr; invalid encodings -> status 0, zeros */
+EXPORT int orc_pairing_batch(const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt, uint8_t *status, int nthreads) {
+    orc_init();
+    pair_args a = {g1, g2, gt, status, 0};
+    parallel_for(n, nthreads, pairing_range, &a);
+    return 0;
+}
+/* one un-exponentiated Miller loop per item */
+EXPORT int orc_miller_loop_batch(const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml, uint8_t *status, int nthreads) {
+    orc_init();
+    pair_args a = {g1, g2, ml, status, 1};
+    parallel_for(n, nthreads, pairing_range, &a);
+    return 0;
+}
+/* multi_miller_loop (pairings.rs:808-857): one 384-byte MillerLoopResult for n pairs */
+EXPORT int orc_multi_miller_loop(const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml) {
+    orc_init();
+    g1a *ps = (g1a *)malloc(sizeof(g1a) * (n ? n : 1));
+    g2a *qs = (g2a *)malloc(sizeof(g2a) * (n ? n : 1));
+    int rc = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (!g1a_from_bytes(&ps[i], g1 + 64 * i)) { rc = -2; break; }
+        if (!g2a_from_bytes(&qs[i], g2 + 128 * i)) { rc = -3; break; }
+    }
+    if (!rc) { fp12 f; multi_miller(&f, ps, qs, n); fp12_to_bytes(ml, &f); }
+    free(ps); free(qs);
+    return rc;
+}
+typedef struct { const uint8_t *in; uint8_t *out; uint8_t *status; } fe_args;
+static void fe_range(void *p, size_t lo, size_t hi) {
+    fe_args *a = (fe_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        fp12 f;
+        int ok = fp12_from_bytes(&f, a->in + 384 * i);
+        if (a->status) a->status[i] = (uint8_t)ok;
+        if (!ok) { memset(a->out + 384 * i, 0, 384); continue; }
+        final_exponentiation(&f, &f);
+        fp12_to_bytes(a->out + 384 * i, &f);
+    }
+}
+EXPORT int orc_final_exponentiation(const uint8_t *ml, size_t n, uint8_t *gt, uint8_t *status, int nthreads) {
+    orc_init();
+    fe_args a = {ml, gt, status};
+    parallel_for(n, nthreads, fe_range, &a);
+    return 0;
+}
+/* Fp12 product of n 384-byte elements (MillerLoopResult + MillerLoopResult, pairings.rs:37-43) */
+EXPORT int orc_fp12_product(const uint8_t *in, size_t n, uint8_t *out) {
+    orc_init();
+    fp12 acc = F12_ONE, t;
+    for (size_t i = 0; i < n; i++) { if (!fp12_from_bytes(&t, in + 384 * i)) return -4; fp12_mul(&acc, &acc, &t); }
+    fp12_to_bytes(out, &acc);
+    return 0;
+}
+
+/* ---- BLS predicates.  variant 0 = min-sig (pk in G2 128 B, sig in G1
+ * 64 B), 1 = min-pk (pk in G1 64 B, sig in G2 128 B).  flags bit0: reject points not on curve. */
+typedef struct {
+    int variant; const uint8_t *pks; const uint8_t *msgs; const uint64_t *off; const uint8_t *sigs;
+    const uint8_t *dst; size_t dst_len; uint32_t flags; uint8_t *ok;
+} verify_args;
+static int verify_one(const verify_args *a, size_t i) {
+    fp12 f;
+    const uint8_t *msg = a->msgs + a->off[i];
+    size_t mlen = a->off[i + 1] - a->off[i];
+    g1a ps[2]; g2a qs[2];
+    if (a->variant == 0) {
+        g2a pk; g1a sig, h;
+        if (!g2a_from_bytes(&pk, a->pks + 128 * i) || !g1a_from_bytes(&sig, a->sigs + 64 * i)) return 0;
+        if ((a->flags & 1) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) return 0;
+        if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
+        ps[0] = sig; qs[0] = NEG_G2_GEN_A; ps[1] = h; qs[1] = pk;
+    } else {
+        g1a pk; g2a sig, h;
+        if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) return 0;
+        if ((a->flags & 1) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) return 0;
+        if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
+        ps[0] = NEG_G1_GEN_A; qs[0] = sig; ps[1] = pk; qs[1] = h;
+    }
+    multi_miller(&f, ps, qs, 2);
+    final_exponentiation(&f, &f);
+    return fp12_eq(&f, &F12_ONE);
+}
+static void verify_range(void *p, size_t lo, size_t hi) {
+    verify_args *a = (verify_args *)p;
+    for (size_t i = lo; i < hi; i++) a->ok[i] = (uint8_t)verify_one(a, i);
+}
+EXPORT int orc_verify_batch(int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, const uint8_t *sigs, size_t n,
+                            const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok, int nthreads) {
+    orc_init();
+    verify_args a = {variant, pks, msgs, off, sigs, dst, dst_len, flags, ok};
+    parallel_for(n, nthreads, verify_range, &a);
+    return 0;
+}
+/* aggregate verify, distinct messages: e(aggsig, -g2) * prod e(H(m_i), pk_i) == 1 (min-sig);
+ * e(-g1, aggsig) * prod e(pk_i, H(m_i)) == 1 (min-pk) */
+typedef struct { int variant; const uint8_t *pks; const uint8_t *msgs; const uint64_t *off; const uint8_t *dst; size_t dst_len; uint32_t flags;
+                 g1a *ps; g2a *qs; int *bad; } agg_args;
+static void agg_range(void *p, size_t lo, size_t hi) {
+    agg_args *a = (agg_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        const uint8_t *msg = a->msgs + a->off[i];
+        size_t mlen = a->off[i + 1] - a->off[i];
+        int ok;
+        if (a->variant == 0) {
+            ok = g2a_from_bytes(&a->qs[i], a->pks + 128 * i) && (!(a->flags & 1) || g2a_on_curve(&a->qs[i])) &&
+                 hash_to_g1_one(&a->ps[i], msg, mlen, a->dst, a->dst_len, 2);
+        } else {
+            ok = g1a_from_bytes(&a->ps[i], a->pks + 64 * i) && (!(a->flags & 1) || g1a_on_curve(&a->ps[i])) &&
+                 hash_to_g2_one(&a->qs[i], msg, mlen, a->dst, a->dst_len, 2);
+        }
+        if (!ok) __atomic_store_n(a->bad, 1, __ATOMIC_RELAXED);
+    }
+}
+typedef struct { const g1a *ps; const g2a *qs; fp12 *partial; size_t n; int parts; } mm_args;
+static void mm_range(void *p, size_t lo, size_t hi) {
+    mm_args *a = (mm_args *)p;
+    for (size_t t = lo; t < hi; t++) {
+        size_t s = a->n * t / a->parts, e = a->n * (t + 1) / a->parts;
+        multi_miller(&a->partial[t], a->ps + s, a->qs + s, e - s);
+    }
+}
+EXPORT int orc_aggregate_verify(int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *agg_sig,
+                                const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok, int nthreads) {
+    orc_init();
+    g1a *ps = (g1a *)malloc(sizeof(g1a) * (n + 1));
+    g2a *qs = (g2a *)malloc(sizeof(g2a) * (n + 1));
+    int bad = 0;
+    agg_args a = {variant, pks, msgs, off, dst, dst_len, flags, ps, qs, &bad};
+    parallel_for(n, nthreads, agg_range, &a);
+    if (variant == 0) {
+        if (!g1a_from_bytes(&ps[n], agg_sig) || ((flags & 1) && !g1a_on_curve(&ps[n]))) bad = 1;
+        qs[n] = NEG_G2_GEN_A;
+    } else {
+        if (!g2a_from_bytes(&qs[n], agg_sig) || ((flags & 1) && !g2a_on_curve(&qs[n]))) bad = 1;
+        ps[n] = NEG_G1_GEN_A;
+    }
+    if (bad) { *ok = 0; free(ps); free(qs); return 0; }
+    int parts = nthreads < 1 ? 1 : nthreads;
+    if ((size_t)parts > n + 1) parts = (int)(n + 1);
+    fp12 *partial = (fp12 *)malloc(sizeof(fp12) * parts);
+    mm_args m = {ps, qs, partial, n + 1, parts};
+    parallel_for((size_t)parts, parts, mm_range, &m);
+    fp12 f = F12_ONE;
+    for (int t = 0; t < parts; t++) fp12_mul(&f, &f, &partial[t]);
+    final_exponentiation(&f, &f);
+    *ok = (uint8_t)fp12_eq(&f, &F12_ONE);
+    free(partial); free(ps); free(qs);
+    return 0;
+}
+
+/* ---- test-data generators: scalar multiplication (g1.rs:821-841, g2.rs:866-886), sums */
+typedef struct { const uint8_t *pts; const uint8_t *sc; uint8_t *out; } mul_args;
+static void scalar_limbs(uint64_t k[4], const uint8_t be[32]) {
+    for (int i = 0; i < 4; i++) { uint64_t v = 0; for (int j = 0; j < 8; j++) v = (v << 8) | be[(3 - i) * 8 + j]; k[i] = v; }
+}
+static void g1_mul_range(void *p, size_t lo, size_t hi) {
+    mul_args *a = (mul_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        g1a P, R; g1p r; uint64_t k[4];
+        if (!g1a_from_bytes(&P, a->pts + 64 * i)) { memset(a->out + 64 * i, 0, 64); continue; }
+        scalar_limbs(k, a->sc + 32 * i);
+        g1_from_affine(&r, &P.x, &P.y, P.inf);
+        g1_mul_limbs(&r, &r, k, 256);
+        g1_to_affine(&R.x, &R.y, &R.inf, &r);
+        g1a_to_bytes(a->out + 64 * i, &R);
+    }
+}
+static void g2_mul_range(void *p, size_t lo, size_t hi) {
+    mul_args *a = (mul_args *)p;
+    for (size_t i = lo; i < hi; i++) {
+        g2a P, R; g2p r; uint64_t k[4];
+        if (!g2a_from_bytes(&P, a->pts + 128 * i)) { memset(a->out + 128 * i, 0, 128); continue; }
+        scalar_limbs(k, a->sc + 32 * i);
+        g2_from_affine(&r, &P.x, &P.y, P.inf);
+        g2_mul_limbs(&r, &r, k, 256);
+        g2_to_affine(&R.x, &R.y, &R.inf, &r);
+        g2a_to_bytes(a->out + 128 * i, &R);
+    }
+}
+/* out[i] = [scalar_i] point_i; scalars 32 B big-endian integers */
+EXPORT int orc_g1_mul(const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out, int nthreads) {
+    orc_init();
+    mul_args a = {pts, scalars, out};
+    parallel_for(n, nthreads, g1_mul_range, &a);
+    return 0;
+}
+EXPORT int orc_g2_mul(const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out, int nthreads) {
+    orc_init();
+    mul_args a = {pts, scalars, out};
+    parallel_for(n, nthreads, g2_mul_range, &a);
+    return 0;
+}
+EXPORT int orc_g1_sum(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    g1p acc, t; g1a P;
+    g1_set_identity(&acc);
+    for (size_t i = 0; i < n; i++) {
+        if (!g1a_from_bytes(&P, pts + 64 * i)) return -2;
+        g1_from_affine(&t, &P.x, &P.y, P.inf);
+        g1_add(&acc, &acc, &t);
+    }
+    g1_to_affine(&P.x, &P.y, &P.inf, &acc);
+    g1a_to_bytes(out, &P);
+    return 0;
+}
+EXPORT int orc_g2_sum(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    g2p acc, t; g2a P;
+    g2_set_identity(&acc);
+    for (size_t i = 0; i < n; i++) {
+        if (!g2a_from_bytes(&P, pts + 128 * i)) return -3;
+        g2_from_affine(&t, &P.x, &P.y, P.inf);
+        g2_add(&acc, &acc, &t);
+    }
+    g2_to_affine(&P.x, &P.y, &P.inf, &acc);
+    g2a_to_bytes(out, &P);
+    return 0;
+}
+EXPORT int orc_g1_generator(uint8_t out[64]) { orc_init(); g1a_to_bytes(out, &G1_GEN_A); return 0; }
+EXPORT int orc_g2_generator(uint8_t out[128]) { orc_init(); g2a_to_bytes(out, &G2_GEN_A); return 0; }
+
+/* ---- compressed codecs.  G1: g1.rs:283-288 / 311-328; G2: g2.rs:274-283 / 309-340.
+ * Decompression selects the root whose PARITY (G1) / sgn0 (G2) equals the flag -- i.e. the
+ * inverse of what to_compressed writes.  (The reference's G1 from_compressed uses is_high,
+ * g1.rs:320, which does not invert its own to_compressed)
+ * as_written != 0 reproduces the reference's is_high selection for G1. */
+EXPORT int orc_g1_compress(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        g1a P;
+        if (!g1a_from_bytes(&P, pts + 64 * i)) { memset(out + 32 * i, 0, 32); continue; }
+        fp_to_be(out + 32 * i, &P.x);
+        out[32 * i] |= (uint8_t)(fp_parity(&P.y) << 7);
+    }
+    return 0;
+}
+static int fp_is_high(const fp *a) { /* fp.rs:182-186: a > (p >> 1) */
+    uint64_t w[4], h[4];
+    fp_to_canon(w, a);
+    for (int i = 0; i < 4; i++) h[i] = (ORC_P[i] >> 1) | (i < 3 ? ORC_P[i + 1] << 63 : 0);
+    for (int i = 3; i >= 0; i--) { if (w[i] > h[i]) return 1; if (w[i] < h[i]) return 0; }
+    return 0;
+}
+EXPORT int orc_g1_decompress(const uint8_t *in, size_t n, uint8_t *out, uint8_t *status, int as_written) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        uint8_t xb[32];
+        fp x, y, gx;
+        g1a P;
+        memcpy(xb, in + 32 * i, 32);
+        int flag = xb[0] >> 7;
+        xb[0] &= 0x7f;
+        int ok = fp_from_be(&x, xb);
+        if (ok && fp_is_zero(&x)) { P.x = FP_ZERO; P.y = FP_ONE; P.inf = 1; }
+        else if (ok) {
+            fp_sqr(&gx, &x); fp_mul(&gx, &gx, &x); fp_add(&gx, &gx, &F_THREE);
+            ok = fp_sqrt(&y, &gx);
+            int cur = as_written ? fp_is_high(&y) : fp_parity(&y);
+            if (cur ^ flag) fp_neg(&y, &y);
+            P.x = x; P.y = y; P.inf = 0;
+        }
+        if (status) status[i] = (uint8_t)ok;
+        if (ok) g1a_to_bytes(out + 64 * i, &P); else memset(out + 64 * i, 0, 64);
+    }
+    return 0;
+}
+EXPORT int orc_g2_compress(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        g2a P;
+        if (!g2a_from_bytes(&P, pts + 128 * i)) { memset(out + 64 * i, 0, 64); continue; }
+        fp_to_be(out + 64 * i, &P.x.c1);
+        fp_to_be(out + 64 * i + 32, &P.x.c0);
+        out[64 * i] |= (uint8_t)(fp2_sgn0(&P.y) << 7);
+    }
+    return 0;
+}
+EXPORT int orc_g2_decompress(const uint8_t *in, size_t n, uint8_t *out, uint8_t *status) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) {
+        uint8_t xb[32];
+        fp2 x, y, gx;
+        g2a P;
+        memcpy(xb, in + 64 * i, 32);
+        int flag = xb[0] >> 7;
+        xb[0] &= 0x7f;
+        int ok = fp_from_be(&x.c1, xb) && fp_from_be(&x.c0, in + 64 * i + 32);
+        if (ok && fp2_is_zero(&x)) { fp2_set_zero(&P.x); fp2_set_one(&P.y); P.inf = 1; }
+        else if (ok) {
+            fp2_sqr(&gx, &x); fp2_mul(&gx, &gx, &x); fp2_add(&gx, &gx, &F2_B);
+            ok = fp2_sqrt(&y, &gx);
+            if (fp2_sgn0(&y) ^ flag) fp2_neg(&y, &y);
+            P.x = x; P.y = y; P.inf = 0;
+        }
+        if (status) status[i] = (uint8_t)ok;
+        if (ok) g2a_to_bytes(out + 128 * i, &P); else memset(out + 128 * i, 0, 128);
+    }
+    return 0;
+}
+/* on-curve predicates (g1.rs:383-391, g2.rs:409-414): out[i] = 1/0; undecodable -> 0 */
+EXPORT int orc_g1_is_on_curve(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) { g1a P; out[i] = (uint8_t)(g1a_from_bytes(&P, pts + 64 * i) && g1a_on_curve(&P)); }
+    return 0;
+}
+EXPORT int orc_g2_is_on_curve(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) { g2a P; out[i] = (uint8_t)(g2a_from_bytes(&P, pts + 128 * i) && g2a_on_curve(&P)); }
+    return 0;
+}

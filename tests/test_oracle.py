@@ -1,0 +1,233 @@
+"""CPU suite: the C oracle and the Python model against the reference's golden vectors
+(tests/golden/reference_kats.json <- g1.rs:980-1141, g2.rs:1038-1313, pairings.rs:387-479),
+against each other on random inputs, and through the algebraic properties SURVEY.md 8(c) lists
+for the parts no reference test pins."""
+import random
+
+import pytest
+
+from oracle import pymodel as pm
+
+H = lambda s: bytes.fromhex(s)
+DST_SIG = b"BLS_SIG_BN254G1_XMD:SHA-256_SVDW_RO_NUL_"
+DST_PK = b"BLS_SIG_BN254G2_XMD:SHA-256_SVDW_RO_NUL_"
+
+
+def g1b(p):
+    return pm.g1_to_uncompressed(p)
+
+
+def g2b(p):
+    return pm.g2_to_uncompressed(p)
+
+
+def test_g1_encode_kats(orc, kats):
+    dst = kats["g1_encode_dst"].encode()
+    msgs = [v["msg"].encode("latin1") for v in kats["g1_encode"]]
+    u = orc.hash_to_field_fp(msgs, dst, 1)
+    out = orc.hash_to_g1(msgs, dst, count=1)
+    for i, v in enumerate(kats["g1_encode"]):
+        assert u[32 * i:32 * i + 32] == H(v["u"])
+        assert out[64 * i:64 * i + 64] == H(v["p_x"]) + H(v["p_y"])
+        assert g1b(pm.encode_to_g1(msgs[i], dst)) == H(v["p_x"]) + H(v["p_y"])
+
+
+def test_g1_hash_kats(orc, kats):
+    dst = kats["g1_hash_dst"].encode()
+    msgs = [v["msg"].encode("latin1") for v in kats["g1_hash"]]
+    u = orc.hash_to_field_fp(msgs, dst, 2)
+    q = orc.svdw_g1(u)
+    out = orc.hash_to_g1(msgs, dst, count=2, nthreads=3)
+    for i, v in enumerate(kats["g1_hash"]):
+        assert u[64 * i:64 * i + 64] == H(v["u0"]) + H(v["u1"])
+        assert q[128 * i:128 * i + 128] == H(v["q0_x"]) + H(v["q0_y"]) + H(v["q1_x"]) + H(v["q1_y"])
+        assert out[64 * i:64 * i + 64] == H(v["p_x"]) + H(v["p_y"])
+        assert g1b(pm.hash_to_g1(msgs[i], dst)) == out[64 * i:64 * i + 64]
+
+
+@pytest.mark.parametrize("suite,count", [("g2_encode", 1), ("g2_hash", 2)])
+def test_g2_kats(orc, kats, suite, count):
+    dst = kats[suite + "_dst"].encode()
+    msgs = [v["msg"].encode("latin1") for v in kats[suite]]
+    out = orc.hash_to_g2(msgs, dst, count=count, nthreads=2)
+    for i, v in enumerate(kats[suite]):
+        exp = H(v["x_c1"]) + H(v["x_c0"]) + H(v["y_c1"]) + H(v["y_c0"])  # wire order c1 || c0 (g2.rs:290-300)
+        assert out[128 * i:128 * i + 128] == exp
+        f = pm.encode_to_g2 if count == 1 else pm.hash_to_g2
+        assert g2b(f(msgs[i], dst)) == exp
+
+
+def test_gt_generator_kat(orc, kats):
+    """pairings.rs:970-980: pairing(g1, g2) == Gt::generator(), and it has order r."""
+    exp = b"".join(H(x) for x in kats["gt_generator"])
+    gt = orc.pairing_batch(orc.g1_generator(), orc.g2_generator())
+    assert gt == exp
+    g = pm.pairing(pm.G1_GEN, pm.G2_GEN)
+    assert pm.gt_to_repr(g) == exp
+    assert pm.f12_pow(g, pm.R_ORDER) == pm.F12_ONE
+    assert g2b(pm.G2_GEN) == orc.g2_generator()
+    assert kats["g2_generator"]["x_c0"] == "%064x" % pm.G2_GEN[0][0]
+
+
+def test_survey_extra_pairing_vector(orc, kats):
+    """pairing(H_G1("abc"), H_G2("abc")) c0.c0 (model-derived vector)."""
+    p = orc.hash_to_g1([b"abc"], kats["g1_hash_dst"].encode())
+    q = orc.hash_to_g2([b"abc"], kats["g2_hash_dst"].encode())
+    gt = orc.pairing_batch(p, q)
+    assert gt[:64].hex() == ("07e603b5fdb03178ad589e88f61de7edf457fe91cdd8c1234e8d9a0bbf59e220"
+                             "24b2ff1c46ceb423d18e4b9b9395fafcbeb13678f2d5ee1e60d216ee1c6105ed")
+    assert gt[352:].hex() == "1d49cb9017ce22075f178f88a7f5b5e340042862d3ac27149f889e6c62bc8ae6"
+
+
+def test_final_exponentiation_matches_plain_power():
+    f = pm.multi_miller_loop([(pm.g1_mul(pm.G1_GEN, 7), pm.g2_mul(pm.G2_GEN, 11))])
+    assert pm.final_exponentiation(f) == pm.final_exponentiation_slow(f)
+
+
+def test_expand_message_xmd_edges(orc):
+    rng = random.Random(1)
+    for mlen in (0, 1, 54, 55, 56, 63, 64, 65, 119, 120, 1000):
+        for dlen in (0, 1, 43, 255, 256, 300):
+            for n in (32, 48, 96, 192):
+                msg = rng.randbytes(mlen)
+                dst = rng.randbytes(dlen)
+                assert orc.expand_message_xmd(msg, dst, n) == pm.expand_message_xmd(msg, dst, n)
+
+
+def test_oracle_vs_model_random(orc):
+    rng = random.Random(2)
+    msgs = [rng.randbytes(rng.choice([0, 1, 31, 32, 33, 100, 200])) for _ in range(12)]
+    out1 = orc.hash_to_g1(msgs, DST_SIG, nthreads=4)
+    out2 = orc.hash_to_g2(msgs, DST_PK, nthreads=4)
+    for i, m in enumerate(msgs):
+        assert out1[64 * i:64 * i + 64] == g1b(pm.hash_to_g1(m, DST_SIG))
+        assert out2[128 * i:128 * i + 128] == g2b(pm.hash_to_g2(m, DST_PK))
+    ps = [pm.g1_mul(pm.G1_GEN, rng.randrange(1, pm.R_ORDER)) for _ in range(4)] + [None]
+    qs = [pm.g2_mul(pm.G2_GEN, rng.randrange(1, pm.R_ORDER)) for _ in range(4)] + [pm.G2_GEN]
+    g1 = b"".join(g1b(p) for p in ps)
+    g2 = b"".join(g2b(q) for q in qs)
+    ml = orc.miller_loop_batch(g1, g2, nthreads=2)
+    gt = orc.pairing_batch(g1, g2, nthreads=2)
+    for i, (p, q) in enumerate(zip(ps, qs)):
+        f = pm.multi_miller_loop([(p, q)])
+        assert ml[384 * i:384 * i + 384] == pm.gt_to_repr(f)
+        assert gt[384 * i:384 * i + 384] == pm.gt_to_repr(pm.final_exponentiation(f))
+    assert gt[384 * 4:] == pm.gt_to_repr(pm.F12_ONE)  # identity contributes 1 (pairings.rs:789-800)
+    mm = orc.multi_miller_loop(g1, g2)
+    assert mm == pm.gt_to_repr(pm.multi_miller_loop(list(zip(ps, qs))))
+    assert orc.fp12_product(ml) == mm
+    assert orc.final_exponentiation(ml) == gt
+
+
+def test_scalar_mul_and_bilinearity(orc):
+    rng = random.Random(3)
+    a, b = rng.randrange(1, pm.R_ORDER), rng.randrange(1, pm.R_ORDER)
+    pa = orc.g1_mul(orc.g1_generator(), a.to_bytes(32, "big"))
+    qb = orc.g2_mul(orc.g2_generator(), b.to_bytes(32, "big"))
+    assert pa == g1b(pm.g1_mul(pm.G1_GEN, a))
+    assert qb == g2b(pm.g2_mul(pm.G2_GEN, b))
+    pab = orc.g1_mul(orc.g1_generator(), (a * b % pm.R_ORDER).to_bytes(32, "big"))
+    assert orc.pairing_batch(pa, qb) == orc.pairing_batch(pab, orc.g2_generator())
+    # group law KAT of the reference: 2*2*G + G == 5*G (g1.rs:1143-1149, g2.rs:1030-1036)
+    g4 = orc.g1_mul(orc.g1_generator(), (4).to_bytes(32, "big"))
+    assert orc.g1_sum(g4 + orc.g1_generator()) == orc.g1_mul(orc.g1_generator(), (5).to_bytes(32, "big"))
+    h4 = orc.g2_mul(orc.g2_generator(), (4).to_bytes(32, "big"))
+    assert orc.g2_sum(h4 + orc.g2_generator()) == orc.g2_mul(orc.g2_generator(), (5).to_bytes(32, "big"))
+    # [r]P = identity = (0, 1) on the wire
+    assert orc.g1_mul(pa, pm.R_ORDER.to_bytes(32, "big")) == bytes(31) + b"\x00" + bytes(31) + b"\x01"
+
+
+def _keys(orc, n, seed):
+    rng = random.Random(seed)
+    sks = [rng.randrange(1, pm.R_ORDER) for _ in range(n)]
+    msgs = [i.to_bytes(8, "little") + rng.randbytes(24) for i in range(n)]
+    sk_b = b"".join(s.to_bytes(32, "big") for s in sks)
+    return sks, msgs, sk_b
+
+
+def test_verify_min_sig(orc):
+    n = 6
+    sks, msgs, sk_b = _keys(orc, n, 4)
+    pks = orc.g2_mul(orc.g2_generator() * n, sk_b, nthreads=2)
+    hs = orc.hash_to_g1(msgs, DST_SIG)
+    sigs = bytearray(orc.g1_mul(hs, sk_b, nthreads=2))
+    assert orc.verify_batch(0, pks, msgs, bytes(sigs), DST_SIG, nthreads=3) == b"\x01" * n
+    assert pm.verify_min_sig(pm.g2_mul(pm.G2_GEN, sks[0]), msgs[0], pm.g1_mul(pm.hash_to_g1(msgs[0], DST_SIG), sks[0]), DST_SIG)
+    bad_msgs = list(msgs)
+    bad_msgs[2] = b"x" + msgs[2][1:]
+    sigs[64 * 4:64 * 5] = sigs[64 * 3:64 * 4]            # valid point, wrong signature
+    sigs[64 * 5:64 * 5 + 32] = b"\xff" * 32                # x >= p after masking -> undecodable
+    assert orc.verify_batch(0, pks, bad_msgs, bytes(sigs), DST_SIG, nthreads=2) == bytes([1, 1, 0, 1, 0, 0])
+    # aggregate
+    agg = orc.g1_sum(orc.g1_mul(hs, sk_b))
+    assert orc.aggregate_verify(0, pks, msgs, agg, DST_SIG, nthreads=3) == 1
+    assert orc.aggregate_verify(0, pks, bad_msgs, agg, DST_SIG, nthreads=1) == 0
+    assert orc.aggregate_verify(0, pks[:128 * 5], msgs[:5], agg, DST_SIG) == 0
+
+
+def test_verify_min_pk(orc):
+    n = 3
+    sks, msgs, sk_b = _keys(orc, n, 5)
+    pks = orc.g1_mul(orc.g1_generator() * n, sk_b)
+    hs = orc.hash_to_g2(msgs, DST_PK)
+    sigs = orc.g2_mul(hs, sk_b)
+    assert orc.verify_batch(1, pks, msgs, sigs, DST_PK) == b"\x01" * n
+    assert orc.verify_batch(1, pks, msgs[::-1], sigs, DST_PK) == bytes([0, 1, 0])
+    agg = orc.g2_sum(sigs)
+    assert orc.aggregate_verify(1, pks, msgs, agg, DST_PK, nthreads=2) == 1
+    assert orc.aggregate_verify(1, pks, msgs[::-1], agg, DST_PK) == 0
+    assert pm.verify_min_pk(pm.g1_mul(pm.G1_GEN, sks[1]), msgs[1], pm.g2_mul(pm.hash_to_g2(msgs[1], DST_PK), sks[1]), DST_PK)
+
+
+def test_codecs(orc, kats):
+    # generator KATs (g1.rs:955-965): x bytes = 0..01, y even
+    c = orc.g1_compress(orc.g1_generator())
+    assert c == bytes(31) + b"\x01"
+    rng = random.Random(6)
+    pts = orc.hash_to_g1([rng.randbytes(8) for _ in range(16)], DST_SIG)
+    comp = orc.g1_compress(pts)
+    back, st = orc.g1_decompress(comp)
+    assert st == b"\x01" * 16 and back == pts
+    for i in range(16):
+        p = (int.from_bytes(pts[64 * i:64 * i + 32], "big"), int.from_bytes(pts[64 * i + 32:64 * i + 64], "big"))
+        assert comp[32 * i:32 * i + 32] == pm.g1_to_compressed(p)
+    # as-written root selection (g1.rs:320) round-trips only when is_high(y) == parity(y)  (quirk Q5)
+    back_w, _ = orc.g1_decompress(comp, as_written=1)
+    same = sum(back_w[64 * i:64 * i + 64] == pts[64 * i:64 * i + 64] for i in range(16))
+    assert 0 < same < 16
+    q = orc.hash_to_g2([rng.randbytes(8) for _ in range(8)], DST_PK)
+    qc = orc.g2_compress(q)
+    qb, st = orc.g2_decompress(qc)
+    assert st == b"\x01" * 8 and qb == q
+    # identity encodings (g1.rs:265-288): 0x80 || 0...
+    ident = bytes(32) + bytes(31) + b"\x01"
+    assert orc.g1_compress(ident) == b"\x80" + bytes(31)
+    assert orc.g1_is_on_curve(pts + ident) == b"\x01" * 17
+    bad = bytearray(q[:128]); bad[127] ^= 1
+    assert orc.g2_is_on_curve(q + bytes(bad)) == b"\x01" * 8 + b"\x00"
+    # x not on curve -> decompress fails
+    j = 1
+    while pm.fp_is_square((j ** 3 + 3) % pm.P):
+        j += 1
+    _, st = orc.g1_decompress(j.to_bytes(32, "big"))
+    assert st == b"\x00"
+
+
+def test_svdw_exception(orc):
+    """u = +-1/2 makes tv1*tv2 = 0: the reference panics (fp.rs:325); here a status, not an abort."""
+    half = (pm.P + 1) // 2
+    out = orc.svdw_g1(half.to_bytes(32, "big") + (pm.P - half).to_bytes(32, "big") + (5).to_bytes(32, "big"))
+    assert out[:128] == bytes(128) and out[128:] != bytes(64)
+    assert pm.svdw_g1(half) is None
+
+
+def test_op_counts(orc):
+    """Work-unit accounting: Fp multiplications per unit, as executed by
+    the oracle (schoolbook Fp2, binary exponent ladders) -- printed for DESIGN.md, sanity-bounded."""
+    orc.mul_count(reset=True)
+    orc.mul_count(reset=True)
+    orc.miller_loop_batch(orc.g1_generator(), orc.g2_generator())
+    ml = orc.mul_count(reset=True)
+    orc.final_exponentiation(pm.gt_to_repr(pm.multi_miller_loop([(pm.G1_GEN, pm.G2_GEN)])))
+    fe = orc.mul_count(reset=True)
+    assert 8000 < ml < 20000 and 8000 < fe < 20000
