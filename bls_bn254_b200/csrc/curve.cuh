@@ -1,0 +1,259 @@
+// curve.cuh -- G1 (y^2 = x^3 + 3 over Fp) and G2 (y^2 = x^3 + 3/(9+u) over Fp2) group law,
+// affine conversion, psi endomorphism, cofactor clearing and the wire codecs.
+//
+// Role of /root/reference/src/inner_types/g1.rs:104-118 (to affine), 283-360 (codecs), 704-841
+// (add / double / multiply); g2.rs:98-112, 274-388, 685-693 (clear_cofactor), 749-886,
+// 938-954 (psi).  The reference uses the complete homogeneous-projective formulas of
+// Renes-Costello-Batina (eprint 2015/1060, a = 0); the same complete law is used here (one
+// branch-free formula for every input, identity included), written once over a field policy.
+// Results are compared after affine conversion, which is representation independent.
+#pragma once
+#include "tower.cuh"
+
+namespace bn {
+
+struct F1 {  // field policy: Fp
+    typedef fp T;
+    static BN_INL void add(T &r, const T &a, const T &b) { fp_add(r, a, b); }
+    static BN_INL void sub(T &r, const T &a, const T &b) { fp_sub(r, a, b); }
+    static BN_INL void mul(T &r, const T &a, const T &b) { fp_mulx(r, a, b); }
+    static BN_INL void sqr(T &r, const T &a) { fp_mulx(r, a, a); }
+    static BN_INL void neg(T &r, const T &a) { fp_neg(r, a); }
+    static BN_INL void mul_by_3b(T &r, const T &a) { fp_mul9(r, a); }  // fp.rs:414-416
+    static BN_INL void inv(T &r, const T &a) { fp_inv(r, a); }
+    static BN_INL bool is_zero(const T &a) { return fp_is_zero(a); }
+    static BN_INL void set_zero(T &r) { fp_set_zero(r); }
+    static BN_INL void set_one(T &r) { fp_set_one(r); }
+};
+struct F2 {  // field policy: Fp2
+    typedef fp2 T;
+    static BN_INL void add(T &r, const T &a, const T &b) { fp2_add(r, a, b); }
+    static BN_INL void sub(T &r, const T &a, const T &b) { fp2_sub(r, a, b); }
+    static BN_INL void mul(T &r, const T &a, const T &b) { fp2_mul(r, a, b); }
+    static BN_INL void sqr(T &r, const T &a) { fp2_sqr(r, a); }
+    static BN_INL void neg(T &r, const T &a) { fp2_neg(r, a); }
+    static BN_INL void mul_by_3b(T &r, const T &a) { fp2_mul(r, a, kfp2(k::B2_3)); }  // fp2.rs:411-413
+    static BN_INL void inv(T &r, const T &a) { fp2_inv(r, a); }
+    static BN_INL bool is_zero(const T &a) { return fp2_is_zero(a); }
+    static BN_INL void set_zero(T &r) { fp2_set_zero(r); }
+    static BN_INL void set_one(T &r) { fp2_set_one(r); }
+};
+
+template <class F>
+struct point {  // homogeneous projective (X : Y : Z); identity = (0 : 1 : 0)
+    typename F::T x, y, z;
+};
+typedef point<F1> g1p;
+typedef point<F2> g2p;
+struct g1a { fp x, y; bool inf; };
+struct g2a { fp2 x, y; bool inf; };
+
+template <class F>
+BN_INL void pt_set_identity(point<F> &r) {
+    F::set_zero(r.x);
+    F::set_one(r.y);
+    F::set_zero(r.z);
+}
+template <class F>
+BN_INL void pt_from_affine(point<F> &r, const typename F::T &x, const typename F::T &y, bool inf) {
+    if (inf) {
+        pt_set_identity(r);
+        return;
+    }
+    r.x = x;
+    r.y = y;
+    F::set_one(r.z);
+}
+
+// complete addition, RCB 2015/1060 Alg. 7 (g1.rs:744-786, g2.rs:789-831): 12 products + 2 by 3b
+template <class F>
+BN_NOINL void pt_add(point<F> &r, const point<F> &a, const point<F> &b) {
+    typename F::T t0, t1, t2, t3, t4, x3, y3, z3;
+    F::mul(t0, a.x, b.x);
+    F::mul(t1, a.y, b.y);
+    F::mul(t2, a.z, b.z);
+    F::add(t3, a.x, a.y);
+    F::add(t4, b.x, b.y);
+    F::mul(t3, t3, t4);
+    F::add(t4, t0, t1);
+    F::sub(t3, t3, t4);
+    F::add(t4, a.y, a.z);
+    F::add(x3, b.y, b.z);
+    F::mul(t4, t4, x3);
+    F::add(x3, t1, t2);
+    F::sub(t4, t4, x3);
+    F::add(x3, a.x, a.z);
+    F::add(y3, b.x, b.z);
+    F::mul(x3, x3, y3);
+    F::add(y3, t0, t2);
+    F::sub(y3, x3, y3);
+    F::add(x3, t0, t0);
+    F::add(t0, x3, t0);
+    F::mul_by_3b(t2, t2);
+    F::add(z3, t1, t2);
+    F::sub(t1, t1, t2);
+    F::mul_by_3b(y3, y3);
+    F::mul(x3, t4, y3);
+    F::mul(t2, t3, t1);
+    F::sub(x3, t2, x3);
+    F::mul(y3, y3, t0);
+    F::mul(t1, t1, z3);
+    F::add(y3, t1, y3);
+    F::mul(t0, t0, t3);
+    F::mul(z3, z3, t4);
+    F::add(z3, z3, t0);
+    r.x = x3;
+    r.y = y3;
+    r.z = z3;
+}
+// doubling, RCB Alg. 9 (g1.rs:789-818, g2.rs:834-863)
+template <class F>
+BN_NOINL void pt_dbl(point<F> &r, const point<F> &a) {
+    typename F::T t0, t1, t2, x3, y3, z3;
+    F::sqr(t0, a.y);
+    F::add(z3, t0, t0);
+    F::add(z3, z3, z3);
+    F::add(z3, z3, z3);
+    F::mul(t1, a.y, a.z);
+    F::sqr(t2, a.z);
+    F::mul_by_3b(t2, t2);
+    F::mul(x3, t2, z3);
+    F::add(y3, t0, t2);
+    F::mul(z3, t1, z3);
+    F::add(t1, t2, t2);
+    F::add(t2, t1, t2);
+    F::sub(t0, t0, t2);
+    F::mul(y3, t0, y3);
+    F::add(y3, x3, y3);
+    F::mul(t1, a.x, a.y);
+    F::mul(x3, t0, t1);
+    F::add(x3, x3, x3);
+    r.x = x3;
+    r.y = y3;
+    r.z = z3;
+}
+// projective -> affine; identity -> (0, 1), inf (g1.rs:104-118, 265-271)
+template <class F>
+BN_INL void pt_to_affine(typename F::T &x, typename F::T &y, bool &inf, const point<F> &a) {
+    typename F::T zi;
+    inf = F::is_zero(a.z);
+    F::inv(zi, a.z);  // 0 -> 0
+    F::mul(x, a.x, zi);
+    F::mul(y, a.y, zi);
+    if (inf) {
+        F::set_zero(x);
+        F::set_one(y);
+    }
+}
+// [k]a, k = nwords 32-bit words little-endian, MSB first double-and-add (g1.rs:821-841,
+// g2.rs:866-886 compute the same group element in constant time; inputs here are public)
+template <class F>
+BN_INL void pt_mul(point<F> &r, const point<F> &a, const uint32_t *kw, int nbits) {
+    point<F> acc, base = a;
+    pt_set_identity(acc);
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        if ((kw[i >> 5] >> (i & 31)) & 1) pt_add(acc, acc, base);
+    }
+    r = acc;
+}
+
+// g2.rs:938-954
+BN_INL void g2_psi(g2p &r, const g2p &a) {
+    fp2 t;
+    fp2_conj(t, a.x);
+    fp2_mul(r.x, t, kfp2(k::ENDO_U));
+    fp2_conj(t, a.y);
+    fp2_mul(r.y, t, kfp2(k::ENDO_V));
+    fp2_conj(r.z, a.z);
+}
+// g2.rs:685-693: [x]P + psi(3[x]P) + psi^2([x]P) + psi^3(P)
+BN_INL void g2_clear_cofactor(g2p &r, const g2p &a) {
+    g2p p0, p1, p2, t;
+    const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
+    pt_mul(p0, a, xw, 63);
+    pt_dbl(t, p0);
+    pt_add(t, t, p0);
+    g2_psi(p1, t);
+    g2_psi(t, p0);
+    g2_psi(p2, t);
+    pt_add(p0, p0, p1);
+    pt_add(p0, p0, p2);
+    g2_psi(t, a);
+    g2_psi(t, t);
+    g2_psi(t, t);
+    pt_add(r, p0, t);
+}
+
+// ---- wire formats -----------------------------------------------------------------------------
+// G1 uncompressed x || y (g1.rs:296-302); decode g1.rs:336-358: top bit of both coordinates
+// masked, x == 0 -> identity, y == 1 -> infinity flag.  Returns false for non-canonical bytes.
+BN_INL void g1a_to_bytes(uint8_t *out, const g1a &a) {
+    fp_to_be(out, a.x);
+    fp_to_be(out + 32, a.y);
+}
+BN_INL bool fp_from_be_masked(fp &r, const uint8_t *b) {
+    fp c;
+    fp_raw_from_be(c, b);
+    c.v[7] &= 0x7fffffffu;
+    bool ok = fp_raw_lt_p(c);
+    fp_to_mont(r, c);
+    return ok;
+}
+BN_INL bool g1a_from_bytes(g1a &a, const uint8_t *in) {
+    bool okx = fp_from_be_masked(a.x, in);
+    bool oky = fp_from_be_masked(a.y, in + 32);
+    if (!okx) return false;
+    if (fp_is_zero(a.x)) {
+        fp_set_one(a.y);
+        a.inf = true;
+        return true;
+    }
+    if (!oky) return false;
+    a.inf = fp_eq(a.y, kfp(k::ONE));
+    return true;
+}
+// G2 uncompressed x.c1 || x.c0 || y.c1 || y.c0 (g2.rs:290-300); decode g2.rs:346-388
+BN_INL void g2a_to_bytes(uint8_t *out, const g2a &a) {
+    fp_to_be(out, a.x.c1);
+    fp_to_be(out + 32, a.x.c0);
+    fp_to_be(out + 64, a.y.c1);
+    fp_to_be(out + 96, a.y.c0);
+}
+BN_INL bool g2a_from_bytes(g2a &a, const uint8_t *in) {
+    bool okx = fp_from_be(a.x.c1, in) & fp_from_be(a.x.c0, in + 32);
+    bool oky = fp_from_be(a.y.c1, in + 64) & fp_from_be(a.y.c0, in + 96);
+    if (!okx) return false;
+    if (fp2_is_zero(a.x)) {
+        fp2_set_one(a.y);
+        a.inf = true;
+        return true;
+    }
+    if (!oky) return false;
+    fp2 one;
+    fp2_set_one(one);
+    a.inf = fp2_eq(a.y, one);
+    return true;
+}
+// g1.rs:383-391, g2.rs:409-414
+BN_INL bool g1a_on_curve(const g1a &a) {
+    fp l, r;
+    if (a.inf) return fp_is_zero(a.x);
+    fp_mul(l, a.y, a.y);
+    fp_mul(r, a.x, a.x);
+    fp_mul(r, r, a.x);
+    fp_add(r, r, kfp(k::THREE));
+    return fp_eq(l, r);
+}
+BN_INL bool g2a_on_curve(const g2a &a) {
+    fp2 l, r;
+    if (a.inf) return true;
+    fp2_sqr(l, a.y);
+    fp2_sqr(r, a.x);
+    fp2_mul(r, r, a.x);
+    fp2_add(r, r, kfp2(k::B2));
+    return fp2_eq(l, r);
+}
+
+}  // namespace bn

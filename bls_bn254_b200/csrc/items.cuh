@@ -1,0 +1,204 @@
+// items.cuh -- the per-item bodies of every kernel (one message / point / pairing per thread).
+// kernels.cu wraps each of these in a __global__ grid-stride launch; tests/hostsim calls the very
+// same bodies in a host loop (g++ build, carry chains emulated) to unit-test the algebra on CPU.
+//
+// Device-internal formats (HBM, Montgomery form, array-of-structures, one 16-byte aligned
+// record per item so each thread moves whole 32-byte sectors):
+//   g1m  { fp x, y }        64 B      g2m  { fp2 x, y }      128 B      fp12            384 B
+//   flag byte per item:  FL_INF (point at infinity)  |  FL_BAD (undecodable / failed)
+#pragma once
+#include "h2c.cuh"
+#include "pairing.cuh"
+
+namespace bn {
+
+enum : uint8_t { FL_INF = 1, FL_BAD = 2 };
+enum : uint32_t { VERIFY_CHECK_ON_CURVE = 1u };
+
+struct __attribute__((aligned(16))) g1m { fp x, y; };
+struct __attribute__((aligned(16))) g2m { fp2 x, y; };
+
+// ---- decode / encode (wire <-> internal) --------------------------------------------------------
+BN_INL void item_g1_decode(g1m &out, uint8_t &fl, const uint8_t *in, bool check_curve) {
+    g1a a;
+    bool ok = g1a_from_bytes(a, in);
+    if (ok && check_curve) ok = g1a_on_curve(a);
+    out.x = a.x;
+    out.y = a.y;
+    fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
+}
+BN_INL void item_g2_decode(g2m &out, uint8_t &fl, const uint8_t *in, bool check_curve) {
+    g2a a;
+    bool ok = g2a_from_bytes(a, in);
+    if (ok && check_curve) ok = g2a_on_curve(a);
+    out.x = a.x;
+    out.y = a.y;
+    fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
+}
+BN_INL void zero_bytes(uint8_t *p, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) p[i] = 0;
+}
+BN_INL void item_g1_encode(uint8_t *out, const g1m &p, uint8_t fl) {
+    if (fl & FL_BAD) {
+        zero_bytes(out, 64);
+        return;
+    }
+    g1a a;
+    a.x = p.x;
+    a.y = p.y;
+    g1a_to_bytes(out, a);
+}
+BN_INL void item_g2_encode(uint8_t *out, const g2m &p, uint8_t fl) {
+    if (fl & FL_BAD) {
+        zero_bytes(out, 128);
+        return;
+    }
+    g2a a;
+    a.x = p.x;
+    a.y = p.y;
+    g2a_to_bytes(out, a);
+}
+
+// ---- hash to curve ---------------------------------------------------------------------------
+BN_INL void item_hash_g1(g1m &out, uint8_t &fl, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len, int count) {
+    g1a a;
+    bool ok = hash_to_g1(a, msg, len, dst, dst_len, count);
+    out.x = a.x;
+    out.y = a.y;
+    fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
+}
+BN_INL void item_hash_g2(g2m &out, uint8_t &fl, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len, int count) {
+    g2a a;
+    bool ok = hash_to_g2(a, msg, len, dst, dst_len, count);
+    out.x = a.x;
+    out.y = a.y;
+    fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
+}
+
+// ---- Miller loops ------------------------------------------------------------------------------
+// one pair (pairing(), pairings.rs:760-802 without the final exponentiation)
+BN_INL void item_miller1(fp12 &f, uint8_t &fl, const g1m &p, uint8_t flp, const g2m &q, uint8_t flq) {
+    fp px[1] = {p.x}, py[1] = {p.y};
+    g2a qa[1];
+    qa[0].x = q.x;
+    qa[0].y = q.y;
+    bool live[1] = {((flp | flq) & (FL_INF | FL_BAD)) == 0};
+    miller_loop<1, false>(f, px, py, qa, live);
+    fl = ((flp | flq) & FL_BAD) ? FL_BAD : 0;
+}
+// two pairs, shared squaring; pair 0 is (p0, -g2) through the precomputed line table when FIXED0
+template <bool FIXED0>
+BN_INL void item_miller2(fp12 &f, uint8_t &fl, const g1m &p0, uint8_t flp0, const g2m *q0, uint8_t flq0, const g1m &p1, uint8_t flp1,
+                         const g2m &q1, uint8_t flq1) {
+    fp px[2] = {p0.x, p1.x}, py[2] = {p0.y, p1.y};
+    g2a qa[2];
+    if (!FIXED0) {
+        qa[0].x = q0->x;
+        qa[0].y = q0->y;
+    }
+    qa[1].x = q1.x;
+    qa[1].y = q1.y;
+    bool live[2] = {((flp0 | flq0) & (FL_INF | FL_BAD)) == 0, ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0};
+    miller_loop<2, FIXED0>(f, px, py, qa, live);
+    fl = ((flp0 | flq0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
+}
+
+// ---- final exponentiation / GT ---------------------------------------------------------------
+BN_INL void item_final_exp(fp12 &f) {
+    fp12 t = f;
+    final_exponentiation(f, t);
+}
+
+// ---- scalar multiplication (sign / keygen / test-data side; g1.rs:821-841, g2.rs:866-886) -------
+BN_INL void scalar_words(uint32_t kw[8], const uint8_t *be) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint8_t *q = be + 4 * (7 - i);
+        kw[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+    }
+}
+BN_INL void item_g1_mul(g1m &out, uint8_t &flo, const g1m &p, uint8_t fl, const uint8_t *scalar_be) {
+    uint32_t kw[8];
+    scalar_words(kw, scalar_be);
+    g1p a, r;
+    pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
+    pt_mul(r, a, kw, 256);
+    bool inf;
+    pt_to_affine(out.x, out.y, inf, r);
+    flo = (fl & FL_BAD) ? FL_BAD : (inf ? FL_INF : 0);
+}
+BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const uint8_t *scalar_be) {
+    uint32_t kw[8];
+    scalar_words(kw, scalar_be);
+    g2p a, r;
+    pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
+    pt_mul(r, a, kw, 256);
+    bool inf;
+    pt_to_affine(out.x, out.y, inf, r);
+    flo = (fl & FL_BAD) ? FL_BAD : (inf ? FL_INF : 0);
+}
+
+// ---- compressed codecs (g1.rs:283-288 / 311-328, g2.rs:274-283 / 309-340) ------------------------
+// Decompression picks the root whose parity (G1) / sgn0 (G2) equals the flag bit, i.e. the inverse
+// of to_compressed.  (The reference's G1 from_compressed selects by is_high, g1.rs:320, which does
+// not invert its own to_compressed for about half of all points)
+BN_INL void item_g1_compress(uint8_t *out, const g1m &p, uint8_t fl) {
+    if (fl & FL_BAD) {
+        zero_bytes(out, 32);
+        return;
+    }
+    fp_to_be(out, p.x);
+    out[0] |= (uint8_t)(fp_parity(p.y) << 7);
+}
+BN_INL void item_g1_decompress(g1m &out, uint8_t &fl, const uint8_t *in) {
+    fp x, y, gx, ny;
+    uint32_t flag = in[0] >> 7;
+    bool ok = fp_from_be_masked(x, in);
+    if (ok && fp_is_zero(x)) {
+        fp_set_zero(out.x);
+        fp_set_one(out.y);
+        fl = FL_INF;
+        return;
+    }
+    fp_mul(gx, x, x);
+    fp_mul(gx, gx, x);
+    fp_add(gx, gx, kfp(k::THREE));
+    ok &= fp_sqrt(y, gx);
+    fp_neg(ny, y);
+    fp_select(y, (fp_parity(y) ^ flag) != 0, ny, y);
+    out.x = x;
+    out.y = y;
+    fl = ok ? 0 : FL_BAD;
+}
+BN_INL void item_g2_compress(uint8_t *out, const g2m &p, uint8_t fl) {
+    if (fl & FL_BAD) {
+        zero_bytes(out, 64);
+        return;
+    }
+    fp_to_be(out, p.x.c1);
+    fp_to_be(out + 32, p.x.c0);
+    out[0] |= (uint8_t)(fp2_sgn0(p.y) << 7);
+}
+BN_INL void item_g2_decompress(g2m &out, uint8_t &fl, const uint8_t *in) {
+    fp2 x, y, gx, ny;
+    uint32_t flag = in[0] >> 7;
+    bool ok = fp_from_be_masked(x.c1, in) & fp_from_be(x.c0, in + 32);
+    if (ok && fp2_is_zero(x)) {
+        fp2_set_zero(out.x);
+        fp2_set_one(out.y);
+        fl = FL_INF;
+        return;
+    }
+    fp2_sqr(gx, x);
+    fp2_mul(gx, gx, x);
+    fp2_add(gx, gx, kfp2(k::B2));
+    ok &= fp2_sqrt(y, gx);
+    fp2_neg(ny, y);
+    fp2_select(y, (fp2_sgn0(y) ^ flag) != 0, ny, y);
+    out.x = x;
+    out.y = y;
+    fl = ok ? 0 : FL_BAD;
+}
+
+}  // namespace bn

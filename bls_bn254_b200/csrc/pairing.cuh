@@ -1,0 +1,197 @@
+// pairing.cuh -- optimal-ate Miller loop and final exponentiation for BN254.
+//
+// Role of /root/reference/src/inner_types/pairings.rs:50-178 (final_exponentiation,
+// cyclotomic_square, exp by x), 609-660 / 725-757 (G2Prepared), 760-886 (pairing,
+// multi_miller_loop, miller_loop), 888-962 (ell, doubling_step, addition_step).
+// doubling_step / addition_step keep the reference's formulas (eprint 2010/354 Alg. 26/27) so the
+// un-exponentiated MillerLoopResult is bit-identical to the oracle's; around them sits the BN254
+// loop the reference's known-answer test requires: NAF(6x+2), two Frobenius
+// additions, D-twist placement 0/3/4, Fuentes-Castaneda hard part scaled by 2x(6x^2+3x+1).
+#pragma once
+#include "curve.cuh"
+
+namespace bn {
+
+struct line_t { fp2 a, b, c; };  // evaluated as (a * yP) + (b * xP) w + c w^3
+struct g2j { fp2 x, y, z; };     // Jacobian accumulator of the Miller loop
+
+// pairings.rs:901-930
+BN_NOINL void doubling_step(line_t &l, g2j &r) {
+    fp2 tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, zsq, t;
+    fp2_sqr(tmp0, r.x);
+    fp2_sqr(tmp1, r.y);
+    fp2_sqr(tmp2, tmp1);
+    fp2_add(tmp3, tmp1, r.x); fp2_sqr(tmp3, tmp3); fp2_sub(tmp3, tmp3, tmp0); fp2_sub(tmp3, tmp3, tmp2);
+    fp2_dbl(tmp3, tmp3);
+    fp2_dbl(tmp4, tmp0); fp2_add(tmp4, tmp4, tmp0);
+    fp2_add(tmp6, r.x, tmp4);
+    fp2_sqr(tmp5, tmp4);
+    fp2_sqr(zsq, r.z);
+    fp2_sub(r.x, tmp5, tmp3); fp2_sub(r.x, r.x, tmp3);
+    fp2_add(t, r.z, r.y); fp2_sqr(t, t); fp2_sub(t, t, tmp1); fp2_sub(r.z, t, zsq);
+    fp2_sub(t, tmp3, r.x); fp2_mul(r.y, t, tmp4);
+    fp2_dbl(tmp2, tmp2); fp2_dbl(tmp2, tmp2); fp2_dbl(tmp2, tmp2);
+    fp2_sub(r.y, r.y, tmp2);
+    fp2_mul(tmp3, tmp4, zsq); fp2_dbl(tmp3, tmp3); fp2_neg(tmp3, tmp3);
+    fp2_sqr(tmp6, tmp6); fp2_sub(tmp6, tmp6, tmp0); fp2_sub(tmp6, tmp6, tmp5);
+    fp2_dbl(tmp1, tmp1); fp2_dbl(tmp1, tmp1);
+    fp2_sub(tmp6, tmp6, tmp1);
+    fp2_mul(tmp0, r.z, zsq); fp2_dbl(tmp0, tmp0);
+    l.a = tmp0;
+    l.b = tmp3;
+    l.c = tmp6;
+}
+// pairings.rs:932-962
+BN_NOINL void addition_step(line_t &l, g2j &r, const fp2 &qx, const fp2 &qy) {
+    fp2 zsq, ysq, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, zt;
+    fp2_sqr(zsq, r.z);
+    fp2_sqr(ysq, qy);
+    fp2_mul(t0, zsq, qx);
+    fp2_add(t1, qy, r.z); fp2_sqr(t1, t1); fp2_sub(t1, t1, ysq); fp2_sub(t1, t1, zsq); fp2_mul(t1, t1, zsq);
+    fp2_sub(t2, t0, r.x);
+    fp2_sqr(t3, t2);
+    fp2_dbl(t4, t3); fp2_dbl(t4, t4);
+    fp2_mul(t5, t4, t2);
+    fp2_sub(t6, t1, r.y); fp2_sub(t6, t6, r.y);
+    fp2_mul(t9, t6, qx);
+    fp2_mul(t7, t4, r.x);
+    fp2_sqr(r.x, t6); fp2_sub(r.x, r.x, t5); fp2_sub(r.x, r.x, t7); fp2_sub(r.x, r.x, t7);
+    fp2_add(r.z, r.z, t2); fp2_sqr(r.z, r.z); fp2_sub(r.z, r.z, zsq); fp2_sub(r.z, r.z, t3);
+    fp2_add(t10, qy, r.z);
+    fp2_sub(t8, t7, r.x); fp2_mul(t8, t8, t6);
+    fp2_mul(t0, r.y, t5); fp2_dbl(t0, t0);
+    fp2_sub(r.y, t8, t0);
+    fp2_sqr(t10, t10); fp2_sub(t10, t10, ysq);
+    fp2_sqr(zt, r.z);
+    fp2_sub(t10, t10, zt);
+    fp2_dbl(t9, t9); fp2_sub(t9, t9, t10);
+    fp2_dbl(t10, r.z);
+    fp2_neg(t6, t6);
+    fp2_dbl(t1, t6);
+    l.a = t10;
+    l.b = t1;
+    l.c = t9;
+}
+// pairings.rs:888-899 with the D-twist placement
+BN_INL void ell(fp12 &f, const line_t &l, const fp &px, const fp &py) {
+    fp2 c0, c1;
+    fp2_mul_fp(c0, l.a, py);
+    fp2_mul_fp(c1, l.b, px);
+    fp12_mul_by_034(f, c0, c1, l.c);
+}
+BN_INL const line_t &fixed_line(int idx) { return *reinterpret_cast<const line_t *>(&k::NEG_G2_LINES[idx][0][0][0]); }
+
+// Product of NP Miller loops with one shared squaring per step (multi_miller_loop,
+// pairings.rs:808-857).  Pair i is skipped when live[i] is false (identity inputs contribute 1,
+// pairings.rs:820-835).  When FIXED0, pair 0 is (P0, -g2) and its 88 lines come from the
+// precomputed table (the G2Prepared role, pairings.rs:609-660) instead of being recomputed.
+template <int NP, bool FIXED0>
+BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const bool *live) {
+    g2j r[NP];
+    fp2 nqy[NP];
+    line_t l;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        if (FIXED0 && i == 0) continue;
+        r[i].x = q[i].x;
+        r[i].y = q[i].y;
+        fp2_set_one(r[i].z);
+        fp2_neg(nqy[i], q[i].y);
+    }
+    fp12_set_one(f);
+    int idx = 0;
+#pragma unroll 1
+    for (int s = 0; s < BN254_ATE_NAF_LEN; s++) {
+        int d = k::ATE_NAF[s];
+        if (s) fp12_sqr(f, f);  // f = 1 on the first step
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            if (!live[i]) continue;
+            if (FIXED0 && i == 0) {
+                ell(f, fixed_line(idx), px[0], py[0]);
+            } else {
+                doubling_step(l, r[i]);
+                ell(f, l, px[i], py[i]);
+            }
+        }
+        idx++;
+        if (d) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                if (!live[i]) continue;
+                if (FIXED0 && i == 0) {
+                    ell(f, fixed_line(idx), px[0], py[0]);
+                } else {
+                    addition_step(l, r[i], q[i].x, d > 0 ? q[i].y : nqy[i]);
+                    ell(f, l, px[i], py[i]);
+                }
+            }
+            idx++;
+        }
+    }
+    // two Frobenius additions: Q1 = psi(Q), Q2 = -psi^2(Q)
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        if (!live[i]) continue;
+        if (FIXED0 && i == 0) {
+            ell(f, fixed_line(idx), px[0], py[0]);
+            ell(f, fixed_line(idx + 1), px[0], py[0]);
+        } else {
+            fp2 q1x, q1y, q2x, q2y, t;
+            fp2_conj(t, q[i].x); fp2_mul(q1x, t, kfp2(k::ENDO_U));
+            fp2_conj(t, q[i].y); fp2_mul(q1y, t, kfp2(k::ENDO_V));
+            fp2_conj(t, q1x); fp2_mul(q2x, t, kfp2(k::ENDO_U));
+            fp2_conj(t, q1y); fp2_mul(q2y, t, kfp2(k::ENDO_V));
+            fp2_neg(q2y, q2y);
+            addition_step(l, r[i], q1x, q1y);
+            ell(f, l, px[i], py[i]);
+            addition_step(l, r[i], q2x, q2y);
+            ell(f, l, px[i], py[i]);
+        }
+    }
+}
+
+// f^x (x = 0x44e992b44a6909f1, 63 bits) in the cyclotomic subgroup, then conjugate
+// (pairings.rs:117-134 role)
+BN_NOINL void cyclotomic_exp_neg_x(fp12 &r, const fp12 &f) {
+    fp12 t = f;
+#pragma unroll 1
+    for (int i = 61; i >= 0; i--) {
+        cyclotomic_square(t, t);
+        if ((BN254_X >> i) & 1) fp12_mul(t, t, f);
+    }
+    fp12_conj(r, t);
+}
+// pairings.rs:50-178 role: easy part f^((p^6-1)(p^2+1)), then the Fuentes-Castaneda hard part
+BN_INL void final_exponentiation(fp12 &out, const fp12 &f) {
+    fp12 r, t, y0, y1, y3, y4, y6;
+    fp12_conj(r, f);
+    fp12_inv(t, f);
+    fp12_mul(t, r, t);          // f^(p^6-1)
+    fp12_frob(r, t, 2);
+    fp12_mul(r, r, t);          // r = f^((p^6-1)(p^2+1))
+    cyclotomic_exp_neg_x(y0, r);
+    cyclotomic_square(y1, y0);
+    cyclotomic_square(t, y1);
+    fp12_mul(y3, t, y1);
+    cyclotomic_exp_neg_x(y4, y3);
+    cyclotomic_square(t, y4);
+    cyclotomic_exp_neg_x(y6, t);
+    fp12_conj(y3, y3);
+    fp12_conj(y6, y6);
+    fp12_mul(t, y6, y4);        // y7
+    fp12_mul(y3, t, y3);        // y8
+    fp12_mul(y0, y3, y1);       // y9
+    fp12_mul(t, y3, y4);        // y10
+    fp12_mul(t, t, r);          // y11
+    fp12_frob(y1, y0, 1);       // y12
+    fp12_mul(t, y1, t);         // y13
+    fp12_frob(y3, y3, 2);
+    fp12_mul(t, y3, t);         // y14
+    fp12_conj(y1, r);
+    fp12_mul(y1, y1, y0);       // y15
+    fp12_frob(y1, y1, 3);
+    fp12_mul(out, y1, t);
+}
+
+}  // namespace bn

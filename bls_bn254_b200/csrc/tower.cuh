@@ -1,0 +1,306 @@
+// tower.cuh -- Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3 - xi), Fp12 = Fp6[w]/(w^2 - v), xi = 9+u.
+//
+// Role of /root/reference/src/inner_types/fp2.rs:95-99,161-218,377-452, fp6.rs:123-287,
+// fp12.rs:120-219 -- with the "Tier B" tower (xi = 9+u, D-twist sparse placement 0/3/4, real
+// Frobenius constants) that the reference's own pairing known-answer test demands
+// (pairings.rs:387-479, 970-980).  Field elements are canonical after
+// every operation, so any algebraically equal formula gives bit-identical wire bytes; the
+// formulas below are chosen for the GPU (Karatsuba Fp2, complex squaring, sparse line products).
+#pragma once
+#include "fp.cuh"
+
+namespace bn {
+
+struct fp2 { fp c0, c1; };
+struct fp6 { fp2 c0, c1, c2; };
+struct fp12 { fp6 c0, c1; };
+
+BN_INL const fp2 &kfp2(const uint32_t (&a)[2][8]) { return *reinterpret_cast<const fp2 *>(&a[0][0]); }
+
+// ------------------------------------------------------------------------------------------ Fp2
+BN_INL void fp2_set_zero(fp2 &r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
+BN_INL void fp2_set_one(fp2 &r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
+BN_INL bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
+BN_INL bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
+BN_INL void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+BN_INL void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+BN_INL void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+BN_INL void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+BN_INL void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
+BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
+
+// fp2.rs:377-390 (there: 4 products); Karatsuba, 3 products
+BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
+    fp t0, t1, s, t;
+    fp_mul(t0, a.c0, b.c0);
+    fp_mul(t1, a.c1, b.c1);
+    fp_add(s, a.c0, a.c1);
+    fp_add(t, b.c0, b.c1);
+    fp_mul(s, s, t);
+    fp_sub(s, s, t0);
+    fp_sub(r.c1, s, t1);
+    fp_sub(r.c0, t0, t1);
+}
+// fp2.rs:392-402
+BN_NOINL void fp2_sqr(fp2 &r, const fp2 &a) {
+    fp s, d, m;
+    fp_add(s, a.c0, a.c1);
+    fp_sub(d, a.c0, a.c1);
+    fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d);
+    fp_dbl(r.c1, m);
+}
+BN_NOINL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
+// (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
+BN_INL void fp2_mul_xi(fp2 &r, const fp2 &a) {
+    fp t0, t1;
+    fp_mul9(t0, a.c0);
+    fp_mul9(t1, a.c1);
+    fp_sub(t0, t0, a.c1);
+    fp_add(r.c1, t1, a.c0);
+    r.c0 = t0;
+}
+// fp2.rs:161-166
+BN_NOINL void fp2_inv(fp2 &r, const fp2 &a) {
+    fp t0, t1;
+    fp_mul(t0, a.c0, a.c0);
+    fp_mul(t1, a.c1, a.c1);
+    fp_add(t0, t0, t1);
+    fp_inv(t0, t0);
+    fp_mul(r.c0, a.c0, t0);
+    fp_neg(t0, t0);
+    fp_mul(r.c1, a.c1, t0);
+}
+BN_INL uint32_t fp2_sgn0(const fp2 &a) {  // fp2.rs:95-99
+    return fp_parity(a.c0) | ((uint32_t)fp_is_zero(a.c0) & fp_parity(a.c1));
+}
+BN_INL void fp2_norm(fp &n, const fp2 &a) {
+    fp t;
+    fp_mul(n, a.c0, a.c0);
+    fp_mul(t, a.c1, a.c1);
+    fp_add(n, n, t);
+}
+BN_INL bool fp2_is_square(const fp2 &a) {  // fp2.rs:441-452
+    fp n;
+    fp2_norm(n, a);
+    return fp_is_square(n);
+}
+// Square root in Fp2 (role of fp2.rs:172-218).  The reference runs Alg. 9 of eprint 2012/685
+// (two Fp2 exponentiations); its callers re-normalise the sign afterwards (fp2.rs:282-283,
+// g2.rs:331), so either root is acceptable and the "complex" method is used here -- two Fp
+// exponentiations and no inversion:
+//   s = sqrt(a0^2 + a1^2);  d = (a0 + s)/2;  w = d^((p-3)/4), t = w d   (t^2 = +-d, w t = +-1)
+//   d a square:      x = t + (a1/2) w u            d a non-square:  x = -(a1/2) w + t u
+// Returns false when a is not a square.
+BN_NOINL bool fp2_sqrt(fp2 &r, const fp2 &a) {
+    fp n, s, d, w, t, h, chk;
+    const fp &half = kfp(k::SVDW1_C2);  // (p-1)/2 = -1/2
+    fp2_norm(n, a);
+    bool ok = fp_sqrt(s, n);
+    fp_add(d, a.c0, s);
+    fp_mul(d, d, half);
+    fp_neg(d, d);  // (a0 + s)/2
+    if (fp_is_zero(d)) {  // a0 = -s: use the other root of the norm (d' = (a0 - s)/2 = a0)
+        fp_sub(d, a.c0, s);
+        fp_mul(d, d, half);
+        fp_neg(d, d);
+    }
+    fp_pow(w, d, k::EXP_P_MINUS_3_DIV_4);
+    fp_mul(t, w, d);
+    fp_mul(chk, t, t);
+    bool dsq = fp_eq(chk, d);
+    fp_mul(h, a.c1, half);
+    fp_mul(h, h, w);  // -(a1/2) w
+    fp2 x, y;
+    fp_neg(x.c1, h);
+    x.c0 = t;
+    y.c0 = h;
+    y.c1 = t;
+    fp2_select(r, dsq, x, y);
+    if (fp_is_zero(d)) fp2_set_zero(r);  // a = 0
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------ Fp6
+BN_INL void fp6_add(fp6 &r, const fp6 &a, const fp6 &b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
+BN_INL void fp6_sub(fp6 &r, const fp6 &a, const fp6 &b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
+BN_INL void fp6_neg(fp6 &r, const fp6 &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
+BN_INL void fp6_dbl(fp6 &r, const fp6 &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
+// Karatsuba, 6 Fp2 products (role of fp6.rs:225-242)
+BN_NOINL void fp6_mul(fp6 &r, const fp6 &a, const fp6 &b) {
+    fp2 v0, v1, v2, t0, t1, t2, c0, c1;
+    fp2_mul(v0, a.c0, b.c0);
+    fp2_mul(v1, a.c1, b.c1);
+    fp2_mul(v2, a.c2, b.c2);
+    fp2_add(t0, a.c1, a.c2); fp2_add(t1, b.c1, b.c2); fp2_mul(t2, t0, t1);
+    fp2_sub(t2, t2, v1); fp2_sub(t2, t2, v2); fp2_mul_xi(t2, t2); fp2_add(c0, t2, v0);
+    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b.c0, b.c1); fp2_mul(t2, t0, t1);
+    fp2_sub(t2, t2, v0); fp2_sub(t2, t2, v1); fp2_mul_xi(t0, v2); fp2_add(c1, t2, t0);
+    fp2_add(t0, a.c0, a.c2); fp2_add(t1, b.c0, b.c2); fp2_mul(t2, t0, t1);
+    fp2_sub(t2, t2, v0); fp2_sub(t2, t2, v2); fp2_add(r.c2, t2, v1);
+    r.c0 = c0;
+    r.c1 = c1;
+}
+// a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01)
+BN_NOINL void fp6_mul_by_01(fp6 &r, const fp6 &a, const fp2 &b0, const fp2 &b1) {
+    fp2 v0, v1, t0, t1, t2, c0, c1;
+    fp2_mul(v0, a.c0, b0);
+    fp2_mul(v1, a.c1, b1);
+    fp2_add(t0, a.c1, a.c2); fp2_mul(t2, t0, b1); fp2_sub(t2, t2, v1); fp2_mul_xi(t2, t2); fp2_add(c0, t2, v0);
+    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t2, t0, t1); fp2_sub(t2, t2, v0); fp2_sub(c1, t2, v1);
+    fp2_add(t0, a.c0, a.c2); fp2_mul(t2, t0, b0); fp2_sub(t2, t2, v0); fp2_add(r.c2, t2, v1);
+    r.c0 = c0;
+    r.c1 = c1;
+}
+BN_INL void fp6_mul_fp2(fp6 &r, const fp6 &a, const fp2 &b) { fp2_mul(r.c0, a.c0, b); fp2_mul(r.c1, a.c1, b); fp2_mul(r.c2, a.c2, b); }
+// multiply by v (fp6.rs:146-152 with xi = 9+u)
+BN_INL void fp6_mul_v(fp6 &r, const fp6 &a) {
+    fp2 t;
+    fp2_mul_xi(t, a.c2);
+    r.c2 = a.c1;
+    r.c1 = a.c0;
+    r.c0 = t;
+}
+// fp6.rs:261-287
+BN_NOINL void fp6_inv(fp6 &r, const fp6 &a) {
+    fp2 t0, t1, t2, d, s;
+    fp2_sqr(t0, a.c0); fp2_mul(s, a.c1, a.c2); fp2_mul_xi(s, s); fp2_sub(t0, t0, s);
+    fp2_sqr(t1, a.c2); fp2_mul_xi(t1, t1); fp2_mul(s, a.c0, a.c1); fp2_sub(t1, t1, s);
+    fp2_sqr(t2, a.c1); fp2_mul(s, a.c0, a.c2); fp2_sub(t2, t2, s);
+    fp2_mul(d, a.c2, t1); fp2_mul(s, a.c1, t2); fp2_add(d, d, s); fp2_mul_xi(d, d);
+    fp2_mul(s, a.c0, t0); fp2_add(d, d, s);
+    fp2_inv(d, d);
+    fp2_mul(r.c0, t0, d); fp2_mul(r.c1, t1, d); fp2_mul(r.c2, t2, d);
+}
+
+// ------------------------------------------------------------------------------------------ Fp12
+BN_INL void fp12_set_one(fp12 &r) {
+    fp2_set_one(r.c0.c0); fp2_set_zero(r.c0.c1); fp2_set_zero(r.c0.c2);
+    fp2_set_zero(r.c1.c0); fp2_set_zero(r.c1.c1); fp2_set_zero(r.c1.c2);
+}
+BN_INL bool fp12_is_one(const fp12 &a) {
+    fp2 one;
+    fp2_set_one(one);
+    return fp2_eq(a.c0.c0, one) & fp2_is_zero(a.c0.c1) & fp2_is_zero(a.c0.c2) & fp2_is_zero(a.c1.c0) & fp2_is_zero(a.c1.c1) &
+           fp2_is_zero(a.c1.c2);
+}
+// fp12.rs:203-210
+BN_NOINL void fp12_mul(fp12 &r, const fp12 &a, const fp12 &b) {
+    fp6 aa, bb, s, t;
+    fp6_mul(aa, a.c0, b.c0);
+    fp6_mul(bb, a.c1, b.c1);
+    fp6_add(s, a.c0, a.c1);
+    fp6_add(t, b.c0, b.c1);
+    fp6_mul(s, s, t);
+    fp6_sub(s, s, aa);
+    fp6_sub(r.c1, s, bb);
+    fp6_mul_v(bb, bb);
+    fp6_add(r.c0, aa, bb);
+}
+// fp12.rs:170-180 (complex squaring, 2 Fp6 products)
+BN_NOINL void fp12_sqr(fp12 &r, const fp12 &a) {
+    fp6 ab, s, t;
+    fp6_mul(ab, a.c0, a.c1);
+    fp6_add(s, a.c0, a.c1);
+    fp6_mul_v(t, a.c1);
+    fp6_add(t, t, a.c0);
+    fp6_mul(s, s, t);
+    fp6_sub(s, s, ab);
+    fp6_mul_v(t, ab);
+    fp6_sub(r.c0, s, t);
+    fp6_dbl(r.c1, ab);
+}
+BN_INL void fp12_conj(fp12 &r, const fp12 &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }  // fp12.rs:131-136
+// fp12.rs:212-219
+BN_NOINL void fp12_inv(fp12 &r, const fp12 &a) {
+    fp6 t0, t1;
+    fp6_mul(t0, a.c0, a.c0);
+    fp6_mul(t1, a.c1, a.c1);
+    fp6_mul_v(t1, t1);
+    fp6_sub(t0, t0, t1);
+    fp6_inv(t0, t0);
+    fp6_mul(r.c0, a.c0, t0);
+    fp6_mul(t1, a.c1, t0);
+    fp6_neg(r.c1, t1);
+}
+// f * (c0 + c3 w + c4 w^3): the D-twist sparse line product, 13 Fp2 products
+// (role of fp12.rs:120-129 mul_by_014 with the placement corrected to 0/3/4)
+BN_NOINL void fp12_mul_by_034(fp12 &f, const fp2 &c0, const fp2 &c3, const fp2 &c4) {
+    fp6 t0, t1, s;
+    fp2 d;
+    fp6_mul_fp2(t0, f.c0, c0);
+    fp6_mul_by_01(t1, f.c1, c3, c4);
+    fp2_add(d, c0, c3);
+    fp6_add(s, f.c0, f.c1);
+    fp6_mul_by_01(s, s, d, c4);
+    fp6_sub(s, s, t0);
+    fp6_sub(f.c1, s, t1);
+    fp6_mul_v(t1, t1);
+    fp6_add(f.c0, t0, t1);
+}
+// coefficient of w^i: i even -> c0.c(i/2), i odd -> c1.c((i-1)/2)
+BN_INL fp2 &fp12_coeff(fp12 &a, int i) {
+    fp6 &h = (i & 1) ? a.c1 : a.c0;
+    return (i >> 1) == 0 ? h.c0 : ((i >> 1) == 1 ? h.c1 : h.c2);
+}
+// x -> x^(p^kk), kk = 1, 2, 3 (role of fp12.rs:139-168 with the real constants xi^(i(p^k-1)/6))
+BN_NOINL void fp12_frob(fp12 &r, const fp12 &a, int kk) {
+    fp12 t = a;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+        fp2 &c = fp12_coeff(t, i);
+        if (kk & 1) fp2_conj(c, c);
+        if (i) {
+            const fp2 &g = *reinterpret_cast<const fp2 *>(&k::GAMMA[kk - 1][i - 1][0][0]);
+            if (kk == 2) fp2_mul_fp(c, c, g.c0);
+            else fp2_mul(c, c, g);
+        }
+    }
+    r = t;
+}
+
+// pairings.rs:52-63
+BN_INL void fp4_square(fp2 &c0, fp2 &c1, const fp2 &a, const fp2 &b) {
+    fp2 t0, t1, t2;
+    fp2_sqr(t0, a);
+    fp2_sqr(t1, b);
+    fp2_mul_xi(t2, t1);
+    fp2_add(c0, t2, t0);
+    fp2_add(t2, a, b);
+    fp2_sqr(t2, t2);
+    fp2_sub(t2, t2, t0);
+    fp2_sub(c1, t2, t1);
+}
+// Granger-Scott squaring in the cyclotomic subgroup (pairings.rs:68-115)
+BN_NOINL void cyclotomic_square(fp12 &r, const fp12 &f) {
+    fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+    fp2 t0, t1, t2, t3;
+    fp4_square(t0, t1, z0, z1);
+    fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
+    fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
+    fp4_square(t0, t1, z2, z3);
+    fp4_square(t2, t3, z4, z5);
+    fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
+    fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
+    fp2_mul_xi(t0, t3);
+    fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
+    fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
+    r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+    r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+}
+
+// wire format: 12 x 32 B big-endian in memory order c0.c0.c0, c0.c0.c1, ... (pairings.rs:499-514)
+BN_INL void fp12_to_bytes(uint8_t *out, const fp12 &a) {
+    const fp *x = reinterpret_cast<const fp *>(&a);
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) fp_to_be(out + 32 * i, x[i]);
+}
+BN_INL bool fp12_from_bytes(fp12 &a, const uint8_t *in) {  // pairings.rs:516-579
+    fp *x = reinterpret_cast<fp *>(&a);
+    bool ok = true;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) ok &= fp_from_be(x[i], in + 32 * i);
+    return ok;
+}
+
+}  // namespace bn

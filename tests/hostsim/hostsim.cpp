@@ -1,0 +1,149 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the device headers (bls_bn254_b200/csrc/*.cuh)
+// with g++ so the exact per-item bodies the CUDA kernels run can be unit-tested on a machine without
+// a GPU (carry chains are emulated in C, see fp.cuh).  Never linked into libbls_bn254_b200.so and
+// never reachable from the C ABI: the product has no CPU path.
+#include <cstring>
+
+#include "../../bls_bn254_b200/csrc/items.cuh"
+
+using namespace bn;
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+EXPORT void sim_fp_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    fp x, y, z;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    fp_mul(z, x, y);
+    memcpy(r, z.v, 32);
+}
+EXPORT void sim_fp_add(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    fp x, y, z;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    fp_add(z, x, y);
+    memcpy(r, z.v, 32);
+}
+EXPORT void sim_fp_sub(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    fp x, y, z;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    fp_sub(z, x, y);
+    memcpy(r, z.v, 32);
+}
+// canonical BE in / out
+EXPORT int sim_fp2_sqrt(uint8_t *out, const uint8_t *in) {
+    fp2 a, r;
+    fp_from_be(a.c0, in);
+    fp_from_be(a.c1, in + 32);
+    bool ok = fp2_sqrt(r, a);
+    fp_to_be(out, r.c0);
+    fp_to_be(out + 32, r.c1);
+    return ok;
+}
+EXPORT void sim_hash_to_g1(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count, uint8_t *out,
+                           uint8_t *status) {
+    for (size_t i = 0; i < n; i++) {
+        g1m p;
+        uint8_t fl;
+        item_hash_g1(p, fl, msgs + off[i], off[i + 1] - off[i], dst, (uint32_t)dst_len, count);
+        item_g1_encode(out + 64 * i, p, fl);
+        if (status) status[i] = !(fl & FL_BAD);
+    }
+}
+EXPORT void sim_hash_to_g2(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count, uint8_t *out,
+                           uint8_t *status) {
+    for (size_t i = 0; i < n; i++) {
+        g2m p;
+        uint8_t fl;
+        item_hash_g2(p, fl, msgs + off[i], off[i + 1] - off[i], dst, (uint32_t)dst_len, count);
+        item_g2_encode(out + 128 * i, p, fl);
+        if (status) status[i] = !(fl & FL_BAD);
+    }
+}
+EXPORT void sim_expand_message_xmd(const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, uint8_t *out, size_t n) {
+    uint8_t d2[32];
+    if (dst_len > 255) {
+        oversize_dst(d2, dst, dst_len);
+        dst = d2;
+        dst_len = 32;
+    }
+    expand_message_xmd(out, (uint32_t)n, msg, msg_len, dst, (uint32_t)dst_len);
+}
+// mode 0: pairing, 1: miller loop only
+EXPORT void sim_pairing_batch(const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *out, uint8_t *status, int mode) {
+    for (size_t i = 0; i < n; i++) {
+        g1m p;
+        g2m q;
+        uint8_t flp, flq, fl;
+        fp12 f;
+        item_g1_decode(p, flp, g1 + 64 * i, false);
+        item_g2_decode(q, flq, g2 + 128 * i, false);
+        item_miller1(f, fl, p, flp, q, flq);
+        if (mode == 0) item_final_exp(f);
+        if (fl & FL_BAD) memset(out + 384 * i, 0, 384);
+        else fp12_to_bytes(out + 384 * i, f);
+        if (status) status[i] = !(fl & FL_BAD);
+    }
+}
+EXPORT void sim_final_exp(const uint8_t *in, size_t n, uint8_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        fp12 f;
+        fp12_from_bytes(f, in + 384 * i);
+        item_final_exp(f);
+        fp12_to_bytes(out + 384 * i, f);
+    }
+}
+// 2-pair Miller loop: fixed != 0 -> pair 0 is (p0, -g2) via the line table (q0 ignored)
+EXPORT void sim_miller2(const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, int fixed, uint8_t *out) {
+    g1m a, c;
+    g2m b, d;
+    uint8_t fa, fb = 0, fc, fd, fl;
+    fp12 f;
+    item_g1_decode(a, fa, p0, false);
+    if (!fixed) item_g2_decode(b, fb, q0, false);
+    item_g1_decode(c, fc, p1, false);
+    item_g2_decode(d, fd, q1, false);
+    if (fixed) item_miller2<true>(f, fl, a, fa, nullptr, 0, c, fc, d, fd);
+    else item_miller2<false>(f, fl, a, fa, &b, fb, c, fc, d, fd);
+    fp12_to_bytes(out, f);
+}
+EXPORT void sim_g1_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        g1m p, r;
+        uint8_t fl, flo;
+        item_g1_decode(p, fl, pts + 64 * i, false);
+        item_g1_mul(r, flo, p, fl, sc + 32 * i);
+        item_g1_encode(out + 64 * i, r, flo);
+    }
+}
+EXPORT void sim_g2_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        g2m p, r;
+        uint8_t fl, flo;
+        item_g2_decode(p, fl, pts + 128 * i, false);
+        item_g2_mul(r, flo, p, fl, sc + 32 * i);
+        item_g2_encode(out + 128 * i, r, flo);
+    }
+}
+EXPORT void sim_g1_codec(const uint8_t *pts, size_t n, uint8_t *comp, uint8_t *back, uint8_t *status) {
+    for (size_t i = 0; i < n; i++) {
+        g1m p, r;
+        uint8_t fl, fl2;
+        item_g1_decode(p, fl, pts + 64 * i, false);
+        item_g1_compress(comp + 32 * i, p, fl);
+        item_g1_decompress(r, fl2, comp + 32 * i);
+        item_g1_encode(back + 64 * i, r, fl2);
+        status[i] = !(fl2 & FL_BAD);
+    }
+}
+EXPORT void sim_g2_codec(const uint8_t *pts, size_t n, uint8_t *comp, uint8_t *back, uint8_t *status) {
+    for (size_t i = 0; i < n; i++) {
+        g2m p, r;
+        uint8_t fl, fl2;
+        item_g2_decode(p, fl, pts + 128 * i, false);
+        item_g2_compress(comp + 64 * i, p, fl);
+        item_g2_decompress(r, fl2, comp + 64 * i);
+        item_g2_encode(back + 128 * i, r, fl2);
+        status[i] = !(fl2 & FL_BAD);
+    }
+}
