@@ -1,0 +1,435 @@
+#!/usr/bin/env python3
+"""bench.py -- BLS-BN254 batch verification throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload verify|verify_pk|hash_g1|hash_g2|pairing|aggregate]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...       # the CPU arm: the oracle port on all host cores
+
+A step = one pass of the hot path (hash-to-G1 -> 2-pair Miller loop -> final exponentiation ->
+accept bit) over one batch of 2^16 synthetic (pk, msg, sig) tuples PER GPU (weak scaling: every rank
+owns a disjoint shard, no inter-GPU traffic; `aggregate` adds one 385-byte NCCL all-gather).
+`value` is timed with CUDA events on the library's launch stream with all inputs resident in HBM;
+`e2e` is the same batch through the host-buffer C ABI call (H2D + kernels + D2H inside the timed
+region).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# canonical work per unit in Fp multiplications M; 1 M = 264 INT32 IMAD-ops
+M_IMAD = 264
+WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868}
+KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400}
+UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
+        "aggregate": "verifications/s"}
+METRIC = {"verify": "bls_verifications_per_sec", "verify_pk": "bls_verifications_per_sec", "hash_g1": "hash_to_g1_per_sec",
+          "hash_g2": "hash_to_g2_per_sec", "pairing": "pairings_per_sec", "aggregate": "bls_aggregate_verified_signatures_per_sec"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent sampling (NVML) of SM clock and throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def make_messages(n, first, seed=0xB15B254):
+    import hashlib
+    import struct
+    return [struct.pack("<Q", i) + hashlib.sha256(struct.pack("<QQ", seed, i)).digest()[:24] for i in range(first, first + n)]
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithms on all host cores (the Rust crate cannot be
+    built in this image: no cargo/rustc).  Each step is a bounded sample of the same workload."""
+    import bls_bn254_b200 as b
+    from oracle import orc
+    cores = orc.ncpu()
+    n = args.ref_sample
+    w = args.workload
+    # inputs: made with the oracle itself (untimed)
+    msgs = make_messages(n, 0)
+    sks = [b.scheme.scalar_from_seed(b.scheme.SEED, i % 64) for i in range(n)]
+    sc = b"".join(s.to_bytes(32, "big") for s in sks)
+    if w in ("verify", "aggregate"):
+        upk = orc.g2_mul(orc.g2_generator() * 64, sc[:64 * 32], nthreads=cores)
+        pks = b"".join(upk[(i % 64) * 128:(i % 64 + 1) * 128] for i in range(n))
+        sigs = orc.g1_mul(orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores), sc, nthreads=cores)
+        agg = orc.g1_sum(sigs)
+    elif w == "verify_pk":
+        upk = orc.g1_mul(orc.g1_generator() * 64, sc[:64 * 32], nthreads=cores)
+        pks = b"".join(upk[(i % 64) * 64:(i % 64 + 1) * 64] for i in range(n))
+        sigs = orc.g2_mul(orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores), sc, nthreads=cores)
+    elif w == "pairing":
+        g1 = orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores)
+        g2 = orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores)
+
+    def step():
+        if w == "verify":
+            ok = orc.verify_batch(0, pks, msgs, sigs, b.DST_MIN_SIG, nthreads=cores)
+            assert sum(ok) == n
+        elif w == "verify_pk":
+            ok = orc.verify_batch(1, pks, msgs, sigs, b.DST_MIN_PK, nthreads=cores)
+            assert sum(ok) == n
+        elif w == "hash_g1":
+            orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores)
+        elif w == "hash_g2":
+            orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores)
+        elif w == "pairing":
+            orc.pairing_batch(g1, g2, nthreads=cores)
+        else:
+            assert orc.aggregate_verify(0, pks, msgs, agg, b.DST_MIN_SIG, nthreads=cores) == 1
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = "%d-tuple sample of the %s workload per step, oracle C port (4x64-bit Montgomery), %d threads" % (n, w, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC[w], "value": v, "unit": UNIT[w], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(w, args),
+        "cpu_baseline": {"value": v, "unit": UNIT[w], "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT[w], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(w, args):
+    names = {
+        "verify": "batch verify 2^%d independent (pk, msg, sig) tuples per GPU, min-sig (pk in G2, sig in G1), distinct 32-byte messages",
+        "verify_pk": "batch verify 2^%d independent tuples per GPU, min-pk (pk in G1, sig in G2), distinct 32-byte messages",
+        "hash_g1": "hash_to_curve: 2^%d 32-byte messages per GPU to G1 (expand_message_xmd SHA-256 + SvdW)",
+        "hash_g2": "hash_to_curve: 2^%d 32-byte messages per GPU to G2 (expand_message_xmd SHA-256 + SvdW + cofactor clearing)",
+        "pairing": "2^%d pairings per GPU (Miller loop + final exponentiation), distinct random G1/G2 points",
+        "aggregate": "aggregate verify: 2^%d signatures on distinct messages per GPU, one multi-Miller product + single final exponentiation",
+    }
+    return {"workload": names[w] % args.log2n, "tuples_per_gpu": 1 << args.log2n, "variant": "min-pk" if w == "verify_pk" else "min-sig",
+            "msg_bytes": 32, "corrupted_fraction": "1/64" if w.startswith("verify") else "0",
+            "l2": "L2 flushed between timed steps (256 MiB write)", "sharding": "independent tuples by index, no data-path collective"
+            if w != "aggregate" else "pairs by index; one 385-byte all-gather of Fp12 partials"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="verify", choices=sorted(WORK_M))
+    ap.add_argument("--log2n", type=int, default=16, help="log2 of tuples per GPU per step")
+    ap.add_argument("--ref-sample", type=int, default=4096, help="tuples per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="tuples of the cpu_baseline leg (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bls_bn254_b200 as b
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bls_bn254_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = args.workload
+    variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
+    n = 1 << args.log2n
+    ctx = b.Context([local_rank])
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+
+    # ---- synthetic inputs (generated on the GPU, untimed) --------------------------------------
+    first = rank * n
+    dst = b.DST_MIN_PK if w in ("verify_pk", "hash_g2") else b.DST_MIN_SIG
+    pks = sigs = agg = g1 = g2 = None
+    expected = None
+    if w in ("verify", "verify_pk"):
+        pks, msgs, sigs, expected = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096))
+    elif w == "aggregate":
+        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096), corrupt_every=0)
+        agg_local = b.scheme.aggregate(ctx, sigs, variant)
+    else:
+        msgs = make_messages(n, first)
+        if w == "pairing":
+            g1 = ctx.hash_to_g1(msgs, b.DST_MIN_SIG)
+            g2 = ctx.hash_to_g2(msgs, b.DST_MIN_PK)
+    blob, off = b.pack_msgs(msgs)
+
+    def dev_bytes(x):
+        return torch.frombuffer(bytearray(x), dtype=torch.uint8).to(dev)
+
+    d_blob = dev_bytes(blob if blob else b"\0")
+    d_off = torch.tensor(list(off), dtype=torch.int64, device=dev)
+    d_dst = dev_bytes(dst)
+    d_pks = dev_bytes(pks) if pks else None
+    d_sigs = dev_bytes(sigs) if sigs else None
+    d_g1 = dev_bytes(g1) if g1 else None
+    d_g2 = dev_bytes(g2) if g2 else None
+    out_rec = {"verify": 1, "verify_pk": 1, "hash_g1": 64, "hash_g2": 128, "pairing": 384, "aggregate": 385}[w]
+    d_out = torch.zeros(n * out_rec if w != "aggregate" else 385, dtype=torch.uint8, device=dev)
+    d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    if w == "aggregate":
+        # the aggregate signature of the WHOLE job (all ranks): sum of the per-rank sums, given to rank 0
+        if world > 1:
+            t = dev_bytes(agg_local)
+            allp = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allp, t)
+            agg = ctx.g1_sum(b"".join(bytes(x.cpu().numpy()) for x in allp))
+        else:
+            agg = agg_local
+        d_agg = dev_bytes(agg) if rank == 0 else None
+        gather_buf = [torch.zeros(385, dtype=torch.uint8, device=dev) for _ in range(world)]
+
+    verdict = {}
+
+    def step_dev():
+        """device-resident pass: everything is enqueued on the library stream"""
+        if w in ("verify", "verify_pk"):
+            ctx.verify_batch_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(),
+                                 len(dst), 0, d_out.data_ptr())
+        elif w == "hash_g1":
+            ctx.hash_to_g1_dev(d_blob.data_ptr(), d_off.data_ptr(), n, d_dst.data_ptr(), len(dst), 2, d_out.data_ptr(), d_status.data_ptr())
+        elif w == "hash_g2":
+            ctx.hash_to_g2_dev(d_blob.data_ptr(), d_off.data_ptr(), n, d_dst.data_ptr(), len(dst), 2, d_out.data_ptr(), d_status.data_ptr())
+        elif w == "pairing":
+            ctx.pairing_dev(d_g1.data_ptr(), d_g2.data_ptr(), n, d_out.data_ptr(), d_status.data_ptr())
+        else:
+            ctx.aggregate_partial_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), n, d_agg.data_ptr() if rank == 0 else None,
+                                      d_dst.data_ptr(), len(dst), 0, d_out.data_ptr(), d_out.data_ptr() + 384)
+            if world > 1:
+                # the path's one exchange step: 385 bytes per rank over NCCL (NVLink / NVSwitch)
+                torch.cuda.current_stream().wait_stream(stream)
+                dist.all_gather(gather_buf, d_out)
+                stream.wait_stream(torch.cuda.current_stream())
+                parts = torch.stack(gather_buf).cpu().numpy()
+            else:
+                ctx.sync()
+                parts = d_out.cpu().numpy().reshape(1, 385)
+            if rank == 0:
+                verdict["ok"] = ctx.aggregate_finish(b"".join(bytes(p[:384]) for p in parts), [int(p[384]) for p in parts])
+
+    def step_e2e():
+        """the call a user makes: host buffers in, host result out"""
+        if w in ("verify", "verify_pk"):
+            return ctx.verify_batch(variant, pks, (blob, off), sigs, dst)
+        if w == "hash_g1":
+            return ctx.hash_to_g1((blob, off), dst)
+        if w == "hash_g2":
+            return ctx.hash_to_g2((blob, off), dst)
+        if w == "pairing":
+            return ctx.pairing(g1, g2)
+        part, bad = ctx.aggregate_partial(variant, pks, (blob, off), agg if rank == 0 else None, dst)
+        if world > 1:
+            t = dev_bytes(part + bytes([bad]))
+            dist.all_gather(gather_buf, t)
+            parts = torch.stack(gather_buf).cpu().numpy()
+        else:
+            parts = [list(part) + [bad]]
+        if rank == 0:
+            return ctx.aggregate_finish(b"".join(bytes(bytearray(p[:384])) for p in parts), [int(p[384]) for p in parts])
+        return None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- roofline denominator: INT32 multiply-add peak, measured live --------------------------
+    peaks = {}
+    if rank == 0:
+        for mode, name in ((0, "mad.lo"), (1, "mad.lo+mad.hi"), (2, "imad.wide")):
+            peaks[name] = max(ctx.imad_peak(mode, 20000)[0] for _ in range(2))
+
+    # ---- warm-up ------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        step_dev()
+        ctx.sync()
+    if args.warmup:
+        got = step_e2e()
+        if expected is not None:
+            assert got == expected, "accept bits differ from the construction"
+            assert bytes(d_out.cpu().numpy()) == expected, "device-resident accept bits differ from the construction"
+        if w == "aggregate" and rank == 0:
+            assert got == 1 and verdict.get("ok") == 1, "aggregate verification rejected a valid aggregate"
+
+    # ---- timed region: EXACTLY K steps, CUDA events on the launch stream, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    ctx.profile(True)
+    ctx.profile_drain()
+    launches0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    host_ms = 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev[k][0].record(stream)
+        step_dev()
+        ev[k][1].record(stream)
+        ev[k][1].synchronize()
+        host_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.result()
+    launches = ctx.launch_count - launches0
+    prof = ctx.profile_drain()
+    ctx.profile(False)
+    dev_ms = sum(a.elapsed_time(bb) for a, bb in ev)
+    if w == "aggregate":
+        dev_ms = host_ms  # the exchange + finish run outside the library stream: wall time of the step
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public call, copies inside the timed region --------------
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    in_bytes = {"verify": len(blob) + 8 * (n + 1) + n * 192 + len(dst), "verify_pk": len(blob) + 8 * (n + 1) + n * 192 + len(dst),
+                "hash_g1": len(blob) + 8 * (n + 1) + len(dst), "hash_g2": len(blob) + 8 * (n + 1) + len(dst), "pairing": n * 192,
+                "aggregate": len(blob) + 8 * (n + 1) + n * 128 + 64 + len(dst)}[w]
+    out_bytes = {"verify": n, "verify_pk": n, "hash_g1": n * 65, "hash_g2": n * 129, "pairing": n * 385, "aggregate": 385 + 1}[w]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region) ---------
+    agg_t = {}
+    for name, items, ms in prof:
+        a = agg_t.setdefault(name, [0, 0.0, 0])
+        a[0] += 1
+        a[1] += ms
+        a[2] = items
+    kern_ms_total = sum(a[1] for a in agg_t.values())
+    top = max(agg_t.items(), key=lambda kv: kv[1][1])
+    top_name, (top_cnt, top_ms, top_items) = top[0], top[1]
+    peak_name = max(peaks, key=peaks.get)
+    peak = peaks[peak_name]
+    top_ops = KERNEL_M.get(top_name, 0) * M_IMAD * top_items
+    achieved = top_ops / (top_ms / top_cnt * 1e-3) if top_ms else 0.0
+    whole_ops = WORK_M[w] * M_IMAD * n * args.steps
+    roofline = {
+        "bound": "int32_imad", "kernel": top_name, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TIMAD-op/s", "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": "measured live by bn254_imad_peak (%s chains, all SMs); MEASURED_PEAKS.json has no INT32 figure" % peak_name,
+        "peaks_measured_tops": {k: v / 1e12 for k, v in peaks.items()},
+        "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
+        "whole_step_frac": whole_ops / (dev_ms * 1e-3) / peak,
+        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(agg_t.items(), key=lambda kv: -kv[1][1])},
+        "hbm": {"algorithmic_bytes_per_step": in_bytes + out_bytes, "achieved_gbs": (in_bytes + out_bytes) / (dev_ms / args.steps * 1e-3) / 1e9,
+                "peak_gbs": 6553.3, "note": "HBM non-binding"},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the box's host cores ----------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import orc
+        cores = orc.ncpu()
+        m = min(n, args.cpu_sample)
+        t0 = time.perf_counter()
+        if w in ("verify", "verify_pk"):
+            rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+            ref = orc.verify_batch(variant, pks[:m * rpk], msgs[:m], sigs[:m * rsig], dst, nthreads=cores)
+            assert ref == expected[:m], "oracle and construction disagree"
+        elif w == "hash_g1":
+            ref = orc.hash_to_g1(msgs[:m], dst, nthreads=cores)
+            assert ref == bytes(d_out[:64 * m].cpu().numpy()), "hash_to_g1 differs from the oracle"
+        elif w == "hash_g2":
+            m = min(m, 4096)
+            ref = orc.hash_to_g2(msgs[:m], dst, nthreads=cores)
+            assert ref == bytes(d_out[:128 * m].cpu().numpy()), "hash_to_g2 differs from the oracle"
+        elif w == "pairing":
+            ref = orc.pairing_batch(g1[:64 * m], g2[:128 * m], nthreads=cores)
+            assert ref == bytes(d_out[:384 * m].cpu().numpy()), "pairing differs from the oracle"
+        else:
+            assert orc.aggregate_verify(0, pks[:m * 128], msgs[:m], orc.g1_sum(sigs[:m * 64]), dst, nthreads=cores) == 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": m / dt, "unit": UNIT[w], "cores": cores, "kind": "port",
+               "sample": "first %d tuples of the same batch, oracle C port (4x64-bit Montgomery) on %d threads, %.1f s; results compared" % (m, cores, dt)}
+
+    line = {
+        "metric": METRIC[w], "value": value, "unit": UNIT[w], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": workload_config(w, args),
+        "e2e": {"value": n * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT[w], "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "pairings_per_sec": value * (2 if w.startswith("verify") else 1) if w in ("verify", "verify_pk", "pairing", "aggregate") else None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

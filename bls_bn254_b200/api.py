@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference crate's `inner_types` API, in batch form, over the C ABI.
+
+Reference function  ->  here (all byte formats are the reference's own, see include/bls_bn254_b200.h)
+  G1Projective::hash / ::encode (g1.rs:910-928)            Context.hash_to_g1 / encode_to_g1
+  G2Projective::hash / ::encode (g2.rs:919-936)            Context.hash_to_g2 / encode_to_g2
+  pairing (pairings.rs:760-802) + Gt::to_repr              Context.pairing
+  multi_miller_loop (pairings.rs:808-857)                  Context.multi_miller_loop
+  MillerLoopResult::final_exponentiation (50-178)          Context.final_exponentiation
+  MillerLoopResult + MillerLoopResult (37-43)              Context.fp12_product
+  to_compressed / from_compressed (g1.rs:283-328, g2.rs)   Context.g1_compress / g1_decompress / g2_...
+  G1Projective * Scalar (g1.rs:821-841, g2.rs:866-886)     Context.g1_mul / g2_mul
+  verify / aggregate_verify (absent upstream) Context.verify_batch / aggregate_verify
+Errors: malformed call-level input raises Bn254Error (error.rs:5-10); per-item problems come back
+as status bytes, never as exceptions.
+"""
+import ctypes as C
+
+from . import _native
+
+MIN_SIG, MIN_PK = 0, 1
+CHECK_ON_CURVE = 1
+
+
+class Bn254Error(Exception):
+    """error.rs:5-10 (InvalidScalarBytes / InvalidG1Bytes / InvalidG2Bytes / InvalidGtBytes) + CUDA errors."""
+    NAMES = {-1: "InvalidScalarBytes", -2: "InvalidG1Bytes", -3: "InvalidG2Bytes", -4: "InvalidGtBytes", -10: "BadArgument", -20: "NoCudaDevice"}
+
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__("%s (%d)%s" % (self.NAMES.get(code, "CudaError"), code, (": " + msg) if msg else ""))
+
+
+def pack_msgs(msgs):
+    """list[bytes] -> (blob, (n+1) x u64 offsets)"""
+    off = (C.c_uint64 * (len(msgs) + 1))()
+    pos = 0
+    for i, m in enumerate(msgs):
+        off[i] = pos
+        pos += len(m)
+    off[len(msgs)] = pos
+    return b"".join(msgs), off
+
+
+def _ptr(x):
+    """bytes / bytearray / ctypes buffer / numpy array / int address / None -> void*"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)) if isinstance(x, bytearray) else C.c_char_p(x), C.c_void_p)
+    if hasattr(x, "ctypes"):  # numpy
+        return C.c_void_p(x.ctypes.data)
+    return C.cast(x, C.c_void_p)
+
+
+class Context:
+    """bn254_ctx: owns streams and device scratch on one or more GPUs of this process."""
+
+    def __init__(self, devices=None):
+        self._L = _native.lib()
+        if devices is None:
+            devices = [0]
+        if isinstance(devices, int):
+            devices = [devices]
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._L.bn254_ctx_create(C.byref(h), arr, len(devices))
+        if rc:
+            raise Bn254Error(rc, "bn254_ctx_create failed (no CUDA device? this library has no CPU fallback)")
+        self._h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bn254_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise Bn254Error(rc, (self._L.bn254_last_error(self._h) or b"").decode())
+
+    @property
+    def launch_count(self):
+        return int(self._L.bn254_launch_count(self._h))
+
+    @property
+    def stream_ptr(self):
+        return int(self._L.bn254_stream(self._h) or 0)
+
+    def sync(self):
+        self._ck(self._L.bn254_sync(self._h))
+
+    def profile(self, on=True):
+        self._ck(self._L.bn254_profile_enable(self._h, 1 if on else 0))
+
+    def profile_drain(self):
+        """[(kernel name, items, milliseconds)] for every launch since the last drain (first device)."""
+        buf = C.create_string_buffer(1 << 20)
+        self._ck(self._L.bn254_profile_drain(self._h, _ptr(buf), len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, items, ms = line.split()
+            out.append((name, int(items), float(ms)))
+        return out
+
+    # ---- hash to curve ------------------------------------------------------------------------
+    def _hash(self, fn, rec, msgs, dst, want_status):
+        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+        n = len(off) - 1
+        out, st = C.create_string_buffer(rec * n), C.create_string_buffer(n)
+        self._ck(fn(self._h, _ptr(blob), _ptr(off), n, _ptr(dst), len(dst), _ptr(out), _ptr(st)))
+        return (out.raw, st.raw) if want_status else out.raw
+
+    def hash_to_g1(self, msgs, dst, want_status=False):
+        return self._hash(self._L.bn254_hash_to_g1, 64, msgs, dst, want_status)
+
+    def encode_to_g1(self, msgs, dst, want_status=False):
+        return self._hash(self._L.bn254_encode_to_g1, 64, msgs, dst, want_status)
+
+    def hash_to_g2(self, msgs, dst, want_status=False):
+        return self._hash(self._L.bn254_hash_to_g2, 128, msgs, dst, want_status)
+
+    def encode_to_g2(self, msgs, dst, want_status=False):
+        return self._hash(self._L.bn254_encode_to_g2, 128, msgs, dst, want_status)
+
+    # ---- pairing engine -----------------------------------------------------------------------
+    def pairing(self, g1, g2, want_status=False):
+        n = len(g1) // 64
+        if len(g1) != 64 * n or len(g2) != 128 * n:
+            raise Bn254Error(-2 if len(g1) != 64 * n else -3, "length mismatch")
+        out, st = C.create_string_buffer(384 * n), C.create_string_buffer(n)
+        self._ck(self._L.bn254_pairing_batch(self._h, _ptr(g1), _ptr(g2), n, _ptr(out), _ptr(st)))
+        return (out.raw, st.raw) if want_status else out.raw
+
+    def miller_loop(self, g1, g2, want_status=False):
+        n = len(g1) // 64
+        if len(g1) != 64 * n or len(g2) != 128 * n:
+            raise Bn254Error(-2 if len(g1) != 64 * n else -3, "length mismatch")
+        out, st = C.create_string_buffer(384 * n), C.create_string_buffer(n)
+        self._ck(self._L.bn254_miller_loop_batch(self._h, _ptr(g1), _ptr(g2), n, _ptr(out), _ptr(st)))
+        return (out.raw, st.raw) if want_status else out.raw
+
+    def multi_miller_loop(self, g1, g2):
+        n = len(g1) // 64
+        if len(g1) != 64 * n or len(g2) != 128 * n:
+            raise Bn254Error(-2 if len(g1) != 64 * n else -3, "length mismatch")
+        out = C.create_string_buffer(384)
+        self._ck(self._L.bn254_multi_miller_loop(self._h, _ptr(g1), _ptr(g2), n, _ptr(out)))
+        return out.raw
+
+    def final_exponentiation(self, ml, want_status=False):
+        n = len(ml) // 384
+        if len(ml) != 384 * n:
+            raise Bn254Error(-4, "length mismatch")
+        out, st = C.create_string_buffer(384 * n), C.create_string_buffer(n)
+        self._ck(self._L.bn254_final_exponentiation(self._h, _ptr(ml), n, _ptr(out), _ptr(st)))
+        return (out.raw, st.raw) if want_status else out.raw
+
+    def fp12_product(self, elems):
+        n = len(elems) // 384
+        if len(elems) != 384 * n:
+            raise Bn254Error(-4, "length mismatch")
+        out = C.create_string_buffer(384)
+        self._ck(self._L.bn254_fp12_product(self._h, _ptr(elems), n, _ptr(out)))
+        return out.raw
+
+    # ---- BLS predicates -----------------------------------------------------------------------
+    @staticmethod
+    def _recs(variant):
+        return (128, 64) if variant == MIN_SIG else (64, 128)
+
+    def verify_batch(self, variant, pks, msgs, sigs, dst, flags=0):
+        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+        n = len(off) - 1
+        rpk, rsig = self._recs(variant)
+        if len(pks) != rpk * n:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if len(sigs) != rsig * n:
+            raise Bn254Error(-2 if variant == MIN_SIG else -3, "signature buffer length")
+        ok = C.create_string_buffer(n)
+        self._ck(self._L.bn254_verify_batch(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags, _ptr(ok)))
+        return ok.raw
+
+    def aggregate_verify(self, variant, pks, msgs, agg_sig, dst, flags=0):
+        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+        n = len(off) - 1
+        rpk, rsig = self._recs(variant)
+        if len(pks) != rpk * n:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if len(agg_sig) != rsig:
+            raise Bn254Error(-2 if variant == MIN_SIG else -3, "signature length")
+        ok = C.create_string_buffer(1)
+        self._ck(self._L.bn254_aggregate_verify(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), n, _ptr(agg_sig), _ptr(dst), len(dst), flags, _ptr(ok)))
+        return ok.raw[0]
+
+    def aggregate_partial(self, variant, pks, msgs, agg_sig, dst, flags=0):
+        """One shard: (384-byte Fp12 partial product, bad flag).  agg_sig only on one shard."""
+        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+        n = len(off) - 1
+        part, bad = C.create_string_buffer(384), C.create_string_buffer(1)
+        self._ck(self._L.bn254_aggregate_partial(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), n, _ptr(agg_sig), _ptr(dst), len(dst), flags,
+                                                 _ptr(part), _ptr(bad)))
+        return part.raw, bad.raw[0]
+
+    def aggregate_finish(self, partials, bads):
+        k = len(partials) // 384
+        ok = C.create_string_buffer(1)
+        self._ck(self._L.bn254_aggregate_finish(self._h, _ptr(partials), _ptr(bytes(bads)), k, _ptr(ok)))
+        return ok.raw[0]
+
+    # ---- codecs, predicates, scalar multiplication ------------------------------------------------
+    def _map(self, fn, data, rin, rout, status=False, extra=None):
+        n = len(data) // rin
+        if len(data) != rin * n:
+            raise Bn254Error(-2, "length mismatch")
+        out = C.create_string_buffer(max(1, rout * n))
+        if extra is not None:
+            self._ck(fn(self._h, _ptr(data), _ptr(extra), n, _ptr(out)))
+            return out.raw[:rout * n]
+        if status:
+            st = C.create_string_buffer(max(1, n))
+            self._ck(fn(self._h, _ptr(data), n, _ptr(out), _ptr(st)))
+            return out.raw[:rout * n], st.raw[:n]
+        self._ck(fn(self._h, _ptr(data), n, _ptr(out)))
+        return out.raw[:rout * n]
+
+    def g1_compress(self, pts): return self._map(self._L.bn254_g1_compress, pts, 64, 32)
+    def g2_compress(self, pts): return self._map(self._L.bn254_g2_compress, pts, 128, 64)
+    def g1_decompress(self, comp): return self._map(self._L.bn254_g1_decompress, comp, 32, 64, status=True)
+    def g2_decompress(self, comp): return self._map(self._L.bn254_g2_decompress, comp, 64, 128, status=True)
+    def g1_is_on_curve(self, pts): return self._map(self._L.bn254_g1_is_on_curve, pts, 64, 1)
+    def g2_is_on_curve(self, pts): return self._map(self._L.bn254_g2_is_on_curve, pts, 128, 1)
+    def g1_mul(self, pts, scalars): return self._map(self._L.bn254_g1_mul, pts, 64, 64, extra=scalars)
+    def g2_mul(self, pts, scalars): return self._map(self._L.bn254_g2_mul, pts, 128, 128, extra=scalars)
+
+    def g1_sum(self, pts):
+        out = C.create_string_buffer(64)
+        self._ck(self._L.bn254_g1_sum(self._h, _ptr(pts), len(pts) // 64, _ptr(out)))
+        return out.raw
+
+    def g2_sum(self, pts):
+        out = C.create_string_buffer(128)
+        self._ck(self._L.bn254_g2_sum(self._h, _ptr(pts), len(pts) // 128, _ptr(out)))
+        return out.raw
+
+    # ---- device-resident entry points (raw device addresses, e.g. torch.Tensor.data_ptr()) ---------
+    def hash_to_g1_dev(self, msgs, offsets, n, dst, dst_len, count, out, status=None):
+        self._ck(self._L.bn254_hash_to_g1_dev(self._h, msgs, offsets, n, dst, dst_len, count, out, status))
+
+    def hash_to_g2_dev(self, msgs, offsets, n, dst, dst_len, count, out, status=None):
+        self._ck(self._L.bn254_hash_to_g2_dev(self._h, msgs, offsets, n, dst, dst_len, count, out, status))
+
+    def pairing_dev(self, g1, g2, n, gt, status=None):
+        self._ck(self._L.bn254_pairing_batch_dev(self._h, g1, g2, n, gt, status))
+
+    def verify_batch_dev(self, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, ok):
+        self._ck(self._L.bn254_verify_batch_dev(self._h, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, ok))
+
+    def aggregate_partial_dev(self, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad):
+        self._ck(self._L.bn254_aggregate_partial_dev(self._h, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad))
+
+    def imad_peak(self, mode=2, iters=4096):
+        """(IMAD-ops/s, ms); mode 0 mad.lo, 1 mad.lo+mad.hi, 2 IMAD.WIDE (2 ops each)."""
+        ops, ms = C.c_double(), C.c_double()
+        self._ck(self._L.bn254_imad_peak(self._h, int(mode), iters, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+
+# G1 / G2 generators in wire form (g1.rs:274-280; fp2.rs:305-348)
+G1_GENERATOR = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+G2_GENERATOR = bytes.fromhex(
+    "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2"
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"
+    "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"
+    "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa")
+DST_MIN_SIG = b"BLS_SIG_BN254G1_XMD:SHA-256_SVDW_RO_NUL_"
+DST_MIN_PK = b"BLS_SIG_BN254G2_XMD:SHA-256_SVDW_RO_NUL_"
+R_ORDER = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001

@@ -1,0 +1,1012 @@
+// capi.cu -- the C ABI of libbls_bn254_b200.so (include/bls_bn254_b200.h): context, scratch
+// memory, chunked host<->device staging, sharding over the ctx's devices, kernel launches.
+// There is no CPU path: without a CUDA device bn254_ctx_create fails with BN254_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bls_bn254_b200.h"
+#include "kernels.cuh"
+
+using namespace bn;
+
+namespace {
+
+enum Scratch {
+    S_IN_A, S_IN_B, S_IN_C, S_MSGS, S_OFF, S_DST, S_OUT, S_STATUS,
+    S_P0, S_FLP0, S_P1, S_FLP1, S_Q0, S_FLQ0, S_Q1, S_FLQ1, S_F, S_FLF, S_F2, S_BAD, S_TMP, S_FLTMP, S_CONST,
+    S_COUNT
+};
+
+struct Buf { void *p = nullptr; size_t cap = 0; };
+
+struct ProfRec { const char *name; size_t items; cudaEvent_t e0, e1; };
+
+struct Dev {
+    int id = 0;
+    cudaStream_t st = nullptr;
+    Buf bufs[S_COUNT];
+    uint64_t launches = 0;
+    std::string err;
+    int rc = 0;
+    bool prof = false;            // record a CUDA event pair around every kernel launch
+    std::vector<ProfRec> recs;
+};
+
+}  // namespace
+
+struct bn254_ctx {
+    std::vector<Dev> devs;
+    std::string err;
+    size_t chunk = (size_t)1 << 18;  // items staged per host<->device round
+};
+
+namespace {
+
+#define CK(d, call)                                                                                                 \
+    do {                                                                                                            \
+        cudaError_t e_ = (call);                                                                                    \
+        if (e_ != cudaSuccess) {                                                                                    \
+            (d).err = std::string(#call) + ": " + cudaGetErrorString(e_);                                          \
+            (d).rc = BN254_ERR_CUDA_BASE - (int)e_;                                                                 \
+            return (d).rc;                                                                                          \
+        }                                                                                                           \
+    } while (0)
+
+int ensure(Dev &d, Scratch s, size_t bytes, void **out) {
+    Buf &b = d.bufs[s];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            CK(d, cudaStreamSynchronize(d.st));
+            CK(d, cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = bytes + bytes / 8 + 256;
+        CK(d, cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return 0;
+}
+template <class T>
+int ensure_t(Dev &d, Scratch s, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = ensure(d, s, count * sizeof(T), &p);
+    *out = (T *)p;
+    return rc;
+}
+
+inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+#define LAUNCH(d, kern, n, tpb, ...)                                             \
+    do {                                                                         \
+        if ((n) > 0) {                                                           \
+            ProfRec pr_ = {#kern, (size_t)(n), nullptr, nullptr};                \
+            if ((d).prof) {                                                      \
+                CK(d, cudaEventCreate(&pr_.e0));                                 \
+                CK(d, cudaEventCreate(&pr_.e1));                                 \
+                CK(d, cudaEventRecord(pr_.e0, (d).st));                          \
+            }                                                                    \
+            kern<<<blocks((n), (tpb)), (tpb), 0, (d).st>>>(__VA_ARGS__);         \
+            (d).launches++;                                                      \
+            if ((d).prof) {                                                      \
+                CK(d, cudaEventRecord(pr_.e1, (d).st));                          \
+                (d).recs.push_back(pr_);                                         \
+            }                                                                    \
+            CK(d, cudaGetLastError());                                           \
+        }                                                                        \
+    } while (0)
+
+// ---- device-level building blocks (all pointers are device pointers on d) ------------------------
+
+// DST: copies / pre-hashes into scratch when needed.  `dst_on_host` tells where dst lives.
+int stage_dst(Dev &d, const uint8_t *dst, size_t dst_len, bool dst_on_host, const uint8_t **d_dst, uint32_t *d_len) {
+    uint8_t *buf;
+    if (int rc = ensure_t(d, S_DST, dst_len + 64, &buf)) return rc;
+    const uint8_t *src = dst;
+    if (dst_on_host) {
+        if (dst_len) CK(d, cudaMemcpyAsync(buf + 32, dst, dst_len, cudaMemcpyHostToDevice, d.st));
+        src = buf + 32;
+    }
+    if (dst_len > 255) {  // RFC 9380 5.3.3
+        LAUNCH(d, k_oversize_dst, 1, 32, buf, src, dst_len);
+        *d_dst = buf;
+        *d_len = 32;
+    } else {
+        *d_dst = src;
+        *d_len = (uint32_t)dst_len;
+    }
+    return 0;
+}
+
+int dev_hash_g1(Dev &d, g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n, const uint8_t *dst,
+                uint32_t dst_len, int count) {
+    LAUNCH(d, k_hash_g1, n, BN_TPB_HEAVY, out, fl, msgs, off, base, n, dst, dst_len, count);
+    return 0;
+}
+int dev_hash_g2(Dev &d, g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n, const uint8_t *dst,
+                uint32_t dst_len, int count) {
+    LAUNCH(d, k_hash_g2, n, BN_TPB_HEAVY, out, fl, msgs, off, base, n, dst, dst_len, count);
+    return 0;
+}
+
+// hash / encode to wire bytes
+int dev_hash_wire(Dev &d, int group, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n, const uint8_t *dst,
+                  uint32_t dst_len, int count, uint8_t *out, uint8_t *status) {
+    uint8_t *fl;
+    if (int rc = ensure_t(d, S_FLP1, n, &fl)) return rc;
+    if (group == 1) {
+        g1m *P;
+        if (int rc = ensure_t(d, S_P1, n, &P)) return rc;
+        if (int rc = dev_hash_g1(d, P, fl, msgs, off, base, n, dst, dst_len, count)) return rc;
+        LAUNCH(d, k_g1_encode, n, BN_TPB_LIGHT, out, status, P, fl, n);
+    } else {
+        g2m *Q;
+        if (int rc = ensure_t(d, S_Q1, n, &Q)) return rc;
+        if (int rc = dev_hash_g2(d, Q, fl, msgs, off, base, n, dst, dst_len, count)) return rc;
+        LAUNCH(d, k_g2_encode, n, BN_TPB_LIGHT, out, status, Q, fl, n);
+    }
+    return 0;
+}
+
+// mode 0: pairing, 1: Miller loop only
+int dev_pairing(Dev &d, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *out, uint8_t *status, int mode) {
+    g1m *P; g2m *Q; uint8_t *flp, *flq, *flf; fp12 *F;
+    if (int rc = ensure_t(d, S_P0, n, &P)) return rc;
+    if (int rc = ensure_t(d, S_Q0, n, &Q)) return rc;
+    if (int rc = ensure_t(d, S_FLP0, n, &flp)) return rc;
+    if (int rc = ensure_t(d, S_FLQ0, n, &flq)) return rc;
+    if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
+    if (int rc = ensure_t(d, S_F, n, &F)) return rc;
+    LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, g1, n, 0);
+    LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, g2, n, 0);
+    LAUNCH(d, k_miller1, n, BN_TPB_HEAVY, F, flf, P, flp, Q, flq, n, (int *)nullptr);
+    if (mode == 0) LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
+    return 0;
+}
+
+int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *status) {
+    fp12 *F; uint8_t *flf;
+    if (int rc = ensure_t(d, S_F, n, &F)) return rc;
+    if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
+    LAUNCH(d, k_fp12_decode, n, BN_TPB_LIGHT, F, flf, ml, n);
+    LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
+    return 0;
+}
+
+// product of n Fp12 records (internal form) -> *result points at one record in scratch
+int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result) {
+    fp12 *A, *B;
+    size_t m0 = std::max<size_t>(1, (n + 15) / 16);
+    if (int rc = ensure_t(d, S_F2, m0 + (m0 + 15) / 16 + 2, &A)) return rc;
+    B = A + m0;
+    const fp12 *src = F;
+    size_t cur = n;
+    fp12 *dstp = A;
+    while (true) {
+        size_t m = std::max<size_t>(1, (cur + 15) / 16);
+        LAUNCH(d, k_fp12_reduce, m, BN_TPB_HEAVY, dstp, src, cur, m);
+        if (m == 1) break;
+        src = dstp;
+        cur = m;
+        dstp = (dstp == A) ? B : A;
+    }
+    *result = dstp;
+    return 0;
+}
+
+const g1m *neg_g1_const(Dev &d, const uint8_t **fl) {
+    // -g1 = (1, -2) in Montgomery form + a zero flag byte, uploaded once per device
+    Buf &b = d.bufs[S_CONST];
+    if (!b.p) {
+        struct { g1m p; uint8_t fl[16]; } h;
+        memset(&h, 0, sizeof h);
+        const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        memcpy(h.p.x.v, one, 32);
+        cudaMemcpyFromSymbol(h.p.y.v, k::NEG_TWO, 32);
+        void *p = nullptr;
+        if (ensure(d, S_CONST, sizeof h, &p)) return nullptr;
+        cudaMemcpy(p, &h, sizeof h, cudaMemcpyHostToDevice);
+    }
+    *fl = (const uint8_t *)b.p + sizeof(g1m);
+    return (const g1m *)b.p;
+}
+
+// verification of one chunk, device pointers in / out
+int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
+               size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+    int check = (flags & BN254_FLAG_CHECK_ON_CURVE) ? 1 : 0;
+    fp12 *F; uint8_t *flf;
+    if (int rc = ensure_t(d, S_F, n, &F)) return rc;
+    if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
+    if (variant == BN254_MIN_SIG) {
+        g1m *P0, *P1; g2m *Q1; uint8_t *flp0, *flp1, *flq1;
+        if (int rc = ensure_t(d, S_P0, n, &P0)) return rc;
+        if (int rc = ensure_t(d, S_P1, n, &P1)) return rc;
+        if (int rc = ensure_t(d, S_Q1, n, &Q1)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, n, &flp0)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, n, &flp1)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, n, &flq1)) return rc;
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flp0, sigs, n, check);
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q1, flq1, pks, n, check);
+        if (int rc = dev_hash_g1(d, P1, flp1, msgs, off, base, n, dst, dst_len, 2)) return rc;
+        LAUNCH(d, k_miller2_fixed, n, BN_TPB_HEAVY, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
+    } else {
+        g1m *P1; g2m *Q0, *Q1; uint8_t *flq0, *flp1, *flq1;
+        if (int rc = ensure_t(d, S_P1, n, &P1)) return rc;
+        if (int rc = ensure_t(d, S_Q0, n, &Q0)) return rc;
+        if (int rc = ensure_t(d, S_Q1, n, &Q1)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, n, &flq0)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, n, &flp1)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, n, &flq1)) return rc;
+        const uint8_t *flc;
+        const g1m *ng1 = neg_g1_const(d, &flc);
+        if (!ng1) return d.rc ? d.rc : BN254_ERR_CUDA_BASE;
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q0, flq0, sigs, n, check);
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
+        if (int rc = dev_hash_g2(d, Q1, flq1, msgs, off, base, n, dst, dst_len, 2)) return rc;
+        LAUNCH(d, k_miller2, n, BN_TPB_HEAVY, F, flf, ng1, flc, (size_t)0, Q0, flq0, P1, flp1, Q1, flq1, n);
+    }
+    LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok, F, flf, n);
+    return 0;
+}
+
+// One shard of an aggregate verification (device pointers).  Writes the 384-byte wire form of
+// prod_i ML(H(m_i), pk_i) [* ML(aggsig, -g2) when agg_sig != NULL] and a bad-input byte.
+int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n,
+                          const uint8_t *agg_sig, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
+    int check = (flags & BN254_FLAG_CHECK_ON_CURVE) ? 1 : 0;
+    size_t tot = n + (agg_sig ? 1 : 0);
+    fp12 *F; g1m *P; g2m *Q; uint8_t *flp, *flq; int *dbad;
+    if (int rc = ensure_t(d, S_F, tot + 1, &F)) return rc;
+    if (int rc = ensure_t(d, S_P1, tot + 1, &P)) return rc;
+    if (int rc = ensure_t(d, S_Q1, tot + 1, &Q)) return rc;
+    if (int rc = ensure_t(d, S_FLP1, tot + 1, &flp)) return rc;
+    if (int rc = ensure_t(d, S_FLQ1, tot + 1, &flq)) return rc;
+    if (int rc = ensure_t(d, S_BAD, 4, &dbad)) return rc;
+    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+    if (variant == BN254_MIN_SIG) {
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, pks, n, check);
+        if (int rc = dev_hash_g1(d, P, flp, msgs, off, base, n, dst, dst_len, 2)) return rc;
+        if (agg_sig) {
+            LAUNCH(d, k_g1_decode, 1, BN_TPB_LIGHT, P + n, flp + n, agg_sig, (size_t)1, check);
+            CK(d, cudaMemcpyFromSymbolAsync(&Q[n].x, k::G2_GEN_X, 64, 0, cudaMemcpyDeviceToDevice, d.st));
+            CK(d, cudaMemcpyFromSymbolAsync(&Q[n].y, k::NEG_G2_GEN_Y, 64, 0, cudaMemcpyDeviceToDevice, d.st));
+            CK(d, cudaMemsetAsync(flq + n, 0, 1, d.st));
+        }
+    } else {
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, pks, n, check);
+        if (int rc = dev_hash_g2(d, Q, flq, msgs, off, base, n, dst, dst_len, 2)) return rc;
+        if (agg_sig) {
+            LAUNCH(d, k_g2_decode, 1, BN_TPB_LIGHT, Q + n, flq + n, agg_sig, (size_t)1, check);
+            const uint8_t *flc;
+            const g1m *ng1 = neg_g1_const(d, &flc);
+            if (!ng1) return d.rc ? d.rc : BN254_ERR_CUDA_BASE;
+            CK(d, cudaMemcpyAsync(P + n, ng1, sizeof(g1m), cudaMemcpyDeviceToDevice, d.st));
+            CK(d, cudaMemsetAsync(flp + n, 0, 1, d.st));
+        }
+    }
+    LAUNCH(d, k_miller1, tot, BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
+    fp12 *res;
+    if (int rc = dev_fp12_product(d, F, tot, &res)) return rc;
+    LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, partial, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
+    CK(d, cudaMemcpyAsync(bad, dbad, 1, cudaMemcpyDeviceToDevice, d.st));  // little-endian low byte
+    return 0;
+}
+
+// partials (wire, device) -> ok byte (device)
+int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, size_t kparts, uint8_t *ok) {
+    fp12 *F; uint8_t *flf; int *dbad;
+    if (int rc = ensure_t(d, S_F, kparts + 1, &F)) return rc;
+    if (int rc = ensure_t(d, S_FLF, kparts + 1, &flf)) return rc;
+    if (int rc = ensure_t(d, S_BAD, 4, &dbad)) return rc;
+    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+    LAUNCH(d, k_fp12_decode, kparts, BN_TPB_LIGHT, F, flf, partials, kparts);
+    LAUNCH(d, k_or_flags, kparts, BN_TPB_LIGHT, dbad, flf, kparts);
+    LAUNCH(d, k_or_bytes, kparts, BN_TPB_LIGHT, dbad, bad, kparts);
+    fp12 *res;
+    if (int rc = dev_fp12_product(d, F, kparts, &res)) return rc;
+    LAUNCH(d, k_final_exp, 1, BN_TPB_HEAVY, res, (size_t)1);
+    LAUNCH(d, k_finish_ok, 1, 32, ok, res, dbad);
+    return 0;
+}
+
+// ---- sharding helpers -----------------------------------------------------------------------------
+template <class Fn>
+int run_sharded(bn254_ctx *ctx, size_t n, Fn fn) {
+    size_t nd = ctx->devs.size();
+    if (nd == 1 || n < nd) {
+        Dev &d = ctx->devs[0];
+        d.rc = 0;
+        cudaSetDevice(d.id);
+        int rc = fn(d, (size_t)0, n);
+        if (rc) ctx->err = d.err;
+        return rc;
+    }
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < nd; g++) {
+        size_t lo = n * g / nd, hi = n * (g + 1) / nd;
+        Dev *d = &ctx->devs[g];
+        d->rc = 0;
+        th.emplace_back([=]() {
+            cudaSetDevice(d->id);
+            d->rc = fn(*d, lo, hi);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (auto &d : ctx->devs)
+        if (d.rc) {
+            ctx->err = d.err;
+            return d.rc;
+        }
+    return 0;
+}
+
+int fail_arg(bn254_ctx *ctx, const char *what) {
+    if (ctx) ctx->err = what;
+    return BN254_ERR_ARG;
+}
+
+// stage messages [lo, hi) of a host blob: copies the byte range and the offsets, returns device ptrs
+int stage_msgs(Dev &d, const uint8_t *msgs, const uint64_t *offsets, size_t lo, size_t hi, const uint8_t **d_msgs, const uint64_t **d_off,
+               uint64_t *base) {
+    uint64_t b0 = offsets[lo], b1 = offsets[hi];
+    uint8_t *dm; uint64_t *dof;
+    if (int rc = ensure_t(d, S_MSGS, (size_t)(b1 - b0) + 16, &dm)) return rc;
+    if (int rc = ensure_t(d, S_OFF, hi - lo + 1, &dof)) return rc;
+    if (b1 > b0) CK(d, cudaMemcpyAsync(dm, msgs + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, d.st));
+    CK(d, cudaMemcpyAsync(dof, offsets + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
+    *d_msgs = dm;
+    *d_off = dof;
+    *base = b0;
+    return 0;
+}
+
+int check_offsets(bn254_ctx *ctx, const uint64_t *offsets, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail_arg(ctx, "offsets must be non-decreasing");
+    return 0;
+}
+
+// host entry for the four hash/encode calls
+int host_hash(bn254_ctx *ctx, int group, int count, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst,
+              size_t dst_len, uint8_t *out, uint8_t *status) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (n && (!offsets || !out)) return fail_arg(ctx, "null pointer");
+    if (n == 0) return 0;
+    if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    size_t rec = group == 1 ? 64 : 128;
+    size_t chunk = ctx->chunk;
+    return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        for (size_t c = lo; c < hi; c += chunk) {
+            size_t e = std::min(hi, c + chunk), m = e - c;
+            const uint8_t *dm; const uint64_t *dof; uint64_t base;
+            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            uint8_t *dout, *dst_status;
+            if (int rc = ensure_t(d, S_OUT, m * rec, &dout)) return rc;
+            if (int rc = ensure_t(d, S_STATUS, m, &dst_status)) return rc;
+            if (int rc = dev_hash_wire(d, group, dm, dof, base, m, ddst, dlen, count, dout, dst_status)) return rc;
+            CK(d, cudaMemcpyAsync(out + c * rec, dout, m * rec, cudaMemcpyDeviceToHost, d.st));
+            if (status) CK(d, cudaMemcpyAsync(status + c, dst_status, m, cudaMemcpyDeviceToHost, d.st));
+            CK(d, cudaStreamSynchronize(d.st));
+        }
+        return 0;
+    });
+}
+
+// generic "wire records in -> wire records out" host wrapper for point-wise kernels
+template <class Fn>
+int host_map(bn254_ctx *ctx, size_t n, const uint8_t *in_a, size_t rec_a, const uint8_t *in_b, size_t rec_b, uint8_t *out, size_t rec_out,
+             uint8_t *status, Fn fn) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (n == 0) return 0;
+    if (!in_a || !out) return fail_arg(ctx, "null pointer");
+    size_t chunk = ctx->chunk;
+    return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
+        for (size_t c = lo; c < hi; c += chunk) {
+            size_t e = std::min(hi, c + chunk), m = e - c;
+            uint8_t *da, *db = nullptr, *dout, *dstat;
+            if (int rc = ensure_t(d, S_IN_A, m * rec_a, &da)) return rc;
+            CK(d, cudaMemcpyAsync(da, in_a + c * rec_a, m * rec_a, cudaMemcpyHostToDevice, d.st));
+            if (in_b) {
+                if (int rc = ensure_t(d, S_IN_B, m * rec_b, &db)) return rc;
+                CK(d, cudaMemcpyAsync(db, in_b + c * rec_b, m * rec_b, cudaMemcpyHostToDevice, d.st));
+            }
+            if (int rc = ensure_t(d, S_OUT, m * rec_out, &dout)) return rc;
+            if (int rc = ensure_t(d, S_STATUS, m, &dstat)) return rc;
+            if (int rc = fn(d, da, db, m, dout, dstat)) return rc;
+            CK(d, cudaMemcpyAsync(out + c * rec_out, dout, m * rec_out, cudaMemcpyDeviceToHost, d.st));
+            if (status) CK(d, cudaMemcpyAsync(status + c, dstat, m, cudaMemcpyDeviceToHost, d.st));
+            CK(d, cudaStreamSynchronize(d.st));
+        }
+        return 0;
+    });
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int bn254_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
+    if (!out || n_dev < 1) return BN254_ERR_ARG;
+    *out = nullptr;
+    int have = bn254_device_count();
+    if (have < 1) return BN254_ERR_NO_DEVICE;
+    bn254_ctx *ctx = new bn254_ctx();
+    for (int i = 0; i < n_dev; i++) {
+        Dev d;
+        d.id = device_ids ? device_ids[i] : i;
+        if (d.id < 0 || d.id >= have) {
+            delete ctx;
+            return BN254_ERR_ARG;
+        }
+        ctx->devs.push_back(d);
+    }
+    for (auto &d : ctx->devs) {
+        cudaError_t e = cudaSetDevice(d.id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            int rc = BN254_ERR_CUDA_BASE - (int)e;
+            bn254_ctx_destroy(ctx);
+            return rc;
+        }
+    }
+    if (const char *s = getenv("BN254_CHUNK")) {
+        long v = atol(s);
+        if (v > 0) ctx->chunk = (size_t)v;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void bn254_ctx_destroy(bn254_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        if (d.st) cudaStreamSynchronize(d.st);
+        for (auto &b : d.bufs)
+            if (b.p) cudaFree(b.p);
+        if (d.st) cudaStreamDestroy(d.st);
+    }
+    delete ctx;
+}
+
+const char *bn254_last_error(const bn254_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uint64_t bn254_launch_count(const bn254_ctx *ctx) {
+    uint64_t t = 0;
+    if (ctx)
+        for (auto &d : ctx->devs) t += d.launches;
+    return t;
+}
+int bn254_profile_enable(bn254_ctx *ctx, int on) {
+    if (!ctx) return BN254_ERR_ARG;
+    for (auto &d : ctx->devs) d.prof = on != 0;
+    return 0;
+}
+// Drains the recorded launches of the first device into `buf` as lines "kernel items ms\n".
+int bn254_profile_drain(bn254_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return BN254_ERR_ARG;
+    Dev &d = ctx->devs[0];
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.st);
+    std::string out;
+    for (auto &r : d.recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        char line[160];
+        snprintf(line, sizeof line, "%s %zu %.6f\n", r.name, r.items, ms);
+        out += line;
+    }
+    d.recs.clear();
+    if (out.size() + 1 > cap) return BN254_ERR_ARG;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+void *bn254_stream(bn254_ctx *ctx) { return ctx ? (void *)ctx->devs[0].st : nullptr; }
+int bn254_sync(bn254_ctx *ctx) {
+    if (!ctx) return BN254_ERR_ARG;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaError_t e = cudaStreamSynchronize(d.st);
+        if (e != cudaSuccess) {
+            ctx->err = cudaGetErrorString(e);
+            return BN254_ERR_CUDA_BASE - (int)e;
+        }
+    }
+    return 0;
+}
+
+int bn254_hash_to_g1(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, uint8_t *out,
+                     uint8_t *status) {
+    return host_hash(ctx, 1, 2, msgs, offsets, n, dst, dst_len, out, status);
+}
+int bn254_encode_to_g1(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                       uint8_t *out, uint8_t *status) {
+    return host_hash(ctx, 1, 1, msgs, offsets, n, dst, dst_len, out, status);
+}
+int bn254_hash_to_g2(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, uint8_t *out,
+                     uint8_t *status) {
+    return host_hash(ctx, 2, 2, msgs, offsets, n, dst, dst_len, out, status);
+}
+int bn254_encode_to_g2(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                       uint8_t *out, uint8_t *status) {
+    return host_hash(ctx, 2, 1, msgs, offsets, n, dst, dst_len, out, status);
+}
+
+int bn254_pairing_batch(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt, uint8_t *status) {
+    if (n && !g2) return fail_arg(ctx, "null pointer");
+    return host_map(ctx, n, g1, 64, g2, 128, gt, 384, status,
+                    [](Dev &d, const uint8_t *a, const uint8_t *b, size_t m, uint8_t *o, uint8_t *s) { return dev_pairing(d, a, b, m, o, s, 0); });
+}
+int bn254_miller_loop_batch(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml, uint8_t *status) {
+    if (n && !g2) return fail_arg(ctx, "null pointer");
+    return host_map(ctx, n, g1, 64, g2, 128, ml, 384, status,
+                    [](Dev &d, const uint8_t *a, const uint8_t *b, size_t m, uint8_t *o, uint8_t *s) { return dev_pairing(d, a, b, m, o, s, 1); });
+}
+int bn254_final_exponentiation(bn254_ctx *ctx, const uint8_t *ml, size_t n, uint8_t *gt, uint8_t *status) {
+    return host_map(ctx, n, ml, 384, nullptr, 0, gt, 384, status,
+                    [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *s) { return dev_final_exp(d, a, m, o, s); });
+}
+
+int bn254_fp12_product(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out) {
+    if (!ctx || !out || (n && !in)) return fail_arg(ctx, "null pointer");
+    Dev &d = ctx->devs[0];
+    d.rc = 0;
+    cudaSetDevice(d.id);
+    auto body = [&]() -> int {
+        uint8_t *din, *dout, *flf; fp12 *F; int *dbad;
+        if (int rc = ensure_t(d, S_IN_A, n * 384 + 16, &din)) return rc;
+        if (int rc = ensure_t(d, S_OUT, 384, &dout)) return rc;
+        if (int rc = ensure_t(d, S_F, n + 1, &F)) return rc;
+        if (int rc = ensure_t(d, S_FLF, n + 1, &flf)) return rc;
+        if (int rc = ensure_t(d, S_BAD, 4, &dbad)) return rc;
+        CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+        if (n) CK(d, cudaMemcpyAsync(din, in, n * 384, cudaMemcpyHostToDevice, d.st));
+        LAUNCH(d, k_fp12_decode, n, BN_TPB_LIGHT, F, flf, din, n);
+        LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad, flf, n);
+        fp12 *res;
+        if (int rc = dev_fp12_product(d, F, n, &res)) return rc;
+        LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
+        int hbad = 0;
+        CK(d, cudaMemcpyAsync(out, dout, 384, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaMemcpyAsync(&hbad, dbad, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        return hbad ? BN254_ERR_INVALID_GT_BYTES : 0;
+    };
+    int rc = body();
+    if (rc && rc != BN254_ERR_INVALID_GT_BYTES) ctx->err = d.err;
+    return rc;
+}
+
+int bn254_multi_miller_loop(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml) {
+    if (!ctx || !ml || (n && (!g1 || !g2))) return fail_arg(ctx, "null pointer");
+    Dev &d = ctx->devs[0];
+    d.rc = 0;
+    cudaSetDevice(d.id);
+    int which = 0;
+    auto body = [&]() -> int {
+        uint8_t *da, *db, *dout, *flp, *flq; g1m *P; g2m *Q; fp12 *F; int *dbad;
+        if (int rc = ensure_t(d, S_IN_A, n * 64 + 16, &da)) return rc;
+        if (int rc = ensure_t(d, S_IN_B, n * 128 + 16, &db)) return rc;
+        if (int rc = ensure_t(d, S_OUT, 384, &dout)) return rc;
+        if (int rc = ensure_t(d, S_P0, n + 1, &P)) return rc;
+        if (int rc = ensure_t(d, S_Q0, n + 1, &Q)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, n + 1, &flp)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, n + 1, &flq)) return rc;
+        if (int rc = ensure_t(d, S_F, n + 1, &F)) return rc;
+        if (int rc = ensure_t(d, S_BAD, 8, &dbad)) return rc;
+        CK(d, cudaMemsetAsync(dbad, 0, 2 * sizeof(int), d.st));
+        if (n) {
+            CK(d, cudaMemcpyAsync(da, g1, n * 64, cudaMemcpyHostToDevice, d.st));
+            CK(d, cudaMemcpyAsync(db, g2, n * 128, cudaMemcpyHostToDevice, d.st));
+        }
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, da, n, 0);
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, db, n, 0);
+        LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad, flp, n);
+        LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad + 1, flq, n);
+        LAUNCH(d, k_miller1, n, BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
+        fp12 *res;
+        if (int rc = dev_fp12_product(d, F, n, &res)) return rc;
+        LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
+        int hbad[2] = {0, 0};
+        CK(d, cudaMemcpyAsync(ml, dout, 384, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaMemcpyAsync(hbad, dbad, 2 * sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        which = hbad[0] ? BN254_ERR_INVALID_G1_BYTES : (hbad[1] ? BN254_ERR_INVALID_G2_BYTES : 0);
+        return which;
+    };
+    int rc = body();
+    if (rc && !which) ctx->err = d.err;
+    return rc;
+}
+
+// ---- verify ------------------------------------------------------------------------------------
+int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs,
+                       size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (n == 0) return 0;
+    if (!pks || !offsets || !sigs || !ok) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
+    size_t chunk = ctx->chunk;
+    return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        for (size_t c = lo; c < hi; c += chunk) {
+            size_t e = std::min(hi, c + chunk), m = e - c;
+            const uint8_t *dm; const uint64_t *dof; uint64_t base;
+            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            uint8_t *dpk, *dsig, *dok;
+            if (int rc = ensure_t(d, S_IN_A, m * rpk, &dpk)) return rc;
+            if (int rc = ensure_t(d, S_IN_B, m * rsig, &dsig)) return rc;
+            if (int rc = ensure_t(d, S_OUT, m, &dok)) return rc;
+            CK(d, cudaMemcpyAsync(dpk, pks + c * rpk, m * rpk, cudaMemcpyHostToDevice, d.st));
+            CK(d, cudaMemcpyAsync(dsig, sigs + c * rsig, m * rsig, cudaMemcpyHostToDevice, d.st));
+            if (int rc = dev_verify(d, variant, dpk, dm, dof, base, dsig, m, ddst, dlen, flags, dok)) return rc;
+            CK(d, cudaMemcpyAsync(ok + c, dok, m, cudaMemcpyDeviceToHost, d.st));
+            CK(d, cudaStreamSynchronize(d.st));
+        }
+        return 0;
+    });
+}
+
+int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (!partial || !bad || (n && (!pks || !offsets))) return fail_arg(ctx, "null pointer");
+    if (n)
+        if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
+    size_t nd = ctx->devs.size();
+    std::vector<uint8_t> parts(nd * 384), bads(nd, 0);
+    static const uint64_t zero_off[1] = {0};
+    const uint64_t *offs = n ? offsets : zero_off;
+    // every device takes a contiguous slice; device 0 also takes the aggregate signature
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < nd; g++) {
+        size_t lo = n * g / nd, hi = n * (g + 1) / nd;
+        Dev *d = &ctx->devs[g];
+        d->rc = 0;
+        auto work = [=, &parts, &bads]() {
+            cudaSetDevice(d->id);
+            d->rc = [&]() -> int {
+                Dev &dd = *d;
+                size_t m = hi - lo;
+                const uint8_t *ddst; uint32_t dlen;
+                if (int rc = stage_dst(dd, dst, dst_len, true, &ddst, &dlen)) return rc;
+                const uint8_t *dm; const uint64_t *dof; uint64_t base;
+                if (int rc = stage_msgs(dd, msgs, offs, lo, hi, &dm, &dof, &base)) return rc;
+                uint8_t *dpk, *dsig = nullptr, *dout;
+                if (int rc = ensure_t(dd, S_IN_A, m * rpk + 16, &dpk)) return rc;
+                if (int rc = ensure_t(dd, S_OUT, 384 + 16, &dout)) return rc;
+                if (m) CK(dd, cudaMemcpyAsync(dpk, pks + lo * rpk, m * rpk, cudaMemcpyHostToDevice, dd.st));
+                if (g == 0 && agg_sig) {
+                    if (int rc = ensure_t(dd, S_IN_B, rsig, &dsig)) return rc;
+                    CK(dd, cudaMemcpyAsync(dsig, agg_sig, rsig, cudaMemcpyHostToDevice, dd.st));
+                }
+                if (int rc = dev_aggregate_partial(dd, variant, dpk, dm, dof, base, m, dsig, ddst, dlen, flags, dout, dout + 384)) return rc;
+                CK(dd, cudaMemcpyAsync(&parts[g * 384], dout, 384, cudaMemcpyDeviceToHost, dd.st));
+                CK(dd, cudaMemcpyAsync(&bads[g], dout + 384, 1, cudaMemcpyDeviceToHost, dd.st));
+                CK(dd, cudaStreamSynchronize(dd.st));
+                return 0;
+            }();
+        };
+        if (nd == 1) work();
+        else th.emplace_back(work);
+    }
+    for (auto &t : th) t.join();
+    for (auto &d : ctx->devs)
+        if (d.rc) {
+            ctx->err = d.err;
+            return d.rc;
+        }
+    if (nd == 1) {
+        memcpy(partial, parts.data(), 384);
+        *bad = bads[0] ? 1 : 0;
+        return 0;
+    }
+    uint8_t b = 0;
+    for (auto x : bads) b |= x;
+    *bad = b ? 1 : 0;
+    return bn254_fp12_product(ctx, parts.data(), nd, partial);
+}
+
+int bn254_aggregate_finish(bn254_ctx *ctx, const uint8_t *partials, const uint8_t *bad, size_t kparts, uint8_t *ok) {
+    if (!ctx || !partials || !ok || kparts == 0) return fail_arg(ctx, "null pointer / no partials");
+    Dev &d = ctx->devs[0];
+    d.rc = 0;
+    cudaSetDevice(d.id);
+    uint8_t anybad = 0;
+    if (bad)
+        for (size_t i = 0; i < kparts; i++) anybad |= bad[i];
+    auto body = [&]() -> int {
+        uint8_t *din, *dok, *dbadz;
+        if (int rc = ensure_t(d, S_IN_A, kparts * 384, &din)) return rc;
+        if (int rc = ensure_t(d, S_OUT, 16, &dok)) return rc;
+        if (int rc = ensure_t(d, S_STATUS, kparts + 16, &dbadz)) return rc;
+        CK(d, cudaMemcpyAsync(din, partials, kparts * 384, cudaMemcpyHostToDevice, d.st));
+        CK(d, cudaMemsetAsync(dbadz, 0, kparts, d.st));
+        if (int rc = dev_aggregate_finish(d, din, dbadz, kparts, dok)) return rc;
+        uint8_t h = 0;
+        CK(d, cudaMemcpyAsync(&h, dok, 1, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        *ok = (h && !anybad) ? 1 : 0;
+        return 0;
+    };
+    int rc = body();
+    if (rc) ctx->err = d.err;
+    return rc;
+}
+
+int bn254_aggregate_verify(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                           const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    if (!ctx || !agg_sig || !ok) return fail_arg(ctx, "null pointer");
+    uint8_t partial[384], bad = 0;
+    int rc = bn254_aggregate_partial(ctx, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, &bad);
+    if (rc == BN254_ERR_INVALID_GT_BYTES) {  // cannot happen for library-produced partials
+        *ok = 0;
+        return 0;
+    }
+    if (rc) return rc;
+    return bn254_aggregate_finish(ctx, partial, &bad, 1, ok);
+}
+
+// ---- codecs / predicates / scalar multiplication ---------------------------------------------------
+int bn254_g1_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 64, nullptr, 0, out, 32, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        g1m *P; uint8_t *fl;
+        if (int rc = ensure_t(d, S_P0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, m, &fl)) return rc;
+        LAUNCH(d, k_g1_decode, m, BN_TPB_LIGHT, P, fl, a, m, 0);
+        LAUNCH(d, k_g1_compress, m, BN_TPB_LIGHT, o, P, fl, m);
+        return 0;
+    });
+}
+int bn254_g2_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 128, nullptr, 0, out, 64, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        g2m *P; uint8_t *fl;
+        if (int rc = ensure_t(d, S_Q0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, m, &fl)) return rc;
+        LAUNCH(d, k_g2_decode, m, BN_TPB_LIGHT, P, fl, a, m, 0);
+        LAUNCH(d, k_g2_compress, m, BN_TPB_LIGHT, o, P, fl, m);
+        return 0;
+    });
+}
+int bn254_g1_decompress(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, uint8_t *status) {
+    return host_map(ctx, n, in, 32, nullptr, 0, out, 64, status, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *s) {
+        g1m *P; uint8_t *fl;
+        if (int rc = ensure_t(d, S_P0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, m, &fl)) return rc;
+        LAUNCH(d, k_g1_decompress, m, BN_TPB_HEAVY, P, fl, a, m);
+        LAUNCH(d, k_g1_encode, m, BN_TPB_LIGHT, o, s, P, fl, m);
+        return 0;
+    });
+}
+int bn254_g2_decompress(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, uint8_t *status) {
+    return host_map(ctx, n, in, 64, nullptr, 0, out, 128, status, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *s) {
+        g2m *P; uint8_t *fl;
+        if (int rc = ensure_t(d, S_Q0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, m, &fl)) return rc;
+        LAUNCH(d, k_g2_decompress, m, BN_TPB_HEAVY, P, fl, a, m);
+        LAUNCH(d, k_g2_encode, m, BN_TPB_LIGHT, o, s, P, fl, m);
+        return 0;
+    });
+}
+int bn254_g1_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 64, nullptr, 0, out, 1, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        LAUNCH(d, k_g1_on_curve, m, BN_TPB_LIGHT, o, a, m);
+        return 0;
+    });
+}
+int bn254_g2_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 128, nullptr, 0, out, 1, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        LAUNCH(d, k_g2_on_curve, m, BN_TPB_LIGHT, o, a, m);
+        return 0;
+    });
+}
+int bn254_g1_mul(bn254_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out) {
+    if (n && !scalars) return fail_arg(ctx, "null pointer");
+    return host_map(ctx, n, pts, 64, scalars, 32, out, 64, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *b, size_t m, uint8_t *o, uint8_t *) {
+        g1m *P, *R; uint8_t *fl, *flo;
+        if (int rc = ensure_t(d, S_P0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_P1, m, &R)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, m, &fl)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, m, &flo)) return rc;
+        LAUNCH(d, k_g1_decode, m, BN_TPB_LIGHT, P, fl, a, m, 0);
+        LAUNCH(d, k_g1_mul, m, BN_TPB_HEAVY, R, flo, P, fl, b, m);
+        LAUNCH(d, k_g1_encode, m, BN_TPB_LIGHT, o, (uint8_t *)nullptr, R, flo, m);
+        return 0;
+    });
+}
+int bn254_g2_mul(bn254_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out) {
+    if (n && !scalars) return fail_arg(ctx, "null pointer");
+    return host_map(ctx, n, pts, 128, scalars, 32, out, 128, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *b, size_t m, uint8_t *o, uint8_t *) {
+        g2m *P, *R; uint8_t *fl, *flo;
+        if (int rc = ensure_t(d, S_Q0, m, &P)) return rc;
+        if (int rc = ensure_t(d, S_Q1, m, &R)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, m, &fl)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, m, &flo)) return rc;
+        LAUNCH(d, k_g2_decode, m, BN_TPB_LIGHT, P, fl, a, m, 0);
+        LAUNCH(d, k_g2_mul, m, BN_TPB_HEAVY, R, flo, P, fl, b, m);
+        LAUNCH(d, k_g2_encode, m, BN_TPB_LIGHT, o, (uint8_t *)nullptr, R, flo, m);
+        return 0;
+    });
+}
+
+static int sum_impl(bn254_ctx *ctx, int group, const uint8_t *pts, size_t n, uint8_t *out) {
+    if (!ctx || !out || (n && !pts)) return fail_arg(ctx, "null pointer");
+    Dev &d = ctx->devs[0];
+    d.rc = 0;
+    cudaSetDevice(d.id);
+    size_t rec = group == 1 ? 64 : 128;
+    int bad = 0;
+    auto body = [&]() -> int {
+        uint8_t *din, *dout, *hfl = nullptr;
+        if (int rc = ensure_t(d, S_IN_A, n * rec + 16, &din)) return rc;
+        if (int rc = ensure_t(d, S_OUT, rec + 16, &dout)) return rc;
+        if (n) CK(d, cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, d.st));
+        size_t m0 = std::max<size_t>(1, (n + 15) / 16);
+        if (group == 1) {
+            g1m *P, *A; uint8_t *fl, *fla;
+            if (int rc = ensure_t(d, S_P0, n + 1, &P)) return rc;
+            if (int rc = ensure_t(d, S_FLP0, n + 1, &fl)) return rc;
+            if (int rc = ensure_t(d, S_P1, 2 * m0 + 2, &A)) return rc;
+            if (int rc = ensure_t(d, S_FLP1, 2 * m0 + 2, &fla)) return rc;
+            LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, fl, din, n, 0);
+            const g1m *src = P; const uint8_t *sfl = fl; size_t cur = n; g1m *dp = A; uint8_t *dfl = fla;
+            while (true) {
+                size_t m = std::max<size_t>(1, (cur + 15) / 16);
+                LAUNCH(d, k_g1_sum, m, BN_TPB_HEAVY, dp, dfl, src, sfl, cur, m);
+                if (m == 1) break;
+                src = dp; sfl = dfl; cur = m;
+                dp = (dp == A) ? A + m0 : A; dfl = (dfl == fla) ? fla + m0 : fla;
+            }
+            LAUNCH(d, k_g1_encode, 1, BN_TPB_LIGHT, dout, dout + rec, dp, dfl, (size_t)1);
+            hfl = dout + rec;
+        } else {
+            g2m *P, *A; uint8_t *fl, *fla;
+            if (int rc = ensure_t(d, S_Q0, n + 1, &P)) return rc;
+            if (int rc = ensure_t(d, S_FLQ0, n + 1, &fl)) return rc;
+            if (int rc = ensure_t(d, S_Q1, 2 * m0 + 2, &A)) return rc;
+            if (int rc = ensure_t(d, S_FLQ1, 2 * m0 + 2, &fla)) return rc;
+            LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, P, fl, din, n, 0);
+            const g2m *src = P; const uint8_t *sfl = fl; size_t cur = n; g2m *dp = A; uint8_t *dfl = fla;
+            while (true) {
+                size_t m = std::max<size_t>(1, (cur + 15) / 16);
+                LAUNCH(d, k_g2_sum, m, BN_TPB_HEAVY, dp, dfl, src, sfl, cur, m);
+                if (m == 1) break;
+                src = dp; sfl = dfl; cur = m;
+                dp = (dp == A) ? A + m0 : A; dfl = (dfl == fla) ? fla + m0 : fla;
+            }
+            LAUNCH(d, k_g2_encode, 1, BN_TPB_LIGHT, dout, dout + rec, dp, dfl, (size_t)1);
+            hfl = dout + rec;
+        }
+        uint8_t st = 1;
+        CK(d, cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaMemcpyAsync(&st, hfl, 1, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        bad = !st;
+        return 0;
+    };
+    int rc = body();
+    if (rc) {
+        ctx->err = d.err;
+        return rc;
+    }
+    if (bad) return group == 1 ? BN254_ERR_INVALID_G1_BYTES : BN254_ERR_INVALID_G2_BYTES;
+    return 0;
+}
+int bn254_g1_sum(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) { return sum_impl(ctx, 1, pts, n, out); }
+int bn254_g2_sum(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) { return sum_impl(ctx, 2, pts, n, out); }
+
+// ---- device-resident entry points ------------------------------------------------------------------
+#define DEV_PROLOGUE()                \
+    if (!ctx) return BN254_ERR_ARG;   \
+    Dev &d = ctx->devs[0];            \
+    d.rc = 0;                         \
+    cudaSetDevice(d.id);
+#define DEV_EPILOGUE(rc)              \
+    if (rc) ctx->err = d.err;         \
+    return rc;
+
+int bn254_hash_to_g1_dev(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int count,
+                         uint8_t *out, uint8_t *status) {
+    DEV_PROLOGUE();
+    if (count != 1 && count != 2) return fail_arg(ctx, "count must be 1 (encode) or 2 (hash)");
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_hash_wire(d, 1, msgs, offsets, 0, n, ddst, dlen, count, out, status);
+    DEV_EPILOGUE(rc);
+}
+int bn254_hash_to_g2_dev(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int count,
+                         uint8_t *out, uint8_t *status) {
+    DEV_PROLOGUE();
+    if (count != 1 && count != 2) return fail_arg(ctx, "count must be 1 (encode) or 2 (hash)");
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_hash_wire(d, 2, msgs, offsets, 0, n, ddst, dlen, count, out, status);
+    DEV_EPILOGUE(rc);
+}
+int bn254_pairing_batch_dev(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt, uint8_t *status) {
+    DEV_PROLOGUE();
+    int rc = dev_pairing(d, g1, g2, n, gt, status, 0);
+    DEV_EPILOGUE(rc);
+}
+int bn254_verify_batch_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs,
+                           size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    DEV_PROLOGUE();
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_verify(d, variant, pks, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
+    DEV_EPILOGUE(rc);
+}
+int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
+    DEV_PROLOGUE();
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_aggregate_partial(d, variant, pks, msgs, offsets, 0, n, agg_sig, ddst, dlen, flags, partial, bad);
+    DEV_EPILOGUE(rc);
+}
+
+int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, double *ms_out) {
+    DEV_PROLOGUE();
+    if (iters < 1 || !ops_per_s) return fail_arg(ctx, "bad argument");
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CK(d, cudaGetDeviceProperties(&prop, d.id));
+        uint32_t *sink;
+        if (int rc = ensure_t(d, S_TMP, 16, &sink)) return rc;
+        int nblk = prop.multiProcessorCount * 8;  // 8 x 256 threads per SM = full occupancy
+        cudaEvent_t e0, e1;
+        CK(d, cudaEventCreate(&e0));
+        CK(d, cudaEventCreate(&e1));
+        k_imad_peak<<<nblk, 256, 0, d.st>>>(sink, iters / 8 + 1, mode);  // warm-up
+        d.launches++;
+        CK(d, cudaEventRecord(e0, d.st));
+        k_imad_peak<<<nblk, 256, 0, d.st>>>(sink, iters, mode);
+        d.launches++;
+        CK(d, cudaEventRecord(e1, d.st));
+        CK(d, cudaEventSynchronize(e1));
+        CK(d, cudaGetLastError());
+        float ms = 0;
+        CK(d, cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        double ops = (double)nblk * 256.0 * (double)iters * 64.0;
+        *ops_per_s = ops / (ms * 1e-3);
+        if (ms_out) *ms_out = ms;
+        return 0;
+    };
+    int rc = body();
+    DEV_EPILOGUE(rc);
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+"""One-process-per-GPU sharding of the path over torch.distributed.
+
+Independent verifications / hashes / pairings shard by index with NO data-path collective: every
+rank runs its contiguous slice [n*rank/world, n*(rank+1)/world) on its own GPU.  Aggregate
+verification has exactly one exchange step: each rank reduces its Miller loops to one Fp12 partial
+product (384 B + 1 flag byte), the partials are all-gathered (NCCL over NVLink / NVSwitch on GPU
+ranks, gloo in the CPU tests), and one final exponentiation decides.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, world, rank):
+    """Contiguous slice of n items owned by `rank` (same split as the C ABI's multi-device ctx)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def shard_tuples(n, world, rank, records):
+    """records: list of (buffer, record_size) -> the rank's slices (messages: pass the list itself with size None)."""
+    lo, hi = shard_range(n, world, rank)
+    out = []
+    for buf, rec in records:
+        out.append(buf[lo:hi] if rec is None else buf[lo * rec:hi * rec])
+    return out
+
+
+def gather_partials(partial, bad, device=None, group=None):
+    """all-gather of the (384 + 1)-byte partial records -> (concatenated partials, list of bad flags)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return partial, [bad]
+    t = torch.tensor(list(partial) + [bad], dtype=torch.uint8, device=device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    rows = [bytes(o.cpu().numpy()) for o in outs]
+    return b"".join(r[:384] for r in rows), [r[384] for r in rows]
+
+
+def aggregate_verify_sharded(ctx, variant, pks_shard, msgs_shard, agg_sig, dst, flags=0, device=None, group=None):
+    """Every rank passes ITS shard of (pk_i, m_i); `agg_sig` is used on rank 0 only.  Returns the
+    verdict (0/1) on every rank.  `ctx` needs aggregate_partial / aggregate_finish (bls_bn254_b200.Context)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    part, bad = ctx.aggregate_partial(variant, pks_shard, msgs_shard, agg_sig if rank == 0 else None, dst, flags)
+    parts, bads = gather_partials(part, bad, device=device, group=group)
+    return ctx.aggregate_finish(parts, bads)
+
+
+def verify_sharded(ctx, variant, pks_shard, msgs_shard, sigs_shard, dst, flags=0, gather=False, device=None, group=None):
+    """Every rank verifies its own shard (no collective).  gather=True additionally all-gathers the
+    accept bytes so each rank holds the whole job's verdicts (shards must be equally long)."""
+    ok = ctx.verify_batch(variant, pks_shard, msgs_shard, sigs_shard, dst, flags)
+    if not gather or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ok
+    t = torch.tensor(list(ok), dtype=torch.uint8, device=device)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(outs, t, group=group)
+    return b"".join(bytes(o.cpu().numpy()) for o in outs)

@@ -1,0 +1,107 @@
+"""BLS scheme layer over the GPU primitives: keys, sign, verify, aggregate, aggregate-verify.
+
+The reference snapshot has no scheme layer (no SecretKey / PublicKey / Signature
+anywhere under src/); north_star names it as the crate API, so it is defined here on top of the
+`inner_types` operations exactly as SURVEY.md 8(a) row V states:
+  min-sig: pk = sk*g2 (G2), sig = sk*H_G1(m) (G1), verify e(sig, -g2) * e(H_G1(m), pk) == 1
+  min-pk : pk = sk*g1 (G1), sig = sk*H_G2(m) (G2), verify e(-g1, sig) * e(pk, H_G2(m)) == 1
+All group work (hashing, scalar multiplication, sums, pairings) runs on the GPU through `Context`.
+"""
+import hashlib
+import struct
+
+from .api import DST_MIN_PK, DST_MIN_SIG, G1_GENERATOR, G2_GENERATOR, MIN_PK, MIN_SIG, R_ORDER
+
+SEED = 0xB15B254
+
+
+def _dst(variant):
+    return DST_MIN_SIG if variant == MIN_SIG else DST_MIN_PK
+
+
+def scalar_from_seed(seed, index):
+    """Deterministic non-zero scalar mod r for (seed, index): SHA-256 counter stream."""
+    v = 0
+    ctr = 0
+    while v == 0:
+        h = hashlib.sha256(struct.pack("<QQQ", seed, index, ctr)).digest() + hashlib.sha256(struct.pack("<QQQ", seed ^ 0x5EED, index, ctr)).digest()
+        v = int.from_bytes(h, "big") % R_ORDER
+        ctr += 1
+    return v
+
+
+class SecretKey:
+    def __init__(self, value):
+        if not 0 < value < R_ORDER:
+            raise ValueError("secret key out of range")
+        self.value = value
+
+    def to_bytes(self):
+        return self.value.to_bytes(32, "big")
+
+
+def public_keys(ctx, sks, variant=MIN_SIG):
+    """pk_i = sk_i * generator (wire bytes, concatenated)."""
+    sc = b"".join(s.to_bytes() for s in sks)
+    if variant == MIN_SIG:
+        return ctx.g2_mul(G2_GENERATOR * len(sks), sc)
+    return ctx.g1_mul(G1_GENERATOR * len(sks), sc)
+
+
+def sign(ctx, sks, msgs, variant=MIN_SIG, dst=None):
+    """sig_i = sk_i * H(m_i) (wire bytes, concatenated)."""
+    dst = _dst(variant) if dst is None else dst
+    sc = b"".join(s.to_bytes() for s in sks)
+    if variant == MIN_SIG:
+        return ctx.g1_mul(ctx.hash_to_g1(msgs, dst), sc)
+    return ctx.g2_mul(ctx.hash_to_g2(msgs, dst), sc)
+
+
+def verify(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=0):
+    """n accept bytes (0/1) for n independent (pk, msg, sig) tuples."""
+    return ctx.verify_batch(variant, pks, msgs, sigs, _dst(variant) if dst is None else dst, flags)
+
+
+def aggregate(ctx, sigs, variant=MIN_SIG):
+    """Sum of signatures (one wire-format point)."""
+    return ctx.g1_sum(sigs) if variant == MIN_SIG else ctx.g2_sum(sigs)
+
+
+def aggregate_verify(ctx, pks, msgs, agg_sig, variant=MIN_SIG, dst=None, flags=0):
+    """Distinct-message aggregate verification: one multi-Miller loop, one final exponentiation."""
+    return ctx.aggregate_verify(variant, pks, msgs, agg_sig, _dst(variant) if dst is None else dst, flags)
+
+
+def synth_batch(ctx, n, variant=MIN_SIG, seed=SEED, first=0, msg_len=32, corrupt_every=64, n_keys=None):
+    """Synthetic workload of SURVEY.md 8(d): random keys (n_keys distinct ones, default one per
+    tuple), distinct `msg_len`-byte messages (first 8 bytes = index), signatures made on the GPU;
+    every `corrupt_every`-th tuple is broken (bit flip in the message, somebody else's key, or a valid
+    signature of another tuple) so both verdicts occur.
+    Returns (pks, msgs list, sigs, expected accept bytes)."""
+    nk = n if not n_keys else min(n_keys, n)
+    uniq = [SecretKey(scalar_from_seed(seed, first + i if nk == n else i)) for i in range(nk)]
+    sks = [uniq[i % nk] for i in range(n)]
+    msgs = []
+    for i in range(first, first + n):
+        body = hashlib.sha256(struct.pack("<QQ", seed, i)).digest()
+        stream = struct.pack("<Q", i) + body * (msg_len // 32 + 1)
+        msgs.append(stream[:msg_len] if msg_len >= 8 else body[:msg_len])
+    rpk, rsig = (128, 64) if variant == MIN_SIG else (64, 128)
+    upk = public_keys(ctx, uniq, variant)
+    pks = bytearray(b"".join(upk[(i % nk) * rpk:(i % nk + 1) * rpk] for i in range(n)) if nk != n else upk)
+    sigs = bytearray(sign(ctx, sks, msgs, variant))
+    expected = bytearray(b"\x01" * n)
+    if corrupt_every and n > 1:
+        for j in range(corrupt_every // 2, n, corrupt_every):
+            kind = (j // corrupt_every) % 3
+            o = (j + 1) % n
+            if kind == 0 and msg_len > 0:      # bit flip in the message
+                b = bytearray(msgs[j])
+                b[-1] ^= 1
+                msgs[j] = bytes(b)
+            elif kind == 1 and sks[o].value != sks[j].value:   # somebody else's key
+                pks[j * rpk:(j + 1) * rpk] = pks[o * rpk:(o + 1) * rpk]
+            else:                              # a valid signature of another tuple
+                sigs[j * rsig:(j + 1) * rsig] = sigs[o * rsig:(o + 1) * rsig]
+            expected[j] = 0
+    return bytes(pks), msgs, bytes(sigs), bytes(expected)

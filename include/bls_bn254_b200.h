@@ -1,0 +1,139 @@
+/* bls_bn254_b200.h -- C ABI of libbls_bn254_b200.so: batch BLS verification over BN254 on B200.
+ *
+ * The reference (mikelodder7/bls-bn254) has no FFI; its boundary is the Rust API of
+ * src/inner_types.  Every entry point below is the BATCH form of one reference function and uses
+ * the reference's own byte formats, so a Rust shim maps 1:1:
+ *
+ *   G1 point   64 B  x || y, 32-byte big-endian each            g1.rs:296-302 (to_uncompressed)
+ *   G2 point  128 B  x.c1 || x.c0 || y.c1 || y.c0               g2.rs:290-300
+ *   G1 / G2 compressed 32 B / 64 B, flag in bit 7 of byte 0     g1.rs:283-288, g2.rs:274-283
+ *   Gt / MillerLoopResult 384 B  c0.c0.c0 || c0.c0.c1 || ...    pairings.rs:499-514 (Gt::to_repr)
+ *   identity = (0, 1) uncompressed                              g1.rs:265-271
+ *   messages: one byte blob + u64 offsets[n+1] (message i = msgs[offsets[i] .. offsets[i+1]))
+ *
+ * Return value: 0 on success; -1..-4 = Bn254Error::{InvalidScalarBytes, InvalidG1Bytes,
+ * InvalidG2Bytes, InvalidGtBytes} (error.rs:5-10) for malformed call-level input; -10 bad argument;
+ * -20 no usable CUDA device (there is NO CPU fallback); -100-k = CUDA error k.  Per-item problems
+ * (undecodable point, SvdW exception where the reference panics: fp.rs:325, fp2.rs:255) never abort
+ * a batch: the item's status byte is 0 and its output is all zero bytes (ok[i] = 0 for verify).
+ *
+ * Threading: calls are synchronous; a ctx is single-caller; several contexts may coexist.
+ * Ownership: the caller owns every buffer; nothing is retained after return.
+ * Host-buffer entry points shard items across the ctx's devices by contiguous index range (no
+ * inter-GPU traffic).  "_dev" entry points take device pointers resident on the ctx's FIRST device.
+ */
+#ifndef BLS_BN254_B200_H
+#define BLS_BN254_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bn254_ctx bn254_ctx;
+
+#define BN254_OK 0
+#define BN254_ERR_INVALID_SCALAR_BYTES (-1)
+#define BN254_ERR_INVALID_G1_BYTES (-2)
+#define BN254_ERR_INVALID_G2_BYTES (-3)
+#define BN254_ERR_INVALID_GT_BYTES (-4)
+#define BN254_ERR_ARG (-10)
+#define BN254_ERR_NO_DEVICE (-20)
+#define BN254_ERR_CUDA_BASE (-100)
+
+#define BN254_MIN_SIG 0 /* pk in G2 (128 B), sig in G1 (64 B), messages hashed to G1 */
+#define BN254_MIN_PK 1  /* pk in G1 (64 B), sig in G2 (128 B), messages hashed to G2 */
+#define BN254_FLAG_CHECK_ON_CURVE 1u /* reject keys / signatures that are not on the curve */
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int bn254_device_count(void);
+/* device_ids == NULL: devices 0..n_dev-1.  Fails with BN254_ERR_NO_DEVICE when CUDA is unavailable. */
+int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev);
+void bn254_ctx_destroy(bn254_ctx *ctx);
+const char *bn254_last_error(const bn254_ctx *ctx);
+/* number of kernels this ctx has launched so far (all devices) */
+uint64_t bn254_launch_count(const bn254_ctx *ctx);
+/* cudaStream_t of the ctx's first device (for event timing of the _dev entry points) */
+void *bn254_stream(bn254_ctx *ctx);
+int bn254_sync(bn254_ctx *ctx);
+/* Per-launch timing: when enabled every kernel launch is bracketed by a CUDA event pair on the
+ * launch stream; bn254_profile_drain synchronises and writes one line per launch of the first
+ * device, "kernel_name items milliseconds\n", into buf (BN254_ERR_ARG if it does not fit). */
+int bn254_profile_enable(bn254_ctx *ctx, int on);
+int bn254_profile_drain(bn254_ctx *ctx, char *buf, size_t cap);
+
+/* ---- hash to curve: G1Projective::hash / ::encode (g1.rs:910-928), G2Projective::hash / ::encode
+ *      (g2.rs:919-936) + to_uncompressed.  status may be NULL. ------------------------------------ */
+int bn254_hash_to_g1(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                     uint8_t *out /* n*64 */, uint8_t *status /* n */);
+int bn254_encode_to_g1(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                       uint8_t *out, uint8_t *status);
+int bn254_hash_to_g2(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                     uint8_t *out /* n*128 */, uint8_t *status);
+int bn254_encode_to_g2(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                       uint8_t *out, uint8_t *status);
+
+/* ---- pairing engine: pairing() (pairings.rs:760-802), multi_miller_loop (808-857),
+ *      MillerLoopResult::final_exponentiation (50-178), MillerLoopResult + (37-43) --------------- */
+int bn254_pairing_batch(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt /* n*384 */, uint8_t *status);
+int bn254_miller_loop_batch(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml /* n*384 */, uint8_t *status);
+int bn254_multi_miller_loop(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *ml /* 384 */);
+int bn254_final_exponentiation(bn254_ctx *ctx, const uint8_t *ml, size_t n, uint8_t *gt, uint8_t *status);
+int bn254_fp12_product(bn254_ctx *ctx, const uint8_t *in /* n*384 */, size_t n, uint8_t *out /* 384 */);
+
+/* ---- BLS predicates (absent from the reference snapshot; defined in SURVEY.md 8(a) row V) ---------
+ * min-sig: e(sig, -g2) * e(H_G1(m), pk) == 1;  min-pk: e(-g1, sig) * e(pk, H_G2(m)) == 1
+ * aggregate (distinct messages): e(aggsig, -g2) * prod e(H(m_i), pk_i) == 1  (resp. min-pk) */
+int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs,
+                       size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* n bytes 0/1 */);
+int bn254_aggregate_verify(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                           const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* 1 byte */);
+/* One shard of an aggregate verification: the Fp12 product of this shard's Miller loops (384 B,
+ * un-exponentiated) and a "bad input" byte.  agg_sig is given to exactly one shard (NULL elsewhere).
+ * The shards' partials are exchanged by the caller (one small all-gather) and finished with
+ * bn254_aggregate_finish: product, ONE final exponentiation, compare with 1. */
+int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial /* 384 */,
+                            uint8_t *bad /* 1 */);
+int bn254_aggregate_finish(bn254_ctx *ctx, const uint8_t *partials /* k*384 */, const uint8_t *bad /* k */, size_t k, uint8_t *ok);
+
+/* ---- codecs and predicates: to_/from_compressed (g1.rs:283-328, g2.rs:274-340), is_on_curve ---- */
+int bn254_g1_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n*32 */);
+int bn254_g1_decompress(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out /* n*64 */, uint8_t *status);
+int bn254_g2_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n*64 */);
+int bn254_g2_decompress(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out /* n*128 */, uint8_t *status);
+int bn254_g1_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
+int bn254_g2_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
+
+/* ---- scalar multiplication and sums (sign / keygen / aggregate side; g1.rs:821-841,
+ *      g2.rs:866-886).  scalars: n x 32-byte big-endian integers. -------------------------------- */
+int bn254_g1_mul(bn254_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out);
+int bn254_g2_mul(bn254_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t *out);
+int bn254_g1_sum(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* 64 */);
+int bn254_g2_sum(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* 128 */);
+
+/* ---- device-resident variants (all pointers are device pointers on the ctx's first device; work is
+ *      enqueued on bn254_stream(ctx) and NOT synchronised -- call bn254_sync or use events) -------- */
+int bn254_hash_to_g1_dev(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                         int count, uint8_t *out, uint8_t *status);
+int bn254_hash_to_g2_dev(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                         int count, uint8_t *out, uint8_t *status);
+int bn254_pairing_batch_dev(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt, uint8_t *status);
+int bn254_verify_batch_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
+                           const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok);
+int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial,
+                                uint8_t *bad);
+
+/* ---- INT32 multiply-add micro-benchmark: the roofline denominator.  Runs `iters` rounds of
+ *      independent multiply-add chains on every SM of the first device (8 chains per thread, full
+ *      occupancy) and returns the sustained rate in IMAD-ops/s.  mode 0: mad.lo.u32; mode 1:
+ *      mad.lo.u32 + mad.hi.u32 pairs; mode 2: 32x32+64 wide multiply-add (IMAD.WIDE.U32, the
+ *      instruction the field multiplication issues), counted as 2 IMAD-ops each. ------------------ */
+int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

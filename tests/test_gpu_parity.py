@@ -1,0 +1,283 @@
+"""GPU parity suite (-m gpu): every result of libbls_bn254_b200.so, called through the C ABI, is
+compared byte for byte with (1) the reference's golden vectors (tests/golden/reference_kats.json),
+(2) the CPU oracle on the same seeded inputs, and (3) at BASELINE.json's sizes, size-independent
+properties (accept bits known by construction, bilinearity, product-of-shards)."""
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H = bytes.fromhex
+QUUX_G1 = b"QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_"
+QUUX_G2 = b"QUUX-V01-CS02-with-BN254G2_XMD:SHA-256_SVDW_RO_"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import bls_bn254_b200 as b
+    c = b.Context([0])
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bls_bn254_b200 as b
+    return b
+
+
+def rand_msgs(rng, n, maxlen=96):
+    out = [b"", b"abc", b"abcdef0123456789", b"q128_" + b"q" * 128, b"a512_" + b"a" * 512]
+    while len(out) < n:
+        out.append(rng.randbytes(rng.randrange(0, maxlen)))
+    return out[:n]
+
+
+# ---------------------------------------------------------------------------------- golden vectors
+def test_g1_kats(ctx, kats):
+    for suite, fn in (("g1_encode", ctx.encode_to_g1), ("g1_hash", ctx.hash_to_g1)):
+        dst = kats[suite + "_dst"].encode()
+        msgs = [v["msg"].encode("latin1") for v in kats[suite]]
+        out, st = fn(msgs, dst, want_status=True)
+        assert st == b"\x01" * len(msgs)
+        for i, v in enumerate(kats[suite]):
+            assert out[64 * i:64 * i + 64] == H(v["p_x"]) + H(v["p_y"]), (suite, i)
+
+
+def test_g2_kats(ctx, kats):
+    for suite, fn in (("g2_encode", ctx.encode_to_g2), ("g2_hash", ctx.hash_to_g2)):
+        dst = kats[suite + "_dst"].encode()
+        msgs = [v["msg"].encode("latin1") for v in kats[suite]]
+        out = fn(msgs, dst)
+        for i, v in enumerate(kats[suite]):
+            assert out[128 * i:128 * i + 128] == H(v["x_c1"]) + H(v["x_c0"]) + H(v["y_c1"]) + H(v["y_c0"]), (suite, i)
+
+
+def test_gt_generator_kat(ctx, kats, B):
+    """pairings.rs:970-980: pairing(g1, g2) == Gt::generator()."""
+    exp = b"".join(H(x) for x in kats["gt_generator"])
+    assert ctx.pairing(B.G1_GENERATOR, B.G2_GENERATOR) == exp
+
+
+# -------------------------------------------------------------------------------- against the oracle
+def test_hash_vs_oracle(ctx, orc):
+    rng = random.Random(11)
+    msgs = rand_msgs(rng, 300)
+    for dst in (QUUX_G1, b"", b"x" * 255, b"y" * 256, b"z" * 700):
+        sub = msgs if dst == QUUX_G1 else msgs[:40]
+        assert ctx.hash_to_g1(sub, dst) == orc.hash_to_g1(sub, dst, 2, nthreads=8)
+        assert ctx.encode_to_g1(sub, dst) == orc.hash_to_g1(sub, dst, 1, nthreads=8)
+    sub = msgs[:120]
+    assert ctx.hash_to_g2(sub, QUUX_G2) == orc.hash_to_g2(sub, QUUX_G2, 2, nthreads=8)
+    assert ctx.encode_to_g2(sub, QUUX_G2) == orc.hash_to_g2(sub, QUUX_G2, 1, nthreads=8)
+    assert ctx.hash_to_g2(sub[:20], b"w" * 300) == orc.hash_to_g2(sub[:20], b"w" * 300, 2, nthreads=8)
+
+
+def test_hash_empty_batch(ctx):
+    assert ctx.hash_to_g1([], QUUX_G1) == b""
+    assert ctx.hash_to_g2([], QUUX_G2) == b""
+
+
+def _points(ctx, orc, n, seed):
+    rng = random.Random(seed)
+    msgs = [rng.randbytes(16) for _ in range(n)]
+    return orc.hash_to_g1(msgs, QUUX_G1, nthreads=8), orc.hash_to_g2(msgs, QUUX_G2, nthreads=8)
+
+
+def test_pairing_vs_oracle(ctx, orc, B):
+    g1, g2 = _points(ctx, orc, 40, 3)
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    ident2 = bytes(64) + bytes(32) + bytes(31) + b"\x01"
+    bad1 = b"\xff" * 64  # x >= p after masking
+    bad2 = b"\xff" * 128
+    g1 = B.G1_GENERATOR + ident1 + g1[:64] + bad1 + g1
+    g2 = B.G2_GENERATOR + g2[:128] + ident2 + g2[:128] + g2
+    # one more undecodable G2
+    g1 += g1[-64:]
+    g2 += bad2
+    gt, st = ctx.pairing(g1, g2, want_status=True)
+    egt, est = orc.pairing_batch(g1, g2, nthreads=8, want_status=True)
+    assert st == est
+    assert gt == egt
+    ml = ctx.miller_loop(g1, g2)
+    assert ml == orc.miller_loop_batch(g1, g2, nthreads=8)
+    # final exponentiation of the valid Miller-loop results
+    good = b"".join(ml[384 * i:384 * i + 384] for i in range(len(st)) if st[i])
+    assert ctx.final_exponentiation(good) == orc.final_exponentiation(good, nthreads=8)
+
+
+def test_multi_miller_and_product(ctx, orc, B):
+    g1, g2 = _points(ctx, orc, 37, 5)
+    assert ctx.multi_miller_loop(g1, g2) == orc.multi_miller_loop(g1, g2)
+    assert ctx.multi_miller_loop(b"", b"") == orc.multi_miller_loop(b"", b"")
+    ml = orc.miller_loop_batch(g1, g2, nthreads=8)
+    assert ctx.fp12_product(ml) == orc.fp12_product(ml)
+    assert ctx.fp12_product(ml[:384]) == ml[:384]
+    with pytest.raises(B.Bn254Error) as e:
+        ctx.multi_miller_loop(b"\xff" * 64, g2[:128])
+    assert e.value.code == -2
+    with pytest.raises(B.Bn254Error) as e:
+        ctx.fp12_product(b"\xff" * 384)
+    assert e.value.code == -4
+
+
+def test_bilinearity(ctx, orc):
+    """e(aP, bQ) == e(abP, Q) == e(P, abQ) on the GPU path alone."""
+    g1, g2 = _points(ctx, orc, 4, 7)
+    a = (123456789123456789 << 64 | 987654321).to_bytes(32, "big")
+    b = (0xdeadbeefcafebabe1122334455667788).to_bytes(32, "big")
+    ab = ((int.from_bytes(a, "big") * int.from_bytes(b, "big")) % 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001).to_bytes(32, "big")
+    aP = ctx.g1_mul(g1, a * 4)
+    bQ = ctx.g2_mul(g2, b * 4)
+    abP = ctx.g1_mul(g1, ab * 4)
+    abQ = ctx.g2_mul(g2, ab * 4)
+    x = ctx.pairing(aP, bQ)
+    assert x == ctx.pairing(abP, g2) == ctx.pairing(g1, abQ)
+
+
+def test_group_ops_vs_oracle(ctx, orc, B):
+    rng = random.Random(9)
+    g1, g2 = _points(ctx, orc, 24, 9)
+    sc = b"".join(rng.randrange(1 << 254).to_bytes(32, "big") for _ in range(24))
+    sc = (0).to_bytes(32, "big") + (1).to_bytes(32, "big") + sc[64:]
+    assert ctx.g1_mul(g1, sc) == orc.g1_mul(g1, sc, nthreads=8)
+    assert ctx.g2_mul(g2, sc) == orc.g2_mul(g2, sc, nthreads=8)
+    assert ctx.g1_sum(g1) == orc.g1_sum(g1)
+    assert ctx.g2_sum(g2) == orc.g2_sum(g2)
+    assert ctx.g1_sum(g1[:64]) == g1[:64]
+    # 2*2*G + G == 5*G (g1.rs:1143-1149, g2.rs:1030-1036)
+    five = (5).to_bytes(32, "big")
+    four = (4).to_bytes(32, "big")
+    assert ctx.g1_sum(ctx.g1_mul(B.G1_GENERATOR, four) + B.G1_GENERATOR) == ctx.g1_mul(B.G1_GENERATOR, five)
+    assert ctx.g2_sum(ctx.g2_mul(B.G2_GENERATOR, four) + B.G2_GENERATOR) == ctx.g2_mul(B.G2_GENERATOR, five)
+
+
+def test_codecs_vs_oracle(ctx, orc, B):
+    g1, g2 = _points(ctx, orc, 50, 13)
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    g1 = B.G1_GENERATOR + ident1 + g1
+    g2 = B.G2_GENERATOR + g2
+    c1, c2 = ctx.g1_compress(g1), ctx.g2_compress(g2)
+    assert c1 == orc.g1_compress(g1)
+    assert c2 == orc.g2_compress(g2)
+    assert c1[32:64] == b"\x80" + bytes(31)  # identity (g1.rs:265-288)
+    d1, s1 = ctx.g1_decompress(c1)
+    assert (d1, s1) == orc.g1_decompress(c1)
+    assert d1 == g1
+    d2, s2 = ctx.g2_decompress(c2)
+    assert (d2, s2) == orc.g2_decompress(c2)
+    assert d2 == g2
+    # x with no point on the curve / non-canonical x
+    junk = b"".join((i + 5).to_bytes(32, "big") for i in range(20)) + b"\x7f" + b"\xff" * 31
+    assert ctx.g1_decompress(junk) == orc.g1_decompress(junk)
+    junk2 = b"".join((i + 5).to_bytes(64, "big") for i in range(12))
+    assert ctx.g2_decompress(junk2) == orc.g2_decompress(junk2)
+    off = bytearray(g1[:64 * 6])
+    off[70] ^= 1
+    assert ctx.g1_is_on_curve(bytes(off)) == orc.g1_is_on_curve(bytes(off))
+    off2 = bytearray(g2[:128 * 5])
+    off2[300] ^= 1
+    assert ctx.g2_is_on_curve(bytes(off2)) == orc.g2_is_on_curve(bytes(off2))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_verify_vs_oracle(ctx, orc, B, variant):
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, 96, variant=variant, corrupt_every=8)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    # add an undecodable key and an identity signature
+    pks = pks + b"\xff" * rpk + pks[:rpk]
+    ident = ((0).to_bytes(32, "big") + (1).to_bytes(32, "big")) if rsig == 64 else (bytes(64) + bytes(63) + b"\x01")
+    sigs = sigs + sigs[:rsig] + ident
+    msgs = msgs + [b"extra-1", b""]
+    got = ctx.verify_batch(variant, pks, msgs, sigs, dst)
+    ref = orc.verify_batch(variant, pks, msgs, sigs, dst, nthreads=8)
+    assert got == ref
+    assert got[:96] == exp
+    assert 0 < sum(exp) < 96
+    # on-curve flag
+    bad = bytearray(sigs)
+    bad[rsig - 1] ^= 1
+    got = ctx.verify_batch(variant, pks, msgs, bytes(bad), dst, flags=B.CHECK_ON_CURVE)
+    assert got == orc.verify_batch(variant, pks, msgs, bytes(bad), dst, flags=1, nthreads=8)
+    assert got[0] == 0
+    assert ctx.verify_batch(variant, b"", [], b"", dst) == b""
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_aggregate_verify(ctx, orc, B, variant):
+    n = 50
+    pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=variant, corrupt_every=0)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    agg = B.scheme.aggregate(ctx, sigs, variant)
+    assert agg == (orc.g1_sum(sigs) if variant == 0 else orc.g2_sum(sigs))
+    assert ctx.aggregate_verify(variant, pks, msgs, agg, dst) == 1 == orc.aggregate_verify(variant, pks, msgs, agg, dst, nthreads=8)
+    msgs2 = list(msgs)
+    msgs2[17] = b"tampered"
+    assert ctx.aggregate_verify(variant, pks, msgs2, agg, dst) == 0 == orc.aggregate_verify(variant, pks, msgs2, agg, dst, nthreads=8)
+    # sharded: three partial products + one finish == the single call; partial product == oracle's Miller product
+    rpk = 128 if variant == 0 else 64
+    cuts = [0, 13, 31, n]
+    parts, bads = b"", []
+    for s in range(3):
+        lo, hi = cuts[s], cuts[s + 1]
+        p, b = ctx.aggregate_partial(variant, pks[lo * rpk:hi * rpk], msgs[lo:hi], agg if s == 1 else None, dst)
+        parts += p
+        bads.append(b)
+    assert bads == [0, 0, 0]
+    assert ctx.aggregate_finish(parts, bads) == 1
+    assert ctx.aggregate_finish(parts, [0, 1, 0]) == 0
+    assert ctx.aggregate_finish(parts[:768], [0, 0]) == 0
+    # a bad key anywhere rejects
+    badpk = b"\xff" * rpk + pks[rpk:]
+    assert ctx.aggregate_verify(variant, badpk, msgs, agg, dst) == 0
+
+
+def test_verify_full_size_property(ctx, orc, B):
+    """BASELINE config 2 size (2^16 tuples, min-sig): accept bits must equal the construction; a 96-tuple
+    sample is re-checked against the oracle."""
+    n = 1 << 16
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=0, n_keys=256)
+    got = ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG)
+    assert got == exp
+    assert sum(exp) == n - n // 64
+    lo = 4000
+    sl = slice(lo, lo + 96)
+    ref = orc.verify_batch(0, pks[lo * 128:(lo + 96) * 128], msgs[sl], sigs[lo * 64:(lo + 96) * 64], B.DST_MIN_SIG, nthreads=8)
+    assert got[sl] == ref
+
+
+def test_hash_full_size_property(ctx, orc):
+    """BASELINE config 3 shape at 2^17 messages: a sample against the oracle, and equal messages hash
+    equally wherever they sit in the batch (chunk / offset handling)."""
+    n = 1 << 17
+    rng = random.Random(21)
+    base = [rng.randbytes(32) for _ in range(1024)]
+    msgs = [base[i % 1024] for i in range(n)]
+    out = ctx.hash_to_g1(msgs, QUUX_G1)
+    ref = orc.hash_to_g1(base, QUUX_G1, nthreads=8)
+    assert out[:64 * 1024] == ref
+    assert out[-64 * 1024:] == ref
+    mid = (n // 2 // 1024) * 1024
+    assert out[64 * mid:64 * (mid + 1024)] == ref
+
+
+def test_multi_device_ctx(orc, B):
+    import ctypes
+    nd = B._native.lib().bn254_device_count() if hasattr(B, "_native") else 1
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c1 = B.Context([0])
+    c2 = B.Context([0, 1])
+    try:
+        pks, msgs, sigs, exp = B.scheme.synth_batch(c1, 700, variant=0, n_keys=16)
+        assert c2.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG) == exp
+        agg = B.scheme.aggregate(c1, sigs, 0)
+        pks2, msgs2, sigs2, _ = B.scheme.synth_batch(c1, 300, variant=0, corrupt_every=0, n_keys=16)
+        agg = B.scheme.aggregate(c1, sigs2, 0)
+        assert c2.aggregate_verify(0, pks2, msgs2, agg, B.DST_MIN_SIG) == 1
+        assert c2.hash_to_g1(msgs, QUUX_G1) == c1.hash_to_g1(msgs, QUUX_G1)
+    finally:
+        c1.close()
+        c2.close()

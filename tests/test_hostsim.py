@@ -1,0 +1,154 @@
+"""CPU suite for the DEVICE code: tests/hostsim compiles bls_bn254_b200/csrc/*.cuh with g++ (carry
+chains emulated in C) and the very per-item bodies the CUDA kernels run are compared with the oracle
+and the reference's golden vectors.  Test infrastructure only: the product never links this build."""
+import ctypes as C
+import pathlib
+import random
+import subprocess
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+P = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+QUUX_G1 = b"QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_"
+QUUX_G2 = b"QUUX-V01-CS02-with-BN254G2_XMD:SHA-256_SVDW_RO_"
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "tests" / "hostsim")])
+    return C.CDLL(str(ROOT / "tests" / "hostsim" / "libhostsim.so"))
+
+
+def _w(x):
+    return (C.c_uint32 * 8)(*[(x >> (32 * i)) & 0xffffffff for i in range(8)])
+
+
+def _r(a):
+    return sum(int(a[i]) << (32 * i) for i in range(8))
+
+
+def test_fp_arithmetic(sim):
+    rng = random.Random(1)
+    ri = pow(1 << 256, -1, P)
+    vals = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 1 << 253, (1 << 253) - 1, 0xffffffff, 0xffffffff << 224 & (P - 1)] + [rng.randrange(P) for _ in range(400)]
+    for _ in range(4000):
+        a, b = rng.choice(vals), rng.choice(vals)
+        o = (C.c_uint32 * 8)()
+        sim.sim_fp_mul(o, _w(a), _w(b))
+        assert _r(o) == a * b * ri % P
+        sim.sim_fp_add(o, _w(a), _w(b))
+        assert _r(o) == (a + b) % P
+        sim.sim_fp_sub(o, _w(a), _w(b))
+        assert _r(o) == (a - b) % P
+
+
+def test_fp2_sqrt(sim):
+    from oracle import pymodel as pm
+    rng = random.Random(2)
+    cases = [(0, 0), (4, 0), (P - 4, 0), (0, 9), (3, 0), (P - 3, 0)]
+    for _ in range(60):
+        x = (rng.randrange(P), rng.randrange(P))
+        cases.append(pm.f2_sqr(x))
+        cases.append(x)
+    for a in cases:
+        out = C.create_string_buffer(64)
+        ok = sim.sim_fp2_sqrt(out, a[0].to_bytes(32, "big") + a[1].to_bytes(32, "big"))
+        assert bool(ok) == pm.f2_is_square(a) or a == (0, 0)
+        if ok:
+            r = (int.from_bytes(out.raw[:32], "big"), int.from_bytes(out.raw[32:], "big"))
+            assert pm.f2_sqr(r) == a
+
+
+def _hash(sim, fn, rec, msgs, dst, count, orc):
+    blob, off = orc.pack_msgs(msgs)
+    out, st = C.create_string_buffer(rec * len(msgs)), C.create_string_buffer(len(msgs))
+    fn(blob, off, C.c_size_t(len(msgs)), dst, C.c_size_t(len(dst)), count, out, st)
+    return out.raw, st.raw
+
+
+def test_hash_kats_and_oracle(sim, orc, kats):
+    for suite, count in (("g1_encode", 1), ("g1_hash", 2)):
+        dst = kats[suite + "_dst"].encode()
+        msgs = [v["msg"].encode("latin1") for v in kats[suite]]
+        out, st = _hash(sim, sim.sim_hash_to_g1, 64, msgs, dst, count, orc)
+        for i, v in enumerate(kats[suite]):
+            assert out[64 * i:64 * i + 64] == H(v["p_x"]) + H(v["p_y"])
+    for suite, count in (("g2_encode", 1), ("g2_hash", 2)):
+        dst = kats[suite + "_dst"].encode()
+        msgs = [v["msg"].encode("latin1") for v in kats[suite]]
+        out, st = _hash(sim, sim.sim_hash_to_g2, 128, msgs, dst, count, orc)
+        for i, v in enumerate(kats[suite]):
+            assert out[128 * i:128 * i + 128] == H(v["x_c1"]) + H(v["x_c0"]) + H(v["y_c1"]) + H(v["y_c0"])
+    rng = random.Random(3)
+    msgs = [rng.randbytes(rng.randrange(0, 150)) for _ in range(40)]
+    for dst in (QUUX_G1, b"", b"d" * 255):
+        assert _hash(sim, sim.sim_hash_to_g1, 64, msgs, dst, 2, orc)[0] == orc.hash_to_g1(msgs, dst)
+    assert _hash(sim, sim.sim_hash_to_g2, 128, msgs[:12], QUUX_G2, 2, orc)[0] == orc.hash_to_g2(msgs[:12], QUUX_G2)
+    for dst in (b"short", b"L" * 256, b"L" * 1000):
+        out = C.create_string_buffer(96)
+        sim.sim_expand_message_xmd(b"msg", C.c_size_t(3), dst, C.c_size_t(len(dst)), out, C.c_size_t(96))
+        assert out.raw == orc.expand_message_xmd(b"msg", dst, 96)
+
+
+def test_pairing_vs_oracle(sim, orc, kats):
+    rng = random.Random(4)
+    msgs = [rng.randbytes(8) for _ in range(4)]
+    g1 = orc.g1_generator() + orc.hash_to_g1(msgs, QUUX_G1)
+    g2 = orc.g2_generator() + orc.hash_to_g2(msgs, QUUX_G2)
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    g1 += ident1 + b"\xff" * 64
+    g2 += g2[:128] * 2
+    n = len(g1) // 64
+    for mode in (1, 0):
+        out, st = C.create_string_buffer(384 * n), C.create_string_buffer(n)
+        sim.sim_pairing_batch(g1, g2, C.c_size_t(n), out, st, mode)
+        ref, rst = (orc.pairing_batch(g1, g2, want_status=True) if mode == 0 else (orc.miller_loop_batch(g1, g2), None))
+        assert out.raw == ref
+        if rst is not None:
+            assert st.raw == rst
+        if mode == 0:
+            assert out.raw[:384] == b"".join(H(x) for x in kats["gt_generator"])  # pairings.rs:970-980
+    ml = orc.miller_loop_batch(g1[:192], g2[:384])
+    out = C.create_string_buffer(len(ml))
+    sim.sim_final_exp(ml, C.c_size_t(3), out)
+    assert out.raw == orc.final_exponentiation(ml)
+
+
+def test_two_pair_miller_loops(sim, orc):
+    """shared-squaring 2-pair loops: variable/variable and (P0, -g2) through the precomputed line table"""
+    rng = random.Random(5)
+    msgs = [rng.randbytes(8) for _ in range(2)]
+    g1 = orc.hash_to_g1(msgs, QUUX_G1)
+    g2 = orc.hash_to_g2(msgs, QUUX_G2)
+    out = C.create_string_buffer(384)
+    sim.sim_miller2(g1[:64], g2[:128], g1[64:], g2[128:], 0, out)
+    assert out.raw == orc.multi_miller_loop(g1, g2)
+    gen = orc.g2_generator()
+    neg = gen[:64] + ((P - int.from_bytes(gen[64:96], "big")) % P).to_bytes(32, "big") + ((P - int.from_bytes(gen[96:], "big")) % P).to_bytes(32, "big")
+    sim.sim_miller2(g1[:64], None, g1[64:], g2[128:], 1, out)
+    assert out.raw == orc.multi_miller_loop(g1, neg + g2[128:])
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    sim.sim_miller2(ident1, None, g1[64:], g2[128:], 1, out)
+    assert out.raw == orc.multi_miller_loop(ident1 + g1[64:], neg + g2[128:]) == orc.miller_loop_batch(g1[64:], g2[128:])
+
+
+def test_scalar_mul_and_codecs(sim, orc):
+    rng = random.Random(6)
+    msgs = [rng.randbytes(8) for _ in range(6)]
+    g1 = orc.g1_generator() + orc.hash_to_g1(msgs, QUUX_G1)
+    g2 = orc.g2_generator() + orc.hash_to_g2(msgs, QUUX_G2)
+    n = 7
+    sc = (0).to_bytes(32, "big") + (1).to_bytes(32, "big") + b"".join(rng.randrange(1 << 255).to_bytes(32, "big") for _ in range(n - 2))
+    o1, o2 = C.create_string_buffer(64 * n), C.create_string_buffer(128 * n)
+    sim.sim_g1_mul(g1, sc, C.c_size_t(n), o1)
+    sim.sim_g2_mul(g2, sc, C.c_size_t(n), o2)
+    assert o1.raw == orc.g1_mul(g1, sc)
+    assert o2.raw == orc.g2_mul(g2, sc)
+    comp, back, st = C.create_string_buffer(32 * n), C.create_string_buffer(64 * n), C.create_string_buffer(n)
+    sim.sim_g1_codec(g1, C.c_size_t(n), comp, back, st)
+    assert comp.raw == orc.g1_compress(g1) and back.raw == g1 and st.raw == b"\x01" * n
+    comp, back = C.create_string_buffer(64 * n), C.create_string_buffer(128 * n)
+    sim.sim_g2_codec(g2, C.c_size_t(n), comp, back, st)
+    assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
