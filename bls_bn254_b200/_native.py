@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = pathlib.Path(__file__).resolve().parent
 ROOT = _HERE.parent
-SO = _HERE / "libbls_bn254_b200.so"
+SO = pathlib.Path(os.environ.get("BN254_SO", str(_HERE / "libbls_bn254_b200.so")))  # BN254_SO: tuning builds
 SRC = _HERE / "csrc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC"]
 

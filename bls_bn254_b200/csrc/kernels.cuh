@@ -11,7 +11,12 @@ namespace bn {
 // point, temporaries) in registers + per-thread local memory; 128-thread blocks give the
 // scheduler 4 warps per CTA and let several CTAs share an SM.
 #define BN_TPB_LIGHT 128
-#define BN_TPB_HEAVY 128
+#ifndef BN_TPB_HEAVY
+#define BN_TPB_HEAVY 64
+#endif
+#ifndef BN_MINB_HEAVY
+#define BN_MINB_HEAVY 8
+#endif
 
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_decode(g1m *out, uint8_t *fl, const uint8_t *in, size_t n, int check) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_on_curve(uint8_t *out, cons
 
 // hash / encode to curve.  offsets are global offsets into the blob; `base` is the blob offset of
 // msgs[0] of this chunk.
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_hash_g1(g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_hash_g1(g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                                                            size_t n, const uint8_t *dst, uint32_t dst_len, int count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_hash_g1(g1m *out, uint8_t *fl,
     out[i] = p;
     fl[i] = f;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                                                            size_t n, const uint8_t *dst, uint32_t dst_len, int count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -88,7 +93,7 @@ __global__ void k_oversize_dst(uint8_t *out, const uint8_t *dst, size_t dst_len)
 }
 
 // Miller loops.  `bad` (optional) receives an atomic OR when an item carries FL_BAD.
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller1(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller1(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
                                                            const uint8_t *flQ, size_t n, int *bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller1(fp12 *F, uint8_t *flF,
     if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
 }
 // pair 0 = (P0[i], -g2) via the precomputed line table; pair 1 = (P1[i], Q1[i])
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller2_fixed(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2_fixed(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
                                                                  const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller2_fixed(fp12 *F, uint8_t
     flF[i] = fl;
 }
 // both pairs variable.  p0_stride = 0 broadcasts one P0 (min-pk: -g1) to every item.
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride,
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride,
                                                            const g2m *Q0, const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1,
                                                            const g2m *Q1, const uint8_t *flQ1, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_miller2(fp12 *F, uint8_t *flF,
     F[i] = f;
     flF[i] = fl;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_final_exp(fp12 *F, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_final_exp(fp12 *F, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp12 f = F[i];
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_fp12_is_one(uint8_t *ok, const
     ok[i] = (!(f & FL_BAD) && fp12_is_one(F[i])) ? 1 : 0;
 }
 // out[t] = in[t] * in[t+m] * in[t+2m] * ...   (MillerLoopResult + MillerLoopResult, pairings.rs:37-43)
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_fp12_reduce(fp12 *out, const fp12 *in, size_t n, size_t m) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_fp12_reduce(fp12 *out, const fp12 *in, size_t n, size_t m) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     fp12 acc;
@@ -180,7 +185,7 @@ __global__ void k_finish_ok(uint8_t *ok, const fp12 *F, const int *bad) {
 }
 
 // scalar multiplication / sums
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g1_mul(g1m *out, uint8_t *flo, const g1m *P, const uint8_t *fl, const uint8_t *sc, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_mul(g1m *out, uint8_t *flo, const g1m *P, const uint8_t *fl, const uint8_t *sc, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1m r;
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_g1_mul(g1m *out, uint8_t *flo,
     out[i] = r;
     flo[i] = f;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g2_mul(g2m *out, uint8_t *flo, const g2m *P, const uint8_t *fl, const uint8_t *sc, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_mul(g2m *out, uint8_t *flo, const g2m *P, const uint8_t *fl, const uint8_t *sc, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2m r;
@@ -216,11 +221,11 @@ __device__ void sum_strided(M *out, uint8_t *flo, const M *in, const uint8_t *fl
     out[t] = r;
     flo[t] = bad ? FL_BAD : (inf ? FL_INF : 0);
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g1_sum(g1m *out, uint8_t *flo, const g1m *in, const uint8_t *fl, size_t n, size_t m) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_sum(g1m *out, uint8_t *flo, const g1m *in, const uint8_t *fl, size_t n, size_t m) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < m) sum_strided<F1, g1m>(out, flo, in, fl, n, m, t);
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g2_sum(g2m *out, uint8_t *flo, const g2m *in, const uint8_t *fl, size_t n, size_t m) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_sum(g2m *out, uint8_t *flo, const g2m *in, const uint8_t *fl, size_t n, size_t m) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < m) sum_strided<F2, g2m>(out, flo, in, fl, n, m, t);
 }
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_compress(uint8_t *out, cons
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) item_g2_compress(out + 64 * i, P[i], fl[i]);
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g1_decompress(g1m *out, uint8_t *fl, const uint8_t *in, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_decompress(g1m *out, uint8_t *fl, const uint8_t *in, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1m p;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY) k_g1_decompress(g1m *out, uint8_
     out[i] = p;
     fl[i] = f;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY) k_g2_decompress(g2m *out, uint8_t *fl, const uint8_t *in, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_decompress(g2m *out, uint8_t *fl, const uint8_t *in, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2m p;

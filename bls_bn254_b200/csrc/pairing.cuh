@@ -152,13 +152,27 @@ BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const
 }
 
 // f^x (x = 0x44e992b44a6909f1, 63 bits) in the cyclotomic subgroup, then conjugate
-// (pairings.rs:117-134 role)
+// (pairings.rs:117-134 role).  Width-4 signed window over f, f^3, f^5, f^7 (a negative digit uses the
+// conjugate, which is the inverse here): 63 cyclotomic squarings + 16 products instead of 62 + 27.
 BN_NOINL void cyclotomic_exp_neg_x(fp12 &r, const fp12 &f) {
-    fp12 t = f;
+    fp12 pw[4], t;
+    pw[0] = f;
+    cyclotomic_square(t, f);
+    fp12_mul(pw[1], pw[0], t);
+    fp12_mul(pw[2], pw[1], t);
+    fp12_mul(pw[3], pw[2], t);
+    t = pw[(k::X_WNAF4[0] - 1) >> 1];
 #pragma unroll 1
-    for (int i = 61; i >= 0; i--) {
+    for (int i = 1; i < BN254_X_WNAF_LEN; i++) {
         cyclotomic_square(t, t);
-        if ((BN254_X >> i) & 1) fp12_mul(t, t, f);
+        int d = k::X_WNAF4[i];
+        if (d > 0) {
+            fp12_mul(t, t, pw[(d - 1) >> 1]);
+        } else if (d < 0) {
+            fp12 c;
+            fp12_conj(c, pw[(-d - 1) >> 1]);
+            fp12_mul(t, t, c);
+        }
     }
     fp12_conj(r, t);
 }

@@ -22,14 +22,57 @@ BN_INL void fp2_set_zero(fp2 &r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
 BN_INL void fp2_set_one(fp2 &r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
 BN_INL bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 BN_INL bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
-BN_INL void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
-BN_INL void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
-BN_INL void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
-BN_INL void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
-BN_INL void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
+// The light Fp2 operations are out-of-line too (BN_LIGHT): the tower code above them is then a
+// sequence of calls on pointers into the thread's local memory, a few KB per Fp12 routine.
+#ifndef BN_INLINE_LIGHT
+#define BN_LIGHT BN_NOINL
+#else
+#define BN_LIGHT BN_INL
+#endif
+// BN_INLINE_FP2: the Fp2 products are inlined as well (their Fp products stay by-value calls), which
+// makes the Fp6-level routines the leaves: their intermediates live in registers instead of being
+// passed through local memory between many tiny functions.
+#ifndef BN_INLINE_FP2
+#define BN_FP2MUL BN_NOINL
+#else
+#define BN_FP2MUL BN_INL
+#endif
+BN_LIGHT void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+BN_LIGHT void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+BN_LIGHT void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+BN_LIGHT void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+BN_LIGHT void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
 BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
 
-// fp2.rs:377-390 (there: 4 products); Karatsuba, 3 products
+// fp2.rs:377-390 (there: 4 products).  Karatsuba with lazy reduction: three 512-bit products, the
+// cross terms combined as integers, two Montgomery reductions.
+//   c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1   (= a0 b1 + a1 b0 >= 0, < 2p^2 < p*2^256)
+//   c0 = a0 b0 - a1 b1                     (+ p*2^256 when negative, so 0 <= . < p*2^256)
+#ifdef BN_FP2_LAZY  // measured slower on B200 in round 1 (the kernels are latency-, not IMAD-bound): off by default
+BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
+    fp sa, sb;
+    (void)add_n(sa.v, a.c0.v, a.c1.v);  // < 2p < 2^255: no reduction needed as a wide-product operand
+    (void)add_n(sb.v, b.c0.v, b.c1.v);
+    fpw w0 = fp_mul_wide_v(a.c0, b.c0);
+    fpw w1 = fp_mul_wide_v(a.c1, b.c1);
+    fpw w2 = fp_mul_wide_v(sa, sb);
+    (void)fpw_sub(w2, w2, w0);
+    (void)fpw_sub(w2, w2, w1);
+    uint32_t neg = fpw_sub(w0, w0, w1);
+    add_p_masked(w0.v + 8, neg);
+    r.c0 = fp_redc_v(w0);
+    r.c1 = fp_redc_v(w2);
+}
+#elif !defined(BN_FP2_KARATSUBA)
+// c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0: two fused dot products (fp_dot2), no Karatsuba additions
+BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
+    fp nb1, c0;
+    fp_neg(nb1, b.c1);
+    fp_dot2(c0, a.c0, b.c0, a.c1, nb1);
+    fp_dot2(r.c1, a.c0, b.c1, a.c1, b.c0);
+    r.c0 = c0;
+}
+#else
 BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp t0, t1, s, t;
     fp_mul(t0, a.c0, b.c0);
@@ -41,8 +84,9 @@ BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp_sub(r.c1, s, t1);
     fp_sub(r.c0, t0, t1);
 }
+#endif
 // fp2.rs:392-402
-BN_NOINL void fp2_sqr(fp2 &r, const fp2 &a) {
+BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
     fp s, d, m;
     fp_add(s, a.c0, a.c1);
     fp_sub(d, a.c0, a.c1);
@@ -50,9 +94,9 @@ BN_NOINL void fp2_sqr(fp2 &r, const fp2 &a) {
     fp_mul(r.c0, s, d);
     fp_dbl(r.c1, m);
 }
-BN_NOINL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
+BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
-BN_INL void fp2_mul_xi(fp2 &r, const fp2 &a) {
+BN_LIGHT void fp2_mul_xi(fp2 &r, const fp2 &a) {
     fp t0, t1;
     fp_mul9(t0, a.c0);
     fp_mul9(t1, a.c1);
