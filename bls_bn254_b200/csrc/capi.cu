@@ -105,6 +105,26 @@ inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1)
         }                                                                        \
     } while (0)
 
+// Pairing kernels: BN_LANES == 1 (default) runs one thread per pairing; 2 runs two lanes per pairing
+// (lane-split Fp2, tower.cuh) -- bit-identical, measured ~7 % slower on B200 in round 1 because its
+// larger code thrashes the instruction cache at the occupancy it needs (profiles/r01_notes.md).
+#ifndef BN_LANES
+#define BN_LANES 1
+#endif
+#if BN_LANES == 2
+#define K_MILLER1 k_miller1_l2
+#define K_MILLER2_FIXED k_miller2_fixed_l2
+#define K_MILLER2 k_miller2_l2
+#define K_FINAL_EXP k_final_exp_l2
+#define PAIR_THREADS(n) (2 * (size_t)(n))
+#else
+#define K_MILLER1 k_miller1
+#define K_MILLER2_FIXED k_miller2_fixed
+#define K_MILLER2 k_miller2
+#define K_FINAL_EXP k_final_exp
+#define PAIR_THREADS(n) ((size_t)(n))
+#endif
+
 // ---- device-level building blocks (all pointers are device pointers on d) ------------------------
 
 // DST: copies / pre-hashes into scratch when needed.  `dst_on_host` tells where dst lives.
@@ -168,8 +188,8 @@ int dev_pairing(Dev &d, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t 
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, g1, n, 0);
     LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, g2, n, 0);
-    LAUNCH(d, k_miller1, n, BN_TPB_HEAVY, F, flf, P, flp, Q, flq, n, (int *)nullptr);
-    if (mode == 0) LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, K_MILLER1, PAIR_THREADS(n), BN_TPB_HEAVY, F, flf, P, flp, Q, flq, n, (int *)nullptr);
+    if (mode == 0) LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, F, n);
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -179,7 +199,7 @@ int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *st
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
     LAUNCH(d, k_fp12_decode, n, BN_TPB_LIGHT, F, flf, ml, n);
-    LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, F, n);
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -240,7 +260,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flp0, sigs, n, check);
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q1, flq1, pks, n, check);
         if (int rc = dev_hash_g1(d, P1, flp1, msgs, off, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH(d, k_miller2_fixed, n, BN_TPB_HEAVY, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
+        LAUNCH(d, K_MILLER2_FIXED, PAIR_THREADS(n), BN_TPB_HEAVY, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
     } else {
         g1m *P1; g2m *Q0, *Q1; uint8_t *flq0, *flp1, *flq1;
         if (int rc = ensure_t(d, S_P1, n, &P1)) return rc;
@@ -255,9 +275,9 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q0, flq0, sigs, n, check);
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
         if (int rc = dev_hash_g2(d, Q1, flq1, msgs, off, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH(d, k_miller2, n, BN_TPB_HEAVY, F, flf, ng1, flc, (size_t)0, Q0, flq0, P1, flp1, Q1, flq1, n);
+        LAUNCH(d, K_MILLER2, PAIR_THREADS(n), BN_TPB_HEAVY, F, flf, ng1, flc, (size_t)0, Q0, flq0, P1, flp1, Q1, flq1, n);
     }
-    LAUNCH(d, k_final_exp, n, BN_TPB_HEAVY, F, n);
+    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, F, n);
     LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok, F, flf, n);
     return 0;
 }
@@ -297,7 +317,7 @@ int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t
             CK(d, cudaMemsetAsync(flp + n, 0, 1, d.st));
         }
     }
-    LAUNCH(d, k_miller1, tot, BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
+    LAUNCH(d, K_MILLER1, PAIR_THREADS(tot), BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, tot, &res)) return rc;
     LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, partial, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
@@ -317,7 +337,7 @@ int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, si
     LAUNCH(d, k_or_bytes, kparts, BN_TPB_LIGHT, dbad, bad, kparts);
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, kparts, &res)) return rc;
-    LAUNCH(d, k_final_exp, 1, BN_TPB_HEAVY, res, (size_t)1);
+    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(1), BN_TPB_HEAVY, res, (size_t)1);
     LAUNCH(d, k_finish_ok, 1, 32, ok, res, dbad);
     return 0;
 }
@@ -627,7 +647,7 @@ int bn254_multi_miller_loop(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, db, n, 0);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad, flp, n);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad + 1, flq, n);
-        LAUNCH(d, k_miller1, n, BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
+        LAUNCH(d, K_MILLER1, PAIR_THREADS(n), BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
         fp12 *res;
         if (int rc = dev_fp12_product(d, F, n, &res)) return rc;
         LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);

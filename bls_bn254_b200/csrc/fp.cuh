@@ -622,20 +622,39 @@ BN_NOINL void fp_pow(fp &r, const fp &a, const uint32_t (&e)[8]) {
     }
     r = acc;
 }
-BN_INL void fp_inv(fp &r, const fp &a) { fp_pow(r, a, k::EXP_P_MINUS_2); }  // fp.rs:207-210; 0 -> 0
-BN_INL bool fp_is_square(const fp &a) {                                     // fp.rs:428-431
+// a^e for one of the fixed exponents, width-4 sliding window over the odd powers a, a^3, ..., a^15:
+// ~250 squarings + ~59 products instead of 255 + ~127.  dig[pos] is the (odd) window value whose
+// lowest bit sits at bit pos; the tables are generated (tools/gen_constants.py).
+BN_NOINL void fp_pow_sw(fp &r, const fp &a, const uint8_t *dig, int top) {
+    fp tbl[8], a2, acc;
+    tbl[0] = a;
+    fp_mul(a2, a, a);
+#pragma unroll 1
+    for (int i = 1; i < 8; i++) fp_mul(tbl[i], tbl[i - 1], a2);
+    acc = tbl[(dig[top] - 1) >> 1];
+#pragma unroll 1
+    for (int pos = top - 1; pos >= 0; pos--) {
+        fp_mul(acc, acc, acc);
+        int d = dig[pos];
+        if (d) fp_mul(acc, acc, tbl[(d - 1) >> 1]);
+    }
+    r = acc;
+}
+BN_INL void fp_inv(fp &r, const fp &a) { fp_pow_sw(r, a, k::SW_P_MINUS_2, BN254_SW_P_MINUS_2_TOP); }  // fp.rs:207-210; 0 -> 0
+BN_INL bool fp_is_square(const fp &a) {                                                                // fp.rs:428-431
     fp t;
-    fp_pow(t, a, k::EXP_P_MINUS_1_DIV_2);
+    fp_pow_sw(t, a, k::SW_P_MINUS_1_DIV_2, BN254_SW_P_MINUS_1_DIV_2_TOP);
     return fp_is_zero(t) || fp_eq(t, kfp(k::ONE));
 }
 // candidate root a^((p+1)/4) (fp.rs:212-243 with v = 1); returns whether it squares to a
 BN_INL bool fp_sqrt(fp &r, const fp &a) {
     fp y, t;
-    fp_pow(y, a, k::EXP_P_PLUS_1_DIV_4);
+    fp_pow_sw(y, a, k::SW_P_PLUS_1_DIV_4, BN254_SW_P_PLUS_1_DIV_4_TOP);
     fp_mul(t, y, y);
     r = y;
     return fp_eq(t, a);
 }
+BN_INL void fp_pow_p_minus_3_div_4(fp &r, const fp &a) { fp_pow_sw(r, a, k::SW_P_MINUS_3_DIV_4, BN254_SW_P_MINUS_3_DIV_4_TOP); }
 
 // Montgomery <-> canonical
 // (the multiplicand scanned row-wise -- second argument -- may be any 256-bit value; the first must be < p)

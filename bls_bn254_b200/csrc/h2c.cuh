@@ -139,10 +139,12 @@ BN_INL void oversize_dst(uint8_t out[32], const uint8_t *dst, size_t dst_len) {
 }
 
 // --------------------------------------------------------------------------------- SvdW maps
-// fp.rs:284-371 (Z = 1, c1 = g(Z) = 4).  Returns false where the reference panics
-// (tv1*tv2 == 0, i.e. u = +-1/2; fp.rs:325).
-BN_NOINL bool svdw_g1(g1a &out, const fp &u) {
-    fp tv1, tv2, tv3, tv4, x1, x2, x3, gx1, gx2, gx, x, y;
+// fp.rs:284-371 (Z = 1, c1 = g(Z) = 4), split in two so that the inversions of both maps of a
+// hash (and only those) share ONE field inversion (Montgomery's trick, 3 extra products):
+//   svdw_g1_pre : tv1 = 1 - 4u^2, tv2 = 1 + 4u^2, tv3 = tv1 tv2     (the value to invert)
+//   svdw_g1_post: everything after tv3 = inv0(tv1 tv2)
+// Returns false where the reference panics (tv1*tv2 == 0, i.e. u = +-1/2; fp.rs:325).
+BN_INL void svdw_g1_pre(fp &tv1, fp &tv2, fp &tv3, const fp &u) {
     const fp &one = kfp(k::ONE);
     fp_mulx(tv1, u, u);
     fp_dbl(tv1, tv1);
@@ -150,8 +152,11 @@ BN_NOINL bool svdw_g1(g1a &out, const fp &u) {
     fp_add(tv2, one, tv1);
     fp_sub(tv1, one, tv1);
     fp_mulx(tv3, tv1, tv2);
+}
+BN_NOINL bool svdw_g1_post(g1a &out, const fp &u, const fp &tv1, const fp &tv2, const fp &tv3 /* inverted */) {
+    fp tv4, x1, x2, x3, gx1, gx2, gx, x, y;
+    const fp &one = kfp(k::ONE);
     bool ok = !fp_is_zero(tv3);
-    fp_inv(tv3, tv3);
     fp_mulx(tv4, u, tv1);
     fp_mulx(tv4, tv4, tv3);
     fp_mulx(tv4, tv4, kfp(k::SVDW1_C3));
@@ -175,17 +180,26 @@ BN_NOINL bool svdw_g1(g1a &out, const fp &u) {
     out.inf = false;
     return ok;
 }
-// fp2.rs:221-287
-BN_NOINL bool svdw_g2(g2a &out, const fp2 &u) {
-    fp2 tv1, tv2, tv3, tv4, x1, x2, x3, gx1, gx2, gx, x, y, one;
+BN_INL bool svdw_g1(g1a &out, const fp &u) {
+    fp tv1, tv2, tv3;
+    svdw_g1_pre(tv1, tv2, tv3, u);
+    fp_inv(tv3, tv3);
+    return svdw_g1_post(out, u, tv1, tv2, tv3);
+}
+// fp2.rs:221-287, same split
+BN_INL void svdw_g2_pre(fp2 &tv1, fp2 &tv2, fp2 &tv3, const fp2 &u) {
+    fp2 one;
     fp2_set_one(one);
     fp2_sqr(tv1, u);
     fp2_mul(tv1, tv1, kfp2(k::SVDW2_C1));
     fp2_add(tv2, one, tv1);
     fp2_sub(tv1, one, tv1);
     fp2_mul(tv3, tv1, tv2);
+}
+BN_NOINL bool svdw_g2_post(g2a &out, const fp2 &u, const fp2 &tv1, const fp2 &tv2, const fp2 &tv3 /* inverted */) {
+    fp2 tv4, x1, x2, x3, gx1, gx2, gx, x, y, one;
+    fp2_set_one(one);
     bool ok = !fp2_is_zero(tv3);
-    fp2_inv(tv3, tv3);
     fp2_mul(tv4, u, tv1);
     fp2_mul(tv4, tv4, tv3);
     fp2_mul(tv4, tv4, kfp2(k::SVDW2_C3));
@@ -209,6 +223,12 @@ BN_NOINL bool svdw_g2(g2a &out, const fp2 &u) {
     out.inf = false;
     return ok;
 }
+BN_INL bool svdw_g2(g2a &out, const fp2 &u) {
+    fp2 tv1, tv2, tv3;
+    svdw_g2_pre(tv1, tv2, tv3, u);
+    fp2_inv(tv3, tv3);
+    return svdw_g2_post(out, u, tv1, tv2, tv3);
+}
 
 // hash (count = 2, g1.rs:910-919) / encode (count = 1, g1.rs:922-928).  False on the SvdW exception.
 BN_INL bool hash_to_g1(g1a &out, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len, int count) {
@@ -217,13 +237,24 @@ BN_INL bool hash_to_g1(g1a &out, const uint8_t *msg, size_t msg_len, const uint8
     g1a q0, q1;
     expand_message_xmd(okm, 48u * (uint32_t)count, msg, msg_len, dst, dst_len);
     fp_from_okm(u, okm);
-    bool ok = svdw_g1(q0, u);
     if (count == 1) {
+        bool ok1 = svdw_g1(q0, u);
         out = q0;
-        return ok;
+        return ok1;
     }
-    fp_from_okm(u, okm + 48);
-    ok &= svdw_g1(q1, u);
+    // both maps share one inversion: 1/a = b (ab)^-1, 1/b = a (ab)^-1 (a zero makes both "inverses"
+    // zero, and the item is reported as the SvdW exception, as for a single zero)
+    fp u1, a1, a2, a3, b1, b2, b3, t;
+    fp_from_okm(u1, okm + 48);
+    svdw_g1_pre(a1, a2, a3, u);
+    svdw_g1_pre(b1, b2, b3, u1);
+    fp_mulx(t, a3, b3);
+    fp_inv(t, t);
+    fp ia, ib;
+    fp_mulx(ia, t, b3);
+    fp_mulx(ib, t, a3);
+    bool ok = svdw_g1_post(q0, u, a1, a2, ia);
+    ok &= svdw_g1_post(q1, u1, b1, b2, ib);
     g1p a, b;
     pt_from_affine(a, q0.x, q0.y, false);
     pt_from_affine(b, q1.x, q1.y, false);
@@ -240,14 +271,25 @@ BN_INL bool hash_to_g2(g2a &out, const uint8_t *msg, size_t msg_len, const uint8
     expand_message_xmd(okm, 96u * (uint32_t)count, msg, msg_len, dst, dst_len);
     fp_from_okm(u.c0, okm);
     fp_from_okm(u.c1, okm + 48);
-    bool ok = svdw_g2(q, u);
-    pt_from_affine(a, q.x, q.y, false);
+    bool ok;
     if (count == 2) {
-        fp_from_okm(u.c0, okm + 96);
-        fp_from_okm(u.c1, okm + 144);
-        ok &= svdw_g2(q, u);
+        fp2 u1, a1, a2, a3, b1, b2, b3, t, ia, ib;
+        fp_from_okm(u1.c0, okm + 96);
+        fp_from_okm(u1.c1, okm + 144);
+        svdw_g2_pre(a1, a2, a3, u);
+        svdw_g2_pre(b1, b2, b3, u1);
+        fp2_mul(t, a3, b3);
+        fp2_inv(t, t);
+        fp2_mul(ia, t, b3);
+        fp2_mul(ib, t, a3);
+        ok = svdw_g2_post(q, u, a1, a2, ia);
+        pt_from_affine(a, q.x, q.y, false);
+        ok &= svdw_g2_post(q, u1, b1, b2, ib);
         pt_from_affine(b, q.x, q.y, false);
         pt_add(a, a, b);
+    } else {
+        ok = svdw_g2(q, u);
+        pt_from_affine(a, q.x, q.y, false);
     }
     g2_clear_cofactor(a, a);
     pt_to_affine(out.x, out.y, out.inf, a);

@@ -80,11 +80,9 @@ BN_INL void item_hash_g2(g2m &out, uint8_t &fl, const uint8_t *msg, size_t len, 
 // one pair (pairing(), pairings.rs:760-802 without the final exponentiation)
 BN_INL void item_miller1(fp12 &f, uint8_t &fl, const g1m &p, uint8_t flp, const g2m &q, uint8_t flq) {
     fp px[1] = {p.x}, py[1] = {p.y};
-    g2a qa[1];
-    qa[0].x = q.x;
-    qa[0].y = q.y;
+    fp2 qx[1] = {q.x}, qy[1] = {q.y};
     bool live[1] = {((flp | flq) & (FL_INF | FL_BAD)) == 0};
-    miller_loop<1, false>(f, px, py, qa, live);
+    miller_loop<1, false, fp2>(f, px, py, qx, qy, live);
     fl = ((flp | flq) & FL_BAD) ? FL_BAD : 0;
 }
 // two pairs, shared squaring; pair 0 is (p0, -g2) through the precomputed line table when FIXED0
@@ -92,22 +90,57 @@ template <bool FIXED0>
 BN_INL void item_miller2(fp12 &f, uint8_t &fl, const g1m &p0, uint8_t flp0, const g2m *q0, uint8_t flq0, const g1m &p1, uint8_t flp1,
                          const g2m &q1, uint8_t flq1) {
     fp px[2] = {p0.x, p1.x}, py[2] = {p0.y, p1.y};
-    g2a qa[2];
+    fp2 qx[2], qy[2];
     if (!FIXED0) {
-        qa[0].x = q0->x;
-        qa[0].y = q0->y;
+        qx[0] = q0->x;
+        qy[0] = q0->y;
     }
-    qa[1].x = q1.x;
-    qa[1].y = q1.y;
+    qx[1] = q1.x;
+    qy[1] = q1.y;
     bool live[2] = {((flp0 | flq0) & (FL_INF | FL_BAD)) == 0, ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0};
-    miller_loop<2, FIXED0>(f, px, py, qa, live);
+    miller_loop<2, FIXED0, fp2>(f, px, py, qx, qy, live);
     fl = ((flp0 | flq0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
 }
 
 // ---- final exponentiation / GT ---------------------------------------------------------------
-BN_INL void item_final_exp(fp12 &f) {
-    fp12 t = f;
-    final_exponentiation(f, t);
+BN_INL void item_final_exp(fp12 &f) { final_exponentiation(f); }
+
+// ---- the same bodies with TWO LANES per pairing (lane-split Fp2, tower.cuh).  Both lanes of a pair
+//      call these with identical arguments; `F` is the item's one-thread record in HBM and each lane
+//      reads / writes its own half of it. -------------------------------------------------------------
+BN_INL void item_miller1_l2(fp12 &F, uint8_t &fl, const g1m &p, uint8_t flp, const g2m &q, uint8_t flq) {
+    fp px[1] = {p.x}, py[1] = {p.y};
+    fp2l qx[1], qy[1];
+    fp2_load(qx[0], q.x);
+    fp2_load(qy[0], q.y);
+    bool live[1] = {((flp | flq) & (FL_INF | FL_BAD)) == 0};
+    fp12l f;
+    miller_loop<1, false, fp2l>(f, px, py, qx, qy, live);
+    fp12_store(F, f);
+    fl = ((flp | flq) & FL_BAD) ? FL_BAD : 0;
+}
+template <bool FIXED0>
+BN_INL void item_miller2_l2(fp12 &F, uint8_t &fl, const g1m &p0, uint8_t flp0, const g2m *q0, uint8_t flq0, const g1m &p1, uint8_t flp1,
+                            const g2m &q1, uint8_t flq1) {
+    fp px[2] = {p0.x, p1.x}, py[2] = {p0.y, p1.y};
+    fp2l qx[2], qy[2];
+    if (!FIXED0) {
+        fp2_load(qx[0], q0->x);
+        fp2_load(qy[0], q0->y);
+    }
+    fp2_load(qx[1], q1.x);
+    fp2_load(qy[1], q1.y);
+    bool live[2] = {((flp0 | flq0) & (FL_INF | FL_BAD)) == 0, ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0};
+    fp12l f;
+    miller_loop<2, FIXED0, fp2l>(f, px, py, qx, qy, live);
+    fp12_store(F, f);
+    fl = ((flp0 | flq0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
+}
+BN_INL void item_final_exp_l2(fp12 &F) {
+    fp12l f;
+    fp12_load(f, F);
+    final_exponentiation(f);
+    fp12_store(F, f);
 }
 
 // ---- scalar multiplication (sign / keygen / test-data side; g1.rs:821-841, g2.rs:866-886) -------

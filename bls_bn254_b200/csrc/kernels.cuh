@@ -127,13 +127,56 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F
     F[i] = f;
     flF[i] = fl;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_final_exp(fp12 *F, size_t n) {
+#ifndef BN_MINB_FEXP
+#define BN_MINB_FEXP BN_MINB_HEAVY
+#endif
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_FEXP) k_final_exp(fp12 *F, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp12 f = F[i];
     item_final_exp(f);
     F[i] = f;
 }
+// ---- two lanes per pairing (lane-split Fp2): thread t works on item t/2, lane parity t&1.  A warp
+//      whose 16 items are all out of range exits as a whole; in the last partial warp the idle pairs
+//      recompute the last item (identical bytes are stored) so that every pair stays convergent.
+#ifndef BN_MINB_L2
+#define BN_MINB_L2 8
+#endif
+#define BN_L2_PROLOGUE()                                                 \
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;            \
+    if (((t & ~(size_t)31) >> 1) >= n) return;                           \
+    size_t i = t >> 1;                                                   \
+    if (i >= n) i = n - 1;
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller1_l2(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
+                                                                           const uint8_t *flQ, size_t n, int *bad) {
+    BN_L2_PROLOGUE();
+    uint8_t fl;
+    item_miller1_l2(F[i], fl, P[i], flP[i], Q[i], flQ[i]);
+    if (flF) flF[i] = fl;
+    if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_fixed_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0,
+                                                                                 const g1m *P1, const uint8_t *flP1, const g2m *Q1,
+                                                                                 const uint8_t *flQ1, size_t n) {
+    BN_L2_PROLOGUE();
+    uint8_t fl;
+    item_miller2_l2<true>(F[i], fl, P0[i], flP0[i], nullptr, 0, P1[i], flP1[i], Q1[i], flQ1[i]);
+    flF[i] = fl;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride,
+                                                                           const g2m *Q0, const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1,
+                                                                           const g2m *Q1, const uint8_t *flQ1, size_t n) {
+    BN_L2_PROLOGUE();
+    uint8_t fl;
+    item_miller2_l2<false>(F[i], fl, P0[i * p0_stride], flP0[i * p0_stride], &Q0[i], flQ0[i], P1[i], flP1[i], Q1[i], flQ1[i]);
+    flF[i] = fl;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_final_exp_l2(fp12 *F, size_t n) {
+    BN_L2_PROLOGUE();
+    item_final_exp_l2(F[i]);
+}
+
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_fp12_encode(uint8_t *out, uint8_t *status, const fp12 *F, const uint8_t *fl, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -12,12 +12,15 @@
 
 namespace bn {
 
-struct line_t { fp2 a, b, c; };  // evaluated as (a * yP) + (b * xP) w + c w^3
-struct g2j { fp2 x, y, z; };     // Jacobian accumulator of the Miller loop
+// Everything here is generic over the Fp2 representation T2 (fp2: one thread per pairing,
+// fp2l: a lane pair per pairing), see tower.cuh.
+template <class T2> struct line_t { T2 a, b, c; };  // evaluated as (a * yP) + (b * xP) w + c w^3
+template <class T2> struct g2j { T2 x, y, z; };     // Jacobian accumulator of the Miller loop
 
 // pairings.rs:901-930
-BN_NOINL void doubling_step(line_t &l, g2j &r) {
-    fp2 tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, zsq, t;
+template <class T2>
+BN_NOINL void doubling_step(line_t<T2> &l, g2j<T2> &r) {
+    T2 tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, zsq, t;
     fp2_sqr(tmp0, r.x);
     fp2_sqr(tmp1, r.y);
     fp2_sqr(tmp2, tmp1);
@@ -42,8 +45,9 @@ BN_NOINL void doubling_step(line_t &l, g2j &r) {
     l.c = tmp6;
 }
 // pairings.rs:932-962
-BN_NOINL void addition_step(line_t &l, g2j &r, const fp2 &qx, const fp2 &qy) {
-    fp2 zsq, ysq, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, zt;
+template <class T2>
+BN_NOINL void addition_step(line_t<T2> &l, g2j<T2> &r, const T2 &qx, const T2 &qy) {
+    T2 zsq, ysq, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, zt;
     fp2_sqr(zsq, r.z);
     fp2_sqr(ysq, qy);
     fp2_mul(t0, zsq, qx);
@@ -73,30 +77,38 @@ BN_NOINL void addition_step(line_t &l, g2j &r, const fp2 &qx, const fp2 &qy) {
     l.c = t9;
 }
 // pairings.rs:888-899 with the D-twist placement
-BN_INL void ell(fp12 &f, const line_t &l, const fp &px, const fp &py) {
-    fp2 c0, c1;
+template <class T2>
+BN_INL void ell(fp12_t<T2> &f, const line_t<T2> &l, const fp &px, const fp &py) {
+    T2 c0, c1;
     fp2_mul_fp(c0, l.a, py);
     fp2_mul_fp(c1, l.b, px);
     fp12_mul_by_034(f, c0, c1, l.c);
 }
-BN_INL const line_t &fixed_line(int idx) { return *reinterpret_cast<const line_t *>(&k::NEG_G2_LINES[idx][0][0][0]); }
+// line idx of the fixed point -g2 (precomputed table, one-thread fp2 layout) in this thread's representation
+template <class T2>
+BN_INL void fixed_line(line_t<T2> &l, int idx) {
+    const line_t<fp2> &m = *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]);
+    fp2_load(l.a, m.a);
+    fp2_load(l.b, m.b);
+    fp2_load(l.c, m.c);
+}
 
 // Product of NP Miller loops with one shared squaring per step (multi_miller_loop,
 // pairings.rs:808-857).  Pair i is skipped when live[i] is false (identity inputs contribute 1,
 // pairings.rs:820-835).  When FIXED0, pair 0 is (P0, -g2) and its 88 lines come from the
 // precomputed table (the G2Prepared role, pairings.rs:609-660) instead of being recomputed.
-template <int NP, bool FIXED0>
-BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const bool *live) {
-    g2j r[NP];
-    fp2 nqy[NP];
-    line_t l;
+template <int NP, bool FIXED0, class T2>
+BN_INL void miller_loop(fp12_t<T2> &f, const fp *px, const fp *py, const T2 *qx, const T2 *qy, const bool *live) {
+    g2j<T2> r[NP];
+    T2 nqy[NP];
+    line_t<T2> l;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         if (FIXED0 && i == 0) continue;
-        r[i].x = q[i].x;
-        r[i].y = q[i].y;
+        r[i].x = qx[i];
+        r[i].y = qy[i];
         fp2_set_one(r[i].z);
-        fp2_neg(nqy[i], q[i].y);
+        fp2_neg(nqy[i], qy[i]);
     }
     fp12_set_one(f);
     int idx = 0;
@@ -107,24 +119,18 @@ BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (!live[i]) continue;
-            if (FIXED0 && i == 0) {
-                ell(f, fixed_line(idx), px[0], py[0]);
-            } else {
-                doubling_step(l, r[i]);
-                ell(f, l, px[i], py[i]);
-            }
+            if (FIXED0 && i == 0) fixed_line(l, idx);
+            else doubling_step(l, r[i]);
+            ell(f, l, px[i], py[i]);
         }
         idx++;
         if (d) {
 #pragma unroll
             for (int i = 0; i < NP; i++) {
                 if (!live[i]) continue;
-                if (FIXED0 && i == 0) {
-                    ell(f, fixed_line(idx), px[0], py[0]);
-                } else {
-                    addition_step(l, r[i], q[i].x, d > 0 ? q[i].y : nqy[i]);
-                    ell(f, l, px[i], py[i]);
-                }
+                if (FIXED0 && i == 0) fixed_line(l, idx);
+                else addition_step(l, r[i], qx[i], d > 0 ? qy[i] : nqy[i]);
+                ell(f, l, px[i], py[i]);
             }
             idx++;
         }
@@ -134,14 +140,18 @@ BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const
     for (int i = 0; i < NP; i++) {
         if (!live[i]) continue;
         if (FIXED0 && i == 0) {
-            ell(f, fixed_line(idx), px[0], py[0]);
-            ell(f, fixed_line(idx + 1), px[0], py[0]);
+            fixed_line(l, idx);
+            ell(f, l, px[0], py[0]);
+            fixed_line(l, idx + 1);
+            ell(f, l, px[0], py[0]);
         } else {
-            fp2 q1x, q1y, q2x, q2y, t;
-            fp2_conj(t, q[i].x); fp2_mul(q1x, t, kfp2(k::ENDO_U));
-            fp2_conj(t, q[i].y); fp2_mul(q1y, t, kfp2(k::ENDO_V));
-            fp2_conj(t, q1x); fp2_mul(q2x, t, kfp2(k::ENDO_U));
-            fp2_conj(t, q1y); fp2_mul(q2y, t, kfp2(k::ENDO_V));
+            T2 q1x, q1y, q2x, q2y, t, eu, ev;
+            fp2_load(eu, kfp2(k::ENDO_U));
+            fp2_load(ev, kfp2(k::ENDO_V));
+            fp2_conj(t, qx[i]); fp2_mul(q1x, t, eu);
+            fp2_conj(t, qy[i]); fp2_mul(q1y, t, ev);
+            fp2_conj(t, q1x); fp2_mul(q2x, t, eu);
+            fp2_conj(t, q1y); fp2_mul(q2y, t, ev);
             fp2_neg(q2y, q2y);
             addition_step(l, r[i], q1x, q1y);
             ell(f, l, px[i], py[i]);
@@ -154,58 +164,70 @@ BN_INL void miller_loop(fp12 &f, const fp *px, const fp *py, const g2a *q, const
 // f^x (x = 0x44e992b44a6909f1, 63 bits) in the cyclotomic subgroup, then conjugate
 // (pairings.rs:117-134 role).  Width-4 signed window over f, f^3, f^5, f^7 (a negative digit uses the
 // conjugate, which is the inverse here): 63 cyclotomic squarings + 16 products instead of 62 + 27.
-BN_NOINL void cyclotomic_exp_neg_x(fp12 &r, const fp12 &f) {
-    fp12 pw[4], t;
+#ifndef BN_XWIN
+#define BN_XWIN 4
+#endif
+template <class T2>
+BN_NOINL void cyclotomic_exp_neg_x(fp12_t<T2> &r, const fp12_t<T2> &f) {
+#if BN_XWIN == 4
+    const int NPW = 4, LEN = BN254_X_WNAF_LEN;
+    const int8_t *dig = k::X_WNAF4;
+#else
+    const int NPW = 2, LEN = BN254_X_WNAF3_LEN;
+    const int8_t *dig = k::X_WNAF3;
+#endif
+    fp12_t<T2> pw[NPW], t;
     pw[0] = f;
     cyclotomic_square(t, f);
-    fp12_mul(pw[1], pw[0], t);
-    fp12_mul(pw[2], pw[1], t);
-    fp12_mul(pw[3], pw[2], t);
-    t = pw[(k::X_WNAF4[0] - 1) >> 1];
 #pragma unroll 1
-    for (int i = 1; i < BN254_X_WNAF_LEN; i++) {
+    for (int i = 1; i < NPW; i++) fp12_mul(pw[i], pw[i - 1], t);
+    t = pw[(dig[0] - 1) >> 1];
+#pragma unroll 1
+    for (int i = 1; i < LEN; i++) {
         cyclotomic_square(t, t);
-        int d = k::X_WNAF4[i];
+        int d = dig[i];
         if (d > 0) {
             fp12_mul(t, t, pw[(d - 1) >> 1]);
-        } else if (d < 0) {
-            fp12 c;
-            fp12_conj(c, pw[(-d - 1) >> 1]);
-            fp12_mul(t, t, c);
+        } else if (d < 0) {  // t * conj(x) = conj(conj(t) * x): no temporary
+            fp12_conj(t, t);
+            fp12_mul(t, t, pw[(-d - 1) >> 1]);
+            fp12_conj(t, t);
         }
     }
     fp12_conj(r, t);
 }
-// pairings.rs:50-178 role: easy part f^((p^6-1)(p^2+1)), then the Fuentes-Castaneda hard part
-BN_INL void final_exponentiation(fp12 &out, const fp12 &f) {
-    fp12 r, t, y0, y1, y3, y4, y6;
+// pairings.rs:50-178 role: easy part f^((p^6-1)(p^2+1)), then the Fuentes-Castaneda hard part.
+// `f` is both input and output; five Fp12 temporaries.
+template <class T2>
+BN_INL void final_exponentiation(fp12_t<T2> &f) {
+    fp12_t<T2> r, t, a, b, c;
     fp12_conj(r, f);
     fp12_inv(t, f);
     fp12_mul(t, r, t);          // f^(p^6-1)
     fp12_frob(r, t, 2);
     fp12_mul(r, r, t);          // r = f^((p^6-1)(p^2+1))
-    cyclotomic_exp_neg_x(y0, r);
-    cyclotomic_square(y1, y0);
-    cyclotomic_square(t, y1);
-    fp12_mul(y3, t, y1);
-    cyclotomic_exp_neg_x(y4, y3);
-    cyclotomic_square(t, y4);
-    cyclotomic_exp_neg_x(y6, t);
-    fp12_conj(y3, y3);
-    fp12_conj(y6, y6);
-    fp12_mul(t, y6, y4);        // y7
-    fp12_mul(y3, t, y3);        // y8
-    fp12_mul(y0, y3, y1);       // y9
-    fp12_mul(t, y3, y4);        // y10
+    cyclotomic_exp_neg_x(a, r);     // y0
+    cyclotomic_square(a, a);        // y1
+    cyclotomic_square(t, a);        // y2
+    fp12_mul(b, t, a);              // y3
+    cyclotomic_exp_neg_x(c, b);     // y4
+    cyclotomic_square(t, c);        // y5
+    cyclotomic_exp_neg_x(f, t);     // y6
+    fp12_conj(b, b);
+    fp12_conj(f, f);
+    fp12_mul(t, f, c);          // y7
+    fp12_mul(b, t, b);          // y8
+    fp12_mul(f, b, a);          // y9  (a = y1 free afterwards)
+    fp12_mul(t, b, c);          // y10
     fp12_mul(t, t, r);          // y11
-    fp12_frob(y1, y0, 1);       // y12
-    fp12_mul(t, y1, t);         // y13
-    fp12_frob(y3, y3, 2);
-    fp12_mul(t, y3, t);         // y14
-    fp12_conj(y1, r);
-    fp12_mul(y1, y1, y0);       // y15
-    fp12_frob(y1, y1, 3);
-    fp12_mul(out, y1, t);
+    fp12_frob(a, f, 1);         // y12
+    fp12_mul(t, a, t);          // y13
+    fp12_frob(b, b, 2);
+    fp12_mul(t, b, t);          // y14
+    fp12_conj(a, r);
+    fp12_mul(a, a, f);          // y15
+    fp12_frob(a, a, 3);
+    fp12_mul(f, a, t);
 }
 
 }  // namespace bn

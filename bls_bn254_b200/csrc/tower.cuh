@@ -12,8 +12,18 @@
 namespace bn {
 
 struct fp2 { fp c0, c1; };
-struct fp6 { fp2 c0, c1, c2; };
-struct fp12 { fp6 c0, c1; };
+// Lane-split Fp2: two adjacent lanes of a warp hold one element, the even lane c0 and the odd lane
+// c1.  Every Fp2 operation then costs each lane ONE Fp operation (a product is one fused two-term
+// dot product per lane), the per-thread state of a pairing halves, and twice as many warps fit the
+// same memory footprint -- see DESIGN.md "two lanes per pairing".
+struct fp2l { fp v; };
+// the tower above Fp2 is generic over the Fp2 representation (fp2: one thread, fp2l: lane pair)
+template <class T2> struct fp6_t { T2 c0, c1, c2; };
+template <class T2> struct fp12_t { fp6_t<T2> c0, c1; };
+typedef fp6_t<fp2> fp6;
+typedef fp12_t<fp2> fp12;
+typedef fp6_t<fp2l> fp6l;
+typedef fp12_t<fp2l> fp12l;
 
 BN_INL const fp2 &kfp2(const uint32_t (&a)[2][8]) { return *reinterpret_cast<const fp2 *>(&a[0][0]); }
 
@@ -149,7 +159,7 @@ BN_NOINL bool fp2_sqrt(fp2 &r, const fp2 &a) {
         fp_mul(d, d, half);
         fp_neg(d, d);
     }
-    fp_pow(w, d, k::EXP_P_MINUS_3_DIV_4);
+    fp_pow_p_minus_3_div_4(w, d);
     fp_mul(t, w, d);
     fp_mul(chk, t, t);
     bool dsq = fp_eq(chk, d);
@@ -165,14 +175,130 @@ BN_NOINL bool fp2_sqrt(fp2 &r, const fp2 &a) {
     return ok;
 }
 
+// constants are stored as one-thread fp2 values
+BN_INL void fp2_load(fp2 &r, const fp2 &m) { r = m; }
+BN_INL void fp2_store(fp2 &m, const fp2 &a) { m = a; }
+
+// ---------------------------------------------------------------------------------- lane-split Fp2
+#if BN_PTX
+BN_INL uint32_t lane_par() { return threadIdx.x & 1u; }
+// Only the two lanes of a pair are named in the shuffle mask: the pair always runs the same control
+// flow, different pairs of a warp may diverge (identity inputs skip their Miller loop).
+BN_INL uint32_t lane_mask() { return 3u << (threadIdx.x & 30u); }
+BN_INL void lane_xchg(fp &out, const fp &in) {  // out = the partner lane's `in`
+    uint32_t m = lane_mask();
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.v[i] = __shfl_xor_sync(m, in.v[i], 1);
+}
+BN_INL bool lane_both(bool x) {
+    int o = __shfl_xor_sync(lane_mask(), (int)x, 1);
+    return x & (o != 0);
+}
+#else
+// host emulation hooks, provided by tests/hostsim (two host threads per lane pair)
+extern "C" uint32_t bn_host_lane_par();
+extern "C" void bn_host_lane_xchg(uint32_t *out, const uint32_t *in, int nwords);
+BN_INL uint32_t lane_par() { return bn_host_lane_par(); }
+BN_INL void lane_xchg(fp &out, const fp &in) { bn_host_lane_xchg(out.v, in.v, 8); }
+BN_INL bool lane_both(bool x) {
+    uint32_t a = x, b;
+    bn_host_lane_xchg(&b, &a, 1);
+    return x & (b != 0);
+}
+#endif
+BN_INL void fp2_load(fp2l &r, const fp2 &m) { r.v = lane_par() ? m.c1 : m.c0; }
+BN_INL void fp2_store(fp2 &m, const fp2l &a) {
+    if (lane_par()) m.c1 = a.v;
+    else m.c0 = a.v;
+}
+BN_INL void fp2_set_zero(fp2l &r) { fp_set_zero(r.v); }
+BN_INL void fp2_set_one(fp2l &r) {
+    fp z;
+    fp_set_zero(z);
+    fp_select(r.v, lane_par() != 0, z, kfp(k::ONE));
+}
+BN_INL bool fp2_is_zero(const fp2l &a) { return lane_both(fp_is_zero(a.v)); }
+BN_INL bool fp2_eq(const fp2l &a, const fp2l &b) { return lane_both(fp_eq(a.v, b.v)); }
+// The lane-pair primitives are out-of-line with operands and result in registers (by value): the
+// tower routines above them are then pure call sequences of a few KB each (instruction cache).
+BN_NOINL fp l2_add_v(fp a, fp b) { fp r; fp_add(r, a, b); return r; }
+BN_NOINL fp l2_sub_v(fp a, fp b) { fp r; fp_sub(r, a, b); return r; }
+BN_NOINL fp l2_neg_v(fp a) { fp r; fp_neg(r, a); return r; }
+BN_NOINL fp l2_conj_v(fp a) {
+    fp n, r;
+    fp_neg(n, a);
+    fp_select(r, lane_par() != 0, n, a);
+    return r;
+}
+// even lane: a0 b0 + a1 (-b1);  odd lane: a0 b1 + a1 b0 -- one fused dot product per lane
+BN_NOINL fp l2_mul_v(fp a, fp b) {
+    fp pa, pb, npb, x, z, w, r;
+    bool odd = lane_par() != 0;
+    lane_xchg(pa, a);
+    lane_xchg(pb, b);
+    fp_neg(npb, pb);
+    fp_select(x, odd, pa, a);    // a0
+    fp_select(z, odd, a, pa);    // a1
+    fp_select(w, odd, pb, npb);  // odd: b0, even: -b1
+    fp_dot2_inl(r, x, b, z, w);
+    return r;
+}
+// even lane: (a0 + a1)(a0 - a1);  odd lane: (a0 + a0) a1
+BN_NOINL fp l2_sqr_v(fp a) {
+    fp pa, s, d, x, y, r;
+    bool odd = lane_par() != 0;
+    lane_xchg(pa, a);
+    fp_select(s, odd, pa, a);  // a0
+    fp_add(x, s, pa);          // even: a0 + a1, odd: a0 + a0
+    fp_sub(d, a, pa);
+    fp_select(y, odd, a, d);   // even: a0 - a1, odd: a1
+    fp_mul_inl(r, x, y);
+    return r;
+}
+// (9+u)(a0 + a1 u): even lane 9 a0 - a1, odd lane 9 a1 + a0
+BN_NOINL fp l2_xi_v(fp a) {
+    fp pa, n, t, u, r;
+    lane_xchg(pa, a);
+    fp_neg(n, pa);
+    fp_mul9(t, a);
+    fp_select(u, lane_par() != 0, pa, n);
+    fp_add(r, t, u);
+    return r;
+}
+BN_INL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_add_v(a.v, b.v); }
+BN_INL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_sub_v(a.v, b.v); }
+BN_INL void fp2_neg(fp2l &r, const fp2l &a) { r.v = l2_neg_v(a.v); }
+BN_INL void fp2_dbl(fp2l &r, const fp2l &a) { r.v = l2_add_v(a.v, a.v); }
+BN_INL void fp2_conj(fp2l &r, const fp2l &a) { r.v = l2_conj_v(a.v); }
+BN_INL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_mul_v(a.v, b.v); }
+BN_INL void fp2_sqr(fp2l &r, const fp2l &a) { r.v = l2_sqr_v(a.v); }
+BN_INL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) { fp_mul(r.v, a.v, s); }
+BN_INL void fp2_mul_xi(fp2l &r, const fp2l &a) { r.v = l2_xi_v(a.v); }
+// fp2.rs:161-166 on a lane pair (both lanes run the same Fp inversion on the shared norm)
+BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
+    fp sq, psq, n, m;
+    fp_mul(sq, a.v, a.v);
+    lane_xchg(psq, sq);
+    fp_add(n, sq, psq);
+    fp_inv(n, n);
+    fp_neg(m, n);
+    fp_select(n, lane_par() != 0, m, n);
+    fp_mul(r.v, a.v, n);
+}
+
 // ------------------------------------------------------------------------------------------ Fp6
-BN_INL void fp6_add(fp6 &r, const fp6 &a, const fp6 &b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
-BN_INL void fp6_sub(fp6 &r, const fp6 &a, const fp6 &b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
-BN_INL void fp6_neg(fp6 &r, const fp6 &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
-BN_INL void fp6_dbl(fp6 &r, const fp6 &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
+template <class T2>
+BN_INL void fp6_add(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
+template <class T2>
+BN_INL void fp6_sub(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
+template <class T2>
+BN_INL void fp6_neg(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
+template <class T2>
+BN_INL void fp6_dbl(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
 // Karatsuba, 6 Fp2 products (role of fp6.rs:225-242)
-BN_NOINL void fp6_mul(fp6 &r, const fp6 &a, const fp6 &b) {
-    fp2 v0, v1, v2, t0, t1, t2, c0, c1;
+template <class T2>
+BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
+    T2 v0, v1, v2, t0, t1, t2, c0, c1;
     fp2_mul(v0, a.c0, b.c0);
     fp2_mul(v1, a.c1, b.c1);
     fp2_mul(v2, a.c2, b.c2);
@@ -186,8 +312,9 @@ BN_NOINL void fp6_mul(fp6 &r, const fp6 &a, const fp6 &b) {
     r.c1 = c1;
 }
 // a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01)
-BN_NOINL void fp6_mul_by_01(fp6 &r, const fp6 &a, const fp2 &b0, const fp2 &b1) {
-    fp2 v0, v1, t0, t1, t2, c0, c1;
+template <class T2>
+BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, const T2 &b1) {
+    T2 v0, v1, t0, t1, t2, c0, c1;
     fp2_mul(v0, a.c0, b0);
     fp2_mul(v1, a.c1, b1);
     fp2_add(t0, a.c1, a.c2); fp2_mul(t2, t0, b1); fp2_sub(t2, t2, v1); fp2_mul_xi(t2, t2); fp2_add(c0, t2, v0);
@@ -196,18 +323,21 @@ BN_NOINL void fp6_mul_by_01(fp6 &r, const fp6 &a, const fp2 &b0, const fp2 &b1) 
     r.c0 = c0;
     r.c1 = c1;
 }
-BN_INL void fp6_mul_fp2(fp6 &r, const fp6 &a, const fp2 &b) { fp2_mul(r.c0, a.c0, b); fp2_mul(r.c1, a.c1, b); fp2_mul(r.c2, a.c2, b); }
+template <class T2>
+BN_INL void fp6_mul_fp2(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b) { fp2_mul(r.c0, a.c0, b); fp2_mul(r.c1, a.c1, b); fp2_mul(r.c2, a.c2, b); }
 // multiply by v (fp6.rs:146-152 with xi = 9+u)
-BN_INL void fp6_mul_v(fp6 &r, const fp6 &a) {
-    fp2 t;
+template <class T2>
+BN_INL void fp6_mul_v(fp6_t<T2> &r, const fp6_t<T2> &a) {
+    T2 t;
     fp2_mul_xi(t, a.c2);
     r.c2 = a.c1;
     r.c1 = a.c0;
     r.c0 = t;
 }
 // fp6.rs:261-287
-BN_NOINL void fp6_inv(fp6 &r, const fp6 &a) {
-    fp2 t0, t1, t2, d, s;
+template <class T2>
+BN_NOINL void fp6_inv(fp6_t<T2> &r, const fp6_t<T2> &a) {
+    T2 t0, t1, t2, d, s;
     fp2_sqr(t0, a.c0); fp2_mul(s, a.c1, a.c2); fp2_mul_xi(s, s); fp2_sub(t0, t0, s);
     fp2_sqr(t1, a.c2); fp2_mul_xi(t1, t1); fp2_mul(s, a.c0, a.c1); fp2_sub(t1, t1, s);
     fp2_sqr(t2, a.c1); fp2_mul(s, a.c0, a.c2); fp2_sub(t2, t2, s);
@@ -218,32 +348,36 @@ BN_NOINL void fp6_inv(fp6 &r, const fp6 &a) {
 }
 
 // ------------------------------------------------------------------------------------------ Fp12
-BN_INL void fp12_set_one(fp12 &r) {
+template <class T2>
+BN_INL void fp12_set_one(fp12_t<T2> &r) {
     fp2_set_one(r.c0.c0); fp2_set_zero(r.c0.c1); fp2_set_zero(r.c0.c2);
     fp2_set_zero(r.c1.c0); fp2_set_zero(r.c1.c1); fp2_set_zero(r.c1.c2);
 }
-BN_INL bool fp12_is_one(const fp12 &a) {
-    fp2 one;
+template <class T2>
+BN_INL bool fp12_is_one(const fp12_t<T2> &a) {
+    T2 one;
     fp2_set_one(one);
     return fp2_eq(a.c0.c0, one) & fp2_is_zero(a.c0.c1) & fp2_is_zero(a.c0.c2) & fp2_is_zero(a.c1.c0) & fp2_is_zero(a.c1.c1) &
            fp2_is_zero(a.c1.c2);
 }
-// fp12.rs:203-210
-BN_NOINL void fp12_mul(fp12 &r, const fp12 &a, const fp12 &b) {
-    fp6 aa, bb, s, t;
-    fp6_mul(aa, a.c0, b.c0);
-    fp6_mul(bb, a.c1, b.c1);
+// fp12.rs:203-210 (Karatsuba over Fp6; r may alias a or b)
+template <class T2>
+BN_NOINL void fp12_mul(fp12_t<T2> &r, const fp12_t<T2> &a, const fp12_t<T2> &b) {
+    fp6_t<T2> s, t, bb;
     fp6_add(s, a.c0, a.c1);
     fp6_add(t, b.c0, b.c1);
-    fp6_mul(s, s, t);
-    fp6_sub(s, s, aa);
+    fp6_mul(s, s, t);            // (a0 + a1)(b0 + b1)
+    fp6_mul(t, a.c0, b.c0);      // aa
+    fp6_mul(bb, a.c1, b.c1);
+    fp6_sub(s, s, t);
     fp6_sub(r.c1, s, bb);
     fp6_mul_v(bb, bb);
-    fp6_add(r.c0, aa, bb);
+    fp6_add(r.c0, t, bb);
 }
 // fp12.rs:170-180 (complex squaring, 2 Fp6 products)
-BN_NOINL void fp12_sqr(fp12 &r, const fp12 &a) {
-    fp6 ab, s, t;
+template <class T2>
+BN_NOINL void fp12_sqr(fp12_t<T2> &r, const fp12_t<T2> &a) {
+    fp6_t<T2> ab, s, t;
     fp6_mul(ab, a.c0, a.c1);
     fp6_add(s, a.c0, a.c1);
     fp6_mul_v(t, a.c1);
@@ -254,10 +388,12 @@ BN_NOINL void fp12_sqr(fp12 &r, const fp12 &a) {
     fp6_sub(r.c0, s, t);
     fp6_dbl(r.c1, ab);
 }
-BN_INL void fp12_conj(fp12 &r, const fp12 &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }  // fp12.rs:131-136
+template <class T2>
+BN_INL void fp12_conj(fp12_t<T2> &r, const fp12_t<T2> &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }  // fp12.rs:131-136
 // fp12.rs:212-219
-BN_NOINL void fp12_inv(fp12 &r, const fp12 &a) {
-    fp6 t0, t1;
+template <class T2>
+BN_NOINL void fp12_inv(fp12_t<T2> &r, const fp12_t<T2> &a) {
+    fp6_t<T2> t0, t1;
     fp6_mul(t0, a.c0, a.c0);
     fp6_mul(t1, a.c1, a.c1);
     fp6_mul_v(t1, t1);
@@ -269,9 +405,10 @@ BN_NOINL void fp12_inv(fp12 &r, const fp12 &a) {
 }
 // f * (c0 + c3 w + c4 w^3): the D-twist sparse line product, 13 Fp2 products
 // (role of fp12.rs:120-129 mul_by_014 with the placement corrected to 0/3/4)
-BN_NOINL void fp12_mul_by_034(fp12 &f, const fp2 &c0, const fp2 &c3, const fp2 &c4) {
-    fp6 t0, t1, s;
-    fp2 d;
+template <class T2>
+BN_NOINL void fp12_mul_by_034(fp12_t<T2> &f, const T2 &c0, const T2 &c3, const T2 &c4) {
+    fp6_t<T2> t0, t1, s;
+    T2 d;
     fp6_mul_fp2(t0, f.c0, c0);
     fp6_mul_by_01(t1, f.c1, c3, c4);
     fp2_add(d, c0, c3);
@@ -283,29 +420,37 @@ BN_NOINL void fp12_mul_by_034(fp12 &f, const fp2 &c0, const fp2 &c3, const fp2 &
     fp6_add(f.c0, t0, t1);
 }
 // coefficient of w^i: i even -> c0.c(i/2), i odd -> c1.c((i-1)/2)
-BN_INL fp2 &fp12_coeff(fp12 &a, int i) {
-    fp6 &h = (i & 1) ? a.c1 : a.c0;
+template <class T2>
+BN_INL T2 &fp12_coeff(fp12_t<T2> &a, int i) {
+    fp6_t<T2> &h = (i & 1) ? a.c1 : a.c0;
     return (i >> 1) == 0 ? h.c0 : ((i >> 1) == 1 ? h.c1 : h.c2);
 }
 // x -> x^(p^kk), kk = 1, 2, 3 (role of fp12.rs:139-168 with the real constants xi^(i(p^k-1)/6))
-BN_NOINL void fp12_frob(fp12 &r, const fp12 &a, int kk) {
-    fp12 t = a;
+template <class T2>
+BN_NOINL void fp12_frob(fp12_t<T2> &r, const fp12_t<T2> &a, int kk) {
+    fp12_t<T2> t = a;
 #pragma unroll 1
     for (int i = 0; i < 6; i++) {
-        fp2 &c = fp12_coeff(t, i);
+        T2 &c = fp12_coeff(t, i);
         if (kk & 1) fp2_conj(c, c);
         if (i) {
             const fp2 &g = *reinterpret_cast<const fp2 *>(&k::GAMMA[kk - 1][i - 1][0][0]);
-            if (kk == 2) fp2_mul_fp(c, c, g.c0);
-            else fp2_mul(c, c, g);
+            if (kk == 2) {
+                fp2_mul_fp(c, c, g.c0);
+            } else {
+                T2 gl;
+                fp2_load(gl, g);
+                fp2_mul(c, c, gl);
+            }
         }
     }
     r = t;
 }
 
 // pairings.rs:52-63
-BN_INL void fp4_square(fp2 &c0, fp2 &c1, const fp2 &a, const fp2 &b) {
-    fp2 t0, t1, t2;
+template <class T2>
+BN_INL void fp4_square(T2 &c0, T2 &c1, const T2 &a, const T2 &b) {
+    T2 t0, t1, t2;
     fp2_sqr(t0, a);
     fp2_sqr(t1, b);
     fp2_mul_xi(t2, t1);
@@ -315,10 +460,14 @@ BN_INL void fp4_square(fp2 &c0, fp2 &c1, const fp2 &a, const fp2 &b) {
     fp2_sub(t2, t2, t0);
     fp2_sub(c1, t2, t1);
 }
-// Granger-Scott squaring in the cyclotomic subgroup (pairings.rs:68-115)
-BN_NOINL void cyclotomic_square(fp12 &r, const fp12 &f) {
-    fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
-    fp2 t0, t1, t2, t3;
+// Granger-Scott squaring in the cyclotomic subgroup (pairings.rs:68-115), in place: the six
+// coefficients are updated where they live (four Fp2 temporaries instead of ten).
+//   (z0, z1) = (c0.c0, c1.c1), (z2, z3) = (c1.c0, c0.c2), (z4, z5) = (c0.c1, c1.c2)
+template <class T2>
+BN_NOINL void cyclotomic_square(fp12_t<T2> &r, const fp12_t<T2> &f) {
+    if (&r != &f) r = f;
+    T2 &z0 = r.c0.c0, &z4 = r.c0.c1, &z3 = r.c0.c2, &z2 = r.c1.c0, &z1 = r.c1.c1, &z5 = r.c1.c2;
+    T2 t0, t1, t2, t3;
     fp4_square(t0, t1, z0, z1);
     fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
     fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
@@ -329,8 +478,18 @@ BN_NOINL void cyclotomic_square(fp12 &r, const fp12 &f) {
     fp2_mul_xi(t0, t3);
     fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
     fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
-    r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
-    r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+}
+
+// one-thread record (HBM) <-> this thread's representation
+BN_INL void fp12_load(fp12 &r, const fp12 &m) { r = m; }
+BN_INL void fp12_store(fp12 &m, const fp12 &a) { m = a; }
+BN_INL void fp12_load(fp12l &r, const fp12 &m) {
+    fp2_load(r.c0.c0, m.c0.c0); fp2_load(r.c0.c1, m.c0.c1); fp2_load(r.c0.c2, m.c0.c2);
+    fp2_load(r.c1.c0, m.c1.c0); fp2_load(r.c1.c1, m.c1.c1); fp2_load(r.c1.c2, m.c1.c2);
+}
+BN_INL void fp12_store(fp12 &m, const fp12l &a) {
+    fp2_store(m.c0.c0, a.c0.c0); fp2_store(m.c0.c1, a.c0.c1); fp2_store(m.c0.c2, a.c0.c2);
+    fp2_store(m.c1.c0, a.c1.c0); fp2_store(m.c1.c1, a.c1.c1); fp2_store(m.c1.c2, a.c1.c2);
 }
 
 // wire format: 12 x 32 B big-endian in memory order c0.c0.c0, c0.c0.c1, ... (pairings.rs:499-514)

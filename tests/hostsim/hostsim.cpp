@@ -179,3 +179,88 @@ EXPORT void sim_fp_dot2(uint32_t *r, const uint32_t *a, const uint32_t *b, const
     fp_dot2_inl(o, x, y, z, w);
     memcpy(r, o.v, 32);
 }
+// ---- lane-pair emulation: two host threads run the same body, exchanging through a rendezvous ----
+#include <pthread.h>
+static thread_local int tl_lane = 0;
+static pthread_barrier_t g_bar;
+static uint32_t g_slot[2][16];
+extern "C" uint32_t bn_host_lane_par() { return (uint32_t)tl_lane; }
+extern "C" void bn_host_lane_xchg(uint32_t *out, const uint32_t *in, int nwords) {
+    memcpy(g_slot[tl_lane], in, 4 * nwords);
+    pthread_barrier_wait(&g_bar);
+    memcpy(out, g_slot[tl_lane ^ 1], 4 * nwords);
+    pthread_barrier_wait(&g_bar);
+}
+struct pair_job { void (*fn)(void *); void *arg; int lane; };
+static void *pair_main(void *p) {
+    pair_job *j = (pair_job *)p;
+    tl_lane = j->lane;
+    j->fn(j->arg);
+    return nullptr;
+}
+static void run_pair(void (*fn)(void *), void *arg) {
+    pthread_barrier_init(&g_bar, nullptr, 2);
+    pthread_t th[2];
+    pair_job jobs[2] = {{fn, arg, 0}, {fn, arg, 1}};
+    for (int i = 0; i < 2; i++) pthread_create(&th[i], nullptr, pair_main, &jobs[i]);
+    for (int i = 0; i < 2; i++) pthread_join(th[i], nullptr);
+    pthread_barrier_destroy(&g_bar);
+}
+// lane-pair versions of the pairing bodies (both emulated lanes run the item function)
+struct l2_args { const uint8_t *g1, *g2; const uint8_t *p0, *q0, *p1, *q1; int fixed; int mode; fp12 F; uint8_t fl; };
+static void l2_pairing_body(void *vp) {
+    l2_args *a = (l2_args *)vp;
+    g1m p;
+    g2m q;
+    uint8_t flp, flq, fl;
+    item_g1_decode(p, flp, a->g1, false);
+    item_g2_decode(q, flq, a->g2, false);
+    item_miller1_l2(a->F, fl, p, flp, q, flq);
+    if (a->mode == 0) {
+        uint32_t dummy_in = 0, dummy_out;
+        bn_host_lane_xchg(&dummy_out, &dummy_in, 1);  // rendezvous: both halves of F are stored before either lane reloads it
+        item_final_exp_l2(a->F);
+    }
+    if (bn_host_lane_par() == 0) a->fl = fl;
+}
+EXPORT void sim_pairing_batch_l2(const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *out, uint8_t *status, int mode) {
+    for (size_t i = 0; i < n; i++) {
+        l2_args a;
+        memset(&a, 0, sizeof a);
+        a.g1 = g1 + 64 * i;
+        a.g2 = g2 + 128 * i;
+        a.mode = mode;
+        run_pair(l2_pairing_body, &a);
+        if (a.fl & FL_BAD) memset(out + 384 * i, 0, 384);
+        else fp12_to_bytes(out + 384 * i, a.F);
+        if (status) status[i] = !(a.fl & FL_BAD);
+    }
+}
+static void l2_miller2_body(void *vp) {
+    l2_args *x = (l2_args *)vp;
+    g1m a, c;
+    g2m b, d;
+    uint8_t fa, fb = 0, fc, fd, fl;
+    item_g1_decode(a, fa, x->p0, false);
+    if (!x->fixed) item_g2_decode(b, fb, x->q0, false);
+    item_g1_decode(c, fc, x->p1, false);
+    item_g2_decode(d, fd, x->q1, false);
+    if (x->fixed) item_miller2_l2<true>(x->F, fl, a, fa, nullptr, 0, c, fc, d, fd);
+    else item_miller2_l2<false>(x->F, fl, a, fa, &b, fb, c, fc, d, fd);
+}
+EXPORT void sim_miller2_l2(const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, int fixed, uint8_t *out) {
+    l2_args a;
+    memset(&a, 0, sizeof a);
+    a.p0 = p0; a.q0 = q0; a.p1 = p1; a.q1 = q1; a.fixed = fixed;
+    run_pair(l2_miller2_body, &a);
+    fp12_to_bytes(out, a.F);
+}
+static void l2_fe_body(void *vp) { item_final_exp_l2(*(fp12 *)vp); }
+EXPORT void sim_final_exp_l2(const uint8_t *in, size_t n, uint8_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        fp12 f;
+        fp12_from_bytes(f, in + 384 * i);
+        run_pair(l2_fe_body, &f);
+        fp12_to_bytes(out + 384 * i, f);
+    }
+}

@@ -152,3 +152,63 @@ def test_scalar_mul_and_codecs(sim, orc):
     comp, back = C.create_string_buffer(64 * n), C.create_string_buffer(128 * n)
     sim.sim_g2_codec(g2, C.c_size_t(n), comp, back, st)
     assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
+
+
+def test_lane_pair_pairing(sim, orc):
+    """two lanes per pairing (lane-split Fp2, BN_LANES=2 kernels): the same bodies run by two emulated
+    lanes exchanging through the shuffle hook must equal the oracle, identity and bad inputs included"""
+    rng = random.Random(4)
+    msgs = [rng.randbytes(8) for _ in range(3)]
+    g1 = orc.g1_generator() + orc.hash_to_g1(msgs, QUUX_G1)
+    g2 = orc.g2_generator() + orc.hash_to_g2(msgs, QUUX_G2)
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    g1 += ident1 + b"\xff" * 64
+    g2 += g2[:256]
+    n = len(g1) // 64
+    for mode in (1, 0):
+        out, st = C.create_string_buffer(384 * n), C.create_string_buffer(n)
+        sim.sim_pairing_batch_l2(g1, g2, C.c_size_t(n), out, st, mode)
+        assert out.raw == (orc.pairing_batch(g1, g2) if mode == 0 else orc.miller_loop_batch(g1, g2))
+    out = C.create_string_buffer(384)
+    sim.sim_miller2_l2(g1[64:128], g2[128:256], g1[128:192], g2[256:384], 0, out)
+    assert out.raw == orc.multi_miller_loop(g1[64:192], g2[128:384])
+    gen = orc.g2_generator()
+    neg = gen[:64] + ((P - int.from_bytes(gen[64:96], "big")) % P).to_bytes(32, "big") + ((P - int.from_bytes(gen[96:], "big")) % P).to_bytes(32, "big")
+    sim.sim_miller2_l2(g1[64:128], None, g1[128:192], g2[256:384], 1, out)
+    assert out.raw == orc.multi_miller_loop(g1[64:192], neg + g2[256:384])
+    ml = orc.miller_loop_batch(g1[:128], g2[:256])
+    o2 = C.create_string_buffer(len(ml))
+    sim.sim_final_exp_l2(ml, C.c_size_t(2), o2)
+    assert o2.raw == orc.final_exponentiation(ml)
+
+
+def test_wide_and_fused_products(sim):
+    """512-bit product, Montgomery reduction, fused two-term dot product, Fp2 product (raw limbs)"""
+    rng = random.Random(7)
+    R = 1 << 256
+    ri = pow(R, -1, P)
+
+    def w(x, n=8):
+        return (C.c_uint32 * n)(*[(x >> (32 * i)) & 0xffffffff for i in range(n)])
+
+    def r(a, n=8):
+        return sum(int(a[i]) << (32 * i) for i in range(n))
+    vals = [0, 1, P - 1, 2**256 - 1, 2**255, 2 * P - 1, 0xffffffff] + [rng.randrange(2**256) for _ in range(60)]
+    for _ in range(800):
+        a, b = rng.choice(vals), rng.choice(vals)
+        o = (C.c_uint32 * 16)()
+        sim.sim_fp_mul_wide(o, w(a), w(b))
+        assert r(o, 16) == a * b
+    for t in [0, 1, P * R - 1, (P - 1) * (P - 1), 2 * P * P - 1, R] + [rng.randrange(P * R) for _ in range(600)]:
+        o = (C.c_uint32 * 8)()
+        sim.sim_fp_redc(o, w(t, 16))
+        assert r(o) == t * ri % P
+    fv = [0, 1, P - 1, P - 2, (P - 1) // 2, 2**253] + [rng.randrange(P) for _ in range(60)]
+    for _ in range(2000):
+        a, b, c, d = [rng.choice(fv) for _ in range(4)]
+        o = (C.c_uint32 * 8)()
+        sim.sim_fp_dot2(o, w(a), w(b), w(c), w(d))
+        assert r(o) == (a * b + c * d) * ri % P
+        o = (C.c_uint32 * 16)()
+        sim.sim_fp2_mul(o, w(a | (b << 256), 16), w(c | (d << 256), 16))
+        assert r(o, 16) == ((a * c - b * d) * ri % P) | (((a * d + b * c) * ri % P) << 256)
