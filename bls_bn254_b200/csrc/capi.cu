@@ -491,6 +491,13 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
             return rc;
         }
     }
+    if (const char *s = getenv("BN254_STACK")) {  // bring-up knob: per-thread stack limit in bytes
+        long v = atol(s);
+        for (auto &d : ctx->devs) {
+            cudaSetDevice(d.id);
+            if (v > 0) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)v);
+        }
+    }
     if (const char *s = getenv("BN254_CHUNK")) {
         long v = atol(s);
         if (v > 0) ctx->chunk = (size_t)v;
@@ -1030,3 +1037,133 @@ int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, doub
 }
 
 }  // extern "C"
+
+#ifdef BN_DEBUG_API
+// ---- debug-only entry points (not part of the ABI; built with -DBN_DEBUG_API for bring-up) ----------
+namespace {
+__global__ void k_dbg_svdw_g2(uint8_t *out, const uint8_t *u, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp2 x;
+    fp_from_be(x.c0, u + 64 * i);
+    fp_from_be(x.c1, u + 64 * i + 32);
+    g2a q;
+    bool ok = svdw_g2(q, x);
+    if (ok) g2a_to_bytes(out + 128 * i, q);
+    else zero_bytes(out + 128 * i, 128);
+}
+__global__ void k_dbg_clear_g2(uint8_t *out, const uint8_t *in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2a a;
+    g2a_from_bytes(a, in + 128 * i);
+    g2p p;
+    pt_from_affine(p, a.x, a.y, false);
+    g2_clear_cofactor(p, p);
+    pt_to_affine(a.x, a.y, a.inf, p);
+    g2a_to_bytes(out + 128 * i, a);
+}
+__global__ void k_dbg_h2f_g2(uint8_t *out, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint8_t okm[192];
+    expand_message_xmd(okm, 192, msg, len, dst, dst_len);
+    for (int k = 0; k < 4; k++) {
+        fp u;
+        fp_from_okm(u, okm + 48 * k);
+        fp_to_be(out + 32 * k, u);
+    }
+}
+// whole hash_to_g2 (count 1) with intermediates: out = u (64) || q (128) || cleared (128) || library result (128)
+__global__ void k_dbg_hash_g2(uint8_t *out, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint8_t okm[192];
+    fp2 u;
+    g2a q;
+    g2p a;
+    expand_message_xmd(okm, 96, msg, len, dst, dst_len);
+    fp_from_okm(u.c0, okm);
+    fp_from_okm(u.c1, okm + 48);
+    fp_to_be(out, u.c0);
+    fp_to_be(out + 32, u.c1);
+    bool ok = svdw_g2(q, u);
+    g2a_to_bytes(out + 64, q);
+    pt_from_affine(a, q.x, q.y, false);
+    g2_clear_cofactor(a, a);
+    g2a r;
+    pt_to_affine(r.x, r.y, r.inf, a);
+    g2a_to_bytes(out + 192, r);
+    // primitives on q: [x]q, psi(q), 2q, q + psi(q)   (each to affine) at out + 512 ...
+    {
+        g2p P, R;
+        g2a A;
+        const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
+        pt_from_affine(P, q.x, q.y, false);
+        pt_mul(R, P, xw, 63);
+        pt_to_affine(A.x, A.y, A.inf, R);
+        g2a_to_bytes(out + 512, A);
+        g2_psi(R, P);
+        pt_to_affine(A.x, A.y, A.inf, R);
+        g2a_to_bytes(out + 640, A);
+        pt_dbl(R, P);
+        pt_to_affine(A.x, A.y, A.inf, R);
+        g2a_to_bytes(out + 768, A);
+        g2p S;
+        g2_psi(S, P);
+        pt_add(R, P, S);
+        pt_to_affine(A.x, A.y, A.inf, R);
+        g2a_to_bytes(out + 896, A);
+    }
+    {   // Fp2 primitives on (q.x, q.y), 64 bytes each (c0 || c1) at out + 1024 + 64 k
+        fp2 r;
+        uint8_t *o = out + 1024;
+#define DUMP(k) fp_to_be(o + 64 * (k), r.c0); fp_to_be(o + 64 * (k) + 32, r.c1);
+        fp2_inv(r, q.x); DUMP(0)
+        fp2_mul(r, q.x, q.y); DUMP(1)
+        fp2_sqr(r, q.x); DUMP(2)
+        fp2_add(r, q.x, q.y); DUMP(3)
+        fp2_sub(r, q.x, q.y); DUMP(4)
+        fp2_neg(r, q.x); DUMP(5)
+        fp2_conj(r, q.x); DUMP(6)
+        fp2_mul_xi(r, q.x); DUMP(7)
+        fp_inv(r.c0, q.x.c0); fp_set_zero(r.c1); DUMP(8)
+        r = q.x; fp2_inv(r, r); DUMP(9)
+        fp2_mul(r, q.x, kfp2(k::B2_3)); DUMP(10)
+        fp2_dbl(r, q.x); DUMP(11)
+        r = q.x; fp2_add(r, r, r); DUMP(12)
+        r = q.x; fp2_mul(r, q.y, r); DUMP(13)
+        r = q.x; fp2_mul(r, r, q.y); DUMP(14)
+        r = q.x; fp2_sqr(r, r); DUMP(15)
+        r = q.x; fp2_sub(r, q.y, r); DUMP(16)
+        r = q.x; fp2_mul(r, r, kfp2(k::B2_3)); DUMP(17)
+        r = q.x; fp2_add(r, q.y, r); DUMP(18)
+        r = q.x; fp2_mul(r, r, r); DUMP(19)
+    }
+    g2a h;
+    int count = (int)out[511];  // runtime value (the host passes it here) so nothing is constant-folded
+    bool ok2 = hash_to_g2(h, msg, len, dst, dst_len, count);
+    g2a_to_bytes(out + 320, h);
+    out[448] = ok;
+    out[449] = ok2;
+}
+}  // namespace
+extern "C" int bn254_debug(bn254_ctx *ctx, int what, const uint8_t *in, size_t n, const uint8_t *dst, size_t dst_len, uint8_t *out) {
+    Dev &d = ctx->devs[0];
+    cudaSetDevice(d.id);
+    size_t rin = what == 0 ? 64 : (what == 1 ? 128 : 1), rout = 128;
+    uint8_t *din, *dout, *ddst;
+    cudaMalloc(&din, n * rin + 16);
+    cudaMalloc(&dout, (what >= 2 ? 24 : n) * rout);
+    cudaMalloc(&ddst, dst_len + 16);
+    cudaMemcpy(din, in, n * rin, cudaMemcpyHostToDevice);
+    if (what == 3) cudaMemcpy(dout, out, 512, cudaMemcpyHostToDevice);
+    if (dst_len) cudaMemcpy(ddst, dst, dst_len, cudaMemcpyHostToDevice);
+    if (what == 0) k_dbg_svdw_g2<<<blocks(n, 64), 64>>>(dout, din, n);
+    else if (what == 1) k_dbg_clear_g2<<<blocks(n, 64), 64>>>(dout, din, n);
+    else if (what == 2) k_dbg_h2f_g2<<<1, 32>>>(dout, din, n, ddst, (uint32_t)dst_len);
+    else k_dbg_hash_g2<<<1, 32>>>(dout, din, n, ddst, (uint32_t)dst_len);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out, dout, (what >= 2 ? 24 : n) * rout, cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout); cudaFree(ddst);
+    return (int)e;
+}
+#endif

@@ -66,8 +66,11 @@ BN_INL void pt_from_affine(point<F> &r, const typename F::T &x, const typename F
 }
 
 // complete addition, RCB 2015/1060 Alg. 7 (g1.rs:744-786, g2.rs:789-831): 12 products + 2 by 3b
+#ifndef BN_PT
+#define BN_PT BN_NOINL
+#endif
 template <class F>
-BN_NOINL void pt_add(point<F> &r, const point<F> &a, const point<F> &b) {
+BN_PT void pt_add(point<F> &r, const point<F> &a, const point<F> &b) {
     typename F::T t0, t1, t2, t3, t4, x3, y3, z3;
     F::mul(t0, a.x, b.x);
     F::mul(t1, a.y, b.y);
@@ -108,7 +111,7 @@ BN_NOINL void pt_add(point<F> &r, const point<F> &a, const point<F> &b) {
 }
 // doubling, RCB Alg. 9 (g1.rs:789-818, g2.rs:834-863)
 template <class F>
-BN_NOINL void pt_dbl(point<F> &r, const point<F> &a) {
+BN_PT void pt_dbl(point<F> &r, const point<F> &a) {
     typename F::T t0, t1, t2, x3, y3, z3;
     F::sqr(t0, a.y);
     F::add(z3, t0, t0);

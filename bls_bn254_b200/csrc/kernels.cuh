@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_hash_g1(g1m *ou
     out[i] = p;
     fl[i] = f;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
+#ifndef BN_MINB_HASH2
+#define BN_MINB_HASH2 BN_MINB_HEAVY
+#endif
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HASH2) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                                                            size_t n, const uint8_t *dst, uint32_t dst_len, int count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -47,11 +47,29 @@ BN_INL bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) & fp_e
 #else
 #define BN_FP2MUL BN_INL
 #endif
-BN_LIGHT void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
-BN_LIGHT void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
-BN_LIGHT void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
-BN_LIGHT void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
-BN_LIGHT void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
+#ifndef BN_L_ADD
+#define BN_L_ADD BN_LIGHT
+#endif
+#ifndef BN_L_SUB
+#define BN_L_SUB BN_LIGHT
+#endif
+#ifndef BN_L_NEG
+#define BN_L_NEG BN_LIGHT
+#endif
+#ifndef BN_L_DBL
+#define BN_L_DBL BN_LIGHT
+#endif
+#ifndef BN_L_CONJ
+#define BN_L_CONJ BN_LIGHT
+#endif
+#ifndef BN_L_XI
+#define BN_L_XI BN_LIGHT
+#endif
+BN_L_ADD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+BN_L_SUB void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+BN_L_NEG void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+BN_L_DBL void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+BN_L_CONJ void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
 BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
 
 // fp2.rs:377-390 (there: 4 products).  Karatsuba with lazy reduction: three 512-bit products, the
@@ -106,7 +124,7 @@ BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
 }
 BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
-BN_LIGHT void fp2_mul_xi(fp2 &r, const fp2 &a) {
+BN_L_XI void fp2_mul_xi(fp2 &r, const fp2 &a) {
     fp t0, t1;
     fp_mul9(t0, a.c0);
     fp_mul9(t1, a.c1);
@@ -114,6 +132,67 @@ BN_LIGHT void fp2_mul_xi(fp2 &r, const fp2 &a) {
     fp_add(r.c1, t1, a.c0);
     r.c0 = t0;
 }
+// ---- fused forms: the Karatsuba glue of the Fp6 routines in ONE call each, intermediates in
+// registers (the tiny add/sub functions they replace spent their time loading and storing operands:
+// profiles/r01_notes.md).
+// r = (a0 + a1)(b0 + b1).  The b-side sums stay unreduced: they are the row-scanned operands of fp_dot2,
+// which may be any 256-bit value; the a-side sums are reduced (multiplicand bound, see fp_dot2_inl).
+#ifndef BN_NO_FUSED
+BN_NOINL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) {
+    fp s0, s1, u0, u1, nu1, c0;
+    fp_add(s0, a0.c0, a1.c0);
+    fp_add(s1, a0.c1, a1.c1);
+    (void)add_n(u0.v, b0.c0.v, b1.c0.v);   // < 2p
+    (void)add_n(u1.v, b0.c1.v, b1.c1.v);   // < 2p
+    fp twop = {{BN_P0 << 1, (BN_P1 << 1) | (BN_P0 >> 31), (BN_P2 << 1) | (BN_P1 >> 31), (BN_P3 << 1) | (BN_P2 >> 31),
+                (BN_P4 << 1) | (BN_P3 >> 31), (BN_P5 << 1) | (BN_P4 >> 31), (BN_P6 << 1) | (BN_P5 >> 31), (BN_P7 << 1) | (BN_P6 >> 31)}};
+    (void)sub_n(nu1.v, twop.v, u1.v);      // 2p - u1 in [0, 2p]: congruent to -u1
+    fp_dot2(c0, s0, u0, s1, nu1);
+    fp_dot2(r.c1, s0, u1, s1, u0);
+    r.c0 = c0;
+}
+// r = (a0 + a1) b
+BN_NOINL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b) {
+    fp s0, s1, nb1, c0;
+    fp_add(s0, a0.c0, a1.c0);
+    fp_add(s1, a0.c1, a1.c1);
+    fp_neg(nb1, b.c1);
+    fp_dot2(c0, s0, b.c0, s1, nb1);
+    fp_dot2(r.c1, s0, b.c1, s1, b.c0);
+    r.c0 = c0;
+}
+BN_INL void fp2_xi_regs(fp2 &r, const fp2 &a) {
+    fp t0, t1;
+    fp_mul9(t0, a.c0);
+    fp_mul9(t1, a.c1);
+    fp_sub(t0, t0, a.c1);
+    fp_add(r.c1, t1, a.c0);
+    r.c0 = t0;
+}
+// mode 0: r = t - s1 - s2 + a1      mode 1: r = xi (t - s1 - s2) + a1      mode 2: r = t - s1 - s2 + xi a1
+// (s2 and a1 may be null: skipped)
+BN_NOINL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode) {
+    fp2 x;
+    fp_sub(x.c0, t.c0, s1.c0);
+    fp_sub(x.c1, t.c1, s1.c1);
+    if (s2) {
+        fp_sub(x.c0, x.c0, s2->c0);
+        fp_sub(x.c1, x.c1, s2->c1);
+    }
+    if (mode == 1) fp2_xi_regs(x, x);
+    if (a1) {
+        fp2 y = *a1;
+        if (mode == 2) fp2_xi_regs(y, y);
+        fp_add(x.c0, x.c0, y.c0);
+        fp_add(x.c1, x.c1, y.c1);
+    }
+    r = x;
+}
+#else
+BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1);
+BN_INL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b);
+BN_INL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode);
+#endif
 // fp2.rs:161-166
 BN_NOINL void fp2_inv(fp2 &r, const fp2 &a) {
     fp t0, t1;
@@ -286,6 +365,42 @@ BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
     fp_mul(r.v, a.v, n);
 }
 
+// generic (unfused) forms of the fused primitives: used by the lane-split type, and by fp2 under BN_NO_FUSED
+template <class T2>
+BN_INL void fp2_mul_sums_g(T2 &r, const T2 &a0, const T2 &a1, const T2 &b0, const T2 &b1) {
+    T2 s, u;
+    fp2_add(s, a0, a1);
+    fp2_add(u, b0, b1);
+    fp2_mul(r, s, u);
+}
+template <class T2>
+BN_INL void fp2_mul_sum1_g(T2 &r, const T2 &a0, const T2 &a1, const T2 &b) {
+    T2 s;
+    fp2_add(s, a0, a1);
+    fp2_mul(r, s, b);
+}
+template <class T2>
+BN_INL void fp2_comb_g(T2 &r, const T2 &t, const T2 &s1, const T2 *s2, const T2 *a1, int mode) {
+    T2 x, y;
+    fp2_sub(x, t, s1);
+    if (s2) fp2_sub(x, x, *s2);
+    if (mode == 1) fp2_mul_xi(x, x);
+    if (a1) {
+        y = *a1;
+        if (mode == 2) fp2_mul_xi(y, y);
+        fp2_add(x, x, y);
+    }
+    r = x;
+}
+BN_INL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
+BN_INL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) { fp2_mul_sum1_g(r, a0, a1, b); }
+BN_INL void fp2_comb(fp2l &r, const fp2l &t, const fp2l &s1, const fp2l *s2, const fp2l *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
+#ifdef BN_NO_FUSED
+BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
+BN_INL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b) { fp2_mul_sum1_g(r, a0, a1, b); }
+BN_INL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
+#endif
+
 // ------------------------------------------------------------------------------------------ Fp6
 template <class T2>
 BN_INL void fp6_add(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
@@ -295,31 +410,34 @@ template <class T2>
 BN_INL void fp6_neg(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
 template <class T2>
 BN_INL void fp6_dbl(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
-// Karatsuba, 6 Fp2 products (role of fp6.rs:225-242)
+// Karatsuba, 6 Fp2 products (role of fp6.rs:225-242); r may alias a or b
 template <class T2>
 BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
-    T2 v0, v1, v2, t0, t1, t2, c0, c1;
+    T2 v0, v1, v2, t, c0, c1;
     fp2_mul(v0, a.c0, b.c0);
     fp2_mul(v1, a.c1, b.c1);
     fp2_mul(v2, a.c2, b.c2);
-    fp2_add(t0, a.c1, a.c2); fp2_add(t1, b.c1, b.c2); fp2_mul(t2, t0, t1);
-    fp2_sub(t2, t2, v1); fp2_sub(t2, t2, v2); fp2_mul_xi(t2, t2); fp2_add(c0, t2, v0);
-    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b.c0, b.c1); fp2_mul(t2, t0, t1);
-    fp2_sub(t2, t2, v0); fp2_sub(t2, t2, v1); fp2_mul_xi(t0, v2); fp2_add(c1, t2, t0);
-    fp2_add(t0, a.c0, a.c2); fp2_add(t1, b.c0, b.c2); fp2_mul(t2, t0, t1);
-    fp2_sub(t2, t2, v0); fp2_sub(t2, t2, v2); fp2_add(r.c2, t2, v1);
+    fp2_mul_sums(t, a.c1, a.c2, b.c1, b.c2);
+    fp2_comb(c0, t, v1, &v2, &v0, 1);      // xi ((a1+a2)(b1+b2) - v1 - v2) + v0
+    fp2_mul_sums(t, a.c0, a.c1, b.c0, b.c1);
+    fp2_comb(c1, t, v0, &v1, &v2, 2);      // (a0+a1)(b0+b1) - v0 - v1 + xi v2
+    fp2_mul_sums(t, a.c0, a.c2, b.c0, b.c2);
+    fp2_comb(r.c2, t, v0, &v2, &v1, 0);    // (a0+a2)(b0+b2) - v0 - v2 + v1
     r.c0 = c0;
     r.c1 = c1;
 }
-// a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01)
+// a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01); r may alias a
 template <class T2>
 BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, const T2 &b1) {
-    T2 v0, v1, t0, t1, t2, c0, c1;
+    T2 v0, v1, t, c0, c1;
     fp2_mul(v0, a.c0, b0);
     fp2_mul(v1, a.c1, b1);
-    fp2_add(t0, a.c1, a.c2); fp2_mul(t2, t0, b1); fp2_sub(t2, t2, v1); fp2_mul_xi(t2, t2); fp2_add(c0, t2, v0);
-    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t2, t0, t1); fp2_sub(t2, t2, v0); fp2_sub(c1, t2, v1);
-    fp2_add(t0, a.c0, a.c2); fp2_mul(t2, t0, b0); fp2_sub(t2, t2, v0); fp2_add(r.c2, t2, v1);
+    fp2_mul_sum1(t, a.c1, a.c2, b1);
+    fp2_comb(c0, t, v1, (const T2 *)nullptr, &v0, 1);   // xi ((a1+a2) b1 - v1) + v0
+    fp2_mul_sums(t, a.c0, a.c1, b0, b1);
+    fp2_comb(c1, t, v0, &v1, (const T2 *)nullptr, 0);   // (a0+a1)(b0+b1) - v0 - v1
+    fp2_mul_sum1(t, a.c0, a.c2, b0);
+    fp2_comb(r.c2, t, v0, (const T2 *)nullptr, &v1, 0); // (a0+a2) b0 - v0 + v1
     r.c0 = c0;
     r.c1 = c1;
 }
