@@ -86,10 +86,12 @@ int ensure_t(Dev &d, Scratch s, size_t count, T **out) {
 
 inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
+#define BN_STR2(x) #x
+#define BN_STR(x) BN_STR2(x)
 #define LAUNCH(d, kern, n, tpb, ...)                                             \
     do {                                                                         \
         if ((n) > 0) {                                                           \
-            ProfRec pr_ = {#kern, (size_t)(n), nullptr, nullptr};                \
+            ProfRec pr_ = {BN_STR(kern), (size_t)(n), nullptr, nullptr};                \
             if ((d).prof) {                                                      \
                 CK(d, cudaEventCreate(&pr_.e0));                                 \
                 CK(d, cudaEventCreate(&pr_.e1));                                 \

@@ -79,8 +79,8 @@ BN_INL void item_hash_g2(g2m &out, uint8_t &fl, const uint8_t *msg, size_t len, 
 // ---- Miller loops ------------------------------------------------------------------------------
 // one pair (pairing(), pairings.rs:760-802 without the final exponentiation)
 BN_INL void item_miller1(fp12 &f, uint8_t &fl, const g1m &p, uint8_t flp, const g2m &q, uint8_t flq) {
-    fp px[1] = {p.x}, py[1] = {p.y};
-    fp2 qx[1] = {q.x}, qy[1] = {q.y};
+    const fp *px[1] = {&p.x}, *py[1] = {&p.y};
+    const fp2 *qx[1] = {&q.x}, *qy[1] = {&q.y};
     bool live[1] = {((flp | flq) & (FL_INF | FL_BAD)) == 0};
     miller_loop<1, false, fp2>(f, px, py, qx, qy, live);
     fl = ((flp | flq) & FL_BAD) ? FL_BAD : 0;
@@ -89,14 +89,8 @@ BN_INL void item_miller1(fp12 &f, uint8_t &fl, const g1m &p, uint8_t flp, const 
 template <bool FIXED0>
 BN_INL void item_miller2(fp12 &f, uint8_t &fl, const g1m &p0, uint8_t flp0, const g2m *q0, uint8_t flq0, const g1m &p1, uint8_t flp1,
                          const g2m &q1, uint8_t flq1) {
-    fp px[2] = {p0.x, p1.x}, py[2] = {p0.y, p1.y};
-    fp2 qx[2], qy[2];
-    if (!FIXED0) {
-        qx[0] = q0->x;
-        qy[0] = q0->y;
-    }
-    qx[1] = q1.x;
-    qy[1] = q1.y;
+    const fp *px[2] = {&p0.x, &p1.x}, *py[2] = {&p0.y, &p1.y};
+    const fp2 *qx[2] = {FIXED0 ? nullptr : &q0->x, &q1.x}, *qy[2] = {FIXED0 ? nullptr : &q0->y, &q1.y};
     bool live[2] = {((flp0 | flq0) & (FL_INF | FL_BAD)) == 0, ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0};
     miller_loop<2, FIXED0, fp2>(f, px, py, qx, qy, live);
     fl = ((flp0 | flq0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
@@ -109,10 +103,11 @@ BN_INL void item_final_exp(fp12 &f) { final_exponentiation(f); }
 //      call these with identical arguments; `F` is the item's one-thread record in HBM and each lane
 //      reads / writes its own half of it. -------------------------------------------------------------
 BN_INL void item_miller1_l2(fp12 &F, uint8_t &fl, const g1m &p, uint8_t flp, const g2m &q, uint8_t flq) {
-    fp px[1] = {p.x}, py[1] = {p.y};
-    fp2l qx[1], qy[1];
-    fp2_load(qx[0], q.x);
-    fp2_load(qy[0], q.y);
+    const fp *px[1] = {&p.x}, *py[1] = {&p.y};
+    fp2l lx[1], ly[1];
+    fp2_load(lx[0], q.x);
+    fp2_load(ly[0], q.y);
+    const fp2l *qx[1] = {&lx[0]}, *qy[1] = {&ly[0]};
     bool live[1] = {((flp | flq) & (FL_INF | FL_BAD)) == 0};
     fp12l f;
     miller_loop<1, false, fp2l>(f, px, py, qx, qy, live);
@@ -122,14 +117,15 @@ BN_INL void item_miller1_l2(fp12 &F, uint8_t &fl, const g1m &p, uint8_t flp, con
 template <bool FIXED0>
 BN_INL void item_miller2_l2(fp12 &F, uint8_t &fl, const g1m &p0, uint8_t flp0, const g2m *q0, uint8_t flq0, const g1m &p1, uint8_t flp1,
                             const g2m &q1, uint8_t flq1) {
-    fp px[2] = {p0.x, p1.x}, py[2] = {p0.y, p1.y};
-    fp2l qx[2], qy[2];
+    const fp *px[2] = {&p0.x, &p1.x}, *py[2] = {&p0.y, &p1.y};
+    fp2l lx[2], ly[2];
     if (!FIXED0) {
-        fp2_load(qx[0], q0->x);
-        fp2_load(qy[0], q0->y);
+        fp2_load(lx[0], q0->x);
+        fp2_load(ly[0], q0->y);
     }
-    fp2_load(qx[1], q1.x);
-    fp2_load(qy[1], q1.y);
+    fp2_load(lx[1], q1.x);
+    fp2_load(ly[1], q1.y);
+    const fp2l *qx[2] = {&lx[0], &lx[1]}, *qy[2] = {&ly[0], &ly[1]};
     bool live[2] = {((flp0 | flq0) & (FL_INF | FL_BAD)) == 0, ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0};
     fp12l f;
     miller_loop<2, FIXED0, fp2l>(f, px, py, qx, qy, live);

@@ -95,15 +95,30 @@ __global__ void k_oversize_dst(uint8_t *out, const uint8_t *dst, size_t dst_len)
     if (blockIdx.x == 0 && threadIdx.x == 0) oversize_dst(out, dst, dst_len);
 }
 
+// Records move between HBM and the thread's (interleaved, coalesced) local memory through one small
+// out-of-line loop instead of unrolled struct copies: code size is what bounds the heavy kernels.
+__device__ __noinline__ void copy_words(uint32_t *dst, const uint32_t *src, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+}
+template <class T>
+__device__ __forceinline__ void copy_rec(T &dst, const T &src) {
+    copy_words(reinterpret_cast<uint32_t *>(&dst), reinterpret_cast<const uint32_t *>(&src), (int)(sizeof(T) / 4));
+}
+
 // Miller loops.  `bad` (optional) receives an atomic OR when an item carries FL_BAD.
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller1(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
                                                            const uint8_t *flQ, size_t n, int *bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f;
     uint8_t fl;
-    item_miller1(f, fl, P[i], flP[i], Q[i], flQ[i]);
-    F[i] = f;
+    fp12 f;
+    g1m p;
+    g2m q;
+    copy_rec(p, P[i]);
+    copy_rec(q, Q[i]);
+    item_miller1(f, fl, p, flP[i], q, flQ[i]);
+    copy_rec(F[i], f);
     if (flF) flF[i] = fl;
     if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
 }
@@ -112,10 +127,15 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2_fixed(f
                                                                  const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f;
     uint8_t fl;
-    item_miller2<true>(f, fl, P0[i], flP0[i], nullptr, 0, P1[i], flP1[i], Q1[i], flQ1[i]);
-    F[i] = f;
+    fp12 f;
+    g1m p0, p1;
+    g2m q1;
+    copy_rec(p0, P0[i]);
+    copy_rec(p1, P1[i]);
+    copy_rec(q1, Q1[i]);
+    item_miller2<true>(f, fl, p0, flP0[i], nullptr, 0, p1, flP1[i], q1, flQ1[i]);
+    copy_rec(F[i], f);
     flF[i] = fl;
 }
 // both pairs variable.  p0_stride = 0 broadcasts one P0 (min-pk: -g1) to every item.
@@ -124,10 +144,16 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F
                                                            const g2m *Q1, const uint8_t *flQ1, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f;
     uint8_t fl;
-    item_miller2<false>(f, fl, P0[i * p0_stride], flP0[i * p0_stride], &Q0[i], flQ0[i], P1[i], flP1[i], Q1[i], flQ1[i]);
-    F[i] = f;
+    fp12 f;
+    g1m p0, p1;
+    g2m q0, q1;
+    copy_rec(p0, P0[i * p0_stride]);
+    copy_rec(p1, P1[i]);
+    copy_rec(q0, Q0[i]);
+    copy_rec(q1, Q1[i]);
+    item_miller2<false>(f, fl, p0, flP0[i * p0_stride], &q0, flQ0[i], p1, flP1[i], q1, flQ1[i]);
+    copy_rec(F[i], f);
     flF[i] = fl;
 }
 #ifndef BN_MINB_FEXP
@@ -136,9 +162,10 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_FEXP) k_final_exp(fp12 *F, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f = F[i];
+    fp12 f;
+    copy_rec(f, F[i]);
     item_final_exp(f);
-    F[i] = f;
+    copy_rec(F[i], f);
 }
 // ---- two lanes per pairing (lane-split Fp2): thread t works on item t/2, lane parity t&1.  A warp
 //      whose 16 items are all out of range exits as a whole; in the last partial warp the idle pairs

@@ -84,31 +84,37 @@ BN_INL void ell(fp12_t<T2> &f, const line_t<T2> &l, const fp &px, const fp &py) 
     fp2_mul_fp(c1, l.b, px);
     fp12_mul_by_034(f, c0, c1, l.c);
 }
-// line idx of the fixed point -g2 (precomputed table, one-thread fp2 layout) in this thread's representation
-template <class T2>
-BN_INL void fixed_line(line_t<T2> &l, int idx) {
+// line idx of the fixed point -g2 (precomputed table in constant memory, one-thread fp2 layout).
+// One thread per pairing multiplies straight out of the table; a lane pair first picks its halves.
+BN_INL void ell_fixed(fp12_t<fp2> &f, int idx, const fp &px, const fp &py) {
+    ell(f, *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]), px, py);
+}
+BN_INL void ell_fixed(fp12_t<fp2l> &f, int idx, const fp &px, const fp &py) {
     const line_t<fp2> &m = *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]);
+    line_t<fp2l> l;
     fp2_load(l.a, m.a);
     fp2_load(l.b, m.b);
     fp2_load(l.c, m.c);
+    ell(f, l, px, py);
 }
 
 // Product of NP Miller loops with one shared squaring per step (multi_miller_loop,
 // pairings.rs:808-857).  Pair i is skipped when live[i] is false (identity inputs contribute 1,
 // pairings.rs:820-835).  When FIXED0, pair 0 is (P0, -g2) and its 88 lines come from the
 // precomputed table (the G2Prepared role, pairings.rs:609-660) instead of being recomputed.
+// Inputs are passed by pointer (no staging copies: code size bounds these kernels).
 template <int NP, bool FIXED0, class T2>
-BN_INL void miller_loop(fp12_t<T2> &f, const fp *px, const fp *py, const T2 *qx, const T2 *qy, const bool *live) {
+BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py, const T2 *const *qx, const T2 *const *qy, const bool *live) {
     g2j<T2> r[NP];
     T2 nqy[NP];
     line_t<T2> l;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         if (FIXED0 && i == 0) continue;
-        r[i].x = qx[i];
-        r[i].y = qy[i];
+        r[i].x = *qx[i];
+        r[i].y = *qy[i];
         fp2_set_one(r[i].z);
-        fp2_neg(nqy[i], qy[i]);
+        fp2_neg(nqy[i], *qy[i]);
     }
     fp12_set_one(f);
     int idx = 0;
@@ -119,18 +125,24 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *px, const fp *py, const T2 *qx,
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (!live[i]) continue;
-            if (FIXED0 && i == 0) fixed_line(l, idx);
-            else doubling_step(l, r[i]);
-            ell(f, l, px[i], py[i]);
+            if (FIXED0 && i == 0) {
+                ell_fixed(f, idx, *px[0], *py[0]);
+            } else {
+                doubling_step(l, r[i]);
+                ell(f, l, *px[i], *py[i]);
+            }
         }
         idx++;
         if (d) {
 #pragma unroll
             for (int i = 0; i < NP; i++) {
                 if (!live[i]) continue;
-                if (FIXED0 && i == 0) fixed_line(l, idx);
-                else addition_step(l, r[i], qx[i], d > 0 ? qy[i] : nqy[i]);
-                ell(f, l, px[i], py[i]);
+                if (FIXED0 && i == 0) {
+                    ell_fixed(f, idx, *px[0], *py[0]);
+                } else {
+                    addition_step(l, r[i], *qx[i], d > 0 ? *qy[i] : nqy[i]);
+                    ell(f, l, *px[i], *py[i]);
+                }
             }
             idx++;
         }
@@ -140,23 +152,21 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *px, const fp *py, const T2 *qx,
     for (int i = 0; i < NP; i++) {
         if (!live[i]) continue;
         if (FIXED0 && i == 0) {
-            fixed_line(l, idx);
-            ell(f, l, px[0], py[0]);
-            fixed_line(l, idx + 1);
-            ell(f, l, px[0], py[0]);
+            ell_fixed(f, idx, *px[0], *py[0]);
+            ell_fixed(f, idx + 1, *px[0], *py[0]);
         } else {
             T2 q1x, q1y, q2x, q2y, t, eu, ev;
             fp2_load(eu, kfp2(k::ENDO_U));
             fp2_load(ev, kfp2(k::ENDO_V));
-            fp2_conj(t, qx[i]); fp2_mul(q1x, t, eu);
-            fp2_conj(t, qy[i]); fp2_mul(q1y, t, ev);
+            fp2_conj(t, *qx[i]); fp2_mul(q1x, t, eu);
+            fp2_conj(t, *qy[i]); fp2_mul(q1y, t, ev);
             fp2_conj(t, q1x); fp2_mul(q2x, t, eu);
             fp2_conj(t, q1y); fp2_mul(q2y, t, ev);
             fp2_neg(q2y, q2y);
             addition_step(l, r[i], q1x, q1y);
-            ell(f, l, px[i], py[i]);
+            ell(f, l, *px[i], *py[i]);
             addition_step(l, r[i], q2x, q2y);
-            ell(f, l, px[i], py[i]);
+            ell(f, l, *px[i], *py[i]);
         }
     }
 }

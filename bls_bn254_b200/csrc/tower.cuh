@@ -137,7 +137,7 @@ BN_L_XI void fp2_mul_xi(fp2 &r, const fp2 &a) {
 // profiles/r01_notes.md).
 // r = (a0 + a1)(b0 + b1).  The b-side sums stay unreduced: they are the row-scanned operands of fp_dot2,
 // which may be any 256-bit value; the a-side sums are reduced (multiplicand bound, see fp_dot2_inl).
-#ifndef BN_NO_FUSED
+#ifdef BN_FUSED  // measured slower on B200 (larger code, instruction cache): opt-in
 BN_NOINL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) {
     fp s0, s1, u0, u1, nu1, c0;
     fp_add(s0, a0.c0, a1.c0);
@@ -395,7 +395,7 @@ BN_INL void fp2_comb_g(T2 &r, const T2 &t, const T2 &s1, const T2 *s2, const T2 
 BN_INL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
 BN_INL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) { fp2_mul_sum1_g(r, a0, a1, b); }
 BN_INL void fp2_comb(fp2l &r, const fp2l &t, const fp2l &s1, const fp2l *s2, const fp2l *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
-#ifdef BN_NO_FUSED
+#ifndef BN_FUSED
 BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
 BN_INL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b) { fp2_mul_sum1_g(r, a0, a1, b); }
 BN_INL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
@@ -410,6 +410,7 @@ template <class T2>
 BN_INL void fp6_neg(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
 template <class T2>
 BN_INL void fp6_dbl(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
+#ifdef BN_FUSED
 // Karatsuba, 6 Fp2 products (role of fp6.rs:225-242); r may alias a or b
 template <class T2>
 BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
@@ -441,8 +442,52 @@ BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, cons
     r.c0 = c0;
     r.c1 = c1;
 }
+#else
+// Karatsuba, 6 Fp2 products (role of fp6.rs:225-242).  r must NOT alias a or b (results are written
+// as they are produced, no staging copies: code size is what bounds these kernels).
+template <class T2>
+BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
+    T2 v0, v1, v2, t0, t1;
+    fp2_mul(v0, a.c0, b.c0);
+    fp2_mul(v1, a.c1, b.c1);
+    fp2_mul(v2, a.c2, b.c2);
+    fp2_add(t0, a.c1, a.c2); fp2_add(t1, b.c1, b.c2); fp2_mul(t0, t0, t1);
+    fp2_sub(t0, t0, v1); fp2_sub(t0, t0, v2); fp2_mul_xi(t0, t0); fp2_add(r.c0, t0, v0);
+    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b.c0, b.c1); fp2_mul(t0, t0, t1);
+    fp2_sub(t0, t0, v0); fp2_sub(t0, t0, v1); fp2_mul_xi(t1, v2); fp2_add(r.c1, t0, t1);
+    fp2_add(t0, a.c0, a.c2); fp2_add(t1, b.c0, b.c2); fp2_mul(t0, t0, t1);
+    fp2_sub(t0, t0, v0); fp2_sub(t0, t0, v2); fp2_add(r.c2, t0, v1);
+}
+// a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01).  r must not alias a.
+template <class T2>
+BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, const T2 &b1) {
+    T2 v0, v1, t0, t1;
+    fp2_mul(v0, a.c0, b0);
+    fp2_mul(v1, a.c1, b1);
+    fp2_add(t0, a.c1, a.c2); fp2_mul(t0, t0, b1); fp2_sub(t0, t0, v1); fp2_mul_xi(t0, t0); fp2_add(r.c0, t0, v0);
+    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t0, t0, t1); fp2_sub(t0, t0, v0); fp2_sub(r.c1, t0, v1);
+    fp2_add(t0, a.c0, a.c2); fp2_mul(t0, t0, b0); fp2_sub(t0, t0, v0); fp2_add(r.c2, t0, v1);
+}
+#endif
 template <class T2>
 BN_INL void fp6_mul_fp2(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b) { fp2_mul(r.c0, a.c0, b); fp2_mul(r.c1, a.c1, b); fp2_mul(r.c2, a.c2, b); }
+// r = a + v b,  r = a - v b  (v (b0, b1, b2) = (xi b2, b0, b1)); r must not alias b
+template <class T2>
+BN_INL void fp6_add_mulv(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
+    T2 t;
+    fp2_mul_xi(t, b.c2);
+    fp2_add(r.c2, a.c2, b.c1);
+    fp2_add(r.c1, a.c1, b.c0);
+    fp2_add(r.c0, a.c0, t);
+}
+template <class T2>
+BN_INL void fp6_sub_mulv(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
+    T2 t;
+    fp2_mul_xi(t, b.c2);
+    fp2_sub(r.c2, a.c2, b.c1);
+    fp2_sub(r.c1, a.c1, b.c0);
+    fp2_sub(r.c0, a.c0, t);
+}
 // multiply by v (fp6.rs:146-152 with xi = 9+u)
 template <class T2>
 BN_INL void fp6_mul_v(fp6_t<T2> &r, const fp6_t<T2> &a) {
@@ -481,44 +526,41 @@ BN_INL bool fp12_is_one(const fp12_t<T2> &a) {
 // fp12.rs:203-210 (Karatsuba over Fp6; r may alias a or b)
 template <class T2>
 BN_NOINL void fp12_mul(fp12_t<T2> &r, const fp12_t<T2> &a, const fp12_t<T2> &b) {
-    fp6_t<T2> s, t, bb;
+    fp6_t<T2> s, t, u;
     fp6_add(s, a.c0, a.c1);
     fp6_add(t, b.c0, b.c1);
-    fp6_mul(s, s, t);            // (a0 + a1)(b0 + b1)
-    fp6_mul(t, a.c0, b.c0);      // aa
-    fp6_mul(bb, a.c1, b.c1);
-    fp6_sub(s, s, t);
-    fp6_sub(r.c1, s, bb);
-    fp6_mul_v(bb, bb);
-    fp6_add(r.c0, t, bb);
+    fp6_mul(u, s, t);            // (a0 + a1)(b0 + b1)
+    fp6_mul(s, a.c0, b.c0);      // aa
+    fp6_mul(t, a.c1, b.c1);      // bb
+    fp6_sub(u, u, s);
+    fp6_sub(r.c1, u, t);
+    fp6_add_mulv(r.c0, s, t);    // aa + v bb
 }
-// fp12.rs:170-180 (complex squaring, 2 Fp6 products)
+// fp12.rs:170-180 (complex squaring, 2 Fp6 products; r may alias a)
 template <class T2>
 BN_NOINL void fp12_sqr(fp12_t<T2> &r, const fp12_t<T2> &a) {
     fp6_t<T2> ab, s, t;
-    fp6_mul(ab, a.c0, a.c1);
     fp6_add(s, a.c0, a.c1);
-    fp6_mul_v(t, a.c1);
-    fp6_add(t, t, a.c0);
-    fp6_mul(s, s, t);
-    fp6_sub(s, s, ab);
-    fp6_mul_v(t, ab);
-    fp6_sub(r.c0, s, t);
+    fp6_add_mulv(t, a.c0, a.c1);     // a0 + v a1
+    fp6_mul(ab, a.c0, a.c1);
     fp6_dbl(r.c1, ab);
+    fp6_mul(r.c0, s, t);             // (a0 + a1)(a0 + v a1)   [a is dead from here]
+    fp6_sub(r.c0, r.c0, ab);
+    fp6_sub_mulv(r.c0, r.c0, ab);    // - ab - v ab
 }
 template <class T2>
 BN_INL void fp12_conj(fp12_t<T2> &r, const fp12_t<T2> &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }  // fp12.rs:131-136
 // fp12.rs:212-219
 template <class T2>
 BN_NOINL void fp12_inv(fp12_t<T2> &r, const fp12_t<T2> &a) {
-    fp6_t<T2> t0, t1;
+    fp6_t<T2> t0, t1, t2;
     fp6_mul(t0, a.c0, a.c0);
     fp6_mul(t1, a.c1, a.c1);
-    fp6_mul_v(t1, t1);
-    fp6_sub(t0, t0, t1);
-    fp6_inv(t0, t0);
-    fp6_mul(r.c0, a.c0, t0);
-    fp6_mul(t1, a.c1, t0);
+    fp6_sub_mulv(t0, t0, t1);
+    fp6_inv(t2, t0);
+    fp6_mul(t0, a.c0, t2);
+    fp6_mul(t1, a.c1, t2);
+    r.c0 = t0;
     fp6_neg(r.c1, t1);
 }
 // f * (c0 + c3 w + c4 w^3): the D-twist sparse line product, 13 Fp2 products
@@ -527,15 +569,14 @@ template <class T2>
 BN_NOINL void fp12_mul_by_034(fp12_t<T2> &f, const T2 &c0, const T2 &c3, const T2 &c4) {
     fp6_t<T2> t0, t1, s;
     T2 d;
-    fp6_mul_fp2(t0, f.c0, c0);
-    fp6_mul_by_01(t1, f.c1, c3, c4);
     fp2_add(d, c0, c3);
     fp6_add(s, f.c0, f.c1);
-    fp6_mul_by_01(s, s, d, c4);
-    fp6_sub(s, s, t0);
-    fp6_sub(f.c1, s, t1);
-    fp6_mul_v(t1, t1);
-    fp6_add(f.c0, t0, t1);
+    fp6_mul_by_01(t1, s, d, c4);         // (f0 + f1)(l0 + l1)
+    fp6_mul_fp2(t0, f.c0, c0);           // f0 l0
+    fp6_mul_by_01(s, f.c1, c3, c4);      // f1 l1
+    fp6_sub(t1, t1, t0);
+    fp6_sub(f.c1, t1, s);
+    fp6_add_mulv(f.c0, t0, s);
 }
 // coefficient of w^i: i even -> c0.c(i/2), i odd -> c1.c((i-1)/2)
 template <class T2>
