@@ -378,9 +378,16 @@ def main():
     top_ops = KERNEL_M.get(top_name, 0) * M_IMAD * top_items
     achieved = top_ops / (top_ms / top_cnt * 1e-3) if top_ms else 0.0
     whole_ops = WORK_M[w] * M_IMAD * n * args.steps
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture (same launch size only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr["items_per_launch"] == top_items and top_name in tr["kernels"]:
+            traffic = tr["kernels"][top_name]["dram_read_bytes"] + tr["kernels"][top_name]["dram_write_bytes"]
+    except Exception:
+        pass
     roofline = {
         "bound": "int32_imad", "kernel": top_name, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TIMAD-op/s", "frac": achieved / peak,
-        "traffic": None,
+        "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json): local-memory stack write-back, not algorithmic bytes",
         "peak_source": "measured live by bn254_imad_peak (%s chains, all SMs); MEASURED_PEAKS.json has no INT32 figure" % peak_name,
         "peaks_measured_tops": {k: v / 1e12 for k, v in peaks.items()},
         "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
