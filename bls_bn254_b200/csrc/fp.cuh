@@ -38,7 +38,10 @@
 
 namespace bn {
 
-struct fp {
+#ifndef BN_FP_ALIGN
+#define BN_FP_ALIGN 16   // 128-bit vector loads / stores of field elements (local, global and constant memory)
+#endif
+struct alignas(BN_FP_ALIGN) fp {
     uint32_t v[8];
 };
 

@@ -65,11 +65,38 @@ BN_INL bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) & fp_e
 #ifndef BN_L_XI
 #define BN_L_XI BN_LIGHT
 #endif
-BN_L_ADD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
-BN_L_SUB void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
-BN_L_NEG void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
-BN_L_DBL void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
-BN_L_CONJ void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }  // fp2.rs:428-437
+// Each of these first copies its operands into registers as whole (16-byte aligned) structs: all the
+// 128-bit loads issue together, before the carry chains, and the result leaves as 128-bit stores.
+BN_L_ADD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) {
+    fp2 x = a, y = b, z;
+    fp_add(z.c0, x.c0, y.c0);
+    fp_add(z.c1, x.c1, y.c1);
+    r = z;
+}
+BN_L_SUB void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) {
+    fp2 x = a, y = b, z;
+    fp_sub(z.c0, x.c0, y.c0);
+    fp_sub(z.c1, x.c1, y.c1);
+    r = z;
+}
+BN_L_NEG void fp2_neg(fp2 &r, const fp2 &a) {
+    fp2 x = a, z;
+    fp_neg(z.c0, x.c0);
+    fp_neg(z.c1, x.c1);
+    r = z;
+}
+BN_L_DBL void fp2_dbl(fp2 &r, const fp2 &a) {
+    fp2 x = a, z;
+    fp_dbl(z.c0, x.c0);
+    fp_dbl(z.c1, x.c1);
+    r = z;
+}
+BN_L_CONJ void fp2_conj(fp2 &r, const fp2 &a) {  // fp2.rs:428-437
+    fp2 x = a, z;
+    z.c0 = x.c0;
+    fp_neg(z.c1, x.c1);
+    r = z;
+}
 BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
 
 // fp2.rs:377-390 (there: 4 products).  Karatsuba with lazy reduction: three 512-bit products, the
@@ -94,11 +121,12 @@ BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
 #elif !defined(BN_FP2_KARATSUBA)
 // c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0: two fused dot products (fp_dot2), no Karatsuba additions
 BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
-    fp nb1, c0;
-    fp_neg(nb1, b.c1);
-    fp_dot2(c0, a.c0, b.c0, a.c1, nb1);
-    fp_dot2(r.c1, a.c0, b.c1, a.c1, b.c0);
-    r.c0 = c0;
+    fp2 x = a, y = b, z;
+    fp nb1;
+    fp_neg(nb1, y.c1);
+    fp_dot2(z.c0, x.c0, y.c0, x.c1, nb1);
+    fp_dot2(z.c1, x.c0, y.c1, x.c1, y.c0);
+    r = z;
 }
 #else
 BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
@@ -115,22 +143,31 @@ BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
 #endif
 // fp2.rs:392-402
 BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
+    fp2 x = a, z;
     fp s, d, m;
-    fp_add(s, a.c0, a.c1);
-    fp_sub(d, a.c0, a.c1);
-    fp_mul(m, a.c0, a.c1);
-    fp_mul(r.c0, s, d);
-    fp_dbl(r.c1, m);
+    fp_add(s, x.c0, x.c1);
+    fp_sub(d, x.c0, x.c1);
+    fp_mul(m, x.c0, x.c1);
+    fp_mul(z.c0, s, d);
+    fp_dbl(z.c1, m);
+    r = z;
 }
-BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
+BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) {
+    fp2 x = a, z;
+    fp y = s;
+    fp_mul(z.c0, x.c0, y);
+    fp_mul(z.c1, x.c1, y);
+    r = z;
+}
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
 BN_L_XI void fp2_mul_xi(fp2 &r, const fp2 &a) {
+    fp2 x = a, z;
     fp t0, t1;
-    fp_mul9(t0, a.c0);
-    fp_mul9(t1, a.c1);
-    fp_sub(t0, t0, a.c1);
-    fp_add(r.c1, t1, a.c0);
-    r.c0 = t0;
+    fp_mul9(t0, x.c0);
+    fp_mul9(t1, x.c1);
+    fp_sub(z.c0, t0, x.c1);
+    fp_add(z.c1, t1, x.c0);
+    r = z;
 }
 // ---- fused forms: the Karatsuba glue of the Fp6 routines in ONE call each, intermediates in
 // registers (the tiny add/sub functions they replace spent their time loading and storing operands:
