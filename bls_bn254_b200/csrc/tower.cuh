@@ -124,8 +124,13 @@ BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp2 x = a, y = b, z;
     fp nb1;
     fp_neg(nb1, y.c1);
+#ifndef BN_FP2MUL_CALLS   // both dot products inline: no call overhead, two independent chains for the scheduler
+    fp_dot2_inl(z.c0, x.c0, y.c0, x.c1, nb1);
+    fp_dot2_inl(z.c1, x.c0, y.c1, x.c1, y.c0);
+#else
     fp_dot2(z.c0, x.c0, y.c0, x.c1, nb1);
     fp_dot2(z.c1, x.c0, y.c1, x.c1, y.c0);
+#endif
     r = z;
 }
 #else
@@ -147,16 +152,26 @@ BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
     fp s, d, m;
     fp_add(s, x.c0, x.c1);
     fp_sub(d, x.c0, x.c1);
+#ifdef BN_FP2SQR_LEAF
+    fp_mul_inl(m, x.c0, x.c1);
+    fp_mul_inl(z.c0, s, d);
+#else
     fp_mul(m, x.c0, x.c1);
     fp_mul(z.c0, s, d);
+#endif
     fp_dbl(z.c1, m);
     r = z;
 }
 BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) {
     fp2 x = a, z;
     fp y = s;
+#ifdef BN_FP2SQR_LEAF
+    fp_mul_inl(z.c0, x.c0, y);
+    fp_mul_inl(z.c1, x.c1, y);
+#else
     fp_mul(z.c0, x.c0, y);
     fp_mul(z.c1, x.c1, y);
+#endif
     r = z;
 }
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
