@@ -72,7 +72,8 @@ def lib():
         L.bn254_aggregate_verify.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp]
         L.bn254_aggregate_partial.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp, vp]
         L.bn254_aggregate_finish.argtypes = [vp, vp, vp, sz, vp]
-        for name in ("bn254_g1_compress", "bn254_g2_compress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve", "bn254_g1_sum", "bn254_g2_sum"):
+        for name in ("bn254_g1_compress", "bn254_g2_compress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve", "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
+                     "bn254_g1_sum", "bn254_g2_sum"):
             getattr(L, name).argtypes = [vp, vp, sz, vp]
         for name in ("bn254_g1_decompress", "bn254_g2_decompress"):
             getattr(L, name).argtypes = [vp, vp, sz, vp, vp]
@@ -94,6 +95,7 @@ EXPORTED_SYMBOLS = [
     "bn254_pairing_batch", "bn254_miller_loop_batch", "bn254_multi_miller_loop", "bn254_final_exponentiation", "bn254_fp12_product",
     "bn254_verify_batch", "bn254_aggregate_verify", "bn254_aggregate_partial", "bn254_aggregate_finish",
     "bn254_g1_compress", "bn254_g1_decompress", "bn254_g2_compress", "bn254_g2_decompress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve",
+    "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
     "bn254_g1_mul", "bn254_g2_mul", "bn254_g1_sum", "bn254_g2_sum",
     "bn254_hash_to_g1_dev", "bn254_hash_to_g2_dev", "bn254_pairing_batch_dev", "bn254_verify_batch_dev", "bn254_aggregate_partial_dev",
     "bn254_imad_peak",

@@ -19,6 +19,7 @@ from . import _native
 
 MIN_SIG, MIN_PK = 0, 1
 CHECK_ON_CURVE = 1
+CHECK_SUBGROUP = 2
 
 
 class Bn254Error(Exception):
@@ -237,6 +238,8 @@ class Context:
     def g2_decompress(self, comp): return self._map(self._L.bn254_g2_decompress, comp, 64, 128, status=True)
     def g1_is_on_curve(self, pts): return self._map(self._L.bn254_g1_is_on_curve, pts, 64, 1)
     def g2_is_on_curve(self, pts): return self._map(self._L.bn254_g2_is_on_curve, pts, 128, 1)
+    def g1_is_torsion_free(self, pts): return self._map(self._L.bn254_g1_is_torsion_free, pts, 64, 1)
+    def g2_is_torsion_free(self, pts): return self._map(self._L.bn254_g2_is_torsion_free, pts, 128, 1)
     def g1_mul(self, pts, scalars): return self._map(self._L.bn254_g1_mul, pts, 64, 64, extra=scalars)
     def g2_mul(self, pts, scalars): return self._map(self._L.bn254_g2_mul, pts, 128, 128, extra=scalars)
 

@@ -262,15 +262,25 @@ struct VerifyBufs {
 int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                      const uint8_t *sigs, size_t lo, size_t hi, const uint8_t *dst, uint32_t dst_len, int check, uint8_t *ok) {
     size_t n = hi - lo;
+    const bool subgroup = (check & 2) != 0;
+    check &= 1;
     if (variant == BN254_MIN_SIG) {
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P0 + lo, b.flp0 + lo, sigs + 64 * lo, n, check);
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
+        if (subgroup) {
+            LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, b.flp0 + lo, b.P0 + lo, n);
+            LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
+        }
         if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         LAUNCH(d, K_MILLER2_FIXED, PAIR_THREADS(n), BN_TPB_HEAVY, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
                b.flq1 + lo, n);
     } else {
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q0 + lo, b.flq0 + lo, sigs + 128 * lo, n, check);
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
+        if (subgroup) {
+            LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq0 + lo, b.Q0 + lo, n);
+            LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, b.flp1 + lo, b.P1 + lo, n);
+        }
         if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         LAUNCH(d, K_MILLER2, PAIR_THREADS(n), BN_TPB_HEAVY, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo,
                b.flp1 + lo, b.Q1 + lo, b.flq1 + lo, n);
@@ -282,7 +292,7 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
 // verification of one chunk, device pointers in / out
 int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
                size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
-    int check = (flags & BN254_FLAG_CHECK_ON_CURVE) ? 1 : 0;
+    int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? 1 : 0) | ((flags & BN254_FLAG_CHECK_SUBGROUP) ? 2 : 0);
     VerifyBufs b = {};
     if (int rc = ensure_t(d, S_F, n, &b.F)) return rc;
     if (int rc = ensure_t(d, S_FLF, n, &b.flf)) return rc;
@@ -906,6 +916,18 @@ int bn254_g1_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *
 int bn254_g2_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
     return host_map(ctx, n, pts, 128, nullptr, 0, out, 1, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
         LAUNCH(d, k_g2_on_curve, m, BN_TPB_LIGHT, o, a, m);
+        return 0;
+    });
+}
+int bn254_g1_is_torsion_free(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 64, nullptr, 0, out, 1, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        LAUNCH(d, k_g1_torsion_free, m, BN_TPB_HEAVY, o, a, m);
+        return 0;
+    });
+}
+int bn254_g2_is_torsion_free(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out) {
+    return host_map(ctx, n, pts, 128, nullptr, 0, out, 1, nullptr, [](Dev &d, const uint8_t *a, const uint8_t *, size_t m, uint8_t *o, uint8_t *) {
+        LAUNCH(d, k_g2_torsion_free, m, BN_TPB_HEAVY, o, a, m);
         return 0;
     });
 }

@@ -168,6 +168,23 @@ BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const 
     flo = (fl & FL_BAD) ? FL_BAD : (inf ? FL_INF : 0);
 }
 
+// ---- subgroup membership (g1.rs:852-855, g2.rs:733-736: is_torsion_free = [r]P is the identity) ----
+// out = 1 for a decodable point on the curve whose order divides r (the identity included).
+BN_INL uint8_t item_g1_torsion_free(const g1m &p, uint8_t fl) {
+    if (fl & FL_BAD) return 0;
+    g1p a, r;
+    pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
+    pt_mul(r, a, k::R_ORDER, 254);
+    return fp_is_zero(r.z) ? 1 : 0;
+}
+BN_INL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
+    if (fl & FL_BAD) return 0;
+    g2p a, r;
+    pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
+    pt_mul(r, a, k::R_ORDER, 254);
+    return fp2_is_zero(r.z) ? 1 : 0;
+}
+
 // ---- compressed codecs (g1.rs:283-288 / 311-328, g2.rs:274-283 / 309-340) ------------------------
 // Decompression picks the root whose parity (G1) / sgn0 (G2) equals the flag bit, i.e. the inverse
 // of to_compressed.  (The reference's G1 from_compressed selects by is_high, g1.rs:320, which does

@@ -66,6 +66,50 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_on_curve(uint8_t *out, cons
     out[i] = (f & FL_BAD) ? 0 : 1;
 }
 
+// Records move between HBM and the thread's (interleaved, coalesced) local memory through one small
+// out-of-line loop instead of unrolled struct copies: code size is what bounds the heavy kernels.
+__device__ __noinline__ void copy_words(uint32_t *dst, const uint32_t *src, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+}
+template <class T>
+__device__ __forceinline__ void copy_rec(T &dst, const T &src) {
+    copy_words(reinterpret_cast<uint32_t *>(&dst), reinterpret_cast<const uint32_t *>(&src), (int)(sizeof(T) / 4));
+}
+
+// subgroup check straight from wire bytes (decode with the on-curve test, then [r]P == O)
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_torsion_free(uint8_t *out, const uint8_t *in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1m p;
+    uint8_t f;
+    item_g1_decode(p, f, in + 64 * i, true);
+    out[i] = item_g1_torsion_free(p, f);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_torsion_free(uint8_t *out, const uint8_t *in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2m p;
+    uint8_t f;
+    item_g2_decode(p, f, in + 128 * i, true);
+    out[i] = item_g2_torsion_free(p, f);
+}
+// flags |= FL_BAD where the (already decoded) point is not in the order-r subgroup
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_require_subgroup(uint8_t *fl, const g1m *P, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1m p;
+    copy_rec(p, P[i]);
+    if (!item_g1_torsion_free(p, fl[i])) fl[i] |= FL_BAD;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_require_subgroup(uint8_t *fl, const g2m *Q, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2m q;
+    copy_rec(q, Q[i]);
+    if (!item_g2_torsion_free(q, fl[i])) fl[i] |= FL_BAD;
+}
+
 // hash / encode to curve.  offsets are global offsets into the blob; `base` is the blob offset of
 // msgs[0] of this chunk.
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_hash_g1(g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
@@ -93,17 +137,6 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HASH2) k_hash_g2(g2m *ou
 }
 __global__ void k_oversize_dst(uint8_t *out, const uint8_t *dst, size_t dst_len) {
     if (blockIdx.x == 0 && threadIdx.x == 0) oversize_dst(out, dst, dst_len);
-}
-
-// Records move between HBM and the thread's (interleaved, coalesced) local memory through one small
-// out-of-line loop instead of unrolled struct copies: code size is what bounds the heavy kernels.
-__device__ __noinline__ void copy_words(uint32_t *dst, const uint32_t *src, int n) {
-#pragma unroll 1
-    for (int i = 0; i < n; i++) dst[i] = src[i];
-}
-template <class T>
-__device__ __forceinline__ void copy_rec(T &dst, const T &src) {
-    copy_words(reinterpret_cast<uint32_t *>(&dst), reinterpret_cast<const uint32_t *>(&src), (int)(sizeof(T) / 4));
 }
 
 // Miller loops.  `bad` (optional) receives an atomic OR when an item carries FL_BAD.

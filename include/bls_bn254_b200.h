@@ -45,6 +45,7 @@ typedef struct bn254_ctx bn254_ctx;
 #define BN254_MIN_SIG 0 /* pk in G2 (128 B), sig in G1 (64 B), messages hashed to G1 */
 #define BN254_MIN_PK 1  /* pk in G1 (64 B), sig in G2 (128 B), messages hashed to G2 */
 #define BN254_FLAG_CHECK_ON_CURVE 1u /* reject keys / signatures that are not on the curve */
+#define BN254_FLAG_CHECK_SUBGROUP 2u /* verify_batch: also require keys / signatures in the order-r subgroup (implies on-curve) */
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int bn254_device_count(void);
@@ -105,6 +106,9 @@ int bn254_g2_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out
 int bn254_g2_decompress(bn254_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out /* n*128 */, uint8_t *status);
 int bn254_g1_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
 int bn254_g2_is_on_curve(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
+/* is_torsion_free (g1.rs:852-855, g2.rs:733-736): 1 for a point on the curve with [r]P = identity */
+int bn254_g1_is_torsion_free(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
+int bn254_g2_is_torsion_free(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n */);
 
 /* ---- scalar multiplication and sums (sign / keygen / aggregate side; g1.rs:821-841,
  *      g2.rs:866-886).  scalars: n x 32-byte big-endian integers. -------------------------------- */

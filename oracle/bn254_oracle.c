@@ -1046,7 +1046,10 @@ EXPORT int orc_fp12_product(const uint8_t *in, size_t n, uint8_t *out) {
 }
 
 /* ---- BLS predicates.  variant 0 = min-sig (pk in G2 128 B, sig in G1
- * 64 B), 1 = min-pk (pk in G1 64 B, sig in G2 128 B).  flags bit0: reject points not on curve. */
+ * 64 B), 1 = min-pk (pk in G1 64 B, sig in G2 128 B).  flags bit0: reject points not on curve;
+ * bit1: also reject points outside the order-r subgroup. */
+static int g1a_torsion_free(const g1a *a);
+static int g2a_torsion_free(const g2a *a);
 typedef struct {
     int variant; const uint8_t *pks; const uint8_t *msgs; const uint64_t *off; const uint8_t *sigs;
     const uint8_t *dst; size_t dst_len; uint32_t flags; uint8_t *ok;
@@ -1059,13 +1062,15 @@ static int verify_one(const verify_args *a, size_t i) {
     if (a->variant == 0) {
         g2a pk; g1a sig, h;
         if (!g2a_from_bytes(&pk, a->pks + 128 * i) || !g1a_from_bytes(&sig, a->sigs + 64 * i)) return 0;
-        if ((a->flags & 1) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) return 0;
+        if ((a->flags & 3) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) return 0;
+        if ((a->flags & 2) && (!g2a_torsion_free(&pk) || !g1a_torsion_free(&sig))) return 0;
         if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
         ps[0] = sig; qs[0] = NEG_G2_GEN_A; ps[1] = h; qs[1] = pk;
     } else {
         g1a pk; g2a sig, h;
         if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) return 0;
-        if ((a->flags & 1) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) return 0;
+        if ((a->flags & 3) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) return 0;
+        if ((a->flags & 2) && (!g1a_torsion_free(&pk) || !g2a_torsion_free(&sig))) return 0;
         if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
         ps[0] = NEG_G1_GEN_A; qs[0] = sig; ps[1] = pk; qs[1] = h;
     }
@@ -1288,6 +1293,31 @@ EXPORT int orc_g2_decompress(const uint8_t *in, size_t n, uint8_t *out, uint8_t 
         if (status) status[i] = (uint8_t)ok;
         if (ok) g2a_to_bytes(out + 128 * i, &P); else memset(out + 128 * i, 0, 128);
     }
+    return 0;
+}
+/* is_torsion_free (g1.rs:852-855, g2.rs:733-736): [r]P == identity, for points on the curve */
+static int g1a_torsion_free(const g1a *a) {
+    g1p p, r;
+    if (!g1a_on_curve(a)) return 0;
+    g1_from_affine(&p, &a->x, &a->y, a->inf);
+    g1_mul_limbs(&r, &p, ORC_R_ORDER, 254);
+    return g1_is_identity(&r);
+}
+static int g2a_torsion_free(const g2a *a) {
+    g2p p, r;
+    if (!g2a_on_curve(a)) return 0;
+    g2_from_affine(&p, &a->x, &a->y, a->inf);
+    g2_mul_limbs(&r, &p, ORC_R_ORDER, 254);
+    return g2_is_identity(&r);
+}
+EXPORT int orc_g1_is_torsion_free(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) { g1a P; out[i] = (uint8_t)(g1a_from_bytes(&P, pts + 64 * i) && g1a_torsion_free(&P)); }
+    return 0;
+}
+EXPORT int orc_g2_is_torsion_free(const uint8_t *pts, size_t n, uint8_t *out) {
+    orc_init();
+    for (size_t i = 0; i < n; i++) { g2a P; out[i] = (uint8_t)(g2a_from_bytes(&P, pts + 128 * i) && g2a_torsion_free(&P)); }
     return 0;
 }
 /* on-curve predicates (g1.rs:383-391, g2.rs:409-414): out[i] = 1/0; undecodable -> 0 */

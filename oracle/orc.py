@@ -217,6 +217,20 @@ def g2_is_on_curve(pts):
     return out.raw
 
 
+def g1_is_torsion_free(pts):
+    n = len(pts) // 64
+    out = _buf(n)
+    lib().orc_g1_is_torsion_free(pts, C.c_size_t(n), out)
+    return out.raw
+
+
+def g2_is_torsion_free(pts):
+    n = len(pts) // 128
+    out = _buf(n)
+    lib().orc_g2_is_torsion_free(pts, C.c_size_t(n), out)
+    return out.raw
+
+
 def mul_count(reset=False):
     v = lib().orc_mul_count()
     if reset:

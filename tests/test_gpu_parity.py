@@ -281,3 +281,55 @@ def test_multi_device_ctx(orc, B):
     finally:
         c1.close()
         c2.close()
+
+
+def test_subgroup_checks(ctx, orc, B):
+    """is_torsion_free (g1.rs:852-855, g2.rs:733-736) and the CHECK_SUBGROUP flag of verify_batch."""
+    g1, g2 = _points(ctx, orc, 6, 17)
+    raw = orc.svdw_g2(b"".join((i + 5).to_bytes(32, "big") + (i + 9).to_bytes(32, "big") for i in range(4)))  # on the curve, outside the subgroup
+    ident2 = bytes(64) + bytes(63) + b"\x01"
+    pts2 = B.G2_GENERATOR + g2 + raw + ident2 + b"\xff" * 128
+    assert ctx.g2_is_torsion_free(pts2) == orc.g2_is_torsion_free(pts2)
+    assert ctx.g2_is_torsion_free(raw) == b"\x00" * 4 and ctx.g2_is_on_curve(raw) == b"\x01" * 4
+    off = bytearray(g1)
+    off[40] ^= 1
+    pts1 = B.G1_GENERATOR + g1 + bytes(off[:64])
+    assert ctx.g1_is_torsion_free(pts1) == orc.g1_is_torsion_free(pts1)
+    # a key outside the subgroup is rejected only with the flag
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, 8, variant=0, corrupt_every=0)
+    pks = raw[:128] + pks[128:]
+    for flags in (0, B.CHECK_ON_CURVE, B.CHECK_SUBGROUP):
+        assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=flags) == orc.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=flags, nthreads=8)
+    assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=B.CHECK_SUBGROUP)[1:] == b"\x01" * 7
+
+
+def test_ragged_sizes_and_long_messages(ctx, orc, B):
+    """batch sizes around the CTA / warp boundaries and messages from 0 bytes to 10 KB"""
+    rng = random.Random(33)
+    for n in (1, 31, 33, 63, 65, 127, 129):
+        msgs = [rng.randbytes(rng.choice((0, 1, 31, 32, 55, 56, 63, 64, 65, 119, 120, 200))) for _ in range(n)]
+        assert ctx.hash_to_g1(msgs, QUUX_G1) == orc.hash_to_g1(msgs, QUUX_G1, nthreads=8)
+    big = [rng.randbytes(10000), b"", rng.randbytes(4097)]
+    assert ctx.hash_to_g1(big, QUUX_G1) == orc.hash_to_g1(big, QUUX_G1)
+    assert ctx.hash_to_g2(big, QUUX_G2) == orc.hash_to_g2(big, QUUX_G2)
+    for n in (1, 33, 65):
+        pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=0, corrupt_every=4)
+        assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG) == exp == orc.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, nthreads=8)
+        g1, g2 = _points(ctx, orc, n, n)
+        assert ctx.pairing(g1, g2) == orc.pairing_batch(g1, g2, nthreads=8)
+
+
+def test_profile_and_launch_count(ctx, orc, B):
+    """every product call launches kernels of this library (no silent fallback), and the per-launch timer sees them"""
+    before = ctx.launch_count
+    ctx.profile(True)
+    ctx.profile_drain()
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, 16, variant=0, corrupt_every=0)
+    ctx.profile_drain()
+    assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG) == exp
+    recs = ctx.profile_drain()
+    ctx.profile(False)
+    names = [r[0] for r in recs]
+    assert names == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_miller2_fixed", "k_final_exp", "k_fp12_is_one"]
+    assert all(r[2] > 0 for r in recs)
+    assert ctx.launch_count > before
