@@ -293,10 +293,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---- roofline denominator: INT32 multiply-add peak, measured live --------------------------
-    peaks = {}
+    peaks, field_peaks = {}, {}
     if rank == 0:
         for mode, name in ((0, "mad.lo"), (1, "mad.lo+mad.hi"), (2, "imad.wide")):
             peaks[name] = max(ctx.imad_peak(mode, 20000)[0] for _ in range(2))
+        # field-level ceilings (registers only, no memory): canonical IMAD-ops/s of dependent Montgomery products /
+        # fused dot products with 1 and 4 warps per scheduler
+        for mode, name in ((1, "fp_mul"), (0, "fp_dot2")):
+            for wps in (4, 16):
+                field_peaks["%s_%dwarps_per_sm" % (name, wps)] = ctx.fp_peak(mode, wps, 4000) / 1e12
 
     # ---- warm-up ------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
@@ -400,6 +405,7 @@ def main():
         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json): local-memory stack write-back, not algorithmic bytes",
         "peak_source": "measured live by bn254_imad_peak (%s chains, all SMs); MEASURED_PEAKS.json has no INT32 figure" % peak_name,
         "peaks_measured_tops": {k: v / 1e12 for k, v in peaks.items()},
+        "field_level_tops": field_peaks,
         "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
         "whole_step_frac": whole_ops / (dev_ms * 1e-3) / peak,
         "kernel_pass_ms_per_step": prof_ms / args.steps,

@@ -85,6 +85,7 @@ def lib():
         L.bn254_verify_batch_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp]
         L.bn254_aggregate_partial_dev.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp, vp]
         L.bn254_imad_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.bn254_fp_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -98,5 +99,5 @@ EXPORTED_SYMBOLS = [
     "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
     "bn254_g1_mul", "bn254_g2_mul", "bn254_g1_sum", "bn254_g2_sum",
     "bn254_hash_to_g1_dev", "bn254_hash_to_g2_dev", "bn254_pairing_batch_dev", "bn254_verify_batch_dev", "bn254_aggregate_partial_dev",
-    "bn254_imad_peak",
+    "bn254_imad_peak", "bn254_fp_peak",
 ]

@@ -276,6 +276,14 @@ class Context:
         return ops.value, ms.value
 
 
+    def _fp_peak(self, mode, warps_per_sm, iters=4000):
+        ops = C.c_double()
+        self._ck(self._L.bn254_fp_peak(self._h, mode, warps_per_sm, iters, C.byref(ops)))
+        return ops.value
+
+
+Context.fp_peak = Context._fp_peak
+
 # G1 / G2 generators in wire form (g1.rs:274-280; fp2.rs:305-348)
 G1_GENERATOR = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
 G2_GENERATOR = bytes.fromhex(

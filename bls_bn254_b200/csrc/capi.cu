@@ -1111,6 +1111,40 @@ int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, doub
     DEV_EPILOGUE(rc);
 }
 
+// Field-level micro-benchmark (k_fp_peak): warps_per_sm warps of dependent fp_dot2 (mode 0) / fp_mul (mode 1)
+// chains per SM; returns canonical IMAD-ops/s (264 per product, 400 + 16 per fused dot product).
+int bn254_fp_peak(bn254_ctx *ctx, int mode, int warps_per_sm, int iters, double *ops_per_s) {
+    DEV_PROLOGUE();
+    if (iters < 1 || warps_per_sm < 1 || !ops_per_s) return fail_arg(ctx, "bad argument");
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CK(d, cudaGetDeviceProperties(&prop, d.id));
+        uint32_t *sink;
+        if (int rc = ensure_t(d, S_TMP, 16, &sink)) return rc;
+        int nblk = prop.multiProcessorCount * warps_per_sm;
+        cudaEvent_t e0, e1;
+        CK(d, cudaEventCreate(&e0));
+        CK(d, cudaEventCreate(&e1));
+        k_fp_peak<<<nblk, 32, 0, d.st>>>(sink, iters / 8 + 1, mode);
+        d.launches++;
+        CK(d, cudaEventRecord(e0, d.st));
+        k_fp_peak<<<nblk, 32, 0, d.st>>>(sink, iters, mode);
+        d.launches++;
+        CK(d, cudaEventRecord(e1, d.st));
+        CK(d, cudaEventSynchronize(e1));
+        CK(d, cudaGetLastError());
+        float ms = 0;
+        CK(d, cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        double per = mode == 0 ? 2.0 * 264.0 : (mode == 1 ? 264.0 : 4.0 * 264.0);   // a dot product does the work of two products
+        *ops_per_s = (double)nblk * 32.0 * (double)iters * per / (ms * 1e-3);
+        return 0;
+    };
+    int rc = body();
+    DEV_EPILOGUE(rc);
+}
+
 }  // extern "C"
 
 #ifdef BN_DEBUG_API

@@ -438,6 +438,64 @@ BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &
     r = s;
 }
 
+// Two independent fused dot products advanced row by row in lock step:
+//   r0 = (a b0 + c d0)/R,  r1 = (a b1 + c d1)/R      (same multiplicands a, c: an Fp2 product)
+// One warp alone reaches only ~64 % of the IMAD pipe on a single dot product (dependent carry chains,
+// measured with k_fp_peak); two interleaved instruction streams give the scheduler what a second warp
+// would.  Same frame and bounds as fp_dot2_inl.
+BN_INL void fp_dot2x2_inl(fp &r0, fp &r1, const fp &a, const fp &c, const fp &b0, const fp &d0, const fp &b1, const fp &d1) {
+    uint32_t E0[8], O0[8], E1[8], O1[8], m0, m1;
+    mul_lanes(E0, a.v[0], a.v[2], a.v[4], a.v[6], b0.v[0]);
+    mul_lanes(E1, a.v[0], a.v[2], a.v[4], a.v[6], b1.v[0]);
+    mul_lanes(O0, a.v[1], a.v[3], a.v[5], a.v[7], b0.v[0]);
+    mul_lanes(O1, a.v[1], a.v[3], a.v[5], a.v[7], b1.v[0]);
+    mad_lanes_nc(O0, c.v[1], c.v[3], c.v[5], c.v[7], d0.v[0]);
+    mad_lanes_nc(O1, c.v[1], c.v[3], c.v[5], c.v[7], d1.v[0]);
+    mad_lanes(E0, O0[7], c.v[0], c.v[2], c.v[4], c.v[6], d0.v[0]);
+    mad_lanes(E1, O1[7], c.v[0], c.v[2], c.v[4], c.v[6], d1.v[0]);
+    m0 = E0[0] * BN254_INV32;
+    m1 = E1[0] * BN254_INV32;
+    mad_p_odd(O0, m0);
+    mad_p_odd(O1, m1);
+    mad_p_even(E0, O0[7], m0);
+    mad_p_even(E1, O1[7], m1);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        uint32_t x0 = E0[1], x1 = E1[1];
+        uint32_t N0[8] = {E0[2], E0[3], E0[4], E0[5], E0[6], E0[7], 0u, 0u};
+        uint32_t N1[8] = {E1[2], E1[3], E1[4], E1[5], E1[6], E1[7], 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; k++) { E0[k] = O0[k]; E1[k] = O1[k]; }
+        mad_lanes_cin(N0, E0[0], x0, a.v[1], a.v[3], a.v[5], a.v[7], b0.v[i]);
+        mad_lanes_cin(N1, E1[0], x1, a.v[1], a.v[3], a.v[5], a.v[7], b1.v[i]);
+        mad_lanes_nc(N0, c.v[1], c.v[3], c.v[5], c.v[7], d0.v[i]);
+        mad_lanes_nc(N1, c.v[1], c.v[3], c.v[5], c.v[7], d1.v[i]);
+        mad_lanes(E0, N0[7], a.v[0], a.v[2], a.v[4], a.v[6], b0.v[i]);
+        mad_lanes(E1, N1[7], a.v[0], a.v[2], a.v[4], a.v[6], b1.v[i]);
+        mad_lanes(E0, N0[7], c.v[0], c.v[2], c.v[4], c.v[6], d0.v[i]);
+        mad_lanes(E1, N1[7], c.v[0], c.v[2], c.v[4], c.v[6], d1.v[i]);
+        m0 = E0[0] * BN254_INV32;
+        m1 = E1[0] * BN254_INV32;
+        mad_p_odd(N0, m0);
+        mad_p_odd(N1, m1);
+        mad_p_even(E0, N0[7], m0);
+        mad_p_even(E1, N1[7], m1);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { O0[k] = N0[k]; O1[k] = N1[k]; }
+    }
+    fp s0, s1;
+    uint32_t h0[8] = {E0[1], E0[2], E0[3], E0[4], E0[5], E0[6], E0[7], 0u};
+    uint32_t h1[8] = {E1[1], E1[2], E1[3], E1[4], E1[5], E1[6], E1[7], 0u};
+    (void)add_n(s0.v, O0, h0);
+    (void)add_n(s1.v, O1, h1);
+    fp_reduce_once(s0);
+    fp_reduce_once(s1);
+    fp_reduce_once(s0);
+    fp_reduce_once(s1);
+    r0 = s0;
+    r1 = s1;
+}
+
 // The ONE out-of-line instance of the product.  Operands and result travel in registers (by value:
 // 16 in, 8 out), so a call costs a handful of moves while every caller stays small: the hot loops
 // of the pairing must fit the 32 KB L1.5 instruction cache, and a fully inlined Miller loop is

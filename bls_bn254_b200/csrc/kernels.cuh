@@ -418,5 +418,29 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters, in
     }
     if (x == 0x12345678u) sink[0] = x;  // keeps the chains alive
 }
+// Field-level speed of light: `iters` dependent fused dot products (mode 0) or products (mode 1)
+// per thread, operands in registers -- what the IMAD stream of the pairing kernels can reach with
+// a given number of warps per scheduler and no memory traffic at all.
+__global__ void k_fp_peak(uint32_t *sink, int iters, int mode) {
+    fp a, b, c, d;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a.v[i] = threadIdx.x * 2654435761u + i;
+        b.v[i] = blockIdx.x * 40503u + 7 * i;
+        c.v[i] = (threadIdx.x + 11) * 2246822519u + i;
+        d.v[i] = (blockIdx.x + 3) * 3266489917u + i;
+    }
+    a.v[7] &= 0x1fffffffu; b.v[7] &= 0x1fffffffu; c.v[7] &= 0x1fffffffu; d.v[7] &= 0x1fffffffu;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        if (mode == 0) a = fp_dot2_v(a, b, c, d);
+        else if (mode == 1) a = fp_mul_v(a, b);
+        else fp_dot2x2_inl(a, c, a, c, b, d, d, b);   // mode 2: two dot products in lock step (counts as two)
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a.v[i];
+    if (x == 0x12345678u) sink[0] = x;
+}
 
 }  // namespace bn

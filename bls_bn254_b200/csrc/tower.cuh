@@ -124,9 +124,11 @@ BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp2 x = a, y = b, z;
     fp nb1;
     fp_neg(nb1, y.c1);
-#ifndef BN_FP2MUL_CALLS   // both dot products inline: no call overhead, two independent chains for the scheduler
+#if defined(BN_FP2MUL_SEQ)   // both dot products inline, one after the other
     fp_dot2_inl(z.c0, x.c0, y.c0, x.c1, nb1);
     fp_dot2_inl(z.c1, x.c0, y.c1, x.c1, y.c0);
+#elif !defined(BN_FP2MUL_CALLS)   // both dot products inline and advanced in lock step (two instruction streams)
+    fp_dot2x2_inl(z.c0, z.c1, x.c0, x.c1, y.c0, nb1, y.c1, y.c0);
 #else
     fp_dot2(z.c0, x.c0, y.c0, x.c1, nb1);
     fp_dot2(z.c1, x.c0, y.c1, x.c1, y.c0);

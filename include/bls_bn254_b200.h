@@ -136,6 +136,9 @@ int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks,
  *      mad.lo.u32 + mad.hi.u32 pairs; mode 2: 32x32+64 wide multiply-add (IMAD.WIDE.U32, the
  *      instruction the field multiplication issues), counted as 2 IMAD-ops each. ------------------ */
 int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, double *ms);
+/* Field-level speed of light: `warps_per_sm` warps per SM of dependent fused dot products (mode 0) or
+ * Montgomery products (mode 1) on registers; canonical IMAD-ops/s (264 per product, 528 per dot product). */
+int bn254_fp_peak(bn254_ctx *ctx, int mode, int warps_per_sm, int iters, double *ops_per_s);
 
 #ifdef __cplusplus
 }
