@@ -390,7 +390,9 @@ def main():
     top_name, (top_cnt, top_ms, top_items) = top[0], top[1]
     peak_name = max(peaks, key=peaks.get)
     peak = peaks[peak_name]
-    top_ops = KERNEL_M.get(top_name, 0) * M_IMAD * top_items
+    lanes = 2 if top_name.endswith("_l2") else 1          # lane-pair kernels: two threads per item
+    top_items //= lanes
+    top_ops = KERNEL_M.get(top_name[:-3] if lanes == 2 else top_name, 0) * M_IMAD * top_items
     achieved = top_ops / (top_ms / top_cnt * 1e-3) if top_ms else 0.0
     whole_ops = WORK_M[w] * M_IMAD * n * args.steps
     traffic = None

@@ -47,6 +47,7 @@ struct Dev {
     cudaEvent_t ev_fork = nullptr, ev_join[MAXSUB] = {};
     cudaStream_t cur = nullptr;   // the stream LAUNCH uses (d.st outside a split region)
     int nsub = 1;
+    size_t lane_wave_threads = 0;   // threads of one full wave of the lane-pair kernels on this device
 };
 
 }  // namespace
@@ -117,25 +118,21 @@ inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1)
         }                                                                        \
     } while (0)
 
-// Pairing kernels: BN_LANES == 1 (default) runs one thread per pairing; 2 runs two lanes per pairing
-// (lane-split Fp2, tower.cuh) -- bit-identical, measured ~7 % slower on B200 in round 1 because its
-// larger code thrashes the instruction cache at the occupancy it needs (profiles/r01_notes.md).
+// Pairing kernels come in two bit-identical shapes: one thread per pairing, and two lanes per pairing
+// (lane-split Fp2, tower.cuh: half the per-thread state, twice the warps).  Measured on B200: the lane
+// pair wins while the batch does not fill the machine with one thread per item (2^14: +10 %, 2^16:
+// +4 %), one thread per pairing wins beyond (2^18, 2^20: +3 %).  BN_LANES = 0 (default) picks per
+// launch: lanes while 2n threads fit one wave of the lane kernels; 1 / 2 force a shape.
 #ifndef BN_LANES
-#define BN_LANES 1
+#define BN_LANES 0
 #endif
-#if BN_LANES == 2
-#define K_MILLER1 k_miller1_l2
-#define K_MILLER2_FIXED k_miller2_fixed_l2
-#define K_MILLER2 k_miller2_l2
-#define K_FINAL_EXP k_final_exp_l2
-#define PAIR_THREADS(n) (2 * (size_t)(n))
-#else
-#define K_MILLER1 k_miller1
-#define K_MILLER2_FIXED k_miller2_fixed
-#define K_MILLER2 k_miller2
-#define K_FINAL_EXP k_final_exp
-#define PAIR_THREADS(n) ((size_t)(n))
-#endif
+#define LAUNCH_PAIR(d, kscalar, klane, n, ...)                                              \
+    do {                                                                                    \
+        if (BN_LANES == 2 || (BN_LANES == 0 && 2 * (size_t)(n) <= (d).lane_wave_threads))    \
+            LAUNCH(d, klane, 2 * (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                   \
+        else                                                                                \
+            LAUNCH(d, kscalar, (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                     \
+    } while (0)
 
 // ---- device-level building blocks (all pointers are device pointers on d) ------------------------
 
@@ -200,8 +197,8 @@ int dev_pairing(Dev &d, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t 
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, g1, n, 0);
     LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, g2, n, 0);
-    LAUNCH(d, K_MILLER1, PAIR_THREADS(n), BN_TPB_HEAVY, F, flf, P, flp, Q, flq, n, (int *)nullptr);
-    if (mode == 0) LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, F, n);
+    LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, flf, P, flp, Q, flq, n, (int *)nullptr);
+    if (mode == 0) LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, F, n);
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -211,7 +208,7 @@ int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *st
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
     LAUNCH(d, k_fp12_decode, n, BN_TPB_LIGHT, F, flf, ml, n);
-    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, F, n);
+    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, F, n);
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -272,7 +269,7 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
         }
         if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH(d, K_MILLER2_FIXED, PAIR_THREADS(n), BN_TPB_HEAVY, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
+        LAUNCH_PAIR(d, k_miller2_fixed, k_miller2_fixed_l2, n, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
                b.flq1 + lo, n);
     } else {
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q0 + lo, b.flq0 + lo, sigs + 128 * lo, n, check);
@@ -282,10 +279,10 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
             LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, b.flp1 + lo, b.P1 + lo, n);
         }
         if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH(d, K_MILLER2, PAIR_THREADS(n), BN_TPB_HEAVY, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo,
+        LAUNCH_PAIR(d, k_miller2, k_miller2_l2, n, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo,
                b.flp1 + lo, b.Q1 + lo, b.flq1 + lo, n);
     }
-    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(n), BN_TPB_HEAVY, b.F + lo, n);
+    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, b.F + lo, n);
     LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok + lo, b.F + lo, b.flf + lo, n);
     return 0;
 }
@@ -364,7 +361,7 @@ int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t
             CK(d, cudaMemsetAsync(flp + n, 0, 1, d.st));
         }
     }
-    LAUNCH(d, K_MILLER1, PAIR_THREADS(tot), BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
+    LAUNCH_PAIR(d, k_miller1, k_miller1_l2, tot, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, tot, &res)) return rc;
     LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, partial, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
@@ -384,7 +381,7 @@ int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, si
     LAUNCH(d, k_or_bytes, kparts, BN_TPB_LIGHT, dbad, bad, kparts);
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, kparts, &res)) return rc;
-    LAUNCH(d, K_FINAL_EXP, PAIR_THREADS(1), BN_TPB_HEAVY, res, (size_t)1);
+    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, 1, res, (size_t)1);
     LAUNCH(d, k_finish_ok, 1, 32, ok, res, dbad);
     return 0;
 }
@@ -533,6 +530,11 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
         cudaError_t e = cudaSetDevice(d.id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking);
         d.cur = d.st;
+        if (e == cudaSuccess) {
+            cudaDeviceProp prop;
+            e = cudaGetDeviceProperties(&prop, d.id);
+            d.lane_wave_threads = (size_t)prop.multiProcessorCount * BN_MINB_L2 * BN_TPB_HEAVY;
+        }
         for (int k = 0; k < Dev::MAXSUB && e == cudaSuccess; k++) {
             e = cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
@@ -717,7 +719,7 @@ int bn254_multi_miller_loop(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, db, n, 0);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad, flp, n);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad + 1, flq, n);
-        LAUNCH(d, K_MILLER1, PAIR_THREADS(n), BN_TPB_HEAVY, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
+        LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
         fp12 *res;
         if (int rc = dev_fp12_product(d, F, n, &res)) return rc;
         LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_FEXP) k_final_exp(fp12 *
 //      whose 16 items are all out of range exits as a whole; in the last partial warp the idle pairs
 //      recompute the last item (identical bytes are stored) so that every pair stays convergent.
 #ifndef BN_MINB_L2
-#define BN_MINB_L2 8
+#define BN_MINB_L2 14   // 72 registers: 2 x 2^16 threads are exactly one wave on 148 SMs
 #endif
 #define BN_L2_PROLOGUE()                                                 \
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;            \

@@ -398,6 +398,11 @@ BN_NOINL fp l2_xi_v(fp a) {
     fp_add(r, t, u);
     return r;
 }
+// BN_L2_BYVALUE: the tower calls the by-value primitives above (values travel in registers, ~25
+// instructions per call site); default: out-of-line functions on pointers (~8 instructions per call
+// site, operands loaded as 128-bit vectors first), which keeps the lane-pair kernels as small as the
+// one-thread ones.
+#ifdef BN_L2_BYVALUE
 BN_INL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_add_v(a.v, b.v); }
 BN_INL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_sub_v(a.v, b.v); }
 BN_INL void fp2_neg(fp2l &r, const fp2l &a) { r.v = l2_neg_v(a.v); }
@@ -407,6 +412,67 @@ BN_INL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_mul_v(a.v,
 BN_INL void fp2_sqr(fp2l &r, const fp2l &a) { r.v = l2_sqr_v(a.v); }
 BN_INL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) { fp_mul(r.v, a.v, s); }
 BN_INL void fp2_mul_xi(fp2l &r, const fp2l &a) { r.v = l2_xi_v(a.v); }
+#else
+BN_NOINL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) {
+    fp x = a.v, y = b.v, z;
+    fp_add(z, x, y);
+    r.v = z;
+}
+BN_NOINL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) {
+    fp x = a.v, y = b.v, z;
+    fp_sub(z, x, y);
+    r.v = z;
+}
+BN_NOINL void fp2_neg(fp2l &r, const fp2l &a) {
+    fp x = a.v, z;
+    fp_neg(z, x);
+    r.v = z;
+}
+BN_INL void fp2_dbl(fp2l &r, const fp2l &a) { fp2_add(r, a, a); }
+BN_NOINL void fp2_conj(fp2l &r, const fp2l &a) {
+    fp x = a.v, n, z;
+    fp_neg(n, x);
+    fp_select(z, lane_par() != 0, n, x);
+    r.v = z;
+}
+BN_NOINL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) {
+    fp x0 = a.v, y0 = b.v, pa, pb, npb, x, z, w, o;
+    bool odd = lane_par() != 0;
+    lane_xchg(pa, x0);
+    lane_xchg(pb, y0);
+    fp_neg(npb, pb);
+    fp_select(x, odd, pa, x0);   // a0
+    fp_select(z, odd, x0, pa);   // a1
+    fp_select(w, odd, pb, npb);  // odd: b0, even: -b1
+    fp_dot2_inl(o, x, y0, z, w);
+    r.v = o;
+}
+BN_NOINL void fp2_sqr(fp2l &r, const fp2l &a) {
+    fp x0 = a.v, pa, s, d, x, y, o;
+    bool odd = lane_par() != 0;
+    lane_xchg(pa, x0);
+    fp_select(s, odd, pa, x0);  // a0
+    fp_add(x, s, pa);           // even: a0 + a1, odd: a0 + a0
+    fp_sub(d, x0, pa);
+    fp_select(y, odd, x0, d);   // even: a0 - a1, odd: a1
+    fp_mul(o, x, y);
+    r.v = o;
+}
+BN_NOINL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) {
+    fp x = a.v, y = s, o;
+    fp_mul(o, x, y);
+    r.v = o;
+}
+BN_NOINL void fp2_mul_xi(fp2l &r, const fp2l &a) {
+    fp x0 = a.v, pa, n, t, u, o;
+    lane_xchg(pa, x0);
+    fp_neg(n, pa);
+    fp_mul9(t, x0);
+    fp_select(u, lane_par() != 0, pa, n);
+    fp_add(o, t, u);
+    r.v = o;
+}
+#endif
 // fp2.rs:161-166 on a lane pair (both lanes run the same Fp inversion on the shared norm)
 BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
     fp sq, psq, n, m;
