@@ -435,16 +435,17 @@ BN_NOINL void fp2_conj(fp2l &r, const fp2l &a) {
     fp_select(z, lane_par() != 0, n, x);
     r.v = z;
 }
+// even lane: a0 b0 + a1 (-b1) = mine_a mine_b + theirs_a (-theirs_b)
+// odd lane:  a1 b0 + a0 b1    = mine_a theirs_b + theirs_a mine_b
 BN_NOINL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) {
-    fp x0 = a.v, y0 = b.v, pa, pb, npb, x, z, w, o;
+    fp x0 = a.v, y0 = b.v, pa, pb, npb, u, w, o;
     bool odd = lane_par() != 0;
     lane_xchg(pa, x0);
     lane_xchg(pb, y0);
     fp_neg(npb, pb);
-    fp_select(x, odd, pa, x0);   // a0
-    fp_select(z, odd, x0, pa);   // a1
-    fp_select(w, odd, pb, npb);  // odd: b0, even: -b1
-    fp_dot2_inl(o, x, y0, z, w);
+    fp_select(u, odd, pb, y0);
+    fp_select(w, odd, y0, npb);
+    fp_dot2_inl(o, x0, u, pa, w);
     r.v = o;
 }
 BN_NOINL void fp2_sqr(fp2l &r, const fp2l &a) {
