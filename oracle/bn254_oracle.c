@@ -649,6 +649,7 @@ static int hash_to_g2_one(g2a *out, const uint8_t *msg, size_t msg_len, const ui
     fp2 u;
     g2a q[2];
     g2p a, b;
+    memset(q, 0, sizeof q);
     if (!expand_message_xmd(okm, 96 * (size_t)count, msg, msg_len, dst, dst_len)) return 0;
     for (int i = 0; i < count; i++) {
         fp_from_okm(&u.c0, okm + 96 * i);
