@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- BLS-BN254 batch verification throughput on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload verify|verify_pk|hash_g1|hash_g2|pairing|aggregate]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload verify|verify_pk|verify_rand|hash_g1|hash_g2|pairing|aggregate]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...       # the CPU arm: the oracle port on all host cores
 
@@ -13,6 +13,7 @@ owns a disjoint shard, no inter-GPU traffic; `aggregate` adds one 385-byte NCCL 
 region).  Rank 0 prints ONE JSON line.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -24,12 +25,19 @@ sys.path.insert(0, ROOT)
 
 # canonical work per unit in Fp multiplications M; 1 M = 264 INT32 IMAD-ops
 M_IMAD = 264
-WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868}
-KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400}
+# verify_rand (randomised batch verification, groups of 256, 64-bit scalars): hash 2204 + one-pair Miller loop 8610 + two 64-bit
+# double-and-add scalings (64 x 8 + 32 x 12 = 896 each) + one affine conversion 332 + product tree 58 + per-group pairing / 256 = 68
+WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 13064}
+KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
+            "k_rbv_scale_g1": 1228, "k_rbv_scale_g1p": 896}
 UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
-        "aggregate": "verifications/s"}
+        "aggregate": "verifications/s", "verify_rand": "verifications/s"}
 METRIC = {"verify": "bls_verifications_per_sec", "verify_pk": "bls_verifications_per_sec", "hash_g1": "hash_to_g1_per_sec",
-          "hash_g2": "hash_to_g2_per_sec", "pairing": "pairings_per_sec", "aggregate": "bls_aggregate_verified_signatures_per_sec"}
+          "hash_g2": "hash_to_g2_per_sec", "pairing": "pairings_per_sec", "aggregate": "bls_aggregate_verified_signatures_per_sec",
+          "verify_rand": "bls_randomized_batch_verifications_per_sec"}
+
+
+RBV_SEED = hashlib.sha256(b"bench.py randomised batch verification seed").digest()
 
 
 class ClockSampler(threading.Thread):
@@ -90,7 +98,7 @@ def run_reference(args):
     msgs = make_messages(n, 0)
     sks = [b.scheme.scalar_from_seed(b.scheme.SEED, i % 64) for i in range(n)]
     sc = b"".join(s.to_bytes(32, "big") for s in sks)
-    if w in ("verify", "aggregate"):
+    if w in ("verify", "aggregate", "verify_rand"):
         upk = orc.g2_mul(orc.g2_generator() * 64, sc[:64 * 32], nthreads=cores)
         pks = b"".join(upk[(i % 64) * 128:(i % 64 + 1) * 128] for i in range(n))
         sigs = orc.g1_mul(orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores), sc, nthreads=cores)
@@ -110,6 +118,9 @@ def run_reference(args):
         elif w == "verify_pk":
             ok = orc.verify_batch(1, pks, msgs, sigs, b.DST_MIN_PK, nthreads=cores)
             assert sum(ok) == n
+        elif w == "verify_rand":
+            ok = orc.verify_batch_randomized(0, pks, msgs, sigs, b.DST_MIN_SIG, RBV_SEED, group=args.group, nthreads=cores)
+            assert all(ok)
         elif w == "hash_g1":
             orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores)
         elif w == "hash_g2":
@@ -145,9 +156,11 @@ def workload_config(w, args):
         "hash_g2": "hash_to_curve: 2^%d 32-byte messages per GPU to G2 (expand_message_xmd SHA-256 + SvdW + cofactor clearing)",
         "pairing": "2^%d pairings per GPU (Miller loop + final exponentiation), distinct random G1/G2 points",
         "aggregate": "aggregate verify: 2^%d signatures on distinct messages per GPU, one multi-Miller product + single final exponentiation",
+        "verify_rand": "randomised batch verify of 2^%d valid (pk, msg, sig) tuples per GPU, min-sig, one accept byte per group of "
+                       + str(args.group) + " tuples (64-bit scalars, one final exponentiation per group)",
     }
     return {"workload": names[w] % args.log2n, "tuples_per_gpu": 1 << args.log2n, "variant": "min-pk" if w == "verify_pk" else "min-sig",
-            "msg_bytes": 32, "corrupted_fraction": "1/64" if w.startswith("verify") else "0",
+            "msg_bytes": 32, "corrupted_fraction": "1/64" if w in ("verify", "verify_pk") else "0",
             "l2": "L2 flushed between timed steps (256 MiB write)", "sharding": "independent tuples by index, no data-path collective"
             if w != "aggregate" else "pairs by index; one 385-byte all-gather of Fp12 partials"}
 
@@ -160,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="verify", choices=sorted(WORK_M))
     ap.add_argument("--log2n", type=int, default=16, help="log2 of tuples per GPU per step")
+    ap.add_argument("--group", type=int, default=256, help="tuples per accept byte of the verify_rand workload")
     ap.add_argument("--ref-sample", type=int, default=4096, help="tuples per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -200,6 +214,10 @@ def main():
     expected = None
     if w in ("verify", "verify_pk"):
         pks, msgs, sigs, expected = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096))
+    elif w == "verify_rand":
+        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096), corrupt_every=0)
+        ngroups = (n + args.group - 1) // args.group
+        expected = b"\x01" * ngroups
     elif w == "aggregate":
         pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096), corrupt_every=0)
         agg_local = b.scheme.aggregate(ctx, sigs, variant)
@@ -220,8 +238,9 @@ def main():
     d_sigs = dev_bytes(sigs) if sigs else None
     d_g1 = dev_bytes(g1) if g1 else None
     d_g2 = dev_bytes(g2) if g2 else None
-    out_rec = {"verify": 1, "verify_pk": 1, "hash_g1": 64, "hash_g2": 128, "pairing": 384, "aggregate": 385}[w]
-    d_out = torch.zeros(n * out_rec if w != "aggregate" else 385, dtype=torch.uint8, device=dev)
+    out_rec = {"verify": 1, "verify_pk": 1, "hash_g1": 64, "hash_g2": 128, "pairing": 384, "aggregate": 385, "verify_rand": 1}[w]
+    d_out = torch.zeros({"aggregate": 385, "verify_rand": (n + args.group - 1) // args.group}.get(w, n * out_rec), dtype=torch.uint8, device=dev)
+    d_seed = dev_bytes(RBV_SEED)
     d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -244,6 +263,9 @@ def main():
         if w in ("verify", "verify_pk"):
             ctx.verify_batch_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(),
                                  len(dst), 0, d_out.data_ptr())
+        elif w == "verify_rand":
+            ctx.verify_batch_randomized_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(),
+                                            len(dst), 0, d_seed.data_ptr(), 64, args.group, d_out.data_ptr())
         elif w == "hash_g1":
             ctx.hash_to_g1_dev(d_blob.data_ptr(), d_off.data_ptr(), n, d_dst.data_ptr(), len(dst), 2, d_out.data_ptr(), d_status.data_ptr())
         elif w == "hash_g2":
@@ -269,6 +291,8 @@ def main():
         """the call a user makes: host buffers in, host result out"""
         if w in ("verify", "verify_pk"):
             return ctx.verify_batch(variant, pks, (blob, off), sigs, dst)
+        if w == "verify_rand":
+            return ctx.verify_batch_randomized(variant, pks, (blob, off), sigs, dst, RBV_SEED, group=args.group)
         if w == "hash_g1":
             return ctx.hash_to_g1((blob, off), dst)
         if w == "hash_g2":
@@ -370,8 +394,9 @@ def main():
     e2e_ms = float(t.item())
     in_bytes = {"verify": len(blob) + 8 * (n + 1) + n * 192 + len(dst), "verify_pk": len(blob) + 8 * (n + 1) + n * 192 + len(dst),
                 "hash_g1": len(blob) + 8 * (n + 1) + len(dst), "hash_g2": len(blob) + 8 * (n + 1) + len(dst), "pairing": n * 192,
-                "aggregate": len(blob) + 8 * (n + 1) + n * 128 + 64 + len(dst)}[w]
-    out_bytes = {"verify": n, "verify_pk": n, "hash_g1": n * 65, "hash_g2": n * 129, "pairing": n * 385, "aggregate": 385 + 1}[w]
+                "aggregate": len(blob) + 8 * (n + 1) + n * 128 + 64 + len(dst), "verify_rand": len(blob) + 8 * (n + 1) + n * 192 + len(dst) + 32}[w]
+    out_bytes = {"verify": n, "verify_pk": n, "hash_g1": n * 65, "hash_g2": n * 129, "pairing": n * 385, "aggregate": 385 + 1,
+                 "verify_rand": (n + args.group - 1) // args.group}[w]
 
     if rank != 0:
         if world > 1:
@@ -427,6 +452,10 @@ def main():
             rpk, rsig = (128, 64) if variant == 0 else (64, 128)
             ref = orc.verify_batch(variant, pks[:m * rpk], msgs[:m], sigs[:m * rsig], dst, nthreads=cores)
             assert ref == expected[:m], "oracle and construction disagree"
+        elif w == "verify_rand":
+            m = max(args.group, m // args.group * args.group)
+            ref = orc.verify_batch_randomized(0, pks[:m * 128], msgs[:m], sigs[:m * 64], dst, RBV_SEED, group=args.group, nthreads=cores)
+            assert ref == expected[:len(ref)], "oracle rejected a valid group"
         elif w == "hash_g1":
             ref = orc.hash_to_g1(msgs[:m], dst, nthreads=cores)
             assert ref == bytes(d_out[:64 * m].cpu().numpy()), "hash_to_g1 differs from the oracle"
@@ -450,7 +479,7 @@ def main():
         "e2e": {"value": n * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT[w], "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "pairings_per_sec": value * (2 if w.startswith("verify") else 1) if w in ("verify", "verify_pk", "pairing", "aggregate") else None,
+        "pairings_per_sec": value * (2 if w in ("verify", "verify_pk") else 1) if w in ("verify", "verify_pk", "pairing", "aggregate", "verify_rand") else None,
     }
     print(json.dumps(line))
     if world > 1:

@@ -70,6 +70,8 @@ def lib():
         L.bn254_fp12_product.argtypes = [vp, vp, sz, vp]
         L.bn254_verify_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp]
         L.bn254_aggregate_verify.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp]
+        for name in ("bn254_verify_batch_randomized", "bn254_verify_batch_randomized_dev"):
+            getattr(L, name).argtypes = [vp, C.c_int, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp, C.c_int, sz, vp]
         L.bn254_aggregate_partial.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp, vp]
         L.bn254_aggregate_finish.argtypes = [vp, vp, vp, sz, vp]
         for name in ("bn254_g1_compress", "bn254_g2_compress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve", "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
@@ -94,10 +96,10 @@ EXPORTED_SYMBOLS = [
     "bn254_device_count", "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_launch_count", "bn254_stream", "bn254_sync", "bn254_profile_enable", "bn254_profile_drain",
     "bn254_hash_to_g1", "bn254_encode_to_g1", "bn254_hash_to_g2", "bn254_encode_to_g2",
     "bn254_pairing_batch", "bn254_miller_loop_batch", "bn254_multi_miller_loop", "bn254_final_exponentiation", "bn254_fp12_product",
-    "bn254_verify_batch", "bn254_aggregate_verify", "bn254_aggregate_partial", "bn254_aggregate_finish",
+    "bn254_verify_batch", "bn254_verify_batch_randomized", "bn254_aggregate_verify", "bn254_aggregate_partial", "bn254_aggregate_finish",
     "bn254_g1_compress", "bn254_g1_decompress", "bn254_g2_compress", "bn254_g2_decompress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve",
     "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
     "bn254_g1_mul", "bn254_g2_mul", "bn254_g1_sum", "bn254_g2_sum",
-    "bn254_hash_to_g1_dev", "bn254_hash_to_g2_dev", "bn254_pairing_batch_dev", "bn254_verify_batch_dev", "bn254_aggregate_partial_dev",
+    "bn254_hash_to_g1_dev", "bn254_hash_to_g2_dev", "bn254_pairing_batch_dev", "bn254_verify_batch_dev", "bn254_verify_batch_randomized_dev", "bn254_aggregate_partial_dev",
     "bn254_imad_peak", "bn254_fp_peak",
 ]

@@ -189,6 +189,24 @@ class Context:
         self._ck(self._L.bn254_verify_batch(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags, _ptr(ok)))
         return ok.raw
 
+    def verify_batch_randomized(self, variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0):
+        """One accept byte per consecutive group of `group` tuples (small-exponent batch test).
+        `seed` = 32 bytes the signers cannot predict (fresh CSPRNG output per call)."""
+        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+        n = len(off) - 1
+        rpk, rsig = self._recs(variant)
+        if len(pks) != rpk * n:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if len(sigs) != rsig * n:
+            raise Bn254Error(-2 if variant == MIN_SIG else -3, "signature buffer length")
+        if len(seed) != 32:
+            raise Bn254Error(-10, "seed must be 32 bytes")
+        ng = (n + group - 1) // group if group > 0 else 0
+        ok = C.create_string_buffer(max(ng, 1))
+        self._ck(self._L.bn254_verify_batch_randomized(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags,
+                                                       _ptr(seed), rand_bits, group, _ptr(ok)))
+        return ok.raw[:ng]
+
     def aggregate_verify(self, variant, pks, msgs, agg_sig, dst, flags=0):
         blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
         n = len(off) - 1
@@ -265,6 +283,10 @@ class Context:
 
     def verify_batch_dev(self, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, ok):
         self._ck(self._L.bn254_verify_batch_dev(self._h, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, ok))
+
+    def verify_batch_randomized_dev(self, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, seed, rand_bits, group, ok_groups):
+        self._ck(self._L.bn254_verify_batch_randomized_dev(self._h, variant, pks, msgs, offsets, sigs, n, dst, dst_len, flags, seed, rand_bits, group,
+                                                           ok_groups))
 
     def aggregate_partial_dev(self, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad):
         self._ck(self._L.bn254_aggregate_partial_dev(self._h, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad))

@@ -21,6 +21,7 @@ namespace {
 enum Scratch {
     S_IN_A, S_IN_B, S_IN_C, S_MSGS, S_OFF, S_DST, S_OUT, S_STATUS,
     S_P0, S_FLP0, S_P1, S_FLP1, S_Q0, S_FLQ0, S_Q1, S_FLQ1, S_F, S_FLF, S_F2, S_BAD, S_TMP, S_FLTMP, S_CONST,
+    S_RB_S0, S_RB_S1, S_RB_S2, S_RB_FA, S_RB_FB, S_RB_FS, S_RB_GP, S_RB_GQ, S_RB_FLP, S_RB_FLQ, S_RB_BAD, S_RB_SEED,
     S_COUNT
 };
 
@@ -46,6 +47,11 @@ struct Dev {
     cudaStream_t sub[MAXSUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAXSUB] = {};
     cudaStream_t cur = nullptr;   // the stream LAUNCH uses (d.st outside a split region)
+    // High-priority side stream: the latency-bound per-group tail of the randomised batch verification (a few
+    // hundred threads running whole Miller loops) is queued here so that its CTAs are placed as soon as a slot
+    // frees up while the full-size kernels of the main stream keep the machine busy.
+    cudaStream_t hi = nullptr;
+    cudaEvent_t ev_hi_fork = nullptr, ev_hi_join = nullptr;
     int nsub = 1;
     size_t lane_wave_threads = 0;   // threads of one full wave of the lane-pair kernels on this device
 };
@@ -326,6 +332,133 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
     return 0;
 }
 
+// ---- randomised batch verification ----------------------------------------------
+// Segmented reduction of n records in groups of `group` (the last group may be short) down to one record per
+// group: levels of fan-in BN_SEG_FAN (4: the tail is latency-bound, 16-way levels measured 0.8 ms slower), ping-pong between A and B.  *res = nseg contiguous records.
+#ifndef BN_SEG_FAN
+#define BN_SEG_FAN 4
+#endif
+#define SEG_LEVELS(d, kern, T, in, A, B, n, group, res)                                                   \
+    do {                                                                                                  \
+        seg_level L_;                                                                                     \
+        L_.nseg = ((n) + (group) - 1) / (group);                                                          \
+        L_.stride_in = (group);                                                                           \
+        L_.len_full = (group);                                                                            \
+        L_.len_last = (n) - (L_.nseg - 1) * (group);                                                      \
+        L_.fan = BN_SEG_FAN;                                                                              \
+        const T *src_ = (in);                                                                             \
+        T *dst_ = (A);                                                                                    \
+        while (L_.len_full > 1) {                                                                         \
+            L_.stride_out = (L_.len_full + BN_SEG_FAN - 1) / BN_SEG_FAN;                                  \
+            LAUNCH(d, kern, L_.nseg * L_.stride_out, BN_TPB_HEAVY, dst_, src_, L_);                       \
+            src_ = dst_;                                                                                  \
+            dst_ = (dst_ == (A)) ? (B) : (A);                                                             \
+            L_.stride_in = L_.stride_out;                                                                 \
+            L_.len_full = L_.stride_out;                                                                  \
+            L_.len_last = (L_.len_last + BN_SEG_FAN - 1) / BN_SEG_FAN;                                    \
+        }                                                                                                 \
+        *(res) = const_cast<T *>(src_);                                                                   \
+    } while (0)
+
+// One chunk: n tuples (device pointers) in groups of `group` -> ceil(n / group) accept bytes.  `idx0` is the
+// index of the chunk's first tuple in the whole call (it enters the scalar derivation).
+int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
+                    size_t n, size_t group, const uint8_t *seed, uint64_t idx0, int nbits, const uint8_t *dst, uint32_t dst_len, uint32_t flags,
+                    uint8_t *ok) {
+    const int check = (flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? 1 : 0;
+    const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
+    const size_t nseg = (n + group - 1) / group;
+    const size_t so0 = (group + BN_SEG_FAN - 1) / BN_SEG_FAN, so1 = (so0 + BN_SEG_FAN - 1) / BN_SEG_FAN;
+    fp12 *F, *FA, *FB, *Fs, *Fg;
+    g1m *P1, *GP; g2m *Q1, *GQ;
+    uint8_t *flp1, *flq1, *gflp, *gflq, *flsig;
+    int *gbad;
+    if (int rc = ensure_t(d, S_F, n, &F)) return rc;
+    if (int rc = ensure_t(d, S_RB_FA, nseg * so0 + 1, &FA)) return rc;
+    if (int rc = ensure_t(d, S_RB_FB, nseg * so1 + 1, &FB)) return rc;
+    if (int rc = ensure_t(d, S_RB_FS, nseg, &Fs)) return rc;
+    if (int rc = ensure_t(d, S_P1, n, &P1)) return rc;
+    if (int rc = ensure_t(d, S_Q1, n, &Q1)) return rc;
+    if (int rc = ensure_t(d, S_FLP1, n, &flp1)) return rc;
+    if (int rc = ensure_t(d, S_FLQ1, n, &flq1)) return rc;
+    if (int rc = ensure_t(d, S_RB_GP, nseg, &GP)) return rc;
+    if (int rc = ensure_t(d, S_RB_GQ, nseg, &GQ)) return rc;
+    if (int rc = ensure_t(d, S_RB_FLP, nseg, &gflp)) return rc;
+    if (int rc = ensure_t(d, S_RB_FLQ, nseg, &gflq)) return rc;
+    if (int rc = ensure_t(d, S_RB_BAD, nseg, &gbad)) return rc;
+    CK(d, cudaMemsetAsync(gbad, 0, nseg * sizeof(int), d.cur));
+    // The signature side (scale, per-group sums, one Miller loop per GROUP against the fixed generator) only needs
+    // the decoded signatures: it runs on the side stream next to the per-tuple pipeline of the main stream.
+    struct SideStream {   // LAUNCH goes to d.cur; always put the main stream back
+        Dev &d; cudaStream_t keep;
+        explicit SideStream(Dev &dd) : d(dd), keep(dd.cur) {}
+        ~SideStream() { d.cur = keep; }
+    };
+    const bool side = !d.prof && d.cur == d.st;   // per-kernel timing wants the kernels serial
+    if (variant == BN254_MIN_SIG) {
+        g1m *P0; g1p *S0, *SA, *SB, *Sg;
+        if (int rc = ensure_t(d, S_P0, n, &P0)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, n, &flsig)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, n, &S0)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, nseg * so0 + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, nseg * so1 + 1, &SB)) return rc;
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flsig, sigs, n, check);
+        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flsig, P0, n);
+        {
+            SideStream guard(d);
+            if (side) {
+                CK(d, cudaEventRecord(d.ev_hi_fork, d.st));
+                CK(d, cudaStreamWaitEvent(d.hi, d.ev_hi_fork, 0));
+                d.cur = d.hi;
+            }
+            LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S0, P0, flsig, seed, idx0, nbits, n);
+            SEG_LEVELS(d, k_g1p_seg_sum, g1p, S0, SA, SB, n, group, &Sg);
+            LAUNCH(d, k_g1p_to_affine, nseg, BN_TPB_HEAVY, GP, gflp, Sg, nseg);
+            LAUNCH(d, k_fill_neg_g2, nseg, BN_TPB_LIGHT, GQ, gflq, nseg);
+            LAUNCH_PAIR(d, k_miller1, k_miller1_l2, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, nseg, (int *)nullptr);
+            if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
+        }
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q1, flq1, pks, n, check);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, flq1, Q1, n);
+        if (int rc = dev_hash_g1(d, P1, flp1, msgs, off, base, n, dst, dst_len, 2)) return rc;
+    } else {
+        g2m *Q0; g2p *S0, *SA, *SB, *Sg;
+        if (int rc = ensure_t(d, S_Q0, n, &Q0)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, n, &flsig)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, n, &S0)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, nseg * so0 + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, nseg * so1 + 1, &SB)) return rc;
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q0, flsig, sigs, n, check);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, flsig, Q0, n);
+        {
+            SideStream guard(d);
+            if (side) {
+                CK(d, cudaEventRecord(d.ev_hi_fork, d.st));
+                CK(d, cudaStreamWaitEvent(d.hi, d.ev_hi_fork, 0));
+                d.cur = d.hi;
+            }
+            LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S0, Q0, flsig, seed, idx0, nbits, n);
+            SEG_LEVELS(d, k_g2p_seg_sum, g2p, S0, SA, SB, n, group, &Sg);
+            LAUNCH(d, k_g2p_to_affine, nseg, BN_TPB_HEAVY, GQ, gflq, Sg, nseg);
+            LAUNCH(d, k_fill_neg_g1, nseg, BN_TPB_LIGHT, GP, gflp, nseg);
+            LAUNCH_PAIR(d, k_miller1, k_miller1_l2, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, nseg, (int *)nullptr);
+            if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
+        }
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
+        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flp1, P1, n);
+        if (int rc = dev_hash_g2(d, Q1, flq1, msgs, off, base, n, dst, dst_len, 2)) return rc;
+    }
+    LAUNCH(d, k_rbv_group_flags, n, BN_TPB_LIGHT, gbad, flsig, flp1, flq1, group, n);
+    LAUNCH(d, k_rbv_scale_g1, n, BN_TPB_HEAVY, P1, flp1, seed, idx0, nbits, n);
+    LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, (uint8_t *)nullptr, P1, flp1, Q1, flq1, n, (int *)nullptr);
+    SEG_LEVELS(d, k_fp12_seg_reduce, fp12, F, FA, FB, n, group, &Fg);
+    if (side) CK(d, cudaStreamWaitEvent(d.st, d.ev_hi_join, 0));
+    LAUNCH(d, k_fp12_mul_into, nseg, BN_TPB_HEAVY, Fg, Fs, nseg);
+    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, nseg, Fg, nseg);
+    LAUNCH(d, k_rbv_ok, nseg, BN_TPB_LIGHT, ok, Fg, gbad, nseg);
+    return 0;
+}
+
 // One shard of an aggregate verification (device pointers).  Writes the 384-byte wire form of
 // prod_i ML(H(m_i), pk_i) [* ML(aggsig, -g2) when agg_sig != NULL] and a bad-input byte.
 int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n,
@@ -540,6 +673,13 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join[k], cudaEventDisableTiming);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            e = cudaStreamCreateWithPriority(&d.hi, cudaStreamNonBlocking, hi_pri);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_join, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             int rc = BN254_ERR_CUDA_BASE - (int)e;
             bn254_ctx_destroy(ctx);
@@ -578,6 +718,9 @@ void bn254_ctx_destroy(bn254_ctx *ctx) {
             if (d.ev_join[k]) cudaEventDestroy(d.ev_join[k]);
         }
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.hi) cudaStreamDestroy(d.hi);
+        if (d.ev_hi_fork) cudaEventDestroy(d.ev_hi_fork);
+        if (d.ev_hi_join) cudaEventDestroy(d.ev_hi_join);
         if (d.st) cudaStreamDestroy(d.st);
     }
     delete ctx;
@@ -760,6 +903,46 @@ int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const ui
             CK(d, cudaMemcpyAsync(dsig, sigs + c * rsig, m * rsig, cudaMemcpyHostToDevice, d.st));
             if (int rc = dev_verify(d, variant, dpk, dm, dof, base, dsig, m, ddst, dlen, flags, dok)) return rc;
             CK(d, cudaMemcpyAsync(ok + c, dok, m, cudaMemcpyDeviceToHost, d.st));
+            CK(d, cudaStreamSynchronize(d.st));
+        }
+        return 0;
+    });
+}
+
+int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
+                                  const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, const uint8_t *seed,
+                                  int rand_bits, size_t group, uint8_t *ok_groups) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (rand_bits != 64 && rand_bits != 128) return fail_arg(ctx, "rand_bits must be 64 or 128");
+    if (group == 0 || group > BN254_RBV_MAX_GROUP) return fail_arg(ctx, "group must be in 1..BN254_RBV_MAX_GROUP");
+    if (n == 0) return 0;
+    if (!pks || !offsets || !sigs || !seed || !ok_groups) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
+    size_t nseg = (n + group - 1) / group;
+    size_t chunk_groups = std::max<size_t>(1, ctx->chunk / group);   // a group never straddles two chunks
+    // groups (not tuples) are what the devices share out
+    return run_sharded(ctx, nseg, [=](Dev &d, size_t glo, size_t ghi) -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        uint8_t *dseed;
+        if (int rc = ensure_t(d, S_RB_SEED, 32, &dseed)) return rc;
+        CK(d, cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, d.st));
+        for (size_t g = glo; g < ghi; g += chunk_groups) {
+            size_t ge = std::min(ghi, g + chunk_groups);
+            size_t c = g * group, e = std::min(n, ge * group), m = e - c;
+            const uint8_t *dm; const uint64_t *dof; uint64_t base;
+            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            uint8_t *dpk, *dsig, *dok;
+            if (int rc = ensure_t(d, S_IN_A, m * rpk, &dpk)) return rc;
+            if (int rc = ensure_t(d, S_IN_B, m * rsig, &dsig)) return rc;
+            if (int rc = ensure_t(d, S_OUT, ge - g, &dok)) return rc;
+            CK(d, cudaMemcpyAsync(dpk, pks + c * rpk, m * rpk, cudaMemcpyHostToDevice, d.st));
+            CK(d, cudaMemcpyAsync(dsig, sigs + c * rsig, m * rsig, cudaMemcpyHostToDevice, d.st));
+            if (int rc = dev_verify_rand(d, variant, dpk, dm, dof, base, dsig, m, group, dseed, (uint64_t)c, rand_bits, ddst, dlen, flags, dok))
+                return rc;
+            CK(d, cudaMemcpyAsync(ok_groups + g, dok, ge - g, cudaMemcpyDeviceToHost, d.st));
             CK(d, cudaStreamSynchronize(d.st));
         }
         return 0;
@@ -1068,6 +1251,19 @@ int bn254_verify_batch_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, cons
     const uint8_t *ddst; uint32_t dlen;
     int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
     if (!rc) rc = dev_verify(d, variant, pks, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
+    DEV_EPILOGUE(rc);
+}
+int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
+                                      const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, const uint8_t *seed,
+                                      int rand_bits, size_t group, uint8_t *ok_groups) {
+    DEV_PROLOGUE();
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (rand_bits != 64 && rand_bits != 128) return fail_arg(ctx, "rand_bits must be 64 or 128");
+    if (group == 0 || group > BN254_RBV_MAX_GROUP) return fail_arg(ctx, "group must be in 1..BN254_RBV_MAX_GROUP");
+    if (n == 0) return 0;
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_verify_rand(d, variant, pks, msgs, offsets, 0, sigs, n, group, seed, 0, rand_bits, ddst, dlen, flags, ok_groups);
     DEV_EPILOGUE(rc);
 }
 int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,

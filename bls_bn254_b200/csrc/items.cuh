@@ -247,4 +247,54 @@ BN_INL void item_g2_decompress(g2m &out, uint8_t &fl, const uint8_t *in) {
     fl = ok ? 0 : FL_BAD;
 }
 
+// ---- randomised batch verification (no counterpart in the reference) -------------
+// Small-exponent test: a group of tuples is accepted when
+//     e(sum_i r_i sig_i, -g2) * prod_i e(r_i H(m_i), pk_i) == 1          (min-sig; min-pk symmetric)
+// with per-tuple scalars r_i the caller cannot predict: r_i = the first nbits (64 or 128) of
+// SHA-256(seed || LE64(i)) read as a big-endian integer, 0 replaced by 1; i is the tuple's index in the
+// whole call.  kw = little-endian 32-bit words.
+BN_INL void rbv_scalar(uint32_t kw[4], const uint8_t *seed, uint64_t idx, int nbits) {
+    sha256 s;
+    sha256_init(s);
+    sha256_update(s, seed, 32);
+#pragma unroll 1
+    for (int b = 0; b < 8; b++) sha256_put(s, (uint8_t)(idx >> (8 * b)));
+    uint8_t dg[32];
+    sha256_final(s, dg);
+    int nw = nbits >> 5;
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t v = 0;
+        if (w < nw) {
+            const uint8_t *q = dg + 4 * (nw - 1 - w);
+            v = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+        }
+        kw[w] = v;
+        any |= v;
+    }
+    if (!any) kw[0] = 1;
+}
+// p <- [r]p, affine in and out (the G1 side of the per-tuple pairing); identity / undecodable points pass through
+BN_INL void item_rbv_scale_g1(g1m &p, uint8_t &fl, const uint32_t kw[4], int nbits) {
+    if (fl & (FL_BAD | FL_INF)) return;
+    g1p a, r;
+    pt_from_affine(a, p.x, p.y, false);
+    pt_mul(r, a, kw, nbits);
+    bool inf;
+    pt_to_affine(p.x, p.y, inf, r);
+    fl = inf ? FL_INF : 0;
+}
+// out <- [r]p, projective (the signature side: summed over the group before it meets a pairing)
+template <class F, class M>
+BN_INL void item_rbv_scale_proj(point<F> &out, const M &p, uint8_t fl, const uint32_t kw[4], int nbits) {
+    if (fl & (FL_BAD | FL_INF)) {
+        pt_set_identity(out);
+        return;
+    }
+    point<F> a;
+    pt_from_affine(a, p.x, p.y, false);
+    pt_mul(out, a, kw, nbits);
+}
+
 }  // namespace bn

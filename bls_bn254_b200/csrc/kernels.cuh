@@ -336,6 +336,137 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_sum(g2m *out
     if (t < m) sum_strided<F2, g2m>(out, flo, in, fl, n, m, t);
 }
 
+// ---- randomised batch verification (items.cuh: rbv_*) -----------------------------------------------
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g1(g1m *A, uint8_t *fl, const uint8_t *seed, uint64_t base, int nbits, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t kw[4];
+    rbv_scalar(kw, seed, base + i, nbits);
+    g1m p;
+    copy_rec(p, A[i]);
+    uint8_t f = fl[i];
+    item_rbv_scale_g1(p, f, kw, nbits);
+    copy_rec(A[i], p);
+    fl[i] = f;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g1p(g1p *S, const g1m *P, const uint8_t *fl, const uint8_t *seed, uint64_t base, int nbits,
+                                                                 size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t kw[4];
+    rbv_scalar(kw, seed, base + i, nbits);
+    g1m p;
+    copy_rec(p, P[i]);
+    g1p r;
+    item_rbv_scale_proj<F1, g1m>(r, p, fl[i], kw, nbits);
+    copy_rec(S[i], r);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g2p(g2p *S, const g2m *P, const uint8_t *fl, const uint8_t *seed, uint64_t base, int nbits,
+                                                                 size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t kw[4];
+    rbv_scalar(kw, seed, base + i, nbits);
+    g2m p;
+    copy_rec(p, P[i]);
+    g2p r;
+    item_rbv_scale_proj<F2, g2m>(r, p, fl[i], kw, nbits);
+    copy_rec(S[i], r);
+}
+// One level of a segmented reduction.  Segment s holds len(s) records at in + s * stride_in (len_full for every
+// segment but the last, len_last there); thread (s, j) folds records [j * fan, min((j + 1) * fan, len(s))) into
+// out[s * stride_out + j], stride_out = ceil(len_full / fan).
+struct seg_level {
+    size_t nseg, stride_in, len_full, len_last, stride_out;
+    int fan;
+};
+template <class T, class Op>
+__device__ __forceinline__ void seg_reduce(T *out, const T *in, const seg_level &L, Op op) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t s = t / L.stride_out, j = t - s * L.stride_out;
+    if (s >= L.nseg) return;
+    size_t len = (s + 1 == L.nseg) ? L.len_last : L.len_full;
+    size_t lo = j * (size_t)L.fan;
+    if (lo >= len) return;
+    size_t hi = lo + (size_t)L.fan < len ? lo + (size_t)L.fan : len;
+    const T *src = in + s * L.stride_in;
+    T acc, x;
+    copy_rec(acc, src[lo]);
+#pragma unroll 1
+    for (size_t q = lo + 1; q < hi; q++) {
+        copy_rec(x, src[q]);
+        op(acc, x);
+    }
+    copy_rec(out[s * L.stride_out + j], acc);
+}
+struct op_fp12_mul { __device__ void operator()(fp12 &a, const fp12 &b) const { fp12_mul(a, a, b); } };
+struct op_g1p_add { __device__ void operator()(g1p &a, const g1p &b) const { pt_add(a, a, b); } };
+struct op_g2p_add { __device__ void operator()(g2p &a, const g2p &b) const { pt_add(a, a, b); } };
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_fp12_seg_reduce(fp12 *out, const fp12 *in, seg_level L) { seg_reduce(out, in, L, op_fp12_mul()); }
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1p_seg_sum(g1p *out, const g1p *in, seg_level L) { seg_reduce(out, in, L, op_g1p_add()); }
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2p_seg_sum(g2p *out, const g2p *in, seg_level L) { seg_reduce(out, in, L, op_g2p_add()); }
+// group sums -> affine records; the other side of that pairing is the fixed generator
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1p_to_affine(g1m *out, uint8_t *fl, const g1p *in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1p a;
+    copy_rec(a, in[i]);
+    g1m r;
+    bool inf;
+    pt_to_affine(r.x, r.y, inf, a);
+    copy_rec(out[i], r);
+    fl[i] = inf ? FL_INF : 0;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2p_to_affine(g2m *out, uint8_t *fl, const g2p *in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2p a;
+    copy_rec(a, in[i]);
+    g2m r;
+    bool inf;
+    pt_to_affine(r.x, r.y, inf, a);
+    copy_rec(out[i], r);
+    fl[i] = inf ? FL_INF : 0;
+}
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_fill_neg_g2(g2m *Q, uint8_t *fl, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2m q;
+    q.x = kfp2(k::G2_GEN_X);
+    q.y = kfp2(k::NEG_G2_GEN_Y);
+    copy_rec(Q[i], q);
+    fl[i] = 0;
+}
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_fill_neg_g1(g1m *P, uint8_t *fl, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1m p;
+    p.x = kfp(k::ONE);
+    p.y = kfp(k::NEG_TWO);
+    copy_rec(P[i], p);
+    fl[i] = 0;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_fp12_mul_into(fp12 *A, const fp12 *B, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 a, b;
+    copy_rec(a, A[i]);
+    copy_rec(b, B[i]);
+    fp12_mul(a, a, b);
+    copy_rec(A[i], a);
+}
+// gbad[i / group] |= any undecodable input of tuple i
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_rbv_group_flags(int *gbad, const uint8_t *fa, const uint8_t *fb, const uint8_t *fc, size_t group, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((fa[i] | fb[i] | fc[i]) & FL_BAD) atomicOr(&gbad[i / group], 1);
+}
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_rbv_ok(uint8_t *ok, const fp12 *F, const int *gbad, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = (!gbad[i] && fp12_is_one(F[i])) ? 1 : 0;
+}
+
 // compressed codecs
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_compress(uint8_t *out, const g1m *P, const uint8_t *fl, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

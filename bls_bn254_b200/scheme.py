@@ -8,8 +8,10 @@ anywhere under src/); north_star names it as the crate API, so it is defined her
 All group work (hashing, scalar multiplication, sums, pairings) runs on the GPU through `Context`.
 """
 import hashlib
+import os
 import struct
 
+from .api import pack_msgs
 from .api import DST_MIN_PK, DST_MIN_SIG, G1_GENERATOR, G2_GENERATOR, MIN_PK, MIN_SIG, R_ORDER
 
 SEED = 0xB15B254
@@ -60,6 +62,44 @@ def sign(ctx, sks, msgs, variant=MIN_SIG, dst=None):
 def verify(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=0):
     """n accept bytes (0/1) for n independent (pk, msg, sig) tuples."""
     return ctx.verify_batch(variant, pks, msgs, sigs, _dst(variant) if dst is None else dst, flags)
+
+
+def rbv_scalar(seed, index, rand_bits=64):
+    """The per-tuple scalar of the randomised batch test (include/bls_bn254_b200.h)."""
+    dg = hashlib.sha256(bytes(seed) + struct.pack("<Q", index)).digest()
+    return int.from_bytes(dg[:rand_bits // 8], "big") or 1
+
+
+def verify_randomized(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=0, group=256, rand_bits=64, seed=None):
+    """n accept bytes like verify(), computed with one final exponentiation per GROUP of tuples: groups that
+    pass the small-exponent test are accepted wholesale (error probability <= 2^-rand_bits per group), the
+    tuples of a rejected group are re-verified one by one with the exact predicate.  `seed` defaults to 32
+    fresh bytes from the OS CSPRNG; pass one only for reproducible tests."""
+    dst = _dst(variant) if dst is None else dst
+    seed = os.urandom(32) if seed is None else seed
+    blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+    n = len(off) - 1
+    if n == 0:
+        return b""
+    groups = ctx.verify_batch_randomized(variant, pks, (blob, off), sigs, dst, seed, group, rand_bits, flags)
+    out = bytearray(n)
+    rpk, rsig = (128, 64) if variant == MIN_SIG else (64, 128)
+    redo = []
+    for g, okg in enumerate(groups):
+        lo, hi = g * group, min(n, (g + 1) * group)
+        if okg:
+            out[lo:hi] = b"\x01" * (hi - lo)
+        else:
+            redo.extend(range(lo, hi))
+    if redo:
+        blob_b = bytes(blob)
+        sub_msgs = [blob_b[off[i]:off[i + 1]] for i in redo]
+        sub_pks = b"".join(pks[i * rpk:(i + 1) * rpk] for i in redo)
+        sub_sigs = b"".join(sigs[i * rsig:(i + 1) * rsig] for i in redo)
+        exact = ctx.verify_batch(variant, sub_pks, sub_msgs, sub_sigs, dst, flags)
+        for i, v in zip(redo, exact):
+            out[i] = v
+    return bytes(out)
 
 
 def aggregate(ctx, sigs, variant=MIN_SIG):

@@ -88,6 +88,22 @@ int bn254_fp12_product(bn254_ctx *ctx, const uint8_t *in /* n*384 */, size_t n, 
  * aggregate (distinct messages): e(aggsig, -g2) * prod e(H(m_i), pk_i) == 1  (resp. min-pk) */
 int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs,
                        size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* n bytes 0/1 */);
+/* Randomised batch verification (no counterpart in the reference).  The tuples are
+ * taken in consecutive groups of `group` (1..BN254_RBV_MAX_GROUP; the last group may be short) and every group
+ * gets ONE accept byte from a small-exponent test:
+ *     min-sig: e(sum_i r_i sig_i, -g2) * prod_i e(r_i H_G1(m_i), pk_i) == 1       (min-pk symmetric)
+ * i.e. one Miller loop per tuple and one final exponentiation per GROUP instead of per tuple.
+ * r_i = first rand_bits (64 or 128) bits of SHA-256(seed[32] || LE64(i)), big-endian, 0 -> 1, i = index of the
+ * tuple in this call.  A group whose tuples all verify is always accepted; a group with an invalid tuple is
+ * accepted with probability <= 2^-rand_bits PROVIDED the seed is unpredictable to whoever produced the
+ * signatures (fresh CSPRNG output per call) and public keys / signatures lie in the order-r subgroups
+ * (BN254_FLAG_CHECK_SUBGROUP for untrusted min-sig public keys / min-pk signatures).  On a rejected group the
+ * caller falls back to bn254_verify_batch on that group's tuples for per-tuple verdicts. */
+#define BN254_RBV_MAX_GROUP 65536
+int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
+                                  const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags,
+                                  const uint8_t *seed /* 32 B */, int rand_bits, size_t group,
+                                  uint8_t *ok_groups /* ceil(n/group) bytes 0/1 */);
 int bn254_aggregate_verify(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* 1 byte */);
 /* One shard of an aggregate verification: the Fp12 product of this shard's Miller loops (384 B,
@@ -126,6 +142,9 @@ int bn254_hash_to_g2_dev(bn254_ctx *ctx, const uint8_t *msgs, const uint64_t *of
 int bn254_pairing_batch_dev(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t *gt, uint8_t *status);
 int bn254_verify_batch_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
                            const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok);
+int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,
+                                      const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags,
+                                      const uint8_t *seed, int rand_bits, size_t group, uint8_t *ok_groups);
 int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                                 const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial,
                                 uint8_t *bad);

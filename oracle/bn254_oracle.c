@@ -1090,6 +1090,98 @@ EXPORT int orc_verify_batch(int variant, const uint8_t *pks, const uint8_t *msgs
     parallel_for(n, nthreads, verify_range, &a);
     return 0;
 }
+/* Randomised batch verification (defined by include/bls_bn254_b200.h, absent in the
+ * reference): per group of `group` consecutive tuples
+ *   min-sig: e(sum r_i sig_i, -g2) * prod e(r_i H(m_i), pk_i) == 1;  min-pk: e(-g1, sum r_i sig_i) * prod e(r_i pk_i, H(m_i)) == 1
+ * r_i = first rand_bits of SHA-256(seed || LE64(i)) as a big-endian integer, 0 -> 1. */
+static void rbv_scalar(uint64_t k[4], const uint8_t seed[32], uint64_t idx, int rand_bits) {
+    sha256_ctx c; uint8_t le[8], dg[32];
+    for (int b = 0; b < 8; b++) le[b] = (uint8_t)(idx >> (8 * b));
+    sha256_init(&c); sha256_update(&c, seed, 32); sha256_update(&c, le, 8); sha256_final(&c, dg);
+    int nb = rand_bits / 8;
+    k[0] = k[1] = k[2] = k[3] = 0;
+    for (int j = 0; j < nb; j++) { int bit = 8 * (nb - 1 - j); k[bit >> 6] |= (uint64_t)dg[j] << (bit & 63); }
+    if (!(k[0] | k[1])) k[0] = 1;
+}
+typedef struct {
+    verify_args v; const uint8_t *seed; int rand_bits; size_t group, n;
+    g1a *ps; g2a *qs; g1p *s1; g2p *s2; uint8_t *bad; uint8_t *okg;
+} rbv_args;
+static void rbv_item_range(void *p, size_t lo, size_t hi) {
+    rbv_args *r = (rbv_args *)p; const verify_args *a = &r->v;
+    for (size_t i = lo; i < hi; i++) {
+        const uint8_t *msg = a->msgs + a->off[i];
+        size_t mlen = a->off[i + 1] - a->off[i];
+        uint64_t k[4];
+        rbv_scalar(k, r->seed, (uint64_t)i, r->rand_bits);
+        r->bad[i] = 1;
+        if (a->variant == 0) {
+            g2a pk; g1a sig, h; g1p t;
+            if (!g2a_from_bytes(&pk, a->pks + 128 * i) || !g1a_from_bytes(&sig, a->sigs + 64 * i)) continue;
+            if ((a->flags & 3) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) continue;
+            if ((a->flags & 2) && (!g2a_torsion_free(&pk) || !g1a_torsion_free(&sig))) continue;
+            if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
+            g1_from_affine(&t, &h.x, &h.y, h.inf); g1_mul_limbs(&t, &t, k, r->rand_bits);
+            g1_to_affine(&r->ps[i].x, &r->ps[i].y, &r->ps[i].inf, &t);
+            r->qs[i] = pk;
+            g1_from_affine(&t, &sig.x, &sig.y, sig.inf); g1_mul_limbs(&r->s1[i], &t, k, r->rand_bits);
+        } else {
+            g1a pk; g2a sig, h; g1p t; g2p u;
+            if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) continue;
+            if ((a->flags & 3) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) continue;
+            if ((a->flags & 2) && (!g1a_torsion_free(&pk) || !g2a_torsion_free(&sig))) continue;
+            if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
+            g1_from_affine(&t, &pk.x, &pk.y, pk.inf); g1_mul_limbs(&t, &t, k, r->rand_bits);
+            g1_to_affine(&r->ps[i].x, &r->ps[i].y, &r->ps[i].inf, &t);
+            r->qs[i] = h;
+            g2_from_affine(&u, &sig.x, &sig.y, sig.inf); g2_mul_limbs(&r->s2[i], &u, k, r->rand_bits);
+        }
+        r->bad[i] = 0;
+    }
+}
+static void rbv_group_range(void *p, size_t lo, size_t hi) {
+    rbv_args *r = (rbv_args *)p;
+    for (size_t g = lo; g < hi; g++) {
+        size_t s = g * r->group, e = s + r->group < r->n ? s + r->group : r->n;
+        int bad = 0;
+        for (size_t i = s; i < e; i++) bad |= r->bad[i];
+        if (bad) { r->okg[g] = 0; continue; }
+        fp12 f, fs; g1a P; g2a Q;
+        multi_miller(&f, r->ps + s, r->qs + s, e - s);
+        if (r->v.variant == 0) {
+            g1p acc; g1_set_identity(&acc);
+            for (size_t i = s; i < e; i++) g1_add(&acc, &acc, &r->s1[i]);
+            g1_to_affine(&P.x, &P.y, &P.inf, &acc);
+            Q = NEG_G2_GEN_A;
+        } else {
+            g2p acc; g2_set_identity(&acc);
+            for (size_t i = s; i < e; i++) g2_add(&acc, &acc, &r->s2[i]);
+            g2_to_affine(&Q.x, &Q.y, &Q.inf, &acc);
+            P = NEG_G1_GEN_A;
+        }
+        multi_miller(&fs, &P, &Q, 1);
+        fp12_mul(&f, &f, &fs);
+        final_exponentiation(&f, &f);
+        r->okg[g] = (uint8_t)fp12_eq(&f, &F12_ONE);
+    }
+}
+EXPORT int orc_verify_batch_randomized(int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, const uint8_t *sigs, size_t n,
+                                       const uint8_t *dst, size_t dst_len, uint32_t flags, const uint8_t *seed, int rand_bits, size_t group,
+                                       uint8_t *ok_groups, int nthreads) {
+    orc_init();
+    if ((rand_bits != 64 && rand_bits != 128) || group == 0) return -10;
+    if (n == 0) return 0;
+    rbv_args r;
+    memset(&r, 0, sizeof r);
+    verify_args v = {variant, pks, msgs, off, sigs, dst, dst_len, flags, NULL};
+    r.v = v; r.seed = seed; r.rand_bits = rand_bits; r.group = group; r.n = n; r.okg = ok_groups;
+    r.ps = (g1a *)calloc(n, sizeof(g1a)); r.qs = (g2a *)calloc(n, sizeof(g2a)); r.bad = (uint8_t *)calloc(n, 1);
+    if (variant == 0) r.s1 = (g1p *)calloc(n, sizeof(g1p)); else r.s2 = (g2p *)calloc(n, sizeof(g2p));
+    parallel_for(n, nthreads, rbv_item_range, &r);
+    parallel_for((n + group - 1) / group, nthreads, rbv_group_range, &r);
+    free(r.ps); free(r.qs); free(r.bad); free(r.s1); free(r.s2);
+    return 0;
+}
 /* aggregate verify, distinct messages: e(aggsig, -g2) * prod e(H(m_i), pk_i) == 1 (min-sig);
  * e(-g1, aggsig) * prod e(pk_i, H(m_i)) == 1 (min-pk) */
 typedef struct { int variant; const uint8_t *pks; const uint8_t *msgs; const uint64_t *off; const uint8_t *dst; size_t dst_len; uint32_t flags;

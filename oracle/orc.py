@@ -130,6 +130,18 @@ def verify_batch(variant, pks, msgs, sigs, dst, flags=0, nthreads=1):
     return ok.raw
 
 
+def verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0, nthreads=1):
+    """one accept byte per group of `group` consecutive tuples (include/bls_bn254_b200.h: bn254_verify_batch_randomized)"""
+    blob, off = pack_msgs(msgs)
+    n = len(msgs)
+    ng = (n + group - 1) // group
+    ok = _buf(max(ng, 1))
+    rc = lib().orc_verify_batch_randomized(variant, pks, blob, off, sigs, C.c_size_t(n), dst, C.c_size_t(len(dst)), C.c_uint32(flags), seed,
+                                           rand_bits, C.c_size_t(group), ok, nthreads)
+    assert rc == 0, rc
+    return ok.raw[:ng]
+
+
 def aggregate_verify(variant, pks, msgs, agg_sig, dst, flags=0, nthreads=1):
     blob, off = pack_msgs(msgs)
     ok = _buf(1)

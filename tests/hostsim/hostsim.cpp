@@ -125,6 +125,39 @@ EXPORT void sim_g2_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t 
         item_g2_encode(out + 128 * i, r, flo);
     }
 }
+// randomised batch verification: the per-tuple scalar and the two scalings of items.cuh
+EXPORT void sim_rbv_scalar(const uint8_t *seed, uint64_t idx, int nbits, uint32_t *kw) { rbv_scalar(kw, seed, idx, nbits); }
+EXPORT void sim_rbv_scale(const uint8_t *g1pts, const uint8_t *g2pts, size_t n, const uint8_t *seed, uint64_t idx0, int nbits, uint8_t *out_g1_affine,
+                          uint8_t *out_g1_sum, uint8_t *out_g2_sum) {
+    g1p s1;
+    g2p s2;
+    pt_set_identity(s1);
+    pt_set_identity(s2);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t kw[4];
+        rbv_scalar(kw, seed, idx0 + i, nbits);
+        g1m p;
+        g2m q;
+        uint8_t fl, flq;
+        item_g1_decode(p, fl, g1pts + 64 * i, false);
+        item_g2_decode(q, flq, g2pts + 128 * i, false);
+        g1p t1;
+        g2p t2;
+        item_rbv_scale_proj<F1, g1m>(t1, p, fl, kw, nbits);
+        item_rbv_scale_proj<F2, g2m>(t2, q, flq, kw, nbits);
+        pt_add(s1, s1, t1);
+        pt_add(s2, s2, t2);
+        item_rbv_scale_g1(p, fl, kw, nbits);
+        item_g1_encode(out_g1_affine + 64 * i, p, fl);
+    }
+    g1m a1;
+    g2m a2;
+    bool inf;
+    pt_to_affine(a1.x, a1.y, inf, s1);
+    item_g1_encode(out_g1_sum, a1, inf ? FL_INF : 0);
+    pt_to_affine(a2.x, a2.y, inf, s2);
+    item_g2_encode(out_g2_sum, a2, inf ? FL_INF : 0);
+}
 EXPORT void sim_g1_codec(const uint8_t *pts, size_t n, uint8_t *comp, uint8_t *back, uint8_t *status) {
     for (size_t i = 0; i < n; i++) {
         g1m p, r;

@@ -234,6 +234,97 @@ def test_aggregate_verify(ctx, orc, B, variant):
     assert ctx.aggregate_verify(variant, badpk, msgs, agg, dst) == 0
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_randomized_batch_verify_vs_oracle(ctx, orc, B, variant):
+    """bn254_verify_batch_randomized: group verdicts equal the oracle's and the AND of the exact
+    per-tuple verdicts; ragged last group, group = 1, group > n, both scalar widths."""
+    n = 203
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=variant, corrupt_every=40)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    seed = bytes(range(7, 39))
+    for group, bits in ((16, 64), (64, 128), (1, 64), (500, 64)):
+        got = ctx.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=group, rand_bits=bits)
+        want = bytes(int(all(exp[g:g + group])) for g in range(0, n, group))
+        assert got == want
+        if group != 1:
+            assert got == orc.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=group, rand_bits=bits, nthreads=8)
+    assert 0 < sum(ctx.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=16)) < 13
+    # undecodable input and the on-curve flag reject the group that holds them
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    junk = b"\xff" * rpk + pks[rpk:]
+    assert ctx.verify_batch_randomized(variant, junk, msgs, sigs, dst, seed, group=16)[0] == 0
+    off = bytearray(sigs)
+    off[rsig * 100 + rsig - 1] ^= 1
+    got = ctx.verify_batch_randomized(variant, pks, msgs, bytes(off), dst, seed, group=16, flags=B.CHECK_ON_CURVE)
+    assert got == orc.verify_batch_randomized(variant, pks, msgs, bytes(off), dst, seed, group=16, flags=1, nthreads=8)
+    assert got[100 // 16] == 0
+    assert ctx.verify_batch_randomized(variant, b"", [], b"", dst, seed) == b""
+    # the wrapper with per-tuple verdicts: accepted groups wholesale, rejected groups re-verified exactly
+    assert B.scheme.verify_randomized(ctx, pks, msgs, sigs, variant=variant, group=32) == exp
+    with pytest.raises(B.Bn254Error):
+        ctx.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=0)
+    with pytest.raises(B.Bn254Error):
+        ctx.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, rand_bits=32)
+
+
+def test_randomized_batch_verify_scalars_and_cancellation(ctx, orc, B):
+    """Errors that cancel in a plain sum are caught; a forgery built from PREDICTED scalars is accepted, which
+    pins r_i = SHA-256(seed || LE64(i))[:rand_bits/8] bit-exactly (and shows why the seed must be secret)."""
+    from rbv_util import _neg_g1, rbv_forgery
+    n = 40
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=0, corrupt_every=0)
+    dst, seed = B.DST_MIN_SIG, bytes(range(32))
+    d = B.G1_GENERATOR
+    forged = bytearray(sigs)
+    forged[0:64] = ctx.g1_sum(sigs[0:64] + d)
+    forged[64:128] = ctx.g1_sum(sigs[64:128] + _neg_g1(d))
+    forged = bytes(forged)
+    assert ctx.verify_batch(0, pks, msgs, forged, dst)[:3] == b"\x00\x00\x01"
+    assert ctx.aggregate_verify(0, pks, msgs, ctx.g1_sum(forged), dst) == 1
+    assert ctx.verify_batch_randomized(0, pks, msgs, forged, dst, seed, group=n) == b"\x00"
+    for bits, (i, j) in ((64, (0, 1)), (128, (3, 38)), (64, (17, 33))):
+        known = rbv_forgery(orc, sigs, seed, bits=bits, i=i, j=j)
+        assert ctx.verify_batch_randomized(0, pks, msgs, known, dst, seed, group=n, rand_bits=bits) == b"\x01"
+        assert ctx.verify_batch_randomized(0, pks, msgs, known, dst, bytes(32), group=n, rand_bits=bits) == b"\x00"
+        assert ctx.verify_batch_randomized(0, pks, msgs, known, dst, seed, group=n, rand_bits=192 - bits) == b"\x00"
+        # the index that enters the scalar is the tuple's index in the CALL, also when the pair sits in a later group
+        want = bytearray(b"\x01" * ((n + 15) // 16))
+        if i // 16 != j // 16:
+            want[i // 16] = want[j // 16] = 0
+        assert ctx.verify_batch_randomized(0, pks, msgs, known, dst, seed, group=16, rand_bits=bits) == bytes(want)
+
+
+def test_randomized_batch_verify_chunked(orc, B, monkeypatch):
+    """groups never straddle a staging chunk: BN254_CHUNK=100 with group 48 makes chunks of 96 tuples"""
+    monkeypatch.setenv("BN254_CHUNK", "100")
+    c = B.Context([0])
+    try:
+        n = 500
+        pks, msgs, sigs, exp = B.scheme.synth_batch(c, n, variant=0, corrupt_every=90)
+        seed = b"\x11" * 32
+        got = c.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=48)
+        assert got == bytes(int(all(exp[g:g + 48])) for g in range(0, n, 48))
+        assert got == orc.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=48, nthreads=8)
+        got = c.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=300)   # group > chunk
+        assert got == b"\x00\x00"
+        assert B.scheme.verify_randomized(c, pks, msgs, sigs, group=48) == exp
+    finally:
+        c.close()
+
+
+def test_randomized_batch_verify_full_size(ctx, B):
+    """2^16 valid tuples in groups of 256: every group accepts; one flipped bit rejects exactly its group"""
+    n = 1 << 16
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=0, n_keys=256, corrupt_every=0)
+    seed = b"\xc3" * 32
+    assert ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=256) == b"\x01" * 256
+    assert ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=65536) == b"\x01"
+    msgs[40000] = msgs[40000][:-1] + bytes([msgs[40000][-1] ^ 1])
+    got = ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=256)
+    assert got == b"\x01" * 156 + b"\x00" + b"\x01" * 99
+    assert ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=65536) == b"\x00"
+
+
 def test_verify_full_size_property(ctx, orc, B):
     """BASELINE config 2 size (2^16 tuples, min-sig): accept bits must equal the construction; a 96-tuple
     sample is re-checked against the oracle."""

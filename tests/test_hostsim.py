@@ -154,6 +154,33 @@ def test_scalar_mul_and_codecs(sim, orc):
     assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
 
 
+def test_randomized_batch_scalars_and_scalings(sim, orc):
+    """rbv_scalar = SHA-256(seed || LE64(i)) truncated (hashlib), and the two scalings of a tuple
+    (affine [r]P for the pairing, projective [r]S summed over the group) against the oracle's scalar multiplication"""
+    import hashlib
+    rng = random.Random(8)
+    seed = rng.randbytes(32)
+    kw = (C.c_uint32 * 4)()
+    for idx in (0, 1, 255, 256, 2**32 + 5, 2**63 + 11):
+        dg = hashlib.sha256(seed + idx.to_bytes(8, "little")).digest()
+        for bits in (64, 128):
+            sim.sim_rbv_scalar(seed, C.c_uint64(idx), bits, kw)
+            assert sum(int(kw[w]) << (32 * w) for w in range(4)) == int.from_bytes(dg[:bits // 8], "big")
+    n = 5
+    msgs = [rng.randbytes(9) for _ in range(n - 1)]
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    ident2 = bytes(64) + bytes(63) + b"\x01"
+    g1 = orc.hash_to_g1(msgs, QUUX_G1) + ident1
+    g2 = orc.hash_to_g2(msgs[:-1], QUUX_G2) + ident2 + orc.g2_generator()
+    for bits, idx0 in ((64, 0), (128, 1000)):
+        rs = b"".join((int.from_bytes(hashlib.sha256(seed + (idx0 + i).to_bytes(8, "little")).digest()[:bits // 8], "big") or 1).to_bytes(32, "big") for i in range(n))
+        o1, s1, s2 = C.create_string_buffer(64 * n), C.create_string_buffer(64), C.create_string_buffer(128)
+        sim.sim_rbv_scale(g1, g2, C.c_size_t(n), seed, C.c_uint64(idx0), bits, o1, s1, s2)
+        assert o1.raw == orc.g1_mul(g1, rs)
+        assert s1.raw == orc.g1_sum(orc.g1_mul(g1, rs))
+        assert s2.raw == orc.g2_sum(orc.g2_mul(g2, rs))
+
+
 def test_lane_pair_pairing(sim, orc):
     """two lanes per pairing (lane-split Fp2, BN_LANES=2 kernels): the same bodies run by two emulated
     lanes exchanging through the shuffle hook must equal the oracle, identity and bad inputs included"""
