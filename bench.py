@@ -25,11 +25,12 @@ sys.path.insert(0, ROOT)
 
 # canonical work per unit in Fp multiplications M; 1 M = 264 INT32 IMAD-ops
 M_IMAD = 264
-# verify_rand (randomised batch verification, groups of 256, 64-bit scalars): hash 2204 + one-pair Miller loop 8610 + two 64-bit
-# double-and-add scalings (64 x 8 + 32 x 12 = 896 each) + one affine conversion 332 + product tree 58 + per-group pairing / 256 = 68
-WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 13064}
+# verify_rand (randomised batch verification, groups of 256, 64-bit scalars a + b lambda): hash 2204 + one-pair Miller loop 8610 +
+# two joint double-and-add scalings (32 x 8 + 25 x 12 + 1 = 557 each) + one affine conversion 332 + product tree 58 + per-group
+# pairing / 256 = 68
+WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 12386}
 KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
-            "k_rbv_scale_g1": 1228, "k_rbv_scale_g1p": 896}
+            "k_rbv_scale_g1": 889, "k_rbv_scale_g1p": 557}
 UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
         "aggregate": "verifications/s", "verify_rand": "verifications/s"}
 METRIC = {"verify": "bls_verifications_per_sec", "verify_pk": "bls_verifications_per_sec", "hash_g1": "hash_to_g1_per_sec",

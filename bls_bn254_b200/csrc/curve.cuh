@@ -24,6 +24,7 @@ struct F1 {  // field policy: Fp
     static BN_INL bool is_zero(const T &a) { return fp_is_zero(a); }
     static BN_INL void set_zero(T &r) { fp_set_zero(r); }
     static BN_INL void set_one(T &r) { fp_set_one(r); }
+    static BN_INL void glv_beta(T &r, const T &a) { fp_mulx(r, a, kfp(k::GLV_BETA1)); }
 };
 struct F2 {  // field policy: Fp2
     typedef fp2 T;
@@ -37,6 +38,7 @@ struct F2 {  // field policy: Fp2
     static BN_INL bool is_zero(const T &a) { return fp2_is_zero(a); }
     static BN_INL void set_zero(T &r) { fp2_set_zero(r); }
     static BN_INL void set_one(T &r) { fp2_set_one(r); }
+    static BN_INL void glv_beta(T &r, const T &a) { fp2_mul_fp(r, a, kfp(k::GLV_BETA2)); }
 };
 
 template <class F>
@@ -158,6 +160,28 @@ BN_INL void pt_mul(point<F> &r, const point<F> &a, const uint32_t *kw, int nbits
     for (int i = nbits - 1; i >= 0; i--) {
         pt_dbl(acc, acc);
         if ((kw[i >> 5] >> (i & 31)) & 1) pt_add(acc, acc, base);
+    }
+    r = acc;
+}
+
+// [a + b lambda]p for nbits-bit a, b (little-endian 32-bit words), lambda the eigenvalue of the endomorphism
+// phi(x, y) = (beta x, y) on the order-r subgroup (constants derived in oracle/pymodel.py::glv_constants):
+// one joint MSB-first double-and-add over the table {p, phi(p), p + phi(p)} -- nbits doublings and ~3/4 nbits
+// additions for a 2*nbits-bit scalar.  Used by the randomised batch verification, whose scalars are drawn in
+// this form; p must lie in the order-r subgroup for the result to equal [a + b lambda mod r]p.
+template <class F>
+BN_INL void pt_mul_glv(point<F> &r, const point<F> &p, const uint32_t *ka, const uint32_t *kb, int nbits) {
+    point<F> tab[3], acc;
+    tab[0] = p;
+    tab[1] = p;
+    F::glv_beta(tab[1].x, p.x);
+    pt_add(tab[2], tab[0], tab[1]);
+    pt_set_identity(acc);
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        uint32_t sel = ((ka[i >> 5] >> (i & 31)) & 1) | (((kb[i >> 5] >> (i & 31)) & 1) << 1);
+        if (sel) pt_add(acc, acc, tab[sel - 1]);
     }
     r = acc;
 }

@@ -250,10 +250,16 @@ BN_INL void item_g2_decompress(g2m &out, uint8_t &fl, const uint8_t *in) {
 // ---- randomised batch verification (no counterpart in the reference) -------------
 // Small-exponent test: a group of tuples is accepted when
 //     e(sum_i r_i sig_i, -g2) * prod_i e(r_i H(m_i), pk_i) == 1          (min-sig; min-pk symmetric)
-// with per-tuple scalars r_i the caller cannot predict: r_i = the first nbits (64 or 128) of
-// SHA-256(seed || LE64(i)) read as a big-endian integer, 0 replaced by 1; i is the tuple's index in the
-// whole call.  kw = little-endian 32-bit words.
-BN_INL void rbv_scalar(uint32_t kw[4], const uint8_t *seed, uint64_t idx, int nbits) {
+// with per-tuple scalars r_i the caller cannot predict.  r_i = a_i + b_i lambda mod r, where a_i and b_i are
+// the first and the second nbits/2 bits (big-endian) of SHA-256(seed || LE64(i)), i the tuple's index in the
+// whole call, and lambda is the eigenvalue of (x, y) -> (beta x, y).  (a, b) -> a + b lambda mod r is
+// injective for a, b < 2^64 (the shortest vector of the lattice {(u, v): u + v lambda = 0 mod r} has a 127-bit
+// coordinate), so r_i is uniform over 2^nbits values and the test's error bound 2^-nbits holds, while [r_i]P
+// costs nbits/2 doublings (curve.cuh: pt_mul_glv).  a = b = 0 is replaced by a = 1.
+struct rbv_k {
+    uint32_t a[2], b[2];   // little-endian words; only the low nbits/2 bits are used
+};
+BN_INL void rbv_scalar(rbv_k &kk, const uint8_t *seed, uint64_t idx, int nbits) {
     sha256 s;
     sha256_init(s);
     sha256_update(s, seed, 32);
@@ -261,40 +267,37 @@ BN_INL void rbv_scalar(uint32_t kw[4], const uint8_t *seed, uint64_t idx, int nb
     for (int b = 0; b < 8; b++) sha256_put(s, (uint8_t)(idx >> (8 * b)));
     uint8_t dg[32];
     sha256_final(s, dg);
-    int nw = nbits >> 5;
-    uint32_t any = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t v = 0;
-        if (w < nw) {
-            const uint8_t *q = dg + 4 * (nw - 1 - w);
-            v = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
-        }
-        kw[w] = v;
-        any |= v;
+    // digest words are big-endian: nbits = 64 -> a = h0, b = h1; nbits = 128 -> a = h0 h1, b = h2 h3
+    auto be32 = [&](int w) { const uint8_t *q = dg + 4 * w; return ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3]; };
+    if (nbits == 64) {
+        kk.a[0] = be32(0); kk.a[1] = 0;
+        kk.b[0] = be32(1); kk.b[1] = 0;
+    } else {
+        kk.a[1] = be32(0); kk.a[0] = be32(1);
+        kk.b[1] = be32(2); kk.b[0] = be32(3);
     }
-    if (!any) kw[0] = 1;
+    if (!(kk.a[0] | kk.a[1] | kk.b[0] | kk.b[1])) kk.a[0] = 1;
 }
 // p <- [r]p, affine in and out (the G1 side of the per-tuple pairing); identity / undecodable points pass through
-BN_INL void item_rbv_scale_g1(g1m &p, uint8_t &fl, const uint32_t kw[4], int nbits) {
+BN_INL void item_rbv_scale_g1(g1m &p, uint8_t &fl, const rbv_k &kk, int nbits) {
     if (fl & (FL_BAD | FL_INF)) return;
     g1p a, r;
     pt_from_affine(a, p.x, p.y, false);
-    pt_mul(r, a, kw, nbits);
+    pt_mul_glv(r, a, kk.a, kk.b, nbits >> 1);
     bool inf;
     pt_to_affine(p.x, p.y, inf, r);
     fl = inf ? FL_INF : 0;
 }
 // out <- [r]p, projective (the signature side: summed over the group before it meets a pairing)
 template <class F, class M>
-BN_INL void item_rbv_scale_proj(point<F> &out, const M &p, uint8_t fl, const uint32_t kw[4], int nbits) {
+BN_INL void item_rbv_scale_proj(point<F> &out, const M &p, uint8_t fl, const rbv_k &kk, int nbits) {
     if (fl & (FL_BAD | FL_INF)) {
         pt_set_identity(out);
         return;
     }
     point<F> a;
     pt_from_affine(a, p.x, p.y, false);
-    pt_mul(out, a, kw, nbits);
+    pt_mul_glv(out, a, kk.a, kk.b, nbits >> 1);
 }
 
 }  // namespace bn

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_sum(g2m *out
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g1(g1m *A, uint8_t *fl, const uint8_t *seed, uint64_t base, int nbits, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t kw[4];
+    rbv_k kw;
     rbv_scalar(kw, seed, base + i, nbits);
     g1m p;
     copy_rec(p, A[i]);
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g1p(g
                                                                  size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t kw[4];
+    rbv_k kw;
     rbv_scalar(kw, seed, base + i, nbits);
     g1m p;
     copy_rec(p, P[i]);
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g2p(g
                                                                  size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t kw[4];
+    rbv_k kw;
     rbv_scalar(kw, seed, base + i, nbits);
     g2m p;
     copy_rec(p, P[i]);

@@ -64,10 +64,17 @@ def verify(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=0):
     return ctx.verify_batch(variant, pks, msgs, sigs, _dst(variant) if dst is None else dst, flags)
 
 
+GLV_LAMBDA = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd   # eigenvalue of (x, y) -> (beta x, y); oracle/pymodel.py::glv_constants
+
+
 def rbv_scalar(seed, index, rand_bits=64):
-    """The per-tuple scalar of the randomised batch test (include/bls_bn254_b200.h)."""
+    """The per-tuple scalar of the randomised batch test (include/bls_bn254_b200.h): a + b lambda mod r."""
     dg = hashlib.sha256(bytes(seed) + struct.pack("<Q", index)).digest()
-    return int.from_bytes(dg[:rand_bits // 8], "big") or 1
+    h = rand_bits // 16
+    a, b = int.from_bytes(dg[:h], "big"), int.from_bytes(dg[h:2 * h], "big")
+    if a == 0 and b == 0:
+        a = 1
+    return (a + b * GLV_LAMBDA) % R_ORDER
 
 
 def verify_randomized(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=0, group=256, rand_bits=64, seed=None):

@@ -93,8 +93,11 @@ int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const ui
  * gets ONE accept byte from a small-exponent test:
  *     min-sig: e(sum_i r_i sig_i, -g2) * prod_i e(r_i H_G1(m_i), pk_i) == 1       (min-pk symmetric)
  * i.e. one Miller loop per tuple and one final exponentiation per GROUP instead of per tuple.
- * r_i = first rand_bits (64 or 128) bits of SHA-256(seed[32] || LE64(i)), big-endian, 0 -> 1, i = index of the
- * tuple in this call.  A group whose tuples all verify is always accepted; a group with an invalid tuple is
+ * r_i = a_i + b_i * lambda mod r with (a_i, b_i) = the first / second rand_bits/2 bits (rand_bits = 64 or 128) of
+ * SHA-256(seed[32] || LE64(i)), big-endian, (0, 0) -> (1, 0); i = index of the tuple in this call and
+ * lambda = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd, the eigenvalue of (x, y) -> (beta x, y) on the
+ * order-r subgroups.  r_i takes 2^rand_bits distinct values ((a, b) -> a + b lambda is injective below 2^64) and
+ * [r_i]P costs only rand_bits/2 doublings.  A group whose tuples all verify is always accepted; a group with an invalid tuple is
  * accepted with probability <= 2^-rand_bits PROVIDED the seed is unpredictable to whoever produced the
  * signatures (fresh CSPRNG output per call) and public keys / signatures lie in the order-r subgroups
  * (BN254_FLAG_CHECK_SUBGROUP for untrusted min-sig public keys / min-pk signatures).  On a rejected group the

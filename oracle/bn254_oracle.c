@@ -188,6 +188,7 @@ static void fp_from_okm(fp *r, const uint8_t b[48]) {
 }
 
 /* ------------------------------------------------------------------ Fp2 = Fp[u]/(u^2+1) */
+static fp FP_GLV_BETA1, FP_GLV_BETA2; /* (beta x, y) = [lambda](x, y) on G1 / on G2, tools/gen_constants.py */
 static fp2 F2_B, F2_B3, F2_ENDO_U, F2_ENDO_V, F2_SVDW_C1, F2_SVDW_C2, F2_SVDW_C3, F2_SVDW_C4;
 static fp2 F2_GAMMA[3][5];
 static fp F_SVDW_C2, F_SVDW_C3, F_SVDW_C4, F_THREE, F_FOUR;
@@ -395,6 +396,9 @@ typedef struct { fp2 x, y; int inf; } g2a;
 
 static void fp_mul_by_3b(fp *r, const fp *a) { fp t; fp_dbl(&t, a); fp_dbl(&t, &t); fp_dbl(&t, &t); fp_add(r, &t, a); } /* fp.rs:414-416 */
 static void fp2_mul_by_3b(fp2 *r, const fp2 *a) { fp2_mul(r, a, &F2_B3); } /* fp2.rs:411-413 */
+
+static void fp_glv_beta(fp *r, const fp *a) { fp_mul(r, a, &FP_GLV_BETA1); }
+static void fp2_glv_beta(fp2 *r, const fp2 *a) { fp2_mul_fp(r, a, &FP_GLV_BETA2); }
 
 #define FE fp
 #define FN(x) fp_##x
@@ -862,6 +866,8 @@ static void init_impl(void) {
     fp_from_canon(&F_SVDW_C4, ORC_SVDW1_C4);
     fp2_from_canon(&F2_B, ORC_B2);
     fp2_add(&F2_B3, &F2_B, &F2_B); fp2_add(&F2_B3, &F2_B3, &F2_B); /* fp2.rs:350 */
+    fp_from_canon(&FP_GLV_BETA1, ORC_GLV_BETA1);
+    fp_from_canon(&FP_GLV_BETA2, ORC_GLV_BETA2);
     fp2_from_canon(&F2_ENDO_U, ORC_ENDO_U);
     fp2_from_canon(&F2_ENDO_V, ORC_ENDO_V);
     fp2_from_canon(&F2_SVDW_C1, ORC_SVDW2_C1);
@@ -1093,15 +1099,19 @@ EXPORT int orc_verify_batch(int variant, const uint8_t *pks, const uint8_t *msgs
 /* Randomised batch verification (defined by include/bls_bn254_b200.h, absent in the
  * reference): per group of `group` consecutive tuples
  *   min-sig: e(sum r_i sig_i, -g2) * prod e(r_i H(m_i), pk_i) == 1;  min-pk: e(-g1, sum r_i sig_i) * prod e(r_i pk_i, H(m_i)) == 1
- * r_i = first rand_bits of SHA-256(seed || LE64(i)) as a big-endian integer, 0 -> 1. */
-static void rbv_scalar(uint64_t k[4], const uint8_t seed[32], uint64_t idx, int rand_bits) {
+ * r_i = a_i + b_i lambda mod r, (a_i, b_i) = the first / second rand_bits/2 bits of SHA-256(seed || LE64(i)) (big-endian),
+ * (0, 0) -> (1, 0); lambda = the eigenvalue of (x, y) -> (beta x, y) (oracle/pymodel.py::glv_constants).  [r_i]P is
+ * evaluated as [a_i]P + [b_i]phi(P) by one joint double-and-add (orc_curve_tmpl.h: mul_glv); tests/test_oracle.py
+ * checks it against the plain multiplication by the integer a_i + b_i lambda mod r. */
+static void rbv_scalar(uint64_t *ka, uint64_t *kb, const uint8_t seed[32], uint64_t idx, int rand_bits) {
     sha256_ctx c; uint8_t le[8], dg[32];
     for (int b = 0; b < 8; b++) le[b] = (uint8_t)(idx >> (8 * b));
     sha256_init(&c); sha256_update(&c, seed, 32); sha256_update(&c, le, 8); sha256_final(&c, dg);
-    int nb = rand_bits / 8;
-    k[0] = k[1] = k[2] = k[3] = 0;
-    for (int j = 0; j < nb; j++) { int bit = 8 * (nb - 1 - j); k[bit >> 6] |= (uint64_t)dg[j] << (bit & 63); }
-    if (!(k[0] | k[1])) k[0] = 1;
+    int h = rand_bits / 16; /* bytes per half */
+    uint64_t a = 0, b = 0;
+    for (int j = 0; j < h; j++) { a = (a << 8) | dg[j]; b = (b << 8) | dg[h + j]; }
+    if (!(a | b)) a = 1;
+    *ka = a; *kb = b;
 }
 typedef struct {
     verify_args v; const uint8_t *seed; int rand_bits; size_t group, n;
@@ -1112,8 +1122,9 @@ static void rbv_item_range(void *p, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; i++) {
         const uint8_t *msg = a->msgs + a->off[i];
         size_t mlen = a->off[i + 1] - a->off[i];
-        uint64_t k[4];
-        rbv_scalar(k, r->seed, (uint64_t)i, r->rand_bits);
+        uint64_t ka, kb;
+        rbv_scalar(&ka, &kb, r->seed, (uint64_t)i, r->rand_bits);
+        const int hb = r->rand_bits / 2;
         r->bad[i] = 1;
         if (a->variant == 0) {
             g2a pk; g1a sig, h; g1p t;
@@ -1121,20 +1132,20 @@ static void rbv_item_range(void *p, size_t lo, size_t hi) {
             if ((a->flags & 3) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) continue;
             if ((a->flags & 2) && (!g2a_torsion_free(&pk) || !g1a_torsion_free(&sig))) continue;
             if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
-            g1_from_affine(&t, &h.x, &h.y, h.inf); g1_mul_limbs(&t, &t, k, r->rand_bits);
+            g1_from_affine(&t, &h.x, &h.y, h.inf); g1_mul_glv(&t, &t, ka, kb, hb);
             g1_to_affine(&r->ps[i].x, &r->ps[i].y, &r->ps[i].inf, &t);
             r->qs[i] = pk;
-            g1_from_affine(&t, &sig.x, &sig.y, sig.inf); g1_mul_limbs(&r->s1[i], &t, k, r->rand_bits);
+            g1_from_affine(&t, &sig.x, &sig.y, sig.inf); g1_mul_glv(&r->s1[i], &t, ka, kb, hb);
         } else {
             g1a pk; g2a sig, h; g1p t; g2p u;
             if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) continue;
             if ((a->flags & 3) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) continue;
             if ((a->flags & 2) && (!g1a_torsion_free(&pk) || !g2a_torsion_free(&sig))) continue;
             if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
-            g1_from_affine(&t, &pk.x, &pk.y, pk.inf); g1_mul_limbs(&t, &t, k, r->rand_bits);
+            g1_from_affine(&t, &pk.x, &pk.y, pk.inf); g1_mul_glv(&t, &t, ka, kb, hb);
             g1_to_affine(&r->ps[i].x, &r->ps[i].y, &r->ps[i].inf, &t);
             r->qs[i] = h;
-            g2_from_affine(&u, &sig.x, &sig.y, sig.inf); g2_mul_limbs(&r->s2[i], &u, k, r->rand_bits);
+            g2_from_affine(&u, &sig.x, &sig.y, sig.inf); g2_mul_glv(&r->s2[i], &u, ka, kb, hb);
         }
         r->bad[i] = 0;
     }

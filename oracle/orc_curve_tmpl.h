@@ -109,3 +109,20 @@ static void PN(mul_limbs)(PT *r, const PT *a, const uint64_t *k, int nbits) {
     }
     *r = acc;
 }
+
+/* r = [a + b lambda]p by one joint MSB-first double-and-add over {p, phi(p), p + phi(p)}, phi(x, y) = (beta x, y);
+ * a, b < 2^nbits (nbits <= 64).  Randomised batch verification only (no counterpart in the reference). */
+static void PN(mul_glv)(PT *r, const PT *p, uint64_t a, uint64_t b, int nbits) {
+    PT tab[3], acc;
+    tab[0] = *p;
+    tab[1] = *p;
+    FN(glv_beta)(&tab[1].x, &p->x);
+    PN(add)(&tab[2], &tab[0], &tab[1]);
+    PN(set_identity)(&acc);
+    for (int i = nbits - 1; i >= 0; i--) {
+        PN(dbl)(&acc, &acc);
+        unsigned sel = (unsigned)((a >> i) & 1) | (unsigned)(((b >> i) & 1) << 1);
+        if (sel) PN(add)(&acc, &acc, &tab[sel - 1]);
+    }
+    *r = acc;
+}

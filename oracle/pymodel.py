@@ -595,3 +595,39 @@ def verify_min_pk(pk_g1, msg, sig_g2, dst):
 def aggregate_verify_min_sig(pks_g2, msgs, aggsig_g1, dst):
     pairs = [(aggsig_g1, g2_neg(G2_GEN))] + [(hash_to_g1(m, dst), pk) for pk, m in zip(pks_g2, msgs)]
     return final_exponentiation(multi_miller_loop(pairs)) == F12_ONE
+
+
+# ---------------------------------------------------------------- GLV endomorphism (randomised batch verification)
+# phi(x, y) = (beta x, y) is an endomorphism of y^2 = x^3 + b over Fp and of the twist over Fp2; on the order-r
+# subgroups it is multiplication by a root lambda of z^2 + z + 1 mod r.  Derived here, not copied: the cube roots
+# of unity are found by exponentiation and matched against a plain scalar multiplication of the generators.
+def _cube_root_of_unity(m):
+    g = 2
+    while pow(g, (m - 1) // 3, m) == 1:
+        g += 1
+    return pow(g, (m - 1) // 3, m)
+
+
+def glv_constants():
+    """(lambda, beta for G1, beta for G2) with (beta1 x, y) = [lambda](x, y) on G1 and (beta2 x, y) = [lambda](x, y) on G2;
+    lambda is the smaller of the two roots."""
+    lam = _cube_root_of_unity(R_ORDER)
+    lam = min(lam, lam * lam % R_ORDER)
+    b = _cube_root_of_unity(P)
+    q1 = g1_mul(G1_GEN, lam)
+    beta1 = next(c for c in (b, b * b % P) if (c * G1_GEN[0] % P, G1_GEN[1]) == (q1[0], q1[1]))
+    q2 = g2_mul(G2_GEN, lam)
+    beta2 = next(c for c in (b, b * b % P) if (tuple(c * t % P for t in G2_GEN[0]), tuple(G2_GEN[1])) == (tuple(q2[0]), tuple(q2[1])))
+    return lam, beta1, beta2
+
+
+def rbv_scalar(seed, index, rand_bits=64):
+    """per-tuple scalar of the randomised batch verification (include/bls_bn254_b200.h): a + b lambda mod r with
+    a, b the first and second rand_bits/2 bits of SHA-256(seed || LE64(index))"""
+    import hashlib
+    dg = hashlib.sha256(bytes(seed) + index.to_bytes(8, "little")).digest()
+    h = rand_bits // 16
+    a, b = int.from_bytes(dg[:h], "big"), int.from_bytes(dg[h:2 * h], "big")
+    if a == 0 and b == 0:
+        a = 1
+    return (a + b * glv_constants()[0]) % R_ORDER

@@ -126,7 +126,11 @@ EXPORT void sim_g2_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t 
     }
 }
 // randomised batch verification: the per-tuple scalar and the two scalings of items.cuh
-EXPORT void sim_rbv_scalar(const uint8_t *seed, uint64_t idx, int nbits, uint32_t *kw) { rbv_scalar(kw, seed, idx, nbits); }
+EXPORT void sim_rbv_scalar(const uint8_t *seed, uint64_t idx, int nbits, uint32_t *kw) {
+    rbv_k kk;
+    rbv_scalar(kk, seed, idx, nbits);
+    kw[0] = kk.a[0]; kw[1] = kk.a[1]; kw[2] = kk.b[0]; kw[3] = kk.b[1];
+}
 EXPORT void sim_rbv_scale(const uint8_t *g1pts, const uint8_t *g2pts, size_t n, const uint8_t *seed, uint64_t idx0, int nbits, uint8_t *out_g1_affine,
                           uint8_t *out_g1_sum, uint8_t *out_g2_sum) {
     g1p s1;
@@ -134,7 +138,7 @@ EXPORT void sim_rbv_scale(const uint8_t *g1pts, const uint8_t *g2pts, size_t n, 
     pt_set_identity(s1);
     pt_set_identity(s2);
     for (size_t i = 0; i < n; i++) {
-        uint32_t kw[4];
+        rbv_k kw;
         rbv_scalar(kw, seed, idx0 + i, nbits);
         g1m p;
         g2m q;

@@ -5,7 +5,8 @@ from oracle import pymodel as pm
 
 
 def _rbv_scalar(seed, i, bits=64):
-    return int.from_bytes(hashlib.sha256(seed + i.to_bytes(8, "little")).digest()[:bits // 8], "big") or 1
+    """r_i = a + b lambda mod r (include/bls_bn254_b200.h), as an integer"""
+    return pm.rbv_scalar(seed, i, bits)
 
 
 def _neg_g1(pt):

@@ -155,17 +155,21 @@ def test_scalar_mul_and_codecs(sim, orc):
 
 
 def test_randomized_batch_scalars_and_scalings(sim, orc):
-    """rbv_scalar = SHA-256(seed || LE64(i)) truncated (hashlib), and the two scalings of a tuple
-    (affine [r]P for the pairing, projective [r]S summed over the group) against the oracle's scalar multiplication"""
+    """rbv_scalar = the two halves of SHA-256(seed || LE64(i)) (hashlib); the two scalings of a tuple (affine [r]P for
+    the pairing, projective [r]S summed over the group), done on the device by the GLV joint double-and-add, against
+    the oracle's PLAIN scalar multiplication by the integer r = a + b lambda mod r"""
     import hashlib
+    from oracle import pymodel as pm
     rng = random.Random(8)
     seed = rng.randbytes(32)
     kw = (C.c_uint32 * 4)()
     for idx in (0, 1, 255, 256, 2**32 + 5, 2**63 + 11):
         dg = hashlib.sha256(seed + idx.to_bytes(8, "little")).digest()
         for bits in (64, 128):
+            h = bits // 16
             sim.sim_rbv_scalar(seed, C.c_uint64(idx), bits, kw)
-            assert sum(int(kw[w]) << (32 * w) for w in range(4)) == int.from_bytes(dg[:bits // 8], "big")
+            assert int(kw[0]) | int(kw[1]) << 32 == int.from_bytes(dg[:h], "big")
+            assert int(kw[2]) | int(kw[3]) << 32 == int.from_bytes(dg[h:2 * h], "big")
     n = 5
     msgs = [rng.randbytes(9) for _ in range(n - 1)]
     ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
@@ -173,7 +177,7 @@ def test_randomized_batch_scalars_and_scalings(sim, orc):
     g1 = orc.hash_to_g1(msgs, QUUX_G1) + ident1
     g2 = orc.hash_to_g2(msgs[:-1], QUUX_G2) + ident2 + orc.g2_generator()
     for bits, idx0 in ((64, 0), (128, 1000)):
-        rs = b"".join((int.from_bytes(hashlib.sha256(seed + (idx0 + i).to_bytes(8, "little")).digest()[:bits // 8], "big") or 1).to_bytes(32, "big") for i in range(n))
+        rs = b"".join(pm.rbv_scalar(seed, idx0 + i, bits).to_bytes(32, "big") for i in range(n))
         o1, s1, s2 = C.create_string_buffer(64 * n), C.create_string_buffer(64), C.create_string_buffer(128)
         sim.sim_rbv_scale(g1, g2, C.c_size_t(n), seed, C.c_uint64(idx0), bits, o1, s1, s2)
         assert o1.raw == orc.g1_mul(g1, rs)
