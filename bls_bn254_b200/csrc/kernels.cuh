@@ -373,6 +373,42 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g2p(g
     item_rbv_scale_proj<F2, g2m>(r, p, fl[i], kw, nbits);
     copy_rec(S[i], r);
 }
+// Two consecutive tuples per thread (resp. lane pair): F[t] = ML(P[2t], Q[2t]) * ML(P[2t+1], Q[2t+1]) as ONE two-pair
+// loop, i.e. one Fp12 squaring per step for both (pairings.rs:808-857) -- the first level of the group product for free.
+// An odd tail item is paired with a dead slot.
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller_twin(fp12 *F, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
+                                                               size_t n, int *bad) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i0 = 2 * t, i1 = 2 * t + 1;
+    if (i0 >= n) return;
+    const bool has1 = i1 < n;
+    if (!has1) i1 = i0;
+    uint8_t fl;
+    fp12 f;
+    g1m p0, p1;
+    g2m q0, q1;
+    copy_rec(p0, P[i0]);
+    copy_rec(p1, P[i1]);
+    copy_rec(q0, Q[i0]);
+    copy_rec(q1, Q[i1]);
+    item_miller2<false>(f, fl, p0, flP[i0], &q0, flQ[i0], p1, has1 ? flP[i1] : (uint8_t)FL_INF, q1, flQ[i1]);
+    copy_rec(F[t], f);
+    if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller_twin_l2(fp12 *F, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
+                                                                               size_t n, int *bad) {
+    size_t th = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t m = (n + 1) / 2;                       // records written
+    if (((th & ~(size_t)31) >> 1) >= m) return;
+    size_t t = th >> 1;
+    if (t >= m) t = m - 1;
+    size_t i0 = 2 * t, i1 = 2 * t + 1;
+    const bool has1 = i1 < n;
+    if (!has1) i1 = i0;
+    uint8_t fl;
+    item_miller2_l2<false>(F[t], fl, P[i0], flP[i0], &Q[i0], flQ[i0], P[i1], has1 ? flP[i1] : (uint8_t)FL_INF, Q[i1], flQ[i1]);
+    if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
+}
 // One level of a segmented reduction.  Segment s holds len(s) records at in + s * stride_in (len_full for every
 // segment but the last, len_last there); thread (s, j) folds records [j * fan, min((j + 1) * fan, len(s))) into
 // out[s * stride_out + j], stride_out = ceil(len_full / fan).
