@@ -84,18 +84,38 @@ BN_INL void ell(fp12_t<T2> &f, const line_t<T2> &l, const fp &px, const fp &py) 
     fp2_mul_fp(c1, l.b, px);
     fp12_mul_by_034(f, c0, c1, l.c);
 }
+// The same with a `live` flag: a dead pair multiplies by the neutral line 1 + 0 w + 0 w^3 (selects, no branch), which
+// keeps the warps of the lane-pair kernels convergent (tower.cuh: lane_mask).
+template <class T2>
+BN_INL void ell_sel(fp12_t<T2> &f, const line_t<T2> &l, const fp &px, const fp &py, bool live) {
+    T2 c0, c1, c2, one, zero;
+    fp2_set_one(one);
+    fp2_sub(zero, one, one);
+    fp2_mul_fp(c0, l.a, py);
+    fp2_mul_fp(c1, l.b, px);
+    fp2_select(c0, live, c0, one);
+    fp2_select(c1, live, c1, zero);
+    fp2_select(c2, live, l.c, zero);
+    fp12_mul_by_034(f, c0, c1, c2);
+}
+// does this Fp2 representation branch around dead pairs (one thread per item) or neutralise them (lane pairs)?
+template <class T2> struct skips_dead { static const bool value = true; };
+#if BN_LANES_CONVERGENT
+template <> struct skips_dead<fp2l> { static const bool value = false; };
+#endif
 // line idx of the fixed point -g2 (precomputed table in constant memory, one-thread fp2 layout).
 // One thread per pairing multiplies straight out of the table; a lane pair first picks its halves.
-BN_INL void ell_fixed(fp12_t<fp2> &f, int idx, const fp &px, const fp &py) {
+BN_INL void ell_fixed(fp12_t<fp2> &f, int idx, const fp &px, const fp &py, bool = true) {
     ell(f, *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]), px, py);
 }
-BN_INL void ell_fixed(fp12_t<fp2l> &f, int idx, const fp &px, const fp &py) {
+BN_INL void ell_fixed(fp12_t<fp2l> &f, int idx, const fp &px, const fp &py, bool live = true) {
     const line_t<fp2> &m = *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]);
     line_t<fp2l> l;
     fp2_load(l.a, m.a);
     fp2_load(l.b, m.b);
     fp2_load(l.c, m.c);
-    ell(f, l, px, py);
+    if (skips_dead<fp2l>::value) ell(f, l, px, py);
+    else ell_sel(f, l, px, py, live);
 }
 
 // Product of NP Miller loops with one shared squaring per step (multi_miller_loop,
@@ -118,30 +138,33 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
     }
     fp12_set_one(f);
     int idx = 0;
+    const bool skip = skips_dead<T2>::value;   // compile-time: branch around dead pairs, or neutralise their lines
 #pragma unroll 1
     for (int s = 0; s < BN254_ATE_NAF_LEN; s++) {
         int d = k::ATE_NAF[s];
         if (s) fp12_sqr(f, f);  // f = 1 on the first step
 #pragma unroll
         for (int i = 0; i < NP; i++) {
-            if (!live[i]) continue;
+            if (skip && !live[i]) continue;
             if (FIXED0 && i == 0) {
-                ell_fixed(f, idx, *px[0], *py[0]);
+                ell_fixed(f, idx, *px[0], *py[0], live[0]);
             } else {
                 doubling_step(l, r[i]);
-                ell(f, l, *px[i], *py[i]);
+                if (skip) ell(f, l, *px[i], *py[i]);
+                else ell_sel(f, l, *px[i], *py[i], live[i]);
             }
         }
         idx++;
         if (d) {
 #pragma unroll
             for (int i = 0; i < NP; i++) {
-                if (!live[i]) continue;
+                if (skip && !live[i]) continue;
                 if (FIXED0 && i == 0) {
-                    ell_fixed(f, idx, *px[0], *py[0]);
+                    ell_fixed(f, idx, *px[0], *py[0], live[0]);
                 } else {
                     addition_step(l, r[i], *qx[i], d > 0 ? *qy[i] : nqy[i]);
-                    ell(f, l, *px[i], *py[i]);
+                    if (skip) ell(f, l, *px[i], *py[i]);
+                    else ell_sel(f, l, *px[i], *py[i], live[i]);
                 }
             }
             idx++;
@@ -150,10 +173,10 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
     // two Frobenius additions: Q1 = psi(Q), Q2 = -psi^2(Q)
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        if (!live[i]) continue;
+        if (skip && !live[i]) continue;
         if (FIXED0 && i == 0) {
-            ell_fixed(f, idx, *px[0], *py[0]);
-            ell_fixed(f, idx + 1, *px[0], *py[0]);
+            ell_fixed(f, idx, *px[0], *py[0], live[0]);
+            ell_fixed(f, idx + 1, *px[0], *py[0], live[0]);
         } else {
             T2 q1x, q1y, q2x, q2y, t, eu, ev;
             fp2_load(eu, kfp2(k::ENDO_U));
@@ -164,9 +187,11 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
             fp2_conj(t, q1y); fp2_mul(q2y, t, ev);
             fp2_neg(q2y, q2y);
             addition_step(l, r[i], q1x, q1y);
-            ell(f, l, *px[i], *py[i]);
+            if (skip) ell(f, l, *px[i], *py[i]);
+            else ell_sel(f, l, *px[i], *py[i], live[i]);
             addition_step(l, r[i], q2x, q2y);
-            ell(f, l, *px[i], *py[i]);
+            if (skip) ell(f, l, *px[i], *py[i]);
+            else ell_sel(f, l, *px[i], *py[i], live[i]);
         }
     }
 }

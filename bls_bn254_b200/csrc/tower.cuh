@@ -315,9 +315,19 @@ BN_INL void fp2_store(fp2 &m, const fp2 &a) { m = a; }
 // ---------------------------------------------------------------------------------- lane-split Fp2
 #if BN_PTX
 BN_INL uint32_t lane_par() { return threadIdx.x & 1u; }
-// Only the two lanes of a pair are named in the shuffle mask: the pair always runs the same control
-// flow, different pairs of a warp may diverge (identity inputs skip their Miller loop).
+// Shuffle mask of the lane-pair kernels.  Default: the whole warp.  Those kernels keep every warp convergent --
+// whole warps exit together (BN_L2_PROLOGUE), exponents and loop schedules are the same for every item, and a pair
+// that contributes nothing (identity / undecodable input) multiplies by a neutral line instead of branching around
+// its Miller loop (pairing.cuh: ell) -- so a full-mask SHFL is legal and compiles to one instruction.  Naming only the
+// two lanes of a pair (-DBN_LANE_PAIR_MASK) makes ptxas wrap most shuffles in BSSY / WARPSYNC / ENDCOLLECTIVE /
+// BSYNC: 5 instructions per exchanged word, 80 of the 186 instructions of the lane-pair Fp2 squaring.
+#ifdef BN_LANE_PAIR_MASK
+#define BN_LANES_CONVERGENT 0
 BN_INL uint32_t lane_mask() { return 3u << (threadIdx.x & 30u); }
+#else
+#define BN_LANES_CONVERGENT 1
+BN_INL uint32_t lane_mask() { return 0xffffffffu; }
+#endif
 BN_INL void lane_xchg(fp &out, const fp &in) {  // out = the partner lane's `in`
     uint32_t m = lane_mask();
 #pragma unroll
@@ -328,6 +338,7 @@ BN_INL bool lane_both(bool x) {
     return x & (o != 0);
 }
 #else
+#define BN_LANES_CONVERGENT 1
 // host emulation hooks, provided by tests/hostsim (two host threads per lane pair)
 extern "C" uint32_t bn_host_lane_par();
 extern "C" void bn_host_lane_xchg(uint32_t *out, const uint32_t *in, int nwords);
@@ -339,10 +350,17 @@ BN_INL bool lane_both(bool x) {
     return x & (b != 0);
 }
 #endif
-BN_INL void fp2_load(fp2l &r, const fp2 &m) { r.v = lane_par() ? m.c1 : m.c0; }
+// Both halves are loaded and one is selected: `lane_par() ? m.c1 : m.c0` compiles to a lane-dependent branch, and with
+// that branch the fixed-line Miller kernel produced wrong results on sm_100a (nvcc 12.9) once the shuffles used the
+// full mask -- also with a __syncwarp() before every exchange, so not a convergence matter (profiles/r01_notes.md).
+BN_INL void fp2_load(fp2l &r, const fp2 &m) {
+    fp a = m.c0, b = m.c1;
+    fp_select(r.v, lane_par() != 0, b, a);
+}
+BN_INL void fp2_select(fp2l &r, bool c, const fp2l &a, const fp2l &b) { fp_select(r.v, c, a.v, b.v); }
 BN_INL void fp2_store(fp2 &m, const fp2l &a) {
-    if (lane_par()) m.c1 = a.v;
-    else m.c0 = a.v;
+    fp *dst = lane_par() ? &m.c1 : &m.c0;   // address select, no branch
+    *dst = a.v;
 }
 BN_INL void fp2_set_zero(fp2l &r) { fp_set_zero(r.v); }
 BN_INL void fp2_set_one(fp2l &r) {
