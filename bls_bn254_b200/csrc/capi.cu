@@ -706,6 +706,17 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
             return rc;
         }
     }
+    if (const char *s = getenv("BN254_CARVEOUT")) {  // experiment knob: preferred shared-memory carveout (percent) of the pairing kernels
+        int v = atoi(s);
+        for (auto &d : ctx->devs) {
+            cudaSetDevice(d.id);
+            cudaFuncSetAttribute(k_miller2_fixed, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+            cudaFuncSetAttribute(k_miller2_fixed_l2, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+            cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+            cudaFuncSetAttribute(k_final_exp_l2, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+            cudaFuncSetAttribute(k_hash_g1, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        }
+    }
     if (const char *s = getenv("BN254_STACK")) {  // bring-up knob: per-thread stack limit in bytes
         long v = atol(s);
         for (auto &d : ctx->devs) {

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller1(fp12 *F
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl;
-    fp12 f;
+    BN_ACC(fp12, f);
     g1m p;
     g2m q;
     copy_rec(p, P[i]);
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2_fixed(f
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl;
-    fp12 f;
+    BN_ACC(fp12, f);
     g1m p0, p1;
     g2m q1;
     copy_rec(p0, P0[i]);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t fl;
-    fp12 f;
+    BN_ACC(fp12, f);
     g1m p0, p1;
     g2m q0, q1;
     copy_rec(p0, P0[i * p0_stride]);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2(fp12 *F
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_FEXP) k_final_exp(fp12 *F, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f;
+    BN_ACC(fp12, f);
     copy_rec(f, F[i]);
     item_final_exp(f);
     copy_rec(F[i], f);
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller_twin(fp1
     const bool has1 = i1 < n;
     if (!has1) i1 = i0;
     uint8_t fl;
-    fp12 f;
+    BN_ACC(fp12, f);
     g1m p0, p1;
     g2m q0, q1;
     copy_rec(p0, P[i0]);
