@@ -6,6 +6,9 @@ verification has exactly one exchange step: each rank reduces its Miller loops t
 product (384 B + 1 flag byte), the partials are all-gathered (NCCL over NVLink / NVSwitch on GPU
 ranks, gloo in the CPU tests), and one final exponentiation decides.
 """
+import hashlib
+import struct
+
 import torch
 import torch.distributed as dist
 
@@ -55,3 +58,20 @@ def verify_sharded(ctx, variant, pks_shard, msgs_shard, sigs_shard, dst, flags=0
     outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
     dist.all_gather(outs, t, group=group)
     return b"".join(bytes(o.cpu().numpy()) for o in outs)
+
+
+def verify_randomized_sharded(ctx, variant, pks_shard, msgs_shard, sigs_shard, dst, seed, group_size=256, rand_bits=64, flags=0,
+                              device=None, group=None):
+    """Randomised batch verification of a sharded job: every rank runs the small-exponent test on ITS shard (groups never
+    span ranks, so there is no data-path collective) with a per-rank seed derived from the common `seed`, then one
+    all-reduce (MIN) of a single byte tells every rank whether the whole job was accepted.
+    Returns (this rank's group verdicts, whole-job verdict 0/1)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rank_seed = hashlib.sha256(bytes(seed) + struct.pack("<I", rank)).digest()
+    local = ctx.verify_batch_randomized(variant, pks_shard, msgs_shard, sigs_shard, dst, rank_seed, group_size, rand_bits, flags)
+    ok = int(all(local))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([ok], dtype=torch.uint8, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        ok = int(t.item())
+    return local, ok

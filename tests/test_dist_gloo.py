@@ -1,5 +1,6 @@
 """world_size-2 gloo test of the N>1 host path (bls_bn254_b200/dist.py): shard ranges, the single
-all-gather of Fp12 partials for aggregate verification, gathered accept bytes.  No GPU here, so the
+all-gather of Fp12 partials for aggregate verification, gathered accept bytes, the all-reduced verdict of the
+randomised batch verification.  No GPU here, so the
 per-rank compute is a stand-in built on the CPU oracle (tests may use it); the plumbing under test
 (sharding, record layout, collective, finish) is the code the GPU ranks run."""
 import os
@@ -45,6 +46,9 @@ class OracleCtx:
     def verify_batch(self, variant, pks, msgs, sigs, dst, flags=0):
         return self.o.verify_batch(variant, pks, msgs, sigs, dst, flags)
 
+    def verify_batch_randomized(self, variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0):
+        return self.o.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=group, rand_bits=rand_bits, flags=flags)
+
 
 def _make(n):
     import hashlib
@@ -86,7 +90,11 @@ def _worker(rank, world, port, q):
         sig2 = bytearray(sigs[:64 * n2])
         sig2[64 * 5:64 * 6] = sigs[64 * 6:64 * 7]
         got = bd.verify_sharded(ctx, 0, pks[128 * lo2:128 * hi2], msgs[lo2:hi2], bytes(sig2[64 * lo2:64 * hi2]), DST, gather=True)
-        q.put((rank, ok, ok_bad, ok_badkey, got))
+        # randomised batch verification: per-rank groups, one all-reduce of the verdict
+        seed = bytes(range(32))
+        rnd_good = bd.verify_randomized_sharded(ctx, 0, p, m, s, DST, seed, group_size=3)
+        rnd_bad = bd.verify_randomized_sharded(ctx, 0, p, bad_msgs, s, DST, seed, group_size=3)
+        q.put((rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad))
     finally:
         dist.destroy_process_group()
 
@@ -105,9 +113,12 @@ def test_world_size_2_gloo():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, ok, ok_bad, ok_badkey, got in res:
+    for rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad in res:
         assert ok == 1 and ok_bad == 0 and ok_badkey == 0
         assert got == b"\x01\x01\x01\x01\x01\x00\x01\x01"
+        # 11 tuples over 2 ranks = 5 + 6: two groups of <= 3 per rank; rank 1's first message was tampered with
+        assert rnd_good == (b"\x01\x01", 1)
+        assert rnd_bad == ((b"\x00\x01", 0) if rank == 1 else (b"\x01\x01", 0))
 
 
 def test_shard_range_covers_everything():

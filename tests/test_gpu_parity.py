@@ -412,6 +412,10 @@ def test_multi_device_ctx(orc, B):
         agg = B.scheme.aggregate(c1, sigs2, 0)
         assert c2.aggregate_verify(0, pks2, msgs2, agg, B.DST_MIN_SIG) == 1
         assert c2.hash_to_g1(msgs, QUUX_G1) == c1.hash_to_g1(msgs, QUUX_G1)
+        # randomised batch verification shares out whole groups
+        seed = b"\x77" * 32
+        want = bytes(int(all(exp[g:g + 32])) for g in range(0, 700, 32))
+        assert c2.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=32) == want == c1.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=32)
     finally:
         c1.close()
         c2.close()
