@@ -29,7 +29,7 @@ M_IMAD = 264
 # two joint double-and-add scalings (32 x 8 + 25 x 12 + 1 = 557 each) + one affine conversion 332 + product tree 58 + per-group
 # pairing / 256 = 68
 WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 12386}
-KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
+KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller_twin": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
             "k_rbv_scale_g1": 889, "k_rbv_scale_g1p": 557}
 UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
         "aggregate": "verifications/s", "verify_rand": "verifications/s"}
@@ -175,8 +175,8 @@ def main():
     ap.add_argument("--workload", default="verify", choices=sorted(WORK_M))
     ap.add_argument("--log2n", type=int, default=16, help="log2 of tuples per GPU per step")
     ap.add_argument("--group", type=int, default=256, help="tuples per accept byte of the verify_rand workload")
-    ap.add_argument("--ref-sample", type=int, default=4096, help="tuples per step of the CPU arm")
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="tuples of the cpu_baseline leg (rank 0, N=1)")
+    ap.add_argument("--ref-sample", type=int, default=16384, help="tuples per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=65536, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -405,15 +405,15 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region) ---------
-    agg_t = {}
-    for name, items, ms in prof:
-        a = agg_t.setdefault(name, [0, 0.0, 0])
+    agg_t, by_name = {}, {}
+    for name, items, ms in prof:          # launches of one kernel at different sizes are different roofline entries
+        a = agg_t.setdefault((name, items), [0, 0.0, items])
         a[0] += 1
         a[1] += ms
-        a[2] = items
+        by_name[name] = by_name.get(name, 0.0) + ms
     kern_ms_total = sum(a[1] for a in agg_t.values())
     top = max(agg_t.items(), key=lambda kv: kv[1][1])
-    top_name, (top_cnt, top_ms, top_items) = top[0], top[1]
+    top_name, (top_cnt, top_ms, top_items) = top[0][0], top[1]
     peak_name = max(peaks, key=peaks.get)
     peak = peaks[peak_name]
     lanes = 2 if top_name.endswith("_l2") else 1          # lane-pair kernels: two threads per item
@@ -437,7 +437,7 @@ def main():
         "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
         "whole_step_frac": whole_ops / (dev_ms * 1e-3) / peak,
         "kernel_pass_ms_per_step": prof_ms / args.steps,
-        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(agg_t.items(), key=lambda kv: -kv[1][1])},
+        "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(by_name.items(), key=lambda kv: -kv[1])},
         "hbm": {"algorithmic_bytes_per_step": in_bytes + out_bytes, "achieved_gbs": (in_bytes + out_bytes) / (dev_ms / args.steps * 1e-3) / 1e9,
                 "peak_gbs": 6553.3, "note": "HBM non-binding"},
     }

@@ -3,7 +3,7 @@
 N=${N:-2}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-for w in verify aggregate; do
+for w in verify verify_rand aggregate; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --workload $w > gpurun_out/bench_${w}_n$N.json 2> gpurun_out/bench_${w}_n$N.err
   echo "$w N=$N rc=$?"; tail -c 400 gpurun_out/bench_${w}_n$N.err
   python - $w $N <<'PY'
@@ -17,3 +17,5 @@ PY
 done
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 1 --warmup 1 | tail -c 300
 timeout 600 python -m pytest tests -m gpu -q -k "multi_device" 2>&1 | tail -3
+# C5: 2^24 tuples through the host-buffer call of ONE process driving all N GPUs (one host thread per device)
+C5_GPUS=$N bash tools/gpu_c5.sh
