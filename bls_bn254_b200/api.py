@@ -271,6 +271,16 @@ class Context:
         self._ck(self._L.bn254_g2_sum(self._h, _ptr(pts), len(pts) // 128, _ptr(out)))
         return out.raw
 
+    # ---- the C ABI itself, for callers that own their buffers ---------------------------------------
+    def raw(self, name, *args):
+        """Call the C entry point `name` (include/bls_bn254_b200.h) on this context with the arguments as given: integers
+        are taken as addresses (e.g. the data_ptr() of a pinned torch tensor or of a numpy array), bytes / ctypes buffers /
+        numpy arrays are passed by pointer.  This is the zero-copy form of every method above: no Python-side staging,
+        results are written where the caller says.  Raises Bn254Error on a non-zero return code."""
+        fn = getattr(self._L, name)
+        conv = [a if isinstance(a, int) or a is None else _ptr(a) if isinstance(a, (bytes, bytearray)) or hasattr(a, "ctypes") else a for a in args]
+        self._ck(fn(self._h, *conv))
+
     # ---- device-resident entry points (raw device addresses, e.g. torch.Tensor.data_ptr()) ---------
     def hash_to_g1_dev(self, msgs, offsets, n, dst, dst_len, count, out, status=None):
         self._ck(self._L.bn254_hash_to_g1_dev(self._h, msgs, offsets, n, dst, dst_len, count, out, status))
