@@ -31,6 +31,9 @@ M_IMAD = 264
 WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 12386}
 KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller_twin": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
             "k_rbv_scale_g1": 889, "k_rbv_scale_g1p": 557}
+# Multiplier work the kernels actually execute where it differs from the canonical count: quadratic-residue tests are binary
+# Jacobi symbols and inversions binary GCDs on the ALU pipe (no IMAD), so hashing needs 3 (G1) / 5 (G2) fewer 309 M exponentiations.
+KERNEL_M_EXECUTED = {"k_hash_g1": 2204 - 3 * 309, "k_hash_g2": 6400 - 5 * 309}
 UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
         "aggregate": "verifications/s", "verify_rand": "verifications/s"}
 METRIC = {"verify": "bls_verifications_per_sec", "verify_pk": "bls_verifications_per_sec", "hash_g1": "hash_to_g1_per_sec",
@@ -449,6 +452,10 @@ def main():
         "peak_source": "measured live by bn254_imad_peak (%s chains, all SMs); MEASURED_PEAKS.json has no INT32 figure" % peak_name,
         "peaks_measured_tops": {k: v / 1e12 for k, v in peaks.items()},
         "field_level_tops": field_peaks,
+        "frac_executed": (KERNEL_M_EXECUTED[top_name] * M_IMAD * top_items / (top_ms / top_cnt * 1e-3) / peak) if top_name in KERNEL_M_EXECUTED and top_ms else None,
+        "frac_note": "frac / whole_step_frac count the CANONICAL multiplier work of SURVEY.md 8(d) (Euler-criterion and Fermat exponentiations "
+                     "included); is_square and inversion run as binary Jacobi / GCD loops on the ALU pipe, so canonical fractions can exceed "
+                     "the share of the IMAD pipe really used (frac_executed where it is known)",
         "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
         "whole_step_frac": whole_ops / (dev_ms * 1e-3) / peak,
         "kernel_pass_ms_per_step": prof_ms / args.steps,

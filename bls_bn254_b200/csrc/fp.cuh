@@ -701,11 +701,183 @@ BN_NOINL void fp_pow_sw(fp &r, const fp &a, const uint8_t *dig, int top) {
     }
     r = acc;
 }
-BN_INL void fp_inv(fp &r, const fp &a) { fp_pow_sw(r, a, k::SW_P_MINUS_2, BN254_SW_P_MINUS_2_TOP); }  // fp.rs:207-210; 0 -> 0
-BN_INL bool fp_is_square(const fp &a) {                                                                // fp.rs:428-431
+BN_INL void fp_inv_fermat(fp &r, const fp &a) { fp_pow_sw(r, a, k::SW_P_MINUS_2, BN254_SW_P_MINUS_2_TOP); }  // 0 -> 0
+// fp.rs:428-431 computes the Euler criterion a^((p-1)/2) in {0, 1}; the same predicate (0 counts as a square) is
+// evaluated here as the Jacobi symbol (a / p) by the binary algorithm -- shifts, one subtraction and one conditional
+// negation per step on 8 limbs, about 1.4 * 254 steps -- which costs a quarter of the 250-squaring exponentiation and
+// none of the multiplier pipe.  The Montgomery factor does not matter: R = 2^256 is a square, so (aR / p) = (a / p).
+// -DBN_EULER_IS_SQUARE restores the exponentiation.
+BN_INL bool fp_is_square_euler(const fp &a) {
     fp t;
     fp_pow_sw(t, a, k::SW_P_MINUS_1_DIV_2, BN254_SW_P_MINUS_1_DIV_2_TOP);
     return fp_is_zero(t) || fp_eq(t, kfp(k::ONE));
+}
+BN_INL uint32_t ctz32(uint32_t x) {  // x != 0
+#if BN_PTX
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+BN_INL uint32_t shr_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [z, z + 32) of hi:lo, 0 < z < 32
+#if BN_PTX
+    return __funnelshift_r(lo, hi, z);
+#else
+    return (lo >> z) | (hi << (32 - z));
+#endif
+}
+BN_NOINL bool fp_is_square_jacobi(const fp &x) {
+    uint32_t a[8], n[8], d[8];
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = x.v[i];
+        n[i] = p_limb(i);
+        any |= a[i];
+    }
+    if (!any) return true;
+    uint32_t neg = 0;  // the symbol so far is (-1)^neg
+#pragma unroll 1
+    for (;;) {
+        // a != 0.  Strip the factors of two: (2 / n) = -1 iff n = 3, 5 mod 8.
+        uint32_t lo = a[0];
+        if (lo == 0) {  // 32 of them at once (an even count: no sign change)
+#pragma unroll
+            for (int i = 0; i < 7; i++) a[i] = a[i + 1];
+            a[7] = 0;
+            continue;
+        }
+        uint32_t z = ctz32(lo);
+        if (z) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
+            a[7] >>= z;
+            uint32_t n8 = n[0] & 7u;
+            neg ^= (z & 1u) & (uint32_t)((n8 == 3u) | (n8 == 5u));
+        }
+        // a odd.  d = a - n; when a < n the roles swap (reciprocity: sign flips iff both are 3 mod 4) and a - n becomes n - a.
+        uint32_t lt = sub_n(d, a, n);
+        neg ^= ((a[0] & n[0]) >> 1) & lt & 1u;
+        uint32_t carry = lt & 1u, zero = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            n[i] = lt ? a[i] : n[i];
+            uint32_t t = d[i] ^ lt;  // two's complement negation of d when lt
+            uint32_t s = t + carry;
+            carry = (uint32_t)(s < t);
+            a[i] = s;
+            zero |= s;
+        }
+        if (!zero) break;  // a == n: the gcd, which is 1 for a prime modulus
+    }
+    return neg == 0;
+}
+BN_INL uint32_t shl_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [32 - z, 64 - z) of hi:lo, 0 < z < 32
+#if BN_PTX
+    return __funnelshift_l(lo, hi, z);
+#else
+    return (hi << z) | (lo >> (32 - z));
+#endif
+}
+// fp.rs:207-210 (the crate calls crypto-bigint's inv_odd_mod): a^-1, 0 -> 0.  Same value as a^(p-2), computed by a
+// binary extended GCD in the "almost inverse" form (Kaliski): the loop keeps
+//     x A = sigma a 2^k,   x N = -sigma n 2^k   (mod p),    a N + n A = p
+// strips the trailing zeros of a (N doubles instead of A halving, so there is no modular halving and several bits
+// go at once), then subtracts the smaller of the two odd values from the larger.  About 0.7 * 254 subtraction steps
+// of ~70 ALU instructions and no multiplier work; the factor 2^k (and the Montgomery factor) is removed at the end by
+// two products.  -DBN_FERMAT_INVERSION restores the exponentiation.
+BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
+    uint32_t a[8], n[8], A[8], N[8], d[8];
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = x.v[i];
+        n[i] = p_limb(i);
+        A[i] = 0;
+        N[i] = 0;
+        any |= a[i];
+    }
+    if (!any) {
+        fp_set_zero(r);
+        return;
+    }
+    A[0] = 1;
+    uint32_t sigma_neg = 0, kk = 0;  // sigma = (-1)^sigma_neg
+#pragma unroll 1
+    for (;;) {
+        uint32_t lo = a[0];
+        if (lo == 0) {  // 32 trailing zeros at once
+#pragma unroll
+            for (int i = 0; i < 7; i++) a[i] = a[i + 1];
+            a[7] = 0;
+#pragma unroll
+            for (int i = 7; i > 0; i--) N[i] = N[i - 1];
+            N[0] = 0;
+            kk += 32;
+            continue;
+        }
+        uint32_t z = ctz32(lo);
+        if (z) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
+            a[7] >>= z;
+#pragma unroll
+            for (int i = 7; i > 0; i--) N[i] = shl_pair(N[i - 1], N[i], z);
+            N[0] <<= z;
+            kk += z;
+        }
+        // a, n odd.  d = a - n; a < n swaps the roles: (a, A) <- (n - a, A + N), (n, N) <- (a, A), sigma <- -sigma
+        uint32_t lt = sub_n(d, a, n);
+        uint32_t S[8];
+        (void)add_n(S, A, N);
+        sigma_neg ^= lt & 1u;
+        uint32_t carry = lt & 1u, zero = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            n[i] = lt ? a[i] : n[i];
+            N[i] = lt ? A[i] : N[i];
+            A[i] = S[i];
+            uint32_t t = d[i] ^ lt;
+            uint32_t s2 = t + carry;
+            carry = (uint32_t)(s2 < t);
+            a[i] = s2;
+            zero |= s2;
+        }
+        if (!zero) break;  // a == n == gcd = 1:  x N = -sigma 2^k
+    }
+    // y = x^-1 2^k = -sigma N mod p  (N <= p)
+    fp y, t;
+    uint32_t ge = ~sub_p(y.v, N);  // N - p when N >= p (only N == p is possible; kept general)
+#pragma unroll
+    for (int i = 0; i < 8; i++) y.v[i] = ge ? y.v[i] : N[i];
+    if (!sigma_neg) fp_neg(y, y);
+    // x = a_true R: y = a_true^-1 R^-1 2^k.  t = y R = a_true^-1 2^k; the result a_true^-1 R = t 2^(256 - k).
+    fp_mul(t, kfp(k::R2), y);
+    if (kk > 256) {
+        uint32_t j = 512 - kk;  // 4 <= j <= 255: t * 2^j / R
+        fp pw;
+        fp_set_zero(pw);
+        pw.v[j >> 5] = 1u << (j & 31);
+        fp_mul(r, t, pw);  // 2^j may exceed p: the row-scanned operand may be unreduced
+    } else {
+#pragma unroll 1
+        for (uint32_t e = kk; e < 256; e++) fp_dbl(t, t);
+        r = t;
+    }
+}
+BN_INL void fp_inv(fp &r, const fp &a) {
+#ifdef BN_FERMAT_INVERSION
+    fp_inv_fermat(r, a);
+#else
+    fp_inv_bingcd(r, a);
+#endif
+}
+BN_INL bool fp_is_square(const fp &a) {
+#ifdef BN_EULER_IS_SQUARE
+    return fp_is_square_euler(a);
+#else
+    return fp_is_square_jacobi(a);
+#endif
 }
 // candidate root a^((p+1)/4) (fp.rs:212-243 with v = 1); returns whether it squares to a
 BN_INL bool fp_sqrt(fp &r, const fp &a) {

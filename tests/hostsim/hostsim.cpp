@@ -125,6 +125,28 @@ EXPORT void sim_g2_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t 
         item_g2_encode(out + 128 * i, r, flo);
     }
 }
+// quadratic-residue test: binary Jacobi symbol vs the Euler exponentiation it replaces (raw limbs, < p)
+EXPORT void sim_fp_is_square(const uint32_t *a, size_t n, uint8_t *jacobi, uint8_t *euler) {
+    for (size_t i = 0; i < n; i++) {
+        fp x;
+        for (int j = 0; j < 8; j++) x.v[j] = a[8 * i + j];
+        jacobi[i] = fp_is_square_jacobi(x) ? 1 : 0;
+        euler[i] = fp_is_square_euler(x) ? 1 : 0;
+    }
+}
+// modular inversion: binary extended GCD vs the Fermat exponentiation it replaces (raw Montgomery limbs, < p)
+EXPORT void sim_fp_inv(const uint32_t *a, size_t n, uint32_t *bingcd, uint32_t *fermat) {
+    for (size_t i = 0; i < n; i++) {
+        fp x, y, z;
+        for (int j = 0; j < 8; j++) x.v[j] = a[8 * i + j];
+        fp_inv_bingcd(y, x);
+        fp_inv_fermat(z, x);
+        for (int j = 0; j < 8; j++) {
+            bingcd[8 * i + j] = y.v[j];
+            fermat[8 * i + j] = z.v[j];
+        }
+    }
+}
 // randomised batch verification: the per-tuple scalar and the two scalings of items.cuh
 EXPORT void sim_rbv_scalar(const uint8_t *seed, uint64_t idx, int nbits, uint32_t *kw) {
     rbv_k kk;

@@ -154,6 +154,47 @@ def test_scalar_mul_and_codecs(sim, orc):
     assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
 
 
+def test_is_square_jacobi(sim):
+    """fp_is_square as a binary Jacobi symbol == the Euler criterion it replaces == Python's pow, on edge values
+    (0, 1, 2, p-1, powers of two, values with long runs of zero bits) and 4000 random residues"""
+    rng = random.Random(12)
+    vals = [0, 1, 2, 3, 4, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 32, 1 << 64, (1 << 64) + 1, 1 << 253, (1 << 253) + (1 << 32),
+            (1 << 200) - (1 << 100), 3 << 96, 0xffffffff, 0x100000000 * 5]
+    vals += [rng.randrange(P) for _ in range(4000)]
+    vals += [rng.randrange(1 << rng.randrange(1, 254)) for _ in range(500)]
+    vals += [(rng.randrange(1 << 60) << rng.randrange(1, 190)) % P for _ in range(500)]
+    n = len(vals)
+    buf = (C.c_uint32 * (8 * n))(*[(v >> (32 * j)) & 0xffffffff for v in vals for j in range(8)])
+    jac, eul = C.create_string_buffer(n), C.create_string_buffer(n)
+    sim.sim_fp_is_square(buf, C.c_size_t(n), jac, eul)
+    want = bytes(1 if v == 0 or pow(v, (P - 1) // 2, P) == 1 else 0 for v in vals)
+    assert jac.raw == want
+    assert eul.raw == want
+    assert 0.4 < sum(want) / n < 0.6
+
+
+def test_inversion_binary_gcd(sim):
+    """fp_inv as a binary extended GCD == the Fermat exponentiation it replaces == Python's pow(x, -1, p), on edge values
+    (0 -> 0, 1, p-1, powers of two, tiny and huge values: the shift count k covers both post-processing branches)"""
+    rng = random.Random(13)
+    R = 1 << 256
+    vals = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 32, 1 << 64, 1 << 253, (1 << 253) + 1, 3 << 96, 0xffffffff, R % P, R * R % P]
+    vals += [rng.randrange(1, P) for _ in range(3000)]
+    vals += [rng.randrange(1, 1 << rng.randrange(1, 254)) for _ in range(500)]
+    vals += [(rng.randrange(1, 1 << 60) << rng.randrange(1, 190)) % P for _ in range(300)]
+    vals += [P - rng.randrange(1, 1 << rng.randrange(1, 200)) for _ in range(300)]
+    n = len(vals)
+    buf = (C.c_uint32 * (8 * n))(*[(v >> (32 * j)) & 0xffffffff for v in vals for j in range(8)])
+    o1, o2 = (C.c_uint32 * (8 * n))(), (C.c_uint32 * (8 * n))()
+    sim.sim_fp_inv(buf, C.c_size_t(n), o1, o2)
+    for i, v in enumerate(vals):
+        got1 = sum(int(o1[8 * i + j]) << (32 * j) for j in range(8))
+        got2 = sum(int(o2[8 * i + j]) << (32 * j) for j in range(8))
+        want = pow(v, -1, P) * R * R % P if v else 0      # Montgomery form in, Montgomery form out
+        assert got1 == want, hex(v)
+        assert got2 == want, hex(v)
+
+
 def test_randomized_batch_scalars_and_scalings(sim, orc):
     """rbv_scalar = the two halves of SHA-256(seed || LE64(i)) (hashlib); the two scalings of a tuple (affine [r]P for
     the pairing, projective [r]S summed over the group), done on the device by the GLV joint double-and-add, against
