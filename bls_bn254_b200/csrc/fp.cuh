@@ -737,8 +737,10 @@ BN_NOINL bool fp_is_square_jacobi(const fp &x) {
     }
     if (!any) return true;
     uint32_t neg = 0;  // the symbol so far is (-1)^neg
+    // every pass removes at least one bit of a + n (at most 2 * 256 passes, plus whole-word shifts); the cap only
+    // guarantees termination should a caller ever hand in a value that is not a residue below p
 #pragma unroll 1
-    for (;;) {
+    for (int pass = 0; pass < 2048; pass++) {
         // a != 0.  Strip the factors of two: (2 / n) = -1 iff n = 3, 5 mod 8.
         uint32_t lo = a[0];
         if (lo == 0) {  // 32 of them at once (an even count: no sign change)
@@ -803,8 +805,10 @@ BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
     }
     A[0] = 1;
     uint32_t sigma_neg = 0, kk = 0;  // sigma = (-1)^sigma_neg
+    // every pass removes at least one bit of a + n (at most 2 * 256 passes, plus whole-word shifts); the cap only
+    // guarantees termination should a caller ever hand in a value that is not a residue below p
 #pragma unroll 1
-    for (;;) {
+    for (int pass = 0; pass < 2048; pass++) {
         uint32_t lo = a[0];
         if (lo == 0) {  // 32 trailing zeros at once
 #pragma unroll
