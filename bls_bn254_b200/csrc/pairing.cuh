@@ -24,19 +24,19 @@ BN_NOINL void doubling_step(line_t<T2> &l, g2j<T2> &r) {
     fp2_sqr(tmp0, r.x);
     fp2_sqr(tmp1, r.y);
     fp2_sqr(tmp2, tmp1);
-    fp2_add(tmp3, tmp1, r.x); fp2_sqr(tmp3, tmp3); fp2_sub(tmp3, tmp3, tmp0); fp2_sub(tmp3, tmp3, tmp2);
+    fp2_add(tmp3, tmp1, r.x); fp2_sqr(tmp3, tmp3); fp2_sub2(tmp3, tmp3, tmp0, tmp2);
     fp2_dbl(tmp3, tmp3);
     fp2_dbl(tmp4, tmp0); fp2_add(tmp4, tmp4, tmp0);
     fp2_add(tmp6, r.x, tmp4);
     fp2_sqr(tmp5, tmp4);
     fp2_sqr(zsq, r.z);
-    fp2_sub(r.x, tmp5, tmp3); fp2_sub(r.x, r.x, tmp3);
-    fp2_add(t, r.z, r.y); fp2_sqr(t, t); fp2_sub(t, t, tmp1); fp2_sub(r.z, t, zsq);
+    fp2_sub2(r.x, tmp5, tmp3, tmp3);
+    fp2_add(t, r.z, r.y); fp2_sqr(t, t); fp2_sub2(r.z, t, tmp1, zsq);
     fp2_sub(t, tmp3, r.x); fp2_mul(r.y, t, tmp4);
     fp2_dbl(tmp2, tmp2); fp2_dbl(tmp2, tmp2); fp2_dbl(tmp2, tmp2);
     fp2_sub(r.y, r.y, tmp2);
     fp2_mul(tmp3, tmp4, zsq); fp2_dbl(tmp3, tmp3); fp2_neg(tmp3, tmp3);
-    fp2_sqr(tmp6, tmp6); fp2_sub(tmp6, tmp6, tmp0); fp2_sub(tmp6, tmp6, tmp5);
+    fp2_sqr(tmp6, tmp6); fp2_sub2(tmp6, tmp6, tmp0, tmp5);
     fp2_dbl(tmp1, tmp1); fp2_dbl(tmp1, tmp1);
     fp2_sub(tmp6, tmp6, tmp1);
     fp2_mul(tmp0, r.z, zsq); fp2_dbl(tmp0, tmp0);
@@ -51,16 +51,16 @@ BN_NOINL void addition_step(line_t<T2> &l, g2j<T2> &r, const T2 &qx, const T2 &q
     fp2_sqr(zsq, r.z);
     fp2_sqr(ysq, qy);
     fp2_mul(t0, zsq, qx);
-    fp2_add(t1, qy, r.z); fp2_sqr(t1, t1); fp2_sub(t1, t1, ysq); fp2_sub(t1, t1, zsq); fp2_mul(t1, t1, zsq);
+    fp2_add(t1, qy, r.z); fp2_sqr(t1, t1); fp2_sub2(t1, t1, ysq, zsq); fp2_mul(t1, t1, zsq);
     fp2_sub(t2, t0, r.x);
     fp2_sqr(t3, t2);
     fp2_dbl(t4, t3); fp2_dbl(t4, t4);
     fp2_mul(t5, t4, t2);
-    fp2_sub(t6, t1, r.y); fp2_sub(t6, t6, r.y);
+    fp2_sub2(t6, t1, r.y, r.y);
     fp2_mul(t9, t6, qx);
     fp2_mul(t7, t4, r.x);
-    fp2_sqr(r.x, t6); fp2_sub(r.x, r.x, t5); fp2_sub(r.x, r.x, t7); fp2_sub(r.x, r.x, t7);
-    fp2_add(r.z, r.z, t2); fp2_sqr(r.z, r.z); fp2_sub(r.z, r.z, zsq); fp2_sub(r.z, r.z, t3);
+    fp2_sqr(r.x, t6); fp2_sub2(r.x, r.x, t5, t7); fp2_sub(r.x, r.x, t7);
+    fp2_add(r.z, r.z, t2); fp2_sqr(r.z, r.z); fp2_sub2(r.z, r.z, zsq, t3);
     fp2_add(t10, qy, r.z);
     fp2_sub(t8, t7, r.x); fp2_mul(t8, t8, t6);
     fp2_mul(t0, r.y, t5); fp2_dbl(t0, t0);

@@ -98,6 +98,20 @@ BN_L_CONJ void fp2_conj(fp2 &r, const fp2 &a) {  // fp2.rs:428-437
     r = z;
 }
 BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
+// Fused light operations (-DBN_NO_FUSED_LIGHT falls back to the two- and three-call forms): the call, the 128-bit
+// operand loads and the result store are what these tiny functions cost, so a - b - c and 2(t -+ z) + t as ONE call
+// each halve that overhead where the tower strings additions together (Karatsuba glue, Granger-Scott squaring).
+#ifndef BN_NO_FUSED_LIGHT
+BN_LIGHT void fp2_sub2(fp2 &r, const fp2 &a, const fp2 &b, const fp2 &c) {  // a - b - c
+    fp2 x = a, y = b, w = c, z;
+    fp_sub(z.c0, x.c0, y.c0); fp_sub(z.c0, z.c0, w.c0);
+    fp_sub(z.c1, x.c1, y.c1); fp_sub(z.c1, z.c1, w.c1);
+    r = z;
+}
+// one thread per element: the three-call forms stay (a fused 16-limb version made the final exponentiation 10 % slower)
+BN_INL void fp2_tsub(fp2 &z, const fp2 &t) { fp2_sub(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }  // z <- 3t - 2z
+BN_INL void fp2_tadd(fp2 &z, const fp2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }  // z <- 3t + 2z
+#endif
 
 // fp2.rs:377-390 (there: 4 products).  Karatsuba with lazy reduction: three 512-bit products, the
 // cross terms combined as integers, two Montgomery reductions.
@@ -186,6 +200,13 @@ BN_L_XI void fp2_mul_xi(fp2 &r, const fp2 &a) {
     fp_add(z.c1, t1, x.c0);
     r = z;
 }
+#ifndef BN_NO_FUSED_LIGHT
+BN_INL void fp2_xi_add(fp2 &r, const fp2 &a, const fp2 &b) {  // xi a + b
+    fp2 t;
+    fp2_mul_xi(t, a);
+    fp2_add(r, t, b);
+}
+#endif
 // ---- fused forms: the Karatsuba glue of the Fp6 routines in ONE call each, intermediates in
 // registers (the tiny add/sub functions they replace spent their time loading and storing operands:
 // profiles/r01_notes.md).
@@ -430,6 +451,10 @@ BN_INL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_mul_v(a.v,
 BN_INL void fp2_sqr(fp2l &r, const fp2l &a) { r.v = l2_sqr_v(a.v); }
 BN_INL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) { fp_mul(r.v, a.v, s); }
 BN_INL void fp2_mul_xi(fp2l &r, const fp2l &a) { r.v = l2_xi_v(a.v); }
+BN_INL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_add_v(l2_xi_v(a.v), b.v); }
+BN_INL void fp2_sub2(fp2l &r, const fp2l &a, const fp2l &b, const fp2l &c) { r.v = l2_sub_v(l2_sub_v(a.v, b.v), c.v); }
+BN_INL void fp2_tsub(fp2l &z, const fp2l &t) { fp x = l2_sub_v(t.v, z.v); z.v = l2_add_v(l2_add_v(x, x), t.v); }
+BN_INL void fp2_tadd(fp2l &z, const fp2l &t) { fp x = l2_add_v(t.v, z.v); z.v = l2_add_v(l2_add_v(x, x), t.v); }
 #else
 BN_NOINL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) {
     fp x = a.v, y = b.v, z;
@@ -441,6 +466,28 @@ BN_NOINL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) {
     fp_sub(z, x, y);
     r.v = z;
 }
+#ifndef BN_NO_FUSED_LIGHT
+BN_NOINL void fp2_sub2(fp2l &r, const fp2l &a, const fp2l &b, const fp2l &c) {
+    fp x = a.v, y = b.v, w = c.v, z;
+    fp_sub(z, x, y);
+    fp_sub(z, z, w);
+    r.v = z;
+}
+BN_NOINL void fp2_tsub(fp2l &z, const fp2l &t) {
+    fp x = t.v, y = z.v, o;
+    fp_sub(o, x, y);
+    fp_dbl(o, o);
+    fp_add(o, o, x);
+    z.v = o;
+}
+BN_NOINL void fp2_tadd(fp2l &z, const fp2l &t) {
+    fp x = t.v, y = z.v, o;
+    fp_add(o, x, y);
+    fp_dbl(o, o);
+    fp_add(o, o, x);
+    z.v = o;
+}
+#endif
 BN_NOINL void fp2_neg(fp2l &r, const fp2l &a) {
     fp x = a.v, z;
     fp_neg(z, x);
@@ -491,6 +538,18 @@ BN_NOINL void fp2_mul_xi(fp2l &r, const fp2l &a) {
     fp_add(o, t, u);
     r.v = o;
 }
+#ifndef BN_NO_FUSED_LIGHT
+BN_NOINL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) {  // xi a + b in one call
+    fp x0 = a.v, y = b.v, pa, n, t, u, o;
+    lane_xchg(pa, x0);
+    fp_neg(n, pa);
+    fp_mul9(t, x0);
+    fp_select(u, lane_par() != 0, pa, n);
+    fp_add(o, t, u);
+    fp_add(o, o, y);
+    r.v = o;
+}
+#endif
 #endif
 // fp2.rs:161-166 on a lane pair (both lanes run the same Fp inversion on the shared norm)
 BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
@@ -504,6 +563,12 @@ BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
     fp_mul(r.v, a.v, n);
 }
 
+#ifdef BN_NO_FUSED_LIGHT
+template <class T2> BN_INL void fp2_sub2(T2 &r, const T2 &a, const T2 &b, const T2 &c) { fp2_sub(r, a, b); fp2_sub(r, r, c); }
+template <class T2> BN_INL void fp2_xi_add(T2 &r, const T2 &a, const T2 &b) { T2 t; fp2_mul_xi(t, a); fp2_add(r, t, b); }
+template <class T2> BN_INL void fp2_tsub(T2 &z, const T2 &t) { fp2_sub(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }
+template <class T2> BN_INL void fp2_tadd(T2 &z, const T2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }
+#endif
 // generic (unfused) forms of the fused primitives: used by the lane-split type, and by fp2 under BN_NO_FUSED
 template <class T2>
 BN_INL void fp2_mul_sums_g(T2 &r, const T2 &a0, const T2 &a1, const T2 &b0, const T2 &b1) {
@@ -591,11 +656,11 @@ BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
     fp2_mul(v1, a.c1, b.c1);
     fp2_mul(v2, a.c2, b.c2);
     fp2_add(t0, a.c1, a.c2); fp2_add(t1, b.c1, b.c2); fp2_mul(t0, t0, t1);
-    fp2_sub(t0, t0, v1); fp2_sub(t0, t0, v2); fp2_mul_xi(t0, t0); fp2_add(r.c0, t0, v0);
+    fp2_sub2(t0, t0, v1, v2); fp2_xi_add(r.c0, t0, v0);
     fp2_add(t0, a.c0, a.c1); fp2_add(t1, b.c0, b.c1); fp2_mul(t0, t0, t1);
-    fp2_sub(t0, t0, v0); fp2_sub(t0, t0, v1); fp2_mul_xi(t1, v2); fp2_add(r.c1, t0, t1);
+    fp2_sub2(t0, t0, v0, v1); fp2_xi_add(r.c1, v2, t0);
     fp2_add(t0, a.c0, a.c2); fp2_add(t1, b.c0, b.c2); fp2_mul(t0, t0, t1);
-    fp2_sub(t0, t0, v0); fp2_sub(t0, t0, v2); fp2_add(r.c2, t0, v1);
+    fp2_sub2(t0, t0, v0, v2); fp2_add(r.c2, t0, v1);
 }
 // a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01).  r must not alias a.
 template <class T2>
@@ -603,8 +668,8 @@ BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, cons
     T2 v0, v1, t0, t1;
     fp2_mul(v0, a.c0, b0);
     fp2_mul(v1, a.c1, b1);
-    fp2_add(t0, a.c1, a.c2); fp2_mul(t0, t0, b1); fp2_sub(t0, t0, v1); fp2_mul_xi(t0, t0); fp2_add(r.c0, t0, v0);
-    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t0, t0, t1); fp2_sub(t0, t0, v0); fp2_sub(r.c1, t0, v1);
+    fp2_add(t0, a.c1, a.c2); fp2_mul(t0, t0, b1); fp2_sub(t0, t0, v1); fp2_xi_add(r.c0, t0, v0);
+    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t0, t0, t1); fp2_sub2(r.c1, t0, v0, v1);
     fp2_add(t0, a.c0, a.c2); fp2_mul(t0, t0, b0); fp2_sub(t0, t0, v0); fp2_add(r.c2, t0, v1);
 }
 #endif
@@ -613,11 +678,9 @@ BN_INL void fp6_mul_fp2(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b) { fp2_mul
 // r = a + v b,  r = a - v b  (v (b0, b1, b2) = (xi b2, b0, b1)); r must not alias b
 template <class T2>
 BN_INL void fp6_add_mulv(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
-    T2 t;
-    fp2_mul_xi(t, b.c2);
     fp2_add(r.c2, a.c2, b.c1);
     fp2_add(r.c1, a.c1, b.c0);
-    fp2_add(r.c0, a.c0, t);
+    fp2_xi_add(r.c0, b.c2, a.c0);
 }
 template <class T2>
 BN_INL void fp6_sub_mulv(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
@@ -751,12 +814,10 @@ BN_INL void fp4_square(T2 &c0, T2 &c1, const T2 &a, const T2 &b) {
     T2 t0, t1, t2;
     fp2_sqr(t0, a);
     fp2_sqr(t1, b);
-    fp2_mul_xi(t2, t1);
-    fp2_add(c0, t2, t0);
+    fp2_xi_add(c0, t1, t0);
     fp2_add(t2, a, b);
     fp2_sqr(t2, t2);
-    fp2_sub(t2, t2, t0);
-    fp2_sub(c1, t2, t1);
+    fp2_sub2(c1, t2, t0, t1);
 }
 // Granger-Scott squaring in the cyclotomic subgroup (pairings.rs:68-115), in place: the six
 // coefficients are updated where they live (four Fp2 temporaries instead of ten).
@@ -767,15 +828,15 @@ BN_NOINL void cyclotomic_square(fp12_t<T2> &r, const fp12_t<T2> &f) {
     T2 &z0 = r.c0.c0, &z4 = r.c0.c1, &z3 = r.c0.c2, &z2 = r.c1.c0, &z1 = r.c1.c1, &z5 = r.c1.c2;
     T2 t0, t1, t2, t3;
     fp4_square(t0, t1, z0, z1);
-    fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
-    fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
+    fp2_tsub(z0, t0);   // 3 t0 - 2 z0
+    fp2_tadd(z1, t1);   // 3 t1 + 2 z1
     fp4_square(t0, t1, z2, z3);
     fp4_square(t2, t3, z4, z5);
-    fp2_sub(z4, t0, z4); fp2_dbl(z4, z4); fp2_add(z4, z4, t0);
-    fp2_add(z5, t1, z5); fp2_dbl(z5, z5); fp2_add(z5, z5, t1);
+    fp2_tsub(z4, t0);
+    fp2_tadd(z5, t1);
     fp2_mul_xi(t0, t3);
-    fp2_add(z2, t0, z2); fp2_dbl(z2, z2); fp2_add(z2, z2, t0);
-    fp2_sub(z3, t2, z3); fp2_dbl(z3, z3); fp2_add(z3, z3, t2);
+    fp2_tadd(z2, t0);
+    fp2_tsub(z3, t2);
 }
 
 // one-thread record (HBM) <-> this thread's representation
