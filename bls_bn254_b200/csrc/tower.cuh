@@ -596,8 +596,38 @@ BN_INL void fp2_comb_g(T2 &r, const T2 &t, const T2 &s1, const T2 *s2, const T2 
     }
     r = x;
 }
+#if defined(BN_L2_MUL_SUMS) && !defined(BN_L2_BYVALUE)
+// lane pairs: the Karatsuba cross products (a0 + a1)(b0 + b1) and (a0 + a1) b as ONE out-of-line call each (the two
+// additions would otherwise be two more calls with their own operand loads and result stores)
+BN_NOINL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) {
+    fp x0 = a0.v, x1 = a1.v, y0 = b0.v, y1 = b1.v, x, y, pa, pb, npb, u, w, o;
+    bool odd = lane_par() != 0;
+    fp_add(x, x0, x1);
+    fp_add(y, y0, y1);
+    lane_xchg(pa, x);
+    lane_xchg(pb, y);
+    fp_neg(npb, pb);
+    fp_select(u, odd, pb, y);
+    fp_select(w, odd, y, npb);
+    fp_dot2_inl(o, x, u, pa, w);
+    r.v = o;
+}
+BN_NOINL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) {
+    fp x0 = a0.v, x1 = a1.v, y = b.v, x, pa, pb, npb, u, w, o;
+    bool odd = lane_par() != 0;
+    fp_add(x, x0, x1);
+    lane_xchg(pa, x);
+    lane_xchg(pb, y);
+    fp_neg(npb, pb);
+    fp_select(u, odd, pb, y);
+    fp_select(w, odd, y, npb);
+    fp_dot2_inl(o, x, u, pa, w);
+    r.v = o;
+}
+#else
 BN_INL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
 BN_INL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) { fp2_mul_sum1_g(r, a0, a1, b); }
+#endif
 BN_INL void fp2_comb(fp2l &r, const fp2l &t, const fp2l &s1, const fp2l *s2, const fp2l *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
 #ifndef BN_FUSED
 BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
@@ -651,26 +681,26 @@ BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, cons
 // as they are produced, no staging copies: code size is what bounds these kernels).
 template <class T2>
 BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
-    T2 v0, v1, v2, t0, t1;
+    T2 v0, v1, v2, t0;
     fp2_mul(v0, a.c0, b.c0);
     fp2_mul(v1, a.c1, b.c1);
     fp2_mul(v2, a.c2, b.c2);
-    fp2_add(t0, a.c1, a.c2); fp2_add(t1, b.c1, b.c2); fp2_mul(t0, t0, t1);
+    fp2_mul_sums(t0, a.c1, a.c2, b.c1, b.c2);
     fp2_sub2(t0, t0, v1, v2); fp2_xi_add(r.c0, t0, v0);
-    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b.c0, b.c1); fp2_mul(t0, t0, t1);
+    fp2_mul_sums(t0, a.c0, a.c1, b.c0, b.c1);
     fp2_sub2(t0, t0, v0, v1); fp2_xi_add(r.c1, v2, t0);
-    fp2_add(t0, a.c0, a.c2); fp2_add(t1, b.c0, b.c2); fp2_mul(t0, t0, t1);
+    fp2_mul_sums(t0, a.c0, a.c2, b.c0, b.c2);
     fp2_sub2(t0, t0, v0, v2); fp2_add(r.c2, t0, v1);
 }
 // a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01).  r must not alias a.
 template <class T2>
 BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, const T2 &b1) {
-    T2 v0, v1, t0, t1;
+    T2 v0, v1, t0;
     fp2_mul(v0, a.c0, b0);
     fp2_mul(v1, a.c1, b1);
-    fp2_add(t0, a.c1, a.c2); fp2_mul(t0, t0, b1); fp2_sub(t0, t0, v1); fp2_xi_add(r.c0, t0, v0);
-    fp2_add(t0, a.c0, a.c1); fp2_add(t1, b0, b1); fp2_mul(t0, t0, t1); fp2_sub2(r.c1, t0, v0, v1);
-    fp2_add(t0, a.c0, a.c2); fp2_mul(t0, t0, b0); fp2_sub(t0, t0, v0); fp2_add(r.c2, t0, v1);
+    fp2_mul_sum1(t0, a.c1, a.c2, b1); fp2_sub(t0, t0, v1); fp2_xi_add(r.c0, t0, v0);
+    fp2_mul_sums(t0, a.c0, a.c1, b0, b1); fp2_sub2(r.c1, t0, v0, v1);
+    fp2_mul_sum1(t0, a.c0, a.c2, b0); fp2_sub(t0, t0, v0); fp2_add(r.c2, t0, v1);
 }
 #endif
 template <class T2>
