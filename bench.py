@@ -164,7 +164,8 @@ def workload_config(w, args):
                        + str(args.group) + " tuples (64-bit scalars, one final exponentiation per group)",
     }
     return {"workload": names[w] % args.log2n, "tuples_per_gpu": 1 << args.log2n, "variant": "min-pk" if w == "verify_pk" else "min-sig",
-            "msg_bytes": 32, "corrupted_fraction": "1/64" if w in ("verify", "verify_pk") else "0",
+            "msg_bytes": 32, "input_validation": "on-curve + subgroup checks inside the timed region" if getattr(args, "check_subgroup", False) else "none (trusted inputs)",
+            "corrupted_fraction": "1/64" if w in ("verify", "verify_pk") else "0",
             "l2": "L2 flushed between timed steps (256 MiB write)", "sharding": "independent tuples by index, no data-path collective"
             if w != "aggregate" else "pairs by index; one 385-byte all-gather of Fp12 partials"}
 
@@ -181,6 +182,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=16384, help="tuples per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=65536, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check-subgroup", action="store_true", help="verify workloads: also validate inputs (on-curve + order-r subgroup)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -207,6 +209,7 @@ def main():
 
     w = args.workload
     variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
+    vflags = b.CHECK_SUBGROUP if args.check_subgroup else 0
     n = 1 << args.log2n
     ctx = b.Context([local_rank])
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
@@ -266,10 +269,10 @@ def main():
         """device-resident pass: everything is enqueued on the library stream"""
         if w in ("verify", "verify_pk"):
             ctx.verify_batch_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(),
-                                 len(dst), 0, d_out.data_ptr())
+                                 len(dst), vflags, d_out.data_ptr())
         elif w == "verify_rand":
             ctx.verify_batch_randomized_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(),
-                                            len(dst), 0, d_seed.data_ptr(), 64, args.group, d_out.data_ptr())
+                                            len(dst), vflags, d_seed.data_ptr(), 64, args.group, d_out.data_ptr())
         elif w == "hash_g1":
             ctx.hash_to_g1_dev(d_blob.data_ptr(), d_off.data_ptr(), n, d_dst.data_ptr(), len(dst), 2, d_out.data_ptr(), d_status.data_ptr())
         elif w == "hash_g2":
@@ -305,12 +308,12 @@ def main():
     def step_e2e():
         """the call a user makes: host buffers in, host result out"""
         if w in ("verify", "verify_pk"):
-            ctx.raw("bn254_verify_batch", variant, h_pks.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst, len(dst), 0,
+            ctx.raw("bn254_verify_batch", variant, h_pks.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst, len(dst), vflags,
                     h_ok.data_ptr())
             return bytes(h_ok[:n].numpy())
         if w == "verify_rand":
             ctx.raw("bn254_verify_batch_randomized", variant, h_pks.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst,
-                    len(dst), 0, RBV_SEED, 64, args.group, h_ok.data_ptr())
+                    len(dst), vflags, RBV_SEED, 64, args.group, h_ok.data_ptr())
             return bytes(h_ok[:(n + args.group - 1) // args.group].numpy())
         if w == "hash_g1":
             return ctx.hash_to_g1((blob, off), dst)

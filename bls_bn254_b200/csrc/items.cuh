@@ -183,20 +183,53 @@ BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const 
 }
 
 // ---- subgroup membership (g1.rs:852-855, g2.rs:733-736: is_torsion_free = [r]P is the identity) ----
-// out = 1 for a decodable point on the curve whose order divides r (the identity included).
+// out = 1 for a decodable point ON THE CURVE whose order divides r (the identity included).  Callers decode with the
+// on-curve check, so FL_BAD already covers "not on the curve".  The same predicate as the reference's [r]P == O,
+// evaluated without the 254-bit multiplication (-DBN_NAIVE_SUBGROUP_CHECK restores it):
+//   G1: #E(Fp) = r (cofactor 1): every point of the curve is in the subgroup, nothing is left to compute.
+//   G2: for BN curves  Q in G2  <=>  [x+1]Q + psi([x]Q) + psi^2([x]Q) = psi^3([2x]Q)  (Dai-Lin-Zhao-Zhou, "Fast subgroup
+//       membership testings on pairing-friendly curves", 2022; the test gnark-crypto uses for this curve): one 63-bit
+//       multiplication and three psi instead of 254 doublings.  Checked against [r]Q on subgroup points, random points of
+//       the twist, points of the cofactor subgroup and sums of both (oracle/pymodel.py, tests/test_hostsim.py, GPU suite).
 BN_INL uint8_t item_g1_torsion_free(const g1m &p, uint8_t fl) {
     if (fl & FL_BAD) return 0;
+#ifdef BN_NAIVE_SUBGROUP_CHECK
     g1p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
     pt_mul(r, a, k::R_ORDER, 254);
     return fp_is_zero(r.z) ? 1 : 0;
+#else
+    (void)p;
+    return 1;
+#endif
 }
 BN_INL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
     if (fl & FL_BAD) return 0;
     g2p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
+#ifdef BN_NAIVE_SUBGROUP_CHECK
     pt_mul(r, a, k::R_ORDER, 254);
     return fp2_is_zero(r.z) ? 1 : 0;
+#else
+    const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
+    g2p xq, b, c, t;
+    pt_mul(xq, a, xw, 63);       // [x]Q
+    g2_psi(b, xq);               // psi([x]Q)
+    g2_psi(c, b);                // psi^2([x]Q)
+    g2_psi(t, c);                // psi^3([x]Q)
+    pt_dbl(t, t);                // psi^3([2x]Q)
+    pt_add(r, xq, a);            // [x+1]Q
+    pt_add(r, r, b);
+    pt_add(r, r, c);
+    // r == t as projective points: cross-multiplied coordinates (both may be the identity)
+    fp2 l, m;
+    fp2_mul(l, r.x, t.z); fp2_mul(m, t.x, r.z);
+    bool eq = fp2_eq(l, m);
+    fp2_mul(l, r.y, t.z); fp2_mul(m, t.y, r.z);
+    eq &= fp2_eq(l, m);
+    bool rz = fp2_is_zero(r.z), tz = fp2_is_zero(t.z);
+    return (rz || tz) ? (uint8_t)(rz && tz) : (uint8_t)eq;
+#endif
 }
 
 // ---- compressed codecs (g1.rs:283-288 / 311-328, g2.rs:274-283 / 309-340) ------------------------

@@ -147,6 +147,21 @@ EXPORT void sim_fp_inv(const uint32_t *a, size_t n, uint32_t *bingcd, uint32_t *
         }
     }
 }
+// subgroup membership as the kernels evaluate it (G1: on-curve; G2: the psi criterion), from wire bytes
+EXPORT void sim_torsion_free(const uint8_t *g1pts, size_t n1, const uint8_t *g2pts, size_t n2, uint8_t *out1, uint8_t *out2) {
+    for (size_t i = 0; i < n1; i++) {
+        g1m p;
+        uint8_t fl;
+        item_g1_decode(p, fl, g1pts + 64 * i, true);
+        out1[i] = item_g1_torsion_free(p, fl);
+    }
+    for (size_t i = 0; i < n2; i++) {
+        g2m q;
+        uint8_t fl;
+        item_g2_decode(q, fl, g2pts + 128 * i, true);
+        out2[i] = item_g2_torsion_free(q, fl);
+    }
+}
 // randomised batch verification: the per-tuple scalar and the two scalings of items.cuh
 EXPORT void sim_rbv_scalar(const uint8_t *seed, uint64_t idx, int nbits, uint32_t *kw) {
     rbv_k kk;

@@ -426,8 +426,11 @@ def test_subgroup_checks(ctx, orc, B):
     g1, g2 = _points(ctx, orc, 6, 17)
     raw = orc.svdw_g2(b"".join((i + 5).to_bytes(32, "big") + (i + 9).to_bytes(32, "big") for i in range(4)))  # on the curve, outside the subgroup
     ident2 = bytes(64) + bytes(63) + b"\x01"
-    pts2 = B.G2_GENERATOR + g2 + raw + ident2 + b"\xff" * 128
-    assert ctx.g2_is_torsion_free(pts2) == orc.g2_is_torsion_free(pts2)
+    from oracle import pymodel as pm
+    cof = orc.g2_mul(raw, pm.R_ORDER.to_bytes(32, "big") * 4)          # components in the cofactor subgroup
+    mixed = b"".join(orc.g2_sum(g2[128 * i:128 * (i + 1)] + cof[128 * i:128 * (i + 1)]) for i in range(4))
+    pts2 = B.G2_GENERATOR + g2 + raw + cof + mixed + ident2 + b"\xff" * 128
+    assert ctx.g2_is_torsion_free(pts2) == orc.g2_is_torsion_free(pts2) == b"\x01" * 7 + b"\x00" * 12 + b"\x01\x00"
     assert ctx.g2_is_torsion_free(raw) == b"\x00" * 4 and ctx.g2_is_on_curve(raw) == b"\x01" * 4
     off = bytearray(g1)
     off[40] ^= 1

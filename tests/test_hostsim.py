@@ -154,6 +154,31 @@ def test_scalar_mul_and_codecs(sim, orc):
     assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
 
 
+def test_subgroup_checks_without_the_big_multiplication(sim, orc):
+    """is_torsion_free as the kernels evaluate it (G1: cofactor 1, so on-curve; G2: [x+1]Q + psi([x]Q) + psi^2([x]Q) ==
+    psi^3([2x]Q)) against the oracle's [r]P == O (g1.rs:852-855, g2.rs:733-736) on subgroup points, points of the twist
+    outside the subgroup, points of the cofactor subgroup, sums of both, the identity, off-curve and undecodable bytes"""
+    from oracle import pymodel as pm
+    rng = random.Random(21)
+    msgs = [rng.randbytes(7) for _ in range(5)]
+    g1 = orc.g1_generator() + orc.hash_to_g1(msgs, QUUX_G1)
+    off1 = bytearray(g1[:64]); off1[40] ^= 1
+    ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    pts1 = g1 + bytes(off1) + ident1 + b"\xff" * 64
+    good2 = orc.g2_generator() + orc.hash_to_g2(msgs, QUUX_G2)
+    raw = orc.svdw_g2(b"".join((i + 5).to_bytes(32, "big") + (i + 9).to_bytes(32, "big") for i in range(4)))   # on the twist, not in G2
+    cof = orc.g2_mul(raw, pm.R_ORDER.to_bytes(32, "big") * 4)                                                   # cofactor-subgroup components
+    mixed = b"".join(orc.g2_sum(good2[128 * i:128 * (i + 1)] + cof[128 * i:128 * (i + 1)]) for i in range(4))
+    off2 = bytearray(good2[:128]); off2[100] ^= 1
+    ident2 = bytes(64) + bytes(63) + b"\x01"
+    pts2 = good2 + raw + cof + mixed + bytes(off2) + ident2 + b"\xff" * 128
+    n1, n2 = len(pts1) // 64, len(pts2) // 128
+    o1, o2 = C.create_string_buffer(n1), C.create_string_buffer(n2)
+    sim.sim_torsion_free(pts1, C.c_size_t(n1), pts2, C.c_size_t(n2), o1, o2)
+    assert o1.raw == orc.g1_is_torsion_free(pts1) == b"\x01" * 6 + b"\x00\x01\x00"
+    assert o2.raw == orc.g2_is_torsion_free(pts2) == b"\x01" * 6 + b"\x00" * 12 + b"\x00\x01\x00"
+
+
 def test_is_square_jacobi(sim):
     """fp_is_square as a binary Jacobi symbol == the Euler criterion it replaces == Python's pow, on edge values
     (0, 1, 2, p-1, powers of two, values with long runs of zero bits) and 4000 random residues"""
