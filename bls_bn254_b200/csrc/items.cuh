@@ -211,9 +211,8 @@ BN_INL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
     pt_mul(r, a, k::R_ORDER, 254);
     return fp2_is_zero(r.z) ? 1 : 0;
 #else
-    const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
     g2p xq, b, c, t;
-    pt_mul(xq, a, xw, 63);       // [x]Q
+    pt_mul_x(xq, a);             // [x]Q
     g2_psi(b, xq);               // psi([x]Q)
     g2_psi(c, b);                // psi^2([x]Q)
     g2_psi(t, c);                // psi^3([x]Q)
