@@ -304,6 +304,9 @@ def main():
     h_pks = pinned(pks) if pks else None
     h_sigs = pinned(sigs) if sigs else None
     h_ok = torch.zeros(max(n, 1), dtype=torch.uint8).pin_memory()
+    h_g1 = pinned(g1) if g1 else None
+    h_g2 = pinned(g2) if g2 else None
+    h_out = torch.zeros(n * out_rec, dtype=torch.uint8).pin_memory() if w in ("hash_g1", "hash_g2", "pairing") else None
 
     def step_e2e():
         """the call a user makes: host buffers in, host result out"""
@@ -315,12 +318,13 @@ def main():
             ctx.raw("bn254_verify_batch_randomized", variant, h_pks.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst,
                     len(dst), vflags, RBV_SEED, 64, args.group, h_ok.data_ptr())
             return bytes(h_ok[:(n + args.group - 1) // args.group].numpy())
-        if w == "hash_g1":
-            return ctx.hash_to_g1((blob, off), dst)
-        if w == "hash_g2":
-            return ctx.hash_to_g2((blob, off), dst)
+        if w in ("hash_g1", "hash_g2"):
+            ctx.raw("bn254_hash_to_g1" if w == "hash_g1" else "bn254_hash_to_g2", h_blob.data_ptr(), h_off.data_ptr(), n, dst, len(dst),
+                    h_out.data_ptr(), h_ok.data_ptr())
+            return None
         if w == "pairing":
-            return ctx.pairing(g1, g2)
+            ctx.raw("bn254_pairing_batch", h_g1.data_ptr(), h_g2.data_ptr(), n, h_out.data_ptr(), h_ok.data_ptr())
+            return None
         part, bad = ctx.aggregate_partial(variant, pks, (blob, off), agg if rank == 0 else None, dst)
         if world > 1:
             t = dev_bytes(part + bytes([bad]))
@@ -360,6 +364,8 @@ def main():
             assert bytes(d_out.cpu().numpy()) == expected, "device-resident accept bits differ from the construction"
         if w == "aggregate" and rank == 0:
             assert got == 1 and verdict.get("ok") == 1, "aggregate verification rejected a valid aggregate"
+        if h_out is not None:
+            assert bytes(h_out.numpy()) == bytes(d_out.cpu().numpy()), "host-buffer call and device-resident call disagree"
 
     # ---- timed region: EXACTLY K steps, CUDA events on the launch stream, L2 flushed between steps ----
     def timed_pass():
