@@ -203,7 +203,10 @@ BN_INL uint8_t item_g1_torsion_free(const g1m &p, uint8_t fl) {
     return 1;
 #endif
 }
-BN_INL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
+// Out of line on purpose: inlined into k_g2_torsion_free (behind the wire decode) the windowed [x]Q version returned 0 for
+// subgroup points on sm_100a (nvcc 12.9) while the same body inside k_g2_require_subgroup and the host build were right --
+// the third context-dependent miscompile of this round (profiles/r01_notes.md); one out-of-line copy serves both kernels.
+BN_NOINL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
     if (fl & FL_BAD) return 0;
     g2p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
