@@ -154,6 +154,47 @@ def test_scalar_mul_and_codecs(sim, orc):
     assert comp.raw == orc.g2_compress(g2) and back.raw == g2 and st.raw == b"\x01" * n
 
 
+def test_fp12_tower_operations_one_by_one(sim, orc):
+    """Fp6 / Fp12 product, square, inverse, conjugate, the three Frobenius maps, the Granger-Scott cyclotomic square and the
+    sparse 0/3/4 line product of the device code against the big-integer model (oracle/pymodel.py) -- the operations no
+    reference test pins individually -- plus the identities x * x^-1 = 1 and frob_k(x) = x^(p^k)"""
+    from oracle import pymodel as pm
+    rng = random.Random(31)
+
+    def rnd12():
+        return tuple(tuple((rng.randrange(P), rng.randrange(P)) for _ in range(3)) for _ in range(2))
+
+    def call(op, a, b=None):
+        out = C.create_string_buffer(384)
+        assert sim.sim_fp12_op(op, pm.gt_to_repr(a), pm.gt_to_repr(b) if b is not None else None, out) == 0
+        return out.raw
+
+    one = pm.gt_to_repr(pm.F12_ONE)
+    for _ in range(4):
+        x, y = rnd12(), rnd12()
+        assert call(0, x, y) == pm.gt_to_repr(pm.f12_mul(x, y))
+        assert call(1, x) == pm.gt_to_repr(pm.f12_sqr(x))
+        inv = pm.f12_inv(x)
+        assert call(2, x) == pm.gt_to_repr(inv)
+        assert call(0, x, inv) == one
+        assert call(3, x) == pm.gt_to_repr(pm.f12_conj(x))
+        for k in (1, 2, 3):
+            assert call(3 + k, x) == pm.gt_to_repr(pm.f12_frob(x, k))
+        c0, c3, c4 = y[0]
+        assert call(8, x, y) == pm.gt_to_repr(pm.f12_mul(x, pm.f12_sparse034(c0, c3, c4)))
+    x = rnd12()
+    assert call(4, x) == pm.gt_to_repr(pm.f12_pow(x, P))          # Frobenius really is the p-th power
+    # cyclotomic subgroup: x^((p^6 - 1)(p^2 + 1)); there squaring has the compressed Granger-Scott form and conj = inverse
+    e = pm.f12_mul(pm.f12_conj(x), pm.f12_inv(x))
+    e = pm.f12_mul(pm.f12_frob(e, 2), e)
+    assert call(7, e) == pm.gt_to_repr(pm.f12_sqr(e)) == call(1, e)
+    assert call(0, e, pm.f12_conj(e)) == one
+    # edge values
+    zero12 = tuple(tuple((0, 0) for _ in range(3)) for _ in range(2))
+    assert call(0, x, zero12) == pm.gt_to_repr(zero12) and call(0, x, pm.F12_ONE) == pm.gt_to_repr(x)
+    assert call(2, zero12) == pm.gt_to_repr(zero12)               # 0 -> 0 like the field inversion underneath
+
+
 def test_subgroup_checks_without_the_big_multiplication(sim, orc):
     """is_torsion_free as the kernels evaluate it (G1: cofactor 1, so on-curve; G2: [x+1]Q + psi([x]Q) + psi^2([x]Q) ==
     psi^3([2x]Q)) against the oracle's [r]P == O (g1.rs:852-855, g2.rs:733-736) on subgroup points, points of the twist
