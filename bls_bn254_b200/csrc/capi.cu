@@ -750,6 +750,7 @@ void bn254_ctx_destroy(bn254_ctx *ctx) {
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.id);
         if (d.st) cudaStreamSynchronize(d.st);
+        if (d.hi) cudaStreamSynchronize(d.hi);   // joined into d.st by every call; an aborted call may have left work on it
         for (auto &b : d.bufs)
             if (b.p) cudaFree(b.p);
         for (int k = 0; k < Dev::MAXSUB; k++) {
