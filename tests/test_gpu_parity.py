@@ -363,6 +363,35 @@ def test_randomized_batch_verify_full_size(ctx, orc, B):
     assert ctx.verify_batch_randomized(0, pks, msgs, tail, B.DST_MIN_SIG, bytes(32), group=g)[i // g] == 0
 
 
+def test_randomized_and_aggregate_beyond_one_lane_wave(ctx, B):
+    """140 001 tuples: more than the lane-pair kernels hold in one wave, so the randomised and aggregate paths run the
+    one-thread shape of the twin kernel (two tuples per thread, odd tail).  Valid groups accept, the groups of two
+    corrupted tuples reject, and the aggregate product equals, byte for byte, the product of shards that take other kernels."""
+    n = 140001
+    pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=0, n_keys=128, corrupt_every=0)
+    seed = b"\x3c" * 32
+    g = 500
+    ng = (n + g - 1) // g
+    agg = B.scheme.aggregate(ctx, sigs, 0)
+    whole, bad = ctx.aggregate_partial(0, pks, msgs, agg, B.DST_MIN_SIG)
+    parts = b""
+    cuts = [0, 30001, 60000, 90001, 120000, n]
+    for k in range(5):
+        lo, hi = cuts[k], cuts[k + 1]
+        part, b2 = ctx.aggregate_partial(0, pks[128 * lo:128 * hi], msgs[lo:hi], agg if k == 0 else None, B.DST_MIN_SIG)
+        parts += part
+        bad |= b2
+    assert bad == 0 and ctx.fp12_product(parts) == whole
+    assert ctx.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG) == 1
+    assert ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=g) == b"\x01" * ng
+    for j in (777, n - 1):
+        msgs[j] = msgs[j][:-1] + bytes([msgs[j][-1] ^ 1])
+    want = bytearray(b"\x01" * ng)
+    want[777 // g] = want[(n - 1) // g] = 0
+    assert ctx.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=g) == bytes(want)
+    assert ctx.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG) == 0
+
+
 def rbv_forgery_at(orc, sigs, seed, i, j, bits=64):
     from rbv_util import rbv_forgery
     return rbv_forgery(orc, sigs, seed, bits=bits, i=i, j=j)
