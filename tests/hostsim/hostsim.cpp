@@ -358,3 +358,36 @@ EXPORT void sim_final_exp_l2(const uint8_t *in, size_t n, uint8_t *out) {
         fp12_to_bytes(out + 384 * i, f);
     }
 }
+
+// the same Fp12 operations as sim_fp12_op in the LANE-PAIR representation (two emulated lanes, tower.cuh: fp2l)
+struct l2_op_args { int op; fp12 x, y, r; };
+static void l2_op_body(void *vp) {
+    l2_op_args *a = (l2_op_args *)vp;
+    fp12l x, y, r;
+    fp12_load(x, a->x);
+    fp12_load(y, a->y);
+    switch (a->op) {
+        case 0: fp12_mul(r, x, y); break;
+        case 1: fp12_sqr(r, x); break;
+        case 2: fp12_inv(r, x); break;
+        case 3: fp12_conj(r, x); break;
+        case 4: case 5: case 6: fp12_frob(r, x, a->op - 3); break;
+        case 7: cyclotomic_square(r, x); break;
+        default: r = x; fp12_mul_by_034(r, y.c0.c0, y.c0.c1, y.c0.c2); break;
+    }
+    fp12_store(a->r, r);
+}
+EXPORT int sim_fp12_op_l2(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    l2_op_args args;
+    args.op = op;
+    if (!fp12_from_bytes(args.x, a)) return -1;
+    if (b) {
+        if (!fp12_from_bytes(args.y, b)) return -1;
+    } else {
+        args.y = args.x;
+    }
+    run_pair(l2_op_body, &args);
+    fp12_to_bytes(out, args.r);
+    return 0;
+}
+

@@ -165,8 +165,11 @@ def test_fp12_tower_operations_one_by_one(sim, orc):
         return tuple(tuple((rng.randrange(P), rng.randrange(P)) for _ in range(3)) for _ in range(2))
 
     def call(op, a, b=None):
-        out = C.create_string_buffer(384)
+        """one thread per element, and the lane-pair representation (two emulated lanes): both must give the same bytes"""
+        out, out2 = C.create_string_buffer(384), C.create_string_buffer(384)
         assert sim.sim_fp12_op(op, pm.gt_to_repr(a), pm.gt_to_repr(b) if b is not None else None, out) == 0
+        assert sim.sim_fp12_op_l2(op, pm.gt_to_repr(a), pm.gt_to_repr(b) if b is not None else None, out2) == 0
+        assert out.raw == out2.raw, "lane-pair result differs (op %d)" % op
         return out.raw
 
     one = pm.gt_to_repr(pm.F12_ONE)
