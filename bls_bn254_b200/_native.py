@@ -59,6 +59,12 @@ def lib():
         L.bn254_stream.argtypes = [vp]
         L.bn254_stream.restype = vp
         L.bn254_sync.argtypes = [vp]
+        L.bn254_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+        L.bn254_host_register.argtypes = [vp, sz]
+        L.bn254_host_unregister.argtypes = [vp]
+        L.bn254_comm_unique_id.argtypes = [vp]
+        L.bn254_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.bn254_comm_nranks.argtypes = [vp]
         L.bn254_profile_enable.argtypes = [vp, C.c_int]
         L.bn254_profile_drain.argtypes = [vp, vp, sz]
         for name in ("bn254_hash_to_g1", "bn254_encode_to_g1", "bn254_hash_to_g2", "bn254_encode_to_g2"):
@@ -73,6 +79,8 @@ def lib():
         for name in ("bn254_verify_batch_randomized", "bn254_verify_batch_randomized_dev"):
             getattr(L, name).argtypes = [vp, C.c_int, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp, C.c_int, sz, vp]
         L.bn254_aggregate_partial.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp, vp]
+        for name in ("bn254_aggregate_verify_dist", "bn254_aggregate_verify_dist_dev"):
+            getattr(L, name).argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp]
         L.bn254_aggregate_finish.argtypes = [vp, vp, vp, sz, vp]
         for name in ("bn254_g1_compress", "bn254_g2_compress", "bn254_g1_is_on_curve", "bn254_g2_is_on_curve", "bn254_g1_is_torsion_free", "bn254_g2_is_torsion_free",
                      "bn254_g1_sum", "bn254_g2_sum"):
@@ -94,6 +102,8 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "bn254_device_count", "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_launch_count", "bn254_stream", "bn254_sync", "bn254_profile_enable", "bn254_profile_drain",
+    "bn254_ctx_set_option", "bn254_host_register", "bn254_host_unregister", "bn254_comm_unique_id", "bn254_comm_init_rank", "bn254_comm_nranks",
+    "bn254_aggregate_verify_dist", "bn254_aggregate_verify_dist_dev",
     "bn254_hash_to_g1", "bn254_encode_to_g1", "bn254_hash_to_g2", "bn254_encode_to_g2",
     "bn254_pairing_batch", "bn254_miller_loop_batch", "bn254_multi_miller_loop", "bn254_final_exponentiation", "bn254_fp12_product",
     "bn254_verify_batch", "bn254_verify_batch_randomized", "bn254_aggregate_verify", "bn254_aggregate_partial", "bn254_aggregate_finish",

@@ -28,7 +28,8 @@ class Bn254Error(Exception):
 
     def __init__(self, code, msg=""):
         self.code = code
-        super().__init__("%s (%d)%s" % (self.NAMES.get(code, "CudaError"), code, (": " + msg) if msg else ""))
+        kind = self.NAMES.get(code, "NcclError" if code <= -200 else "CudaError")
+        super().__init__("%s (%d)%s" % (kind, code, (": " + msg) if msg else ""))
 
 
 def pack_msgs(msgs):
@@ -40,6 +41,21 @@ def pack_msgs(msgs):
         pos += len(m)
     off[len(msgs)] = pos
     return b"".join(msgs), off
+
+
+def _msgs(msgs):
+    """list[bytes] or an already packed (blob, offsets) pair -> (blob, offsets, n); a packed pair is checked against its
+    blob (the C ABI has no blob length: offsets[n] is what bounds the reads)."""
+    if not isinstance(msgs, tuple):
+        blob, off = pack_msgs(msgs)
+        return blob, off, len(off) - 1
+    blob, off = msgs
+    n = len(off) - 1
+    if n < 0:
+        raise Bn254Error(-10, "offsets must hold n + 1 entries")
+    if isinstance(blob, (bytes, bytearray)) and n >= 0 and int(off[n]) > len(blob):
+        raise Bn254Error(-10, "offsets[n] exceeds the message blob")
+    return blob, off, n
 
 
 def _ptr(x):
@@ -98,11 +114,32 @@ class Context:
     def sync(self):
         self._ck(self._L.bn254_sync(self._h))
 
+    def set_option(self, name, value):
+        """"lanes" (0 per launch / 1 one thread per pairing / 2 lane pair), "chunk", "split": include/bls_bn254_b200.h"""
+        self._ck(self._L.bn254_ctx_set_option(self._h, name.encode(), int(value)))
+
+    # ---- NCCL communicator of a one-process-per-GPU job (the aggregate path's single exchange) -----------------
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self._L.bn254_comm_unique_id(_ptr(buf))
+        if rc:
+            raise Bn254Error(rc, "bn254_comm_unique_id (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init_rank(self, unique_id, nranks, rank):
+        if len(unique_id) != 128:
+            raise Bn254Error(-10, "unique id must be 128 bytes")
+        self._ck(self._L.bn254_comm_init_rank(self._h, _ptr(bytes(unique_id)), int(nranks), int(rank)))
+
+    @property
+    def comm_nranks(self):
+        return int(self._L.bn254_comm_nranks(self._h))
+
     def profile(self, on=True):
         self._ck(self._L.bn254_profile_enable(self._h, 1 if on else 0))
 
     def profile_drain(self):
-        """[(kernel name, items, milliseconds)] for every launch since the last drain (first device)."""
+        """[(kernel name, items, milliseconds)] for every launch since the last drain (all devices, device order)."""
         buf = C.create_string_buffer(1 << 20)
         self._ck(self._L.bn254_profile_drain(self._h, _ptr(buf), len(buf)))
         out = []
@@ -113,8 +150,7 @@ class Context:
 
     # ---- hash to curve ------------------------------------------------------------------------
     def _hash(self, fn, rec, msgs, dst, want_status):
-        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
-        n = len(off) - 1
+        blob, off, n = _msgs(msgs)
         out, st = C.create_string_buffer(rec * n), C.create_string_buffer(n)
         self._ck(fn(self._h, _ptr(blob), _ptr(off), n, _ptr(dst), len(dst), _ptr(out), _ptr(st)))
         return (out.raw, st.raw) if want_status else out.raw
@@ -178,8 +214,7 @@ class Context:
         return (128, 64) if variant == MIN_SIG else (64, 128)
 
     def verify_batch(self, variant, pks, msgs, sigs, dst, flags=0):
-        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
-        n = len(off) - 1
+        blob, off, n = _msgs(msgs)
         rpk, rsig = self._recs(variant)
         if len(pks) != rpk * n:
             raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
@@ -192,8 +227,7 @@ class Context:
     def verify_batch_randomized(self, variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0):
         """One accept byte per consecutive group of `group` tuples (small-exponent batch test).
         `seed` = 32 bytes the signers cannot predict (fresh CSPRNG output per call)."""
-        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
-        n = len(off) - 1
+        blob, off, n = _msgs(msgs)
         rpk, rsig = self._recs(variant)
         if len(pks) != rpk * n:
             raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
@@ -208,8 +242,7 @@ class Context:
         return ok.raw[:ng]
 
     def aggregate_verify(self, variant, pks, msgs, agg_sig, dst, flags=0):
-        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
-        n = len(off) - 1
+        blob, off, n = _msgs(msgs)
         rpk, rsig = self._recs(variant)
         if len(pks) != rpk * n:
             raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
@@ -219,10 +252,28 @@ class Context:
         self._ck(self._L.bn254_aggregate_verify(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), n, _ptr(agg_sig), _ptr(dst), len(dst), flags, _ptr(ok)))
         return ok.raw[0]
 
+    def aggregate_verify_dist(self, variant, pks_shard, msgs_shard, agg_sig, dst, flags=0):
+        """Every rank of a one-process-per-GPU job calls this with ITS shard; agg_sig is read on rank 0.  One NCCL
+        all-gather of 400 bytes per rank, one post-gather kernel; returns the job's verdict on every rank."""
+        blob, off, n = _msgs(msgs_shard)
+        rpk, rsig = self._recs(variant)
+        if len(pks_shard) != rpk * n:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if agg_sig is not None and len(agg_sig) != rsig:
+            raise Bn254Error(-2 if variant == MIN_SIG else -3, "signature length")
+        ok = C.create_string_buffer(1)
+        self._ck(self._L.bn254_aggregate_verify_dist(self._h, variant, _ptr(pks_shard), _ptr(blob), _ptr(off), n, _ptr(agg_sig), _ptr(dst), len(dst),
+                                                     flags, _ptr(ok)))
+        return ok.raw[0]
+
     def aggregate_partial(self, variant, pks, msgs, agg_sig, dst, flags=0):
         """One shard: (384-byte Fp12 partial product, bad flag).  agg_sig only on one shard."""
-        blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
-        n = len(off) - 1
+        blob, off, n = _msgs(msgs)
+        rpk, rsig = self._recs(variant)
+        if len(pks) != rpk * n:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if agg_sig is not None and len(agg_sig) != rsig:
+            raise Bn254Error(-2 if variant == MIN_SIG else -3, "signature length")
         part, bad = C.create_string_buffer(384), C.create_string_buffer(1)
         self._ck(self._L.bn254_aggregate_partial(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), n, _ptr(agg_sig), _ptr(dst), len(dst), flags,
                                                  _ptr(part), _ptr(bad)))
@@ -230,6 +281,8 @@ class Context:
 
     def aggregate_finish(self, partials, bads):
         k = len(partials) // 384
+        if k == 0 or len(partials) != 384 * k or len(bads) != k:
+            raise Bn254Error(-4, "partials must be k x 384 bytes with k flags")
         ok = C.create_string_buffer(1)
         self._ck(self._L.bn254_aggregate_finish(self._h, _ptr(partials), _ptr(bytes(bads)), k, _ptr(ok)))
         return ok.raw[0]
@@ -241,6 +294,8 @@ class Context:
             raise Bn254Error(-2, "length mismatch")
         out = C.create_string_buffer(max(1, rout * n))
         if extra is not None:
+            if len(extra) != 32 * n:
+                raise Bn254Error(-1, "scalars must be n x 32 bytes")
             self._ck(fn(self._h, _ptr(data), _ptr(extra), n, _ptr(out)))
             return out.raw[:rout * n]
         if status:
@@ -262,11 +317,15 @@ class Context:
     def g2_mul(self, pts, scalars): return self._map(self._L.bn254_g2_mul, pts, 128, 128, extra=scalars)
 
     def g1_sum(self, pts):
+        if len(pts) % 64:
+            raise Bn254Error(-2, "length mismatch")
         out = C.create_string_buffer(64)
         self._ck(self._L.bn254_g1_sum(self._h, _ptr(pts), len(pts) // 64, _ptr(out)))
         return out.raw
 
     def g2_sum(self, pts):
+        if len(pts) % 128:
+            raise Bn254Error(-3, "length mismatch")
         out = C.create_string_buffer(128)
         self._ck(self._L.bn254_g2_sum(self._h, _ptr(pts), len(pts) // 128, _ptr(out)))
         return out.raw
@@ -300,6 +359,9 @@ class Context:
 
     def aggregate_partial_dev(self, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad):
         self._ck(self._L.bn254_aggregate_partial_dev(self._h, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, bad))
+
+    def aggregate_verify_dist_dev(self, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, ok):
+        self._ck(self._L.bn254_aggregate_verify_dist_dev(self._h, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, ok))
 
     def imad_peak(self, mode=2, iters=4096):
         """(IMAD-ops/s, ms); mode 0 mad.lo, 1 mad.lo+mad.hi, 2 IMAD.WIDE (2 ops each)."""

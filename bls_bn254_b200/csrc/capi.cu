@@ -13,6 +13,7 @@
 
 #include "../../include/bls_bn254_b200.h"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 
 using namespace bn;
 
@@ -22,8 +23,25 @@ enum Scratch {
     S_IN_A, S_IN_B, S_IN_C, S_MSGS, S_OFF, S_DST, S_OUT, S_STATUS,
     S_P0, S_FLP0, S_P1, S_FLP1, S_Q0, S_FLQ0, S_Q1, S_FLQ1, S_F, S_FLF, S_F2, S_BAD, S_TMP, S_FLTMP, S_CONST,
     S_RB_S0, S_RB_S1, S_RB_S2, S_RB_FA, S_RB_FB, S_RB_FS, S_RB_GP, S_RB_GQ, S_RB_FLP, S_RB_FLQ, S_RB_BAD, S_RB_SEED,
+    // second set of staging buffers: the chunk pipeline copies chunk k+1 in while the kernels of chunk k read the first set
+    S_IN_A2, S_IN_B2, S_IN_C2, S_MSGS2, S_OFF2, S_OUT2, S_STATUS2,
+    S_AGG_SEND, S_AGG_RECV,   // agg_rec: this rank's record / the gathered records of all ranks
     S_COUNT
 };
+// staging set s (0 / 1) of the chunk pipeline
+inline Scratch stage_buf(Scratch first, int s) {
+    if (!s) return first;
+    switch (first) {
+        case S_IN_A: return S_IN_A2;
+        case S_IN_B: return S_IN_B2;
+        case S_IN_C: return S_IN_C2;
+        case S_MSGS: return S_MSGS2;
+        case S_OFF: return S_OFF2;
+        case S_OUT: return S_OUT2;
+        case S_STATUS: return S_STATUS2;
+        default: return first;
+    }
+}
 
 struct Buf { void *p = nullptr; size_t cap = 0; };
 
@@ -54,6 +72,18 @@ struct Dev {
     cudaEvent_t ev_hi_fork = nullptr, ev_hi_join = nullptr;
     int nsub = 1;
     size_t lane_wave_threads = 0;   // threads of one full wave of the lane-pair kernels on this device
+    // Shape of the pairing kernels: 0 = picked per launch (lane pairs while 2n threads fit one wave), 1 = one thread per
+    // pairing, 2 = two lanes per pairing.  BN254_LANES / bn254_ctx_set_option("lanes") force a shape so that the parity
+    // suite meets BOTH shapes at every size (the big-batch shape is what a 2^24-tuple job runs).
+    int shape = 0;
+    // Chunk pipeline of the host-buffer entry points: copies run on `cp`, kernels on `st`; two staging sets.
+    cudaStream_t cp = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {};
+    void *pin[2] = {};              // pinned result staging (used when the caller's result buffer is pageable)
+    size_t pin_cap[2] = {};
+    // NCCL communicator of the aggregate path (one rank per device; null on a lone device without bn254_comm_init_rank)
+    bn_nccl::comm_t comm = nullptr;
+    int nranks = 1, rank = 0;
 };
 
 }  // namespace
@@ -82,6 +112,7 @@ int ensure(Dev &d, Scratch s, size_t bytes, void **out) {
     if (b.cap < bytes) {
         if (b.p) {
             CK(d, cudaStreamSynchronize(d.st));
+            if (d.cp) CK(d, cudaStreamSynchronize(d.cp));
             CK(d, cudaFree(b.p));
             b.p = nullptr;
             b.cap = 0;
@@ -105,21 +136,29 @@ inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1)
 
 #define BN_STR2(x) #x
 #define BN_STR(x) BN_STR2(x)
+// per-launch timing: the event pair is owned by d.recs from the moment it exists, so no error path leaks it
+int prof_begin(Dev &d, const char *name, size_t n) {
+    if (!d.prof) return 0;
+    ProfRec pr = {name, n, nullptr, nullptr};
+    d.recs.push_back(pr);
+    ProfRec &r = d.recs.back();
+    CK(d, cudaEventCreate(&r.e0));
+    CK(d, cudaEventCreate(&r.e1));
+    CK(d, cudaEventRecord(r.e0, d.cur));
+    return 0;
+}
+int prof_end(Dev &d) {
+    if (!d.prof) return 0;
+    CK(d, cudaEventRecord(d.recs.back().e1, d.cur));
+    return 0;
+}
 #define LAUNCH(d, kern, n, tpb, ...)                                             \
     do {                                                                         \
         if ((n) > 0) {                                                           \
-            ProfRec pr_ = {BN_STR(kern), (size_t)(n), nullptr, nullptr};                \
-            if ((d).prof) {                                                      \
-                CK(d, cudaEventCreate(&pr_.e0));                                 \
-                CK(d, cudaEventCreate(&pr_.e1));                                 \
-                CK(d, cudaEventRecord(pr_.e0, (d).cur));                          \
-            }                                                                    \
+            if (int rcp_ = prof_begin(d, BN_STR(kern), (size_t)(n))) return rcp_; \
             kern<<<blocks((n), (tpb)), (tpb), 0, (d).cur>>>(__VA_ARGS__);         \
             (d).launches++;                                                      \
-            if ((d).prof) {                                                      \
-                CK(d, cudaEventRecord(pr_.e1, (d).cur));                          \
-                (d).recs.push_back(pr_);                                         \
-            }                                                                    \
+            if (int rcp_ = prof_end(d)) return rcp_;                             \
             CK(d, cudaGetLastError());                                           \
         }                                                                        \
     } while (0)
@@ -127,14 +166,11 @@ inline unsigned blocks(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1)
 // Pairing kernels come in two bit-identical shapes: one thread per pairing, and two lanes per pairing
 // (lane-split Fp2, tower.cuh: half the per-thread state, twice the warps).  Measured on B200: the lane
 // pair wins while the batch does not fill the machine with one thread per item (2^14: +10 %, 2^16:
-// +4 %), one thread per pairing wins beyond (2^18, 2^20: +3 %).  BN_LANES = 0 (default) picks per
-// launch: lanes while 2n threads fit one wave of the lane kernels; 1 / 2 force a shape.
-#ifndef BN_LANES
-#define BN_LANES 0
-#endif
+// +4 %), the two are level beyond.  d.shape = 0 (default) picks per launch: lanes while 2n threads fit
+// one wave of the lane kernels; 1 / 2 force a shape (BN254_LANES, bn254_ctx_set_option).
 #define LAUNCH_PAIR(d, kscalar, klane, n, ...)                                              \
     do {                                                                                    \
-        if (BN_LANES == 2 || (BN_LANES == 0 && 2 * (size_t)(n) <= (d).lane_wave_threads))    \
+        if ((d).shape == 2 || ((d).shape == 0 && 2 * (size_t)(n) <= (d).lane_wave_threads))   \
             LAUNCH(d, klane, 2 * (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                   \
         else                                                                                \
             LAUNCH(d, kscalar, (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                     \
@@ -219,8 +255,9 @@ int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *st
     return 0;
 }
 
-// product of n Fp12 records (internal form) -> *result points at one record in scratch
-int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result) {
+// product of n Fp12 records (internal form) -> *result points at one record: `final_dst` when given (the last pass of
+// the tree then writes straight into it, e.g. the NCCL send record), else a scratch record
+int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result, fp12 *final_dst = nullptr) {
     fp12 *A, *B;
     size_t m0 = std::max<size_t>(1, (n + 15) / 16);
     if (int rc = ensure_t(d, S_F2, m0 + (m0 + 15) / 16 + 2, &A)) return rc;
@@ -230,6 +267,7 @@ int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result) {
     fp12 *dstp = A;
     while (true) {
         size_t m = std::max<size_t>(1, (cur + 15) / 16);
+        if (m == 1 && final_dst) dstp = final_dst;
         LAUNCH(d, k_fp12_reduce, m, BN_TPB_HEAVY, dstp, src, cur, m);
         if (m == 1) break;
         src = dstp;
@@ -240,21 +278,17 @@ int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result) {
     return 0;
 }
 
-const g1m *neg_g1_const(Dev &d, const uint8_t **fl) {
-    // -g1 = (1, -2) in Montgomery form + a zero flag byte, uploaded once per device
+// -g1 = (1, -2) in Montgomery form + a zero flag byte, filled once per device by a kernel on the launch stream
+int neg_g1_const(Dev &d, const g1m **pt, const uint8_t **fl) {
     Buf &b = d.bufs[S_CONST];
     if (!b.p) {
-        struct { g1m p; uint8_t fl[16]; } h;
-        memset(&h, 0, sizeof h);
-        const uint32_t one[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
-        memcpy(h.p.x.v, one, 32);
-        cudaMemcpyFromSymbol(h.p.y.v, k::NEG_TWO, 32);
         void *p = nullptr;
-        if (ensure(d, S_CONST, sizeof h, &p)) return nullptr;
-        cudaMemcpy(p, &h, sizeof h, cudaMemcpyHostToDevice);
+        if (int rc = ensure(d, S_CONST, sizeof(g1m) + 16, &p)) return rc;
+        LAUNCH(d, k_fill_neg_g1, 1, BN_TPB_LIGHT, (g1m *)p, (uint8_t *)p + sizeof(g1m), (size_t)1);
     }
     *fl = (const uint8_t *)b.p + sizeof(g1m);
-    return (const g1m *)b.p;
+    *pt = (const g1m *)b.p;
+    return 0;
 }
 
 // verification of items [lo, hi) of one chunk on the current stream (all arrays are chunk-sized)
@@ -266,7 +300,7 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
                      const uint8_t *sigs, size_t lo, size_t hi, const uint8_t *dst, uint32_t dst_len, int check, uint8_t *ok) {
     size_t n = hi - lo;
     const bool subgroup = (check & 2) != 0;
-    check &= 1;
+    check = (check & 1) | DEC_NO_IDENTITY;   // an identity key or signature never verifies (items.cuh: DEC_NO_IDENTITY)
     if (variant == BN254_MIN_SIG) {
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P0 + lo, b.flp0 + lo, sigs + 64 * lo, n, check);
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
@@ -313,8 +347,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
     } else {
         if (int rc = ensure_t(d, S_Q0, n, &b.Q0)) return rc;
         if (int rc = ensure_t(d, S_FLQ0, n, &b.flq0)) return rc;
-        b.ng1 = neg_g1_const(d, &b.flc);
-        if (!b.ng1) return d.rc ? d.rc : BN254_ERR_CUDA_BASE;
+        if (int rc = neg_g1_const(d, &b.ng1, &b.flc)) return rc;
     }
     int S = d.nsub;
     if (d.prof || n < (size_t)2048 * (size_t)S) S = 1;   // per-kernel timing wants the kernels serial
@@ -372,7 +405,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
 int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
                     size_t n, size_t group, const uint8_t *seed, uint64_t idx0, int nbits, const uint8_t *dst, uint32_t dst_len, uint32_t flags,
                     uint8_t *ok) {
-    const int check = (flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? 1 : 0;
+    const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
     const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
     const size_t nseg = (n + group - 1) / group;
     const size_t so0 = (group + BN_SEG_FAN - 1) / BN_SEG_FAN, so1 = (so0 + BN_SEG_FAN - 1) / BN_SEG_FAN;
@@ -480,11 +513,15 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
     return 0;
 }
 
-// One shard of an aggregate verification (device pointers).  Writes the 384-byte wire form of
-// prod_i ML(H(m_i), pk_i) [* ML(aggsig, -g2) when agg_sig != NULL] and a bad-input byte.
-int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n,
-                          const uint8_t *agg_sig, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
-    int check = (flags & BN254_FLAG_CHECK_ON_CURVE) ? 1 : 0;
+// One shard of an aggregate verification (device pointers): rec->f = prod_i ML(H(m_i), pk_i) [* ML(aggsig, -g2) when
+// agg_sig != NULL] in internal form, rec->bad = a key was undecodable / the identity / failed the requested checks, or a
+// message hit the SvdW exception.  The last pass of the product tree writes rec->f in place (rec may be the NCCL send
+// record).  flags: CHECK_SUBGROUP implies CHECK_ON_CURVE, as in verify; G1 has cofactor 1, so only G2 inputs (min-sig
+// keys, a min-pk aggregate signature) need the psi criterion.
+int dev_aggregate_rec(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n,
+                      const uint8_t *agg_sig, const uint8_t *dst, uint32_t dst_len, uint32_t flags, agg_rec *rec) {
+    const int check = (flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0;
+    const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
     size_t tot = n + (agg_sig ? 1 : 0);
     fp12 *F; g1m *P; g2m *Q; uint8_t *flp, *flq; int *dbad;
     if (int rc = ensure_t(d, S_F, tot + 1, &F)) return rc;
@@ -493,26 +530,28 @@ int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t
     if (int rc = ensure_t(d, S_FLP1, tot + 1, &flp)) return rc;
     if (int rc = ensure_t(d, S_FLQ1, tot + 1, &flq)) return rc;
     if (int rc = ensure_t(d, S_BAD, 4, &dbad)) return rc;
-    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.cur));
     if (variant == BN254_MIN_SIG) {
-        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, pks, n, check);
+        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, pks, n, check | DEC_NO_IDENTITY);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, flq, Q, n);
         if (int rc = dev_hash_g1(d, P, flp, msgs, off, base, n, dst, dst_len, 2)) return rc;
         if (agg_sig) {
             LAUNCH(d, k_g1_decode, 1, BN_TPB_LIGHT, P + n, flp + n, agg_sig, (size_t)1, check);
-            CK(d, cudaMemcpyFromSymbolAsync(&Q[n].x, k::G2_GEN_X, 64, 0, cudaMemcpyDeviceToDevice, d.st));
-            CK(d, cudaMemcpyFromSymbolAsync(&Q[n].y, k::NEG_G2_GEN_Y, 64, 0, cudaMemcpyDeviceToDevice, d.st));
-            CK(d, cudaMemsetAsync(flq + n, 0, 1, d.st));
+#ifdef BN_NAIVE_SUBGROUP_CHECK
+            if (subgroup) LAUNCH(d, k_g1_require_subgroup, 1, BN_TPB_HEAVY, flp + n, P + n, (size_t)1);
+#endif
+            LAUNCH(d, k_fill_neg_g2, 1, BN_TPB_LIGHT, Q + n, flq + n, (size_t)1);
         }
     } else {
-        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, pks, n, check);
+        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, pks, n, check | DEC_NO_IDENTITY);
+#ifdef BN_NAIVE_SUBGROUP_CHECK
+        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flp, P, n);
+#endif
         if (int rc = dev_hash_g2(d, Q, flq, msgs, off, base, n, dst, dst_len, 2)) return rc;
         if (agg_sig) {
             LAUNCH(d, k_g2_decode, 1, BN_TPB_LIGHT, Q + n, flq + n, agg_sig, (size_t)1, check);
-            const uint8_t *flc;
-            const g1m *ng1 = neg_g1_const(d, &flc);
-            if (!ng1) return d.rc ? d.rc : BN254_ERR_CUDA_BASE;
-            CK(d, cudaMemcpyAsync(P + n, ng1, sizeof(g1m), cudaMemcpyDeviceToDevice, d.st));
-            CK(d, cudaMemsetAsync(flp + n, 0, 1, d.st));
+            if (subgroup) LAUNCH(d, k_g2_require_subgroup, 1, BN_TPB_HEAVY, flq + n, Q + n, (size_t)1);
+            LAUNCH(d, k_fill_neg_g1, 1, BN_TPB_LIGHT, P + n, flp + n, (size_t)1);
         }
     }
     // a batch that overfills the machine takes two pairs per thread: one shared Fp12 squaring per step (see dev_verify_rand)
@@ -524,9 +563,18 @@ int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t
         LAUNCH_PAIR(d, k_miller1, k_miller1_l2, tot, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
     }
     fp12 *res;
-    if (int rc = dev_fp12_product(d, F, nf, &res)) return rc;
-    LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, partial, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);
-    CK(d, cudaMemcpyAsync(bad, dbad, 1, cudaMemcpyDeviceToDevice, d.st));  // little-endian low byte
+    if (int rc = dev_fp12_product(d, F, nf, &res, &rec->f)) return rc;
+    LAUNCH(d, k_agg_rec_flag, 1, 32, rec, dbad);
+    return 0;
+}
+// the same with the partial in wire form (384 bytes) and the flag as one byte: bn254_aggregate_partial[_dev]
+int dev_aggregate_partial(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, size_t n,
+                          const uint8_t *agg_sig, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
+    agg_rec *rec;
+    if (int rc = ensure_t(d, S_AGG_SEND, 1, &rec)) return rc;
+    if (int rc = dev_aggregate_rec(d, variant, pks, msgs, off, base, n, agg_sig, dst, dst_len, flags, rec)) return rc;
+    LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, partial, (uint8_t *)nullptr, &rec->f, (const uint8_t *)nullptr, (size_t)1);
+    CK(d, cudaMemcpyAsync(bad, &rec->bad, 1, cudaMemcpyDeviceToDevice, d.cur));  // little-endian low byte
     return 0;
 }
 
@@ -536,7 +584,7 @@ int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, si
     if (int rc = ensure_t(d, S_F, kparts + 1, &F)) return rc;
     if (int rc = ensure_t(d, S_FLF, kparts + 1, &flf)) return rc;
     if (int rc = ensure_t(d, S_BAD, 4, &dbad)) return rc;
-    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+    CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.cur));
     LAUNCH(d, k_fp12_decode, kparts, BN_TPB_LIGHT, F, flf, partials, kparts);
     LAUNCH(d, k_or_flags, kparts, BN_TPB_LIGHT, dbad, flf, kparts);
     LAUNCH(d, k_or_bytes, kparts, BN_TPB_LIGHT, dbad, bad, kparts);
@@ -544,6 +592,41 @@ int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, si
     if (int rc = dev_fp12_product(d, F, kparts, &res)) return rc;
     LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, 1, res, (size_t)1);
     LAUNCH(d, k_finish_ok, 1, 32, ok, res, dbad);
+    return 0;
+}
+
+// ---- the aggregate path's exchange: ONE ncclAllGather of 400 bytes per rank on the launch stream, then
+//      ONE kernel (product of <= nranks partials, the single final exponentiation, compare).  No host round trip.
+#define NCCLCK(d, call)                                                                                  \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != bn_nccl::kSuccess) {                                                                   \
+            (d).err = std::string(#call) + ": " + (bn_nccl::api().GetErrorString ? bn_nccl::api().GetErrorString(r_) : "NCCL error"); \
+            (d).rc = BN254_ERR_NCCL_BASE - r_;                                                           \
+            return (d).rc;                                                                               \
+        }                                                                                                \
+    } while (0)
+int need_comm(Dev &d) {
+    if (d.comm) return 0;
+    d.err = bn_nccl::api().ok() ? "no communicator: call bn254_comm_init_rank (or create the ctx with several devices)"
+                                : (bn_nccl::api().why ? bn_nccl::api().why : "NCCL unavailable");
+    d.rc = BN254_ERR_NCCL_BASE;
+    return d.rc;
+}
+// this rank's record (device, S_AGG_SEND) -> every rank's records (device, S_AGG_RECV); enqueued on d.cur
+int dev_gather_recs(Dev &d, const agg_rec *send, agg_rec **recv) {
+    if (int rc = ensure_t(d, S_AGG_RECV, (size_t)d.nranks, recv)) return rc;
+    if (d.nranks == 1) {
+        CK(d, cudaMemcpyAsync(*recv, send, sizeof(agg_rec), cudaMemcpyDeviceToDevice, d.cur));
+        return 0;
+    }
+    if (int rc = need_comm(d)) return rc;
+    NCCLCK(d, bn_nccl::api().AllGather(send, *recv, sizeof(agg_rec), bn_nccl::kUint8, d.comm, d.cur));
+    d.launches++;   // NCCL's kernel
+    return 0;
+}
+int dev_gather_finish(Dev &d, const agg_rec *recs, uint8_t *ok) {
+    LAUNCH(d, k_gather_finish_l2, 32, 32, ok, (fp12 *)nullptr, recs, d.nranks);
     return 0;
 }
 
@@ -583,15 +666,104 @@ int fail_arg(bn254_ctx *ctx, const char *what) {
     return BN254_ERR_ARG;
 }
 
-// stage messages [lo, hi) of a host blob: copies the byte range and the offsets, returns device ptrs
-int stage_msgs(Dev &d, const uint8_t *msgs, const uint64_t *offsets, size_t lo, size_t hi, const uint8_t **d_msgs, const uint64_t **d_off,
-               uint64_t *base) {
+// ---- chunk pipeline of the host-buffer entry points ---------------------------------------------------
+// A 2^24-tuple job is 64 chunks of 2^18 tuples per device.  Copies run on the copy stream d.cp, kernels on d.st, with two
+// sets of staging buffers: while the kernels of chunk k read set k & 1, chunk k+1 is copied into the other set, and the
+// results of chunk k-1 travel back.  Result bytes go straight to the caller's buffer when it is pinned (cudaHostAlloc /
+// cudaHostRegister / bn254_host_register: the copy is then truly asynchronous); a pageable result buffer is served through
+// a pinned staging area of the ctx, because a device-to-pageable copy would block the host for the whole chunk and with
+// it the upload of the next one.  Pageable INPUT only costs the host-side staging copy of cudaMemcpyAsync, which overlaps
+// the kernels already queued.
+bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+struct Pipe {
+    struct Pending { uint8_t *host; size_t off, bytes; };
+    Dev &d;
+    size_t k = 0;
+    size_t pin_used = 0;
+    std::vector<Pending> pend[2];
+    explicit Pipe(Dev &dd) : d(dd) {}
+    int set() const { return (int)(k & 1); }
+    // staging set k & 1 was last used by chunk k - 2: wait for it and hand its staged results to the caller
+    int deliver(int s) {
+        if (pend[s].empty() && k < 2) return 0;
+        CK(d, cudaEventSynchronize(d.ev_out[s]));
+        for (auto &q : pend[s]) memcpy(q.host, (const uint8_t *)d.pin[s] + q.off, q.bytes);
+        pend[s].clear();
+        return 0;
+    }
+    int begin(size_t staged_result_bytes) {
+        int s = set();
+        if (k >= 2)
+            if (int rc = deliver(s)) return rc;
+        if (d.pin_cap[s] < staged_result_bytes) {
+            if (d.pin[s]) CK(d, cudaFreeHost(d.pin[s]));
+            d.pin[s] = nullptr;
+            d.pin_cap[s] = 0;
+            size_t cap = staged_result_bytes + staged_result_bytes / 8 + 4096;
+            CK(d, cudaHostAlloc(&d.pin[s], cap, cudaHostAllocDefault));
+            d.pin_cap[s] = cap;
+        }
+        pin_used = 0;
+        return 0;
+    }
+    int h2d(void *dst, const void *src, size_t bytes) {
+        if (bytes) CK(d, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.cp));
+        return 0;
+    }
+    int inputs_ready() {
+        int s = set();
+        CK(d, cudaEventRecord(d.ev_in[s], d.cp));
+        CK(d, cudaStreamWaitEvent(d.st, d.ev_in[s], 0));
+        return 0;
+    }
+    int d2h(uint8_t *host, bool pinned, const uint8_t *dev, size_t bytes) {
+        if (!bytes) return 0;
+        if (pinned) {
+            CK(d, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d.st));
+            return 0;
+        }
+        int s = set();
+        CK(d, cudaMemcpyAsync((uint8_t *)d.pin[s] + pin_used, dev, bytes, cudaMemcpyDeviceToHost, d.st));
+        pend[s].push_back({host, pin_used, bytes});
+        pin_used += (bytes + 63) & ~(size_t)63;
+        return 0;
+    }
+    int end() {
+        CK(d, cudaEventRecord(d.ev_out[set()], d.st));
+        k++;
+        return 0;
+    }
+    int finish() {
+        // the last two chunks, oldest first
+        for (int j = 0; j < 2; j++) {
+            int s = (int)((k + j) & 1);
+            if (k + j >= 2)
+                if (int rc = deliver(s)) return rc;
+        }
+        CK(d, cudaStreamSynchronize(d.st));
+        return 0;
+    }
+};
+inline size_t pad64(size_t b) { return (b + 63) & ~(size_t)63; }
+
+// stage messages [lo, hi) of a host blob into staging set `set` on the copy stream: the byte range and the offsets
+int stage_msgs(Dev &d, Pipe *pipe, const uint8_t *msgs, const uint64_t *offsets, size_t lo, size_t hi, const uint8_t **d_msgs,
+               const uint64_t **d_off, uint64_t *base) {
     uint64_t b0 = offsets[lo], b1 = offsets[hi];
     uint8_t *dm; uint64_t *dof;
-    if (int rc = ensure_t(d, S_MSGS, (size_t)(b1 - b0) + 16, &dm)) return rc;
-    if (int rc = ensure_t(d, S_OFF, hi - lo + 1, &dof)) return rc;
-    if (b1 > b0) CK(d, cudaMemcpyAsync(dm, msgs + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, d.st));
-    CK(d, cudaMemcpyAsync(dof, offsets + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
+    int set = pipe ? pipe->set() : 0;
+    cudaStream_t st = pipe ? d.cp : d.st;
+    if (int rc = ensure_t(d, stage_buf(S_MSGS, set), (size_t)(b1 - b0) + 16, &dm)) return rc;
+    if (int rc = ensure_t(d, stage_buf(S_OFF, set), hi - lo + 1, &dof)) return rc;
+    if (b1 > b0) CK(d, cudaMemcpyAsync(dm, msgs + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+    CK(d, cudaMemcpyAsync(dof, offsets + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     *d_msgs = dm;
     *d_off = dof;
     *base = b0;
@@ -613,22 +785,27 @@ int host_hash(bn254_ctx *ctx, int group, int count, const uint8_t *msgs, const u
     if (int rc = check_offsets(ctx, offsets, n)) return rc;
     size_t rec = group == 1 ? 64 : 128;
     size_t chunk = ctx->chunk;
+    const bool pin_out = host_ptr_is_pinned(out), pin_st = status && host_ptr_is_pinned(status);
     return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
         const uint8_t *ddst; uint32_t dlen;
         if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        Pipe pipe(d);
         for (size_t c = lo; c < hi; c += chunk) {
             size_t e = std::min(hi, c + chunk), m = e - c;
+            if (int rc = pipe.begin((pin_out ? 0 : pad64(m * rec)) + (pin_st ? 0 : pad64(m)))) return rc;
             const uint8_t *dm; const uint64_t *dof; uint64_t base;
-            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            if (int rc = stage_msgs(d, &pipe, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
             uint8_t *dout, *dst_status;
-            if (int rc = ensure_t(d, S_OUT, m * rec, &dout)) return rc;
-            if (int rc = ensure_t(d, S_STATUS, m, &dst_status)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m * rec, &dout)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_STATUS, pipe.set()), m, &dst_status)) return rc;
             if (int rc = dev_hash_wire(d, group, dm, dof, base, m, ddst, dlen, count, dout, dst_status)) return rc;
-            CK(d, cudaMemcpyAsync(out + c * rec, dout, m * rec, cudaMemcpyDeviceToHost, d.st));
-            if (status) CK(d, cudaMemcpyAsync(status + c, dst_status, m, cudaMemcpyDeviceToHost, d.st));
-            CK(d, cudaStreamSynchronize(d.st));
+            if (int rc = pipe.d2h(out + c * rec, pin_out, dout, m * rec)) return rc;
+            if (status)
+                if (int rc = pipe.d2h(status + c, pin_st, dst_status, m)) return rc;
+            if (int rc = pipe.end()) return rc;
         }
-        return 0;
+        return pipe.finish();
     });
 }
 
@@ -640,24 +817,29 @@ int host_map(bn254_ctx *ctx, size_t n, const uint8_t *in_a, size_t rec_a, const 
     if (n == 0) return 0;
     if (!in_a || !out) return fail_arg(ctx, "null pointer");
     size_t chunk = ctx->chunk;
+    const bool pin_out = host_ptr_is_pinned(out), pin_st = status && host_ptr_is_pinned(status);
     return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
+        Pipe pipe(d);
         for (size_t c = lo; c < hi; c += chunk) {
             size_t e = std::min(hi, c + chunk), m = e - c;
+            if (int rc = pipe.begin((pin_out ? 0 : pad64(m * rec_out)) + (pin_st ? 0 : pad64(m)))) return rc;
             uint8_t *da, *db = nullptr, *dout, *dstat;
-            if (int rc = ensure_t(d, S_IN_A, m * rec_a, &da)) return rc;
-            CK(d, cudaMemcpyAsync(da, in_a + c * rec_a, m * rec_a, cudaMemcpyHostToDevice, d.st));
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), m * rec_a, &da)) return rc;
+            if (int rc = pipe.h2d(da, in_a + c * rec_a, m * rec_a)) return rc;
             if (in_b) {
-                if (int rc = ensure_t(d, S_IN_B, m * rec_b, &db)) return rc;
-                CK(d, cudaMemcpyAsync(db, in_b + c * rec_b, m * rec_b, cudaMemcpyHostToDevice, d.st));
+                if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rec_b, &db)) return rc;
+                if (int rc = pipe.h2d(db, in_b + c * rec_b, m * rec_b)) return rc;
             }
-            if (int rc = ensure_t(d, S_OUT, m * rec_out, &dout)) return rc;
-            if (int rc = ensure_t(d, S_STATUS, m, &dstat)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m * rec_out, &dout)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_STATUS, pipe.set()), m, &dstat)) return rc;
             if (int rc = fn(d, da, db, m, dout, dstat)) return rc;
-            CK(d, cudaMemcpyAsync(out + c * rec_out, dout, m * rec_out, cudaMemcpyDeviceToHost, d.st));
-            if (status) CK(d, cudaMemcpyAsync(status + c, dstat, m, cudaMemcpyDeviceToHost, d.st));
-            CK(d, cudaStreamSynchronize(d.st));
+            if (int rc = pipe.d2h(out + c * rec_out, pin_out, dout, m * rec_out)) return rc;
+            if (status)
+                if (int rc = pipe.d2h(status + c, pin_st, dstat, m)) return rc;
+            if (int rc = pipe.end()) return rc;
         }
-        return 0;
+        return pipe.finish();
     });
 }
 
@@ -708,6 +890,11 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking);
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+            e = cudaEventCreateWithFlags(&d.ev_in[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_out[k], cudaEventDisableTiming);
+        }
         if (e != cudaSuccess) {
             int rc = BN254_ERR_CUDA_BASE - (int)e;
             bn254_ctx_destroy(ctx);
@@ -741,8 +928,91 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
         long v = atol(s);
         if (v > 0) ctx->chunk = (size_t)v;
     }
+    if (const char *s = getenv("BN254_LANES")) {  // shape of the pairing kernels: 0 per launch, 1 one thread, 2 lane pair
+        long v = atol(s);
+        if (v >= 0 && v <= 2)
+            for (auto &d : ctx->devs) d.shape = (int)v;
+    }
+    // Several devices in one process: one NCCL communicator per device for the aggregate path's all-gather.  A box without
+    // libnccl still gets a working ctx for everything that needs no exchange; the aggregate calls then fail with -200.
+    if (ctx->devs.size() > 1 && bn_nccl::api().ok()) {
+        std::vector<bn_nccl::comm_t> comms(ctx->devs.size());
+        std::vector<int> ids;
+        for (auto &d : ctx->devs) ids.push_back(d.id);
+        int r = bn_nccl::api().CommInitAll(comms.data(), (int)ids.size(), ids.data());
+        if (r != bn_nccl::kSuccess) {
+            bn254_ctx_destroy(ctx);
+            return BN254_ERR_NCCL_BASE - r;
+        }
+        for (size_t g = 0; g < ctx->devs.size(); g++) {
+            ctx->devs[g].comm = comms[g];
+            ctx->devs[g].nranks = (int)ctx->devs.size();
+            ctx->devs[g].rank = (int)g;
+        }
+    }
     *out = ctx;
     return 0;
+}
+
+int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value) {
+    if (!ctx || !name) return BN254_ERR_ARG;
+    std::string k(name);
+    if (k == "lanes" && value >= 0 && value <= 2) {
+        for (auto &d : ctx->devs) d.shape = (int)value;
+    } else if (k == "chunk" && value > 0) {
+        ctx->chunk = (size_t)value;
+    } else if (k == "split" && value >= 1 && value <= Dev::MAXSUB) {
+        for (auto &d : ctx->devs) d.nsub = (int)value;
+    } else {
+        return fail_arg(ctx, "unknown option or value out of range (lanes 0..2, chunk > 0, split 1..8)");
+    }
+    return 0;
+}
+
+// ---- NCCL communicator of a one-device ctx (one process per GPU: torchrun, MPI, ...) -------------------------------
+int bn254_comm_unique_id(uint8_t *out) {
+    if (!out) return BN254_ERR_ARG;
+    if (!bn_nccl::api().ok()) return BN254_ERR_NCCL_BASE;
+    bn_nccl::unique_id id;
+    int r = bn_nccl::api().GetUniqueId(&id);
+    if (r != bn_nccl::kSuccess) return BN254_ERR_NCCL_BASE - r;
+    memcpy(out, id.internal, BN254_COMM_ID_BYTES);
+    return 0;
+}
+int bn254_comm_init_rank(bn254_ctx *ctx, const uint8_t *id_bytes, int nranks, int rank) {
+    if (!ctx || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return fail_arg(ctx, "bad communicator arguments");
+    if (ctx->devs.size() != 1) return fail_arg(ctx, "bn254_comm_init_rank needs a one-device ctx (a multi-device ctx owns its communicators)");
+    Dev &d = ctx->devs[0];
+    if (d.comm) return fail_arg(ctx, "communicator already initialised");
+    if (!bn_nccl::api().ok()) {
+        ctx->err = bn_nccl::api().why ? bn_nccl::api().why : "NCCL unavailable";
+        return BN254_ERR_NCCL_BASE;
+    }
+    cudaSetDevice(d.id);
+    bn_nccl::unique_id id;
+    memcpy(id.internal, id_bytes, BN254_COMM_ID_BYTES);
+    int r = bn_nccl::api().CommInitRank(&d.comm, nranks, id, rank);
+    if (r != bn_nccl::kSuccess) {
+        d.comm = nullptr;
+        ctx->err = std::string("ncclCommInitRank: ") + bn_nccl::api().GetErrorString(r);
+        return BN254_ERR_NCCL_BASE - r;
+    }
+    d.nranks = nranks;
+    d.rank = rank;
+    return 0;
+}
+int bn254_comm_nranks(const bn254_ctx *ctx) { return ctx ? ctx->devs[0].nranks : 0; }
+
+// pin / unpin caller memory so that the chunk pipeline's copies are asynchronous (cudaHostRegister)
+int bn254_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return BN254_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    return e == cudaSuccess ? 0 : BN254_ERR_CUDA_BASE - (int)e;
+}
+int bn254_host_unregister(void *p) {
+    if (!p) return BN254_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? 0 : BN254_ERR_CUDA_BASE - (int)e;
 }
 
 void bn254_ctx_destroy(bn254_ctx *ctx) {
@@ -761,6 +1031,20 @@ void bn254_ctx_destroy(bn254_ctx *ctx) {
         if (d.hi) cudaStreamDestroy(d.hi);
         if (d.ev_hi_fork) cudaEventDestroy(d.ev_hi_fork);
         if (d.ev_hi_join) cudaEventDestroy(d.ev_hi_join);
+        if (d.cp) {
+            cudaStreamSynchronize(d.cp);
+            cudaStreamDestroy(d.cp);
+        }
+        for (int k = 0; k < 2; k++) {
+            if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
+            if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
+            if (d.pin[k]) cudaFreeHost(d.pin[k]);
+        }
+        for (auto &r : d.recs) {
+            if (r.e0) cudaEventDestroy(r.e0);
+            if (r.e1) cudaEventDestroy(r.e1);
+        }
+        if (d.comm && bn_nccl::api().ok()) bn_nccl::api().CommDestroy(d.comm);
         if (d.st) cudaStreamDestroy(d.st);
     }
     delete ctx;
@@ -779,23 +1063,25 @@ int bn254_profile_enable(bn254_ctx *ctx, int on) {
     for (auto &d : ctx->devs) d.prof = on != 0;
     return 0;
 }
-// Drains the recorded launches of the first device into `buf` as lines "kernel items ms\n".
+// Drains the recorded launches of every device (device order) into `buf` as lines "kernel items ms\n".
 int bn254_profile_drain(bn254_ctx *ctx, char *buf, size_t cap) {
     if (!ctx || !buf || cap == 0) return BN254_ERR_ARG;
-    Dev &d = ctx->devs[0];
-    cudaSetDevice(d.id);
-    cudaStreamSynchronize(d.st);
     std::string out;
-    for (auto &r : d.recs) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, r.e0, r.e1);
-        cudaEventDestroy(r.e0);
-        cudaEventDestroy(r.e1);
-        char line[160];
-        snprintf(line, sizeof line, "%s %zu %.6f\n", r.name, r.items, ms);
-        out += line;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaStreamSynchronize(d.st);
+        for (auto &r : d.recs) {
+            float ms = 0;
+            if (r.e0 && r.e1 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+                char line[160];
+                snprintf(line, sizeof line, "%s %zu %.6f\n", r.name, r.items, ms);
+                out += line;
+            }
+            if (r.e0) cudaEventDestroy(r.e0);
+            if (r.e1) cudaEventDestroy(r.e1);
+        }
+        d.recs.clear();
     }
-    d.recs.clear();
     if (out.size() + 1 > cap) return BN254_ERR_ARG;
     memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
@@ -928,24 +1214,28 @@ int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const ui
     if (int rc = check_offsets(ctx, offsets, n)) return rc;
     size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
     size_t chunk = ctx->chunk;
+    const bool pin_ok = host_ptr_is_pinned(ok);
     return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
         const uint8_t *ddst; uint32_t dlen;
         if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        Pipe pipe(d);
         for (size_t c = lo; c < hi; c += chunk) {
             size_t e = std::min(hi, c + chunk), m = e - c;
+            if (int rc = pipe.begin(pin_ok ? 0 : pad64(m))) return rc;
             const uint8_t *dm; const uint64_t *dof; uint64_t base;
-            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            if (int rc = stage_msgs(d, &pipe, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
             uint8_t *dpk, *dsig, *dok;
-            if (int rc = ensure_t(d, S_IN_A, m * rpk, &dpk)) return rc;
-            if (int rc = ensure_t(d, S_IN_B, m * rsig, &dsig)) return rc;
-            if (int rc = ensure_t(d, S_OUT, m, &dok)) return rc;
-            CK(d, cudaMemcpyAsync(dpk, pks + c * rpk, m * rpk, cudaMemcpyHostToDevice, d.st));
-            CK(d, cudaMemcpyAsync(dsig, sigs + c * rsig, m * rsig, cudaMemcpyHostToDevice, d.st));
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), m * rpk, &dpk)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rsig, &dsig)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m, &dok)) return rc;
+            if (int rc = pipe.h2d(dpk, pks + c * rpk, m * rpk)) return rc;
+            if (int rc = pipe.h2d(dsig, sigs + c * rsig, m * rsig)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
             if (int rc = dev_verify(d, variant, dpk, dm, dof, base, dsig, m, ddst, dlen, flags, dok)) return rc;
-            CK(d, cudaMemcpyAsync(ok + c, dok, m, cudaMemcpyDeviceToHost, d.st));
-            CK(d, cudaStreamSynchronize(d.st));
+            if (int rc = pipe.d2h(ok + c, pin_ok, dok, m)) return rc;
+            if (int rc = pipe.end()) return rc;
         }
-        return 0;
+        return pipe.finish();
     });
 }
 
@@ -962,6 +1252,7 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
     size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
     size_t nseg = (n + group - 1) / group;
     size_t chunk_groups = std::max<size_t>(1, ctx->chunk / group);   // a group never straddles two chunks
+    const bool pin_ok = host_ptr_is_pinned(ok_groups);
     // groups (not tuples) are what the devices share out
     return run_sharded(ctx, nseg, [=](Dev &d, size_t glo, size_t ghi) -> int {
         const uint8_t *ddst; uint32_t dlen;
@@ -969,45 +1260,46 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
         uint8_t *dseed;
         if (int rc = ensure_t(d, S_RB_SEED, 32, &dseed)) return rc;
         CK(d, cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, d.st));
+        Pipe pipe(d);
         for (size_t g = glo; g < ghi; g += chunk_groups) {
             size_t ge = std::min(ghi, g + chunk_groups);
             size_t c = g * group, e = std::min(n, ge * group), m = e - c;
+            if (int rc = pipe.begin(pin_ok ? 0 : pad64(ge - g))) return rc;
             const uint8_t *dm; const uint64_t *dof; uint64_t base;
-            if (int rc = stage_msgs(d, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            if (int rc = stage_msgs(d, &pipe, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
             uint8_t *dpk, *dsig, *dok;
-            if (int rc = ensure_t(d, S_IN_A, m * rpk, &dpk)) return rc;
-            if (int rc = ensure_t(d, S_IN_B, m * rsig, &dsig)) return rc;
-            if (int rc = ensure_t(d, S_OUT, ge - g, &dok)) return rc;
-            CK(d, cudaMemcpyAsync(dpk, pks + c * rpk, m * rpk, cudaMemcpyHostToDevice, d.st));
-            CK(d, cudaMemcpyAsync(dsig, sigs + c * rsig, m * rsig, cudaMemcpyHostToDevice, d.st));
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), m * rpk, &dpk)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rsig, &dsig)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), ge - g, &dok)) return rc;
+            if (int rc = pipe.h2d(dpk, pks + c * rpk, m * rpk)) return rc;
+            if (int rc = pipe.h2d(dsig, sigs + c * rsig, m * rsig)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
             if (int rc = dev_verify_rand(d, variant, dpk, dm, dof, base, dsig, m, group, dseed, (uint64_t)c, rand_bits, ddst, dlen, flags, dok))
                 return rc;
-            CK(d, cudaMemcpyAsync(ok_groups + g, dok, ge - g, cudaMemcpyDeviceToHost, d.st));
-            CK(d, cudaStreamSynchronize(d.st));
+            if (int rc = pipe.d2h(ok_groups + g, pin_ok, dok, ge - g)) return rc;
+            if (int rc = pipe.end()) return rc;
         }
-        return 0;
+        return pipe.finish();
     });
 }
 
-int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
-                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
-    if (!ctx) return BN254_ERR_ARG;
-    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
-    if (!partial || !bad || (n && (!pks || !offsets))) return fail_arg(ctx, "null pointer");
-    if (n)
-        if (int rc = check_offsets(ctx, offsets, n)) return rc;
+namespace {
+// Every device of the ctx reduces its contiguous slice of the (pk_i, m_i) pairs to ONE record in its NCCL send buffer
+// (device 0 -- rank 0 of a one-process-per-GPU job -- also takes the aggregate signature), the records are all-gathered
+// over NVLink (one ncclAllGather per device inside one NCCL group), and the devices end with every rank's record in
+// S_AGG_RECV.  Host threads: one per device for the shard, the caller's thread for the collective.
+int aggregate_shards_gathered(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                              const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags) {
     size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
     size_t nd = ctx->devs.size();
-    std::vector<uint8_t> parts(nd * 384), bads(nd, 0);
     static const uint64_t zero_off[1] = {0};
     const uint64_t *offs = n ? offsets : zero_off;
-    // every device takes a contiguous slice; device 0 also takes the aggregate signature
     std::vector<std::thread> th;
     for (size_t g = 0; g < nd; g++) {
         size_t lo = n * g / nd, hi = n * (g + 1) / nd;
         Dev *d = &ctx->devs[g];
         d->rc = 0;
-        auto work = [=, &parts, &bads]() {
+        auto work = [=]() {
             cudaSetDevice(d->id);
             d->rc = [&]() -> int {
                 Dev &dd = *d;
@@ -1015,20 +1307,17 @@ int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, con
                 const uint8_t *ddst; uint32_t dlen;
                 if (int rc = stage_dst(dd, dst, dst_len, true, &ddst, &dlen)) return rc;
                 const uint8_t *dm; const uint64_t *dof; uint64_t base;
-                if (int rc = stage_msgs(dd, msgs, offs, lo, hi, &dm, &dof, &base)) return rc;
-                uint8_t *dpk, *dsig = nullptr, *dout;
+                if (int rc = stage_msgs(dd, nullptr, msgs, offs, lo, hi, &dm, &dof, &base)) return rc;
+                uint8_t *dpk, *dsig = nullptr;
+                agg_rec *send;
                 if (int rc = ensure_t(dd, S_IN_A, m * rpk + 16, &dpk)) return rc;
-                if (int rc = ensure_t(dd, S_OUT, 384 + 16, &dout)) return rc;
+                if (int rc = ensure_t(dd, S_AGG_SEND, 1, &send)) return rc;
                 if (m) CK(dd, cudaMemcpyAsync(dpk, pks + lo * rpk, m * rpk, cudaMemcpyHostToDevice, dd.st));
                 if (g == 0 && agg_sig) {
                     if (int rc = ensure_t(dd, S_IN_B, rsig, &dsig)) return rc;
                     CK(dd, cudaMemcpyAsync(dsig, agg_sig, rsig, cudaMemcpyHostToDevice, dd.st));
                 }
-                if (int rc = dev_aggregate_partial(dd, variant, dpk, dm, dof, base, m, dsig, ddst, dlen, flags, dout, dout + 384)) return rc;
-                CK(dd, cudaMemcpyAsync(&parts[g * 384], dout, 384, cudaMemcpyDeviceToHost, dd.st));
-                CK(dd, cudaMemcpyAsync(&bads[g], dout + 384, 1, cudaMemcpyDeviceToHost, dd.st));
-                CK(dd, cudaStreamSynchronize(dd.st));
-                return 0;
+                return dev_aggregate_rec(dd, variant, dpk, dm, dof, base, m, dsig, ddst, dlen, flags, send);
             }();
         };
         if (nd == 1) work();
@@ -1040,15 +1329,74 @@ int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, con
             ctx->err = d.err;
             return d.rc;
         }
-    if (nd == 1) {
-        memcpy(partial, parts.data(), 384);
-        *bad = bads[0] ? 1 : 0;
-        return 0;
+    // the exchange: every device's all-gather inside one NCCL group (a lone device without a communicator copies)
+    const bool grouped = nd > 1;
+    if (grouped) {
+        if (int rc = need_comm(ctx->devs[0])) {
+            ctx->err = ctx->devs[0].err;
+            return rc;
+        }
+        bn_nccl::api().GroupStart();
     }
-    uint8_t b = 0;
-    for (auto x : bads) b |= x;
-    *bad = b ? 1 : 0;
-    return bn254_fp12_product(ctx, parts.data(), nd, partial);
+    int rc = 0;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        agg_rec *recv;
+        rc = dev_gather_recs(d, (const agg_rec *)d.bufs[S_AGG_SEND].p, &recv);
+        if (rc) {
+            ctx->err = d.err;
+            break;
+        }
+    }
+    if (grouped) {
+        int r = bn_nccl::api().GroupEnd();
+        if (!rc && r != bn_nccl::kSuccess) {
+            ctx->err = std::string("ncclGroupEnd: ") + bn_nccl::api().GetErrorString(r);
+            rc = BN254_ERR_NCCL_BASE - r;
+        }
+    }
+    return rc;
+}
+}  // namespace
+
+int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial, uint8_t *bad) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (!partial || !bad || (n && (!pks || !offsets))) return fail_arg(ctx, "null pointer");
+    if (n)
+        if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    // A multi-device ctx is ONE shard towards its caller: its devices' records are gathered (NCCL) and device 0 multiplies them.
+    // A one-device ctx must not touch its job-level communicator here (the other ranks are not in this call).
+    Dev &d = ctx->devs[0];
+    const int keep_ranks = d.nranks;
+    bn_nccl::comm_t keep_comm = d.comm;
+    if (ctx->devs.size() == 1) { d.nranks = 1; d.comm = nullptr; }
+    int rc = aggregate_shards_gathered(ctx, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags);
+    const int k = d.nranks;
+    d.nranks = keep_ranks;
+    d.comm = keep_comm;
+    if (rc) return rc;
+    cudaSetDevice(d.id);
+    auto body = [&]() -> int {
+        fp12 *prod; int *dbad; uint8_t *dout;
+        if (int rc2 = ensure_t(d, S_F2, 4, &prod)) return rc2;
+        if (int rc2 = ensure_t(d, S_BAD, 4, &dbad)) return rc2;
+        if (int rc2 = ensure_t(d, S_OUT, 384 + 16, &dout)) return rc2;
+        CK(d, cudaMemsetAsync(dbad, 0, sizeof(int), d.st));
+        LAUNCH(d, k_gather_product_l2, 32, 32, prod, dbad, (const agg_rec *)d.bufs[S_AGG_RECV].p, k);
+        LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, prod, (const uint8_t *)nullptr, (size_t)1);
+        int hbad = 0;
+        CK(d, cudaMemcpyAsync(partial, dout, 384, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaMemcpyAsync(&hbad, dbad, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        *bad = hbad ? 1 : 0;
+        return 0;
+    };
+    rc = body();
+    if (rc) ctx->err = d.err;
+    if (!rc) return bn254_sync(ctx);   // the other devices' gathers
+    return rc;
 }
 
 int bn254_aggregate_finish(bn254_ctx *ctx, const uint8_t *partials, const uint8_t *bad, size_t kparts, uint8_t *ok) {
@@ -1078,17 +1426,69 @@ int bn254_aggregate_finish(bn254_ctx *ctx, const uint8_t *partials, const uint8_
     return rc;
 }
 
+// One call = the whole predicate on this ctx's devices: shards -> all-gather -> ONE post-gather kernel on device 0.
 int bn254_aggregate_verify(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                            const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
     if (!ctx || !agg_sig || !ok) return fail_arg(ctx, "null pointer");
-    uint8_t partial[384], bad = 0;
-    int rc = bn254_aggregate_partial(ctx, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags, partial, &bad);
-    if (rc == BN254_ERR_INVALID_GT_BYTES) {  // cannot happen for library-produced partials
-        *ok = 0;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (n && (!pks || !offsets)) return fail_arg(ctx, "null pointer");
+    if (n)
+        if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    Dev &d = ctx->devs[0];
+    const int keep_ranks = d.nranks;
+    bn_nccl::comm_t keep_comm = d.comm;
+    if (ctx->devs.size() == 1) { d.nranks = 1; d.comm = nullptr; }   // a lone-device ctx verifies the whole aggregate itself
+    int rc = aggregate_shards_gathered(ctx, variant, pks, msgs, offsets, n, agg_sig, dst, dst_len, flags);
+    auto body = [&]() -> int {
+        uint8_t *dok;
+        if (int rc2 = ensure_t(d, S_OUT, 16, &dok)) return rc2;
+        if (int rc2 = dev_gather_finish(d, (const agg_rec *)d.bufs[S_AGG_RECV].p, dok)) return rc2;
+        uint8_t h = 0;
+        CK(d, cudaMemcpyAsync(&h, dok, 1, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        *ok = h;
         return 0;
+    };
+    if (!rc) {
+        cudaSetDevice(d.id);
+        rc = body();
+        if (rc) ctx->err = d.err;
     }
+    d.nranks = keep_ranks;
+    d.comm = keep_comm;
+    if (!rc) return bn254_sync(ctx);
+    return rc;
+}
+
+// The same predicate for a job of one process per GPU (torchrun / MPI): EVERY rank calls this with ITS shard of the
+// (pk_i, m_i) pairs; agg_sig is read on rank 0 only (may be NULL elsewhere).  One ncclAllGather of 400 bytes per rank on
+// the library stream, then every rank runs the post-gather kernel, so *ok is the job's verdict on every rank.
+int bn254_aggregate_verify_dist(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    if (!ctx || !ok) return fail_arg(ctx, "null pointer");
+    if (ctx->devs.size() != 1) return fail_arg(ctx, "bn254_aggregate_verify_dist needs a one-device ctx");
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (n && (!pks || !offsets)) return fail_arg(ctx, "null pointer");
+    Dev &d = ctx->devs[0];
+    if (d.rank == 0 && !agg_sig) return fail_arg(ctx, "rank 0 needs the aggregate signature");
+    if (n)
+        if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    int rc = aggregate_shards_gathered(ctx, variant, pks, msgs, offsets, n, d.rank == 0 ? agg_sig : nullptr, dst, dst_len, flags);
     if (rc) return rc;
-    return bn254_aggregate_finish(ctx, partial, &bad, 1, ok);
+    cudaSetDevice(d.id);
+    auto body = [&]() -> int {
+        uint8_t *dok;
+        if (int rc2 = ensure_t(d, S_OUT, 16, &dok)) return rc2;
+        if (int rc2 = dev_gather_finish(d, (const agg_rec *)d.bufs[S_AGG_RECV].p, dok)) return rc2;
+        uint8_t h = 0;
+        CK(d, cudaMemcpyAsync(&h, dok, 1, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        *ok = h;
+        return 0;
+    };
+    rc = body();
+    if (rc) ctx->err = d.err;
+    return rc;
 }
 
 // ---- codecs / predicates / scalar multiplication ---------------------------------------------------
@@ -1316,6 +1716,27 @@ int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks,
     DEV_EPILOGUE(rc);
 }
 
+// device-resident form of bn254_aggregate_verify_dist: everything (shard, all-gather, post-gather kernel) is enqueued on
+// bn254_stream(ctx); *ok (device byte) holds the job's verdict on every rank once the stream has drained
+int bn254_aggregate_verify_dist_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                    const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    DEV_PROLOGUE();
+    if (ctx->devs.size() != 1) return fail_arg(ctx, "needs a one-device ctx");
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (d.rank == 0 && !agg_sig) return fail_arg(ctx, "rank 0 needs the aggregate signature");
+    auto body = [&]() -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        agg_rec *send, *recv;
+        if (int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen)) return rc;
+        if (int rc = ensure_t(d, S_AGG_SEND, 1, &send)) return rc;
+        if (int rc = dev_aggregate_rec(d, variant, pks, msgs, offsets, 0, n, d.rank == 0 ? agg_sig : nullptr, ddst, dlen, flags, send)) return rc;
+        if (int rc = dev_gather_recs(d, send, &recv)) return rc;
+        return dev_gather_finish(d, recv, ok);
+    };
+    int rc = body();
+    DEV_EPILOGUE(rc);
+}
+
 int bn254_imad_peak(bn254_ctx *ctx, int mode, int iters, double *ops_per_s, double *ms_out) {
     DEV_PROLOGUE();
     if (iters < 1 || !ops_per_s) return fail_arg(ctx, "bad argument");
@@ -1384,133 +1805,3 @@ int bn254_fp_peak(bn254_ctx *ctx, int mode, int warps_per_sm, int iters, double 
 }
 
 }  // extern "C"
-
-#ifdef BN_DEBUG_API
-// ---- debug-only entry points (not part of the ABI; built with -DBN_DEBUG_API for bring-up) ----------
-namespace {
-__global__ void k_dbg_svdw_g2(uint8_t *out, const uint8_t *u, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fp2 x;
-    fp_from_be(x.c0, u + 64 * i);
-    fp_from_be(x.c1, u + 64 * i + 32);
-    g2a q;
-    bool ok = svdw_g2(q, x);
-    if (ok) g2a_to_bytes(out + 128 * i, q);
-    else zero_bytes(out + 128 * i, 128);
-}
-__global__ void k_dbg_clear_g2(uint8_t *out, const uint8_t *in, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g2a a;
-    g2a_from_bytes(a, in + 128 * i);
-    g2p p;
-    pt_from_affine(p, a.x, a.y, false);
-    g2_clear_cofactor(p, p);
-    pt_to_affine(a.x, a.y, a.inf, p);
-    g2a_to_bytes(out + 128 * i, a);
-}
-__global__ void k_dbg_h2f_g2(uint8_t *out, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len) {
-    if (threadIdx.x || blockIdx.x) return;
-    uint8_t okm[192];
-    expand_message_xmd(okm, 192, msg, len, dst, dst_len);
-    for (int k = 0; k < 4; k++) {
-        fp u;
-        fp_from_okm(u, okm + 48 * k);
-        fp_to_be(out + 32 * k, u);
-    }
-}
-// whole hash_to_g2 (count 1) with intermediates: out = u (64) || q (128) || cleared (128) || library result (128)
-__global__ void k_dbg_hash_g2(uint8_t *out, const uint8_t *msg, size_t len, const uint8_t *dst, uint32_t dst_len) {
-    if (threadIdx.x || blockIdx.x) return;
-    uint8_t okm[192];
-    fp2 u;
-    g2a q;
-    g2p a;
-    expand_message_xmd(okm, 96, msg, len, dst, dst_len);
-    fp_from_okm(u.c0, okm);
-    fp_from_okm(u.c1, okm + 48);
-    fp_to_be(out, u.c0);
-    fp_to_be(out + 32, u.c1);
-    bool ok = svdw_g2(q, u);
-    g2a_to_bytes(out + 64, q);
-    pt_from_affine(a, q.x, q.y, false);
-    g2_clear_cofactor(a, a);
-    g2a r;
-    pt_to_affine(r.x, r.y, r.inf, a);
-    g2a_to_bytes(out + 192, r);
-    // primitives on q: [x]q, psi(q), 2q, q + psi(q)   (each to affine) at out + 512 ...
-    {
-        g2p P, R;
-        g2a A;
-        const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
-        pt_from_affine(P, q.x, q.y, false);
-        pt_mul(R, P, xw, 63);
-        pt_to_affine(A.x, A.y, A.inf, R);
-        g2a_to_bytes(out + 512, A);
-        g2_psi(R, P);
-        pt_to_affine(A.x, A.y, A.inf, R);
-        g2a_to_bytes(out + 640, A);
-        pt_dbl(R, P);
-        pt_to_affine(A.x, A.y, A.inf, R);
-        g2a_to_bytes(out + 768, A);
-        g2p S;
-        g2_psi(S, P);
-        pt_add(R, P, S);
-        pt_to_affine(A.x, A.y, A.inf, R);
-        g2a_to_bytes(out + 896, A);
-    }
-    {   // Fp2 primitives on (q.x, q.y), 64 bytes each (c0 || c1) at out + 1024 + 64 k
-        fp2 r;
-        uint8_t *o = out + 1024;
-#define DUMP(k) fp_to_be(o + 64 * (k), r.c0); fp_to_be(o + 64 * (k) + 32, r.c1);
-        fp2_inv(r, q.x); DUMP(0)
-        fp2_mul(r, q.x, q.y); DUMP(1)
-        fp2_sqr(r, q.x); DUMP(2)
-        fp2_add(r, q.x, q.y); DUMP(3)
-        fp2_sub(r, q.x, q.y); DUMP(4)
-        fp2_neg(r, q.x); DUMP(5)
-        fp2_conj(r, q.x); DUMP(6)
-        fp2_mul_xi(r, q.x); DUMP(7)
-        fp_inv(r.c0, q.x.c0); fp_set_zero(r.c1); DUMP(8)
-        r = q.x; fp2_inv(r, r); DUMP(9)
-        fp2_mul(r, q.x, kfp2(k::B2_3)); DUMP(10)
-        fp2_dbl(r, q.x); DUMP(11)
-        r = q.x; fp2_add(r, r, r); DUMP(12)
-        r = q.x; fp2_mul(r, q.y, r); DUMP(13)
-        r = q.x; fp2_mul(r, r, q.y); DUMP(14)
-        r = q.x; fp2_sqr(r, r); DUMP(15)
-        r = q.x; fp2_sub(r, q.y, r); DUMP(16)
-        r = q.x; fp2_mul(r, r, kfp2(k::B2_3)); DUMP(17)
-        r = q.x; fp2_add(r, q.y, r); DUMP(18)
-        r = q.x; fp2_mul(r, r, r); DUMP(19)
-    }
-    g2a h;
-    int count = (int)out[511];  // runtime value (the host passes it here) so nothing is constant-folded
-    bool ok2 = hash_to_g2(h, msg, len, dst, dst_len, count);
-    g2a_to_bytes(out + 320, h);
-    out[448] = ok;
-    out[449] = ok2;
-}
-}  // namespace
-extern "C" int bn254_debug(bn254_ctx *ctx, int what, const uint8_t *in, size_t n, const uint8_t *dst, size_t dst_len, uint8_t *out) {
-    Dev &d = ctx->devs[0];
-    cudaSetDevice(d.id);
-    size_t rin = what == 0 ? 64 : (what == 1 ? 128 : 1), rout = 128;
-    uint8_t *din, *dout, *ddst;
-    cudaMalloc(&din, n * rin + 16);
-    cudaMalloc(&dout, (what >= 2 ? 24 : n) * rout);
-    cudaMalloc(&ddst, dst_len + 16);
-    cudaMemcpy(din, in, n * rin, cudaMemcpyHostToDevice);
-    if (what == 3) cudaMemcpy(dout, out, 512, cudaMemcpyHostToDevice);
-    if (dst_len) cudaMemcpy(ddst, dst, dst_len, cudaMemcpyHostToDevice);
-    if (what == 0) k_dbg_svdw_g2<<<blocks(n, 64), 64>>>(dout, din, n);
-    else if (what == 1) k_dbg_clear_g2<<<blocks(n, 64), 64>>>(dout, din, n);
-    else if (what == 2) k_dbg_h2f_g2<<<1, 32>>>(dout, din, n, ddst, (uint32_t)dst_len);
-    else k_dbg_hash_g2<<<1, 32>>>(dout, din, n, ddst, (uint32_t)dst_len);
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaMemcpy(out, dout, (what >= 2 ? 24 : n) * rout, cudaMemcpyDeviceToHost);
-    cudaFree(din); cudaFree(dout); cudaFree(ddst);
-    return (int)e;
-}
-#endif

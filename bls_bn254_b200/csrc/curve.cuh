@@ -25,6 +25,7 @@ struct F1 {  // field policy: Fp
     static BN_INL void set_zero(T &r) { fp_set_zero(r); }
     static BN_INL void set_one(T &r) { fp_set_one(r); }
     static BN_INL void glv_beta(T &r, const T &a) { fp_mulx(r, a, kfp(k::GLV_BETA1)); }
+    static BN_INL void select(T &r, bool c, const T &a, const T &b) { fp_select(r, c, a, b); }
 };
 struct F2 {  // field policy: Fp2
     typedef fp2 T;
@@ -39,6 +40,7 @@ struct F2 {  // field policy: Fp2
     static BN_INL void set_zero(T &r) { fp2_set_zero(r); }
     static BN_INL void set_one(T &r) { fp2_set_one(r); }
     static BN_INL void glv_beta(T &r, const T &a) { fp2_mul_fp(r, a, kfp(k::GLV_BETA2)); }
+    static BN_INL void select(T &r, bool c, const T &a, const T &b) { fp2_select(r, c, a, b); }
 };
 
 template <class F>
@@ -150,8 +152,26 @@ BN_INL void pt_to_affine(typename F::T &x, typename F::T &y, bool &inf, const po
         F::set_one(y);
     }
 }
-// [k]a, k = nwords 32-bit words little-endian, MSB first double-and-add (g1.rs:821-841,
-// g2.rs:866-886 compute the same group element in constant time; inputs here are public)
+// [k]a for a SECRET k (sign, keygen: g1.rs:821-841, g2.rs:866-886 are constant time, and so is this): every one of the
+// nbits steps runs one doubling AND one complete addition, and the scalar bit only picks the result through selects, so
+// the instruction stream and every memory address are independent of k (the complete RCB law has no special cases).
+template <class F>
+BN_INL void pt_mul_ct(point<F> &r, const point<F> &a, const uint32_t *kw, int nbits) {
+    point<F> acc, t, base = a;
+    pt_set_identity(acc);
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        pt_add(t, acc, base);
+        const bool bit = ((kw[i >> 5] >> (i & 31)) & 1) != 0;
+        F::select(acc.x, bit, t.x, acc.x);
+        F::select(acc.y, bit, t.y, acc.y);
+        F::select(acc.z, bit, t.z, acc.z);
+    }
+    r = acc;
+}
+// [k]a for a PUBLIC k, k = nwords 32-bit words little-endian, MSB first double-and-add: branches on the bits of k
+// (subgroup checks, curve constants); never called with a secret
 template <class F>
 BN_INL void pt_mul(point<F> &r, const point<F> &a, const uint32_t *kw, int nbits) {
     point<F> acc, base = a;

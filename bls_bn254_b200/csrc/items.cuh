@@ -33,18 +33,26 @@ struct __attribute__((aligned(16))) g1m { fp x, y; };
 struct __attribute__((aligned(16))) g2m { fp2 x, y; };
 
 // ---- decode / encode (wire <-> internal) --------------------------------------------------------
-BN_INL void item_g1_decode(g1m &out, uint8_t &fl, const uint8_t *in, bool check_curve) {
+// `check` is a bit set: DEC_ON_CURVE = the curve equation must hold; DEC_NO_IDENTITY = a point that decodes as the identity
+// (x == 0, or y == 1: the reference's infinity convention, g1.rs:318-324 / g2.rs:329-335) is rejected like an
+// undecodable one.  The verification predicates decode public keys and signatures with DEC_NO_IDENTITY (KeyValidate of
+// the IETF BLS draft): an identity key would otherwise drop out of the Miller product and accept an identity signature
+// on every message.
+enum : int { DEC_ON_CURVE = 1, DEC_NO_IDENTITY = 4 };
+BN_INL void item_g1_decode(g1m &out, uint8_t &fl, const uint8_t *in, int check) {
     g1a a;
     bool ok = g1a_from_bytes(a, in);
-    if (ok && check_curve) ok = g1a_on_curve(a);
+    if (ok && (check & DEC_ON_CURVE)) ok = g1a_on_curve(a);
+    if (ok && (check & DEC_NO_IDENTITY) && a.inf) ok = false;
     out.x = a.x;
     out.y = a.y;
     fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
 }
-BN_INL void item_g2_decode(g2m &out, uint8_t &fl, const uint8_t *in, bool check_curve) {
+BN_INL void item_g2_decode(g2m &out, uint8_t &fl, const uint8_t *in, int check) {
     g2a a;
     bool ok = g2a_from_bytes(a, in);
-    if (ok && check_curve) ok = g2a_on_curve(a);
+    if (ok && (check & DEC_ON_CURVE)) ok = g2a_on_curve(a);
+    if (ok && (check & DEC_NO_IDENTITY) && a.inf) ok = false;
     out.x = a.x;
     out.y = a.y;
     fl = ok ? (a.inf ? FL_INF : 0) : FL_BAD;
@@ -153,7 +161,8 @@ BN_INL void item_final_exp_l2(fp12 &F) {
     fp12_store(F, f);
 }
 
-// ---- scalar multiplication (sign / keygen / test-data side; g1.rs:821-841, g2.rs:866-886) -------
+// ---- scalar multiplication (sign / keygen / test-data side; g1.rs:821-841, g2.rs:866-886): the scalar may be a
+//      secret key, so this is the constant-time ladder (curve.cuh: pt_mul_ct) ------------------------------------
 BN_INL void scalar_words(uint32_t kw[8], const uint8_t *be) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -166,7 +175,7 @@ BN_INL void item_g1_mul(g1m &out, uint8_t &flo, const g1m &p, uint8_t fl, const 
     scalar_words(kw, scalar_be);
     g1p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
-    pt_mul(r, a, kw, 256);
+    pt_mul_ct(r, a, kw, 256);
     bool inf;
     pt_to_affine(out.x, out.y, inf, r);
     flo = (fl & FL_BAD) ? FL_BAD : (inf ? FL_INF : 0);
@@ -176,7 +185,7 @@ BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const 
     scalar_words(kw, scalar_be);
     g2p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
-    pt_mul(r, a, kw, 256);
+    pt_mul_ct(r, a, kw, 256);
     bool inf;
     pt_to_affine(out.x, out.y, inf, r);
     flo = (fl & FL_BAD) ? FL_BAD : (inf ? FL_INF : 0);

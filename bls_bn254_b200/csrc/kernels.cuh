@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_decode(g1m *out, uint8_t *f
     if (i >= n) return;
     g1m p;
     uint8_t f;
-    item_g1_decode(p, f, in + 64 * i, check != 0);
+    item_g1_decode(p, f, in + 64 * i, check);
     out[i] = p;
     fl[i] = f;
 }
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_decode(g2m *out, uint8_t *f
     if (i >= n) return;
     g2m p;
     uint8_t f;
-    item_g2_decode(p, f, in + 128 * i, check != 0);
+    item_g2_decode(p, f, in + 128 * i, check);
     out[i] = p;
     fl[i] = f;
 }
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_on_curve(uint8_t *out, cons
     if (i >= n) return;
     g1m p;
     uint8_t f;
-    item_g1_decode(p, f, in + 64 * i, true);
+    item_g1_decode(p, f, in + 64 * i, DEC_ON_CURVE);
     out[i] = (f & FL_BAD) ? 0 : 1;
 }
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_on_curve(uint8_t *out, const uint8_t *in, size_t n) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_on_curve(uint8_t *out, cons
     if (i >= n) return;
     g2m p;
     uint8_t f;
-    item_g2_decode(p, f, in + 128 * i, true);
+    item_g2_decode(p, f, in + 128 * i, DEC_ON_CURVE);
     out[i] = (f & FL_BAD) ? 0 : 1;
 }
 
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_torsion_free
     if (i >= n) return;
     g1m p;
     uint8_t f;
-    item_g1_decode(p, f, in + 64 * i, true);
+    item_g1_decode(p, f, in + 64 * i, DEC_ON_CURVE);
     out[i] = item_g1_torsion_free(p, f);
 }
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_torsion_free(uint8_t *out, const uint8_t *in, size_t n) {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_torsion_free
     if (i >= n) return;
     g2m p;
     uint8_t f;
-    item_g2_decode(p, f, in + 128 * i, true);
+    item_g2_decode(p, f, in + 128 * i, DEC_ON_CURVE);
     out[i] = item_g2_torsion_free(p, f);
 }
 // flags |= FL_BAD where the (already decoded) point is not in the order-r subgroup
@@ -288,6 +288,54 @@ __global__ void k_or_bytes(int *bad, const uint8_t *b, size_t n) {
 // aggregate verdict: the exponentiated product is 1 and no shard saw a bad input
 __global__ void k_finish_ok(uint8_t *ok, const fp12 *F, const int *bad) {
     if (blockIdx.x == 0 && threadIdx.x == 0) ok[0] = (fp12_is_one(F[0]) && !*bad) ? 1 : 0;
+}
+
+// ---- the aggregate path's exchange record and its post-gather kernel -----------------------
+// Each rank's last product-tree pass writes its Fp12 partial (internal Montgomery form: every rank runs this binary)
+// straight into `f` of its send record, the bad-input word follows, ncclAllGather moves 400 bytes per rank, and ONE
+// launch of k_gather_finish_l2 multiplies the <= 8 partials, runs the single final exponentiation and compares with 1
+// (pairings.rs:37-43 MillerLoopResult +, 50-178).  One warp; every lane pair computes the same item (cf. BN_L2_PROLOGUE).
+struct alignas(16) agg_rec {
+    fp12 f;
+    uint32_t bad;
+    uint32_t pad[3];
+};
+__global__ void k_agg_rec_flag(agg_rec *rec, const int *bad) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rec->bad = *bad ? 1u : 0u;
+        rec->pad[0] = rec->pad[1] = rec->pad[2] = 0;
+    }
+}
+__global__ void __launch_bounds__(32) k_gather_finish_l2(uint8_t *ok, fp12 *gt, const agg_rec *recs, int k) {
+    fp12l acc, x;
+    uint32_t bad = 0;
+    fp12_load(acc, recs[0].f);
+    bad |= recs[0].bad;
+#pragma unroll 1
+    for (int i = 1; i < k; i++) {
+        fp12_load(x, recs[i].f);
+        bad |= recs[i].bad;
+        fp12_mul(acc, acc, x);
+    }
+    final_exponentiation(acc);
+    bool one = fp12_is_one(acc);
+    if (gt) fp12_store(*gt, acc);
+    if (threadIdx.x == 0) ok[0] = (one && !bad) ? 1 : 0;
+}
+// product of the gathered partials only (bn254_aggregate_partial on a multi-device ctx): out = prod recs[i].f, *bad |= any flag
+__global__ void __launch_bounds__(32) k_gather_product_l2(fp12 *out, int *bad, const agg_rec *recs, int k) {
+    fp12l acc, x;
+    uint32_t b = 0;
+    fp12_load(acc, recs[0].f);
+    b |= recs[0].bad;
+#pragma unroll 1
+    for (int i = 1; i < k; i++) {
+        fp12_load(x, recs[i].f);
+        b |= recs[i].bad;
+        fp12_mul(acc, acc, x);
+    }
+    fp12_store(*out, acc);
+    if (threadIdx.x == 0 && b) atomicOr(bad, 1);
 }
 
 // scalar multiplication / sums

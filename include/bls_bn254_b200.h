@@ -13,14 +13,28 @@
  *
  * Return value: 0 on success; -1..-4 = Bn254Error::{InvalidScalarBytes, InvalidG1Bytes,
  * InvalidG2Bytes, InvalidGtBytes} (error.rs:5-10) for malformed call-level input; -10 bad argument;
- * -20 no usable CUDA device (there is NO CPU fallback); -100-k = CUDA error k.  Per-item problems
+ * -20 no usable CUDA device (there is NO CPU fallback); -100-k = CUDA error k; -200-k = NCCL error k
+ * (-200 itself: libnccl could not be loaded / no communicator).  Per-item problems
  * (undecodable point, SvdW exception where the reference panics: fp.rs:325, fp2.rs:255) never abort
  * a batch: the item's status byte is 0 and its output is all zero bytes (ok[i] = 0 for verify).
  *
  * Threading: calls are synchronous; a ctx is single-caller; several contexts may coexist.
  * Ownership: the caller owns every buffer; nothing is retained after return.
  * Host-buffer entry points shard items across the ctx's devices by contiguous index range (no
- * inter-GPU traffic).  "_dev" entry points take device pointers resident on the ctx's FIRST device.
+ * inter-GPU traffic) and stream each device's share through a two-stage chunk pipeline (upload of
+ * chunk k+1 and download of chunk k-1 overlap the kernels of chunk k).  Pinned caller buffers
+ * (cudaHostAlloc / cudaHostRegister / bn254_host_register) make every copy asynchronous; pageable
+ * buffers work and are staged.  "_dev" entry points take device pointers resident on the ctx's FIRST device.
+ *
+ * Latency note: a lone verification through this library takes ~9 ms (a single pairing is a latency-
+ * bound chain of ~17 000 dependent field multiplications; a CPU core does it in ~2 ms).  The library
+ * is for batches: throughput saturates from ~2^14 tuples per call.
+ *
+ * Identity policy of the verification predicates: a public key or (per-tuple) signature that decodes
+ * as the identity -- x == 0, or y == 1 under the reference's decode convention (g1.rs:318-324) -- is
+ * rejected like an undecodable one (KeyValidate of the IETF BLS draft); an aggregate signature may be
+ * the identity.  The pairing / Miller-loop entry points keep the reference's semantics (an identity
+ * input contributes the factor 1, pairings.rs:789-800).
  */
 #ifndef BLS_BN254_B200_H
 #define BLS_BN254_B200_H
@@ -41,11 +55,12 @@ typedef struct bn254_ctx bn254_ctx;
 #define BN254_ERR_ARG (-10)
 #define BN254_ERR_NO_DEVICE (-20)
 #define BN254_ERR_CUDA_BASE (-100)
+#define BN254_ERR_NCCL_BASE (-200)
 
 #define BN254_MIN_SIG 0 /* pk in G2 (128 B), sig in G1 (64 B), messages hashed to G1 */
 #define BN254_MIN_PK 1  /* pk in G1 (64 B), sig in G2 (128 B), messages hashed to G2 */
 #define BN254_FLAG_CHECK_ON_CURVE 1u /* reject keys / signatures that are not on the curve */
-#define BN254_FLAG_CHECK_SUBGROUP 2u /* verify_batch: also require keys / signatures in the order-r subgroup (implies on-curve) */
+#define BN254_FLAG_CHECK_SUBGROUP 2u /* also require keys / signatures in the order-r subgroup (implies on-curve); every verify / aggregate entry point */
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int bn254_device_count(void);
@@ -53,13 +68,29 @@ int bn254_device_count(void);
 int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev);
 void bn254_ctx_destroy(bn254_ctx *ctx);
 const char *bn254_last_error(const bn254_ctx *ctx);
-/* number of kernels this ctx has launched so far (all devices) */
+/* Tuning / test knobs of a live ctx (the BN254_LANES, BN254_CHUNK, BN254_SPLIT environment variables set the same values at
+ * creation): "lanes" = shape of the pairing kernels -- 0 picked per launch (default), 1 one thread per pairing, 2 two lanes
+ * per pairing; results are bit-identical in every shape (the parity suite runs all of them); "chunk" = items staged per
+ * host<->device round (default 2^18); "split" = concurrent slices per verification batch (default 1). */
+int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value);
+/* Pin / unpin caller memory (cudaHostRegister) so that the chunk pipeline copies it asynchronously. */
+int bn254_host_register(void *p, size_t bytes);
+int bn254_host_unregister(void *p);
+/* ---- NCCL communicator for jobs of one process per GPU (the aggregate path's single exchange).
+ * Rank 0 calls bn254_comm_unique_id and ships the 128 bytes to the other ranks by any means (torch.distributed, MPI, a
+ * socket); every rank then calls bn254_comm_init_rank on its one-device ctx.  A ctx created with several devices owns one
+ * communicator per device already (ncclCommInitAll).  libnccl.so.2 is bound at run time. */
+#define BN254_COMM_ID_BYTES 128
+int bn254_comm_unique_id(uint8_t *out /* 128 */);
+int bn254_comm_init_rank(bn254_ctx *ctx, const uint8_t *id /* 128 */, int nranks, int rank);
+int bn254_comm_nranks(const bn254_ctx *ctx);
+/* number of kernels this ctx has launched so far (all devices; an NCCL collective counts as one) */
 uint64_t bn254_launch_count(const bn254_ctx *ctx);
 /* cudaStream_t of the ctx's first device (for event timing of the _dev entry points) */
 void *bn254_stream(bn254_ctx *ctx);
 int bn254_sync(bn254_ctx *ctx);
 /* Per-launch timing: when enabled every kernel launch is bracketed by a CUDA event pair on the
- * launch stream; bn254_profile_drain synchronises and writes one line per launch of the first
+ * launch stream; bn254_profile_drain synchronises and writes one line per launch, device after
  * device, "kernel_name items milliseconds\n", into buf (BN254_ERR_ARG if it does not fit). */
 int bn254_profile_enable(bn254_ctx *ctx, int on);
 int bn254_profile_drain(bn254_ctx *ctx, char *buf, size_t cap);
@@ -117,6 +148,12 @@ int bn254_aggregate_partial(bn254_ctx *ctx, int variant, const uint8_t *pks, con
                             const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial /* 384 */,
                             uint8_t *bad /* 1 */);
 int bn254_aggregate_finish(bn254_ctx *ctx, const uint8_t *partials /* k*384 */, const uint8_t *bad /* k */, size_t k, uint8_t *ok);
+/* The whole predicate for a job of one process per GPU: every rank passes ITS shard of (pk_i, m_i); agg_sig is read on rank 0
+ * only.  Per rank: hash -> Miller loops -> product tree whose last pass writes the NCCL send record; ONE ncclAllGather of 400
+ * bytes per rank over NVLink on the library stream; ONE kernel (<= nranks products, the single final exponentiation, compare).
+ * *ok = the job's verdict, on every rank.  Needs bn254_comm_init_rank when nranks > 1. */
+int bn254_aggregate_verify_dist(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* 1 byte */);
 
 /* ---- codecs and predicates: to_/from_compressed (g1.rs:283-328, g2.rs:274-340), is_on_curve ---- */
 int bn254_g1_compress(bn254_ctx *ctx, const uint8_t *pts, size_t n, uint8_t *out /* n*32 */);
@@ -151,6 +188,9 @@ int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t
 int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                                 const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *partial,
                                 uint8_t *bad);
+
+int bn254_aggregate_verify_dist_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                    const uint8_t *agg_sig, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* device byte */);
 
 /* ---- INT32 multiply-add micro-benchmark: the roofline denominator.  Runs `iters` rounds of
  *      independent multiply-add chains on every SM of the first device (8 chains per thread, full

@@ -1069,6 +1069,7 @@ static int verify_one(const verify_args *a, size_t i) {
     if (a->variant == 0) {
         g2a pk; g1a sig, h;
         if (!g2a_from_bytes(&pk, a->pks + 128 * i) || !g1a_from_bytes(&sig, a->sigs + 64 * i)) return 0;
+        if (pk.inf || sig.inf) return 0; /* KeyValidate: an identity key (or signature) never verifies */
         if ((a->flags & 3) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) return 0;
         if ((a->flags & 2) && (!g2a_torsion_free(&pk) || !g1a_torsion_free(&sig))) return 0;
         if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
@@ -1076,6 +1077,7 @@ static int verify_one(const verify_args *a, size_t i) {
     } else {
         g1a pk; g2a sig, h;
         if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) return 0;
+        if (pk.inf || sig.inf) return 0;
         if ((a->flags & 3) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) return 0;
         if ((a->flags & 2) && (!g1a_torsion_free(&pk) || !g2a_torsion_free(&sig))) return 0;
         if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) return 0;
@@ -1129,6 +1131,7 @@ static void rbv_item_range(void *p, size_t lo, size_t hi) {
         if (a->variant == 0) {
             g2a pk; g1a sig, h; g1p t;
             if (!g2a_from_bytes(&pk, a->pks + 128 * i) || !g1a_from_bytes(&sig, a->sigs + 64 * i)) continue;
+            if (pk.inf || sig.inf) continue;
             if ((a->flags & 3) && (!g2a_on_curve(&pk) || !g1a_on_curve(&sig))) continue;
             if ((a->flags & 2) && (!g2a_torsion_free(&pk) || !g1a_torsion_free(&sig))) continue;
             if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
@@ -1139,6 +1142,7 @@ static void rbv_item_range(void *p, size_t lo, size_t hi) {
         } else {
             g1a pk; g2a sig, h; g1p t; g2p u;
             if (!g1a_from_bytes(&pk, a->pks + 64 * i) || !g2a_from_bytes(&sig, a->sigs + 128 * i)) continue;
+            if (pk.inf || sig.inf) continue;
             if ((a->flags & 3) && (!g1a_on_curve(&pk) || !g2a_on_curve(&sig))) continue;
             if ((a->flags & 2) && (!g1a_torsion_free(&pk) || !g2a_torsion_free(&sig))) continue;
             if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
@@ -1194,7 +1198,9 @@ EXPORT int orc_verify_batch_randomized(int variant, const uint8_t *pks, const ui
     return 0;
 }
 /* aggregate verify, distinct messages: e(aggsig, -g2) * prod e(H(m_i), pk_i) == 1 (min-sig);
- * e(-g1, aggsig) * prod e(pk_i, H(m_i)) == 1 (min-pk) */
+ * e(-g1, aggsig) * prod e(pk_i, H(m_i)) == 1 (min-pk).  An identity public key rejects the aggregate (KeyValidate);
+ * an identity aggregate signature is a legal group element and stays in the product as the factor 1.  flags bit1
+ * (subgroup) implies bit0 (on curve), as in verify. */
 typedef struct { int variant; const uint8_t *pks; const uint8_t *msgs; const uint64_t *off; const uint8_t *dst; size_t dst_len; uint32_t flags;
                  g1a *ps; g2a *qs; int *bad; } agg_args;
 static void agg_range(void *p, size_t lo, size_t hi) {
@@ -1204,11 +1210,11 @@ static void agg_range(void *p, size_t lo, size_t hi) {
         size_t mlen = a->off[i + 1] - a->off[i];
         int ok;
         if (a->variant == 0) {
-            ok = g2a_from_bytes(&a->qs[i], a->pks + 128 * i) && (!(a->flags & 1) || g2a_on_curve(&a->qs[i])) &&
-                 hash_to_g1_one(&a->ps[i], msg, mlen, a->dst, a->dst_len, 2);
+            ok = g2a_from_bytes(&a->qs[i], a->pks + 128 * i) && !a->qs[i].inf && (!(a->flags & 3) || g2a_on_curve(&a->qs[i])) &&
+                 (!(a->flags & 2) || g2a_torsion_free(&a->qs[i])) && hash_to_g1_one(&a->ps[i], msg, mlen, a->dst, a->dst_len, 2);
         } else {
-            ok = g1a_from_bytes(&a->ps[i], a->pks + 64 * i) && (!(a->flags & 1) || g1a_on_curve(&a->ps[i])) &&
-                 hash_to_g2_one(&a->qs[i], msg, mlen, a->dst, a->dst_len, 2);
+            ok = g1a_from_bytes(&a->ps[i], a->pks + 64 * i) && !a->ps[i].inf && (!(a->flags & 3) || g1a_on_curve(&a->ps[i])) &&
+                 (!(a->flags & 2) || g1a_torsion_free(&a->ps[i])) && hash_to_g2_one(&a->qs[i], msg, mlen, a->dst, a->dst_len, 2);
         }
         if (!ok) __atomic_store_n(a->bad, 1, __ATOMIC_RELAXED);
     }
@@ -1230,10 +1236,10 @@ EXPORT int orc_aggregate_verify(int variant, const uint8_t *pks, const uint8_t *
     agg_args a = {variant, pks, msgs, off, dst, dst_len, flags, ps, qs, &bad};
     parallel_for(n, nthreads, agg_range, &a);
     if (variant == 0) {
-        if (!g1a_from_bytes(&ps[n], agg_sig) || ((flags & 1) && !g1a_on_curve(&ps[n]))) bad = 1;
+        if (!g1a_from_bytes(&ps[n], agg_sig) || ((flags & 3) && !g1a_on_curve(&ps[n])) || ((flags & 2) && !g1a_torsion_free(&ps[n]))) bad = 1;
         qs[n] = NEG_G2_GEN_A;
     } else {
-        if (!g2a_from_bytes(&qs[n], agg_sig) || ((flags & 1) && !g2a_on_curve(&qs[n]))) bad = 1;
+        if (!g2a_from_bytes(&qs[n], agg_sig) || ((flags & 3) && !g2a_on_curve(&qs[n])) || ((flags & 2) && !g2a_torsion_free(&qs[n]))) bad = 1;
         ps[n] = NEG_G1_GEN_A;
     }
     if (bad) { *ok = 0; free(ps); free(qs); return 0; }

@@ -43,6 +43,20 @@ class OracleCtx:
         one = (1).to_bytes(32, "big") + bytes(352)
         return int(self.o.final_exponentiation(self.o.fp12_product(parts)) == one)
 
+    # a fake communicator so that bd.init_comm (rank 0 draws the id, torch.distributed ships it) is exercised on gloo
+    comm = None
+
+    @property
+    def comm_nranks(self):
+        return self.comm[1] if self.comm else 1
+
+    def comm_unique_id(self):
+        return bytes((7 * i + 3) & 0xff for i in range(128))
+
+    def comm_init_rank(self, uid, nranks, rank):
+        assert self.comm is None and len(uid) == 128
+        self.comm = (bytes(uid), nranks, rank)
+
     def verify_batch(self, variant, pks, msgs, sigs, dst, flags=0):
         return self.o.verify_batch(variant, pks, msgs, sigs, dst, flags)
 
@@ -77,6 +91,8 @@ def _worker(rank, world, port, q):
         lo, hi = bd.shard_range(n, world, rank)
         p, m, s = bd.shard_tuples(n, world, rank, [(pks, 128), (msgs, None), (sigs, 64)])
         assert len(m) == hi - lo and len(p) == 128 * (hi - lo)
+        assert bd.init_comm(ctx) == world and bd.init_comm(ctx) == world      # second call: already initialised
+        assert ctx.comm == (OracleCtx().comm_unique_id(), world, rank)
         ok = bd.aggregate_verify_sharded(ctx, 0, p, m, agg, DST)
         bad_msgs = list(m)
         if rank == 1:

@@ -27,6 +27,27 @@ def B():
     return b
 
 
+@pytest.fixture(params=[1, 2], ids=["one-thread", "lane-pair"])
+def shape(request, ctx):
+    """Force one shape of the pairing kernels for the test (bn254_ctx_set_option "lanes"): 1 = one thread per pairing (what
+    every batch beyond one wave -- C5's 2^18-tuple chunks -- runs), 2 = two lanes per pairing.  Results are bit-identical."""
+    ctx.set_option("lanes", request.param)
+    yield request.param
+    ctx.set_option("lanes", 0)
+
+
+def launched(ctx, fn):
+    """run fn() with per-launch profiling on; returns (result, set of kernel names launched)"""
+    ctx.profile(True)
+    ctx.profile_drain()
+    try:
+        out = fn()
+        names = {r[0] for r in ctx.profile_drain()}
+    finally:
+        ctx.profile(False)
+    return out, names
+
+
 def rand_msgs(rng, n, maxlen=96):
     out = [b"", b"abc", b"abcdef0123456789", b"q128_" + b"q" * 128, b"a512_" + b"a" * 512]
     while len(out) < n:
@@ -85,7 +106,7 @@ def _points(ctx, orc, n, seed):
     return orc.hash_to_g1(msgs, QUUX_G1, nthreads=8), orc.hash_to_g2(msgs, QUUX_G2, nthreads=8)
 
 
-def test_pairing_vs_oracle(ctx, orc, B):
+def test_pairing_vs_oracle(ctx, orc, B, shape):
     g1, g2 = _points(ctx, orc, 40, 3)
     ident1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
     ident2 = bytes(64) + bytes(32) + bytes(31) + b"\x01"
@@ -107,7 +128,7 @@ def test_pairing_vs_oracle(ctx, orc, B):
     assert ctx.final_exponentiation(good) == orc.final_exponentiation(good, nthreads=8)
 
 
-def test_multi_miller_and_product(ctx, orc, B):
+def test_multi_miller_and_product(ctx, orc, B, shape):
     g1, g2 = _points(ctx, orc, 37, 5)
     assert ctx.multi_miller_loop(g1, g2) == orc.multi_miller_loop(g1, g2)
     assert ctx.multi_miller_loop(b"", b"") == orc.multi_miller_loop(b"", b"")
@@ -182,7 +203,7 @@ def test_codecs_vs_oracle(ctx, orc, B):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_verify_vs_oracle(ctx, orc, B, variant):
+def test_verify_vs_oracle(ctx, orc, B, variant, shape):
     pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, 96, variant=variant, corrupt_every=8)
     dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
     rpk, rsig = (128, 64) if variant == 0 else (64, 128)
@@ -203,10 +224,59 @@ def test_verify_vs_oracle(ctx, orc, B, variant):
     assert got == orc.verify_batch(variant, pks, msgs, bytes(bad), dst, flags=1, nthreads=8)
     assert got[0] == 0
     assert ctx.verify_batch(variant, b"", [], b"", dst) == b""
+    # the kernels of the forced shape really ran
+    _, names = launched(ctx, lambda: ctx.verify_batch(variant, pks, msgs, sigs, dst))
+    want = {0: ("k_miller2_fixed", "k_final_exp"), 1: ("k_miller2", "k_final_exp")}[variant]
+    assert {w + ("_l2" if shape == 2 else "") for w in want} <= names
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_aggregate_verify(ctx, orc, B, variant):
+def test_identity_and_y_equals_one_inputs_never_verify(ctx, orc, B, variant):
+    """an identity public key drops out of the Miller product, so (pk = identity, sig = identity)
+    used to verify on every message; so did pk = (x, 1) / sig = (x, 1), which the reference's decode convention flags as
+    infinity (g1.rs:318-324) -- an off-curve forgery under default flags.  All of them are rejected now, by the exact
+    predicate, the randomised one and the aggregate one, on the GPU and in the oracle."""
+    n = 12
+    pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=variant, corrupt_every=0)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    id1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    id2 = bytes(64) + bytes(63) + b"\x01"
+    y1_g1 = (12345).to_bytes(32, "big") + (1).to_bytes(32, "big")          # any x, y = 1: "infinity" by convention, not on the curve
+    y1_g2 = (7).to_bytes(32, "big") + (9).to_bytes(32, "big") + bytes(63) + b"\x01"
+    idpk, idsig = (id2, id1) if variant == 0 else (id1, id2)
+    y1pk, y1sig = (y1_g2, y1_g1) if variant == 0 else (y1_g1, y1_g2)
+    P, S = bytearray(pks), bytearray(sigs)
+    P[0:rpk], S[0:rsig] = idpk, idsig                    # tuple 0: identity key and identity signature
+    P[2 * rpk:3 * rpk], S[2 * rsig:3 * rsig] = y1pk, y1sig   # tuple 2: the y == 1 forgery
+    P[4 * rpk:5 * rpk] = idpk                            # tuple 4: identity key, honest signature
+    S[6 * rsig:7 * rsig] = idsig                         # tuple 6: honest key, identity signature
+    P, S = bytes(P), bytes(S)
+    want = bytearray(exp)
+    for j in (0, 2, 4, 6):
+        want[j] = 0
+    for flags in (0, 1, 3):
+        got = ctx.verify_batch(variant, P, msgs, S, dst, flags=flags)
+        assert got == bytes(want), flags
+        assert got == orc.verify_batch(variant, P, msgs, S, dst, flags=flags, nthreads=8)
+    seed = bytes(range(32))
+    got = ctx.verify_batch_randomized(variant, P, msgs, S, dst, seed, group=1)
+    assert got == bytes(want)
+    got = ctx.verify_batch_randomized(variant, P, msgs, S, dst, seed, group=4)
+    assert got == b"\x00\x00\x01" == orc.verify_batch_randomized(variant, P, msgs, S, dst, seed, group=4, nthreads=8)
+    # aggregate: an identity key (or the y == 1 key) rejects even though the product itself would be 1
+    agg = B.scheme.aggregate(ctx, sigs, variant)
+    assert ctx.aggregate_verify(variant, pks, msgs, agg, dst) == 1
+    for bad_pk in (idpk, y1pk):
+        Q = bad_pk + pks[rpk:]
+        rest = B.scheme.aggregate(ctx, sigs[rsig:], variant)    # what the product needs once tuple 0 dropped out
+        assert ctx.aggregate_verify(variant, Q, msgs, rest, dst) == 0 == orc.aggregate_verify(variant, Q, msgs, rest, dst, nthreads=8)
+    # an identity AGGREGATE signature is a legal group element: the verdict is the product's
+    assert ctx.aggregate_verify(variant, pks, msgs, idsig, dst) == 0 == orc.aggregate_verify(variant, pks, msgs, idsig, dst, nthreads=8)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_aggregate_verify(ctx, orc, B, variant, shape):
     n = 50
     pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=variant, corrupt_every=0)
     dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
@@ -235,7 +305,7 @@ def test_aggregate_verify(ctx, orc, B, variant):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_randomized_batch_verify_vs_oracle(ctx, orc, B, variant):
+def test_randomized_batch_verify_vs_oracle(ctx, orc, B, variant, shape):
     """bn254_verify_batch_randomized: group verdicts equal the oracle's and the AND of the exact
     per-tuple verdicts; ragged last group, group = 1, group > n, both scalar widths."""
     n = 203
@@ -473,7 +543,7 @@ def test_subgroup_checks(ctx, orc, B):
     assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=B.CHECK_SUBGROUP)[1:] == b"\x01" * 7
 
 
-def test_ragged_sizes_and_long_messages(ctx, orc, B):
+def test_ragged_sizes_and_long_messages(ctx, orc, B, shape):
     """batch sizes around the CTA / warp boundaries and messages from 0 bytes to 10 KB"""
     rng = random.Random(33)
     for n in (1, 31, 33, 63, 65, 127, 129):
@@ -504,3 +574,144 @@ def test_profile_and_launch_count(ctx, orc, B):
     assert [x[:-3] if x.endswith("_l2") else x for x in names] == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_miller2_fixed", "k_final_exp", "k_fp12_is_one"]
     assert all(r[2] > 0 for r in recs)
     assert ctx.launch_count > before
+
+
+def test_aggregate_verify_honours_the_validation_flags(ctx, orc, B):
+    """CHECK_SUBGROUP used to be ignored by the aggregate path (and, alone, even switched the on-curve
+    test off).  A min-sig key on the twist but outside the order-r subgroup, and an off-curve key, against the oracle."""
+    n = 9
+    pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=0, corrupt_every=0)
+    agg = B.scheme.aggregate(ctx, sigs, 0)
+    raw = orc.svdw_g2((5).to_bytes(32, "big") + (9).to_bytes(32, "big"))     # on the curve, outside the subgroup
+    assert ctx.g2_is_on_curve(raw) == b"\x01" and ctx.g2_is_torsion_free(raw) == b"\x00"
+    off = bytearray(pks[:128])
+    off[127] ^= 1                                                              # not on the curve
+    for bad_pk, verdicts in ((raw, {0: None, 1: None, 2: 0, 3: 0}), (bytes(off), {0: None, 1: 0, 2: 0, 3: 0})):
+        Q = pks[:128 * 3] + bad_pk + pks[128 * 4:]
+        for flags, want in verdicts.items():
+            got = ctx.aggregate_verify(0, Q, msgs, agg, B.DST_MIN_SIG, flags=flags)
+            assert got == orc.aggregate_verify(0, Q, msgs, agg, B.DST_MIN_SIG, flags=flags, nthreads=8), flags
+            if want is not None:
+                assert got == want
+    for flags in (0, 1, 2, 3):
+        assert ctx.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG, flags=flags) == 1
+    # min-pk: the aggregate SIGNATURE is the G2 input
+    pks1, msgs1, sigs1, _ = B.scheme.synth_batch(ctx, n, variant=1, corrupt_every=0)
+    agg1 = B.scheme.aggregate(ctx, sigs1, 1)
+    assert ctx.aggregate_verify(1, pks1, msgs1, agg1, B.DST_MIN_PK, flags=3) == 1
+    mixed = orc.g2_sum(agg1 + orc.g2_mul(raw, B.R_ORDER.to_bytes(32, "big")))  # + a point of the cofactor subgroup
+    for flags in (0, 1, 2, 3):
+        got = ctx.aggregate_verify(1, pks1, msgs1, mixed, B.DST_MIN_PK, flags=flags)
+        assert got == orc.aggregate_verify(1, pks1, msgs1, mixed, B.DST_MIN_PK, flags=flags, nthreads=8)
+    assert ctx.aggregate_verify(1, pks1, msgs1, mixed, B.DST_MIN_PK, flags=2) == 0
+    # the scheme layer validates by default
+    assert B.scheme.aggregate_verify(ctx, pks[:128 * 3] + raw + pks[128 * 4:], msgs, agg) == 0
+    assert B.scheme.verify(ctx, raw + pks[128:], msgs, sigs)[1:] == b"\x01" * (n - 1)
+
+
+def test_verify_c5_shape(orc, B):
+    """The shape BASELINE config 5 (2^24 tuples) runs: chunks of 2^18 through the double-buffered host pipeline, every
+    chunk on the one-thread kernels (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097 is two chunks with a ragged tail:
+    accept bytes equal the construction, a 512-tuple slice straddling the chunk boundary equals the oracle, and the
+    kernels of that shape are the ones that launched.  Pageable and pinned result buffers take different copy paths."""
+    import numpy as np
+    import torch
+    c = B.Context([0])
+    try:
+        n = (1 << 18) + 4097
+        pks, msgs, sigs, exp = B.scheme.synth_batch(c, n, variant=0, n_keys=64)
+        (got), names = launched(c, lambda: c.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG))
+        assert got == exp
+        assert {"k_miller2_fixed", "k_final_exp", "k_hash_g1"} <= names and not any(x.endswith("_l2") for x in names)
+        lo = (1 << 18) - 256
+        ref = orc.verify_batch(0, pks[128 * lo:128 * (lo + 512)], msgs[lo:lo + 512], sigs[64 * lo:64 * (lo + 512)], B.DST_MIN_SIG, nthreads=orc.ncpu())
+        assert got[lo:lo + 512] == ref
+        assert 0 < sum(ref) < 512
+        # pinned caller buffers: the zero-staging path of the pipeline, three chunks
+        c.set_option("chunk", 100000)
+        blob, off = B.pack_msgs(msgs)
+        pin = lambda x: torch.frombuffer(bytearray(x), dtype=torch.uint8).pin_memory()
+        h_pk, h_sig, h_blob = pin(pks), pin(sigs), pin(blob)
+        h_off = torch.tensor(list(off), dtype=torch.int64).pin_memory()
+        h_ok = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        c.raw("bn254_verify_batch", 0, h_pk.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sig.data_ptr(), n, B.DST_MIN_SIG, len(B.DST_MIN_SIG), 0,
+              h_ok.data_ptr())
+        assert bytes(h_ok.numpy()) == exp
+        # randomised, same job: groups of 512 over three chunks (twin kernel, one thread per two tuples)
+        seed = b"\x5a" * 32
+        grp, names = launched(c, lambda: c.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=512))
+        assert grp == bytes(int(all(exp[g:g + 512])) for g in range(0, n, 512))
+        assert "k_miller_twin" in names
+    finally:
+        c.close()
+
+
+def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B):
+    """70 001 pairings: more than one wave of lane pairs, so pairing_batch / miller_loop_batch / final_exponentiation run
+    k_miller1 and k_final_exp (one thread per item).  Samples from the head, the middle and the ragged tail against the
+    oracle; the profiler confirms which kernels ran."""
+    n = 70001
+    rng = random.Random(99)
+    base = 257
+    msgs = [rng.randbytes(16) for _ in range(base)]
+    b1, b2 = orc.hash_to_g1(msgs, QUUX_G1, nthreads=8), orc.hash_to_g2(msgs, QUUX_G2, nthreads=8)
+    idx = [(i * 31 + i // base) % base for i in range(n)]            # item i pairs P[idx[i]] with Q[(idx[i] * 7 + i // base) % base]
+    jdx = [(idx[i] * 7 + i // base) % base for i in range(n)]
+    g1 = b"".join(b1[64 * k:64 * k + 64] for k in idx)
+    g2 = b"".join(b2[128 * k:128 * k + 128] for k in jdx)
+    (gt, st), names = launched(ctx, lambda: ctx.pairing(g1, g2, want_status=True))
+    assert {"k_miller1", "k_final_exp"} <= names and not any(x.endswith("_l2") for x in names)
+    assert st == b"\x01" * n
+    for lo in (0, 35000, n - 40):
+        sl = slice(lo, lo + 40)
+        ref = orc.pairing_batch(g1[64 * lo:64 * (lo + 40)], g2[128 * lo:128 * (lo + 40)], nthreads=8)
+        assert gt[384 * lo:384 * (lo + 40)] == ref, lo
+    ml = ctx.miller_loop(g1, g2)
+    lo = n - 33
+    assert ml[384 * lo:] == orc.miller_loop_batch(g1[64 * lo:], g2[128 * lo:], nthreads=8)
+    fe, names = launched(ctx, lambda: ctx.final_exponentiation(ml))
+    assert "k_final_exp" in names
+    assert fe == gt
+    # min-pk verification at this size: k_miller2 (both pairs variable, one thread per item)
+    m = 66400
+    pks, vm, sigs, exp = B.scheme.synth_batch(ctx, m, variant=1, n_keys=32)
+    got, names = launched(ctx, lambda: ctx.verify_batch(1, pks, vm, sigs, B.DST_MIN_PK))
+    assert got == exp and "k_miller2" in names and "k_hash_g2" in names
+    lo = m - 48
+    assert got[lo:] == orc.verify_batch(1, pks[64 * lo:], vm[lo:], sigs[128 * lo:], B.DST_MIN_PK, nthreads=8)
+
+
+def test_aggregate_exchange_single_rank(ctx, orc, B):
+    """bn254_aggregate_verify_dist on a lone rank (no communicator needed): product tree -> send record -> post-gather
+    kernel, the same launches a rank of an 8-GPU job makes.  Verdicts against the oracle."""
+    n = 300
+    pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=0, corrupt_every=0, n_keys=16)
+    agg = B.scheme.aggregate(ctx, sigs, 0)
+    ok, names = launched(ctx, lambda: ctx.aggregate_verify_dist(0, pks, msgs, agg, B.DST_MIN_SIG))
+    assert ok == 1 == orc.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG, nthreads=8)
+    assert {"k_fp12_reduce", "k_agg_rec_flag", "k_gather_finish_l2"} <= names
+    msgs[7] = b"tampered"
+    assert ctx.aggregate_verify_dist(0, pks, msgs, agg, B.DST_MIN_SIG) == 0
+    assert ctx.aggregate_verify_dist(0, b"\xff" * 128 + pks[128:], msgs, agg, B.DST_MIN_SIG) == 0
+    with pytest.raises(B.Bn254Error):
+        ctx.aggregate_verify_dist(0, pks, msgs, None, B.DST_MIN_SIG)      # rank 0 must bring the aggregate signature
+
+
+def test_nccl_exchange_in_multi_device_ctx(orc, B):
+    """A ctx over two devices: shards on both, ncclAllGather inside the library, one post-gather kernel on device 0."""
+    nd = B._native.lib().bn254_device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c1, c2 = B.Context([0]), B.Context([0, 1])
+    try:
+        assert c2.comm_nranks == 2
+        n = 501
+        pks, msgs, sigs, _ = B.scheme.synth_batch(c1, n, variant=0, corrupt_every=0, n_keys=16)
+        agg = B.scheme.aggregate(c1, sigs, 0)
+        assert c2.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG) == 1
+        assert c2.aggregate_partial(0, pks, msgs, agg, B.DST_MIN_SIG) == c1.aggregate_partial(0, pks, msgs, agg, B.DST_MIN_SIG)
+        msgs[400] = b"tampered"                                          # device 1's shard
+        assert c2.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG) == 0 == orc.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG, nthreads=8)
+    finally:
+        c1.close()
+        c2.close()

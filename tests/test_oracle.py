@@ -167,6 +167,39 @@ def test_verify_min_sig(orc):
     assert orc.aggregate_verify(0, pks[:128 * 5], msgs[:5], agg, DST_SIG) == 0
 
 
+def test_identity_keys_and_signatures_never_verify(orc):
+    """KeyValidate: an identity public key used to drop out of the Miller product, so (identity, identity) verified on
+    every message; the reference's decode convention (y == 1 means infinity, g1.rs:318-324) extended that to off-curve
+    (x, 1) inputs.  Both predicates and the aggregate now reject an identity key; the aggregate keeps accepting an identity
+    aggregate SIGNATURE as the group element it is."""
+    n = 5
+    sks, msgs, sk_b = _keys(orc, n, 9)
+    pks = orc.g2_mul(orc.g2_generator() * n, sk_b)
+    sigs = orc.g1_mul(orc.hash_to_g1(msgs, DST_SIG), sk_b)
+    id1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    id2 = bytes(64) + bytes(63) + b"\x01"
+    y1_g1 = (12345).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    y1_g2 = (7).to_bytes(32, "big") + (9).to_bytes(32, "big") + bytes(63) + b"\x01"
+    P = id2 + y1_g2 + id2 + pks[128 * 3:]
+    S = id1 + y1_g1 + sigs[64 * 2:64 * 3] + id1 + sigs[64 * 4:]
+    for flags in (0, 1, 3):
+        assert orc.verify_batch(0, P, msgs, S, DST_SIG, flags=flags) == bytes([0, 0, 0, 0, 1])
+    seed = bytes(32)
+    assert orc.verify_batch_randomized(0, P, msgs, S, DST_SIG, seed, group=1) == bytes([0, 0, 0, 0, 1])
+    agg_rest = orc.g1_sum(sigs[64:])
+    assert orc.aggregate_verify(0, pks[128:], msgs[1:], agg_rest, DST_SIG) == 1
+    assert orc.aggregate_verify(0, id2 + pks[128:], msgs, agg_rest, DST_SIG) == 0     # the product alone would be 1
+    assert orc.aggregate_verify(0, y1_g2 + pks[128:], msgs, agg_rest, DST_SIG) == 0
+    assert orc.aggregate_verify(0, pks, msgs, id1, DST_SIG) == 0
+    # subgroup flag on the aggregate path: a key on the twist outside the order-r subgroup
+    raw = orc.svdw_g2((5).to_bytes(32, "big") + (9).to_bytes(32, "big"))
+    Q = raw + pks[128:]
+    agg = orc.g1_sum(sigs)
+    assert orc.g2_is_on_curve(raw) == b"\x01" and orc.g2_is_torsion_free(raw) == b"\x00"
+    assert orc.aggregate_verify(0, Q, msgs, agg, DST_SIG, flags=2) == 0 == orc.aggregate_verify(0, Q, msgs, agg, DST_SIG, flags=3)
+    assert orc.aggregate_verify(0, pks, msgs, agg, DST_SIG, flags=3) == 1
+
+
 def test_verify_min_pk(orc):
     n = 3
     sks, msgs, sk_b = _keys(orc, n, 5)
