@@ -36,6 +36,16 @@
 #define BN_PTX 0
 #endif
 
+// Executed-work counter of the host build (tests/hostsim): every multiplier routine reports the INT32 multiply-add
+// operations it issues (one IMAD.WIDE = 2), so that tools/count_ops.py can freeze the EXECUTED work per item next to the
+// canonical counts of SURVEY.md 8(d) (profiles/executed_ops.json).  Compiles to nothing under nvcc.
+#if !BN_PTX
+extern "C" void bn_host_count_ops(unsigned ops);
+#define BN_COUNT_OPS(n) bn_host_count_ops(n)
+#else
+#define BN_COUNT_OPS(n) ((void)0)
+#endif
+
 namespace bn {
 
 #ifndef BN_FP_ALIGN
@@ -372,6 +382,7 @@ BN_INL void fp_select(fp &r, bool c, const fp &a, const fp &b) {  // r = c ? a :
 // T < 2^32*2p + 2p < 2^288 throughout, so O (< T / 2^32) never overflows; E may carry out of
 // word 7 (weight = O[7]) and that carry is folded into O[7] by the closing addc of the chain.
 BN_INL void fp_mul_inl(fp &r, const fp &a, const fp &b) {  // fp.rs:404-407
+    BN_COUNT_OPS(264);   // 8 rows x (16 + 16 wide-IMAD halves... = 128 + 128 ops) + 8 quotient digits
     uint32_t E[8], O[8], m;
     mul_lanes(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
     mul_lanes(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
@@ -406,6 +417,7 @@ BN_INL void fp_mul_inl(fp &r, const fp &a, const fp &b) {  // fp.rs:404-407
 // This is how Fp2 products are formed: c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0 -- 2 x 200 wide
 // IMADs and one negation instead of Karatsuba's 3 x 136 and five additions.
 BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &d) {
+    BN_COUNT_OPS(392);   // two product rows (2 x 128) + one reduction (128) + 8 quotient digits
     uint32_t E[8], O[8], m;
     mul_lanes(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
     mul_lanes(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
@@ -444,6 +456,7 @@ BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &
 // measured with k_fp_peak); two interleaved instruction streams give the scheduler what a second warp
 // would.  Same frame and bounds as fp_dot2_inl.
 BN_INL void fp_dot2x2_inl(fp &r0, fp &r1, const fp &a, const fp &c, const fp &b0, const fp &d0, const fp &b1, const fp &d1) {
+    BN_COUNT_OPS(784);
     uint32_t E0[8], O0[8], E1[8], O1[8], m0, m1;
     mul_lanes(E0, a.v[0], a.v[2], a.v[4], a.v[6], b0.v[0]);
     mul_lanes(E1, a.v[0], a.v[2], a.v[4], a.v[6], b1.v[0]);
@@ -530,6 +543,7 @@ struct fpw {
 // r (512 bit) = a * b, any 256-bit a, b.  Even/odd accumulators at absolute word positions: E holds
 // the products that start on an even word, O (offset by one word) those that start on an odd word.
 BN_INL void fp_mul_wide(fpw &r, const fp &a, const fp &b) {
+    BN_COUNT_OPS(128);
     uint32_t E[18], O[18];
 #pragma unroll
     for (int i = 8; i < 18; i++) { E[i] = 0; O[i] = 0; }
@@ -603,6 +617,7 @@ BN_INL void mad_p_odd_cin(uint32_t acc[8], uint32_t &e0, uint32_t x, uint32_t m)
 // Same frame as fp_mul_inl (running value S = E + O*2^32), the a*b_i rows replaced by shifting in
 // the next word of T at frame word 7 (= O'[6], a fresh word).  S < 2^256 + p throughout.
 BN_INL void fp_redc(fp &r, const fpw &t) {
+    BN_COUNT_OPS(136);
     uint32_t E[8], O[8], m;
 #pragma unroll
     for (int i = 0; i < 8; i++) { E[i] = t.v[i]; O[i] = 0; }

@@ -2,12 +2,20 @@
 // with g++ so the exact per-item bodies the CUDA kernels run can be unit-tested on a machine without
 // a GPU (carry chains are emulated in C, see fp.cuh).  Never linked into libbls_bn254_b200.so and
 // never reachable from the C ABI: the product has no CPU path.
+#include <atomic>
 #include <cstring>
 
 #include "../../bls_bn254_b200/csrc/items.cuh"
 
 using namespace bn;
 #define EXPORT extern "C" __attribute__((visibility("default")))
+
+// executed-work counter (fp.cuh: BN_COUNT_OPS): INT32 multiply-add operations issued by the multiplier routines since
+// the last reset, summed over all emulated lanes.  tools/count_ops.py freezes the per-item figures.
+static std::atomic<unsigned long long> g_ops{0};
+extern "C" void bn_host_count_ops(unsigned ops) { g_ops.fetch_add(ops, std::memory_order_relaxed); }
+EXPORT unsigned long long sim_ops(void) { return g_ops.load(); }
+EXPORT void sim_ops_reset(void) { g_ops.store(0); }
 
 EXPORT void sim_fp_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     fp x, y, z;
