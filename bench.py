@@ -2,15 +2,23 @@
 """bench.py -- BLS-BN254 batch verification throughput on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload verify|verify_pk|verify_rand|hash_g1|hash_g2|pairing|aggregate]
+                  [--sub all|none|c1,c3,c4,c5,pairing]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...       # the CPU arm: the oracle port on all host cores
 
-A step = one pass of the hot path (hash-to-G1 -> 2-pair Miller loop -> final exponentiation ->
-accept bit) over one batch of 2^16 synthetic (pk, msg, sig) tuples PER GPU (weak scaling: every rank
-owns a disjoint shard, no inter-GPU traffic; `aggregate` adds one 385-byte NCCL all-gather).
-`value` is timed with CUDA events on the library's launch stream with all inputs resident in HBM;
-`e2e` is the same batch through the host-buffer C ABI call (H2D + kernels + D2H inside the timed
-region).  Rank 0 prints ONE JSON line.
+A step = one pass of the hot path (hash-to-G1 -> 2-pair Miller loop -> final exponentiation -> accept bit) over one
+batch of 2^16 synthetic (pk, msg, sig) tuples PER GPU (BASELINE config 2; weak scaling: every rank owns a disjoint shard,
+no inter-GPU traffic).  `value` is timed with CUDA events on the library's launch stream with all inputs resident in
+HBM; `e2e` is the same batch through the host-buffer C ABI call (pinned host buffers, H2D + kernels + D2H inside the
+timed region).  The same JSON line carries one sub-record per remaining BASELINE config, measured in the same run:
+  c1       sign + verify of ONE 32-byte message (latency; GPU library and the CPU port)
+  c3       hash_to_curve: 2^20 messages per GPU to G1 and to G2
+  pairing  2^16 standalone pairings per GPU (bn254_pairing_batch: Miller loop + final exponentiation) -> pairings_per_sec
+  c4       aggregate verify: 2^16 signatures in TOTAL sharded over the N ranks, ONE ncclAllGather inside the library,
+           one final exponentiation (strong scaling)
+  c5       batch verify 2^24 tuples in TOTAL sharded over the N ranks through the host-buffer call (strong scaling),
+           exact and randomised
+Rank 0 prints ONE JSON line.
 """
 import argparse
 import hashlib
@@ -23,7 +31,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# canonical work per unit in Fp multiplications M (BASELINE.md section 3); 1 M = 264 INT32 IMAD-ops
+# canonical work per unit in Fp multiplications M (BASELINE.md section 3, SURVEY.md 8(d)); 1 M = 264 INT32 IMAD-ops
 M_IMAD = 264
 # verify_rand (randomised batch verification, groups of 256, 64-bit scalars a + b lambda): hash 2204 + one-pair Miller loop 8610 +
 # two joint double-and-add scalings (32 x 8 + 25 x 12 + 1 = 557 each) + one affine conversion 332 + product tree 58 + per-group
@@ -31,17 +39,33 @@ M_IMAD = 264
 WORK_M = {"verify": 23015, "verify_pk": 29687, "hash_g1": 2204, "hash_g2": 6400, "pairing": 17037, "aggregate": 10868, "verify_rand": 12386}
 KERNEL_M = {"k_miller2_fixed": 12384, "k_miller2": 14860, "k_miller_twin": 14860, "k_miller1": 8610, "k_final_exp": 8427, "k_hash_g1": 2204, "k_hash_g2": 6400,
             "k_rbv_scale_g1": 889, "k_rbv_scale_g1p": 557}
-# Multiplier work the kernels actually execute where it differs from the canonical count: quadratic-residue tests are binary
-# Jacobi symbols and inversions binary GCDs on the ALU pipe (no IMAD), so hashing needs 3 (G1) / 5 (G2) fewer 309 M exponentiations.
-KERNEL_M_EXECUTED = {"k_hash_g1": 2204 - 3 * 309, "k_hash_g2": 6400 - 5 * 309}
 UNIT = {"verify": "verifications/s", "verify_pk": "verifications/s", "hash_g1": "hashes/s", "hash_g2": "hashes/s", "pairing": "pairings/s",
         "aggregate": "verifications/s", "verify_rand": "verifications/s"}
 METRIC = {"verify": "bls_verifications_per_sec", "verify_pk": "bls_verifications_per_sec", "hash_g1": "hash_to_g1_per_sec",
           "hash_g2": "hash_to_g2_per_sec", "pairing": "pairings_per_sec", "aggregate": "bls_aggregate_verified_signatures_per_sec",
           "verify_rand": "bls_randomized_batch_verifications_per_sec"}
-
-
 RBV_SEED = hashlib.sha256(b"bench.py randomised batch verification seed").digest()
+N_KEYS = 4096          # distinct keys of every synthetic batch
+CORRUPT_EVERY = 64     # one tuple in 64 is broken, so both verdicts occur
+
+
+def executed_ops():
+    """EXECUTED multiplier work per item (INT32 multiply-add ops), frozen by tools/count_ops.py from the host build"""
+    try:
+        return {k: v["imad_ops_per_item"] for k, v in json.load(open(os.path.join(ROOT, "profiles", "executed_ops.json")))["kernels"].items()}
+    except Exception:
+        return {}
+
+
+def source_sha16():
+    """identity of the kernel sources: ncu-derived numbers committed under profiles/ are only quoted for the sources they were taken from"""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "bls_bn254_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -84,55 +108,62 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def make_messages(n, first, seed=0xB15B254):
-    import hashlib
-    import struct
-    return [struct.pack("<Q", i) + hashlib.sha256(struct.pack("<QQ", seed, i)).digest()[:24] for i in range(first, first + n)]
+def make_messages(n, first):
+    from bls_bn254_b200 import scheme
+    m = scheme.synth_messages_np(n, first)
+    return [bytes(r) for r in m]
+
+
+class OracleGroupOps:
+    """The group operations scheme.synth_batch needs (keys, signatures), on the CPU oracle: the reference arm builds the SAME
+    synthetic batch as the GPU arm without touching the CUDA library."""
+
+    def __init__(self, orc, threads):
+        self.o, self.t = orc, threads
+
+    def g1_mul(self, pts, sc): return self.o.g1_mul(pts, sc, nthreads=self.t)
+    def g2_mul(self, pts, sc): return self.o.g2_mul(pts, sc, nthreads=self.t)
+    def hash_to_g1(self, msgs, dst): return self.o.hash_to_g1(msgs, dst, nthreads=self.t)
+    def hash_to_g2(self, msgs, dst): return self.o.hash_to_g2(msgs, dst, nthreads=self.t)
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the reference algorithms on all host cores (the Rust crate cannot be
-    built in this image: no cargo/rustc).  Each step is a bounded sample of the same workload."""
+    """CPU arm: the oracle port of the reference algorithms on all host cores (the Rust crate cannot be built in this image:
+    no cargo/rustc).  Each step runs the FIRST --ref-sample tuples of the very batch the GPU arm verifies (same seed, same
+    4096 keys, same corrupted tuples), and the accept bits are checked against the construction."""
     import bls_bn254_b200 as b
     from oracle import orc
     cores = orc.ncpu()
-    n = args.ref_sample
+    n = min(args.ref_sample, 1 << args.log2n)
     w = args.workload
-    # inputs: made with the oracle itself (untimed)
-    msgs = make_messages(n, 0)
-    sks = [b.scheme.scalar_from_seed(b.scheme.SEED, i % 64) for i in range(n)]
-    sc = b"".join(s.to_bytes(32, "big") for s in sks)
-    if w in ("verify", "aggregate", "verify_rand"):
-        upk = orc.g2_mul(orc.g2_generator() * 64, sc[:64 * 32], nthreads=cores)
-        pks = b"".join(upk[(i % 64) * 128:(i % 64 + 1) * 128] for i in range(n))
-        sigs = orc.g1_mul(orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores), sc, nthreads=cores)
+    ops = OracleGroupOps(orc, cores)
+    variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
+    dst = b.DST_MIN_PK if w in ("verify_pk", "hash_g2") else b.DST_MIN_SIG
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    expected = pks = sigs = agg = g1 = g2 = None
+    if w in ("verify", "verify_pk"):
+        pks, msgs, sigs, expected = b.scheme.synth_batch(ops, n, variant=variant, n_keys=N_KEYS, corrupt_every=CORRUPT_EVERY)
+    elif w in ("verify_rand", "aggregate"):
+        pks, msgs, sigs, _ = b.scheme.synth_batch(ops, n, variant=variant, n_keys=N_KEYS, corrupt_every=0)
         agg = orc.g1_sum(sigs)
-    elif w == "verify_pk":
-        upk = orc.g1_mul(orc.g1_generator() * 64, sc[:64 * 32], nthreads=cores)
-        pks = b"".join(upk[(i % 64) * 64:(i % 64 + 1) * 64] for i in range(n))
-        sigs = orc.g2_mul(orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores), sc, nthreads=cores)
-    elif w == "pairing":
-        g1 = orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores)
-        g2 = orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores)
+    else:
+        msgs = make_messages(n, 0)
+        if w == "pairing":
+            g1, g2 = ops.hash_to_g1(msgs, b.DST_MIN_SIG), ops.hash_to_g2(msgs, b.DST_MIN_PK)
 
     def step():
-        if w == "verify":
-            ok = orc.verify_batch(0, pks, msgs, sigs, b.DST_MIN_SIG, nthreads=cores)
-            assert sum(ok) == n
-        elif w == "verify_pk":
-            ok = orc.verify_batch(1, pks, msgs, sigs, b.DST_MIN_PK, nthreads=cores)
-            assert sum(ok) == n
+        if w in ("verify", "verify_pk"):
+            assert orc.verify_batch(variant, pks, msgs, sigs, dst, nthreads=cores) == expected, "oracle and construction disagree"
         elif w == "verify_rand":
-            ok = orc.verify_batch_randomized(0, pks, msgs, sigs, b.DST_MIN_SIG, RBV_SEED, group=args.group, nthreads=cores)
-            assert all(ok)
+            assert all(orc.verify_batch_randomized(0, pks, msgs, sigs, dst, RBV_SEED, group=args.group, nthreads=cores))
         elif w == "hash_g1":
-            orc.hash_to_g1(msgs, b.DST_MIN_SIG, nthreads=cores)
+            orc.hash_to_g1(msgs, dst, nthreads=cores)
         elif w == "hash_g2":
-            orc.hash_to_g2(msgs, b.DST_MIN_PK, nthreads=cores)
+            orc.hash_to_g2(msgs, dst, nthreads=cores)
         elif w == "pairing":
             orc.pairing_batch(g1, g2, nthreads=cores)
         else:
-            assert orc.aggregate_verify(0, pks, msgs, agg, b.DST_MIN_SIG, nthreads=cores) == 1
+            assert orc.aggregate_verify(0, pks, msgs, agg, dst, nthreads=cores) == 1
 
     for _ in range(args.warmup):
         step()
@@ -141,7 +172,9 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = "%d-tuple sample of the %s workload per step, oracle C port (4x64-bit Montgomery), %d threads" % (n, w, cores)
+    sample = ("the first %d tuples of the arm's own synthetic batch per step (same seed, %d keys, %s), oracle C port of the reference algorithms "
+              "(4x64-bit Montgomery), %d threads; accept bits checked against the construction" %
+              (n, N_KEYS, "1 tuple in %d corrupted" % CORRUPT_EVERY if expected is not None else "all tuples valid", cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC[w], "value": v, "unit": UNIT[w], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -164,10 +197,11 @@ def workload_config(w, args):
                        + str(args.group) + " tuples (64-bit scalars, one final exponentiation per group)",
     }
     return {"workload": names[w] % args.log2n, "tuples_per_gpu": 1 << args.log2n, "variant": "min-pk" if w == "verify_pk" else "min-sig",
-            "msg_bytes": 32, "input_validation": "on-curve + subgroup checks inside the timed region" if getattr(args, "check_subgroup", False) else "none (trusted inputs)",
-            "corrupted_fraction": "1/64" if w in ("verify", "verify_pk") else "0",
+            "msg_bytes": 32, "distinct_keys": N_KEYS,
+            "input_validation": "on-curve + subgroup checks inside the timed region" if getattr(args, "check_subgroup", False) else "none (trusted inputs); identity keys / signatures rejected",
+            "corrupted_fraction": "1/%d" % CORRUPT_EVERY if w in ("verify", "verify_pk") else "0",
             "l2": "L2 flushed between timed steps (256 MiB write)", "sharding": "independent tuples by index, no data-path collective"
-            if w != "aggregate" else "pairs by index; one 385-byte all-gather of Fp12 partials"}
+            if w != "aggregate" else "pairs by index; one ncclAllGather of 400-byte records inside the library"}
 
 
 def main():
@@ -183,6 +217,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=65536, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-subgroup", action="store_true", help="verify workloads: also validate inputs (on-curve + order-r subgroup)")
+    ap.add_argument("--sub", default=None, help="sub-records of the other BASELINE configs: all | none | comma list of c1,c3,c4,c5,pairing "
+                                                "(default: all for the verify workload, none otherwise)")
+    ap.add_argument("--c5-log2n", type=int, default=24, help="log2 of the TOTAL tuples of the c5 sub-record (sharded over the ranks)")
+    ap.add_argument("--c3-log2n", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -195,6 +233,7 @@ def main():
             run_reference(args)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import bls_bn254_b200 as b
@@ -208,25 +247,65 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     w = args.workload
+    subs = args.sub if args.sub is not None else ("all" if w == "verify" else "none")
+    subs = {"all": {"c1", "c3", "c4", "c5", "pairing"}, "none": set()}.get(subs, set(subs.split(",")))
     variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
     vflags = b.CHECK_SUBGROUP if args.check_subgroup else 0
     n = 1 << args.log2n
     ctx = b.Context([local_rank])
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    if world > 1:
+        b.dist.init_comm(ctx, device=dev)   # the library's own NCCL communicator (aggregate path)
 
-    # ---- synthetic inputs (generated on the GPU, untimed) --------------------------------------
+    def dev_bytes(x):
+        return torch.frombuffer(bytearray(x) if isinstance(x, (bytes, bytearray)) else x, dtype=torch.uint8).to(dev)
+
+    def pinned(x):
+        return torch.frombuffer(bytearray(x) if isinstance(x, (bytes, bytearray)) else x, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed_dev(step, steps):
+        """steps passes of `step` (everything enqueued on the library stream), CUDA events on that stream, L2 flushed between
+        passes; returns (sum of device ms, sum of host wall ms)"""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall = 0.0
+        for k in range(steps):
+            flush.fill_(k & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            evs[k][0].record(stream)
+            step()
+            evs[k][1].record(stream)
+            evs[k][1].synchronize()
+            wall += (time.perf_counter() - t0) * 1e3
+        return sum(a.elapsed_time(bb) for a, bb in evs), wall
+
+    # ---- synthetic inputs of the primary workload (generated on the GPU, untimed) --------------------------
     first = rank * n
     dst = b.DST_MIN_PK if w in ("verify_pk", "hash_g2") else b.DST_MIN_SIG
     pks = sigs = agg = g1 = g2 = None
     expected = None
     if w in ("verify", "verify_pk"):
-        pks, msgs, sigs, expected = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096))
+        pks, msgs, sigs, expected = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, N_KEYS), corrupt_every=CORRUPT_EVERY)
     elif w == "verify_rand":
-        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096), corrupt_every=0)
+        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, N_KEYS), corrupt_every=0)
         ngroups = (n + args.group - 1) // args.group
         expected = b"\x01" * ngroups
     elif w == "aggregate":
-        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, 4096), corrupt_every=0)
+        pks, msgs, sigs, _ = b.scheme.synth_batch(ctx, n, variant=variant, first=first, n_keys=min(n, N_KEYS), corrupt_every=0)
         agg_local = b.scheme.aggregate(ctx, sigs, variant)
     else:
         msgs = make_messages(n, first)
@@ -235,9 +314,6 @@ def main():
             g2 = ctx.hash_to_g2(msgs, b.DST_MIN_PK)
     blob, off = b.pack_msgs(msgs)
 
-    def dev_bytes(x):
-        return torch.frombuffer(bytearray(x), dtype=torch.uint8).to(dev)
-
     d_blob = dev_bytes(blob if blob else b"\0")
     d_off = torch.tensor(list(off), dtype=torch.int64, device=dev)
     d_dst = dev_bytes(dst)
@@ -245,25 +321,23 @@ def main():
     d_sigs = dev_bytes(sigs) if sigs else None
     d_g1 = dev_bytes(g1) if g1 else None
     d_g2 = dev_bytes(g2) if g2 else None
-    out_rec = {"verify": 1, "verify_pk": 1, "hash_g1": 64, "hash_g2": 128, "pairing": 384, "aggregate": 385, "verify_rand": 1}[w]
-    d_out = torch.zeros({"aggregate": 385, "verify_rand": (n + args.group - 1) // args.group}.get(w, n * out_rec), dtype=torch.uint8, device=dev)
+    out_rec = {"verify": 1, "verify_pk": 1, "hash_g1": 64, "hash_g2": 128, "pairing": 384, "aggregate": 1, "verify_rand": 1}[w]
+    d_out = torch.zeros({"aggregate": 16, "verify_rand": (n + args.group - 1) // args.group}.get(w, n * out_rec), dtype=torch.uint8, device=dev)
     d_seed = dev_bytes(RBV_SEED)
     d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def job_aggregate_signature(local_sum):
+        """sum over the ranks of the per-rank signature sums (setup, untimed): what rank 0 hands to the aggregate check"""
+        if world == 1:
+            return local_sum
+        t = dev_bytes(local_sum)
+        allp = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allp, t)
+        return ctx.g1_sum(b"".join(bytes(x.cpu().numpy()) for x in allp))
 
     if w == "aggregate":
-        # the aggregate signature of the WHOLE job (all ranks): sum of the per-rank sums, given to rank 0
-        if world > 1:
-            t = dev_bytes(agg_local)
-            allp = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(allp, t)
-            agg = ctx.g1_sum(b"".join(bytes(x.cpu().numpy()) for x in allp))
-        else:
-            agg = agg_local
+        agg = job_aggregate_signature(agg_local)
         d_agg = dev_bytes(agg) if rank == 0 else None
-        gather_buf = [torch.zeros(385, dtype=torch.uint8, device=dev) for _ in range(world)]
-
-    verdict = {}
 
     def step_dev():
         """device-resident pass: everything is enqueued on the library stream"""
@@ -280,25 +354,12 @@ def main():
         elif w == "pairing":
             ctx.pairing_dev(d_g1.data_ptr(), d_g2.data_ptr(), n, d_out.data_ptr(), d_status.data_ptr())
         else:
-            ctx.aggregate_partial_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), n, d_agg.data_ptr() if rank == 0 else None,
-                                      d_dst.data_ptr(), len(dst), 0, d_out.data_ptr(), d_out.data_ptr() + 384)
-            if world > 1:
-                # the path's one exchange step: 385 bytes per rank over NCCL (NVLink / NVSwitch)
-                torch.cuda.current_stream().wait_stream(stream)
-                dist.all_gather(gather_buf, d_out)
-                stream.wait_stream(torch.cuda.current_stream())
-                parts = torch.stack(gather_buf).cpu().numpy()
-            else:
-                ctx.sync()
-                parts = d_out.cpu().numpy().reshape(1, 385)
-            if rank == 0:
-                verdict["ok"] = ctx.aggregate_finish(b"".join(bytes(p[:384]) for p in parts), [int(p[384]) for p in parts])
+            # shards -> product tree -> ONE ncclAllGather (400 B per rank) -> ONE post-gather kernel, all on the library stream
+            ctx.aggregate_verify_dist_dev(variant, d_pks.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), n, d_agg.data_ptr() if rank == 0 else None,
+                                          d_dst.data_ptr(), len(dst), vflags, d_out.data_ptr())
 
     # e2e inputs live in PINNED host memory and go through the host-buffer C entry points (Context.raw): every step copies
     # them to the device, runs the kernels and copies the result back inside the timed region
-    def pinned(x):
-        return torch.frombuffer(bytearray(x), dtype=torch.uint8).pin_memory()
-
     h_blob = pinned(blob if blob else b"\0")
     h_off = torch.tensor(list(off), dtype=torch.int64).pin_memory()
     h_pks = pinned(pks) if pks else None
@@ -325,22 +386,7 @@ def main():
         if w == "pairing":
             ctx.raw("bn254_pairing_batch", h_g1.data_ptr(), h_g2.data_ptr(), n, h_out.data_ptr(), h_ok.data_ptr())
             return None
-        part, bad = ctx.aggregate_partial(variant, pks, (blob, off), agg if rank == 0 else None, dst)
-        if world > 1:
-            t = dev_bytes(part + bytes([bad]))
-            dist.all_gather(gather_buf, t)
-            parts = torch.stack(gather_buf).cpu().numpy()
-        else:
-            parts = [list(part) + [bad]]
-        if rank == 0:
-            return ctx.aggregate_finish(b"".join(bytes(bytearray(p[:384])) for p in parts), [int(p[384]) for p in parts])
-        return None
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        return ctx.aggregate_verify_dist(variant, pks, (blob, off), agg if rank == 0 else None, dst, vflags)
 
     # ---- roofline denominator: INT32 multiply-add peak, measured live --------------------------
     peaks, field_peaks = {}, {}
@@ -362,49 +408,28 @@ def main():
         if expected is not None:
             assert got == expected, "accept bits differ from the construction"
             assert bytes(d_out.cpu().numpy()) == expected, "device-resident accept bits differ from the construction"
-        if w == "aggregate" and rank == 0:
-            assert got == 1 and verdict.get("ok") == 1, "aggregate verification rejected a valid aggregate"
+        if w == "aggregate":
+            assert got == 1 and int(d_out[0].item()) == 1, "aggregate verification rejected a valid aggregate"
         if h_out is not None:
             assert bytes(h_out.numpy()) == bytes(d_out.cpu().numpy()), "host-buffer call and device-resident call disagree"
 
     # ---- timed region: EXACTLY K steps, CUDA events on the launch stream, L2 flushed between steps ----
-    def timed_pass():
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        wall = 0.0
-        for k in range(args.steps):
-            flush.fill_(k & 0xff)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            evs[k][0].record(stream)
-            step_dev()
-            evs[k][1].record(stream)
-            evs[k][1].synchronize()
-            wall += (time.perf_counter() - t0) * 1e3
-        return sum(a.elapsed_time(bb) for a, bb in evs), wall
-
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count
     barrier()
     sampler.start()
-    dev_ms, host_ms = timed_pass()
+    dev_ms, host_ms = timed_dev(step_dev, args.steps)
     barrier()
     clocks = sampler.result()
     launches = ctx.launch_count - launches0
-    if w == "aggregate":
-        dev_ms = host_ms  # the exchange + finish run outside the library stream: wall time of the step
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = max_over_ranks(dev_ms)
     value = n * world * args.steps / (total_ms * 1e-3)
 
     # ---- per-kernel durations for the roofline: the same K steps again with a CUDA event pair around
-    #      every launch.  In this pass the library runs its kernels back to back on one stream (in the
-    #      timed pass above it overlaps the slices of a batch on several streams), so each duration is
-    #      that kernel's alone.
+    #      every launch (the library then runs its kernels back to back on one stream)
     ctx.profile(True)
     ctx.profile_drain()
-    prof_ms, _ = timed_pass()
+    prof_ms, _ = timed_dev(step_dev, args.steps)
     prof = ctx.profile_drain()
     ctx.profile(False)
     barrier()
@@ -415,16 +440,211 @@ def main():
     for k in range(args.steps):
         step_e2e()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     in_bytes = {"verify": len(blob) + 8 * (n + 1) + n * 192 + len(dst), "verify_pk": len(blob) + 8 * (n + 1) + n * 192 + len(dst),
                 "hash_g1": len(blob) + 8 * (n + 1) + len(dst), "hash_g2": len(blob) + 8 * (n + 1) + len(dst), "pairing": n * 192,
                 "aggregate": len(blob) + 8 * (n + 1) + n * 128 + 64 + len(dst), "verify_rand": len(blob) + 8 * (n + 1) + n * 192 + len(dst) + 32}[w]
-    out_bytes = {"verify": n, "verify_pk": n, "hash_g1": n * 65, "hash_g2": n * 129, "pairing": n * 385, "aggregate": 385 + 1,
+    out_bytes = {"verify": n, "verify_pk": n, "hash_g1": n * 65, "hash_g2": n * 129, "pairing": n * 385, "aggregate": 1,
                  "verify_rand": (n + args.group - 1) // args.group}[w]
+
+    # =====================================================================================================
+    # sub-records: the other BASELINE configs, same run, every rank takes part
+    # =====================================================================================================
+    sub = {}
+    ssteps = max(2, min(args.steps, 3))
+
+    if "pairing" in subs:
+        pm = make_messages(n, first + (1 << 40))
+        pg1, pg2 = ctx.hash_to_g1(pm, b.DST_MIN_SIG), ctx.hash_to_g2(pm, b.DST_MIN_PK)
+        dp1, dp2 = dev_bytes(pg1), dev_bytes(pg2)
+        dgt = torch.zeros(n * 384, dtype=torch.uint8, device=dev)
+        hp1, hp2 = pinned(pg1), pinned(pg2)
+        hgt = torch.zeros(n * 384, dtype=torch.uint8).pin_memory()
+        hst = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        run = lambda: ctx.pairing_dev(dp1.data_ptr(), dp2.data_ptr(), n, dgt.data_ptr(), d_status.data_ptr())
+        run(); ctx.sync()
+        barrier()
+        ms, _ = timed_dev(run, ssteps)
+        ms = max_over_ranks(ms)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ssteps):
+            ctx.raw("bn254_pairing_batch", hp1.data_ptr(), hp2.data_ptr(), n, hgt.data_ptr(), hst.data_ptr())
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert bytes(hgt.numpy()) == bytes(dgt.cpu().numpy()), "pairing: host-buffer call and device-resident call disagree"
+        check = None
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import orc
+            assert orc.pairing_batch(pg1[:64 * 64], pg2[:128 * 64], nthreads=orc.ncpu()) == bytes(hgt[:384 * 64].numpy()), "pairing differs from the oracle"
+            check = "first 64 GT elements byte-equal to the oracle"
+        sub["pairing"] = {"config": "2^%d standalone pairings per GPU (bn254_pairing_batch: one Miller loop + one final exponentiation each)" % args.log2n,
+                          "pairings_per_sec": n * world * ssteps / (ms * 1e-3), "ms_per_step": ms / ssteps, "steps": ssteps,
+                          "e2e_pairings_per_sec": n * world * ssteps / (ems * 1e-3), "checked": check}
+        del dp1, dp2, dgt
+        torch.cuda.empty_cache()
+
+    if "c3" in subs:
+        n3 = 1 << args.c3_log2n
+        m3 = b.scheme.synth_messages_np(n3, rank * n3 + (1 << 41))
+        off3 = np.arange(0, 32 * (n3 + 1), 32, dtype=np.uint64)
+        dm3, do3 = torch.from_numpy(m3.reshape(-1)).to(dev), torch.from_numpy(off3.view(np.int64)).to(dev)
+        hm3, ho3 = torch.from_numpy(m3.reshape(-1)).pin_memory(), torch.from_numpy(off3.view(np.int64)).pin_memory()
+        rec3 = {}
+        for grp, rec, dstg in ((1, 64, b.DST_MIN_SIG), (2, 128, b.DST_MIN_PK)):
+            dd = dev_bytes(dstg)
+            dout = torch.zeros(n3 * rec, dtype=torch.uint8, device=dev)
+            dst3 = torch.zeros(n3, dtype=torch.uint8, device=dev)
+            hout = torch.zeros(n3 * rec, dtype=torch.uint8).pin_memory()
+            hst3 = torch.zeros(n3, dtype=torch.uint8).pin_memory()
+            fn = ctx.hash_to_g1_dev if grp == 1 else ctx.hash_to_g2_dev
+            run = lambda: fn(dm3.data_ptr(), do3.data_ptr(), n3, dd.data_ptr(), len(dstg), 2, dout.data_ptr(), dst3.data_ptr())
+            run(); ctx.sync()
+            barrier()
+            ms, _ = timed_dev(run, ssteps)
+            ms = max_over_ranks(ms)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ssteps):
+                ctx.raw("bn254_hash_to_g1" if grp == 1 else "bn254_hash_to_g2", hm3.data_ptr(), ho3.data_ptr(), n3, dstg, len(dstg), hout.data_ptr(), hst3.data_ptr())
+            ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            assert bytes(hout[:rec * 4096].numpy()) == bytes(dout[:rec * 4096].cpu().numpy()) and int(hst3.min()) == 1
+            check = None
+            if rank == 0 and not args.no_cpu_baseline:
+                from oracle import orc
+                k3 = 2048 if grp == 1 else 512
+                ref = (orc.hash_to_g1 if grp == 1 else orc.hash_to_g2)([bytes(r) for r in m3[:k3]], dstg, nthreads=orc.ncpu())
+                assert ref == bytes(hout[:rec * k3].numpy()), "hash_to_g%d differs from the oracle" % grp
+                check = "first %d points byte-equal to the oracle" % k3
+            rec3["hash_g%d" % grp] = {"hashes_per_sec": n3 * world * ssteps / (ms * 1e-3), "ms_per_step": ms / ssteps,
+                                      "e2e_hashes_per_sec": n3 * world * ssteps / (ems * 1e-3), "checked": check}
+            del dout, dst3
+        sub["c3"] = dict(rec3, config="hash_to_curve: 2^%d 32-byte messages per GPU to G1 and to G2 (expand_message_xmd SHA-256 + SvdW [+ cofactor clearing])" % args.c3_log2n,
+                         steps=ssteps, scaling="weak")
+        del dm3, do3
+        torch.cuda.empty_cache()
+
+    if "c4" in subs:
+        # BASELINE config 4: 2^16 signatures in TOTAL as one multi-Miller product + a single final exponentiation, sharded over the ranks
+        n4_total = 1 << 16
+        lo4, hi4 = b.dist.shard_range(n4_total, world, rank)
+        n4 = hi4 - lo4
+        pk4, m4, s4, _ = b.scheme.synth_batch(ctx, n4, variant=0, first=(1 << 42) + lo4, n_keys=min(n4, N_KEYS), corrupt_every=0)
+        agg4 = job_aggregate_signature(b.scheme.aggregate(ctx, s4, 0))
+        blob4, off4 = b.pack_msgs(m4)
+        dpk4, dbl4 = dev_bytes(pk4), dev_bytes(blob4)
+        dof4 = torch.tensor(list(off4), dtype=torch.int64, device=dev)
+        dag4 = dev_bytes(agg4) if rank == 0 else None
+        dds4 = dev_bytes(b.DST_MIN_SIG)
+        dok4 = torch.zeros(16, dtype=torch.uint8, device=dev)
+        run = lambda: ctx.aggregate_verify_dist_dev(0, dpk4.data_ptr(), dbl4.data_ptr(), dof4.data_ptr(), n4, dag4.data_ptr() if rank == 0 else None,
+                                                    dds4.data_ptr(), len(b.DST_MIN_SIG), 0, dok4.data_ptr())
+        run(); ctx.sync()
+        assert int(dok4[0].item()) == 1, "c4: a valid aggregate was rejected"
+        barrier()
+        ms, _ = timed_dev(run, ssteps)
+        ms = max_over_ranks(ms)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ssteps):
+            v4 = ctx.aggregate_verify_dist(0, pk4, (blob4, off4), agg4 if rank == 0 else None, b.DST_MIN_SIG)
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert v4 == 1
+        # a tampered message on the LAST rank must flip the verdict on every rank (the exchange really carries the partials)
+        m4b = list(m4)
+        if rank == world - 1:
+            m4b[-1] = b"tampered"
+        assert ctx.aggregate_verify_dist(0, pk4, m4b, agg4 if rank == 0 else None, b.DST_MIN_SIG) == 0, "c4: a tampered message was accepted"
+        check = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import orc
+            k4 = 4096
+            assert orc.aggregate_verify(0, pk4[:128 * k4], m4[:k4], orc.g1_sum(s4[:64 * k4]), b.DST_MIN_SIG, nthreads=orc.ncpu()) == 1
+            check = "verdict equals the oracle's on the first 2^12 tuples"
+        sub["c4"] = {"config": "aggregate verify: 2^16 signatures on distinct messages in total, sharded over %d rank(s); per rank hash -> Miller loops -> product "
+                               "tree -> one 400-byte record; ONE ncclAllGather inside the library; one post-gather kernel (product, single final exponentiation, compare)" % world,
+                     "signatures_total": n4_total, "signatures_per_sec": n4_total * ssteps / (ms * 1e-3), "ms_per_aggregate": ms / ssteps, "steps": ssteps,
+                     "e2e_signatures_per_sec": n4_total * ssteps / (ems * 1e-3), "verdict": 1, "tampered_verdict": 0, "comm_nranks": ctx.comm_nranks if world > 1 else 1,
+                     "scaling": "strong", "checked": check}
+        del dpk4, dbl4, dof4
+
+    if "c5" in subs:
+        # BASELINE config 5: 2^24 tuples in TOTAL sharded over the ranks, through the host-buffer call (pinned buffers, chunk pipeline)
+        n5_total = 1 << args.c5_log2n
+        lo5, hi5 = b.dist.shard_range(n5_total, world, rank)
+        n5 = hi5 - lo5
+        tg0 = time.perf_counter()
+        pk5, m5, of5, sg5, ex5 = b.scheme.synth_batch_np(ctx, n5, variant=0, first=(1 << 43) + lo5, n_keys=N_KEYS, corrupt_every=CORRUPT_EVERY)
+        gen_s = time.perf_counter() - tg0
+        hpk5, hm5 = torch.from_numpy(pk5.reshape(-1)).pin_memory(), torch.from_numpy(m5.reshape(-1)).pin_memory()
+        hof5, hsg5 = torch.from_numpy(of5.view(np.int64)).pin_memory(), torch.from_numpy(sg5.reshape(-1)).pin_memory()
+        hok5 = torch.zeros(n5, dtype=torch.uint8).pin_memory()
+        wn = min(n5, 1 << 18)   # warm-up: one chunk (allocates the staging buffers)
+        ctx.raw("bn254_verify_batch", 0, hpk5.data_ptr(), hm5.data_ptr(), hof5.data_ptr(), hsg5.data_ptr(), wn, b.DST_MIN_SIG, len(b.DST_MIN_SIG), 0, hok5.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        ctx.raw("bn254_verify_batch", 0, hpk5.data_ptr(), hm5.data_ptr(), hof5.data_ptr(), hsg5.data_ptr(), n5, b.DST_MIN_SIG, len(b.DST_MIN_SIG), 0, hok5.data_ptr())
+        exact_s = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(hok5.numpy(), ex5), "c5: accept bits differ from the construction"
+        grp5 = 256
+        ng5 = (n5 + grp5 - 1) // grp5
+        want5 = np.minimum.reduceat(ex5, np.arange(0, n5, grp5))
+        hgr5 = torch.zeros(ng5, dtype=torch.uint8).pin_memory()
+        ctx.raw("bn254_verify_batch_randomized", 0, hpk5.data_ptr(), hm5.data_ptr(), hof5.data_ptr(), hsg5.data_ptr(), wn, b.DST_MIN_SIG, len(b.DST_MIN_SIG), 0,
+                RBV_SEED, 64, grp5, hgr5.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        ctx.raw("bn254_verify_batch_randomized", 0, hpk5.data_ptr(), hm5.data_ptr(), hof5.data_ptr(), hsg5.data_ptr(), n5, b.DST_MIN_SIG, len(b.DST_MIN_SIG), 0,
+                RBV_SEED, 64, grp5, hgr5.data_ptr())
+        rand_s = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(hgr5.numpy(), want5), "c5: randomised group verdicts differ from the construction"
+        check = None
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import orc
+            lo = (1 << 18) - 128 if n5 > (1 << 18) else 0
+            k5 = min(256, n5 - lo)
+            ref = orc.verify_batch(0, pk5[lo:lo + k5].tobytes(), [bytes(r) for r in m5[lo:lo + k5]], sg5[lo:lo + k5].tobytes(), b.DST_MIN_SIG, nthreads=orc.ncpu())
+            assert ref == bytes(hok5[lo:lo + k5].numpy()), "c5: accept bits differ from the oracle"
+            check = "all accept bytes equal the construction; %d tuples straddling the first chunk boundary byte-equal to the oracle" % k5
+        sub["c5"] = {"config": "batch verify 2^%d independent (pk, msg, sig) tuples in total (min-sig, %d keys, 1/%d corrupted) sharded over %d rank(s), "
+                               "through bn254_verify_batch on pinned host buffers: chunks of 2^18, upload / kernels / download overlapped" %
+                               (args.c5_log2n, N_KEYS, CORRUPT_EVERY, world),
+                     "tuples_total": n5_total, "tuples_per_rank": n5, "scaling": "strong",
+                     "exact": {"seconds": exact_s, "verifications_per_sec": n5_total / exact_s},
+                     "randomized": {"seconds": rand_s, "verifications_per_sec": n5_total / rand_s, "group": grp5, "rand_bits": 64},
+                     "h2d_bytes_per_rank": int(pk5.nbytes + m5.nbytes + of5.nbytes + sg5.nbytes), "d2h_bytes_per_rank": int(n5),
+                     "data_generation_s": gen_s, "checked": check}
+        del hpk5, hm5, hof5, hsg5, pk5, m5, sg5
+
+    c1 = None
+    if "c1" in subs and rank == 0:
+        # BASELINE config 1: sign + verify of ONE 32-byte message (latency).  The GPU library with n = 1, and the CPU port.
+        sk = b.scheme.SecretKey(b.scheme.scalar_from_seed(b.scheme.SEED, 7))
+        msg1 = [hashlib.sha256(b"config 1").digest()]
+        pk1 = b.scheme.public_keys(ctx, [sk], 0)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sig1 = b.scheme.sign(ctx, [sk], msg1, 0)
+        t_sign = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ok1 = ctx.verify_batch(0, pk1, msg1, sig1, b.DST_MIN_SIG)
+        t_ver = (time.perf_counter() - t0) / reps
+        assert ok1 == b"\x01"
+        c1 = {"config": "sign + verify of one 32-byte message (latency of a lone call)", "gpu_sign_ms": t_sign * 1e3, "gpu_verify_ms": t_ver * 1e3}
+        if not args.no_cpu_baseline:
+            from oracle import orc
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                s_cpu = orc.g1_mul(orc.hash_to_g1(msg1, b.DST_MIN_SIG), sk.to_bytes())
+            c1["cpu_sign_ms"] = (time.perf_counter() - t0) / reps * 1e3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ok_cpu = orc.verify_batch(0, pk1, msg1, s_cpu, b.DST_MIN_SIG, nthreads=1)
+            c1["cpu_verify_ms"] = (time.perf_counter() - t0) / reps * 1e3
+            assert s_cpu == sig1 and ok_cpu == b"\x01", "c1: GPU and CPU signatures differ"
+            c1["note"] = "identical signature bytes; a lone pairing is a latency-bound chain, the GPU path is for batches"
+        sub["c1"] = c1
 
     if rank != 0:
         if world > 1:
@@ -443,31 +663,63 @@ def main():
     top_name, (top_cnt, top_ms, top_items) = top[0][0], top[1]
     peak_name = max(peaks, key=peaks.get)
     peak = peaks[peak_name]
-    lanes = 2 if top_name.endswith("_l2") else 1          # lane-pair kernels: two threads per item
-    top_items //= lanes
-    top_ops = KERNEL_M.get(top_name[:-3] if lanes == 2 else top_name, 0) * M_IMAD * top_items
+    execd = executed_ops()
+
+    def base(name):
+        return name[:-3] if name.endswith("_l2") else name
+
+    def kernel_row(name, cnt, ms, items):
+        lanes = 2 if name.endswith("_l2") else 1          # lane-pair kernels: two threads per item
+        it = items // lanes
+        per = ms / cnt * 1e-3
+        row = {"ms_per_launch": ms / cnt, "items": it}
+        if base(name) in KERNEL_M:
+            row["canonical_M"] = KERNEL_M[base(name)]
+            row["frac_canonical"] = KERNEL_M[base(name)] * M_IMAD * it / per / peak
+        if base(name) in execd:
+            row["executed_M"] = round(execd[base(name)] / M_IMAD, 1)
+            row["frac_executed"] = execd[base(name)] * it / per / peak
+        return row
+
+    kernels = {}
+    for (name, items), (cnt, ms, _) in sorted(agg_t.items(), key=lambda kv: -kv[1][1]):
+        if ms / kern_ms_total >= 0.002:
+            kernels["%s[%d]" % (name, items)] = kernel_row(name, cnt, ms, items)
+    top_row = kernel_row(top_name, top_cnt, top_ms, top_items)
+    top_ops = KERNEL_M.get(base(top_name), 0) * M_IMAD * top_row["items"]
     achieved = top_ops / (top_ms / top_cnt * 1e-3) if top_ms else 0.0
-    whole_ops = WORK_M[w] * M_IMAD * n * args.steps
-    traffic = None
-    try:  # DRAM bytes of the dominant kernel from the committed ncu capture (same launch size only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tr["items_per_launch"] == top_items and top_name in tr["kernels"]:
+    # Where a kernel executes much less multiplier work than the canonical count assumes (hashing: Jacobi symbols and binary
+    # GCDs on the ALU pipe instead of exponentiations), the canonical fraction is not a pipe utilisation and can pass 1:
+    # `frac` is then the executed fraction, the canonical one is kept beside it as `frac_canonical`.
+    frac = achieved / peak
+    if "frac_executed" in top_row and top_row["frac_executed"] < 0.9 * frac:
+        frac = top_row["frac_executed"]
+        achieved = frac * peak
+    whole_exec = sum(execd.get(base(nm), 0) * (it // (2 if nm.endswith("_l2") else 1)) * cnt for (nm, it), (cnt, ms, _) in agg_t.items())
+    traffic, traffic_note = None, "no ncu capture of these kernel sources is committed"
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture: same sources, same launch size only
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("source_sha16") != source_sha16():
+            traffic_note = "profiles/traffic.json was captured from other kernel sources (%s): not quoted" % tr.get("source_sha16")
+        elif tr["items_per_launch"] == top_row["items"] and top_name in tr["kernels"]:
             traffic = tr["kernels"][top_name]["dram_read_bytes"] + tr["kernels"][top_name]["dram_write_bytes"]
+            traffic_note = "DRAM bytes per launch (ncu --set full, profiles/traffic.json, same kernel sources): per-thread stack write-back, not algorithmic bytes"
     except Exception:
         pass
     roofline = {
-        "bound": "int32_imad", "kernel": top_name, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TIMAD-op/s", "frac": achieved / peak,
-        "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json): local-memory stack write-back, not algorithmic bytes",
+        "bound": "int32_imad", "kernel": top_name, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TIMAD-op/s", "frac": frac,
+        "frac_canonical": top_row.get("frac_canonical"), "frac_executed": top_row.get("frac_executed"),
+        "traffic": traffic, "traffic_unit": traffic_note,
         "peak_source": "measured live by bn254_imad_peak (%s chains, all SMs); MEASURED_PEAKS.json has no INT32 figure" % peak_name,
         "peaks_measured_tops": {k: v / 1e12 for k, v in peaks.items()},
         "field_level_tops": field_peaks,
-        "frac_executed": (KERNEL_M_EXECUTED[top_name] * M_IMAD * top_items / (top_ms / top_cnt * 1e-3) / peak) if top_name in KERNEL_M_EXECUTED and top_ms else None,
-        "frac_note": "frac / whole_step_frac count the CANONICAL multiplier work of SURVEY.md 8(d) (Euler-criterion and Fermat exponentiations "
-                     "included); is_square and inversion run as binary Jacobi / GCD loops on the ALU pipe, so canonical fractions can exceed "
-                     "the share of the IMAD pipe really used (frac_executed where it is known)",
+        "frac_note": "frac = canonical multiplier work of SURVEY.md 8(d) (items x M x 264 INT32 multiply-adds) / kernel time / peak; frac_executed counts the "
+                     "work the kernel really issues (profiles/executed_ops.json, from the host build's op counter).  Per kernel under `kernels`.",
         "algorithmic_ops_per_launch": top_ops, "kernel_ms_per_launch": top_ms / top_cnt, "kernel_share_of_step": top_ms / kern_ms_total,
-        "whole_step_frac": whole_ops / (dev_ms * 1e-3) / peak,
+        "whole_step_frac_canonical": WORK_M[w] * M_IMAD * n * args.steps / (dev_ms * 1e-3) / peak,
+        "whole_step_frac_executed": whole_exec / (prof_ms * 1e-3) / peak if whole_exec else None,
         "kernel_pass_ms_per_step": prof_ms / args.steps,
+        "kernels": kernels,
         "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(by_name.items(), key=lambda kv: -kv[1])},
         "hbm": {"algorithmic_bytes_per_step": in_bytes + out_bytes, "achieved_gbs": (in_bytes + out_bytes) / (dev_ms / args.steps * 1e-3) / 1e9,
                 "peak_gbs": 6553.3, "note": "HBM non-binding"},
@@ -511,8 +763,11 @@ def main():
         "e2e": {"value": n * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT[w], "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "pairings_per_sec": value * (2 if w in ("verify", "verify_pk") else 1) if w in ("verify", "verify_pk", "pairing", "aggregate", "verify_rand") else None,
+        # "pairing" = one Miller loop + one final exponentiation: the standalone bn254_pairing_batch rate
+        "pairings_per_sec": sub["pairing"]["pairings_per_sec"] if "pairing" in sub else (value if w == "pairing" else None),
+        "miller_loops_per_sec_inside_verify": value * 2 if w in ("verify", "verify_pk") else None,
     }
+    line.update(sub)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

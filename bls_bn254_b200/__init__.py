@@ -3,3 +3,11 @@ final exponentiation) behind a C ABI.  CUDA only: importing works anywhere, comp
 from .api import (CHECK_ON_CURVE, CHECK_SUBGROUP, DST_MIN_PK, DST_MIN_SIG, G1_GENERATOR, G2_GENERATOR, MIN_PK, MIN_SIG, R_ORDER, Bn254Error, Context,  # noqa: F401
                   pack_msgs)
 from . import scheme  # noqa: F401
+
+
+def __getattr__(name):
+    # bls_bn254_b200.dist needs torch.distributed: imported on first use only
+    if name == "dist":
+        import importlib
+        return importlib.import_module(".dist", __name__)
+    raise AttributeError(name)

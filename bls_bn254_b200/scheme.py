@@ -159,3 +159,63 @@ def synth_batch(ctx, n, variant=MIN_SIG, seed=SEED, first=0, msg_len=32, corrupt
                 sigs[j * rsig:(j + 1) * rsig] = sigs[o * rsig:(o + 1) * rsig]
             expected[j] = 0
     return bytes(pks), msgs, bytes(sigs), bytes(expected)
+
+
+def _splitmix64(x):
+    """numpy uint64 array -> SplitMix64 output (wrapping arithmetic)"""
+    import numpy as np
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def synth_messages_np(n, first=0, seed=SEED):
+    """n distinct 32-byte messages as an (n, 32) uint8 array: bytes 0..7 = the tuple's global index (little-endian, which
+    makes them distinct), bytes 8..31 = SplitMix64(seed, index) output.  Vectorised: 2^24 messages take about a second."""
+    import numpy as np
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    cols = [idx]
+    with np.errstate(over="ignore"):
+        for k in range(3):
+            cols.append(_splitmix64(idx * np.uint64(3) + np.uint64(k) + np.uint64(seed) * np.uint64(0x100000001B3)))
+    return np.ascontiguousarray(np.stack(cols, axis=1).astype("<u8")).view(np.uint8).reshape(n, 32)
+
+
+def synth_batch_np(ctx, n, variant=MIN_SIG, seed=SEED, first=0, n_keys=4096, corrupt_every=64):
+    """The synthetic workload of SURVEY.md 8(d) for BIG batches (BASELINE config 5: 2^24 tuples): the same construction as
+    synth_batch -- n_keys distinct random keys used round-robin, distinct 32-byte messages, signatures made on the GPU,
+    every corrupt_every-th tuple broken in one of three ways -- with every per-tuple step vectorised in numpy.
+    Returns numpy arrays (pks [n, rpk], msgs [n, 32], offsets [n + 1] u64, sigs [n, rsig], expected [n])."""
+    import numpy as np
+    nk = min(n_keys, n)
+    uniq = [SecretKey(scalar_from_seed(seed, i)) for i in range(nk)]
+    rpk, rsig = (128, 64) if variant == MIN_SIG else (64, 128)
+    upk = np.frombuffer(public_keys(ctx, uniq, variant), dtype=np.uint8).reshape(nk, rpk)
+    usc = np.frombuffer(b"".join(s.to_bytes() for s in uniq), dtype=np.uint8).reshape(nk, 32)
+    key_of = (np.arange(first, first + n, dtype=np.int64) % nk)
+    pks = upk[key_of].copy()
+    msgs = synth_messages_np(n, first, seed)
+    off = np.arange(0, 32 * (n + 1), 32, dtype=np.uint64)
+    sc = np.ascontiguousarray(usc[key_of]).reshape(-1)     # 1-D uint8 views: len() is the byte count the wrappers check
+    dst = _dst(variant)
+    if variant == MIN_SIG:
+        sig_b = ctx.g1_mul(ctx.hash_to_g1((msgs.reshape(-1), off), dst), sc)
+    else:
+        sig_b = ctx.g2_mul(ctx.hash_to_g2((msgs.reshape(-1), off), dst), sc)
+    sigs = np.frombuffer(sig_b, dtype=np.uint8).reshape(n, rsig).copy()
+    expected = np.ones(n, dtype=np.uint8)
+    if corrupt_every and n > 1:
+        j = np.arange(corrupt_every // 2, n, corrupt_every, dtype=np.int64)
+        kind = (j // corrupt_every) % 3
+        o = (j + 1) % n
+        same_key = key_of[o] == key_of[j]
+        j0 = j[kind == 0]
+        msgs[j0, 31] ^= 1                                   # bit flip in the message
+        m1 = (kind == 1) & ~same_key
+        pks[j[m1]] = pks[o[m1]]                             # somebody else's key
+        m2 = (kind == 2) | ((kind == 1) & same_key)
+        sigs[j[m2]] = sigs[o[m2]]                           # a valid signature of another tuple
+        expected[j] = 0
+    return pks, msgs, off, sigs, expected

@@ -399,3 +399,33 @@ EXPORT int sim_fp12_op_l2(int op, const uint8_t *a, const uint8_t *b, uint8_t *o
     return 0;
 }
 
+
+// Executed multiplier work (INT32 multiply-add operations, fp.cuh: BN_COUNT_OPS) of ONE kernel body on ONE item, wire
+// codecs excluded.  kind: 0 hash_to_g1, 1 hash_to_g2 (count 2), 2 one-pair Miller loop, 3 two-pair Miller loop with the
+// fixed -g2 table, 4 two-pair Miller loop (both variable), 5 final exponentiation (of the kind-2 result), 6 G2 subgroup check.
+EXPORT unsigned long long sim_count_item(int kind, const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, const uint8_t *msg,
+                                         size_t mlen, const uint8_t *dst, size_t dst_len) {
+    g1m a, c;
+    g2m b, d;
+    uint8_t fa = 0, fb = 0, fc = 0, fd = 0, fl;
+    fp12 f;
+    if (kind >= 2) {
+        item_g1_decode(a, fa, p0, false);
+        item_g2_decode(b, fb, q0, false);
+        item_g1_decode(c, fc, p1, false);
+        item_g2_decode(d, fd, q1, false);
+    }
+    if (kind == 5) item_miller1(f, fl, a, fa, b, fb);
+    g_ops.store(0);
+    switch (kind) {
+        case 0: item_hash_g1(a, fl, msg, mlen, dst, (uint32_t)dst_len, 2); break;
+        case 1: item_hash_g2(b, fl, msg, mlen, dst, (uint32_t)dst_len, 2); break;
+        case 2: item_miller1(f, fl, a, fa, b, fb); break;
+        case 3: item_miller2<true>(f, fl, a, fa, nullptr, 0, c, fc, d, fd); break;
+        case 4: item_miller2<false>(f, fl, a, fa, &b, fb, c, fc, d, fd); break;
+        case 5: item_final_exp(f); break;
+        case 6: (void)item_g2_torsion_free(b, fb); break;
+        default: break;
+    }
+    return g_ops.load();
+}
