@@ -322,3 +322,22 @@ def test_op_counts(orc):
     orc.final_exponentiation(pm.gt_to_repr(pm.multi_miller_loop([(pm.G1_GEN, pm.G2_GEN)])))
     fe = orc.mul_count(reset=True)
     assert 8000 < ml < 20000 and 8000 < fe < 20000
+
+
+def test_pairing_as_written_audit(orc, kats):
+    """the literal transcription of the reference's pairing code (oracle/as_written.py: xi = 1 + u, the
+    X >> 1 loop, mul_by_014, the BLS12 final exponentiation, Fp6::square's typo) reproduces the value recorded in SURVEY.md
+    Appendix A, differs from the reference's own known-answer Gt::generator() (pairings.rs:387-479), does not have order r and
+    is not bilinear -- which is why the oracle, the model and the kernels implement the function that KAT pins (Tier B)."""
+    from oracle import as_written as aw
+    g = aw.pairing_as_written(pm.G1_GEN, pm.G2_GEN)
+    assert g[0][0] == (0x2c48d725fcc388048fa1c20b06fa1144a9754c10f54b8ff41173de73d917e7e1,
+                       0x2398cff41bcafe8da25d65e5cc8980a8c6fa5cb9d76d8ed3da3022ffd49d341e)
+    flat = [c for h in g for f2 in h for c in f2]
+    kat = [int(x, 16) for x in kats["gt_generator"]]
+    assert flat != kat
+    assert aw.f12_pow(g, pm.R_ORDER) != aw.F12_ONE                      # pairings.rs:977-979 would fail
+    g2 = aw.pairing_as_written(pm.g1_mul(pm.G1_GEN, 2), pm.G2_GEN)
+    assert g2 != aw.f12_mul(g, g)                                       # e(2P, Q) != e(P, Q)^2
+    # the intended function, by contrast, meets the KAT (both oracles)
+    assert [c for h in pm.pairing(pm.G1_GEN, pm.G2_GEN) for f2 in h for c in f2] == kat
