@@ -26,6 +26,7 @@ enum Scratch {
     // second set of staging buffers: the chunk pipeline copies chunk k+1 in while the kernels of chunk k read the first set
     S_IN_A2, S_IN_B2, S_IN_C2, S_MSGS2, S_OFF2, S_OUT2, S_STATUS2,
     S_AGG_SEND, S_AGG_RECV,   // agg_rec: this rank's record / the gathered records of all ranks
+    S_VM_SCRATCH,             // per-item scratch variables of the slot-machine final exponentiation
     S_COUNT
 };
 // staging set s (0 / 1) of the chunk pipeline
@@ -176,6 +177,72 @@ int prof_end(Dev &d) {
             LAUNCH(d, kscalar, (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                     \
     } while (0)
 
+// The slot-machine shape (d.shape == 3, vm.cuh): a lane pair per item like the lane kernels, one warp per CTA, dynamic shared
+// memory = slots x 32 bytes x BN_VM_TPB.
+#define LAUNCH_VM(d, kern, n, nslot, ...)                                                                   \
+    do {                                                                                                    \
+        if ((n) > 0) {                                                                                      \
+            if (int rcp_ = prof_begin(d, BN_STR(kern), 2 * (size_t)(n))) return rcp_;                       \
+            kern<<<blocks(2 * (size_t)(n), BN_VM_TPB), BN_VM_TPB, BN_VM_SMEM(nslot), (d).cur>>>(__VA_ARGS__); \
+            (d).launches++;                                                                                 \
+            if (int rcp_ = prof_end(d)) return rcp_;                                                        \
+            CK(d, cudaGetLastError());                                                                      \
+        }                                                                                                   \
+    } while (0)
+
+// ---- the pairing kernels behind one call each: the shape (one thread / lane pair / slot machine) is picked here -----------
+int launch_miller2_fixed(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0, const uint8_t *flp0, const g1m *P1, const uint8_t *flp1,
+                         const g2m *Q1, const uint8_t *flq1) {
+    if (d.shape == 3) {
+        LAUNCH_VM(d, k_vm_miller2_fixed, n, vm::NSLOT_M1, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
+        LAUNCH(d, k_vm_fixup_miller2_fixed, n, BN_TPB_HEAVY, F, P0, flp0, P1, flp1, Q1, flq1, n);
+        return 0;
+    }
+    LAUNCH_PAIR(d, k_miller2_fixed, k_miller2_fixed_l2, n, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
+    return 0;
+}
+int launch_miller2(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0, const uint8_t *flp0, size_t p0_stride, const g2m *Q0, const uint8_t *flq0,
+                   const g1m *P1, const uint8_t *flp1, const g2m *Q1, const uint8_t *flq1) {
+    if (d.shape == 3) {
+        LAUNCH_VM(d, k_vm_miller2, n, vm::NSLOT_M2V, F, flf, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1);
+        LAUNCH(d, k_vm_fixup_miller2, n, BN_TPB_HEAVY, F, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1, n);
+        return 0;
+    }
+    LAUNCH_PAIR(d, k_miller2, k_miller2_l2, n, F, flf, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n);
+    return 0;
+}
+int launch_miller1(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P, const uint8_t *flp, const g2m *Q, const uint8_t *flq, int *bad) {
+    if (d.shape == 3) {
+        LAUNCH_VM(d, k_vm_miller1, n, vm::NSLOT_M1, F, flf, P, flp, Q, flq, n, bad);
+        return 0;
+    }
+    LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, flf, P, flp, Q, flq, n, bad);
+    return 0;
+}
+// F[t] = ML(P[2t], Q[2t]) * ML(P[2t+1], Q[2t+1]) for t < ceil(ntuples / 2)
+int launch_miller_twin(Dev &d, size_t ntuples, fp12 *F, const g1m *P, const uint8_t *flp, const g2m *Q, const uint8_t *flq, int *bad) {
+    const size_t half = (ntuples + 1) / 2;
+    if (d.shape == 3) {
+        LAUNCH_VM(d, k_vm_miller2, half, vm::NSLOT_M2V, F, (uint8_t *)nullptr, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2);
+        LAUNCH(d, k_vm_fixup_miller2, half, BN_TPB_HEAVY, F, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2, ntuples);
+        if (bad) LAUNCH(d, k_or_flags, ntuples, BN_TPB_LIGHT, bad, flp, ntuples);
+        if (bad) LAUNCH(d, k_or_flags, ntuples, BN_TPB_LIGHT, bad, flq, ntuples);
+        return 0;
+    }
+    LAUNCH_PAIR(d, k_miller_twin, k_miller_twin_l2, half, F, P, flp, Q, flq, ntuples, bad);
+    return 0;
+}
+int launch_final_exp(Dev &d, fp12 *F, size_t n) {
+    if (d.shape == 3) {
+        fp2 *scratch;
+        if (int rc = ensure_t(d, S_VM_SCRATCH, (size_t)vm::FEXP_SCRATCH_FP2 * n, &scratch)) return rc;
+        LAUNCH_VM(d, k_vm_final_exp, n, vm::NSLOT_FEXP, F, n, scratch);
+        return 0;
+    }
+    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, F, n);
+    return 0;
+}
+
 // ---- device-level building blocks (all pointers are device pointers on d) ------------------------
 
 // DST: copies / pre-hashes into scratch when needed.  `dst_on_host` tells where dst lives.
@@ -239,8 +306,9 @@ int dev_pairing(Dev &d, const uint8_t *g1, const uint8_t *g2, size_t n, uint8_t 
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, g1, n, 0);
     LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, g2, n, 0);
-    LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, flf, P, flp, Q, flq, n, (int *)nullptr);
-    if (mode == 0) LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, F, n);
+    if (int rc = launch_miller1(d, n, F, flf, P, flp, Q, flq, (int *)nullptr)) return rc;
+    if (mode == 0)
+        if (int rc = launch_final_exp(d, F, n)) return rc;
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -250,7 +318,7 @@ int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *st
     if (int rc = ensure_t(d, S_F, n, &F)) return rc;
     if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
     LAUNCH(d, k_fp12_decode, n, BN_TPB_LIGHT, F, flf, ml, n);
-    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, F, n);
+    if (int rc = launch_final_exp(d, F, n)) return rc;
     LAUNCH(d, k_fp12_encode, n, BN_TPB_LIGHT, out, status, F, flf, n);
     return 0;
 }
@@ -311,8 +379,7 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
         }
         if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH_PAIR(d, k_miller2_fixed, k_miller2_fixed_l2, n, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
-               b.flq1 + lo, n);
+        if (int rc = launch_miller2_fixed(d, n, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo, b.flq1 + lo)) return rc;
     } else {
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q0 + lo, b.flq0 + lo, sigs + 128 * lo, n, check);
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
@@ -323,10 +390,11 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
 #endif
         }
         if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
-        LAUNCH_PAIR(d, k_miller2, k_miller2_l2, n, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo,
-               b.flp1 + lo, b.Q1 + lo, b.flq1 + lo, n);
+        if (int rc = launch_miller2(d, n, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
+                                    b.flq1 + lo))
+            return rc;
     }
-    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, n, b.F + lo, n);
+    if (int rc = launch_final_exp(d, b.F + lo, n)) return rc;
     LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok + lo, b.F + lo, b.flf + lo, n);
     return 0;
 }
@@ -457,7 +525,7 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
             SEG_LEVELS(d, k_g1p_seg_sum, g1p, S0, SA, SB, n, group, &Sg);
             LAUNCH(d, k_g1p_to_affine, nseg, BN_TPB_HEAVY, GP, gflp, Sg, nseg);
             LAUNCH(d, k_fill_neg_g2, nseg, BN_TPB_LIGHT, GQ, gflq, nseg);
-            LAUNCH_PAIR(d, k_miller1, k_miller1_l2, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, nseg, (int *)nullptr);
+            if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
             if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
         }
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q1, flq1, pks, n, check);
@@ -483,7 +551,7 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
             SEG_LEVELS(d, k_g2p_seg_sum, g2p, S0, SA, SB, n, group, &Sg);
             LAUNCH(d, k_g2p_to_affine, nseg, BN_TPB_HEAVY, GQ, gflq, Sg, nseg);
             LAUNCH(d, k_fill_neg_g1, nseg, BN_TPB_LIGHT, GP, gflp, nseg);
-            LAUNCH_PAIR(d, k_miller1, k_miller1_l2, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, nseg, (int *)nullptr);
+            if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
             if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
         }
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
@@ -500,15 +568,15 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
     // group size is even, 2 (default) when, in addition, one thread per tuple would overfill one wave of lane pairs.
     if (group % 2 == 0 && (BN_RBV_TWIN == 1 || (BN_RBV_TWIN == 2 && 2 * n > d.lane_wave_threads))) {
         const size_t half = (n + 1) / 2;
-        LAUNCH_PAIR(d, k_miller_twin, k_miller_twin_l2, half, F, P1, flp1, Q1, flq1, n, (int *)nullptr);
+        if (int rc = launch_miller_twin(d, n, F, P1, flp1, Q1, flq1, (int *)nullptr)) return rc;
         SEG_LEVELS(d, k_fp12_seg_reduce, fp12, F, FA, FB, half, group / 2, &Fg);
     } else {
-        LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, (uint8_t *)nullptr, P1, flp1, Q1, flq1, n, (int *)nullptr);
+        if (int rc = launch_miller1(d, n, F, (uint8_t *)nullptr, P1, flp1, Q1, flq1, (int *)nullptr)) return rc;
         SEG_LEVELS(d, k_fp12_seg_reduce, fp12, F, FA, FB, n, group, &Fg);
     }
     if (side) CK(d, cudaStreamWaitEvent(d.st, d.ev_hi_join, 0));
     LAUNCH(d, k_fp12_mul_into, nseg, BN_TPB_HEAVY, Fg, Fs, nseg);
-    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, nseg, Fg, nseg);
+    if (int rc = launch_final_exp(d, Fg, nseg)) return rc;
     LAUNCH(d, k_rbv_ok, nseg, BN_TPB_LIGHT, ok, Fg, gbad, nseg);
     return 0;
 }
@@ -558,9 +626,9 @@ int dev_aggregate_rec(Dev &d, int variant, const uint8_t *pks, const uint8_t *ms
     size_t nf = tot;
     if (BN_RBV_TWIN == 1 || (BN_RBV_TWIN == 2 && 2 * tot > d.lane_wave_threads)) {
         nf = (tot + 1) / 2;
-        LAUNCH_PAIR(d, k_miller_twin, k_miller_twin_l2, nf, F, P, flp, Q, flq, tot, dbad);
+        if (int rc = launch_miller_twin(d, tot, F, P, flp, Q, flq, dbad)) return rc;
     } else {
-        LAUNCH_PAIR(d, k_miller1, k_miller1_l2, tot, F, (uint8_t *)nullptr, P, flp, Q, flq, tot, dbad);
+        if (int rc = launch_miller1(d, tot, F, (uint8_t *)nullptr, P, flp, Q, flq, dbad)) return rc;
     }
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, nf, &res, &rec->f)) return rc;
@@ -590,7 +658,7 @@ int dev_aggregate_finish(Dev &d, const uint8_t *partials, const uint8_t *bad, si
     LAUNCH(d, k_or_bytes, kparts, BN_TPB_LIGHT, dbad, bad, kparts);
     fp12 *res;
     if (int rc = dev_fp12_product(d, F, kparts, &res)) return rc;
-    LAUNCH_PAIR(d, k_final_exp, k_final_exp_l2, 1, res, (size_t)1);
+    if (int rc = launch_final_exp(d, res, (size_t)1)) return rc;
     LAUNCH(d, k_finish_ok, 1, 32, ok, res, dbad);
     return 0;
 }
@@ -901,6 +969,13 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
             return rc;
         }
     }
+    for (auto &d : ctx->devs) {   // the slot-machine kernels live on shared memory: ask for the largest carve-out
+        cudaSetDevice(d.id);
+        cudaFuncSetAttribute(k_vm_miller2_fixed, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_vm_miller2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_vm_miller1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_vm_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (const char *s = getenv("BN254_CARVEOUT")) {  // experiment knob: preferred shared-memory carveout (percent) of the pairing kernels
         int v = atoi(s);
         for (auto &d : ctx->devs) {
@@ -930,7 +1005,7 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
     }
     if (const char *s = getenv("BN254_LANES")) {  // shape of the pairing kernels: 0 per launch, 1 one thread, 2 lane pair
         long v = atol(s);
-        if (v >= 0 && v <= 2)
+        if (v >= 0 && v <= 3)
             for (auto &d : ctx->devs) d.shape = (int)v;
     }
     // Several devices in one process: one NCCL communicator per device for the aggregate path's all-gather.  A box without
@@ -957,14 +1032,14 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
 int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value) {
     if (!ctx || !name) return BN254_ERR_ARG;
     std::string k(name);
-    if (k == "lanes" && value >= 0 && value <= 2) {
+    if (k == "lanes" && value >= 0 && value <= 3) {
         for (auto &d : ctx->devs) d.shape = (int)value;
     } else if (k == "chunk" && value > 0) {
         ctx->chunk = (size_t)value;
     } else if (k == "split" && value >= 1 && value <= Dev::MAXSUB) {
         for (auto &d : ctx->devs) d.nsub = (int)value;
     } else {
-        return fail_arg(ctx, "unknown option or value out of range (lanes 0..2, chunk > 0, split 1..8)");
+        return fail_arg(ctx, "unknown option or value out of range (lanes 0..3, chunk > 0, split 1..8)");
     }
     return 0;
 }
@@ -1188,7 +1263,7 @@ int bn254_multi_miller_loop(bn254_ctx *ctx, const uint8_t *g1, const uint8_t *g2
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, flq, db, n, 0);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad, flp, n);
         LAUNCH(d, k_or_flags, n, BN_TPB_LIGHT, dbad + 1, flq, n);
-        LAUNCH_PAIR(d, k_miller1, k_miller1_l2, n, F, (uint8_t *)nullptr, P, flp, Q, flq, n, (int *)nullptr);
+        if (int rc = launch_miller1(d, n, F, (uint8_t *)nullptr, P, flp, Q, flq, (int *)nullptr)) return rc;
         fp12 *res;
         if (int rc = dev_fp12_product(d, F, n, &res)) return rc;
         LAUNCH(d, k_fp12_encode, 1, BN_TPB_LIGHT, dout, (uint8_t *)nullptr, res, (const uint8_t *)nullptr, (size_t)1);

@@ -4,6 +4,7 @@
 // 148 SMs and the memory layout only needs whole-sector accesses (16-byte aligned records).
 #pragma once
 #include "items.cuh"
+#include "vm.cuh"
 
 namespace bn {
 
@@ -238,6 +239,116 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_l2(fp12 *F
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_final_exp_l2(fp12 *F, size_t n) {
     BN_L2_PROLOGUE();
     item_final_exp_l2(F[i]);
+}
+
+// ---- the slot machine (vm.cuh): a lane pair per pairing, every live value in a shared-memory slot, the tower algebra as
+//      constant-memory programs.  Thread t works on item t / 2 exactly as in the lane-pair kernels above (BN_L2_PROLOGUE).
+//      These kernels assume LIVE pairs (no identity input): an item with a dead pair is recomputed afterwards by the fix-up
+//      kernel below with the one-thread code, which knows how to skip a pair (pairings.rs:820-835).  Dynamic shared memory:
+//      slots x 32 bytes x BN_VM_TPB.
+#define BN_VM_SMEM(nslot) ((size_t)(nslot) * 32 * BN_VM_TPB)
+__global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller2_fixed(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+                                                                const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1, size_t n) {
+    extern __shared__ uint4 vm_smem[];
+    BN_L2_PROLOGUE();
+    const vm::Slots M = vm::make_slots(vm_smem);
+    vm::Env E = {};
+    E.sc[0] = &P0[i].x; E.sc[1] = &P0[i].y; E.sc[2] = &P1[i].x; E.sc[3] = &P1[i].y;
+    E.in[2] = &Q1[i].x; E.in[3] = &Q1[i].y;
+    vm::miller(M, E, vm::FAM_M2F);
+    vm::store_f12(F[i], M, lane_par() != 0);
+    flF[i] = ((flP0[i] | flP1[i] | flQ1[i]) & FL_BAD) ? FL_BAD : 0;
+}
+// both pairs variable.  p0_stride = 0 broadcasts one P0 (min-pk: -g1) to every item; `twin`: item t pairs tuples 2t and
+// 2t + 1 of ONE (P, Q) array (k_miller_twin's job), an odd tail item is completed by the fix-up kernel.
+__global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride, const g2m *Q0,
+                                                          const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1,
+                                                          size_t n, size_t step) {
+    extern __shared__ uint4 vm_smem[];
+    BN_L2_PROLOGUE();
+    const vm::Slots M = vm::make_slots(vm_smem);
+    const size_t j = i * step;     // step = 1: item i of four arrays; step = 2 (twin): tuples 2 i (pair 0) and 2 i + 1 (pair 1), P1 = P0 + 1 etc.
+    vm::Env E = {};
+    E.sc[0] = &P0[j * p0_stride].x; E.sc[1] = &P0[j * p0_stride].y; E.sc[2] = &P1[j].x; E.sc[3] = &P1[j].y;
+    E.in[0] = &Q0[j].x; E.in[1] = &Q0[j].y; E.in[2] = &Q1[j].x; E.in[3] = &Q1[j].y;
+    vm::miller(M, E, vm::FAM_M2V);
+    vm::store_f12(F[i], M, lane_par() != 0);
+    if (flF) flF[i] = ((flP0[j * p0_stride] | flQ0[j] | flP1[j] | flQ1[j]) & FL_BAD) ? FL_BAD : 0;
+}
+// one pair; an identity input gives the neutral element (pairings.rs:789-800), written here directly
+__global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller1(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
+                                                          size_t n, int *bad) {
+    extern __shared__ uint4 vm_smem[];
+    BN_L2_PROLOGUE();
+    const vm::Slots M = vm::make_slots(vm_smem);
+    const bool odd = lane_par() != 0;
+    vm::Env E = {};
+    E.sc[2] = &P[i].x; E.sc[3] = &P[i].y;
+    E.in[2] = &Q[i].x; E.in[3] = &Q[i].y;
+    vm::miller(M, E, vm::FAM_M1);
+    const uint8_t fl = flP[i] | flQ[i];
+    if (fl & FL_INF) {          // warp-uniform instruction stream again from here: plain stores
+        fp z, o;
+        fp_set_zero(z);
+        o = vm::const_half(vm::NCONST - 1, odd);     // ONE
+        M.st(0, o);
+#pragma unroll 1
+        for (int k = 1; k < 6; k++) M.st(k, z);
+    }
+    vm::store_f12(F[i], M, odd);
+    if (flF) flF[i] = (fl & FL_BAD) ? FL_BAD : 0;
+    if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
+}
+__global__ void __launch_bounds__(BN_VM_TPB) k_vm_final_exp(fp12 *F, size_t n, fp2 *scratch) {
+    extern __shared__ uint4 vm_smem[];
+    BN_L2_PROLOGUE();
+    const vm::Slots M = vm::make_slots(vm_smem);
+    const bool odd = lane_par() != 0;
+    vm::Env E = {};
+    E.scratch = scratch + i;      // entry e of item i: scratch[e * n + i] (a warp's 16 items are 1 KB contiguous)
+    E.scratch_stride = n;
+    vm::load_f12(M, F[i], odd);
+    vm::final_exp(M, E);
+    vm::store_f12(F[i], M, odd);
+}
+// Fix-up of the two-pair slot-machine kernels: items with an identity input in exactly the way that makes a pair "dead"
+// (contributes 1) are recomputed with the one-thread loop, which skips dead pairs.  One thread per item; all but a
+// vanishing fraction return at once.
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_vm_fixup_miller2_fixed(fp12 *F, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+                                                                          const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t any = flP0[i] | flP1[i] | flQ1[i];
+    if ((any & FL_BAD) || !(any & FL_INF)) return;
+    uint8_t fl;
+    fp12 f;
+    g1m p0, p1;
+    g2m q1;
+    copy_rec(p0, P0[i]);
+    copy_rec(p1, P1[i]);
+    copy_rec(q1, Q1[i]);
+    item_miller2<true>(f, fl, p0, flP0[i], nullptr, 0, p1, flP1[i], q1, flQ1[i]);
+    copy_rec(F[i], f);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_vm_fixup_miller2(fp12 *F, const g1m *P0, const uint8_t *flP0, size_t p0_stride, const g2m *Q0,
+                                                                    const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1, const g2m *Q1,
+                                                                    const uint8_t *flQ1, size_t n, size_t step, size_t ntuples) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t j = i * step;
+    const bool tail = step == 2 && j + 1 >= ntuples;       // twin: the odd last tuple has no partner
+    const uint8_t f0 = flP0[j * p0_stride] | flQ0[j], f1 = tail ? (uint8_t)FL_INF : (uint8_t)(flP1[j] | flQ1[j]);
+    if (((f0 | f1) & FL_BAD) || !((f0 | f1) & FL_INF)) return;
+    uint8_t fl;
+    fp12 f;
+    g1m p0, p1;
+    g2m q0, q1;
+    copy_rec(p0, P0[j * p0_stride]);
+    copy_rec(q0, Q0[j]);
+    copy_rec(p1, tail ? P0[j * p0_stride] : P1[j]);
+    copy_rec(q1, tail ? Q0[j] : Q1[j]);
+    item_miller2<false>(f, fl, p0, f0, &q0, 0, p1, f1, q1, 0);
+    copy_rec(F[i], f);
 }
 
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_fp12_encode(uint8_t *out, uint8_t *status, const fp12 *F, const uint8_t *fl, size_t n) {

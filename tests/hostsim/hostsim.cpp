@@ -429,3 +429,45 @@ EXPORT unsigned long long sim_count_item(int kind, const uint8_t *p0, const uint
     }
     return g_ops.load();
 }
+
+// ---- the slot machine (vm.cuh) on two emulated lanes: fam 0 one pair (p1, q1), 1 two pairs with the fixed -g2 table
+//      (p0; p1, q1), 2 two variable pairs; mode bit 0: also run the final exponentiation.  Wire bytes in, 384 wire bytes out.
+#include "../../bls_bn254_b200/csrc/vm.cuh"
+struct vm_args { int fam, fexp; g1m p0, p1; g2m q0, q1; fp12 F; fp2 scratch[vm::FEXP_SCRATCH_FP2]; };
+static void vm_body(void *vp) {
+    vm_args *a = (vm_args *)vp;
+    fp slots[64];
+    const vm::Slots M = {slots};
+    vm::Env E = {};
+    E.sc[0] = &a->p0.x; E.sc[1] = &a->p0.y; E.sc[2] = &a->p1.x; E.sc[3] = &a->p1.y;
+    E.in[0] = &a->q0.x; E.in[1] = &a->q0.y; E.in[2] = &a->q1.x; E.in[3] = &a->q1.y;
+    E.scratch = a->scratch;
+    E.scratch_stride = 1;
+    const bool odd = bn_host_lane_par() != 0;
+    if (a->fam >= 0) vm::miller(M, E, a->fam);
+    else vm::load_f12(M, a->F, odd);
+    if (a->fexp) vm::final_exp(M, E);
+    uint32_t dummy_in = 0, dummy_out;
+    bn_host_lane_xchg(&dummy_out, &dummy_in, 1);
+    vm::store_f12(a->F, M, odd);
+}
+EXPORT void sim_vm(int fam, int fexp, const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, const uint8_t *f_in, uint8_t *out) {
+    static vm_args a;
+    memset(&a, 0, sizeof a);
+    uint8_t fl;
+    a.fam = fam;
+    a.fexp = fexp;
+    if (p0) item_g1_decode(a.p0, fl, p0, 0);
+    if (q0) item_g2_decode(a.q0, fl, q0, 0);
+    if (p1) item_g1_decode(a.p1, fl, p1, 0);
+    if (q1) item_g2_decode(a.q1, fl, q1, 0);
+    if (f_in) fp12_from_bytes(a.F, f_in);
+    run_pair(vm_body, &a);
+    fp12_to_bytes(out, a.F);
+}
+EXPORT unsigned long long sim_vm_ops(int fam, int fexp, const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, const uint8_t *f_in) {
+    uint8_t out[384];
+    g_ops.store(0);
+    sim_vm(fam, fexp, p0, q0, p1, q1, f_in, out);
+    return g_ops.load();
+}

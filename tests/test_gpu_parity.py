@@ -27,10 +27,11 @@ def B():
     return b
 
 
-@pytest.fixture(params=[1, 2], ids=["one-thread", "lane-pair"])
+@pytest.fixture(params=[1, 2, 3], ids=["one-thread", "lane-pair", "slot-machine"])
 def shape(request, ctx):
-    """Force one shape of the pairing kernels for the test (bn254_ctx_set_option "lanes"): 1 = one thread per pairing (what
-    every batch beyond one wave -- C5's 2^18-tuple chunks -- runs), 2 = two lanes per pairing.  Results are bit-identical."""
+    """Force one shape of the pairing kernels for the test (bn254_ctx_set_option "lanes"): 1 = one thread per pairing, 2 = two
+    lanes per pairing (tower code on local memory), 3 = the slot machine (vm.cuh: two lanes per pairing, operands in shared
+    memory, the tower as constant-memory programs).  Results are bit-identical."""
     ctx.set_option("lanes", request.param)
     yield request.param
     ctx.set_option("lanes", 0)
@@ -227,7 +228,10 @@ def test_verify_vs_oracle(ctx, orc, B, variant, shape):
     # the kernels of the forced shape really ran
     _, names = launched(ctx, lambda: ctx.verify_batch(variant, pks, msgs, sigs, dst))
     want = {0: ("k_miller2_fixed", "k_final_exp"), 1: ("k_miller2", "k_final_exp")}[variant]
-    assert {w + ("_l2" if shape == 2 else "") for w in want} <= names
+    if shape == 3:
+        assert {"k_vm_" + w[2:] for w in want} <= names
+    else:
+        assert {w + ("_l2" if shape == 2 else "") for w in want} <= names
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -642,7 +646,7 @@ def test_verify_c5_shape(orc, B):
         seed = b"\x5a" * 32
         grp, names = launched(c, lambda: c.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=512))
         assert grp == bytes(int(all(exp[g:g + 512])) for g in range(0, n, 512))
-        assert "k_miller_twin" in names
+        assert names & {"k_miller_twin", "k_miller_twin_l2"}      # two tuples per thread / lane pair
     finally:
         c.close()
 

@@ -1,0 +1,113 @@
+"""The pairing slot machine (bls_bn254_b200/csrc/vm.cuh + the generated vm_prog.cuh) before a GPU sees it:
+  1. every routine of tools/gen_vm_programs.py runs in the generator's big-integer simulator against oracle/pymodel.py;
+  2. the committed vm_prog.cuh is what the generator emits (no drift);
+  3. the C++ interpreter itself, compiled for the host with two emulated lanes per pairing (tests/hostsim), reproduces the C
+     oracle byte for byte: Miller loops of all three families, final exponentiation, whole pairings."""
+import ctypes as C
+import pathlib
+import random
+import subprocess
+import sys
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+DST = b"QUUX-V01-CS02-with-BN254G1_XMD:SHA-256_SVDW_RO_"
+
+
+@pytest.fixture(scope="module")
+def gen():
+    import gen_vm_programs as g
+    consts, cidx = g.build_constants()
+    return g, consts, g.routines(cidx)
+
+
+def _flat(f):
+    return [f[0][0], f[0][1], f[0][2], f[1][0], f[1][1], f[1][2]]
+
+
+def test_programs_in_the_simulator(gen):
+    from oracle import pymodel as m
+    g, consts, R = gen
+    rng = random.Random(5)
+    for trial in range(2):
+        P0, P1 = (m.g1_mul(m.G1_GEN, rng.randrange(1, m.R_ORDER)) for _ in range(2))
+        Q0, Q1 = (m.g2_mul(m.G2_GEN, rng.randrange(1, m.R_ORDER)) for _ in range(2))
+        for fam, pairs in (("M2F", [(P0, m.g2_neg(m.G2_GEN)), (P1, Q1)]), ("M1", [(P1, Q1)]), ("M2V", [(P0, Q0), (P1, Q1)])):
+            sim = g.Sim(32, consts)
+            sim.scalars = [P0[0], P0[1], P1[0], P1[1]]
+            sim.inputs = [Q0[0], Q0[1], Q1[0], Q1[1]]
+            assert g.sim_miller(sim, R, fam) == _flat(m.multi_miller_loop(pairs)), fam
+        f = m.multi_miller_loop([(P1, Q1)])
+        sim = g.Sim(32, consts)
+        for i, c in enumerate(_flat(f)):
+            sim.s[i] = c
+        assert g.sim_final_exp(sim, R) == _flat(m.final_exponentiation(f))
+    # the known-answer test of the reference (pairings.rs:970-980) through the simulator
+    sim = g.Sim(32, consts)
+    sim.scalars = [0, 0, m.G1_GEN[0], m.G1_GEN[1]]
+    sim.inputs = [(0, 0), (0, 0), m.G2_GEN[0], m.G2_GEN[1]]
+    g.sim_miller(sim, R, "M1")
+    assert g.sim_final_exp(sim, R) == _flat(m.pairing(m.G1_GEN, m.G2_GEN))
+
+
+def test_committed_programs_match_the_generator(gen, tmp_path):
+    g = gen[0]
+    path = ROOT / "bls_bn254_b200" / "csrc" / "vm_prog.cuh"
+    before = path.read_text()
+    g.emit()
+    after = path.read_text()
+    assert before == after, "bls_bn254_b200/csrc/vm_prog.cuh is stale: run python tools/gen_vm_programs.py"
+
+
+def test_window_digits_are_the_kernels(gen):
+    """the C++ driver reads k::X_WNAF4 / k::ATE_NAF; the simulator's digit strings must denote the same integers"""
+    g = gen[0]
+    x = 0
+    for d in g.wnaf4(g.X_PARAM):
+        x = 2 * x + d
+    assert x == g.X_PARAM
+    assert sum(d << i for i, d in enumerate(g.ATE_NAF)) == 6 * g.X_PARAM + 2 and len(g.ATE_NAF) == 66
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "tests" / "hostsim")])
+    lib = C.CDLL(str(ROOT / "tests" / "hostsim" / "libhostsim.so"))
+    lib.sim_vm.argtypes = [C.c_int, C.c_int] + [C.c_char_p] * 6
+    return lib
+
+
+def _neg_g2(orc):
+    P = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    g = orc.g2_generator()
+    neg = lambda b: ((P - int.from_bytes(b, "big")) % P).to_bytes(32, "big")
+    return g[:64] + neg(g[64:96]) + neg(g[96:])
+
+
+def test_interpreter_on_emulated_lanes_vs_oracle(sim, orc, kats):
+    rng = random.Random(12)
+    msgs = [rng.randbytes(20) for _ in range(4)]
+    g1 = orc.hash_to_g1(msgs, DST)
+    g2 = orc.hash_to_g2(msgs, DST)
+    out = C.create_string_buffer(384)
+    p0, p1, q0, q1 = g1[:64], g1[64:128], g2[:128], g2[128:256]
+    # one pair, Miller loop only / whole pairing
+    sim.sim_vm(0, 0, None, None, p1, q1, None, out)
+    assert out.raw == orc.miller_loop_batch(p1, q1)
+    sim.sim_vm(0, 1, None, None, p1, q1, None, out)
+    assert out.raw == orc.pairing_batch(p1, q1)
+    # two pairs with the fixed -g2 table (the verification shape)
+    sim.sim_vm(1, 0, p0, None, p1, q1, None, out)
+    assert out.raw == orc.multi_miller_loop(p0 + p1, _neg_g2(orc) + q1)
+    # two variable pairs
+    sim.sim_vm(2, 0, p0, q0, p1, q1, None, out)
+    assert out.raw == orc.multi_miller_loop(p0 + p1, q0 + q1)
+    # final exponentiation alone
+    ml = orc.miller_loop_batch(p0, q0)
+    sim.sim_vm(-1, 1, None, None, None, None, ml, out)
+    assert out.raw == orc.final_exponentiation(ml)
+    # pairing(g1, g2) == Gt::generator() (pairings.rs:970-980)
+    sim.sim_vm(0, 1, None, None, orc.g1_generator(), orc.g2_generator(), None, out)
+    assert out.raw == b"".join(bytes.fromhex(x) for x in kats["gt_generator"])
