@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller2_fixed(fp12 *F, uint8_t
     BN_L2_PROLOGUE();
     const vm::Slots M = vm::make_slots(vm_smem);
     vm::Env E = {};
-    E.sc[0] = &P0[i].x; E.sc[1] = &P0[i].y; E.sc[2] = &P1[i].x; E.sc[3] = &P1[i].y;
-    E.in[2] = &Q1[i].x; E.in[3] = &Q1[i].y;
+    E.p0 = &P0[i].x; E.p1 = &P1[i].x;     // g1m = {fp x, y}, g2m = {fp2 x, y}: the coordinates are consecutive
+    E.q1 = &Q1[i].x;
     vm::miller(M, E, vm::FAM_M2F);
     vm::store_f12(F[i], M, lane_par() != 0);
     flF[i] = ((flP0[i] | flP1[i] | flQ1[i]) & FL_BAD) ? FL_BAD : 0;
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller2(fp12 *F, uint8_t *flF,
     const vm::Slots M = vm::make_slots(vm_smem);
     const size_t j = i * step;     // step = 1: item i of four arrays; step = 2 (twin): tuples 2 i (pair 0) and 2 i + 1 (pair 1), P1 = P0 + 1 etc.
     vm::Env E = {};
-    E.sc[0] = &P0[j * p0_stride].x; E.sc[1] = &P0[j * p0_stride].y; E.sc[2] = &P1[j].x; E.sc[3] = &P1[j].y;
-    E.in[0] = &Q0[j].x; E.in[1] = &Q0[j].y; E.in[2] = &Q1[j].x; E.in[3] = &Q1[j].y;
+    E.p0 = &P0[j * p0_stride].x; E.p1 = &P1[j].x;
+    E.q0 = &Q0[j].x; E.q1 = &Q1[j].x;
     vm::miller(M, E, vm::FAM_M2V);
     vm::store_f12(F[i], M, lane_par() != 0);
     if (flF) flF[i] = ((flP0[j * p0_stride] | flQ0[j] | flP1[j] | flQ1[j]) & FL_BAD) ? FL_BAD : 0;
@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(BN_VM_TPB) k_vm_miller1(fp12 *F, uint8_t *flF,
     const vm::Slots M = vm::make_slots(vm_smem);
     const bool odd = lane_par() != 0;
     vm::Env E = {};
-    E.sc[2] = &P[i].x; E.sc[3] = &P[i].y;
-    E.in[2] = &Q[i].x; E.in[3] = &Q[i].y;
+    E.p1 = &P[i].x;
+    E.q1 = &Q[i].x;
     vm::miller(M, E, vm::FAM_M1);
     const uint8_t fl = flP[i] | flQ[i];
     if (fl & FL_INF) {          // warp-uniform instruction stream again from here: plain stores

@@ -32,8 +32,8 @@ namespace vm {
 // what a routine can reach besides its slots: the item's Fp scalars (G1 coordinates) and Fp2 inputs (G2 coordinates) in
 // HBM (Montgomery records of items.cuh), the per-item scratch of the final exponentiation, and two driver registers
 struct Env {
-    const fp *sc[4];      // P0.x, P0.y, P1.x, P1.y
-    const fp2 *in[4];     // Q0.x, Q0.y, Q1.x, Q1.y
+    const fp *p0, *p1;    // scalars 0, 1 = p0[0], p0[1] (P0.x, P0.y); scalars 2, 3 = p1[0], p1[1] (P1.x, P1.y)
+    const fp2 *q0, *q1;   // inputs 0, 1 = q0[0], q0[1] (Q0.x, Q0.y); inputs 2, 3 = q1[0], q1[1]
     fp2 *scratch;         // entry e of this item lives at scratch[e * scratch_stride]
     size_t scratch_stride;
     int line;             // line counter of the fixed-point table ("rel" constants: index + 3 * line)
@@ -77,14 +77,16 @@ struct Slots {            // host build: one array per emulated lane
 #endif
 
 // (9 + u) v for this lane's half: even lane 9 v0 - v1, odd lane 9 v1 + v0
-BN_INL void lane_xi(fp &r, const fp &v, bool odd) {
-    fp pv, n, t, u;
+BN_NOINL fp lane_xi_v(fp v, bool odd) {
+    fp pv, n, t, u, r;
     lane_xchg(pv, v);
     fp_neg(n, pv);
     fp_mul9(t, v);
     fp_select(u, odd, pv, n);
     fp_add(r, t, u);
+    return r;
 }
+BN_INL void lane_xi(fp &r, const fp &v, bool odd) { r = lane_xi_v(v, odd); }
 
 // the descriptor queue of an instruction: 12 bytes in three words, consumed from the low end
 struct Desc {
@@ -99,7 +101,7 @@ struct Desc {
 };
 
 // sum of the next n operand terms (n >= 1): +-[xi] slot
-BN_NOINL fp gather(const Slots M, Desc &D, int n, bool odd) {
+BN_INL fp gather(const Slots M, Desc &D, int n, bool odd) {
     fp acc;
     fp_set_zero(acc);
 #pragma unroll 1
@@ -133,7 +135,7 @@ BN_INL fp global_half(const fp2 *q, bool odd) {
 
 // Runs one routine.  All lanes of a warp execute the same instruction stream (the program is warp uniform), so the lane
 // exchanges inside are full-mask shuffles.
-BN_NOINL void run(const Slots M, Env &E, int routine) {
+BN_NOINL void run(const Slots M, const Env E, int routine) {
     const bool odd = lane_par() != 0;
     int pc = VM_DIR[routine][0];
     const int end = pc + VM_DIR[routine][1];
@@ -181,7 +183,7 @@ BN_NOINL void run(const Slots M, Env &E, int routine) {
                     fp_select(y, odd, x, dd);
                     fp_add(x, s, px);
                 } else {
-                    y = *E.sc[aux];   // OP_MULFP / OP_MULFPC: an Fp scalar of the item, the same for both lanes
+                    y = ((aux & 2) ? E.p1 : E.p0)[aux & 1];   // OP_MULFP / OP_MULFPC: an Fp scalar of the item, the same for both lanes
                 }
                 fp_mul_inl(p, x, y);
             }
@@ -227,7 +229,7 @@ BN_NOINL void run(const Slots M, Env &E, int routine) {
         } else if (op == OP_LDC) {
             M.st(d, const_half(cidx, odd));
         } else if (op == OP_LDG) {
-            M.st(d, global_half(E.in[aux], odd));
+            M.st(d, global_half(((aux & 2) ? E.q1 : E.q0) + (aux & 1), odd));
         } else if (op == OP_INV) {
             fp2l a, r;
             a.v = gather(M, D, nx, odd);

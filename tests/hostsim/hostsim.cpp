@@ -439,8 +439,8 @@ static void vm_body(void *vp) {
     fp slots[64];
     const vm::Slots M = {slots};
     vm::Env E = {};
-    E.sc[0] = &a->p0.x; E.sc[1] = &a->p0.y; E.sc[2] = &a->p1.x; E.sc[3] = &a->p1.y;
-    E.in[0] = &a->q0.x; E.in[1] = &a->q0.y; E.in[2] = &a->q1.x; E.in[3] = &a->q1.y;
+    E.p0 = &a->p0.x; E.p1 = &a->p1.x;
+    E.q0 = &a->q0.x; E.q1 = &a->q1.x;
     E.scratch = a->scratch;
     E.scratch_stride = 1;
     const bool odd = bn_host_lane_par() != 0;

@@ -614,16 +614,21 @@ def test_aggregate_verify_honours_the_validation_flags(ctx, orc, B):
 
 
 def test_verify_c5_shape(orc, B):
-    """The shape BASELINE config 5 (2^24 tuples) runs: chunks of 2^18 through the double-buffered host pipeline, every
-    chunk on the one-thread kernels (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097 is two chunks with a ragged tail:
-    accept bytes equal the construction, a 512-tuple slice straddling the chunk boundary equals the oracle, and the
-    kernels of that shape are the ones that launched.  Pageable and pinned result buffers take different copy paths."""
+    """The shapes BASELINE config 5 (2^24 tuples) runs through the double-buffered host pipeline.  By default exact
+    verification streams chunks of one wave of lane pairs (66 304 tuples: k_miller2_fixed_l2, k_final_exp_l2); with the chunk
+    set to 2^18 every full chunk runs one thread per pairing (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097: accept bytes
+    equal the construction in both, a 512-tuple slice straddling a chunk boundary equals the oracle, and the profiler confirms
+    which kernels launched.  Pageable and pinned result buffers take different copy paths."""
     import numpy as np
     import torch
     c = B.Context([0])
     try:
         n = (1 << 18) + 4097
         pks, msgs, sigs, exp = B.scheme.synth_batch(c, n, variant=0, n_keys=64)
+        (got), names = launched(c, lambda: c.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG))
+        assert got == exp
+        assert {"k_miller2_fixed_l2", "k_final_exp_l2", "k_hash_g1"} <= names and "k_miller2_fixed" not in names
+        c.set_option("chunk", 1 << 18)
         (got), names = launched(c, lambda: c.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG))
         assert got == exp
         # the full chunk runs one thread per pairing; the 4097-tuple tail fits one wave of lane pairs and takes that shape
