@@ -378,9 +378,6 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P0 + lo, b.flp0 + lo, sigs + 64 * lo, n, check);
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
         if (subgroup) {
-#ifdef BN_NAIVE_SUBGROUP_CHECK  // G1 has cofactor 1: the on-curve check done by the decode is the subgroup check
-            LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, b.flp0 + lo, b.P0 + lo, n);
-#endif
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
         }
         if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
@@ -390,9 +387,6 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
         if (subgroup) {
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq0 + lo, b.Q0 + lo, n);
-#ifdef BN_NAIVE_SUBGROUP_CHECK  // G1 has cofactor 1: the on-curve check done by the decode is the subgroup check
-            LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, b.flp1 + lo, b.P1 + lo, n);
-#endif
         }
         if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         if (int rc = launch_miller2(d, n, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
@@ -516,9 +510,6 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
         if (int rc = ensure_t(d, S_RB_S1, nseg * so0 + 1, &SA)) return rc;
         if (int rc = ensure_t(d, S_RB_S2, nseg * so1 + 1, &SB)) return rc;
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flsig, sigs, n, check);
-#ifdef BN_NAIVE_SUBGROUP_CHECK  // G1 has cofactor 1: the on-curve check done by the decode is the subgroup check
-        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flsig, P0, n);
-#endif
         {
             SideStream guard(d);
             if (side) {
@@ -560,9 +551,6 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
             if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
         }
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
-#ifdef BN_NAIVE_SUBGROUP_CHECK  // G1 has cofactor 1: the on-curve check done by the decode is the subgroup check
-        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flp1, P1, n);
-#endif
         if (int rc = dev_hash_g2(d, Q1, flq1, msgs, off, base, n, dst, dst_len, 2)) return rc;
     }
     LAUNCH(d, k_rbv_group_flags, n, BN_TPB_LIGHT, gbad, flsig, flp1, flq1, group, n);
@@ -610,16 +598,10 @@ int dev_aggregate_rec(Dev &d, int variant, const uint8_t *pks, const uint8_t *ms
         if (int rc = dev_hash_g1(d, P, flp, msgs, off, base, n, dst, dst_len, 2)) return rc;
         if (agg_sig) {
             LAUNCH(d, k_g1_decode, 1, BN_TPB_LIGHT, P + n, flp + n, agg_sig, (size_t)1, check);
-#ifdef BN_NAIVE_SUBGROUP_CHECK
-            if (subgroup) LAUNCH(d, k_g1_require_subgroup, 1, BN_TPB_HEAVY, flp + n, P + n, (size_t)1);
-#endif
             LAUNCH(d, k_fill_neg_g2, 1, BN_TPB_LIGHT, Q + n, flq + n, (size_t)1);
         }
     } else {
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P, flp, pks, n, check | DEC_NO_IDENTITY);
-#ifdef BN_NAIVE_SUBGROUP_CHECK
-        if (subgroup) LAUNCH(d, k_g1_require_subgroup, n, BN_TPB_HEAVY, flp, P, n);
-#endif
         if (int rc = dev_hash_g2(d, Q, flq, msgs, off, base, n, dst, dst_len, 2)) return rc;
         if (agg_sig) {
             LAUNCH(d, k_g2_decode, 1, BN_TPB_LIGHT, Q + n, flq + n, agg_sig, (size_t)1, check);

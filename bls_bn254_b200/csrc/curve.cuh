@@ -208,13 +208,9 @@ BN_INL void pt_mul_glv(point<F> &r, const point<F> &p, const uint32_t *ka, const
 
 // [x]a for the curve parameter x = 0x44e992b44a6909f1 with the width-4 signed-digit string the final exponentiation uses
 // (k::X_WNAF4: 14 non-zero digits): 62 doublings + 13 additions after a 4-entry table (1 doubling + 3 additions), against 27
-// additions for the plain binary expansion.  Same group element as pt_mul(r, a, x, 63).  -DBN_PLAIN_X_MUL restores that.
+// additions for the plain binary expansion.  Same group element as pt_mul(r, a, x, 63).
 template <class F>
 BN_INL void pt_mul_x(point<F> &r, const point<F> &a) {
-#ifdef BN_PLAIN_X_MUL
-    const uint32_t xw[2] = {(uint32_t)(BN254_X & 0xffffffffu), (uint32_t)(BN254_X >> 32)};
-    pt_mul(r, a, xw, 63);
-#else
     point<F> tab[4], d2, acc, t;
     tab[0] = a;
     pt_dbl(d2, a);
@@ -234,7 +230,6 @@ BN_INL void pt_mul_x(point<F> &r, const point<F> &a) {
         }
     }
     r = acc;
-#endif
 }
 
 // g2.rs:938-954

@@ -513,7 +513,6 @@ BN_INL void fp_dot2x2_inl(fp &r0, fp &r1, const fp &a, const fp &c, const fp &b0
 // 16 in, 8 out), so a call costs a handful of moves while every caller stays small: the hot loops
 // of the pairing must fit the 32 KB L1.5 instruction cache, and a fully inlined Miller loop is
 // ~180 KB of IMAD code (28 % of issue slots lost to instruction-fetch stalls, profiles/r01).
-#ifndef BN_INLINE_FP_MUL
 BN_NOINL fp fp_mul_v(fp a, fp b) {
     fp r;
     fp_mul_inl(r, a, b);
@@ -526,146 +525,7 @@ BN_NOINL fp fp_dot2_v(fp a, fp b, fp c, fp d) {
 }
 BN_INL void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_v(a, b); }
 BN_INL void fp_dot2(fp &r, const fp &a, const fp &b, const fp &c, const fp &d) { r = fp_dot2_v(a, b, c, d); }
-#else
-BN_INL void fp_mul(fp &r, const fp &a, const fp &b) { fp_mul_inl(r, a, b); }
-BN_INL void fp_dot2(fp &r, const fp &a, const fp &b, const fp &c, const fp &d) { fp_dot2_inl(r, a, b, c, d); }
-#endif
 BN_INL void fp_sqr(fp &r, const fp &a) { fp_mul(r, a, a); }  // fp.rs:409-412
-
-// ---------------------------------------------------------------------------------------------
-// Double-width arithmetic for lazy reduction (Fp2 products: 3 wide products + 2 reductions instead
-// of 3 full Montgomery products, 336 instead of 408 wide IMADs).
-// ---------------------------------------------------------------------------------------------
-struct fpw {
-    uint32_t v[16];
-};
-
-// r (512 bit) = a * b, any 256-bit a, b.  Even/odd accumulators at absolute word positions: E holds
-// the products that start on an even word, O (offset by one word) those that start on an odd word.
-BN_INL void fp_mul_wide(fpw &r, const fp &a, const fp &b) {
-    BN_COUNT_OPS(128);
-    uint32_t E[18], O[18];
-#pragma unroll
-    for (int i = 8; i < 18; i++) { E[i] = 0; O[i] = 0; }
-    mul_lanes(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
-    mul_lanes(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
-#pragma unroll
-    for (int i = 1; i < 8; i++) {
-        if (i & 1) {
-            // products a_even * b_i start at odd positions i+j -> O[i-1+j]; a_odd * b_i -> E[i+1+j-1]
-            mad_lanes(&O[i - 1], O[i + 7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-            mad_lanes(&E[i + 1], E[i + 9], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-        } else {
-            mad_lanes(&E[i], E[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-            mad_lanes(&O[i], O[i + 8], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-        }
-    }
-    // r = E + (O << 32)
-    uint32_t lo[8], hi[8];
-    r.v[0] = E[0];
-    uint32_t sh0[8] = {E[1], E[2], E[3], E[4], E[5], E[6], E[7], E[8]};
-    uint32_t c = add_n(lo, sh0, O);
-    uint32_t sh1[8] = {E[9], E[10], E[11], E[12], E[13], E[14], E[15], 0u};
-    uint32_t o1[8] = {O[8], O[9], O[10], O[11], O[12], O[13], O[14], 0u};
-    (void)add_n(hi, sh1, o1);
-    // propagate the carry of the low half into the high half
-    uint32_t cc[8] = {c, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    (void)add_n(hi, hi, cc);
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[1 + i] = lo[i];
-#pragma unroll
-    for (int i = 0; i < 7; i++) r.v[9 + i] = hi[i];
-}
-
-// r = a + b, r = a - b on 512-bit values; sub returns the borrow mask
-BN_INL void fpw_add(fpw &r, const fpw &a, const fpw &b) {
-    uint32_t c = add_n(r.v, a.v, b.v);
-    uint32_t t[8] = {c, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, h[8];
-    (void)add_n(h, a.v + 8, b.v + 8);
-    (void)add_n(r.v + 8, h, t);
-}
-BN_INL uint32_t fpw_sub(fpw &r, const fpw &a, const fpw &b) {
-    uint32_t m = sub_n(r.v, a.v, b.v);
-    uint32_t t[8] = {m & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, h[8];
-    uint32_t m1 = sub_n(h, a.v + 8, b.v + 8);
-    uint32_t m2 = sub_n(r.v + 8, h, t);
-    return m1 | m2;
-}
-
-// e0 += x (carry c, weight of acc word 0); acc += {p1,p3,p5,p7} * m + c
-BN_INL void mad_p_odd_cin(uint32_t acc[8], uint32_t &e0, uint32_t x, uint32_t m) {
-#if BN_PTX
-    asm("add.cc.u32 %8, %8, %9;\n\t"
-        "madc.lo.cc.u32 %0, %10, 0x3c208c16, %0;\n\t"
-        "madc.hi.cc.u32 %1, %10, 0x3c208c16, %1;\n\t"
-        "madc.lo.cc.u32 %2, %10, 0x97816a91, %2;\n\t"
-        "madc.hi.cc.u32 %3, %10, 0x97816a91, %3;\n\t"
-        "madc.lo.cc.u32 %4, %10, 0xb85045b6, %4;\n\t"
-        "madc.hi.cc.u32 %5, %10, 0xb85045b6, %5;\n\t"
-        "madc.lo.cc.u32 %6, %10, 0x30644e72, %6;\n\t"
-        "madc.hi.u32 %7, %10, 0x30644e72, %7;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(e0)
-        : "r"(x), "r"(m));
-#else
-    uint64_t s = (uint64_t)e0 + x;
-    e0 = (uint32_t)s;
-    (void)host_mad_lanes(acc, BN_P1, BN_P3, BN_P5, BN_P7, m, (uint32_t)(s >> 32));
-#endif
-}
-
-// Montgomery reduction r = T / 2^256 mod p for T < p * 2^256; result canonical.
-// Same frame as fp_mul_inl (running value S = E + O*2^32), the a*b_i rows replaced by shifting in
-// the next word of T at frame word 7 (= O'[6], a fresh word).  S < 2^256 + p throughout.
-BN_INL void fp_redc(fp &r, const fpw &t) {
-    BN_COUNT_OPS(136);
-    uint32_t E[8], O[8], m;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { E[i] = t.v[i]; O[i] = 0; }
-    m = E[0] * BN254_INV32;
-    mad_p_odd(O, m);
-    mad_p_even(E, O[7], m);
-#pragma unroll
-    for (int i = 1; i < 8; i++) {
-        uint32_t x = E[1];
-        uint32_t N[8] = {E[2], E[3], E[4], E[5], E[6], E[7], t.v[7 + i], 0u};
-#pragma unroll
-        for (int k = 0; k < 8; k++) E[k] = O[k];
-        m = (E[0] + x) * BN254_INV32;
-        mad_p_odd_cin(N, E[0], x, m);
-        mad_p_even(E, N[7], m);
-#pragma unroll
-        for (int k = 0; k < 8; k++) O[k] = N[k];
-    }
-    fp s;
-    uint32_t hi[8] = {E[1], E[2], E[3], E[4], E[5], E[6], E[7], t.v[15]};
-    (void)add_n(s.v, O, hi);
-    fp_reduce_once(s);
-    r = s;
-}
-
-#ifndef BN_INLINE_FP_MUL
-BN_NOINL fpw fp_mul_wide_v(fp a, fp b) {
-    fpw r;
-    fp_mul_wide(r, a, b);
-    return r;
-}
-BN_NOINL fp fp_redc_v(fpw t) {
-    fp r;
-    fp_redc(r, t);
-    return r;
-}
-#else
-BN_INL fpw fp_mul_wide_v(const fp &a, const fp &b) {
-    fpw r;
-    fp_mul_wide(r, a, b);
-    return r;
-}
-BN_INL fp fp_redc_v(const fpw &t) {
-    fp r;
-    fp_redc(r, t);
-    return r;
-}
-#endif
 
 // small multiples
 BN_INL void fp_mul3(fp &r, const fp &a) { fp t; fp_dbl(t, a); fp_add(r, t, a); }
@@ -721,7 +581,6 @@ BN_INL void fp_inv_fermat(fp &r, const fp &a) { fp_pow_sw(r, a, k::SW_P_MINUS_2,
 // evaluated here as the Jacobi symbol (a / p) by the binary algorithm -- shifts, one subtraction and one conditional
 // negation per step on 8 limbs, about 1.4 * 254 steps -- which costs a quarter of the 250-squaring exponentiation and
 // none of the multiplier pipe.  The Montgomery factor does not matter: R = 2^256 is a square, so (aR / p) = (a / p).
-// -DBN_EULER_IS_SQUARE restores the exponentiation.
 BN_INL bool fp_is_square_euler(const fp &a) {
     fp t;
     fp_pow_sw(t, a, k::SW_P_MINUS_1_DIV_2, BN254_SW_P_MINUS_1_DIV_2_TOP);
@@ -802,7 +661,7 @@ BN_INL uint32_t shl_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [32 - 
 // strips the trailing zeros of a (N doubles instead of A halving, so there is no modular halving and several bits
 // go at once), then subtracts the smaller of the two odd values from the larger.  About 0.7 * 254 subtraction steps
 // of ~70 ALU instructions and no multiplier work; the factor 2^k (and the Montgomery factor) is removed at the end by
-// two products.  -DBN_FERMAT_INVERSION restores the exponentiation.
+// two products.
 BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
     uint32_t a[8], n[8], A[8], N[8], d[8];
     uint32_t any = 0;
@@ -885,18 +744,10 @@ BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
     }
 }
 BN_INL void fp_inv(fp &r, const fp &a) {
-#ifdef BN_FERMAT_INVERSION
-    fp_inv_fermat(r, a);
-#else
     fp_inv_bingcd(r, a);
-#endif
 }
 BN_INL bool fp_is_square(const fp &a) {
-#ifdef BN_EULER_IS_SQUARE
-    return fp_is_square_euler(a);
-#else
     return fp_is_square_jacobi(a);
-#endif
 }
 // candidate root a^((p+1)/4) (fp.rs:212-243 with v = 1); returns whether it squares to a
 BN_INL bool fp_sqrt(fp &r, const fp &a) {

@@ -12,19 +12,10 @@
 
 namespace bn {
 
-// The Fp12 accumulator of a pairing kernel can live in shared memory (-DBN_SMEM_ACC): per-thread local memory is
-// interleaved over the SM's whole thread population, so the long-lived accumulator always misses L1 (measured: shrinking
-// L1 from the maximum to the minimum costs these kernels only 4-8 %), while a shared-memory slot is a guaranteed on-chip
-// hit.  Slots are padded by 16 bytes so that the 128-bit accesses of consecutive threads fall in distinct banks.
 #ifndef BN_TPB_HEAVY
 #define BN_TPB_HEAVY 64
 #endif
-#if BN_PTX && defined(BN_SMEM_ACC)
-template <class T> struct alignas(16) acc_slot { T v; uint32_t pad[4]; };
-#define BN_ACC(T, name) __shared__ acc_slot<T> name##_slots[BN_TPB_HEAVY]; T &name = name##_slots[threadIdx.x].v
-#else
 #define BN_ACC(T, name) T name
-#endif
 
 enum : uint8_t { FL_INF = 1, FL_BAD = 2 };
 enum : uint32_t { VERIFY_CHECK_ON_CURVE = 1u };
@@ -194,7 +185,7 @@ BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const 
 // ---- subgroup membership (g1.rs:852-855, g2.rs:733-736: is_torsion_free = [r]P is the identity) ----
 // out = 1 for a decodable point ON THE CURVE whose order divides r (the identity included).  Callers decode with the
 // on-curve check, so FL_BAD already covers "not on the curve".  The same predicate as the reference's [r]P == O,
-// evaluated without the 254-bit multiplication (-DBN_NAIVE_SUBGROUP_CHECK restores it):
+// evaluated without the 254-bit multiplication:
 //   G1: #E(Fp) = r (cofactor 1): every point of the curve is in the subgroup, nothing is left to compute.
 //   G2: for BN curves  Q in G2  <=>  [x+1]Q + psi([x]Q) + psi^2([x]Q) = psi^3([2x]Q)  (Dai-Lin-Zhao-Zhou, "Fast subgroup
 //       membership testings on pairing-friendly curves", 2022; the test gnark-crypto uses for this curve): one 63-bit
@@ -202,15 +193,8 @@ BN_INL void item_g2_mul(g2m &out, uint8_t &flo, const g2m &p, uint8_t fl, const 
 //       the twist, points of the cofactor subgroup and sums of both (oracle/pymodel.py, tests/test_hostsim.py, GPU suite).
 BN_INL uint8_t item_g1_torsion_free(const g1m &p, uint8_t fl) {
     if (fl & FL_BAD) return 0;
-#ifdef BN_NAIVE_SUBGROUP_CHECK
-    g1p a, r;
-    pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
-    pt_mul(r, a, k::R_ORDER, 254);
-    return fp_is_zero(r.z) ? 1 : 0;
-#else
     (void)p;
     return 1;
-#endif
 }
 // Out of line on purpose: inlined into k_g2_torsion_free (behind the wire decode) the windowed [x]Q version returned 0 for
 // subgroup points on sm_100a (nvcc 12.9) while the same body inside k_g2_require_subgroup and the host build were right --
@@ -219,10 +203,6 @@ BN_NOINL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
     if (fl & FL_BAD) return 0;
     g2p a, r;
     pt_from_affine(a, p.x, p.y, (fl & FL_INF) != 0);
-#ifdef BN_NAIVE_SUBGROUP_CHECK
-    pt_mul(r, a, k::R_ORDER, 254);
-    return fp2_is_zero(r.z) ? 1 : 0;
-#else
     g2p xq, b, c, t;
     pt_mul_x(xq, a);             // [x]Q
     g2_psi(b, xq);               // psi([x]Q)
@@ -240,7 +220,6 @@ BN_NOINL uint8_t item_g2_torsion_free(const g2m &p, uint8_t fl) {
     eq &= fp2_eq(l, m);
     bool rz = fp2_is_zero(r.z), tz = fp2_is_zero(t.z);
     return (rz || tz) ? (uint8_t)(rz && tz) : (uint8_t)eq;
-#endif
 }
 
 // ---- compressed codecs (g1.rs:283-288 / 311-328, g2.rs:274-283 / 309-340) ------------------------

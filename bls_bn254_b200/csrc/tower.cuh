@@ -32,39 +32,19 @@ BN_INL void fp2_set_zero(fp2 &r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
 BN_INL void fp2_set_one(fp2 &r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
 BN_INL bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 BN_INL bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
-// The light Fp2 operations are out-of-line too (BN_LIGHT): the tower code above them is then a
-// sequence of calls on pointers into the thread's local memory, a few KB per Fp12 routine.
-#ifndef BN_INLINE_LIGHT
+// The light Fp2 operations and the Fp2 products are OUT-OF-LINE functions on pointers: the tower code above them is then a
+// sequence of calls, a few KB per Fp12 routine.  Measured in round 1 (profiles/r01_notes.md): inlining them (Fp6-level
+// leaves, lazy-reduction or Karatsuba Fp2 products, by-value lane primitives, shared-memory accumulators) always lost to the
+// larger code -- the 32 KB instruction cache is the first-order constraint -- so those build options are gone; round 2
+// re-measured two more shapes (paired products for ILP: -23 %; the slot machine of vm.cuh) with the same outcome.
 #define BN_LIGHT BN_NOINL
-#else
-#define BN_LIGHT BN_INL
-#endif
-// BN_INLINE_FP2: the Fp2 products are inlined as well (their Fp products stay by-value calls), which
-// makes the Fp6-level routines the leaves: their intermediates live in registers instead of being
-// passed through local memory between many tiny functions.
-#ifndef BN_INLINE_FP2
 #define BN_FP2MUL BN_NOINL
-#else
-#define BN_FP2MUL BN_INL
-#endif
-#ifndef BN_L_ADD
 #define BN_L_ADD BN_LIGHT
-#endif
-#ifndef BN_L_SUB
 #define BN_L_SUB BN_LIGHT
-#endif
-#ifndef BN_L_NEG
 #define BN_L_NEG BN_LIGHT
-#endif
-#ifndef BN_L_DBL
 #define BN_L_DBL BN_LIGHT
-#endif
-#ifndef BN_L_CONJ
 #define BN_L_CONJ BN_LIGHT
-#endif
-#ifndef BN_L_XI
 #define BN_L_XI BN_LIGHT
-#endif
 // Each of these first copies its operands into registers as whole (16-byte aligned) structs: all the
 // 128-bit loads issue together, before the carry chains, and the result leaves as 128-bit stores.
 BN_L_ADD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) {
@@ -101,7 +81,6 @@ BN_INL void fp2_select(fp2 &r, bool c, const fp2 &a, const fp2 &b) { fp_select(r
 // Fused light operations (-DBN_NO_FUSED_LIGHT falls back to the two- and three-call forms): the call, the 128-bit
 // operand loads and the result store are what these tiny functions cost, so a - b - c and 2(t -+ z) + t as ONE call
 // each halve that overhead where the tower strings additions together (Karatsuba glue, Granger-Scott squaring).
-#ifndef BN_NO_FUSED_LIGHT
 BN_LIGHT void fp2_sub2(fp2 &r, const fp2 &a, const fp2 &b, const fp2 &c) {  // a - b - c
     fp2 x = a, y = b, w = c, z;
     fp_sub(z.c0, x.c0, y.c0); fp_sub(z.c0, z.c0, w.c0);
@@ -111,83 +90,35 @@ BN_LIGHT void fp2_sub2(fp2 &r, const fp2 &a, const fp2 &b, const fp2 &c) {  // a
 // one thread per element: the three-call forms stay (a fused 16-limb version made the final exponentiation 10 % slower)
 BN_INL void fp2_tsub(fp2 &z, const fp2 &t) { fp2_sub(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }  // z <- 3t - 2z
 BN_INL void fp2_tadd(fp2 &z, const fp2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }  // z <- 3t + 2z
-#endif
 
 // fp2.rs:377-390 (there: 4 products).  Karatsuba with lazy reduction: three 512-bit products, the
 // cross terms combined as integers, two Montgomery reductions.
 //   c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1   (= a0 b1 + a1 b0 >= 0, < 2p^2 < p*2^256)
 //   c0 = a0 b0 - a1 b1                     (+ p*2^256 when negative, so 0 <= . < p*2^256)
-#ifdef BN_FP2_LAZY  // measured slower on B200 in round 1 (the kernels are latency-, not IMAD-bound): off by default
-BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
-    fp sa, sb;
-    (void)add_n(sa.v, a.c0.v, a.c1.v);  // < 2p < 2^255: no reduction needed as a wide-product operand
-    (void)add_n(sb.v, b.c0.v, b.c1.v);
-    fpw w0 = fp_mul_wide_v(a.c0, b.c0);
-    fpw w1 = fp_mul_wide_v(a.c1, b.c1);
-    fpw w2 = fp_mul_wide_v(sa, sb);
-    (void)fpw_sub(w2, w2, w0);
-    (void)fpw_sub(w2, w2, w1);
-    uint32_t neg = fpw_sub(w0, w0, w1);
-    add_p_masked(w0.v + 8, neg);
-    r.c0 = fp_redc_v(w0);
-    r.c1 = fp_redc_v(w2);
-}
-#elif !defined(BN_FP2_KARATSUBA)
 // c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0: two fused dot products (fp_dot2), no Karatsuba additions
 BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp2 x = a, y = b, z;
     fp nb1;
     fp_neg(nb1, y.c1);
-#if defined(BN_FP2MUL_SEQ)   // both dot products inline, one after the other
-    fp_dot2_inl(z.c0, x.c0, y.c0, x.c1, nb1);
-    fp_dot2_inl(z.c1, x.c0, y.c1, x.c1, y.c0);
-#elif !defined(BN_FP2MUL_CALLS)   // both dot products inline and advanced in lock step (two instruction streams)
     fp_dot2x2_inl(z.c0, z.c1, x.c0, x.c1, y.c0, nb1, y.c1, y.c0);
-#else
-    fp_dot2(z.c0, x.c0, y.c0, x.c1, nb1);
-    fp_dot2(z.c1, x.c0, y.c1, x.c1, y.c0);
-#endif
     r = z;
 }
-#else
-BN_NOINL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
-    fp t0, t1, s, t;
-    fp_mul(t0, a.c0, b.c0);
-    fp_mul(t1, a.c1, b.c1);
-    fp_add(s, a.c0, a.c1);
-    fp_add(t, b.c0, b.c1);
-    fp_mul(s, s, t);
-    fp_sub(s, s, t0);
-    fp_sub(r.c1, s, t1);
-    fp_sub(r.c0, t0, t1);
-}
-#endif
 // fp2.rs:392-402
 BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
     fp2 x = a, z;
     fp s, d, m;
     fp_add(s, x.c0, x.c1);
     fp_sub(d, x.c0, x.c1);
-#ifdef BN_FP2SQR_LEAF
-    fp_mul_inl(m, x.c0, x.c1);
-    fp_mul_inl(z.c0, s, d);
-#else
     fp_mul(m, x.c0, x.c1);
     fp_mul(z.c0, s, d);
-#endif
     fp_dbl(z.c1, m);
     r = z;
 }
 BN_FP2MUL void fp2_mul_fp(fp2 &r, const fp2 &a, const fp &s) {
     fp2 x = a, z;
     fp y = s;
-#ifdef BN_FP2SQR_LEAF
-    fp_mul_inl(z.c0, x.c0, y);
-    fp_mul_inl(z.c1, x.c1, y);
-#else
     fp_mul(z.c0, x.c0, y);
     fp_mul(z.c1, x.c1, y);
-#endif
     r = z;
 }
 // (9+u)(a0 + a1 u) = (9 a0 - a1) + (a0 + 9 a1) u
@@ -200,74 +131,11 @@ BN_L_XI void fp2_mul_xi(fp2 &r, const fp2 &a) {
     fp_add(z.c1, t1, x.c0);
     r = z;
 }
-#ifndef BN_NO_FUSED_LIGHT
 BN_INL void fp2_xi_add(fp2 &r, const fp2 &a, const fp2 &b) {  // xi a + b
     fp2 t;
     fp2_mul_xi(t, a);
     fp2_add(r, t, b);
 }
-#endif
-// ---- fused forms: the Karatsuba glue of the Fp6 routines in ONE call each, intermediates in
-// registers (the tiny add/sub functions they replace spent their time loading and storing operands:
-// profiles/r01_notes.md).
-// r = (a0 + a1)(b0 + b1).  The b-side sums stay unreduced: they are the row-scanned operands of fp_dot2,
-// which may be any 256-bit value; the a-side sums are reduced (multiplicand bound, see fp_dot2_inl).
-#ifdef BN_FUSED  // measured slower on B200 (larger code, instruction cache): opt-in
-BN_NOINL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) {
-    fp s0, s1, u0, u1, nu1, c0;
-    fp_add(s0, a0.c0, a1.c0);
-    fp_add(s1, a0.c1, a1.c1);
-    (void)add_n(u0.v, b0.c0.v, b1.c0.v);   // < 2p
-    (void)add_n(u1.v, b0.c1.v, b1.c1.v);   // < 2p
-    fp twop = {{BN_P0 << 1, (BN_P1 << 1) | (BN_P0 >> 31), (BN_P2 << 1) | (BN_P1 >> 31), (BN_P3 << 1) | (BN_P2 >> 31),
-                (BN_P4 << 1) | (BN_P3 >> 31), (BN_P5 << 1) | (BN_P4 >> 31), (BN_P6 << 1) | (BN_P5 >> 31), (BN_P7 << 1) | (BN_P6 >> 31)}};
-    (void)sub_n(nu1.v, twop.v, u1.v);      // 2p - u1 in [0, 2p]: congruent to -u1
-    fp_dot2(c0, s0, u0, s1, nu1);
-    fp_dot2(r.c1, s0, u1, s1, u0);
-    r.c0 = c0;
-}
-// r = (a0 + a1) b
-BN_NOINL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b) {
-    fp s0, s1, nb1, c0;
-    fp_add(s0, a0.c0, a1.c0);
-    fp_add(s1, a0.c1, a1.c1);
-    fp_neg(nb1, b.c1);
-    fp_dot2(c0, s0, b.c0, s1, nb1);
-    fp_dot2(r.c1, s0, b.c1, s1, b.c0);
-    r.c0 = c0;
-}
-BN_INL void fp2_xi_regs(fp2 &r, const fp2 &a) {
-    fp t0, t1;
-    fp_mul9(t0, a.c0);
-    fp_mul9(t1, a.c1);
-    fp_sub(t0, t0, a.c1);
-    fp_add(r.c1, t1, a.c0);
-    r.c0 = t0;
-}
-// mode 0: r = t - s1 - s2 + a1      mode 1: r = xi (t - s1 - s2) + a1      mode 2: r = t - s1 - s2 + xi a1
-// (s2 and a1 may be null: skipped)
-BN_NOINL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode) {
-    fp2 x;
-    fp_sub(x.c0, t.c0, s1.c0);
-    fp_sub(x.c1, t.c1, s1.c1);
-    if (s2) {
-        fp_sub(x.c0, x.c0, s2->c0);
-        fp_sub(x.c1, x.c1, s2->c1);
-    }
-    if (mode == 1) fp2_xi_regs(x, x);
-    if (a1) {
-        fp2 y = *a1;
-        if (mode == 2) fp2_xi_regs(y, y);
-        fp_add(x.c0, x.c0, y.c0);
-        fp_add(x.c1, x.c1, y.c1);
-    }
-    r = x;
-}
-#else
-BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1);
-BN_INL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b);
-BN_INL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode);
-#endif
 // fp2.rs:161-166
 BN_NOINL void fp2_inv(fp2 &r, const fp2 &a) {
     fp t0, t1;
@@ -339,16 +207,11 @@ BN_INL uint32_t lane_par() { return threadIdx.x & 1u; }
 // Shuffle mask of the lane-pair kernels.  Default: the whole warp.  Those kernels keep every warp convergent --
 // whole warps exit together (BN_L2_PROLOGUE), exponents and loop schedules are the same for every item, and a pair
 // that contributes nothing (identity / undecodable input) multiplies by a neutral line instead of branching around
-// its Miller loop (pairing.cuh: ell) -- so a full-mask SHFL is legal and compiles to one instruction.  Naming only the
-// two lanes of a pair (-DBN_LANE_PAIR_MASK) makes ptxas wrap most shuffles in BSSY / WARPSYNC / ENDCOLLECTIVE /
-// BSYNC: 5 instructions per exchanged word, 80 of the 186 instructions of the lane-pair Fp2 squaring.
-#ifdef BN_LANE_PAIR_MASK
-#define BN_LANES_CONVERGENT 0
-BN_INL uint32_t lane_mask() { return 3u << (threadIdx.x & 30u); }
-#else
+// its Miller loop (pairing.cuh: ell) -- so a full-mask SHFL is legal and compiles to one instruction.  (Naming only the
+// two lanes of a pair made ptxas wrap most shuffles in BSSY / WARPSYNC / ENDCOLLECTIVE / BSYNC: 5 instructions per
+// exchanged word, 80 of the 186 instructions of the lane-pair Fp2 squaring.)
 #define BN_LANES_CONVERGENT 1
 BN_INL uint32_t lane_mask() { return 0xffffffffu; }
-#endif
 BN_INL void lane_xchg(fp &out, const fp &in) {  // out = the partner lane's `in`
     uint32_t m = lane_mask();
 #pragma unroll
@@ -391,71 +254,8 @@ BN_INL void fp2_set_one(fp2l &r) {
 }
 BN_INL bool fp2_is_zero(const fp2l &a) { return lane_both(fp_is_zero(a.v)); }
 BN_INL bool fp2_eq(const fp2l &a, const fp2l &b) { return lane_both(fp_eq(a.v, b.v)); }
-// The lane-pair primitives are out-of-line with operands and result in registers (by value): the
-// tower routines above them are then pure call sequences of a few KB each (instruction cache).
-BN_NOINL fp l2_add_v(fp a, fp b) { fp r; fp_add(r, a, b); return r; }
-BN_NOINL fp l2_sub_v(fp a, fp b) { fp r; fp_sub(r, a, b); return r; }
-BN_NOINL fp l2_neg_v(fp a) { fp r; fp_neg(r, a); return r; }
-BN_NOINL fp l2_conj_v(fp a) {
-    fp n, r;
-    fp_neg(n, a);
-    fp_select(r, lane_par() != 0, n, a);
-    return r;
-}
-// even lane: a0 b0 + a1 (-b1);  odd lane: a0 b1 + a1 b0 -- one fused dot product per lane
-BN_NOINL fp l2_mul_v(fp a, fp b) {
-    fp pa, pb, npb, x, z, w, r;
-    bool odd = lane_par() != 0;
-    lane_xchg(pa, a);
-    lane_xchg(pb, b);
-    fp_neg(npb, pb);
-    fp_select(x, odd, pa, a);    // a0
-    fp_select(z, odd, a, pa);    // a1
-    fp_select(w, odd, pb, npb);  // odd: b0, even: -b1
-    fp_dot2_inl(r, x, b, z, w);
-    return r;
-}
-// even lane: (a0 + a1)(a0 - a1);  odd lane: (a0 + a0) a1
-BN_NOINL fp l2_sqr_v(fp a) {
-    fp pa, s, d, x, y, r;
-    bool odd = lane_par() != 0;
-    lane_xchg(pa, a);
-    fp_select(s, odd, pa, a);  // a0
-    fp_add(x, s, pa);          // even: a0 + a1, odd: a0 + a0
-    fp_sub(d, a, pa);
-    fp_select(y, odd, a, d);   // even: a0 - a1, odd: a1
-    fp_mul_inl(r, x, y);
-    return r;
-}
-// (9+u)(a0 + a1 u): even lane 9 a0 - a1, odd lane 9 a1 + a0
-BN_NOINL fp l2_xi_v(fp a) {
-    fp pa, n, t, u, r;
-    lane_xchg(pa, a);
-    fp_neg(n, pa);
-    fp_mul9(t, a);
-    fp_select(u, lane_par() != 0, pa, n);
-    fp_add(r, t, u);
-    return r;
-}
-// BN_L2_BYVALUE: the tower calls the by-value primitives above (values travel in registers, ~25
-// instructions per call site); default: out-of-line functions on pointers (~8 instructions per call
-// site, operands loaded as 128-bit vectors first), which keeps the lane-pair kernels as small as the
-// one-thread ones.
-#ifdef BN_L2_BYVALUE
-BN_INL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_add_v(a.v, b.v); }
-BN_INL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_sub_v(a.v, b.v); }
-BN_INL void fp2_neg(fp2l &r, const fp2l &a) { r.v = l2_neg_v(a.v); }
-BN_INL void fp2_dbl(fp2l &r, const fp2l &a) { r.v = l2_add_v(a.v, a.v); }
-BN_INL void fp2_conj(fp2l &r, const fp2l &a) { r.v = l2_conj_v(a.v); }
-BN_INL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_mul_v(a.v, b.v); }
-BN_INL void fp2_sqr(fp2l &r, const fp2l &a) { r.v = l2_sqr_v(a.v); }
-BN_INL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) { fp_mul(r.v, a.v, s); }
-BN_INL void fp2_mul_xi(fp2l &r, const fp2l &a) { r.v = l2_xi_v(a.v); }
-BN_INL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) { r.v = l2_add_v(l2_xi_v(a.v), b.v); }
-BN_INL void fp2_sub2(fp2l &r, const fp2l &a, const fp2l &b, const fp2l &c) { r.v = l2_sub_v(l2_sub_v(a.v, b.v), c.v); }
-BN_INL void fp2_tsub(fp2l &z, const fp2l &t) { fp x = l2_sub_v(t.v, z.v); z.v = l2_add_v(l2_add_v(x, x), t.v); }
-BN_INL void fp2_tadd(fp2l &z, const fp2l &t) { fp x = l2_add_v(t.v, z.v); z.v = l2_add_v(l2_add_v(x, x), t.v); }
-#else
+// The tower calls out-of-line functions on pointers (~8 instructions per call site, operands loaded as 128-bit vectors
+// first), which keeps the lane-pair kernels as small as the one-thread ones.
 BN_NOINL void fp2_add(fp2l &r, const fp2l &a, const fp2l &b) {
     fp x = a.v, y = b.v, z;
     fp_add(z, x, y);
@@ -466,7 +266,6 @@ BN_NOINL void fp2_sub(fp2l &r, const fp2l &a, const fp2l &b) {
     fp_sub(z, x, y);
     r.v = z;
 }
-#ifndef BN_NO_FUSED_LIGHT
 BN_NOINL void fp2_sub2(fp2l &r, const fp2l &a, const fp2l &b, const fp2l &c) {
     fp x = a.v, y = b.v, w = c.v, z;
     fp_sub(z, x, y);
@@ -487,7 +286,6 @@ BN_NOINL void fp2_tadd(fp2l &z, const fp2l &t) {
     fp_add(o, o, x);
     z.v = o;
 }
-#endif
 BN_NOINL void fp2_neg(fp2l &r, const fp2l &a) {
     fp x = a.v, z;
     fp_neg(z, x);
@@ -538,7 +336,6 @@ BN_NOINL void fp2_mul_xi(fp2l &r, const fp2l &a) {
     fp_add(o, t, u);
     r.v = o;
 }
-#ifndef BN_NO_FUSED_LIGHT
 BN_NOINL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) {  // xi a + b in one call
     fp x0 = a.v, y = b.v, pa, n, t, u, o;
     lane_xchg(pa, x0);
@@ -549,8 +346,6 @@ BN_NOINL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) {  // xi a + b i
     fp_add(o, o, y);
     r.v = o;
 }
-#endif
-#endif
 // fp2.rs:161-166 on a lane pair (both lanes run the same Fp inversion on the shared norm)
 BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
     fp sq, psq, n, m;
@@ -563,12 +358,6 @@ BN_INL void fp2_inv(fp2l &r, const fp2l &a) {
     fp_mul(r.v, a.v, n);
 }
 
-#ifdef BN_NO_FUSED_LIGHT
-template <class T2> BN_INL void fp2_sub2(T2 &r, const T2 &a, const T2 &b, const T2 &c) { fp2_sub(r, a, b); fp2_sub(r, r, c); }
-template <class T2> BN_INL void fp2_xi_add(T2 &r, const T2 &a, const T2 &b) { T2 t; fp2_mul_xi(t, a); fp2_add(r, t, b); }
-template <class T2> BN_INL void fp2_tsub(T2 &z, const T2 &t) { fp2_sub(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }
-template <class T2> BN_INL void fp2_tadd(T2 &z, const T2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); }
-#endif
 // generic (unfused) forms of the fused primitives: used by the lane-split type, and by fp2 under BN_NO_FUSED
 template <class T2>
 BN_INL void fp2_mul_sums_g(T2 &r, const T2 &a0, const T2 &a1, const T2 &b0, const T2 &b1) {
@@ -583,57 +372,10 @@ BN_INL void fp2_mul_sum1_g(T2 &r, const T2 &a0, const T2 &a1, const T2 &b) {
     fp2_add(s, a0, a1);
     fp2_mul(r, s, b);
 }
-template <class T2>
-BN_INL void fp2_comb_g(T2 &r, const T2 &t, const T2 &s1, const T2 *s2, const T2 *a1, int mode) {
-    T2 x, y;
-    fp2_sub(x, t, s1);
-    if (s2) fp2_sub(x, x, *s2);
-    if (mode == 1) fp2_mul_xi(x, x);
-    if (a1) {
-        y = *a1;
-        if (mode == 2) fp2_mul_xi(y, y);
-        fp2_add(x, x, y);
-    }
-    r = x;
-}
-#if defined(BN_L2_MUL_SUMS) && !defined(BN_L2_BYVALUE)
-// lane pairs: the Karatsuba cross products (a0 + a1)(b0 + b1) and (a0 + a1) b as ONE out-of-line call each (the two
-// additions would otherwise be two more calls with their own operand loads and result stores)
-BN_NOINL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) {
-    fp x0 = a0.v, x1 = a1.v, y0 = b0.v, y1 = b1.v, x, y, pa, pb, npb, u, w, o;
-    bool odd = lane_par() != 0;
-    fp_add(x, x0, x1);
-    fp_add(y, y0, y1);
-    lane_xchg(pa, x);
-    lane_xchg(pb, y);
-    fp_neg(npb, pb);
-    fp_select(u, odd, pb, y);
-    fp_select(w, odd, y, npb);
-    fp_dot2_inl(o, x, u, pa, w);
-    r.v = o;
-}
-BN_NOINL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) {
-    fp x0 = a0.v, x1 = a1.v, y = b.v, x, pa, pb, npb, u, w, o;
-    bool odd = lane_par() != 0;
-    fp_add(x, x0, x1);
-    lane_xchg(pa, x);
-    lane_xchg(pb, y);
-    fp_neg(npb, pb);
-    fp_select(u, odd, pb, y);
-    fp_select(w, odd, y, npb);
-    fp_dot2_inl(o, x, u, pa, w);
-    r.v = o;
-}
-#else
 BN_INL void fp2_mul_sums(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b0, const fp2l &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
 BN_INL void fp2_mul_sum1(fp2l &r, const fp2l &a0, const fp2l &a1, const fp2l &b) { fp2_mul_sum1_g(r, a0, a1, b); }
-#endif
-BN_INL void fp2_comb(fp2l &r, const fp2l &t, const fp2l &s1, const fp2l *s2, const fp2l *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
-#ifndef BN_FUSED
 BN_INL void fp2_mul_sums(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b0, const fp2 &b1) { fp2_mul_sums_g(r, a0, a1, b0, b1); }
 BN_INL void fp2_mul_sum1(fp2 &r, const fp2 &a0, const fp2 &a1, const fp2 &b) { fp2_mul_sum1_g(r, a0, a1, b); }
-BN_INL void fp2_comb(fp2 &r, const fp2 &t, const fp2 &s1, const fp2 *s2, const fp2 *a1, int mode) { fp2_comb_g(r, t, s1, s2, a1, mode); }
-#endif
 
 // ------------------------------------------------------------------------------------------ Fp6
 template <class T2>
@@ -644,39 +386,6 @@ template <class T2>
 BN_INL void fp6_neg(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
 template <class T2>
 BN_INL void fp6_dbl(fp6_t<T2> &r, const fp6_t<T2> &a) { fp2_dbl(r.c0, a.c0); fp2_dbl(r.c1, a.c1); fp2_dbl(r.c2, a.c2); }
-#ifdef BN_FUSED
-// Karatsuba, 6 Fp2 products (role of fp6.rs:225-242); r may alias a or b
-template <class T2>
-BN_NOINL void fp6_mul(fp6_t<T2> &r, const fp6_t<T2> &a, const fp6_t<T2> &b) {
-    T2 v0, v1, v2, t, c0, c1;
-    fp2_mul(v0, a.c0, b.c0);
-    fp2_mul(v1, a.c1, b.c1);
-    fp2_mul(v2, a.c2, b.c2);
-    fp2_mul_sums(t, a.c1, a.c2, b.c1, b.c2);
-    fp2_comb(c0, t, v1, &v2, &v0, 1);      // xi ((a1+a2)(b1+b2) - v1 - v2) + v0
-    fp2_mul_sums(t, a.c0, a.c1, b.c0, b.c1);
-    fp2_comb(c1, t, v0, &v1, &v2, 2);      // (a0+a1)(b0+b1) - v0 - v1 + xi v2
-    fp2_mul_sums(t, a.c0, a.c2, b.c0, b.c2);
-    fp2_comb(r.c2, t, v0, &v2, &v1, 0);    // (a0+a2)(b0+b2) - v0 - v2 + v1
-    r.c0 = c0;
-    r.c1 = c1;
-}
-// a * (b0 + b1 v): 5 Fp2 products (role of fp6.rs:123-144 mul_by_01); r may alias a
-template <class T2>
-BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, const T2 &b1) {
-    T2 v0, v1, t, c0, c1;
-    fp2_mul(v0, a.c0, b0);
-    fp2_mul(v1, a.c1, b1);
-    fp2_mul_sum1(t, a.c1, a.c2, b1);
-    fp2_comb(c0, t, v1, (const T2 *)nullptr, &v0, 1);   // xi ((a1+a2) b1 - v1) + v0
-    fp2_mul_sums(t, a.c0, a.c1, b0, b1);
-    fp2_comb(c1, t, v0, &v1, (const T2 *)nullptr, 0);   // (a0+a1)(b0+b1) - v0 - v1
-    fp2_mul_sum1(t, a.c0, a.c2, b0);
-    fp2_comb(r.c2, t, v0, (const T2 *)nullptr, &v1, 0); // (a0+a2) b0 - v0 + v1
-    r.c0 = c0;
-    r.c1 = c1;
-}
-#else
 // Karatsuba, 6 Fp2 products (role of fp6.rs:225-242).  r must NOT alias a or b (results are written
 // as they are produced, no staging copies: code size is what bounds these kernels).
 template <class T2>
@@ -702,7 +411,6 @@ BN_NOINL void fp6_mul_by_01(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b0, cons
     fp2_mul_sums(t0, a.c0, a.c1, b0, b1); fp2_sub2(r.c1, t0, v0, v1);
     fp2_mul_sum1(t0, a.c0, a.c2, b0); fp2_sub(t0, t0, v0); fp2_add(r.c2, t0, v1);
 }
-#endif
 template <class T2>
 BN_INL void fp6_mul_fp2(fp6_t<T2> &r, const fp6_t<T2> &a, const T2 &b) { fp2_mul(r.c0, a.c0, b); fp2_mul(r.c1, a.c1, b); fp2_mul(r.c2, a.c2, b); }
 // r = a + v b,  r = a - v b  (v (b0, b1, b2) = (xi b2, b0, b1)); r must not alias b

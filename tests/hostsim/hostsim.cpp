@@ -250,21 +250,6 @@ EXPORT void sim_g2_codec(const uint8_t *pts, size_t n, uint8_t *comp, uint8_t *b
     }
 }
 // wide product / reduction / Fp2 product in isolation (raw limbs)
-EXPORT void sim_fp_mul_wide(uint32_t *r, const uint32_t *a, const uint32_t *b) {
-    fp x, y;
-    fpw w;
-    memcpy(x.v, a, 32);
-    memcpy(y.v, b, 32);
-    fp_mul_wide(w, x, y);
-    memcpy(r, w.v, 64);
-}
-EXPORT void sim_fp_redc(uint32_t *r, const uint32_t *t) {
-    fpw w;
-    fp x;
-    memcpy(w.v, t, 64);
-    fp_redc(x, w);
-    memcpy(r, x.v, 32);
-}
 EXPORT void sim_fp2_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     fp2 x, y, z;
     memcpy(&x, a, 64);

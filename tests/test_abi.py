@@ -56,3 +56,23 @@ def test_product_does_not_touch_the_oracle(native):
             assert "oracle" not in inc and "tests" not in inc and "orc_" not in inc, (f, inc)
     needed = subprocess.run(["readelf", "-d", str(native.SO)], capture_output=True, text=True).stdout
     assert "liborc" not in needed and "hostsim" not in needed
+
+
+def test_rust_ffi_block_matches_the_header():
+    """shim/src/ffi.rs (the extern "C" block of the Rust shim) is generated from include/bls_bn254_b200.h and must not drift"""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ffi = (ROOT / "shim" / "src" / "ffi.rs").read_text()
+    hdr = (ROOT / "include" / "bls_bn254_b200.h").read_text()
+    for name in set(re.findall(r"\b(bn254_[a-z0-9_]+)\s*\(", hdr)):
+        assert "pub fn %s(" % name in ffi, name
+
+
+def test_executed_op_counts_are_in_sync_with_the_kernel_sources():
+    """profiles/executed_ops.json (bench.py's frac_executed) is what the host build of the device headers counts today"""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "count_ops.py"), "--check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

@@ -323,8 +323,8 @@ def test_lane_pair_pairing(sim, orc):
     assert o2.raw == orc.final_exponentiation(ml)
 
 
-def test_wide_and_fused_products(sim):
-    """512-bit product, Montgomery reduction, fused two-term dot product, Fp2 product (raw limbs)"""
+def test_fused_products(sim):
+    """fused two-term dot product and the Fp2 product built from it (raw limbs)"""
     rng = random.Random(7)
     R = 1 << 256
     ri = pow(R, -1, P)
@@ -334,16 +334,6 @@ def test_wide_and_fused_products(sim):
 
     def r(a, n=8):
         return sum(int(a[i]) << (32 * i) for i in range(n))
-    vals = [0, 1, P - 1, 2**256 - 1, 2**255, 2 * P - 1, 0xffffffff] + [rng.randrange(2**256) for _ in range(60)]
-    for _ in range(800):
-        a, b = rng.choice(vals), rng.choice(vals)
-        o = (C.c_uint32 * 16)()
-        sim.sim_fp_mul_wide(o, w(a), w(b))
-        assert r(o, 16) == a * b
-    for t in [0, 1, P * R - 1, (P - 1) * (P - 1), 2 * P * P - 1, R] + [rng.randrange(P * R) for _ in range(600)]:
-        o = (C.c_uint32 * 8)()
-        sim.sim_fp_redc(o, w(t, 16))
-        assert r(o) == t * ri % P
     fv = [0, 1, P - 1, P - 2, (P - 1) // 2, 2**253] + [rng.randrange(P) for _ in range(60)]
     for _ in range(2000):
         a, b, c, d = [rng.choice(fv) for _ in range(4)]
