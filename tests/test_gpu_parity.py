@@ -682,13 +682,18 @@ def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B):
     fe, names = launched(ctx, lambda: ctx.final_exponentiation(ml))
     assert "k_final_exp" in names
     assert fe == gt
-    # min-pk verification at this size: k_miller2 (both pairs variable, one thread per item)
+    # min-pk verification in one chunk of this size: k_miller2 (both pairs variable, one thread per item)
     m = 66400
-    pks, vm, sigs, exp = B.scheme.synth_batch(ctx, m, variant=1, n_keys=32)
-    got, names = launched(ctx, lambda: ctx.verify_batch(1, pks, vm, sigs, B.DST_MIN_PK))
-    assert got == exp and "k_miller2" in names and "k_hash_g2" in names
-    lo = m - 48
-    assert got[lo:] == orc.verify_batch(1, pks[64 * lo:], vm[lo:], sigs[128 * lo:], B.DST_MIN_PK, nthreads=8)
+    c = B.Context([0])
+    try:
+        c.set_option("chunk", 1 << 18)
+        pks, vm, sigs, exp = B.scheme.synth_batch(c, m, variant=1, n_keys=32)
+        got, names = launched(c, lambda: c.verify_batch(1, pks, vm, sigs, B.DST_MIN_PK))
+        assert got == exp and "k_miller2" in names and "k_hash_g2" in names
+        lo = m - 48
+        assert got[lo:] == orc.verify_batch(1, pks[64 * lo:], vm[lo:], sigs[128 * lo:], B.DST_MIN_PK, nthreads=8)
+    finally:
+        c.close()
 
 
 def test_aggregate_exchange_single_rank(ctx, orc, B):
