@@ -466,6 +466,7 @@ def main():
         barrier()
         ms, _ = timed_dev(run, ssteps)
         ms = max_over_ranks(ms)
+        ctx.raw("bn254_pairing_batch", hp1.data_ptr(), hp2.data_ptr(), n, hgt.data_ptr(), hst.data_ptr())   # untimed: sizes the staging buffers
         barrier()
         t0 = time.perf_counter()
         for _ in range(ssteps):
@@ -502,6 +503,7 @@ def main():
             barrier()
             ms, _ = timed_dev(run, ssteps)
             ms = max_over_ranks(ms)
+            ctx.raw("bn254_hash_to_g1" if grp == 1 else "bn254_hash_to_g2", hm3.data_ptr(), ho3.data_ptr(), n3, dstg, len(dstg), hout.data_ptr(), hst3.data_ptr())
             barrier()
             t0 = time.perf_counter()
             for _ in range(ssteps):
@@ -543,6 +545,7 @@ def main():
         barrier()
         ms, _ = timed_dev(run, ssteps)
         ms = max_over_ranks(ms)
+        ctx.aggregate_verify_dist(0, pk4, (blob4, off4), agg4 if rank == 0 else None, b.DST_MIN_SIG)   # untimed
         barrier()
         t0 = time.perf_counter()
         for _ in range(ssteps):
@@ -606,7 +609,8 @@ def main():
             assert ref == bytes(hok5[lo:lo + k5].numpy()), "c5: accept bits differ from the oracle"
             check = "all accept bytes equal the construction; %d tuples straddling the first chunk boundary byte-equal to the oracle" % k5
         sub["c5"] = {"config": "batch verify 2^%d independent (pk, msg, sig) tuples in total (min-sig, %d keys, 1/%d corrupted) sharded over %d rank(s), "
-                               "through bn254_verify_batch on pinned host buffers: chunks of 2^18, upload / kernels / download overlapped" %
+                               "through bn254_verify_batch[_randomized] on pinned host buffers: chunks of one lane-pair wave (66 304 tuples; randomised: 2^18), "
+                               "upload / kernels / download overlapped on two staging sets" %
                                (args.c5_log2n, N_KEYS, CORRUPT_EVERY, world),
                      "tuples_total": n5_total, "tuples_per_rank": n5, "scaling": "strong",
                      "exact": {"seconds": exact_s, "verifications_per_sec": n5_total / exact_s},
