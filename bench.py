@@ -18,6 +18,7 @@ timed region).  The same JSON line carries one sub-record per remaining BASELINE
            one final exponentiation (strong scaling)
   c5       batch verify 2^24 tuples in TOTAL sharded over the N ranks through the host-buffer call (strong scaling),
            exact and randomised
+  prepared the primary batch again with its 4096 public keys PREPARED once (G2Prepared, bn254_verify_batch_prepared)
 Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -217,7 +218,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=65536, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-subgroup", action="store_true", help="verify workloads: also validate inputs (on-curve + order-r subgroup)")
-    ap.add_argument("--sub", default=None, help="sub-records of the other BASELINE configs: all | none | comma list of c1,c3,c4,c5,pairing "
+    ap.add_argument("--sub", default=None, help="sub-records of the other BASELINE configs: all | none | comma list of c1,c3,c4,c5,pairing,prepared "
                                                 "(default: all for the verify workload, none otherwise)")
     ap.add_argument("--c5-log2n", type=int, default=24, help="log2 of the TOTAL tuples of the c5 sub-record (sharded over the ranks)")
     ap.add_argument("--c3-log2n", type=int, default=20)
@@ -248,7 +249,7 @@ def main():
 
     w = args.workload
     subs = args.sub if args.sub is not None else ("all" if w == "verify" else "none")
-    subs = {"all": {"c1", "c3", "c4", "c5", "pairing"}, "none": set()}.get(subs, set(subs.split(",")))
+    subs = {"all": {"c1", "c3", "c4", "c5", "pairing", "prepared"}, "none": set()}.get(subs, set(subs.split(",")))
     variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
     vflags = b.CHECK_SUBGROUP if args.check_subgroup else 0
     n = 1 << args.log2n
@@ -452,6 +453,43 @@ def main():
     # =====================================================================================================
     sub = {}
     ssteps = max(2, min(args.steps, 3))
+
+    if "prepared" in subs and w == "verify":
+        # the primary batch once more, its N_KEYS distinct public keys prepared ONCE (G2Prepared): tuple i names key i mod N_KEYS
+        nk = min(n, N_KEYS)
+        upk = b.scheme.public_keys(ctx, [b.scheme.SecretKey(b.scheme.scalar_from_seed(b.scheme.SEED, i)) for i in range(nk)], 0)   # synth_batch's key list
+        t0 = time.perf_counter()
+        prep = ctx.g2_prepare(upk)
+        prep_s = time.perf_counter() - t0
+        kidx = np.arange(n, dtype=np.uint32) % np.uint32(nk)
+        # synth_batch replaces the key of some corrupted tuples by a neighbour's: follow that in the index array
+        for j in range(n):
+            if expected[j] == 0 and pks[128 * j:128 * (j + 1)] != upk[128 * (j % nk):128 * (j % nk + 1)]:
+                kidx[j] = (j + 1) % nk
+        dki = torch.from_numpy(kidx.view(np.int32)).to(dev)
+        hki = torch.from_numpy(kidx.view(np.int32)).pin_memory()
+        dokp = torch.zeros(n, dtype=torch.uint8, device=dev)
+        run = lambda: ctx.verify_batch_prepared_dev(prep, dki.data_ptr(), d_blob.data_ptr(), d_off.data_ptr(), d_sigs.data_ptr(), n, d_dst.data_ptr(), len(dst),
+                                                    vflags, dokp.data_ptr())
+        run(); ctx.sync()
+        assert bytes(dokp.cpu().numpy()) == expected, "prepared-key verification differs from the construction"
+        barrier()
+        ms, _ = timed_dev(run, args.steps)
+        ms = max_over_ranks(ms)
+        ctx.raw("bn254_verify_batch_prepared", prep._h, hki.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst, len(dst), vflags, h_ok.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.raw("bn254_verify_batch_prepared", prep._h, hki.data_ptr(), h_blob.data_ptr(), h_off.data_ptr(), h_sigs.data_ptr(), n, dst, len(dst), vflags, h_ok.data_ptr())
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert bytes(h_ok[:n].numpy()) == expected
+        sub["prepared"] = {"config": "the primary batch with its %d distinct public keys prepared once (G2Prepared: 88 line triples per key, %.1f MB on the "
+                                     "device); bn254_verify_batch_prepared: both Miller line sequences from tables, no twist-point arithmetic" % (nk, nk * 16896 / 1e6),
+                           "verifications_per_sec": n * world * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                           "e2e_verifications_per_sec": n * world * args.steps / (ems * 1e-3), "prepare_seconds": prep_s,
+                           "checked": "accept bytes equal the construction (= the exact path's)"}
+        prep.close()
+        del dki, dokp
 
     if "pairing" in subs:
         pm = make_messages(n, first + (1 << 40))

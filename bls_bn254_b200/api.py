@@ -71,6 +71,35 @@ def _ptr(x):
     return C.cast(x, C.c_void_p)
 
 
+class PreparedKeys:
+    """G2Prepared (pairings.rs:609-660) for a set of min-sig public keys: the 88 line triples of every key, resident on the
+    GPU(s) of the Context that made it (Context.g2_prepare).  Free with close() (or let it go out of scope)."""
+
+    def __init__(self, ctx, handle, n):
+        self._ctx, self._h, self.n = ctx, handle, n
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._ctx._L.bn254_g2_prepared_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.n
+
+    def export(self, first=0, count=None):
+        """(tables, status): 88 x 192 bytes per key (88 x 3 Fp2 as c0 || c1 big-endian), one status byte per key"""
+        count = self.n - first if count is None else count
+        out, st = C.create_string_buffer(max(1, 88 * 192 * count)), C.create_string_buffer(max(1, count))
+        self._ctx._ck(self._ctx._L.bn254_g2_prepared_export(self._ctx._h, self._h, first, count, _ptr(out), _ptr(st)))
+        return out.raw[:88 * 192 * count], st.raw[:count]
+
+
 class Context:
     """bn254_ctx: owns streams and device scratch on one or more GPUs of this process."""
 
@@ -223,6 +252,31 @@ class Context:
         ok = C.create_string_buffer(n)
         self._ck(self._L.bn254_verify_batch(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags, _ptr(ok)))
         return ok.raw
+
+    def g2_prepare(self, pks, flags=0):
+        """G2Prepared::from for n min-sig public keys (n x 128 bytes): prepare once, verify many (verify_batch_prepared).
+        `flags` = validation of the keys (CHECK_ON_CURVE / CHECK_SUBGROUP); identity keys are unusable either way."""
+        n = len(pks) // 128
+        if len(pks) != 128 * n:
+            raise Bn254Error(-3, "public-key buffer length")
+        h = C.c_void_p()
+        self._ck(self._L.bn254_g2_prepare(self._h, _ptr(pks), n, flags, C.byref(h)))
+        return PreparedKeys(self, h, n)
+
+    def verify_batch_prepared(self, prepared, key_index, msgs, sigs, dst, flags=0):
+        """n accept bytes: tuple i is (prepared key key_index[i], msg i, sig i), min-sig.  Same verdicts as verify_batch."""
+        blob, off, n = _msgs(msgs)
+        if len(key_index) != n:
+            raise Bn254Error(-10, "one key index per tuple")
+        if len(sigs) != 64 * n:
+            raise Bn254Error(-2, "signature buffer length")
+        ki = key_index if hasattr(key_index, "ctypes") else (C.c_uint32 * n)(*key_index)
+        ok = C.create_string_buffer(max(1, n))
+        self._ck(self._L.bn254_verify_batch_prepared(self._h, prepared._h, _ptr(ki), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags, _ptr(ok)))
+        return ok.raw[:n]
+
+    def verify_batch_prepared_dev(self, prepared, key_index, msgs, offsets, sigs, n, dst, dst_len, flags, ok):
+        self._ck(self._L.bn254_verify_batch_prepared_dev(self._h, prepared._h, key_index, msgs, offsets, sigs, n, dst, dst_len, flags, ok))
 
     def verify_batch_randomized(self, variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0):
         """One accept byte per consecutive group of `group` tuples (small-exponent batch test).

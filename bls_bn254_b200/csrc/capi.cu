@@ -100,6 +100,14 @@ struct bn254_ctx {
     size_t verify_chunk(const Dev &d) const { return chunk_is_default && d.shape == 0 ? std::min(chunk, d.lane_wave_threads / 2) : chunk; }
 };
 
+// G2Prepared for a set of public keys: per device of the ctx the 88 line triples of every key (16 896 bytes per key) and one
+// flag byte per key (undecodable / identity / failed the requested checks -> every tuple that names the key is rejected)
+struct bn254_g2_prepared {
+    bn254_ctx *ctx = nullptr;
+    size_t n = 0;
+    std::vector<void *> tab, fl;
+};
+
 namespace {
 
 #define CK(d, call)                                                                                                 \
@@ -433,6 +441,26 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
     d.cur = d.st;
     if (rc) return rc;
     for (int k = 0; k < S; k++) CK(d, cudaStreamWaitEvent(d.st, d.ev_join[k], 0));   // join
+    return 0;
+}
+
+// min-sig verification of one chunk against PREPARED public keys (G2Prepared): decode the signatures, hash, the two-pair loop
+// with both line sequences precomputed (no twist-point arithmetic), final exponentiation, compare
+int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, const uint32_t *key_index, const uint8_t *msgs, const uint64_t *off,
+                        uint64_t base, const uint8_t *sigs, size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+    const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
+    fp12 *F; uint8_t *flf, *flp0, *flp1; g1m *P0, *P1;
+    if (int rc = ensure_t(d, S_F, n, &F)) return rc;
+    if (int rc = ensure_t(d, S_FLF, n, &flf)) return rc;
+    if (int rc = ensure_t(d, S_P0, n, &P0)) return rc;
+    if (int rc = ensure_t(d, S_FLP0, n, &flp0)) return rc;
+    if (int rc = ensure_t(d, S_P1, n, &P1)) return rc;
+    if (int rc = ensure_t(d, S_FLP1, n, &flp1)) return rc;
+    LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flp0, sigs, n, check);
+    if (int rc = dev_hash_g1(d, P1, flp1, msgs, off, base, n, dst, dst_len, 2)) return rc;
+    LAUNCH_PAIR(d, k_miller2_prep, k_miller2_prep_l2, n, F, flf, P0, flp0, P1, flp1, tab, flk, key_index, n);
+    if (int rc = launch_final_exp(d, F, n)) return rc;
+    LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok, F, flf, n);
     return 0;
 }
 
@@ -1349,6 +1377,120 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
     });
 }
 
+// ---- prepared public keys (G2Prepared, pairings.rs:609-660): prepare once, verify many --------------------------------------
+int bn254_g2_prepare(bn254_ctx *ctx, const uint8_t *pks, size_t n, uint32_t flags, bn254_g2_prepared **out) {
+    if (!ctx || !out || (n && !pks)) return fail_arg(ctx, "null pointer");
+    *out = nullptr;
+    bn254_g2_prepared *pr = new bn254_g2_prepared();
+    pr->ctx = ctx;
+    pr->n = n;
+    const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
+    const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
+    int rc = 0;
+    for (auto &d : ctx->devs) {     // every device holds the whole table: tuples are sharded, keys are not
+        cudaSetDevice(d.id);
+        d.rc = 0;
+        rc = [&]() -> int {
+            void *tab = nullptr, *fl = nullptr;
+            CK(d, cudaMalloc(&tab, std::max<size_t>(1, n) * BN254_NUM_LINES * sizeof(line_t<fp2>)));
+            pr->tab.push_back(tab);
+            CK(d, cudaMalloc(&fl, std::max<size_t>(16, n)));
+            pr->fl.push_back(fl);
+            uint8_t *din; g2m *Q;
+            if (int r = ensure_t(d, S_IN_A, n * 128 + 16, &din)) return r;
+            if (int r = ensure_t(d, S_Q0, n + 1, &Q)) return r;
+            if (n) CK(d, cudaMemcpyAsync(din, pks, n * 128, cudaMemcpyHostToDevice, d.st));
+            LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, (uint8_t *)fl, din, n, check);
+            if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, (uint8_t *)fl, Q, n);
+            LAUNCH(d, k_g2_prepare, n, BN_TPB_HEAVY, (line_t<fp2> *)tab, Q, (const uint8_t *)fl, n);
+            CK(d, cudaStreamSynchronize(d.st));
+            return 0;
+        }();
+        if (rc) {
+            ctx->err = d.err;
+            break;
+        }
+    }
+    if (rc) {
+        bn254_g2_prepared_free(pr);
+        return rc;
+    }
+    *out = pr;
+    return 0;
+}
+void bn254_g2_prepared_free(bn254_g2_prepared *pr) {
+    if (!pr) return;
+    for (size_t g = 0; g < pr->tab.size(); g++) {
+        cudaSetDevice(pr->ctx->devs[g].id);
+        if (pr->tab[g]) cudaFree(pr->tab[g]);
+        if (g < pr->fl.size() && pr->fl[g]) cudaFree(pr->fl[g]);
+    }
+    delete pr;
+}
+size_t bn254_g2_prepared_count(const bn254_g2_prepared *pr) { return pr ? pr->n : 0; }
+int bn254_g2_prepared_export(bn254_ctx *ctx, const bn254_g2_prepared *pr, size_t first, size_t count, uint8_t *out, uint8_t *status) {
+    if (!ctx || !pr || pr->ctx != ctx || !out || first + count > pr->n) return fail_arg(ctx, "bad prepared-key range");
+    if (!count) return 0;
+    Dev &d = ctx->devs[0];
+    d.rc = 0;
+    cudaSetDevice(d.id);
+    auto body = [&]() -> int {
+        const size_t nfp2 = count * BN254_NUM_LINES * 3;
+        uint8_t *dout;
+        if (int rc = ensure_t(d, S_OUT, nfp2 * 64, &dout)) return rc;
+        LAUNCH(d, k_prepared_encode, nfp2, BN_TPB_LIGHT, dout, (const line_t<fp2> *)pr->tab[0] + first * BN254_NUM_LINES, nfp2);
+        CK(d, cudaMemcpyAsync(out, dout, nfp2 * 64, cudaMemcpyDeviceToHost, d.st));
+        std::vector<uint8_t> fl(count);
+        CK(d, cudaMemcpyAsync(fl.data(), (const uint8_t *)pr->fl[0] + first, count, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaStreamSynchronize(d.st));
+        for (size_t i = 0; i < count; i++) {
+            const bool good = !(fl[i] & (FL_BAD | FL_INF));
+            if (status) status[i] = good ? 1 : 0;
+            if (!good) memset(out + i * BN254_NUM_LINES * 192, 0, (size_t)BN254_NUM_LINES * 192);   // the table of an unusable key is undefined
+        }
+        return 0;
+    };
+    int rc = body();
+    if (rc) ctx->err = d.err;
+    return rc;
+}
+int bn254_verify_batch_prepared(bn254_ctx *ctx, const bn254_g2_prepared *pr, const uint32_t *key_index, const uint8_t *msgs, const uint64_t *offsets,
+                                const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (!pr || pr->ctx != ctx) return fail_arg(ctx, "prepared keys belong to another ctx");
+    if (n == 0) return 0;
+    if (!key_index || !offsets || !sigs || !ok) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, offsets, n)) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (key_index[i] >= pr->n) return fail_arg(ctx, "key index out of range");
+    const bool pin_ok = host_ptr_is_pinned(ok);
+    return run_sharded(ctx, n, [=](Dev &d, size_t lo, size_t hi) -> int {
+        const size_t g = (size_t)(&d - &ctx->devs[0]);
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        const size_t chunk = ctx->verify_chunk(d);
+        Pipe pipe(d);
+        for (size_t c = lo; c < hi; c += chunk) {
+            size_t e = std::min(hi, c + chunk), m = e - c;
+            if (int rc = pipe.begin(pin_ok ? 0 : pad64(m))) return rc;
+            const uint8_t *dm; const uint64_t *dof; uint64_t base;
+            if (int rc = stage_msgs(d, &pipe, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            uint8_t *dsig, *dok; uint32_t *dki;
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), m, &dki)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * 64, &dsig)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m, &dok)) return rc;
+            if (int rc = pipe.h2d(dki, key_index + c, m * sizeof(uint32_t))) return rc;
+            if (int rc = pipe.h2d(dsig, sigs + c * 64, m * 64)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
+            if (int rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[g], (const uint8_t *)pr->fl[g], dki, dm, dof, base, dsig, m, ddst, dlen, flags, dok))
+                return rc;
+            if (int rc = pipe.d2h(ok + c, pin_ok, dok, m)) return rc;
+            if (int rc = pipe.end()) return rc;
+        }
+        return pipe.finish();
+    });
+}
+
 namespace {
 // Every device of the ctx reduces its contiguous slice of the (pk_i, m_i) pairs to ONE record in its NCCL send buffer
 // (device 0 -- rank 0 of a one-process-per-GPU job -- also takes the aggregate signature), the records are all-gathered
@@ -1757,6 +1899,15 @@ int bn254_verify_batch_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, cons
     const uint8_t *ddst; uint32_t dlen;
     int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
     if (!rc) rc = dev_verify(d, variant, pks, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
+    DEV_EPILOGUE(rc);
+}
+int bn254_verify_batch_prepared_dev(bn254_ctx *ctx, const bn254_g2_prepared *pr, const uint32_t *key_index, const uint8_t *msgs, const uint64_t *offsets,
+                                    const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok) {
+    DEV_PROLOGUE();
+    if (!pr || pr->ctx != ctx) return fail_arg(ctx, "prepared keys belong to another ctx");
+    const uint8_t *ddst; uint32_t dlen;
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[0], (const uint8_t *)pr->fl[0], key_index, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
     DEV_EPILOGUE(rc);
 }
 int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,

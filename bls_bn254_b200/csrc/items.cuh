@@ -109,6 +109,26 @@ BN_INL void item_miller2(fp12 &f, uint8_t &fl, const g1m &p0, uint8_t flp0, cons
     fl = ((flp0 | flq0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
 }
 
+// two pairs, both from precomputed lines: pair 0 = (p0, -g2), pair 1 = (p1, the prepared point behind tab1 / flq1)
+BN_INL void item_miller2_prep(fp12 &f, uint8_t &fl, const g1m &p0, uint8_t flp0, const g1m &p1, uint8_t flp1, const line_t<fp2> *tab1, uint8_t flq1) {
+    const bool live0 = (flp0 & (FL_INF | FL_BAD)) == 0, live1 = ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0;
+    miller_loop_prepared<fp2>(f, p0.x, p0.y, live0, p1.x, p1.y, tab1, live1);
+    fl = ((flp0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
+}
+BN_INL void item_miller2_prep_l2(fp12 &F, uint8_t &fl, const g1m &p0, uint8_t flp0, const g1m &p1, uint8_t flp1, const line_t<fp2> *tab1, uint8_t flq1) {
+    const bool live0 = (flp0 & (FL_INF | FL_BAD)) == 0, live1 = ((flp1 | flq1) & (FL_INF | FL_BAD)) == 0;
+    fp c0x = p0.x, c0y = p0.y, c1x = p1.x, c1y = p1.y;   // local copies: one address space per pointer parameter of the leaves
+    fp12l f;
+    miller_loop_prepared<fp2l>(f, c0x, c0y, live0, c1x, c1y, tab1, live1);
+    fp12_store(F, f);
+    fl = ((flp0 | flp1 | flq1) & FL_BAD) ? FL_BAD : 0;
+}
+// G2Prepared::from for one decoded point
+BN_INL void item_g2_prepare(line_t<fp2> *out, const g2m &q, uint8_t fl) {
+    if (fl & (FL_BAD | FL_INF)) return;      // the table of an unusable key is never read: its tuples are dead / rejected
+    g2_prepare_lines(out, q.x, q.y);
+}
+
 // ---- final exponentiation / GT ---------------------------------------------------------------
 BN_INL void item_final_exp(fp12 &f) { final_exponentiation(f); }
 

@@ -247,6 +247,48 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_final_exp_l2(fp12 
     item_final_exp_l2(F[i]);
 }
 
+// ---- prepared public keys (G2Prepared): the 88 line triples per key, and the two-pair loop that reads them ----------------
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_prepare(line_t<fp2> *tab, const g2m *Q, const uint8_t *fl, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2m q;
+    copy_rec(q, Q[i]);
+    item_g2_prepare(tab + (size_t)BN254_NUM_LINES * i, q, fl[i]);
+}
+// tuple i: pair 0 = (P0[i], -g2), pair 1 = (P1[i], key[key_index[i]])
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2_prep(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+                                                                const uint8_t *flP1, const line_t<fp2> *tab, const uint8_t *flK,
+                                                                const uint32_t *key_index, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t fl;
+    fp12 f;
+    g1m p0, p1;
+    copy_rec(p0, P0[i]);
+    copy_rec(p1, P1[i]);
+    const size_t kidx = key_index[i];
+    item_miller2_prep(f, fl, p0, flP0[i], p1, flP1[i], tab + (size_t)BN254_NUM_LINES * kidx, flK[kidx]);
+    copy_rec(F[i], f);
+    flF[i] = fl;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_prep_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+                                                                                const uint8_t *flP1, const line_t<fp2> *tab, const uint8_t *flK,
+                                                                                const uint32_t *key_index, size_t n) {
+    BN_L2_PROLOGUE();
+    uint8_t fl;
+    const size_t kidx = key_index[i];
+    item_miller2_prep_l2(F[i], fl, P0[i], flP0[i], P1[i], flP1[i], tab + (size_t)BN254_NUM_LINES * kidx, flK[kidx]);
+    flF[i] = fl;
+}
+// wire form of a prepared key (88 x 3 Fp2 as c0 || c1, 32-byte big-endian each): parity checks against the oracle
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_prepared_encode(uint8_t *out, const line_t<fp2> *tab, size_t nfp2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfp2) return;
+    const fp2 *c = reinterpret_cast<const fp2 *>(tab) + i;
+    fp_to_be(out + 64 * i, c->c0);
+    fp_to_be(out + 64 * i + 32, c->c1);
+}
+
 // ---- the slot machine (vm.cuh): a lane pair per pairing, every live value in a shared-memory slot, the tower algebra as
 //      constant-memory programs.  Thread t works on item t / 2 exactly as in the lane-pair kernels above (BN_L2_PROLOGUE).
 //      These kernels assume LIVE pairs (no identity input): an item with a dead pair is recomputed afterwards by the fix-up

@@ -196,6 +196,77 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
     }
 }
 
+// ---- G2Prepared (pairings.rs:609-660, 725-757): the 88 line triples of a G2 point, computed once per public key ----------
+// out[0..87] in consumption order: per NAF digit a doubling line [and an addition line], then the two Frobenius additions --
+// the schedule miller_loop runs, with the same doubling_step / addition_step, so a loop fed from the table is bit-identical.
+BN_INL void g2_prepare_lines(line_t<fp2> *out, const fp2 &qx, const fp2 &qy) {
+    g2j<fp2> r;
+    fp2 nqy;
+    line_t<fp2> l;
+    r.x = qx;
+    r.y = qy;
+    fp2_set_one(r.z);
+    fp2_neg(nqy, qy);
+    int idx = 0;
+#pragma unroll 1
+    for (int s = 0; s < BN254_ATE_NAF_LEN; s++) {
+        int d = k::ATE_NAF[s];
+        doubling_step(l, r);
+        out[idx++] = l;
+        if (d) {
+            addition_step(l, r, qx, d > 0 ? qy : nqy);
+            out[idx++] = l;
+        }
+    }
+    fp2 q1x, q1y, q2x, q2y, t, eu, ev;
+    fp2_load(eu, kfp2(k::ENDO_U));
+    fp2_load(ev, kfp2(k::ENDO_V));
+    fp2_conj(t, qx); fp2_mul(q1x, t, eu);
+    fp2_conj(t, qy); fp2_mul(q1y, t, ev);
+    fp2_conj(t, q1x); fp2_mul(q2x, t, eu);
+    fp2_conj(t, q1y); fp2_mul(q2y, t, ev);
+    fp2_neg(q2y, q2y);
+    addition_step(l, r, q1x, q1y);
+    out[idx++] = l;
+    addition_step(l, r, q2x, q2y);
+    out[idx++] = l;
+}
+// line `tab[idx]` of a prepared point (HBM, one-thread fp2 layout) -> this thread's / lane's representation
+BN_INL void line_load(line_t<fp2> &l, const line_t<fp2> &m) { l = m; }
+BN_INL void line_load(line_t<fp2l> &l, const line_t<fp2> &m) {
+    const bool odd = lane_par() != 0;
+    const fp *pa = odd ? &m.a.c1 : &m.a.c0, *pb = odd ? &m.b.c1 : &m.b.c0, *pc = odd ? &m.c.c1 : &m.c.c0;   // address selects, one load path
+    l.a.v = *pa;
+    l.b.v = *pb;
+    l.c.v = *pc;
+}
+// Two-pair Miller loop with BOTH line sequences precomputed: pair 0 = (P0, -g2) from the constant table, pair 1 = (P1, Q1)
+// from Q1's prepared table in HBM.  No twist-point arithmetic at all: per step one Fp12 squaring and two sparse products
+// (multi_miller_loop over G2Prepared terms, pairings.rs:808-857).
+template <class T2>
+BN_INL void miller_loop_prepared(fp12_t<T2> &f, const fp &p0x, const fp &p0y, bool live0, const fp &p1x, const fp &p1y, const line_t<fp2> *tab1, bool live1) {
+    const bool skip = skips_dead<T2>::value;
+    line_t<T2> l;
+    fp12_set_one(f);
+    int idx = 0;
+#pragma unroll 1
+    for (int s = 0; s < BN254_ATE_NAF_LEN + 1; s++) {
+        // s < NAF_LEN: the doubling line and, for a non-zero digit, the addition line; s == NAF_LEN: the two Frobenius lines
+        const int nlines = s < BN254_ATE_NAF_LEN ? (k::ATE_NAF[s] ? 2 : 1) : 2;
+        if (s && s < BN254_ATE_NAF_LEN) fp12_sqr(f, f);
+#pragma unroll 1
+        for (int j = 0; j < nlines; j++) {
+            if (!skip || live0) ell_fixed(f, idx, p0x, p0y, live0);
+            if (!skip || live1) {
+                line_load(l, tab1[idx]);
+                if (skip) ell(f, l, p1x, p1y);
+                else ell_sel(f, l, p1x, p1y, live1);
+            }
+            idx++;
+        }
+    }
+}
+
 // f^x (x = 0x44e992b44a6909f1, 63 bits) in the cyclotomic subgroup, then conjugate
 // (pairings.rs:117-134 role).  Width-4 signed window over f, f^3, f^5, f^7 (a negative digit uses the
 // conjugate, which is the inverse here): 63 cyclotomic squarings + 16 products instead of 62 + 27.

@@ -1044,6 +1044,32 @@ EXPORT int orc_final_exponentiation(const uint8_t *ml, size_t n, uint8_t *gt, ui
     return 0;
 }
 /* Fp12 product of n 384-byte elements (MillerLoopResult + MillerLoopResult, pairings.rs:37-43) */
+/* G2Prepared::from (pairings.rs:609-660, 725-757, with the 88-line BN254 schedule of SURVEY.md 0.5): the line triples of
+ * each point in consumption order, as 88 x 3 Fp2 values in the Gt coefficient byte convention (c0 || c1, 32-byte big-endian
+ * each: pairings.rs:499-514), 88 x 192 bytes per point.  status 0 (and zero bytes) for an undecodable / identity point. */
+EXPORT int orc_g2_prepare(const uint8_t *pts, size_t n, uint8_t *out, uint8_t *status) {
+    orc_init();
+    line_t lines[NUM_LINES];
+    for (size_t i = 0; i < n; i++) {
+        g2a q;
+        uint8_t *o = out + (size_t)NUM_LINES * 192 * i;
+        if (!g2a_from_bytes(&q, pts + 128 * i) || q.inf) {
+            memset(o, 0, (size_t)NUM_LINES * 192);
+            if (status) status[i] = 0;
+            continue;
+        }
+        prepare_lines(lines, &q);
+        for (int k = 0; k < NUM_LINES; k++) {
+            const fp2 *c = (const fp2 *)&lines[k];
+            for (int j = 0; j < 3; j++) {
+                fp_to_be(o + 192 * k + 64 * j, &c[j].c0);
+                fp_to_be(o + 192 * k + 64 * j + 32, &c[j].c1);
+            }
+        }
+        if (status) status[i] = 1;
+    }
+    return 0;
+}
 EXPORT int orc_fp12_product(const uint8_t *in, size_t n, uint8_t *out) {
     orc_init();
     fp12 acc = F12_ONE, t;

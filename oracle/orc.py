@@ -100,6 +100,14 @@ def miller_loop_batch(g1, g2, nthreads=1):
     return out.raw
 
 
+def g2_prepare(pts):
+    """88 x 192 bytes of line coefficients per point (G2Prepared), status byte per point"""
+    n = len(pts) // 128
+    out, st = _buf(88 * 192 * n), _buf(n)
+    lib().orc_g2_prepare(pts, C.c_size_t(n), out, st)
+    return out.raw, st.raw
+
+
 def multi_miller_loop(g1, g2):
     n = len(g1) // 64
     out = _buf(384)

@@ -456,3 +456,37 @@ EXPORT unsigned long long sim_vm_ops(int fam, int fexp, const uint8_t *p0, const
     sim_vm(fam, fexp, p0, q0, p1, q1, f_in, out);
     return g_ops.load();
 }
+
+// ---- G2Prepared: the line tables (wire form as the oracle's orc_g2_prepare) and the two-pair loop fed from them ----------
+EXPORT void sim_g2_prepare(const uint8_t *pt, uint8_t *out) {
+    static line_t<fp2> tab[BN254_NUM_LINES];
+    g2m q;
+    uint8_t fl;
+    item_g2_decode(q, fl, pt, 0);
+    item_g2_prepare(tab, q, fl);
+    const fp2 *c = reinterpret_cast<const fp2 *>(tab);
+    for (int i = 0; i < BN254_NUM_LINES * 3; i++) {
+        fp_to_be(out + 64 * i, c[i].c0);
+        fp_to_be(out + 64 * i + 32, c[i].c1);
+    }
+}
+struct prep_args { g1m p0, p1; uint8_t f0, f1, fq; line_t<fp2> tab[BN254_NUM_LINES]; fp12 F; uint8_t fl; };
+static void prep_l2_body(void *vp) {
+    prep_args *a = (prep_args *)vp;
+    uint8_t fl;
+    item_miller2_prep_l2(a->F, fl, a->p0, a->f0, a->p1, a->f1, a->tab, a->fq);
+    if (bn_host_lane_par() == 0) a->fl = fl;
+}
+// lanes = 0: one thread per pairing, 1: two emulated lanes
+EXPORT void sim_miller2_prepared(const uint8_t *p0, const uint8_t *p1, const uint8_t *q1, int lanes, uint8_t *out) {
+    static prep_args a;
+    memset(&a, 0, sizeof a);
+    g2m q;
+    item_g1_decode(a.p0, a.f0, p0, 0);
+    item_g1_decode(a.p1, a.f1, p1, 0);
+    item_g2_decode(q, a.fq, q1, 0);
+    item_g2_prepare(a.tab, q, a.fq);
+    if (lanes) run_pair(prep_l2_body, &a);
+    else item_miller2_prep(a.F, a.fl, a.p0, a.f0, a.p1, a.f1, a.tab, a.fq);
+    fp12_to_bytes(out, a.F);
+}

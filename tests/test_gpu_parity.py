@@ -730,3 +730,50 @@ def test_nccl_exchange_in_multi_device_ctx(orc, B):
     finally:
         c1.close()
         c2.close()
+
+
+def test_verify_with_prepared_keys(ctx, orc, B, shape):
+    """bn254_g2_prepare / bn254_verify_batch_prepared (G2Prepared, pairings.rs:609-660): the exported line tables equal the
+    oracle's, and verification against prepared keys gives the accept bytes of bn254_verify_batch on the expanded key array --
+    which equal the oracle's -- with unusable keys (identity, undecodable, outside the subgroup when asked) rejecting their tuples."""
+    nk, n = 9, 230
+    sks = [B.scheme.SecretKey(B.scheme.scalar_from_seed(77, i)) for i in range(nk)]
+    keys = bytearray(B.scheme.public_keys(ctx, sks, 0))
+    ident2 = bytes(64) + bytes(63) + b"\x01"
+    raw = orc.svdw_g2((5).to_bytes(32, "big") + (9).to_bytes(32, "big"))        # on the twist, outside the subgroup
+    keys[128 * 6:128 * 7] = ident2
+    keys[128 * 7:128 * 8] = b"\xff" * 128
+    keys[128 * 8:128 * 9] = raw
+    keys = bytes(keys)
+    rng = random.Random(41)
+    kidx = [rng.randrange(nk) for _ in range(n)]
+    msgs = [rng.randbytes(rng.choice((0, 5, 32, 77))) for _ in range(n)]
+    sc = b"".join(sks[k].to_bytes() for k in kidx)
+    sigs = bytearray(ctx.g1_mul(ctx.hash_to_g1(msgs, B.DST_MIN_SIG), sc))
+    for j in range(5, n, 17):                                                   # a few wrong signatures
+        sigs[64 * j:64 * (j + 1)] = sigs[64 * (j - 1):64 * j]
+    sigs = bytes(sigs)
+    pks = b"".join(keys[128 * k:128 * (k + 1)] for k in kidx)
+    for flags in (0, B.CHECK_SUBGROUP):
+        prep = ctx.g2_prepare(keys, flags)
+        assert len(prep) == nk
+        tabs, st = prep.export()
+        ref_tabs, ref_st = orc.g2_prepare(keys)
+        want_st = bytearray(ref_st)
+        if flags:
+            want_st[8] = 0
+        assert st == bytes(want_st)
+        for k in range(nk):
+            if st[k]:
+                assert tabs[88 * 192 * k:88 * 192 * (k + 1)] == ref_tabs[88 * 192 * k:88 * 192 * (k + 1)], k
+        got, names = launched(ctx, lambda: ctx.verify_batch_prepared(prep, kidx, msgs, sigs, B.DST_MIN_SIG))
+        assert got == ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=flags)
+        assert got == orc.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG, flags=flags, nthreads=8)
+        assert names & {"k_miller2_prep", "k_miller2_prep_l2"}
+        assert 0 < sum(got) < n and all(got[i] == 0 for i in range(n) if kidx[i] in (6, 7) or (flags and kidx[i] == 8))
+        prep.close()
+    prep = ctx.g2_prepare(keys[:128 * 6])
+    with pytest.raises(B.Bn254Error):
+        ctx.verify_batch_prepared(prep, [6] + kidx[1:], msgs, sigs, B.DST_MIN_SIG)      # key index out of range
+    assert ctx.verify_batch_prepared(prep, [], [], b"", B.DST_MIN_SIG) == b""
+    prep.close()

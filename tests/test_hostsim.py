@@ -343,3 +343,25 @@ def test_fused_products(sim):
         o = (C.c_uint32 * 16)()
         sim.sim_fp2_mul(o, w(a | (b << 256), 16), w(c | (d << 256), 16))
         assert r(o, 16) == ((a * c - b * d) * ri % P) | (((a * d + b * c) * ri % P) << 256)
+
+
+def test_prepared_keys(sim, orc):
+    """G2Prepared (pairings.rs:609-660): the line tables equal the oracle's byte for byte, and the two-pair loop fed from the
+    table equals multi_miller_loop in both shapes, a dead pair included"""
+    rng = random.Random(3)
+    msgs = [rng.randbytes(9) for _ in range(3)]
+    g1, g2 = orc.hash_to_g1(msgs, QUUX_G1), orc.hash_to_g2(msgs, QUUX_G2)
+    out = C.create_string_buffer(88 * 192)
+    for i in range(3):
+        sim.sim_g2_prepare(g2[128 * i:128 * (i + 1)], out)
+        assert out.raw == orc.g2_prepare(g2[128 * i:128 * (i + 1)])[0]
+    g = orc.g2_generator()
+    neg = lambda b: ((P - int.from_bytes(b, "big")) % P).to_bytes(32, "big")
+    ng2 = g[:64] + neg(g[64:96]) + neg(g[96:])
+    ident = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    o = C.create_string_buffer(384)
+    for lanes in (0, 1):
+        sim.sim_miller2_prepared(g1[:64], g1[64:128], g2[128:256], lanes, o)
+        assert o.raw == orc.multi_miller_loop(g1[:128], ng2 + g2[128:256])
+        sim.sim_miller2_prepared(g1[:64], ident, g2[128:256], lanes, o)
+        assert o.raw == orc.multi_miller_loop(g1[:64] + ident, ng2 + g2[128:256])
