@@ -339,6 +339,32 @@ inline std::vector<uint8_t> verify_batch_randomized(const Context &ctx, const st
                                                 dst.data(), dst.size(), flags, seed.data(), rand_bits, group, ok.data()));
     return ok;
 }
+// G2Prepared (pairings.rs:609-660) for a set of public keys: prepare once, verify many.  Tuple i of verify_batch names key
+// key_index[i]; the accept flags equal verify_batch's on the expanded key array.
+class G2Prepared {
+  public:
+    G2Prepared(const Context &ctx, const std::vector<PublicKey> &keys, uint32_t flags = 0) : h_(nullptr) {
+        ctx.check(bn254_g2_prepare(ctx.raw(), keys.empty() ? nullptr : keys[0].bytes.data(), keys.size(), flags, &h_));
+    }
+    ~G2Prepared() { bn254_g2_prepared_free(h_); }
+    G2Prepared(const G2Prepared &) = delete;
+    G2Prepared &operator=(const G2Prepared &) = delete;
+    size_t size() const { return bn254_g2_prepared_count(h_); }
+    std::vector<uint8_t> verify_batch(const Context &ctx, const std::vector<uint32_t> &key_index, const Messages &msgs, const std::vector<Signature> &sigs,
+                                      uint32_t flags = 0) const {
+        size_t n = msgs.size();
+        if (key_index.size() != n || sigs.size() != n) throw Bn254Error(BN254_ERR_ARG, "length mismatch");
+        std::vector<uint8_t> ok(n);
+        Bytes dst = dst_of(MinSig);
+        if (n)
+            ctx.check(bn254_verify_batch_prepared(ctx.raw(), h_, key_index.data(), msgs.data(), msgs.offsets.data(), sigs[0].bytes.data(), n, dst.data(),
+                                                  dst.size(), flags, ok.data()));
+        return ok;
+    }
+
+  private:
+    bn254_g2_prepared *h_;
+};
 inline Signature aggregate(const Context &ctx, const std::vector<Signature> &sigs) { return G1Affine::sum(ctx, sigs); }
 // distinct messages: e(agg, -g2) * prod e(H(m_i), pk_i) == 1
 inline bool aggregate_verify(const Context &ctx, const std::vector<PublicKey> &pks, const Messages &msgs, const Signature &agg, uint32_t flags = 0) {

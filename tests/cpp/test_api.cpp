@@ -132,6 +132,14 @@ int main(int argc, char **argv) {
     CHECK(verify_batch_randomized(ctx, pks, msgs, sigs, seed, 10) == std::vector<uint8_t>(4, 1));
     std::vector<uint8_t> grp = verify_batch_randomized(ctx, pks, msgs, bad, seed, 10);
     CHECK(grp.size() == 4 && grp[0] == 0 && grp[1] == 1 && grp[2] == 1 && grp[3] == 1);
+    {   // prepared keys: the same verdicts with the public keys' line tables computed once
+        G2Prepared prep(ctx, pks, BN254_FLAG_CHECK_SUBGROUP);
+        std::vector<uint32_t> idx(pks.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+        CHECK(prep.size() == pks.size());
+        CHECK(prep.verify_batch(ctx, idx, msgs, sigs) == verify_batch(ctx, pks, msgs, sigs));
+        CHECK(prep.verify_batch(ctx, idx, msgs, bad) == verify_batch(ctx, pks, msgs, bad));
+    }
     Signature agg = aggregate(ctx, sigs);
     CHECK(aggregate_verify(ctx, pks, msgs, agg));
     CHECK(!aggregate_verify(ctx, pks, msgs, sigs[0]));

@@ -8,6 +8,6 @@ import json
 d=json.load(open('gpurun_out/bench_verify.json'))
 print('value',d['value'],'e2e',d['e2e']['value'],'frac',d['roofline']['frac'],d['roofline']['kernel'])
 for k,v in d['roofline']['kernels'].items(): print(' ',k,v)
-for k in ('c1','c3','pairing','c4','c5'): print(k, json.dumps(d.get(k)))
+for k in ('c1','c3','pairing','prepared','c4','c5'): print(k, json.dumps(d.get(k)))
 print('cpu',d['cpu_baseline'])
 "
