@@ -27,6 +27,7 @@ enum Scratch {
     S_IN_A2, S_IN_B2, S_IN_C2, S_MSGS2, S_OFF2, S_OUT2, S_STATUS2,
     S_AGG_SEND, S_AGG_RECV,   // agg_rec: this rank's record / the gathered records of all ranks
     S_VM_SCRATCH,             // per-item scratch variables of the slot-machine final exponentiation
+    S_RB_T, S_RB_T2, S_RB_BAD2,   // per staging set: group products / bad flags handed to the overlapped tail of the randomised path
     S_COUNT
 };
 // staging set s (0 / 1) of the chunk pipeline
@@ -40,6 +41,8 @@ inline Scratch stage_buf(Scratch first, int s) {
         case S_OFF: return S_OFF2;
         case S_OUT: return S_OUT2;
         case S_STATUS: return S_STATUS2;
+        case S_RB_T: return S_RB_T2;
+        case S_RB_BAD: return S_RB_BAD2;
         default: return first;
     }
 }
@@ -71,6 +74,10 @@ struct Dev {
     // frees up while the full-size kernels of the main stream keep the machine busy.
     cudaStream_t hi = nullptr;
     cudaEvent_t ev_hi_fork = nullptr, ev_hi_join = nullptr;
+    // Second high-priority stream: the per-group TAIL of a randomised chunk (one final exponentiation per group on a few
+    // thousand threads, ~4 ms of latency that fills 2 % of the machine) runs here, next to the main kernels of the NEXT chunk.
+    cudaStream_t tail = nullptr;
+    cudaEvent_t ev_tail[2] = {};
     int nsub = 1;
     size_t lane_wave_threads = 0;   // threads of one full wave of the lane-pair kernels on this device
     // Shape of the pairing kernels: 0 = picked per launch (lane pairs while 2n threads fit one wave), 1 = one thread per
@@ -497,9 +504,11 @@ int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, cons
 
 // One chunk: n tuples (device pointers) in groups of `group` -> ceil(n / group) accept bytes.  `idx0` is the
 // index of the chunk's first tuple in the whole call (it enters the scalar derivation).
+// `tail_set` >= 0 (the host pipeline): the per-group tail -- final exponentiation and verdict -- runs on d.tail with buffers of
+// that staging set, so that it overlaps the main kernels of the next chunk; the caller collects `ok` on d.tail.
 int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
                     size_t n, size_t group, const uint8_t *seed, uint64_t idx0, int nbits, const uint8_t *dst, uint32_t dst_len, uint32_t flags,
-                    uint8_t *ok) {
+                    uint8_t *ok, int tail_set = -1) {
     const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
     const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
     const size_t nseg = (n + group - 1) / group;
@@ -520,7 +529,8 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
     if (int rc = ensure_t(d, S_RB_GQ, nseg, &GQ)) return rc;
     if (int rc = ensure_t(d, S_RB_FLP, nseg, &gflp)) return rc;
     if (int rc = ensure_t(d, S_RB_FLQ, nseg, &gflq)) return rc;
-    if (int rc = ensure_t(d, S_RB_BAD, nseg, &gbad)) return rc;
+    if (tail_set >= 0 && (d.prof || d.shape == 3 || d.cur != d.st)) tail_set = -1;   // per-kernel timing / shared scratch want it serial
+    if (int rc = ensure_t(d, stage_buf(S_RB_BAD, tail_set > 0 ? 1 : 0), nseg, &gbad)) return rc;
     CK(d, cudaMemsetAsync(gbad, 0, nseg * sizeof(int), d.cur));
     // The signature side (scale, per-group sums, one Miller loop per GROUP against the fixed generator) only needs
     // the decoded signatures: it runs on the side stream next to the per-tuple pipeline of the main stream.
@@ -596,9 +606,26 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
         SEG_LEVELS(d, k_fp12_seg_reduce, fp12, F, FA, FB, n, group, &Fg);
     }
     if (side) CK(d, cudaStreamWaitEvent(d.st, d.ev_hi_join, 0));
-    LAUNCH(d, k_fp12_mul_into, nseg, BN_TPB_HEAVY, Fg, Fs, nseg);
-    if (int rc = launch_final_exp(d, Fg, nseg)) return rc;
-    LAUNCH(d, k_rbv_ok, nseg, BN_TPB_LIGHT, ok, Fg, gbad, nseg);
+    if (tail_set < 0) {
+        LAUNCH(d, k_fp12_mul_into, nseg, BN_TPB_HEAVY, Fg, Fs, nseg);
+        if (int rc = launch_final_exp(d, Fg, nseg)) return rc;
+        LAUNCH(d, k_rbv_ok, nseg, BN_TPB_LIGHT, ok, Fg, gbad, nseg);
+        return 0;
+    }
+    // hand the group products to the tail stream in a buffer of this staging set; everything the next chunk overwrites
+    // (F, FA, FB, Fs) has been consumed on the launch stream by then
+    fp12 *T;
+    if (int rc = ensure_t(d, stage_buf(S_RB_T, tail_set), nseg, &T)) return rc;
+    LAUNCH(d, k_fp12_mul_out, nseg, BN_TPB_HEAVY, T, Fg, Fs, nseg);
+    CK(d, cudaEventRecord(d.ev_tail[tail_set], d.st));
+    CK(d, cudaStreamWaitEvent(d.tail, d.ev_tail[tail_set], 0));
+    struct Cur {   // LAUNCH goes to d.cur; always put the main stream back
+        Dev &d; cudaStream_t keep;
+        explicit Cur(Dev &dd) : d(dd), keep(dd.cur) { dd.cur = dd.tail; }
+        ~Cur() { d.cur = keep; }
+    } guard(d);
+    if (int rc = launch_final_exp(d, T, nseg)) return rc;
+    LAUNCH(d, k_rbv_ok, nseg, BN_TPB_LIGHT, ok, T, gbad, nseg);
     return 0;
 }
 
@@ -771,7 +798,8 @@ struct Pipe {
     size_t k = 0;
     size_t pin_used = 0;
     std::vector<Pending> pend[2];
-    explicit Pipe(Dev &dd) : d(dd) {}
+    cudaStream_t rs;      // the stream a chunk's results appear on (the launch stream unless a tail stream finishes the chunk)
+    explicit Pipe(Dev &dd) : d(dd), rs(dd.st) {}
     int set() const { return (int)(k & 1); }
     // staging set k & 1 was last used by chunk k - 2: wait for it and hand its staged results to the caller
     int deliver(int s) {
@@ -809,17 +837,17 @@ struct Pipe {
     int d2h(uint8_t *host, bool pinned, const uint8_t *dev, size_t bytes) {
         if (!bytes) return 0;
         if (pinned) {
-            CK(d, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d.st));
+            CK(d, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, rs));
             return 0;
         }
         int s = set();
-        CK(d, cudaMemcpyAsync((uint8_t *)d.pin[s] + pin_used, dev, bytes, cudaMemcpyDeviceToHost, d.st));
+        CK(d, cudaMemcpyAsync((uint8_t *)d.pin[s] + pin_used, dev, bytes, cudaMemcpyDeviceToHost, rs));
         pend[s].push_back({host, pin_used, bytes});
         pin_used += (bytes + 63) & ~(size_t)63;
         return 0;
     }
     int end() {
-        CK(d, cudaEventRecord(d.ev_out[set()], d.st));
+        CK(d, cudaEventRecord(d.ev_out[set()], rs));
         k++;
         return 0;
     }
@@ -831,6 +859,7 @@ struct Pipe {
                 if (int rc = deliver(s)) return rc;
         }
         CK(d, cudaStreamSynchronize(d.st));
+        if (rs != d.st) CK(d, cudaStreamSynchronize(rs));
         return 0;
     }
 };
@@ -973,6 +1002,12 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_hi_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            e = cudaStreamCreateWithPriority(&d.tail, cudaStreamNonBlocking, hi_pri);
+        }
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&d.ev_tail[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking);
         for (int k = 0; k < 2 && e == cudaSuccess; k++) {
             e = cudaEventCreateWithFlags(&d.ev_in[k], cudaEventDisableTiming);
@@ -1129,6 +1164,12 @@ void bn254_ctx_destroy(bn254_ctx *ctx) {
             cudaStreamSynchronize(d.cp);
             cudaStreamDestroy(d.cp);
         }
+        if (d.tail) {
+            cudaStreamSynchronize(d.tail);
+            cudaStreamDestroy(d.tail);
+        }
+        for (int k = 0; k < 2; k++)
+            if (d.ev_tail[k]) cudaEventDestroy(d.ev_tail[k]);
         for (int k = 0; k < 2; k++) {
             if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
             if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
@@ -1355,6 +1396,8 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
         if (int rc = ensure_t(d, S_RB_SEED, 32, &dseed)) return rc;
         CK(d, cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, d.st));
         Pipe pipe(d);
+        const bool overlap_tail = !d.prof && d.shape != 3;
+        if (overlap_tail) pipe.rs = d.tail;
         for (size_t g = glo; g < ghi; g += chunk_groups) {
             size_t ge = std::min(ghi, g + chunk_groups);
             size_t c = g * group, e = std::min(n, ge * group), m = e - c;
@@ -1368,7 +1411,8 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
             if (int rc = pipe.h2d(dpk, pks + c * rpk, m * rpk)) return rc;
             if (int rc = pipe.h2d(dsig, sigs + c * rsig, m * rsig)) return rc;
             if (int rc = pipe.inputs_ready()) return rc;
-            if (int rc = dev_verify_rand(d, variant, dpk, dm, dof, base, dsig, m, group, dseed, (uint64_t)c, rand_bits, ddst, dlen, flags, dok))
+            if (int rc = dev_verify_rand(d, variant, dpk, dm, dof, base, dsig, m, group, dseed, (uint64_t)c, rand_bits, ddst, dlen, flags, dok,
+                                         overlap_tail ? pipe.set() : -1))
                 return rc;
             if (int rc = pipe.d2h(ok_groups + g, pin_ok, dok, ge - g)) return rc;
             if (int rc = pipe.end()) return rc;

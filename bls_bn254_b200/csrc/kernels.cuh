@@ -698,6 +698,15 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_fp12_mul_into(f
     fp12_mul(a, a, b);
     copy_rec(A[i], a);
 }
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_fp12_mul_out(fp12 *T, const fp12 *A, const fp12 *B, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 a, b;
+    copy_rec(a, A[i]);
+    copy_rec(b, B[i]);
+    fp12_mul(a, a, b);
+    copy_rec(T[i], a);
+}
 // gbad[i / group] |= any undecodable input of tuple i
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_rbv_group_flags(int *gbad, const uint8_t *fa, const uint8_t *fb, const uint8_t *fc, size_t group, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
