@@ -28,7 +28,7 @@ class Bn254Error(Exception):
 
     def __init__(self, code, msg=""):
         self.code = code
-        kind = self.NAMES.get(code, "NcclError" if code <= -200 else "CudaError")
+        kind = self.NAMES.get(code, "NcclError" if code <= -2000 else "CudaError")
         super().__init__("%s (%d)%s" % (kind, code, (": " + msg) if msg else ""))
 
 
@@ -252,6 +252,21 @@ class Context:
         ok = C.create_string_buffer(n)
         self._ck(self._L.bn254_verify_batch(self._h, variant, _ptr(pks), _ptr(blob), _ptr(off), _ptr(sigs), n, _ptr(dst), len(dst), flags, _ptr(ok)))
         return ok.raw
+
+    def fast_aggregate_verify_batch(self, variant, pks, key_counts, msgs, agg_sigs, dst, flags=0):
+        """FastAggregateVerify for many groups: group g = the next key_counts[g] public keys of `pks`, message g, aggregate
+        signature g.  One accept byte per group."""
+        blob, off, n = _msgs(msgs)
+        rpk, rsig = self._recs(variant)
+        if len(key_counts) != n or len(agg_sigs) != rsig * n or len(pks) != rpk * sum(key_counts):
+            raise Bn254Error(-10, "one key count and one aggregate signature per message; pks must hold sum(key_counts) keys")
+        koff = (C.c_uint64 * (n + 1))()
+        for i, k in enumerate(key_counts):
+            koff[i + 1] = koff[i] + k
+        ok = C.create_string_buffer(max(1, n))
+        self._ck(self._L.bn254_fast_aggregate_verify_batch(self._h, variant, _ptr(pks), _ptr(koff), _ptr(blob), _ptr(off), _ptr(agg_sigs), n, _ptr(dst),
+                                                           len(dst), flags, _ptr(ok)))
+        return ok.raw[:n]
 
     def g2_prepare(self, pks, flags=0):
         """G2Prepared::from for n min-sig public keys (n x 128 bytes): prepare once, verify many (verify_batch_prepared).

@@ -173,6 +173,14 @@ int prof_end(Dev &d) {
     CK(d, cudaEventRecord(d.recs.back().e1, d.cur));
     return 0;
 }
+// the launch itself failed, or an earlier asynchronous fault surfaced here: say which launch reported it
+int launch_check(Dev &d, const char *kernel) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    d.err = std::string("at the launch of ") + kernel + " (asynchronous errors of earlier kernels surface here too): " + cudaGetErrorString(e);
+    d.rc = BN254_ERR_CUDA_BASE - (int)e;
+    return d.rc;
+}
 #define LAUNCH(d, kern, n, tpb, ...)                                             \
     do {                                                                         \
         if ((n) > 0) {                                                           \
@@ -180,7 +188,7 @@ int prof_end(Dev &d) {
             kern<<<blocks((n), (tpb)), (tpb), 0, (d).cur>>>(__VA_ARGS__);         \
             (d).launches++;                                                      \
             if (int rcp_ = prof_end(d)) return rcp_;                             \
-            CK(d, cudaGetLastError());                                           \
+            if (int rcl_ = launch_check(d, BN_STR(kern))) return rcl_;           \
         }                                                                        \
     } while (0)
 
@@ -206,7 +214,7 @@ int prof_end(Dev &d) {
             kern<<<blocks(2 * (size_t)(n), BN_VM_TPB), BN_VM_TPB, BN_VM_SMEM(nslot), (d).cur>>>(__VA_ARGS__); \
             (d).launches++;                                                                                 \
             if (int rcp_ = prof_end(d)) return rcp_;                                                        \
-            CK(d, cudaGetLastError());                                                                      \
+            if (int rcl_ = launch_check(d, BN_STR(kern))) return rcl_;                                      \
         }                                                                                                   \
     } while (0)
 
@@ -384,6 +392,7 @@ struct VerifyBufs {
     fp12 *F; uint8_t *flf; g1m *P0, *P1; g2m *Q0, *Q1; uint8_t *flp0, *flp1, *flq0, *flq1;
     const g1m *ng1; const uint8_t *flc;
 };
+// pks == nullptr: the public keys are already decoded and validated in b.Q1 / b.flq1 (min-sig) or b.P1 / b.flp1 (min-pk)
 int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                      const uint8_t *sigs, size_t lo, size_t hi, const uint8_t *dst, uint32_t dst_len, int check, uint8_t *ok) {
     size_t n = hi - lo;
@@ -391,15 +400,17 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
     check = (check & 1) | DEC_NO_IDENTITY;   // an identity key or signature never verifies (items.cuh: DEC_NO_IDENTITY)
     if (variant == BN254_MIN_SIG) {
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P0 + lo, b.flp0 + lo, sigs + 64 * lo, n, check);
-        LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
-        if (subgroup) {
-            LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
+        if (pks) {
+            LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
+            if (subgroup) {
+                LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
+            }
         }
         if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         if (int rc = launch_miller2_fixed(d, n, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo, b.flq1 + lo)) return rc;
     } else {
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q0 + lo, b.flq0 + lo, sigs + 128 * lo, n, check);
-        LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
+        if (pks) LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
         if (subgroup) {
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq0 + lo, b.Q0 + lo, n);
         }
@@ -469,6 +480,33 @@ int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, cons
     if (int rc = launch_final_exp(d, F, n)) return rc;
     LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok, F, flf, n);
     return 0;
+}
+
+// FastAggregateVerify for G groups (device pointers): decode + validate all keys, the aggregate key of every group (one thread per
+// group), then the ordinary verification pipeline on (aggregate key, message, aggregate signature) with the keys pre-decoded
+int dev_fast_aggregate(Dev &d, int variant, const uint8_t *pks, size_t nkeys, const uint64_t *koff, uint64_t kbase, const uint8_t *msgs,
+                       const uint64_t *off, uint64_t base, const uint8_t *sigs, size_t G, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+    const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
+    const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
+    uint8_t *flk, *flsum;
+    if (int rc = ensure_t(d, S_FLTMP, nkeys + 1, &flk)) return rc;
+    if (variant == BN254_MIN_SIG) {
+        g2m *K, *Q1;
+        if (int rc = ensure_t(d, S_TMP, (nkeys + 1) * sizeof(g2m), (uint8_t **)&K)) return rc;
+        if (int rc = ensure_t(d, S_Q1, G, &Q1)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, G, &flsum)) return rc;
+        LAUNCH(d, k_g2_decode, nkeys, BN_TPB_LIGHT, K, flk, pks, nkeys, check);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, nkeys, BN_TPB_HEAVY, flk, K, nkeys);
+        LAUNCH(d, k_g2_seg_sum_var, G, BN_TPB_HEAVY, Q1, flsum, K, flk, koff, kbase, G);
+    } else {
+        g1m *K, *P1;
+        if (int rc = ensure_t(d, S_TMP, (nkeys + 1) * sizeof(g1m), (uint8_t **)&K)) return rc;
+        if (int rc = ensure_t(d, S_P1, G, &P1)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, G, &flsum)) return rc;
+        LAUNCH(d, k_g1_decode, nkeys, BN_TPB_LIGHT, K, flk, pks, nkeys, check);
+        LAUNCH(d, k_g1_seg_sum_var, G, BN_TPB_HEAVY, P1, flsum, K, flk, koff, kbase, G);
+    }
+    return dev_verify(d, variant, nullptr, msgs, off, base, sigs, G, dst, dst_len, flags, ok);
 }
 
 // ---- randomised batch verification ----------------------------------------------
@@ -1416,6 +1454,49 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
                 return rc;
             if (int rc = pipe.d2h(ok_groups + g, pin_ok, dok, ge - g)) return rc;
             if (int rc = pipe.end()) return rc;
+        }
+        return pipe.finish();
+    });
+}
+
+// FastAggregateVerify of the IETF BLS draft for G groups: group g = the public keys [key_offsets[g], key_offsets[g+1]) of `pks`,
+// message g, aggregate signature g.  Groups (with their keys) are what the devices share out and what the chunk pipeline streams.
+int bn254_fast_aggregate_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets, const uint8_t *msgs,
+                                      const uint64_t *offsets, const uint8_t *agg_sigs, size_t n_groups, const uint8_t *dst, size_t dst_len,
+                                      uint32_t flags, uint8_t *ok) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (n_groups == 0) return 0;
+    if (!key_offsets || !offsets || !agg_sigs || !ok || (key_offsets[n_groups] && !pks)) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, offsets, n_groups)) return rc;
+    if (int rc = check_offsets(ctx, key_offsets, n_groups)) return rc;
+    const size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
+    const bool pin_ok = host_ptr_is_pinned(ok);
+    const size_t max_keys = ctx->chunk;     // keys staged per round; a single bigger group still goes through alone
+    return run_sharded(ctx, n_groups, [=](Dev &d, size_t lo, size_t hi) -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        Pipe pipe(d);
+        for (size_t c = lo; c < hi;) {
+            size_t e = c + 1;
+            while (e < hi && e - c < ctx->verify_chunk(d) && key_offsets[e + 1] - key_offsets[c] <= max_keys) e++;
+            const size_t m = e - c, nk = (size_t)(key_offsets[e] - key_offsets[c]);
+            if (int rc = pipe.begin(pin_ok ? 0 : pad64(m))) return rc;
+            const uint8_t *dm; const uint64_t *dof; uint64_t base;
+            if (int rc = stage_msgs(d, &pipe, msgs, offsets, c, e, &dm, &dof, &base)) return rc;
+            uint8_t *dpk, *dsig, *dok; uint64_t *dko;
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), nk * rpk + 16, &dpk)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rsig, &dsig)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_C, pipe.set()), m + 1, &dko)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m, &dok)) return rc;
+            if (int rc = pipe.h2d(dpk, pks + (size_t)key_offsets[c] * rpk, nk * rpk)) return rc;
+            if (int rc = pipe.h2d(dsig, agg_sigs + c * rsig, m * rsig)) return rc;
+            if (int rc = pipe.h2d(dko, key_offsets + c, (m + 1) * sizeof(uint64_t))) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
+            if (int rc = dev_fast_aggregate(d, variant, dpk, nk, dko, key_offsets[c], dm, dof, base, dsig, m, ddst, dlen, flags, dok)) return rc;
+            if (int rc = pipe.d2h(ok + c, pin_ok, dok, m)) return rc;
+            if (int rc = pipe.end()) return rc;
+            c = e;
         }
         return pipe.finish();
     });

@@ -543,6 +543,40 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_sum(g2m *out
     if (t < m) sum_strided<F2, g2m>(out, flo, in, fl, n, m, t);
 }
 
+// FastAggregateVerify: the aggregate public key of every group, one thread per group (committees of 10^2..10^3 keys, many
+// groups).  out[g] = sum of in[koff[g] .. koff[g+1]); the flag is FL_BAD for an empty set, an unusable member or an identity sum.
+template <class F, class M>
+__device__ void seg_sum_var(M *out, uint8_t *flo, const M *in, const uint8_t *fl, const uint64_t *koff, uint64_t kbase, size_t g) {
+    point<F> acc, x;
+    pt_set_identity(acc);
+    const uint64_t lo = koff[g] - kbase, hi = koff[g + 1] - kbase;
+    uint8_t bad = hi > lo ? 0 : FL_BAD;
+#pragma unroll 1
+    for (uint64_t j = lo; j < hi; j++) {
+        M p;
+        copy_rec(p, in[j]);
+        const uint8_t f = fl[j];
+        bad |= (f & (FL_BAD | FL_INF)) ? FL_BAD : 0;
+        pt_from_affine(x, p.x, p.y, (f & FL_INF) != 0);
+        pt_add(acc, acc, x);
+    }
+    M r;
+    bool inf;
+    pt_to_affine(r.x, r.y, inf, acc);
+    copy_rec(out[g], r);
+    flo[g] = (bad || inf) ? FL_BAD : 0;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g1_seg_sum_var(g1m *out, uint8_t *flo, const g1m *in, const uint8_t *fl, const uint64_t *koff,
+                                                                  uint64_t kbase, size_t G) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) seg_sum_var<F1, g1m>(out, flo, in, fl, koff, kbase, g);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_seg_sum_var(g2m *out, uint8_t *flo, const g2m *in, const uint8_t *fl, const uint64_t *koff,
+                                                                  uint64_t kbase, size_t G) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) seg_sum_var<F2, g2m>(out, flo, in, fl, koff, kbase, g);
+}
+
 // ---- randomised batch verification (items.cuh: rbv_*) -----------------------------------------------
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_rbv_scale_g1(g1m *A, uint8_t *fl, const uint8_t *seed, uint64_t base, int nbits, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

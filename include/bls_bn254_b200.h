@@ -13,8 +13,9 @@
  *
  * Return value: 0 on success; -1..-4 = Bn254Error::{InvalidScalarBytes, InvalidG1Bytes,
  * InvalidG2Bytes, InvalidGtBytes} (error.rs:5-10) for malformed call-level input; -10 bad argument;
- * -20 no usable CUDA device (there is NO CPU fallback); -100-k = CUDA error k; -200-k = NCCL error k
- * (-200 itself: libnccl could not be loaded / no communicator).  Per-item problems
+ * -20 no usable CUDA device (there is NO CPU fallback); -100-k = CUDA error k (k < 1000); -2000-k = NCCL error k
+ * (-2000 itself: libnccl could not be loaded / no communicator; SURVEY.md 8(b) proposed -200-k, which collides with CUDA error
+ * numbers above 100, e.g. 700 "illegal address").  Per-item problems
  * (undecodable point, SvdW exception where the reference panics: fp.rs:325, fp2.rs:255) never abort
  * a batch: the item's status byte is 0 and its output is all zero bytes (ok[i] = 0 for verify).
  *
@@ -55,7 +56,7 @@ typedef struct bn254_ctx bn254_ctx;
 #define BN254_ERR_ARG (-10)
 #define BN254_ERR_NO_DEVICE (-20)
 #define BN254_ERR_CUDA_BASE (-100)
-#define BN254_ERR_NCCL_BASE (-200)
+#define BN254_ERR_NCCL_BASE (-2000)
 
 #define BN254_MIN_SIG 0 /* pk in G2 (128 B), sig in G1 (64 B), messages hashed to G1 */
 #define BN254_MIN_PK 1  /* pk in G1 (64 B), sig in G2 (128 B), messages hashed to G2 */
@@ -138,6 +139,14 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
                                   const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags,
                                   const uint8_t *seed /* 32 B */, int rand_bits, size_t group,
                                   uint8_t *ok_groups /* ceil(n/group) bytes 0/1 */);
+/* FastAggregateVerify of the IETF BLS draft (many signers, ONE message per group), n_groups groups at once: group g = the public
+ * keys [key_offsets[g], key_offsets[g+1]) of `pks`, message g, aggregate signature g:
+ *     min-sig: e(aggsig_g, -g2) * e(H_G1(m_g), sum pk) == 1          min-pk: e(-g1, aggsig_g) * e(sum pk, H_G2(m_g)) == 1
+ * The aggregate key of every group is summed on the GPU; then one ordinary verification per GROUP.  A group with no key, with an
+ * undecodable / identity / (per flags) invalid key, or whose keys sum to the identity is rejected. */
+int bn254_fast_aggregate_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets /* n_groups+1 */,
+                                      const uint8_t *msgs, const uint64_t *offsets, const uint8_t *agg_sigs, size_t n_groups,
+                                      const uint8_t *dst, size_t dst_len, uint32_t flags, uint8_t *ok /* n_groups bytes 0/1 */);
 /* ---- prepared public keys: G2Prepared (pairings.rs:609-660, 725-757) for min-sig keys.  bn254_g2_prepare computes the 88 line
  * triples of every key once (16 896 bytes per key, resident on every device of the ctx; `flags` = the validation applied to the
  * keys: on-curve / subgroup; identity and undecodable keys are remembered as unusable).  bn254_verify_batch_prepared verifies

@@ -177,6 +177,17 @@ def g1_sum(pts):
     return out.raw
 
 
+def fast_aggregate_verify_batch(variant, pks, key_counts, msgs, sigs, dst, flags=0):
+    """one accept byte per group: group g = the next key_counts[g] public keys, message g, aggregate signature g"""
+    blob, off = pack_msgs(msgs)
+    koff = (C.c_uint64 * (len(key_counts) + 1))()
+    for i, k in enumerate(key_counts):
+        koff[i + 1] = koff[i] + k
+    ok = _buf(max(1, len(msgs)))
+    lib().orc_fast_aggregate_verify_batch(variant, pks, koff, blob, off, sigs, C.c_size_t(len(msgs)), dst, C.c_size_t(len(dst)), C.c_uint32(flags), ok)
+    return ok.raw[:len(msgs)]
+
+
 def g2_sum(pts):
     out = _buf(128)
     assert lib().orc_g2_sum(pts, C.c_size_t(len(pts) // 128), out) == 0

@@ -24,7 +24,7 @@ impl Bn254Error {
             -4 => Self::InvalidGtBytes,
             -10 => Self::BadArgument(msg),
             -20 => Self::NoDevice,
-            rc if rc <= -200 => Self::Nccl(-200 - rc, msg),
+            rc if rc <= -2000 => Self::Nccl(-2000 - rc, msg),
             rc => Self::Cuda(-100 - rc, msg),
         }
     }

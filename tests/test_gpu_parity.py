@@ -777,3 +777,44 @@ def test_verify_with_prepared_keys(ctx, orc, B, shape):
         ctx.verify_batch_prepared(prep, [6] + kidx[1:], msgs, sigs, B.DST_MIN_SIG)      # key index out of range
     assert ctx.verify_batch_prepared(prep, [], [], b"", B.DST_MIN_SIG) == b""
     prep.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fast_aggregate_verify_batch(ctx, orc, B, variant):
+    """bn254_fast_aggregate_verify_batch (FastAggregateVerify of the IETF draft: many signers, one message per group): verdicts
+    equal the oracle's -- valid committees accept; an empty key set, an identity key, an undecodable key, a missing signer, a
+    tampered message and two keys that cancel reject."""
+    rng = random.Random(61 + variant)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    sizes = [1, 3, 17, 0, 5, 4, 64, 2, 6, 2]
+    G = len(sizes)
+    msgs = [rng.randbytes(rng.choice((0, 7, 32, 100))) for _ in range(G)]
+    R = B.R_ORDER
+    keys, sigs = b"", b""
+    ident_pk = (bytes(64) + bytes(63) + b"\x01") if variant == 0 else ((0).to_bytes(32, "big") + (1).to_bytes(32, "big"))
+    ident_sig = ((0).to_bytes(32, "big") + (1).to_bytes(32, "big")) if variant == 0 else (bytes(64) + bytes(63) + b"\x01")
+    for g, k in enumerate(sizes):
+        sks = [B.scheme.SecretKey(rng.randrange(1, R)) for _ in range(k)]
+        if g == 9:      # two keys that cancel: the aggregate key is the identity
+            sks[1] = B.scheme.SecretKey(R - sks[0].value)
+        pk = bytearray(B.scheme.public_keys(ctx, sks, variant)) if k else bytearray()
+        if k:
+            per = B.scheme.sign(ctx, sks, [msgs[g]] * k, variant)
+            agg = B.scheme.aggregate(ctx, per, variant)
+        else:
+            agg = ident_sig
+        if g == 4:
+            pk[rpk * 2:rpk * 3] = ident_pk          # an identity key inside the committee
+        if g == 5:
+            pk[rpk:2 * rpk] = b"\xff" * rpk          # an undecodable key
+        if g == 7:      # one signer missing from the aggregate
+            agg = B.scheme.sign(ctx, sks[:1], [msgs[g]], variant)
+        keys += bytes(pk)
+        sigs += agg
+    msgs[8] = msgs[8] + b"!"                         # tampered message
+    for flags in (0, 3):
+        got = ctx.fast_aggregate_verify_batch(variant, keys, sizes, msgs, sigs, dst, flags=flags)
+        assert got == orc.fast_aggregate_verify_batch(variant, keys, sizes, msgs, sigs, dst, flags=flags), flags
+        assert got == bytes([1, 1, 1, 0, 0, 0, 1, 0, 0, 0])
+    assert ctx.fast_aggregate_verify_batch(variant, b"", [], [], b"", dst) == b""
