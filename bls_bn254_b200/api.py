@@ -144,7 +144,8 @@ class Context:
         self._ck(self._L.bn254_sync(self._h))
 
     def set_option(self, name, value):
-        """"lanes" (0 per launch / 1 one thread per pairing / 2 lane pair), "chunk", "split": include/bls_bn254_b200.h"""
+        """"lanes" (0 per launch / 1 one thread per pairing / 2 lane pair / 3 slot machine / 4 wide slot machine), "wide_max", "chunk", "split":
+        include/bls_bn254_b200.h"""
         self._ck(self._L.bn254_ctx_set_option(self._h, name.encode(), int(value)))
 
     # ---- NCCL communicator of a one-process-per-GPU job (the aggregate path's single exchange) -----------------

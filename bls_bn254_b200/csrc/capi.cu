@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -84,6 +85,11 @@ struct Dev {
     // pairing, 2 = two lanes per pairing.  BN254_LANES / bn254_ctx_set_option("lanes") force a shape so that the parity
     // suite meets BOTH shapes at every size (the big-batch shape is what a 2^24-tuple job runs).
     int shape = 0;
+    // 3 = the slot machine, 4 = the WIDE slot machine (one warp per item: the latency shape).  In shape 0 a launch of at most
+    // wide_max items uses the wide kernels ("wide_max" option / BN254_WIDE_MAX; 0 = never).  Default: about ten warps per SM,
+    // below which a warp per item beats a lane pair per item (measured per verification batch: 512 items 5.7 against 8.8 ms,
+    // 1536 items 7.8 against 8.9 ms, 2048 items 10.8 against 9.0 ms).
+    size_t wide_max = 1536;
     // Chunk pipeline of the host-buffer entry points: copies run on `cp`, kernels on `st`; two staging sets.
     cudaStream_t cp = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_out[2] = {};
@@ -218,9 +224,47 @@ int launch_check(Dev &d, const char *kernel) {
         }                                                                                                   \
     } while (0)
 
+// The wide slot machine (d.shape == 4, or automatically for n <= d.wide_max): one WARP per item (vm.cuh: run on WSlots).
+#define LAUNCH_W(d, kern, r_lo, r_hi, n, ...)                                                      \
+    do {                                                                                           \
+        if ((n) > 0) {                                                                             \
+            const size_t smem_ = wide_smem(vm::r_lo, vm::r_hi);                                    \
+            static std::atomic<unsigned> attr_set_{0};   /* per kernel and device: opt in to > 48 KB of shared memory */ \
+            if (!((attr_set_.load() >> (d).id) & 1u)) {                                            \
+                CK(d, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+                attr_set_.fetch_or(1u << (d).id);                                                  \
+            }                                                                                      \
+            if (int rcp_ = prof_begin(d, BN_STR(kern), (size_t)(n))) return rcp_;                  \
+            kern<<<blocks((n), BN_W_WARPS), 32 * BN_W_WARPS, smem_, (d).cur>>>(__VA_ARGS__);       \
+            (d).launches++;                                                                        \
+            if (int rcp_ = prof_end(d)) return rcp_;                                               \
+            if (int rcl_ = launch_check(d, BN_STR(kern))) return rcl_;                             \
+        }                                                                                          \
+    } while (0)
+// shared memory of a wide-machine CTA running routines [r_lo, r_hi] (host copy of the generated tables)
+inline size_t wide_smem(int r_lo, int r_hi) {
+    static uint16_t dir[vm::R_COUNT][2];
+    static std::vector<uint16_t> boff;
+    static bool have = false;
+    if (!have) {
+        cudaMemcpyFromSymbol(dir, vm::W_DIR, sizeof dir);
+        boff.resize(sizeof(vm::W_BOFF) / 2);
+        cudaMemcpyFromSymbol(boff.data(), vm::W_BOFF, sizeof(vm::W_BOFF));
+        have = true;
+    }
+    const int i_lo = boff[dir[r_lo][0]], i_hi = boff[dir[r_hi][0] + dir[r_hi][1]];
+    return vm::wide_smem_bytes(r_lo, r_hi, BN_W_WARPS, i_lo, i_hi);
+}
+inline bool use_wide(const Dev &d, size_t n) { return d.shape == 4 || (d.shape == 0 && n <= d.wide_max); }
+
 // ---- the pairing kernels behind one call each: the shape (one thread / lane pair / slot machine) is picked here -----------
 int launch_miller2_fixed(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0, const uint8_t *flp0, const g1m *P1, const uint8_t *flp1,
                          const g2m *Q1, const uint8_t *flq1) {
+    if (use_wide(d, n)) {
+        LAUNCH_W(d, k_w_miller2_fixed, R_M2F_INIT, R_M2F_FROB, n, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
+        LAUNCH(d, k_vm_fixup_miller2_fixed, n, BN_TPB_HEAVY, F, P0, flp0, P1, flp1, Q1, flq1, n);
+        return 0;
+    }
     if (d.shape == 3) {
         LAUNCH_VM(d, k_vm_miller2_fixed, n, vm::NSLOT_M1, F, flf, P0, flp0, P1, flp1, Q1, flq1, n);
         LAUNCH(d, k_vm_fixup_miller2_fixed, n, BN_TPB_HEAVY, F, P0, flp0, P1, flp1, Q1, flq1, n);
@@ -231,6 +275,11 @@ int launch_miller2_fixed(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0,
 }
 int launch_miller2(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0, const uint8_t *flp0, size_t p0_stride, const g2m *Q0, const uint8_t *flq0,
                    const g1m *P1, const uint8_t *flp1, const g2m *Q1, const uint8_t *flq1) {
+    if (use_wide(d, n)) {
+        LAUNCH_W(d, k_w_miller2, R_M2V_INIT, R_M2V_FROB, n, F, flf, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1);
+        LAUNCH(d, k_vm_fixup_miller2, n, BN_TPB_HEAVY, F, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1, n);
+        return 0;
+    }
     if (d.shape == 3) {
         LAUNCH_VM(d, k_vm_miller2, n, vm::NSLOT_M2V, F, flf, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1);
         LAUNCH(d, k_vm_fixup_miller2, n, BN_TPB_HEAVY, F, P0, flp0, p0_stride, Q0, flq0, P1, flp1, Q1, flq1, n, (size_t)1, n);
@@ -240,6 +289,10 @@ int launch_miller2(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P0, const
     return 0;
 }
 int launch_miller1(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P, const uint8_t *flp, const g2m *Q, const uint8_t *flq, int *bad) {
+    if (use_wide(d, n)) {
+        LAUNCH_W(d, k_w_miller1, R_M2F_INIT, R_M1_FROB, n, F, flf, P, flp, Q, flq, n, bad);
+        return 0;
+    }
     if (d.shape == 3) {
         LAUNCH_VM(d, k_vm_miller1, n, vm::NSLOT_M1, F, flf, P, flp, Q, flq, n, bad);
         return 0;
@@ -250,6 +303,13 @@ int launch_miller1(Dev &d, size_t n, fp12 *F, uint8_t *flf, const g1m *P, const 
 // F[t] = ML(P[2t], Q[2t]) * ML(P[2t+1], Q[2t+1]) for t < ceil(ntuples / 2)
 int launch_miller_twin(Dev &d, size_t ntuples, fp12 *F, const g1m *P, const uint8_t *flp, const g2m *Q, const uint8_t *flq, int *bad) {
     const size_t half = (ntuples + 1) / 2;
+    if (use_wide(d, half)) {
+        LAUNCH_W(d, k_w_miller2, R_M2V_INIT, R_M2V_FROB, half, F, (uint8_t *)nullptr, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2);
+        LAUNCH(d, k_vm_fixup_miller2, half, BN_TPB_HEAVY, F, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2, ntuples);
+        if (bad) LAUNCH(d, k_or_flags, ntuples, BN_TPB_LIGHT, bad, flp, ntuples);
+        if (bad) LAUNCH(d, k_or_flags, ntuples, BN_TPB_LIGHT, bad, flq, ntuples);
+        return 0;
+    }
     if (d.shape == 3) {
         LAUNCH_VM(d, k_vm_miller2, half, vm::NSLOT_M2V, F, (uint8_t *)nullptr, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2);
         LAUNCH(d, k_vm_fixup_miller2, half, BN_TPB_HEAVY, F, P, flp, (size_t)1, Q, flq, P + 1, flp + 1, Q + 1, flq + 1, half, (size_t)2, ntuples);
@@ -261,6 +321,10 @@ int launch_miller_twin(Dev &d, size_t ntuples, fp12 *F, const g1m *P, const uint
     return 0;
 }
 int launch_final_exp(Dev &d, fp12 *F, size_t n) {
+    if (use_wide(d, n)) {
+        LAUNCH_W(d, k_w_final_exp, R_FE_CYCSQR, R_FE_STF, n, F, n);
+        return 0;
+    }
     if (d.shape == 3) {
         fp2 *scratch;
         if (int rc = ensure_t(d, S_VM_SCRATCH, (size_t)vm::FEXP_SCRATCH_FP2 * n, &scratch)) return rc;
@@ -568,6 +632,13 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
     if (int rc = ensure_t(d, S_RB_FLP, nseg, &gflp)) return rc;
     if (int rc = ensure_t(d, S_RB_FLQ, nseg, &gflq)) return rc;
     if (tail_set >= 0 && (d.prof || d.shape == 3 || d.cur != d.st)) tail_set = -1;   // per-kernel timing / shared scratch want it serial
+    // A tail that overlaps the next chunk's kernels is off the critical path: it keeps the throughput shape (the wide machine
+    // buys latency with shared memory and registers the overlapped kernels want).
+    struct WideOff {
+        Dev &d; size_t keep;
+        WideOff(Dev &dd, bool off) : d(dd), keep(dd.wide_max) { if (off) d.wide_max = 0; }
+        ~WideOff() { d.wide_max = keep; }
+    } wide_off(d, tail_set >= 0);
     if (int rc = ensure_t(d, stage_buf(S_RB_BAD, tail_set > 0 ? 1 : 0), nseg, &gbad)) return rc;
     CK(d, cudaMemsetAsync(gbad, 0, nseg * sizeof(int), d.cur));
     // The signature side (scale, per-group sums, one Miller loop per GROUP against the fixed generator) only needs
@@ -774,6 +845,10 @@ int dev_gather_recs(Dev &d, const agg_rec *send, agg_rec **recv) {
     return 0;
 }
 int dev_gather_finish(Dev &d, const agg_rec *recs, uint8_t *ok) {
+    if (use_wide(d, 1)) {
+        LAUNCH_W(d, k_w_gather_finish, R_FE_CYCSQR, R_FE_STF, 1, ok, (fp12 *)nullptr, recs, d.nranks);
+        return 0;
+    }
     LAUNCH(d, k_gather_finish_l2, 32, 32, ok, (fp12 *)nullptr, recs, d.nranks);
     return 0;
 }
@@ -1094,13 +1169,18 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
             ctx->chunk_is_default = false;
         }
     }
-    if (const char *s = getenv("BN254_LANES")) {  // shape of the pairing kernels: 0 per launch, 1 one thread, 2 lane pair
+    if (const char *s = getenv("BN254_LANES")) {  // shape of the pairing kernels: 0 per launch, 1 one thread, 2 lane pair, 3 / 4 slot machines
         long v = atol(s);
-        if (v >= 0 && v <= 3)
+        if (v >= 0 && v <= 4)
             for (auto &d : ctx->devs) d.shape = (int)v;
     }
+    if (const char *s = getenv("BN254_WIDE_MAX")) {
+        long v = atol(s);
+        if (v >= 0)
+            for (auto &d : ctx->devs) d.wide_max = (size_t)v;
+    }
     // Several devices in one process: one NCCL communicator per device for the aggregate path's all-gather.  A box without
-    // libnccl still gets a working ctx for everything that needs no exchange; the aggregate calls then fail with -200.
+    // libnccl still gets a working ctx for everything that needs no exchange; the aggregate calls then fail with -2000.
     if (ctx->devs.size() > 1 && bn_nccl::api().ok()) {
         std::vector<bn_nccl::comm_t> comms(ctx->devs.size());
         std::vector<int> ids;
@@ -1123,15 +1203,17 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
 int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value) {
     if (!ctx || !name) return BN254_ERR_ARG;
     std::string k(name);
-    if (k == "lanes" && value >= 0 && value <= 3) {
+    if (k == "lanes" && value >= 0 && value <= 4) {
         for (auto &d : ctx->devs) d.shape = (int)value;
+    } else if (k == "wide_max" && value >= 0) {
+        for (auto &d : ctx->devs) d.wide_max = (size_t)value;
     } else if (k == "chunk" && value > 0) {
         ctx->chunk = (size_t)value;
         ctx->chunk_is_default = false;
     } else if (k == "split" && value >= 1 && value <= Dev::MAXSUB) {
         for (auto &d : ctx->devs) d.nsub = (int)value;
     } else {
-        return fail_arg(ctx, "unknown option or value out of range (lanes 0..3, chunk > 0, split 1..8)");
+        return fail_arg(ctx, "unknown option or value out of range (lanes 0..4, wide_max >= 0, chunk > 0, split 1..8)");
     }
     return 0;
 }

@@ -399,6 +399,66 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_vm_fixup_miller
     copy_rec(F[i], f);
 }
 
+// ---- the WIDE slot machine (vm.cuh: run on WSlots): one item per WARP, its 16 lane pairs execute up to 16 independent
+//      instructions at a time.  The latency shape: a lone pairing is a ~4 ms dependent chain on one lane pair, a fraction of
+//      that on a warp; used for small batches (bn254 ctx option "lanes" = 4, or automatically below "wide_max" items).
+//      BN_W_WARPS items per CTA, which share one staged copy of the programs (vm.cuh: wide_stage).  Dead pairs: the same
+//      fix-up kernels as the slot machine.
+#ifndef BN_W_WARPS
+#define BN_W_WARPS 4      // items (warps) per CTA: they share one staged copy of the programs
+#endif
+#define BN_W_PROLOGUE(r_lo, r_hi)                                                   \
+    extern __shared__ uint4 vm_smem[];                                              \
+    const vm::WSlots M = vm::wide_stage(vm_smem, (r_lo), (r_hi));                   \
+    const size_t i = (size_t)blockIdx.x * BN_W_WARPS + (threadIdx.x >> 5);          \
+    if (i >= n) return;                                                             \
+    const uint32_t lane = threadIdx.x & 31u;                                        \
+    vm::Env E = {};
+__global__ void __launch_bounds__(32 * BN_W_WARPS) k_w_miller2_fixed(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+                                                                     const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1, size_t n) {
+    BN_W_PROLOGUE(vm::R_M2F_INIT, vm::R_M2F_FROB);
+    vm::wide_set_item(M, &P0[i].x, nullptr, &P1[i].x, &Q1[i].x);
+    vm::miller(M, E, vm::FAM_M2F);
+    vm::store_f12(F[i], M);
+    if (lane == 0) flF[i] = ((flP0[i] | flP1[i] | flQ1[i]) & FL_BAD) ? FL_BAD : 0;
+}
+__global__ void __launch_bounds__(32 * BN_W_WARPS) k_w_miller2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride, const g2m *Q0,
+                                                               const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1, const g2m *Q1, const uint8_t *flQ1,
+                                                               size_t n, size_t step) {
+    BN_W_PROLOGUE(vm::R_M2V_INIT, vm::R_M2V_FROB);
+    const size_t j = i * step;
+    vm::wide_set_item(M, &P0[j * p0_stride].x, &Q0[j].x, &P1[j].x, &Q1[j].x);
+    vm::miller(M, E, vm::FAM_M2V);
+    vm::store_f12(F[i], M);
+    if (flF && lane == 0) flF[i] = ((flP0[j * p0_stride] | flQ0[j] | flP1[j] | flQ1[j]) & FL_BAD) ? FL_BAD : 0;
+}
+__global__ void __launch_bounds__(32 * BN_W_WARPS) k_w_miller1(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
+                                                               size_t n, int *bad) {
+    BN_W_PROLOGUE(vm::R_M2F_INIT, vm::R_M1_FROB);
+    vm::wide_set_item(M, nullptr, nullptr, &P[i].x, &Q[i].x);
+    vm::miller(M, E, vm::FAM_M1);
+    const uint8_t fl = flP[i] | flQ[i];
+    if (fl & FL_INF) {          // an identity input gives the neutral element (pairings.rs:789-800)
+        fp v;
+        fp_set_zero(v);
+        if (lane == 0) v = kfp(k::ONE);
+        if (lane < 12) M.sth((int)(lane >> 1), (int)(lane & 1u), v);
+        vm::wide_sync();
+    }
+    vm::store_f12(F[i], M);
+    if (lane == 0) {
+        if (flF) flF[i] = (fl & FL_BAD) ? FL_BAD : 0;
+        if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
+    }
+}
+__global__ void __launch_bounds__(32 * BN_W_WARPS) k_w_final_exp(fp12 *F, size_t n) {
+    BN_W_PROLOGUE(vm::R_FE_CYCSQR, vm::R_FE_STF);
+    (void)lane;
+    vm::load_f12(M, F[i]);
+    vm::final_exp(M, E);
+    vm::store_f12(F[i], M);
+}
+
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_fp12_encode(uint8_t *out, uint8_t *status, const fp12 *F, const uint8_t *fl, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -480,6 +540,29 @@ __global__ void __launch_bounds__(32) k_gather_finish_l2(uint8_t *ok, fp12 *gt, 
     bool one = fp12_is_one(acc);
     if (gt) fp12_store(*gt, acc);
     if (threadIdx.x == 0) ok[0] = (one && !bad) ? 1 : 0;
+}
+// the same on the wide slot machine (one warp, 16 units): the single final exponentiation is a latency-bound chain, ~1.8 ms
+// here against ~3.2 ms on one lane pair
+__global__ void __launch_bounds__(32 * BN_W_WARPS) k_w_gather_finish(uint8_t *ok, fp12 *gt, const agg_rec *recs, int k) {
+    const size_t n = 1;
+    BN_W_PROLOGUE(vm::R_FE_CYCSQR, vm::R_FE_STF);
+    uint32_t bad = recs[0].bad;
+    vm::load_f12(M, recs[0].f);
+#pragma unroll 1
+    for (int j = 1; j < k; j++) {
+        bad |= recs[j].bad;
+        vm::load_f12(M, recs[j].f, 6);       // register G
+        vm::run(M, E, vm::R_FE_MUL);
+    }
+    vm::final_exp(M, E);
+    bool mine = true;
+    if (lane < 12) {
+        const fp v = M.ldh((int)(lane >> 1), (int)(lane & 1u));
+        mine = lane == 0 ? fp_eq(v, kfp(k::ONE)) : fp_is_zero(v);
+    }
+    const bool one = __all_sync(0xffffffffu, mine);
+    if (gt) vm::store_f12(*gt, M);
+    if (lane == 0) ok[0] = (one && !bad) ? 1 : 0;
 }
 // product of the gathered partials only (bn254_aggregate_partial on a multi-device ctx): out = prod recs[i].f, *bad |= any flag
 __global__ void __launch_bounds__(32) k_gather_product_l2(fp12 *out, int *bad, const agg_rec *recs, int k) {

@@ -246,11 +246,286 @@ BN_NOINL void run(const Slots M, const Env E, int routine) {
     }
 }
 
+// ---- the WIDE machine: one item per warp, 16 units (lane pairs), bundles of independent instructions ------------------------
+// Programs: vmw_prog.cuh (tools/gen_vm_programs.py, "the WIDE machine").  Every unit of the warp takes instruction `unit` of
+// the bundle (units beyond the bundle's size idle), reads its operands from the item's slots, the warp synchronises, the
+// unit computes and stores, the warp synchronises.  Units run different opcodes, so the warp diverges inside a bundle and
+// the pair exchanges name only the two lanes of the unit.  A slot is 64 bytes: [c0 | c1].  Slot ids: 0..11 the Fp12
+// registers / twist points as in the sequential machine, W_SC + i the item's Fp scalars (c0 half), W_IN + i its Fp2 inputs,
+// W_VAR + 6 v + i the scratch variables of the final exponentiation, W_TMP.. temporaries, W_CONST + c = constant c (read
+// from constant memory, never written).
+#if defined(__CUDACC__)
+#define BN_GDECL __device__ __align__(16) const
+#else
+#define BN_GDECL alignas(16) static const
+#endif
+}  // namespace vm
+}  // namespace bn
+#include "vmw_prog.cuh"
+namespace bn {
+namespace vm {
+
+#if defined(__CUDACC__)
+// The CTA's shared memory: [W_DIR | W_BOFF | the instructions of the routines the kernel runs | one slot array per warp].
+// Programs are staged there once per CTA (wide_stage): fetched from global memory, the three dependent loads per bundle
+// (bundle offsets, instruction, operands) cost ~3000 cycles -- more than the arithmetic.
+constexpr int W_DIR_BYTES = ((R_COUNT * 4 + 15) / 16) * 16;
+constexpr int W_BOFF_BYTES = (((int)(sizeof(W_BOFF)) + 15) / 16) * 16;
+struct WSlots {
+    uint32_t base;      // shared-space address of the item's slot array
+    uint32_t prog;      // shared-space address instruction i lives at prog + 32 i (the staged range starts at its first instruction)
+    uint32_t tabs;      // shared-space address of the directory copy; the bundle offsets follow it
+    __device__ __forceinline__ fp ldh(int s, int half) const {
+        fp r;
+        const uint32_t a = base + (uint32_t)s * 64u + (uint32_t)half * 32u;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(a) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(a + 16u) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ void sth(int s, int half, const fp &v) const {
+        const uint32_t a = base + (uint32_t)s * 64u + (uint32_t)half * 32u;
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.v[0]), "r"(v.v[1]), "r"(v.v[2]), "r"(v.v[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16u), "r"(v.v[4]), "r"(v.v[5]), "r"(v.v[6]), "r"(v.v[7]) : "memory");
+    }
+    __device__ __forceinline__ int dir(int routine, int k) const {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tabs + 4u * (uint32_t)routine + 2u * (uint32_t)k));
+        return (int)v;
+    }
+    __device__ __forceinline__ int boff(int b) const {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tabs + (uint32_t)W_DIR_BYTES + 2u * (uint32_t)b));
+        return (int)v;
+    }
+    __device__ __forceinline__ void ins(int i, uint32_t (&w)[8]) const {
+        const uint32_t a = prog + 32u * (uint32_t)i;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(a + 16u));
+    }
+};
+// bytes of shared memory a CTA of `warps` items needs to run routines [r_lo, r_hi]
+__host__ __device__ inline size_t wide_smem_bytes(int r_lo, int r_hi, int warps, int i_lo, int i_hi) {
+    (void)r_lo; (void)r_hi;
+    return (size_t)W_DIR_BYTES + W_BOFF_BYTES + (size_t)(i_hi - i_lo) * 32 + (size_t)warps * W_NSLOT * 64;
+}
+// All threads of the CTA: copy the tables and the instructions of routines [r_lo, r_hi] into shared memory, barrier, and
+// return this warp's machine.
+__device__ __forceinline__ WSlots wide_stage(void *smem, int r_lo, int r_hi) {
+    const int i_lo = W_BOFF[W_DIR[r_lo][0]], i_hi = W_BOFF[W_DIR[r_hi][0] + W_DIR[r_hi][1]];
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
+    for (int k = threadIdx.x; k < R_COUNT * 2; k += blockDim.x) tab[k] = W_DIR[k >> 1][k & 1];
+    uint16_t *bo = tab + W_DIR_BYTES / 2;
+    for (int k = threadIdx.x; k < (int)(sizeof(W_BOFF) / 2); k += blockDim.x) bo[k] = W_BOFF[k];
+    uint4 *pr = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem) + W_DIR_BYTES + W_BOFF_BYTES);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&W_PROG[i_lo][0]);
+    for (int k = threadIdx.x; k < 2 * (i_hi - i_lo); k += blockDim.x) pr[k] = src[k];
+    __syncthreads();
+    WSlots m;
+    m.tabs = (uint32_t)__cvta_generic_to_shared(smem);
+    m.prog = m.tabs + (uint32_t)(W_DIR_BYTES + W_BOFF_BYTES) - 32u * (uint32_t)i_lo;
+    m.base = m.tabs + (uint32_t)(W_DIR_BYTES + W_BOFF_BYTES) + 32u * (uint32_t)(i_hi - i_lo) + (threadIdx.x >> 5) * (uint32_t)(W_NSLOT * 64);
+    return m;
+}
+__device__ __forceinline__ int wide_lane() { return (int)(threadIdx.x & 31u); }
+__device__ __forceinline__ void wide_sync() { __syncwarp(); }
+__device__ __forceinline__ void wide_xchg(fp &out, const fp &in) {   // the partner lane's `in`; only the two lanes of the unit take part
+    const uint32_t m = 3u << (threadIdx.x & 30u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.v[i] = __shfl_xor_sync(m, in.v[i], 1);
+}
+#else
+extern "C" int bn_host_lane_id();
+extern "C" void bn_host_warp_sync();
+struct WSlots {            // host build: one array shared by the 32 emulated lanes
+    fp (*a)[2];
+    fp ldh(int s, int half) const { return a[s][half]; }
+    void sth(int s, int half, const fp &v) const { a[s][half] = v; }
+    int dir(int routine, int k) const { return W_DIR[routine][k]; }
+    int boff(int b) const { return W_BOFF[b]; }
+    void ins(int i, uint32_t (&w)[8]) const {
+        for (int k = 0; k < 8; k++) w[k] = W_PROG[i][k];
+    }
+};
+inline int wide_lane() { return bn_host_lane_id(); }
+inline void wide_sync() { bn_host_warp_sync(); }
+inline void wide_xchg(fp &out, const fp &in) { bn_host_lane_xchg(out.v, in.v, 8); }
+#endif
+
+BN_INL fp wide_xi(const fp &v, bool odd) {     // (9 + u) v for this lane's half
+    fp pv, n, t, u, r;
+    wide_xchg(pv, v);
+    fp_neg(n, pv);
+    fp_mul9(t, v);
+    fp_select(u, odd, pv, n);
+    fp_add(r, t, u);
+    return r;
+}
+// descriptor queue of a wide instruction: twelve 16-bit descriptors in six words, consumed from the low end
+struct WDesc {
+    uint32_t w[6];
+    BN_INL uint32_t pop() {
+        const uint32_t d = w[0] & 0xffffu;
+#pragma unroll
+        for (int i = 0; i < 5; i++) w[i] = (w[i] >> 16) | (w[i + 1] << 16);
+        w[5] >>= 16;
+        return d;
+    }
+};
+BN_INL int wide_slot(const Env &E, uint32_t d) {
+    int s = (int)(d & 1023u);
+    if (d & 0x1000u) s += 3 * E.line;
+    if (d & 0x2000u) s += 6 * E.var;
+    return s;
+}
+BN_INL fp wide_load(const WSlots M, const Env &E, uint32_t d, int half) {
+    const int s = wide_slot(E, d);
+    if (s >= W_CONST) return const_half(s - W_CONST, half != 0);
+    return M.ldh(s, half);
+}
+// sum of the next n terms: +- [xi] coef * slot
+BN_INL fp wide_gather(const WSlots M, const Env &E, WDesc &D, int n, bool odd) {
+    fp acc;
+    fp_set_zero(acc);
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const uint32_t d = D.pop();
+        fp v = wide_load(M, E, d, odd ? 1 : 0);
+        if (d & 0x800u) v = wide_xi(v, odd);
+        const int c = (int)(d >> 14);      // coefficient - 1
+        fp t = v;
+        if (c >= 1) fp_dbl(t, v);
+        if (c == 2) fp_add(t, t, v);
+        if (c == 3) fp_dbl(t, t);
+        if (d & 0x400u) fp_sub(acc, acc, t);
+        else fp_add(acc, acc, t);
+    }
+    return acc;
+}
+
+BN_NOINL void run(const WSlots M, const Env E, int routine) {
+    const int lane = wide_lane(), unit = lane >> 1;
+    const bool odd = (lane & 1) != 0;
+    int b = M.dir(routine, 0);
+    const int bend = b + M.dir(routine, 1);
+#pragma unroll 1
+    for (; b < bend; b++) {
+        const int off = M.boff(b), cnt = M.boff(b + 1) - off;
+        const bool active = unit < cnt;
+        fp x, y, q, r;
+        uint32_t w0 = 0;
+        if (active) {
+            uint32_t ins[8];
+            M.ins(off + unit, ins);
+            w0 = ins[0];
+            WDesc D = {{ins[2], ins[3], ins[4], ins[5], ins[6], ins[7]}};
+            const int op = (int)(w0 & 15u);
+            const int nx = (int)((w0 >> 14) & 15u), ny = (int)((w0 >> 18) & 7u), nq = (int)((w0 >> 21) & 3u), nr = (int)((w0 >> 23) & 7u);
+            x = wide_gather(M, E, D, nx, odd);
+            if (op == W_MUL) y = ny ? wide_gather(M, E, D, ny, odd) : x;     // no Y terms: a squaring run as a general product
+            else if (op == W_MULFP) y = wide_load(M, E, D.pop(), 0);     // the Fp scalar: c0 half, the same for both lanes
+            if (nq) q = wide_gather(M, E, D, nq, odd);
+            if (nr) r = wide_gather(M, E, D, nr, odd);
+        }
+        wide_sync();       // every operand of the bundle is in registers: results may now overwrite slots
+        if (active) {
+            const int op = (int)(w0 & 15u);
+            int d = (int)((w0 >> 4) & 1023u);
+            if ((w0 >> 30) & 1u) d += 6 * E.var;
+            const int nq = (int)((w0 >> 21) & 3u), nr = (int)((w0 >> 23) & 7u), dbl = (int)((w0 >> 27) & 3u);
+            const bool xi = (w0 >> 26) & 1u, conjx = (w0 >> 29) & 1u;
+            fp p;
+            if (op == W_LIN) {
+                p = x;
+#pragma unroll 1
+                for (int k = 0; k < dbl; k++) fp_dbl(p, p);
+                if (conjx) {
+                    fp n;
+                    fp_neg(n, p);
+                    fp_select(p, odd, n, p);
+                }
+            } else if (op == W_INV) {
+                // 1 / (x0 + x1 u) = (x0 - x1 u) / (x0^2 + x1^2)   (fp2.rs:289-303)
+                fp px, n, ni;
+                wide_xchg(px, x);
+                fp_dot2_inl(n, x, x, px, px);
+                fp_inv(ni, n);
+                fp_mul_inl(p, x, ni);
+                fp_neg(n, p);
+                fp_select(p, odd, n, p);
+            } else {
+                if (conjx) {
+                    fp n;
+                    fp_neg(n, x);
+                    fp_select(x, odd, n, x);
+                }
+                if (op == W_MUL) {
+                    fp px, py, npy, u, w;
+                    wide_xchg(px, x);
+                    wide_xchg(py, y);
+                    fp_neg(npy, py);
+                    fp_select(u, odd, py, y);
+                    fp_select(w, odd, y, npy);
+                    fp_dot2_inl(p, x, u, px, w);
+                } else {
+                    if (op == W_SQR) {
+                        fp px, s, dd;
+                        wide_xchg(px, x);
+                        fp_select(s, odd, px, x);
+                        fp_sub(dd, x, px);
+                        fp_select(y, odd, x, dd);
+                        fp_add(x, s, px);
+                    }
+                    fp_mul_inl(p, x, y);
+                }
+                if (nq) fp_add(p, p, q);
+                if (xi) p = wide_xi(p, odd);
+                if (nr) fp_add(p, p, r);
+#pragma unroll 1
+                for (int k = 0; k < dbl; k++) fp_dbl(p, p);
+            }
+            M.sth(d, odd ? 1 : 0, p);
+        }
+        wide_sync();
+    }
+}
+// the item's inputs into their slots (units 0..3: one scalar and one input each); absent pairs are passed as nullptr
+BN_INL void wide_set_item(const WSlots M, const fp *p0, const fp2 *q0, const fp *p1, const fp2 *q1) {
+    const int lane = wide_lane(), unit = lane >> 1;
+    const bool odd = (lane & 1) != 0;
+    if (unit < 4) {
+        const fp *p = (unit & 2) ? p1 : p0;
+        const fp2 *q = (unit & 2) ? q1 : q0;
+        if (p) {            // the scalar as the Fp2 value (s, 0): MULFP reads the c0 half, a general product by the slot is the same
+            fp v;
+            fp_set_zero(v);
+            if (!odd) v = p[unit & 1];
+            M.sth(W_SC + unit, odd ? 1 : 0, v);
+        }
+        if (q) M.sth(W_IN + unit, odd ? 1 : 0, global_half(q + (unit & 1), odd));
+    }
+    wide_sync();
+}
+BN_INL void load_f12(const WSlots M, const fp12 &F, int first_slot = 0) {
+    const int lane = wide_lane(), unit = lane >> 1;
+    const fp2 *c = reinterpret_cast<const fp2 *>(&F);
+    if (unit < 6) M.sth(first_slot + unit, lane & 1, global_half(&c[unit], (lane & 1) != 0));
+    wide_sync();
+}
+BN_INL void store_f12(fp12 &F, const WSlots M) {
+    const int lane = wide_lane(), unit = lane >> 1;
+    fp2 *c = reinterpret_cast<fp2 *>(&F);
+    if (unit < 6) {
+        fp *p = (lane & 1) ? &c[unit].c1 : &c[unit].c0;
+        *p = M.ldh(unit, lane & 1);
+    }
+}
+
 // ---- drivers: the loops over NAF / window digits ---------------------------------------------------------------------
 enum Family : int { FAM_M1 = 0, FAM_M2F = 1, FAM_M2V = 2 };
 
 // Miller loop of one item (pairings.rs:808-857, 862-886 with the BN254 loop of SURVEY.md 0.5); result in slots 0..5
-BN_INL void miller(const Slots M, Env &E, int fam) {
+template <class S>
+BN_INL void miller(const S M, Env &E, int fam) {
     const int r_init = fam == FAM_M2V ? R_M2V_INIT : R_M2F_INIT;
     const int r_dbl = fam == FAM_M1 ? R_M1_DBL : (fam == FAM_M2F ? R_M2F_DBL : R_M2V_DBL);
     const int r_addp = fam == FAM_M1 ? R_M1_ADDP : (fam == FAM_M2F ? R_M2F_ADDP : R_M2V_ADDP);
@@ -273,13 +548,16 @@ BN_INL void miller(const Slots M, Env &E, int fam) {
 
 // scratch variables of the final exponentiation
 enum : int { V_R = 0, V_T = 1, V_A = 2, V_B = 3, V_C = 4, V_PW = 5 };
-BN_INL void fe(const Slots M, Env &E, int routine) { run(M, E, routine); }
-BN_INL void fe_var(const Slots M, Env &E, int routine, int var) {
+template <class S>
+BN_INL void fe(const S M, Env &E, int routine) { run(M, E, routine); }
+template <class S>
+BN_INL void fe_var(const S M, Env &E, int routine, int var) {
     E.var = var;
     run(M, E, routine);
 }
 // F <- conj(F^x): width-4 signed window over f, f^3, f^5, f^7 kept in scratch (pairing.cuh: cyclotomic_exp_neg_x)
-BN_NOINL void fe_exp_neg_x(const Slots M, Env &E) {
+template <class S>
+BN_NOINL void fe_exp_neg_x(const S M, Env &E) {
     fe_var(M, E, R_FE_STF, V_PW);
     fe(M, E, R_FE_MOVGF);
     fe(M, E, R_FE_CYCSQR);
@@ -310,7 +588,8 @@ BN_NOINL void fe_exp_neg_x(const Slots M, Env &E) {
 }
 // pairings.rs:50-178 role (easy part, then Fuentes-Castaneda): input and result in slots 0..5.  The step list is the one
 // tools/gen_vm_programs.py::sim_final_exp checks against the big-integer model.
-BN_INL void final_exp(const Slots M, Env &E) {
+template <class S>
+BN_INL void final_exp(const S M, Env &E) {
     fe_var(M, E, R_FE_STF, V_A);
     fe(M, E, R_FE_INV);
     fe_var(M, E, R_FE_STF, V_T);

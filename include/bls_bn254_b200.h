@@ -69,10 +69,12 @@ int bn254_device_count(void);
 int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev);
 void bn254_ctx_destroy(bn254_ctx *ctx);
 const char *bn254_last_error(const bn254_ctx *ctx);
-/* Tuning / test knobs of a live ctx (the BN254_LANES, BN254_CHUNK, BN254_SPLIT environment variables set the same values at
- * creation): "lanes" = shape of the pairing kernels -- 0 picked per launch (default), 1 one thread per pairing, 2 two lanes
- * per pairing; results are bit-identical in every shape (the parity suite runs all of them); "chunk" = items staged per
- * host<->device round (default 2^18); "split" = concurrent slices per verification batch (default 1). */
+/* Tuning / test knobs of a live ctx (the BN254_LANES, BN254_WIDE_MAX, BN254_CHUNK, BN254_SPLIT environment variables set the
+ * same values at creation): "lanes" = shape of the pairing kernels -- 0 picked per launch (default), 1 one thread per pairing,
+ * 2 two lanes per pairing, 3 the slot machine (two lanes, operands in shared memory), 4 the wide slot machine (one WARP per
+ * pairing: the latency shape); results are bit-identical in every shape (the parity suite runs all of them); "wide_max" =
+ * with "lanes" 0, launches of at most this many pairings use the wide shape; "chunk" = items staged per host<->device round
+ * (default 2^18); "split" = concurrent slices per verification batch (default 1). */
 int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value);
 /* Pin / unpin caller memory (cudaHostRegister) so that the chunk pipeline copies it asynchronously. */
 int bn254_host_register(void *p, size_t bytes);

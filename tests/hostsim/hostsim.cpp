@@ -266,17 +266,20 @@ EXPORT void sim_fp_dot2(uint32_t *r, const uint32_t *a, const uint32_t *b, const
     fp_dot2_inl(o, x, y, z, w);
     memcpy(r, o.v, 32);
 }
-// ---- lane-pair emulation: two host threads run the same body, exchanging through a rendezvous ----
+// ---- lane emulation: host threads run the same body; the two lanes of a pair exchange through a rendezvous, and (wide slot
+//      machine: 32 lanes = 16 pairs) the whole emulated warp can synchronise ----
 #include <pthread.h>
 static thread_local int tl_lane = 0;
-static pthread_barrier_t g_bar;
-static uint32_t g_slot[2][16];
-extern "C" uint32_t bn_host_lane_par() { return (uint32_t)tl_lane; }
+static pthread_barrier_t g_bar[16], g_wbar;
+static uint32_t g_slot[32][16];
+extern "C" uint32_t bn_host_lane_par() { return (uint32_t)(tl_lane & 1); }
+extern "C" int bn_host_lane_id() { return tl_lane; }
+extern "C" void bn_host_warp_sync() { pthread_barrier_wait(&g_wbar); }
 extern "C" void bn_host_lane_xchg(uint32_t *out, const uint32_t *in, int nwords) {
     memcpy(g_slot[tl_lane], in, 4 * nwords);
-    pthread_barrier_wait(&g_bar);
+    pthread_barrier_wait(&g_bar[tl_lane >> 1]);
     memcpy(out, g_slot[tl_lane ^ 1], 4 * nwords);
-    pthread_barrier_wait(&g_bar);
+    pthread_barrier_wait(&g_bar[tl_lane >> 1]);
 }
 struct pair_job { void (*fn)(void *); void *arg; int lane; };
 static void *pair_main(void *p) {
@@ -285,14 +288,20 @@ static void *pair_main(void *p) {
     j->fn(j->arg);
     return nullptr;
 }
-static void run_pair(void (*fn)(void *), void *arg) {
-    pthread_barrier_init(&g_bar, nullptr, 2);
-    pthread_t th[2];
-    pair_job jobs[2] = {{fn, arg, 0}, {fn, arg, 1}};
-    for (int i = 0; i < 2; i++) pthread_create(&th[i], nullptr, pair_main, &jobs[i]);
-    for (int i = 0; i < 2; i++) pthread_join(th[i], nullptr);
-    pthread_barrier_destroy(&g_bar);
+static void run_lanes(void (*fn)(void *), void *arg, int nlanes) {
+    for (int i = 0; i < nlanes / 2; i++) pthread_barrier_init(&g_bar[i], nullptr, 2);
+    pthread_barrier_init(&g_wbar, nullptr, nlanes);
+    pthread_t th[32];
+    pair_job jobs[32];
+    for (int i = 0; i < nlanes; i++) {
+        jobs[i] = {fn, arg, i};
+        pthread_create(&th[i], nullptr, pair_main, &jobs[i]);
+    }
+    for (int i = 0; i < nlanes; i++) pthread_join(th[i], nullptr);
+    for (int i = 0; i < nlanes / 2; i++) pthread_barrier_destroy(&g_bar[i]);
+    pthread_barrier_destroy(&g_wbar);
 }
+static void run_pair(void (*fn)(void *), void *arg) { run_lanes(fn, arg, 2); }
 // lane-pair versions of the pairing bodies (both emulated lanes run the item function)
 struct l2_args { const uint8_t *g1, *g2; const uint8_t *p0, *q0, *p1, *q1; int fixed; int mode; fp12 F; uint8_t fl; };
 static void l2_pairing_body(void *vp) {
@@ -455,6 +464,40 @@ EXPORT unsigned long long sim_vm_ops(int fam, int fexp, const uint8_t *p0, const
     g_ops.store(0);
     sim_vm(fam, fexp, p0, q0, p1, q1, f_in, out);
     return g_ops.load();
+}
+
+// ---- the WIDE slot machine (vm.cuh: run on WSlots) on 32 emulated lanes: same arguments and meaning as sim_vm ----
+struct vmw_args { int fam, fexp; g1m p0, p1; g2m q0, q1; fp12 F; fp (*slots)[2]; };
+static void vmw_body(void *vp) {
+    vmw_args *a = (vmw_args *)vp;
+    const vm::WSlots M = {a->slots};
+    vm::Env E = {};
+    if (a->fam >= 0) {
+        vm::wide_set_item(M, a->fam == 0 ? nullptr : &a->p0.x, a->fam == 2 ? &a->q0.x : nullptr, &a->p1.x, &a->q1.x);
+        vm::miller(M, E, a->fam);
+    } else {
+        vm::load_f12(M, a->F);
+    }
+    if (a->fexp) vm::final_exp(M, E);
+    vm::wide_sync();
+    vm::store_f12(a->F, M);
+}
+EXPORT void sim_vm_wide(int fam, int fexp, const uint8_t *p0, const uint8_t *q0, const uint8_t *p1, const uint8_t *q1, const uint8_t *f_in, uint8_t *out) {
+    static vmw_args a;
+    static fp slots[vm::W_NSLOT][2];
+    memset(&a, 0, sizeof a);
+    memset(slots, 0, sizeof slots);
+    uint8_t fl;
+    a.fam = fam;
+    a.fexp = fexp;
+    a.slots = slots;
+    if (p0) item_g1_decode(a.p0, fl, p0, 0);
+    if (q0) item_g2_decode(a.q0, fl, q0, 0);
+    if (p1) item_g1_decode(a.p1, fl, p1, 0);
+    if (q1) item_g2_decode(a.q1, fl, q1, 0);
+    if (f_in) fp12_from_bytes(a.F, f_in);
+    run_lanes(vmw_body, &a, 32);
+    fp12_to_bytes(out, a.F);
 }
 
 // ---- G2Prepared: the line tables (wire form as the oracle's orc_g2_prepare) and the two-pair loop fed from them ----------

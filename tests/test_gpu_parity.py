@@ -27,11 +27,12 @@ def B():
     return b
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["one-thread", "lane-pair", "slot-machine"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["one-thread", "lane-pair", "slot-machine", "wide"])
 def shape(request, ctx):
     """Force one shape of the pairing kernels for the test (bn254_ctx_set_option "lanes"): 1 = one thread per pairing, 2 = two
     lanes per pairing (tower code on local memory), 3 = the slot machine (vm.cuh: two lanes per pairing, operands in shared
-    memory, the tower as constant-memory programs).  Results are bit-identical."""
+    memory, the tower as constant-memory programs), 4 = the wide slot machine (one warp per pairing, up to 16 independent
+    instructions at a time: the latency shape).  Results are bit-identical."""
     ctx.set_option("lanes", request.param)
     yield request.param
     ctx.set_option("lanes", 0)
@@ -228,8 +229,8 @@ def test_verify_vs_oracle(ctx, orc, B, variant, shape):
     # the kernels of the forced shape really ran
     _, names = launched(ctx, lambda: ctx.verify_batch(variant, pks, msgs, sigs, dst))
     want = {0: ("k_miller2_fixed", "k_final_exp"), 1: ("k_miller2", "k_final_exp")}[variant]
-    if shape == 3:
-        assert {"k_vm_" + w[2:] for w in want} <= names
+    if shape in (3, 4):
+        assert {("k_vm_" if shape == 3 else "k_w_") + w[2:] for w in want} <= names
     else:
         assert {w + ("_l2" if shape == 2 else "") for w in want} <= names
 
@@ -574,8 +575,18 @@ def test_profile_and_launch_count(ctx, orc, B):
     recs = ctx.profile_drain()
     ctx.profile(False)
     names = [r[0] for r in recs]
-    # small batches run the lane-pair (two threads per pairing) shape of the two pairing kernels
-    assert [x[:-3] if x.endswith("_l2") else x for x in names] == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_miller2_fixed", "k_final_exp", "k_fp12_is_one"]
+    # a batch this small runs the latency shape of the two pairing kernels (one warp per pairing, k_w_*) plus the fix-up pass
+    # for dead pairs; "wide_max" = 0 sends it to the lane-pair shape
+    assert names == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_w_miller2_fixed", "k_vm_fixup_miller2_fixed", "k_w_final_exp", "k_fp12_is_one"]
+    ctx.set_option("wide_max", 0)
+    ctx.profile(True)
+    try:
+        assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG) == exp
+        names = [r[0] for r in ctx.profile_drain()]
+        assert names == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_miller2_fixed_l2", "k_final_exp_l2", "k_fp12_is_one"]
+    finally:
+        ctx.profile(False)
+        ctx.set_option("wide_max", 1536)
     assert all(r[2] > 0 for r in recs)
     assert ctx.launch_count > before
 
@@ -704,7 +715,13 @@ def test_aggregate_exchange_single_rank(ctx, orc, B):
     agg = B.scheme.aggregate(ctx, sigs, 0)
     ok, names = launched(ctx, lambda: ctx.aggregate_verify_dist(0, pks, msgs, agg, B.DST_MIN_SIG))
     assert ok == 1 == orc.aggregate_verify(0, pks, msgs, agg, B.DST_MIN_SIG, nthreads=8)
-    assert {"k_fp12_reduce", "k_agg_rec_flag", "k_gather_finish_l2"} <= names
+    assert {"k_fp12_reduce", "k_agg_rec_flag", "k_w_gather_finish"} <= names      # the lone final exponentiation: the latency shape
+    ctx.set_option("wide_max", 0)
+    try:
+        ok, names = launched(ctx, lambda: ctx.aggregate_verify_dist(0, pks, msgs, agg, B.DST_MIN_SIG))
+        assert ok == 1 and "k_gather_finish_l2" in names
+    finally:
+        ctx.set_option("wide_max", 1536)
     msgs[7] = b"tampered"
     assert ctx.aggregate_verify_dist(0, pks, msgs, agg, B.DST_MIN_SIG) == 0
     assert ctx.aggregate_verify_dist(0, b"\xff" * 128 + pks[128:], msgs, agg, B.DST_MIN_SIG) == 0

@@ -52,13 +52,38 @@ def test_programs_in_the_simulator(gen):
     assert g.sim_final_exp(sim, R) == _flat(m.pairing(m.G1_GEN, m.G2_GEN))
 
 
+def test_wide_schedules_in_the_simulator(gen):
+    """the wide machine's programs: every routine after move elimination, post splitting and list scheduling, executed bundle by
+    bundle (all units read, then all units write) on big integers, against oracle/pymodel.py"""
+    from oracle import pymodel as m
+    g, consts, _ = gen
+    _, cidx = g.build_constants()
+    R = g.routines_wide(cidx)
+    for a in R.values():       # a bundle never holds more instructions than the warp has units, and every instruction is placed once
+        assert all(1 <= len(b) <= g.W_UNITS for b in a.bundles)
+        assert sorted(i for b in a.bundles for i in b) == list(range(len(a.ins)))
+    rng = random.Random(6)
+    P0, P1 = (m.g1_mul(m.G1_GEN, rng.randrange(1, m.R_ORDER)) for _ in range(2))
+    Q0, Q1 = (m.g2_mul(m.G2_GEN, rng.randrange(1, m.R_ORDER)) for _ in range(2))
+    for fam, pairs in (("M2F", [(P0, m.g2_neg(m.G2_GEN)), (P1, Q1)]), ("M1", [(P1, Q1)]), ("M2V", [(P0, Q0), (P1, Q1)])):
+        sim = g.WSim(consts)
+        sim.set_item([P0[0], P0[1], P1[0], P1[1]], [Q0[0], Q0[1], Q1[0], Q1[1]])
+        assert g.sim_miller(sim, R, fam) == _flat(m.multi_miller_loop(pairs)), fam
+    f = m.multi_miller_loop([(P1, Q1)])
+    sim = g.WSim(consts)
+    for i, c in enumerate(_flat(f)):
+        sim.s[i] = c
+    assert g.sim_final_exp(sim, R) == _flat(m.final_exponentiation(f))
+
+
 def test_committed_programs_match_the_generator(gen, tmp_path):
     g = gen[0]
-    path = ROOT / "bls_bn254_b200" / "csrc" / "vm_prog.cuh"
-    before = path.read_text()
-    g.emit()
-    after = path.read_text()
-    assert before == after, "bls_bn254_b200/csrc/vm_prog.cuh is stale: run python tools/gen_vm_programs.py"
+    for name, emit in (("vm_prog.cuh", g.emit), ("vmw_prog.cuh", g.emit_wide)):
+        path = ROOT / "bls_bn254_b200" / "csrc" / name
+        before = path.read_text()
+        emit()
+        after = path.read_text()
+        assert before == after, "bls_bn254_b200/csrc/%s is stale: run python tools/gen_vm_programs.py" % name
 
 
 def test_window_digits_are_the_kernels(gen):
@@ -76,6 +101,7 @@ def sim():
     subprocess.check_call(["make", "-s", "-C", str(ROOT / "tests" / "hostsim")])
     lib = C.CDLL(str(ROOT / "tests" / "hostsim" / "libhostsim.so"))
     lib.sim_vm.argtypes = [C.c_int, C.c_int] + [C.c_char_p] * 6
+    lib.sim_vm_wide.argtypes = [C.c_int, C.c_int] + [C.c_char_p] * 6
     return lib
 
 
@@ -86,7 +112,10 @@ def _neg_g2(orc):
     return g[:64] + neg(g[64:96]) + neg(g[96:])
 
 
-def test_interpreter_on_emulated_lanes_vs_oracle(sim, orc, kats):
+@pytest.mark.parametrize("machine", ["sim_vm", "sim_vm_wide"])
+def test_interpreter_on_emulated_lanes_vs_oracle(sim, orc, kats, machine):
+    """sim_vm: the slot machine on two emulated lanes; sim_vm_wide: the wide machine on 32 emulated lanes (16 units, bundles)"""
+    run = getattr(sim, machine)
     rng = random.Random(12)
     msgs = [rng.randbytes(20) for _ in range(4)]
     g1 = orc.hash_to_g1(msgs, DST)
@@ -94,20 +123,20 @@ def test_interpreter_on_emulated_lanes_vs_oracle(sim, orc, kats):
     out = C.create_string_buffer(384)
     p0, p1, q0, q1 = g1[:64], g1[64:128], g2[:128], g2[128:256]
     # one pair, Miller loop only / whole pairing
-    sim.sim_vm(0, 0, None, None, p1, q1, None, out)
+    run(0, 0, None, None, p1, q1, None, out)
     assert out.raw == orc.miller_loop_batch(p1, q1)
-    sim.sim_vm(0, 1, None, None, p1, q1, None, out)
+    run(0, 1, None, None, p1, q1, None, out)
     assert out.raw == orc.pairing_batch(p1, q1)
     # two pairs with the fixed -g2 table (the verification shape)
-    sim.sim_vm(1, 0, p0, None, p1, q1, None, out)
+    run(1, 0, p0, None, p1, q1, None, out)
     assert out.raw == orc.multi_miller_loop(p0 + p1, _neg_g2(orc) + q1)
     # two variable pairs
-    sim.sim_vm(2, 0, p0, q0, p1, q1, None, out)
+    run(2, 0, p0, q0, p1, q1, None, out)
     assert out.raw == orc.multi_miller_loop(p0 + p1, q0 + q1)
     # final exponentiation alone
     ml = orc.miller_loop_batch(p0, q0)
-    sim.sim_vm(-1, 1, None, None, None, None, ml, out)
+    run(-1, 1, None, None, None, None, ml, out)
     assert out.raw == orc.final_exponentiation(ml)
     # pairing(g1, g2) == Gt::generator() (pairings.rs:970-980)
-    sim.sim_vm(0, 1, None, None, orc.g1_generator(), orc.g2_generator(), None, out)
+    run(0, 1, None, None, orc.g1_generator(), orc.g2_generator(), None, out)
     assert out.raw == b"".join(bytes.fromhex(x) for x in kats["gt_generator"])

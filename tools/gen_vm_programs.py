@@ -43,23 +43,29 @@ IN_Q0X, IN_Q0Y, IN_Q1X, IN_Q1Y = 0, 1, 2, 3
 class T:
     """operand term: slot with optional negation / multiplication by xi = 9 + u (and a small coefficient for LIN)"""
 
-    def __init__(self, slot, neg=False, xi=False, coef=1):
+    def __init__(self, slot, neg=False, xi=False, coef=1, rell=False, relv=False):
         self.slot, self.neg, self.xi, self.coef = slot, neg, xi, coef
+        self.rell, self.relv = rell, relv       # wide machine only: slot += 3 * line / slot += 6 * var at run time
 
     def __neg__(self):
-        return T(self.slot, not self.neg, self.xi, self.coef)
+        return T(self.slot, not self.neg, self.xi, self.coef, self.rell, self.relv)
 
     def x(self):
-        return T(self.slot, self.neg, True, self.coef)
+        return T(self.slot, self.neg, True, self.coef, self.rell, self.relv)
 
     def __mul__(self, k):
-        return T(self.slot, self.neg != (k < 0), self.xi, self.coef * abs(k))
+        return T(self.slot, self.neg != (k < 0), self.xi, self.coef * abs(k), self.rell, self.relv)
 
     __rmul__ = __mul__
 
     def byte(self):
-        assert 0 <= self.slot < 64
+        assert 0 <= self.slot < 64 and not (self.rell or self.relv)
         return self.slot | (NEG if self.neg else 0) | (XI if self.xi else 0)
+
+    def half(self):
+        """16-bit descriptor of the wide machine: slot(10) | NEG | XI | RELL | RELV | coef - 1 (2)"""
+        assert 0 <= self.slot < 1024 and 1 <= self.coef <= 4
+        return (self.slot | int(self.neg) << 10 | int(self.xi) << 11 | int(self.rell) << 12 | int(self.relv) << 13 | (self.coef - 1) << 14)
 
 
 def terms(x):
@@ -126,7 +132,7 @@ class Asm:
 
     # -- product class.  Posts that do not fit one instruction spill into a following LIN.
     def _prod(self, op, d, xs, ys=(), q=(), r=(), xi=False, dbl=0, **kw):
-        expand = lambda ts: [T(t.slot, t.neg, t.xi) for t in terms(ts) for _ in range(t.coef)]
+        expand = lambda ts: [T(t.slot, t.neg, t.xi, 1, t.rell, t.relv) for t in terms(ts) for _ in range(t.coef)]
         xs, ys, q, r = expand(xs), expand(ys), expand(q), expand(r)
         limit = 10 if kw.get("cidx") is not None else 12
         extra = []
@@ -403,11 +409,12 @@ NSLOT_MILLER = 32      # assembler limit; the emitted per-family counts are the 
 NSLOT_FEXP = 32
 
 
-def routines(cidx):
+def routines(cidx, asm=None):
     R = {}
+    asm = asm or Asm
 
     def new(name, first_tmp, nslot):
-        a = Asm(name, nslot, first_tmp)
+        a = asm(name, nslot, first_tmp)
         R[name] = a
         return a
 
@@ -801,6 +808,331 @@ def sim_final_exp(sim, R):
     return [sim.s[i] for i in range(6)]
 
 
+# ---------------------------------------------------------------------------------------- the WIDE machine
+# Same algebra, other shape (vm.cuh: run_wide): ONE item per warp, the 16 lane pairs of the warp are 16 units that execute up
+# to 16 INDEPENDENT instructions of a routine at once (a BUNDLE), exchanging values through the item's slots in shared
+# memory.  It is the latency shape -- a lone pairing is a 4 ms dependent chain on one lane pair and ~0.3 ms on a warp -- used
+# for small batches (one verification, the single final exponentiation of an aggregate, the per-group tail of the
+# randomised path).  Differences from the sequential machine:
+#   * slots are plentiful (one item per warp), so every temporary gets a FRESH slot (no reuse, no false dependencies);
+#   * item scalars, item inputs, scratch variables and constants are slots too (ids below), so the only opcodes are
+#     MUL, SQR, MULFP (times the c0 half of a slot), LIN and INV; 16-bit operand descriptors;
+#   * a list scheduler packs each routine into bundles; inside a bundle every unit reads its operands, the warp
+#     synchronises, every unit writes its result, the warp synchronises -- so an instruction may share a bundle with earlier
+#     readers of its destination (write-after-read), but not with the producer of an operand or an earlier writer.
+W_NOP, W_MUL, W_SQR, W_MULFP, W_LIN, W_INV = 0, 1, 2, 3, 4, 5
+W_NAMES = {W_MUL: "MUL", W_SQR: "SQR", W_MULFP: "MULFP", W_LIN: "LIN", W_INV: "INV"}
+W_SC, W_IN, W_VAR, W_TMP, W_CONST = 12, 16, 20, 80, 700     # slot ids: 4 scalars, 4 inputs, 60 scratch entries, temporaries, constants
+W_UNITS = 16
+
+
+class WIns:
+    def __init__(self, op, d, xs=(), ys=(), q=(), r=(), xi=False, dbl=0, conjx=False, drelv=False):
+        self.op, self.d, self.xs, self.ys, self.q, self.r = op, d, terms(xs), terms(ys), terms(q), terms(r)
+        self.xi, self.dbl, self.conjx, self.drelv = xi, dbl, conjx, drelv
+
+    def reads(self):
+        return [(t.slot, t.rell, t.relv) for t in self.xs + self.ys + self.q + self.r]
+
+    def write(self):
+        return (self.d, False, self.drelv)
+
+    def encode(self, as_mul=False):
+        """as_mul: a squaring / scalar product that shares its bundle with general products is encoded as one (MUL with no Y
+        terms squares X; the scalar's slot holds (s, 0), so the general product by it is the scalar product)"""
+        op = W_MUL if as_mul and self.op in (W_SQR, W_MULFP) else self.op
+        nx, ny, nq, nr = len(self.xs), len(self.ys), len(self.q), len(self.r)
+        assert nx <= 12 and ny <= 7 and nq <= 3 and nr <= 7 and nx + ny + nq + nr <= 12 and 0 <= self.dbl <= 3 and 0 <= self.d < 1024
+        if self.op != W_LIN:
+            assert all(t.coef == 1 for t in self.xs + self.ys + self.q + self.r)
+        assert not (self.op == W_MUL and ny == 0)
+        w0 = (op | self.d << 4 | nx << 14 | ny << 18 | nq << 21 | nr << 23 | int(self.xi) << 26 | self.dbl << 27 | int(self.conjx) << 29 |
+              int(self.drelv) << 30)
+        desc = [t.half() for t in self.xs + self.ys + self.q + self.r]
+        desc += [0] * (12 - len(desc))
+        return [w0, 0] + [desc[2 * i] | desc[2 * i + 1] << 16 for i in range(6)]
+
+
+class WAsm:
+    """the assembler interface of the tower macros, emitting wide-machine instructions"""
+
+    def __init__(self, name, nslot, first_tmp):
+        self.name, self.ins, self.next_tmp, self.high = name, [], W_TMP, W_TMP
+
+    def tmp(self, n=None):
+        if n is not None:
+            return [self.tmp() for _ in range(n)]
+        s = self.next_tmp
+        self.next_tmp += 1
+        self.high = self.next_tmp
+        assert self.high <= W_CONST
+        return s
+
+    def free(self, *slots):
+        pass
+
+    def _prod(self, op, d, xs, ys=(), q=(), r=(), xi=False, dbl=0, conjx=False):
+        expand = lambda ts: [T(t.slot, t.neg, t.xi, 1, t.rell, t.relv) for t in terms(ts) for _ in range(t.coef)]
+        xs, ys, q, r = expand(xs), expand(ys), expand(q), expand(r)
+        extra = []
+        while len(xs) + len(ys) + len(q) + len(r) > 12 or len(r) > 7:
+            assert r and dbl == 0, "cannot split"
+            extra.append(r.pop())
+        self.ins.append(WIns(op, d, xs, ys, q, r, xi=xi, dbl=dbl, conjx=conjx))
+        if extra:
+            self.lin(d, [T(d)] + extra)
+
+    def mul(self, d, xs, ys, q=(), r=(), xi=False, dbl=0): self._prod(W_MUL, d, xs, ys, q, r, xi, dbl)
+    def sqr(self, d, xs, q=(), r=(), xi=False, dbl=0): self._prod(W_SQR, d, xs, (), q, r, xi, dbl)
+    def mulfp(self, d, xs, sc, r=()): self._prod(W_MULFP, d, xs, [T(W_SC + sc)], (), r)
+    def mulc(self, d, xs, cidx, conjx=False, rel=False, r=()): self._prod(W_MUL, d, xs, [T(W_CONST + cidx, rell=rel)], (), r, conjx=conjx)
+    def mulfpc(self, d, cidx, sc, rel=False): self._prod(W_MULFP, d, [T(W_CONST + cidx, rell=rel)], [T(W_SC + sc)])
+
+    def lin(self, d, xs, dbl=0, conj=False, drelv=False):
+        xs = terms(xs)
+        assert len(xs) <= 12
+        self.ins.append(WIns(W_LIN, d, xs, dbl=dbl, conjx=conj, drelv=drelv))
+
+    def mov(self, d, s): self.lin(d, [T(s)])
+    def ldc(self, d, cidx, rel=False): self.lin(d, [T(W_CONST + cidx, rell=rel)])
+    def ldg(self, d, field): self.lin(d, [T(W_IN + field)])
+    def inv(self, d, s): self.ins.append(WIns(W_INV, d, [T(s)]))
+    def fill(self, d, k, rel=False): self.lin(d, [T(W_VAR + k, relv=rel)])
+    def spill(self, s, k, rel=False): self.lin(W_VAR + k, [T(s)], drelv=rel)
+
+
+def schedule(ins, units=W_UNITS):
+    """list scheduling of one routine into bundles of <= `units` instructions; returns a list of lists of indices"""
+    n = len(ins)
+    strict, weak = [set() for _ in ins], [set() for _ in ins]
+    last_write, readers = {}, {}
+    for i, I in enumerate(ins):
+        for k in I.reads():
+            if k in last_write:
+                strict[i].add(last_write[k])              # read after write
+            readers.setdefault(k, []).append(i)
+        w = I.write()
+        if w in last_write:
+            strict[i].add(last_write[w])                  # write after write
+        for j in readers.get(w, []):
+            if j != i:
+                weak[i].add(j)                            # write after read: same bundle is fine (reads come first)
+        last_write[w] = i
+        readers[w] = []
+    # priority: longest chain of strict dependencies below the instruction
+    succ = [[] for _ in ins]
+    for i in range(n):
+        for j in strict[i]:
+            succ[j].append((i, 1))
+        for j in weak[i]:
+            succ[j].append((i, 0))
+    height = [0] * n
+    for i in reversed(range(n)):
+        height[i] = max([height[k] + c for k, c in succ[i]], default=0)
+    # A warp runs ONE code path at a time: a bundle costs the sum of the paths of the opcode classes in it.  So bundles are
+    # built class by class: the class of the most urgent ready instruction first, every ready instruction of that class with
+    # it; another class joins only if leaving it out would stretch the critical path (its tail is as long as what remains
+    # after this bundle); linear steps always join (cheap).  Squarings and scalar products that share a bundle with general
+    # products are executed as general products (the same field element, one path less).
+    path = {W_MUL: 16, W_SQR: 13, W_MULFP: 12, W_LIN: 4, W_INV: 600}
+    tail = [0] * n
+    for i in reversed(range(n)):
+        tail[i] = path[ins[i].op] + max([tail[k] for k, c in succ[i] if c], default=0)
+    level, bundles, left = [None] * n, [], set(range(n))
+    while left:
+        b, cur = len(bundles), []
+
+        def ready():
+            return [i for i in left if all(level[j] is not None and level[j] < b for j in strict[i])
+                    and all(level[j] is not None and level[j] <= b for j in weak[i])]
+
+        def take(i):
+            level[i] = b
+            cur.append(i)
+            left.remove(i)
+
+        ok = ready()
+        assert ok
+        lead = max(ok, key=lambda i: (tail[i], -i))
+        heavy = ins[lead].op != W_LIN
+        classes = {ins[lead].op}
+        progress = True
+        while progress and len(cur) < units:
+            progress = False
+            for i in sorted(ready(), key=lambda i: (-tail[i], i)):
+                if len(cur) >= units:
+                    break
+                op = ins[i].op
+                product = op in (W_MUL, W_SQR, W_MULFP)
+                lead_product = ins[lead].op in (W_MUL, W_SQR, W_MULFP)
+                if op in classes or (product and lead_product) or (op == W_LIN and not (ins[lead].op == W_INV)):
+                    take(i)
+                    classes.add(op)
+                    progress = True
+                elif op != W_INV and ins[lead].op != W_INV and tail[i] + path[ins[lead].op] > tail[lead]:
+                    take(i)
+                    classes.add(op)
+                    progress = True
+        bundles.append(cur)
+    return bundles
+
+
+class WSim(Sim):
+    """bundle-level simulator of the wide machine: all units read, then all units write"""
+
+    def __init__(self, consts):
+        Sim.__init__(self, W_CONST, consts)
+        self.s = {}
+
+    def set_item(self, scalars, inputs):
+        for i, v in enumerate(scalars):
+            self.s[W_SC + i] = (v, 0)
+        for i, v in enumerate(inputs):
+            self.s[W_IN + i] = v
+
+    def addr(self, slot, rell, relv):
+        return slot + (3 * self.line if rell else 0) + (6 * self.var if relv else 0)
+
+    def term(self, t):
+        a = self.addr(t.slot, t.rell, t.relv)
+        v = self.consts[a - W_CONST] if a >= W_CONST else self.s[a]
+        if t.xi:
+            v = self.xi(v)
+        if t.neg:
+            v = self.neg(v)
+        return v
+
+    def result(self, ins):
+        if ins.op == W_LIN:
+            res = self.total(ins.xs)
+            for _ in range(ins.dbl):
+                res = self.add(res, res)
+            return self.conj(res) if ins.conjx else res
+        x = self.total(ins.xs)
+        if ins.op == W_INV:
+            n = pow((x[0] * x[0] + x[1] * x[1]) % P, P - 2, P)
+            return (x[0] * n % P, (-x[1]) * n % P)
+        if ins.conjx:
+            x = self.conj(x)
+        if ins.op == W_MUL:
+            p = self.mul(x, self.total(ins.ys))
+        elif ins.op == W_SQR:
+            p = self.mul(x, x)
+        else:
+            sc = self.total(ins.ys)[0]
+            p = (x[0] * sc % P, x[1] * sc % P)
+        t = self.add(p, self.total(ins.q))
+        if ins.xi:
+            t = self.xi(t)
+        res = self.add(t, self.total(ins.r))
+        for _ in range(ins.dbl):
+            res = self.add(res, res)
+        return res
+
+    def run(self, asm):
+        for b in asm.bundles:
+            out = [(self.addr(*asm.ins[i].write()), self.result(asm.ins[i])) for i in b]
+            assert len({a for a, _ in out}) == len(out)
+            for a, v in out:
+                self.s[a] = v
+            self.count[len(b)] = self.count.get(len(b), 0) + 1
+
+
+def split_posts(a):
+    """A product whose post terms (q, r) become available later than its factors is split into the bare product (fresh slot)
+    and a linear step, so that the products of a Karatsuba wave do not wait for one another."""
+    avail, out = {}, []
+    ready = lambda ts: max([avail.get((t.slot, t.rell, t.relv), 0) for t in ts], default=0)
+    for I in a.ins:
+        if I.op in (W_MUL, W_SQR, W_MULFP) and (I.q or I.r) and ready(I.q + I.r) > ready(I.xs + I.ys):
+            assert not any(t.xi for t in I.q) or not I.xi
+            t = a.tmp()
+            bare = WIns(I.op, t, I.xs, I.ys, conjx=I.conjx)
+            flip = lambda u: T(u.slot, u.neg, u.xi or I.xi, u.coef, u.rell, u.relv)
+            lin = WIns(W_LIN, I.d, [T(t, xi=I.xi)] + [flip(u) for u in I.q] + list(I.r), dbl=I.dbl)
+            lvl = ready(bare.xs + bare.ys)
+            avail[bare.write()] = lvl + 1
+            avail[lin.write()] = max(lvl + 1, ready(lin.xs)) + 1
+            out += [bare, lin]
+        else:
+            avail[I.write()] = ready(I.xs + I.ys + I.q + I.r) + 1
+            out.append(I)
+    a.ins = out
+
+
+def sink_into_moves(a):
+    """`t = expr; ...; d = t` (the sequential macros protect in-place updates that way) becomes `d = expr` at the position of
+    the move when nothing in between touches t or changes an operand of expr: one bundle less on the critical path."""
+    key = lambda t: (t.slot, t.rell, t.relv)
+    changed = True
+    while changed:
+        changed = False
+        for i, I in enumerate(a.ins):
+            if not (I.op == W_LIN and len(I.xs) == 1 and not I.dbl and not I.conjx and not I.drelv):
+                continue
+            t = I.xs[0]
+            if t.neg or t.xi or t.coef != 1 or t.rell or t.relv or t.slot < W_TMP:
+                continue
+            src = key(t)
+            js = [j for j in range(i) if a.ins[j].write() == src]
+            if not js:
+                continue
+            j = js[-1]
+            J = a.ins[j]
+            users = [k for k in range(j + 1, len(a.ins)) if k != i and src in a.ins[k].reads()]
+            later_writers = [k for k in range(j + 1, len(a.ins)) if a.ins[k].write() == src]
+            if users and not (later_writers and later_writers[0] < users[0]):
+                continue
+            operands = set(J.reads())
+            if any(a.ins[k].write() in operands for k in range(j + 1, i)):
+                continue
+            a.ins[i] = WIns(J.op, I.d, J.xs, J.ys, J.q, J.r, xi=J.xi, dbl=J.dbl, conjx=J.conjx)
+            del a.ins[j]
+            changed = True
+            break
+
+
+def routines_wide(cidx):
+    R = routines(cidx, WAsm)
+    for a in R.values():
+        sink_into_moves(a)
+        split_posts(a)
+        a.bundles = schedule(a.ins)
+    return R
+
+
+def emit_wide():
+    consts, cidx = build_constants()
+    R = routines_wide(cidx)
+    out = ["// GENERATED by tools/gen_vm_programs.py -- do not edit.  Bundled programs of the WIDE slot machine (vm.cuh: run_wide): one item",
+           "// per warp, up to 16 independent instructions per bundle.  Routine ids and constants are those of vm_prog.cuh.",
+           "#pragma once", "#include <stdint.h>", "", "namespace bn {", "namespace vm {", ""]
+    for name, val in (("W_MUL", W_MUL), ("W_SQR", W_SQR), ("W_MULFP", W_MULFP), ("W_LIN", W_LIN), ("W_INV", W_INV), ("W_SC", W_SC), ("W_IN", W_IN),
+                      ("W_VAR", W_VAR), ("W_TMP", W_TMP), ("W_CONST", W_CONST), ("W_UNITS", W_UNITS)):
+        out.append("constexpr int %s = %d;" % (name, val))
+    out.append("constexpr int W_NSLOT = %d;   // slots per item (high-water mark of the temporaries)" % max(a.high for a in R.values()))
+    words, boff, dirs = [], [0], []
+    for n in R:
+        a = R[n]
+        dirs.append((len(boff) - 1, len(a.bundles)))
+        for b in a.bundles:
+            mixed = len({a.ins[i].op for i in b if a.ins[i].op in (W_MUL, W_SQR, W_MULFP)}) > 1
+            for i in b:
+                words.append(a.ins[i].encode(as_mul=mixed))
+            boff.append(len(words))
+    out.append("// routine directory: {first bundle, bundle count}; bundle b = instructions [W_BOFF[b], W_BOFF[b + 1])")
+    out.append("BN_GDECL uint16_t W_DIR[R_COUNT][2] = {" + ", ".join("{%d, %d}" % d for d in dirs) + "};")
+    out.append("BN_GDECL uint16_t W_BOFF[%d] = {%s};" % (len(boff), ", ".join(str(x) for x in boff)))
+    out.append("// %d instructions in %d bundles, 32 bytes each" % (len(words), len(boff) - 1))
+    out.append("BN_GDECL uint32_t W_PROG[%d][8] = {" % len(words))
+    for w in words:
+        out.append("    {" + ", ".join("0x%08xu" % x for x in w) + "},")
+    out.append("};")
+    out += ["", "}  // namespace vm", "}  // namespace bn", ""]
+    (ROOT / "bls_bn254_b200" / "csrc" / "vmw_prog.cuh").write_text("\n".join(out))
+    return R
+
+
 # ---------------------------------------------------------------------------------------- emission
 def mont_words(v):
     v = v * R256 % P
@@ -855,6 +1187,13 @@ def emit():
 
 
 if __name__ == "__main__":
+    RW = emit_wide()
+    print("vmw_prog.cuh: %d routines, %d instructions in %d bundles, %d slots per item" % (
+        len(RW), sum(len(a.ins) for a in RW.values()), sum(len(a.bundles) for a in RW.values()), max(a.high for a in RW.values())))
+    for name, a in RW.items():
+        heavy = lambda b: any(a.ins[i].op != W_LIN for i in b)
+        print("  %-10s %3d instr in %3d bundles (%2d with products)  %s" % (name, len(a.ins), len(a.bundles), sum(heavy(b) for b in a.bundles),
+                                                                          " ".join(("%d" if heavy(b) else "(%d)") % len(b) for b in a.bundles)))
     R, consts, cidx, n = emit()
     print("vm_prog.cuh: %d routines, %d instructions (%d bytes), %d constants" % (len(R), n, 16 * n, len(consts)))
     for name, a in R.items():
