@@ -10,7 +10,7 @@
 //!   verify / aggregate_verify (absent upstream) Context::verify_batch / aggregate_verify
 //!
 //! A crate that wants the single-item signatures of the reference calls these with one element (see `hash_g1_one`,
-//! `pairing_one`); throughput needs batches (a lone pairing on a GPU takes ~9 ms, 2^16 of them 24 ms).
+//! `pairing_one`); throughput needs batches (a lone pairing on a GPU takes ~5 ms, 2^16 of them 24 ms).
 pub mod error;
 pub mod ffi;
 
