@@ -75,18 +75,63 @@ BN_INL void sha256_put(sha256 &s, uint8_t byte) {
         s.fill = 0;
     }
 }
+// One big-endian word at a word boundary of the block (fill % 4 == 0): a single store instead of four read-modify-writes.
+BN_INL void sha256_put_word(sha256 &s, uint32_t word) {
+    s.w[s.fill >> 2] = word;
+    s.fill += 4;
+    s.len += 4;
+    if (s.fill == 64) {
+        sha256_compress(s.h, s.w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s.w[i] = 0;
+        s.fill = 0;
+    }
+}
+BN_INL uint32_t load_be32(const uint8_t *d) {
+    if ((reinterpret_cast<uintptr_t>(d) & 3u) == 0) {
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(d);
+#if BN_PTX
+        return __byte_perm(v, 0, 0x0123);
+#else
+        return __builtin_bswap32(v);
+#endif
+    }
+    return (uint32_t)d[0] << 24 | (uint32_t)d[1] << 16 | (uint32_t)d[2] << 8 | (uint32_t)d[3];
+}
+// word-wise absorption: bytes up to the next word boundary of the block, whole words, the remaining bytes
 BN_INL void sha256_update(sha256 &s, const uint8_t *d, size_t n) {
 #pragma unroll 1
-    for (size_t i = 0; i < n; i++) sha256_put(s, d[i]);
+    while (n && (s.fill & 3u)) {
+        sha256_put(s, *d++);
+        n--;
+    }
+#pragma unroll 1
+    while (n >= 4) {
+        sha256_put_word(s, load_be32(d));
+        d += 4;
+        n -= 4;
+    }
+#pragma unroll 1
+    while (n) {
+        sha256_put(s, *d++);
+        n--;
+    }
 }
-BN_INL void sha256_final(sha256 &s, uint8_t out[32]) {
+// padding and the last compression(s); the digest stays in s.h as eight big-endian words
+BN_INL void sha256_finish(sha256 &s) {
     uint64_t bits = s.len * 8;
     sha256_put(s, 0x80);
 #pragma unroll 1
-    while (s.fill != 56) sha256_put(s, 0);
+    while (s.fill != 56) {
+        if (s.fill & 3u) sha256_put(s, 0);
+        else sha256_put_word(s, 0);
+    }
     s.w[14] = (uint32_t)(bits >> 32);
     s.w[15] = (uint32_t)bits;
     sha256_compress(s.h, s.w);
+}
+BN_INL void sha256_final(sha256 &s, uint8_t out[32]) {
+    sha256_finish(s);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         out[4 * i] = (uint8_t)(s.h[i] >> 24);
@@ -95,37 +140,51 @@ BN_INL void sha256_final(sha256 &s, uint8_t out[32]) {
         out[4 * i + 3] = (uint8_t)s.h[i];
     }
 }
+// SHA-256 state after the 64 zero bytes of Z_pad (RFC 9380 5.3.1 step 7): the first block of every b_0 is constant, so its
+// compression is done once, here (tools: the value is the compression function applied to the IV and a zero block).
+BN_INL void sha256_init_zpad(sha256 &s) {
+    s.h[0] = 0xda5698be; s.h[1] = 0x17b9b469; s.h[2] = 0x62335799; s.h[3] = 0x779fbeca;
+    s.h[4] = 0x8ce5d491; s.h[5] = 0xc0d26243; s.h[6] = 0xbafef9ea; s.h[7] = 0x1837a9d8;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s.w[i] = 0;
+    s.fill = 0;
+    s.len = 64;
+}
 
 // RFC 9380 5.3.1 with H = SHA-256 (b = 32, s = 64); n <= 255*32.  dst_len <= 255 (an oversize DST
 // is replaced by H("H2C-OVERSIZE-DST-" || DST) before this is called, see oversize_dst()).
+// b_0 and the b_i stay as big-endian WORDS: b_0 xor b_(i-1) is fed to the next hash eight words at a time.
 BN_INL void expand_message_xmd(uint8_t *out, uint32_t n, const uint8_t *msg, size_t msg_len, const uint8_t *dst, uint32_t dst_len) {
-    uint8_t b0[32], bi[32];
+    uint32_t b0[8], bi[8];
     sha256 s;
     uint32_t ell = (n + 31) / 32;
-    sha256_init(s);
-#pragma unroll 1
-    for (int i = 0; i < 64; i++) sha256_put(s, 0);  // Z_pad
+    sha256_init_zpad(s);
     sha256_update(s, msg, msg_len);
     sha256_put(s, (uint8_t)(n >> 8));
     sha256_put(s, (uint8_t)n);
     sha256_put(s, 0);
     sha256_update(s, dst, dst_len);
     sha256_put(s, (uint8_t)dst_len);
-    sha256_final(s, b0);
-#pragma unroll 1
-    for (int j = 0; j < 32; j++) bi[j] = 0;
+    sha256_finish(s);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        b0[j] = s.h[j];
+        bi[j] = 0;
+    }
 #pragma unroll 1
     for (uint32_t i = 1; i <= ell; i++) {
         sha256_init(s);
-#pragma unroll 1
-        for (int j = 0; j < 32; j++) sha256_put(s, b0[j] ^ bi[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sha256_put_word(s, b0[j] ^ bi[j]);
         sha256_put(s, (uint8_t)i);
         sha256_update(s, dst, dst_len);
         sha256_put(s, (uint8_t)dst_len);
-        sha256_final(s, bi);
+        sha256_finish(s);
+#pragma unroll
+        for (int j = 0; j < 8; j++) bi[j] = s.h[j];
         uint32_t off = (i - 1) * 32, take = n - off < 32 ? n - off : 32;
 #pragma unroll 1
-        for (uint32_t j = 0; j < take; j++) out[off + j] = bi[j];
+        for (uint32_t j = 0; j < take; j++) out[off + j] = (uint8_t)(bi[j >> 2] >> (24 - 8 * (j & 3u)));
     }
 }
 BN_INL void oversize_dst(uint8_t out[32], const uint8_t *dst, size_t dst_len) {
