@@ -417,16 +417,20 @@ int dev_final_exp(Dev &d, const uint8_t *ml, size_t n, uint8_t *out, uint8_t *st
 
 // product of n Fp12 records (internal form) -> *result points at one record: `final_dst` when given (the last pass of
 // the tree then writes straight into it, e.g. the NCCL send record), else a scratch record
+// Fan-in per pass: 16 while a pass still fills the machine, 4 below that -- a pass is then a latency-bound chain of fan - 1
+// dependent Fp12 products per thread (~23 us each), so 2^16 partials cost 8 x 3 products instead of 4 x 15.
 int dev_fp12_product(Dev &d, fp12 *F, size_t n, fp12 **result, fp12 *final_dst = nullptr) {
+    auto fan_of = [](size_t cur) -> size_t { return cur > ((size_t)1 << 18) ? 16 : 4; };
     fp12 *A, *B;
-    size_t m0 = std::max<size_t>(1, (n + 15) / 16);
-    if (int rc = ensure_t(d, S_F2, m0 + (m0 + 15) / 16 + 2, &A)) return rc;
+    size_t m0 = std::max<size_t>(1, (n + fan_of(n) - 1) / fan_of(n));
+    if (int rc = ensure_t(d, S_F2, m0 + (m0 + 3) / 4 + 2, &A)) return rc;
     B = A + m0;
     const fp12 *src = F;
     size_t cur = n;
     fp12 *dstp = A;
     while (true) {
-        size_t m = std::max<size_t>(1, (cur + 15) / 16);
+        const size_t fan = fan_of(cur);
+        size_t m = std::max<size_t>(1, (cur + fan - 1) / fan);
         if (m == 1 && final_dst) dstp = final_dst;
         LAUNCH(d, k_fp12_reduce, m, BN_TPB_HEAVY, dstp, src, cur, m);
         if (m == 1) break;
