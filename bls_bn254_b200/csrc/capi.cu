@@ -87,8 +87,8 @@ struct Dev {
     int shape = 0;
     // 3 = the slot machine, 4 = the WIDE slot machine (one warp per item: the latency shape).  In shape 0 a launch of at most
     // wide_max items uses the wide kernels ("wide_max" option / BN254_WIDE_MAX; 0 = never).  Default: about ten warps per SM,
-    // below which a warp per item beats a lane pair per item (measured per verification batch: 512 items 5.7 against 8.8 ms,
-    // 1536 items 7.8 against 8.9 ms, 2048 items 10.8 against 9.0 ms).
+    // below which a warp per item beats a lane pair per item (measured per verification batch: 256 items 4.1 against 8.7 ms,
+    // 1024 items 4.9 against 8.8 ms, 2048 items 9.0 against 8.9 ms, 3072 items 11.8 against 9.0 ms).
     size_t wide_max = 1536;
     // Chunk pipeline of the host-buffer entry points: copies run on `cp`, kernels on `st`; two staging sets.
     cudaStream_t cp = nullptr;
@@ -614,7 +614,7 @@ int dev_fast_aggregate(Dev &d, int variant, const uint8_t *pks, size_t nkeys, co
 // that staging set, so that it overlaps the main kernels of the next chunk; the caller collects `ok` on d.tail.
 int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
                     size_t n, size_t group, const uint8_t *seed, uint64_t idx0, int nbits, const uint8_t *dst, uint32_t dst_len, uint32_t flags,
-                    uint8_t *ok, int tail_set = -1) {
+                    uint8_t *ok, int tail_set = -1, bool tail_hidden = false) {
     const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
     const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
     const size_t nseg = (n + group - 1) / group;
@@ -642,7 +642,7 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
         Dev &d; size_t keep;
         WideOff(Dev &dd, bool off) : d(dd), keep(dd.wide_max) { if (off) d.wide_max = 0; }
         ~WideOff() { d.wide_max = keep; }
-    } wide_off(d, tail_set >= 0);
+    } wide_off(d, tail_set >= 0 && tail_hidden);
     if (int rc = ensure_t(d, stage_buf(S_RB_BAD, tail_set > 0 ? 1 : 0), nseg, &gbad)) return rc;
     CK(d, cudaMemsetAsync(gbad, 0, nseg * sizeof(int), d.cur));
     // The signature side (scale, per-group sums, one Miller loop per GROUP against the fixed generator) only needs
@@ -672,7 +672,11 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
             SEG_LEVELS(d, k_g1p_seg_sum, g1p, S0, SA, SB, n, group, &Sg);
             LAUNCH(d, k_g1p_to_affine, nseg, BN_TPB_HEAVY, GP, gflp, Sg, nseg);
             LAUNCH(d, k_fill_neg_g2, nseg, BN_TPB_LIGHT, GQ, gflq, nseg);
-            if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
+            {   // runs beside the per-tuple pipeline of the main stream: throughput shape (measured: a wide group loop costs the
+                // main stream more than it saves, 19.6 -> 21.0 ms per 2^16 tuples)
+                WideOff beside(d, true);
+                if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
+            }
             if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
         }
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q1, flq1, pks, n, check);
@@ -698,7 +702,11 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
             SEG_LEVELS(d, k_g2p_seg_sum, g2p, S0, SA, SB, n, group, &Sg);
             LAUNCH(d, k_g2p_to_affine, nseg, BN_TPB_HEAVY, GQ, gflq, Sg, nseg);
             LAUNCH(d, k_fill_neg_g1, nseg, BN_TPB_LIGHT, GP, gflp, nseg);
-            if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
+            {   // runs beside the per-tuple pipeline of the main stream: throughput shape (measured: a wide group loop costs the
+                // main stream more than it saves, 19.6 -> 21.0 ms per 2^16 tuples)
+                WideOff beside(d, true);
+                if (int rc = launch_miller1(d, nseg, Fs, (uint8_t *)nullptr, GP, gflp, GQ, gflq, (int *)nullptr)) return rc;
+            }
             if (side) CK(d, cudaEventRecord(d.ev_hi_join, d.hi));
         }
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P1, flp1, pks, n, check);
@@ -1536,7 +1544,7 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
             if (int rc = pipe.h2d(dsig, sigs + c * rsig, m * rsig)) return rc;
             if (int rc = pipe.inputs_ready()) return rc;
             if (int rc = dev_verify_rand(d, variant, dpk, dm, dof, base, dsig, m, group, dseed, (uint64_t)c, rand_bits, ddst, dlen, flags, dok,
-                                         overlap_tail ? pipe.set() : -1))
+                                         overlap_tail ? pipe.set() : -1, ge < ghi /* another chunk follows and hides this tail */))
                 return rc;
             if (int rc = pipe.d2h(ok_groups + g, pin_ok, dok, ge - g)) return rc;
             if (int rc = pipe.end()) return rc;

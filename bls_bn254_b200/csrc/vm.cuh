@@ -371,10 +371,83 @@ struct WDesc {
         return d;
     }
 };
+// ---- lazy linear combinations.  A gather sums up to twelve terms +- [xi] c * slot (c <= 4).  Reducing after every term costs
+// ~30 dependent instructions per term (and a multiplication by xi = 9 + u a lane exchange and four modular operations); here
+// the terms are accumulated UNREDUCED in a signed 288-bit accumulator -- a term is one multiply-add by a small constant, and
+// xi * v = (9 v0 - v1) + (9 v1 + v0) u reads both halves of v from the slot instead of exchanging -- and one reduction ends
+// the gather: add 512 p (every accumulator stays within +- 480 p), estimate the quotient from the top 64 bits, subtract q p,
+// at most two conditional subtractions.
+struct WAcc {
+    uint32_t a[9];
+};
+BN_INL void wacc_zero(WAcc &A) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) A.a[i] = 0;
+}
+// A += (neg ? -1 : 1) * k * v   (two's complement; branch free)
+BN_INL void wacc_mad(WAcc &A, const fp &v, uint32_t k, bool neg) {
+    uint32_t w[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint64_t t = (uint64_t)v.v[i] * k + c;
+        w[i] = (uint32_t)t;
+        c = t >> 32;
+    }
+    w[8] = (uint32_t)c;
+    const uint32_t m = neg ? 0xffffffffu : 0u;
+    uint64_t cc = neg ? 1u : 0u;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint64_t t = (uint64_t)A.a[i] + (w[i] ^ m) + cc;
+        A.a[i] = (uint32_t)t;
+        cc = t >> 32;
+    }
+}
+// the canonical residue of an accumulator within (-512 p, 512 p)
+BN_INL fp wacc_reduce(const WAcc &A) {
+    // D = A + 512 p in (0, 1024 p) < 2^264
+    const uint32_t K512P[9] = {0xf9fa8e00u, 0x41182db0u, 0xe3951a78u, 0x02d522d0u, 0x02b0bb2fu, 0xa08b6d03u, 0x63405370u, 0xc89ce5c2u, 0x00000060u};
+    uint32_t D[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint64_t t = (uint64_t)A.a[i] + K512P[i] + c;
+        D[i] = (uint32_t)t;
+        c = t >> 32;
+    }
+    // q = floor(D / p) or one less: floor(top64(D) * floor(2^64 / (top32(p) + 1)) / 2^64)
+    const uint64_t top = (uint64_t)D[8] << 32 | D[7];
+#if BN_PTX
+    const uint32_t q = (uint32_t)__umul64hi(top, 22721021474ull);
+#else
+    const uint32_t q = (uint32_t)(((unsigned __int128)top * 22721021474ull) >> 64);
+#endif
+    // R = D - q p  in [0, 2p): fits eight words
+    uint32_t R[8];
+    uint64_t mc = 0;
+    int64_t bw = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint64_t t = (uint64_t)p_limb(i) * q + mc;
+        mc = t >> 32;
+        const int64_t dlt = (int64_t)D[i] - (int64_t)(uint32_t)t + bw;
+        R[i] = (uint32_t)dlt;
+        bw = dlt >> 32;      // 0 or -1
+    }
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = R[i];
+    fp_reduce_once(r);
+    fp_reduce_once(r);
+    return r;
+}
 BN_INL int wide_slot(const Env &E, uint32_t d) {
     int s = (int)(d & 1023u);
-    if (d & 0x1000u) s += 3 * E.line;
-    if (d & 0x2000u) s += 6 * E.var;
+    if (d & 0x3000u) {
+        if (d & 0x1000u) s += 3 * E.line;
+        if (d & 0x2000u) s += 6 * E.var;
+    }
     return s;
 }
 BN_INL fp wide_load(const WSlots M, const Env &E, uint32_t d, int half) {
@@ -382,24 +455,26 @@ BN_INL fp wide_load(const WSlots M, const Env &E, uint32_t d, int half) {
     if (s >= W_CONST) return const_half(s - W_CONST, half != 0);
     return M.ldh(s, half);
 }
-// sum of the next n terms: +- [xi] coef * slot
+// sum of the next n terms: +- [xi] coef * slot, this lane's half
 BN_INL fp wide_gather(const WSlots M, const Env &E, WDesc &D, int n, bool odd) {
-    fp acc;
-    fp_set_zero(acc);
+    WAcc A;
+    wacc_zero(A);
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
         const uint32_t d = D.pop();
-        fp v = wide_load(M, E, d, odd ? 1 : 0);
-        if (d & 0x800u) v = wide_xi(v, odd);
-        const int c = (int)(d >> 14);      // coefficient - 1
-        fp t = v;
-        if (c >= 1) fp_dbl(t, v);
-        if (c == 2) fp_add(t, t, v);
-        if (c == 3) fp_dbl(t, t);
-        if (d & 0x400u) fp_sub(acc, acc, t);
-        else fp_add(acc, acc, t);
+        const uint32_t k = (d >> 14) + 1u;
+        const bool neg = (d & 0x400u) != 0;
+        const fp v = wide_load(M, E, d, odd ? 1 : 0);
+        if (d & 0x800u) {
+            // xi * v: even lane 9 v0 - v1, odd lane 9 v1 + v0
+            const fp o = wide_load(M, E, d, odd ? 0 : 1);
+            wacc_mad(A, v, 9u * k, neg);
+            wacc_mad(A, o, k, neg != !odd);
+        } else {
+            wacc_mad(A, v, k, neg);
+        }
     }
-    return acc;
+    return wacc_reduce(A);
 }
 
 BN_NOINL void run(const WSlots M, const Env E, int routine) {
@@ -419,9 +494,10 @@ BN_NOINL void run(const WSlots M, const Env E, int routine) {
             w0 = ins[0];
             WDesc D = {{ins[2], ins[3], ins[4], ins[5], ins[6], ins[7]}};
             const int op = (int)(w0 & 15u);
-            const int nx = (int)((w0 >> 14) & 15u), ny = (int)((w0 >> 18) & 7u), nq = (int)((w0 >> 21) & 3u), nr = (int)((w0 >> 23) & 7u);
+            const int nx = (int)((w0 >> 14) & 15u), ny = (int)((w0 >> 18) & 15u), nq = (int)((w0 >> 22) & 3u), nr = (int)((w0 >> 24) & 7u);
             x = wide_gather(M, E, D, nx, odd);
             if (op == W_MUL) y = ny ? wide_gather(M, E, D, ny, odd) : x;     // no Y terms: a squaring run as a general product
+            else if (op == W_LIN && ny) y = wide_gather(M, E, D, ny, odd);    // linear step xi * (sum X) + (sum Y)
             else if (op == W_MULFP) y = wide_load(M, E, D.pop(), 0);     // the Fp scalar: c0 half, the same for both lanes
             if (nq) q = wide_gather(M, E, D, nq, odd);
             if (nr) r = wide_gather(M, E, D, nr, odd);
@@ -430,12 +506,14 @@ BN_NOINL void run(const WSlots M, const Env E, int routine) {
         if (active) {
             const int op = (int)(w0 & 15u);
             int d = (int)((w0 >> 4) & 1023u);
-            if ((w0 >> 30) & 1u) d += 6 * E.var;
-            const int nq = (int)((w0 >> 21) & 3u), nr = (int)((w0 >> 23) & 7u), dbl = (int)((w0 >> 27) & 3u);
-            const bool xi = (w0 >> 26) & 1u, conjx = (w0 >> 29) & 1u;
+            if ((w0 >> 31) & 1u) d += 6 * E.var;
+            const int ny = (int)((w0 >> 18) & 15u), nq = (int)((w0 >> 22) & 3u), nr = (int)((w0 >> 24) & 7u), dbl = (int)((w0 >> 28) & 3u);
+            const bool xi = (w0 >> 27) & 1u, conjx = (w0 >> 30) & 1u;
             fp p;
             if (op == W_LIN) {
                 p = x;
+                if (xi) p = wide_xi(p, odd);
+                if (ny) fp_add(p, p, y);
 #pragma unroll 1
                 for (int k = 0; k < dbl; k++) fp_dbl(p, p);
                 if (conjx) {

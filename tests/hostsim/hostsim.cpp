@@ -500,6 +500,23 @@ EXPORT void sim_vm_wide(int fam, int fexp, const uint8_t *p0, const uint8_t *q0,
     fp12_to_bytes(out, a.F);
 }
 
+// the wide machine's lazy linear combination: sum_i coef[i] * val[i] mod p through the unreduced accumulator (plain integers in
+// and out, 32 bytes big-endian each; |coef| <= 40, n <= 12 -- the bound the interpreter's gathers stay within)
+EXPORT void sim_wide_lincomb(const uint8_t *vals, const int *coefs, int n, uint8_t *out) {
+    vm::WAcc A;
+    vm::wacc_zero(A);
+    for (int i = 0; i < n; i++) {
+        fp v;
+        fp_raw_from_be(v, vals + 32 * i);
+        vm::wacc_mad(A, v, (uint32_t)(coefs[i] < 0 ? -coefs[i] : coefs[i]), coefs[i] < 0);
+    }
+    fp r = vm::wacc_reduce(A);
+    for (int i = 0; i < 8; i++) {
+        uint8_t *q = out + 4 * (7 - i);
+        q[0] = (uint8_t)(r.v[i] >> 24); q[1] = (uint8_t)(r.v[i] >> 16); q[2] = (uint8_t)(r.v[i] >> 8); q[3] = (uint8_t)r.v[i];
+    }
+}
+
 // ---- G2Prepared: the line tables (wire form as the oracle's orc_g2_prepare) and the two-pair loop fed from them ----------
 EXPORT void sim_g2_prepare(const uint8_t *pt, uint8_t *out) {
     static line_t<fp2> tab[BN254_NUM_LINES];

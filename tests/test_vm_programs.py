@@ -140,3 +140,35 @@ def test_interpreter_on_emulated_lanes_vs_oracle(sim, orc, kats, machine):
     # pairing(g1, g2) == Gt::generator() (pairings.rs:970-980)
     run(0, 1, None, None, orc.g1_generator(), orc.g2_generator(), None, out)
     assert out.raw == b"".join(bytes.fromhex(x) for x in kats["gt_generator"])
+
+
+def test_wide_lazy_linear_combination(sim):
+    """vm.cuh: wacc_mad / wacc_reduce -- the unreduced signed accumulator of the wide machine's gathers and its single reduction
+    (quotient estimate from the top 64 bits) against big integers, at the extremes of the bound (12 terms, |coefficient| <= 40,
+    values 0, 1, p - 1) and at random"""
+    P = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    sim.sim_wide_lincomb.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_char_p]
+    rng = random.Random(31)
+    out = C.create_string_buffer(32)
+
+    def check(vals, coefs):
+        buf = b"".join(v.to_bytes(32, "big") for v in vals)
+        arr = (C.c_int * len(coefs))(*coefs)
+        sim.sim_wide_lincomb(buf, arr, len(coefs), out)
+        assert int.from_bytes(out.raw, "big") == sum(c * v for c, v in zip(coefs, vals)) % P, (vals, coefs)
+
+    check([], [])
+    for v in (0, 1, P - 1):
+        for c in (40, -40, 1, -1):
+            check([v] * 12, [c] * 12)
+            check([v], [c])
+    check([P - 1] * 12, [40, -40] * 6)
+    check([P - 1] * 6 + [0] * 6, [40] * 6 + [-40] * 6)
+    for _ in range(3000):
+        n = rng.randrange(1, 13)
+        vals = [rng.choice((rng.randrange(P), P - 1 - rng.randrange(4), rng.randrange(4))) for _ in range(n)]
+        coefs = [rng.choice((1, -1, 2, -2, 3, 4, 9, -9, 18, 27, 36, -36, 40, -40)) for _ in range(n)]
+        check(vals, coefs)
+    # values whose combination lands next to a multiple of p (quotient estimate one short -> the conditional subtractions)
+    for k in range(1, 400, 7):
+        check([P - 1, 1], [k % 41 or 1, (k * 3) % 41 or 1])

@@ -185,6 +185,8 @@ def fp6_mul(A, out, a, b, extra=None, out_direct_last=True):
 
 def fp12_sqr(A, f):
     """f <- f^2 in place (complex squaring, fp12.rs:170-180): c1 = 2 a b, c0 = (a + b)(a + v b) - ab - v ab"""
+    if getattr(A, "wide", False):
+        return w_fp12_sqr(A, f)
     a, b = f[0:3], f[3:6]
     ab = A.tmp(3)
     fp6_mul(A, ab, [[T(x)] for x in a], [[T(x)] for x in b])
@@ -205,6 +207,8 @@ def fp12_sqr(A, f):
 
 def fp12_mul_by_034(A, f, l0, l3, l4):
     """f <- f * (l0 + l3 w + l4 w^3) in place: the D-twist sparse product, 13 Fp2 products (role of fp12.rs:120-129)"""
+    if getattr(A, "wide", False):
+        return w_fp12_mul_by_034(A, f, l0, l3, l4)
     a, b = f[0:3], f[3:6]
     # B = b * (l3 + l4 v)
     u0, u1 = A.tmp(2)
@@ -235,6 +239,8 @@ def fp12_mul_by_034(A, f, l0, l3, l4):
 def doubling_step(A, Tp, line, sc_px, sc_py):
     """pairings.rs:901-930 on the Jacobian point Tp = (X, Y, Z) in place; line = 3 slots receiving the SCALED coefficients
     (l0 = t0 yP, l3 = t3 xP, l4 = t6: pairings.rs:888-899).  line[0] / line[1] serve as temporaries until the end."""
+    if getattr(A, "wide", False):
+        return w_doubling_step(A, Tp, line, sc_px, sc_py)
     X, Y, Z = Tp
     t0, t1, t3, t4, zs, q = A.tmp(6)
     t2, t5 = line[0], line[1]
@@ -260,6 +266,8 @@ def doubling_step(A, Tp, line, sc_px, sc_py):
 
 def addition_step(A, Tp, qx, qy, line, sc_px, sc_py):
     """pairings.rs:932-962; qx, qy are TERMS (so that -Q costs nothing).  The three line slots host short-lived temporaries."""
+    if getattr(A, "wide", False):
+        return w_addition_step(A, Tp, qx, qy, line, sc_px, sc_py)
     X, Y, Z = Tp
     qx, qy = terms(qx)[0], terms(qy)[0]
     zs, ys, a, b, c, f = A.tmp(6)
@@ -299,6 +307,8 @@ def fixed_line(A, line, cbase, sc_px, sc_py):
 
 def fp12_mul(A, x, y):
     """x <- x * y (fp12.rs:203-210, Karatsuba over Fp6, 18 products); x, y = 6 slots each"""
+    if getattr(A, "wide", False):
+        return w_fp12_mul(A, x, y)
     a, b, c, d = x[0:3], x[3:6], y[0:3], y[3:6]
     aa, bb = A.tmp(3), A.tmp(3)
     fp6_mul(A, aa, [[T(i)] for i in a], [[T(i)] for i in c])
@@ -316,6 +326,8 @@ def fp12_mul(A, x, y):
 
 def cyclotomic_square(A, f):
     """Granger-Scott squaring in the cyclotomic subgroup, in place (pairings.rs:68-115): 9 squarings + 6 linear steps"""
+    if getattr(A, "wide", False):
+        return w_cyclotomic_square(A, f)
     z0, z4, z3, z2, z1, z5 = f
     t0, t1, c1, t2, t3, c3 = A.tmp(6)
     # (z0, z1)
@@ -842,12 +854,12 @@ class WIns:
         terms squares X; the scalar's slot holds (s, 0), so the general product by it is the scalar product)"""
         op = W_MUL if as_mul and self.op in (W_SQR, W_MULFP) else self.op
         nx, ny, nq, nr = len(self.xs), len(self.ys), len(self.q), len(self.r)
-        assert nx <= 12 and ny <= 7 and nq <= 3 and nr <= 7 and nx + ny + nq + nr <= 12 and 0 <= self.dbl <= 3 and 0 <= self.d < 1024
+        assert nx <= 12 and ny <= 12 and nq <= 3 and nr <= 7 and nx + ny + nq + nr <= 12 and 0 <= self.dbl <= 3 and 0 <= self.d < 1024
         if self.op != W_LIN:
             assert all(t.coef == 1 for t in self.xs + self.ys + self.q + self.r)
-        assert not (self.op == W_MUL and ny == 0)
-        w0 = (op | self.d << 4 | nx << 14 | ny << 18 | nq << 21 | nr << 23 | int(self.xi) << 26 | self.dbl << 27 | int(self.conjx) << 29 |
-              int(self.drelv) << 30)
+        assert not (self.op == W_MUL and ny == 0) and not (self.op == W_LIN and (nq or nr))
+        w0 = (op | self.d << 4 | nx << 14 | ny << 18 | nq << 22 | nr << 24 | int(self.xi) << 27 | self.dbl << 28 | int(self.conjx) << 30 |
+              int(self.drelv) << 31)
         desc = [t.half() for t in self.xs + self.ys + self.q + self.r]
         desc += [0] * (12 - len(desc))
         return [w0, 0] + [desc[2 * i] | desc[2 * i + 1] << 16 for i in range(6)]
@@ -855,6 +867,8 @@ class WIns:
 
 class WAsm:
     """the assembler interface of the tower macros, emitting wide-machine instructions"""
+
+    wide = True
 
     def __init__(self, name, nslot, first_tmp):
         self.name, self.ins, self.next_tmp, self.high = name, [], W_TMP, W_TMP
@@ -892,6 +906,25 @@ class WAsm:
         xs = terms(xs)
         assert len(xs) <= 12
         self.ins.append(WIns(W_LIN, d, xs, dbl=dbl, conjx=conj, drelv=drelv))
+
+    def linx(self, d, e, dbl=0):
+        """d = 2^dbl (xi * sum(e.xi) + sum(e.pl)) for a linear expression e (class Lx); one multiplication by xi per instruction"""
+        def split(terms_of):
+            out = []
+            for slot, c in terms_of.items():
+                k, neg = abs(c), c < 0
+                while k:
+                    step = min(k, 4)
+                    out.append(T(slot, neg=neg, coef=step))
+                    k -= step
+            return out
+        xs, ys = split(e.xi), split(e.pl)
+        assert xs or ys
+        if not xs:
+            self.ins.append(WIns(W_LIN, d, ys, dbl=dbl))
+        else:
+            assert len(xs) + len(ys) <= 12
+            self.ins.append(WIns(W_LIN, d, xs, ys, xi=True, dbl=dbl))
 
     def mov(self, d, s): self.lin(d, [T(s)])
     def ldc(self, d, cidx, rel=False): self.lin(d, [T(W_CONST + cidx, rell=rel)])
@@ -977,6 +1010,178 @@ def schedule(ins, units=W_UNITS):
     return bundles
 
 
+class Lx:
+    """linear expression xi * (sum c_i s_i) + (sum c_j s_j) over slots, for WAsm.linx"""
+
+    def __init__(self, pl=None, xi=None):
+        self.pl, self.xi = dict(pl or {}), dict(xi or {})
+
+    @staticmethod
+    def of(slot, c=1):
+        return Lx({slot: c})
+
+    def __add__(self, o):
+        r = Lx(self.pl, self.xi)
+        for src, dst in ((o.pl, r.pl), (o.xi, r.xi)):
+            for k, v in src.items():
+                dst[k] = dst.get(k, 0) + v
+                if dst[k] == 0:
+                    del dst[k]
+        return r
+
+    def __neg__(self): return Lx({k: -v for k, v in self.pl.items()}, {k: -v for k, v in self.xi.items()})
+    def __sub__(self, o): return self + (-o)
+    def __rmul__(self, c): return Lx({k: c * v for k, v in self.pl.items()}, {k: c * v for k, v in self.xi.items()})
+
+    def times_xi(self):
+        assert not self.xi, "xi^2 is not representable"
+        return Lx({}, self.pl)
+
+
+def w_fp6(A, a, b, sparse01=False):
+    """Karatsuba products of the Fp6 product a * b as FRESH slots, all independent; a[i], b[i] are term lists (b[2] = None for a
+    sparse (b0, b1, 0) operand: five products).  Returns the three coefficients as Lx expressions over the product slots."""
+    if sparse01:
+        u0, u1, p0, p1, p2 = A.tmp(5)
+        A.mul(u0, a[0], b[0])
+        A.mul(u1, a[1], b[1])
+        A.mul(p0, add_lists(a[1], a[2]), b[1])
+        A.mul(p1, add_lists(a[0], a[1]), add_lists(b[0], b[1]))
+        A.mul(p2, add_lists(a[0], a[2]), b[0])
+        return [Lx({u0: 1}, {p0: 1, u1: -1}), Lx({p1: 1, u0: -1, u1: -1}), Lx({p2: 1, u0: -1, u1: 1})]
+    v0, v1, v2, m0, m1, m2 = A.tmp(6)
+    A.mul(v0, a[0], b[0])
+    A.mul(v1, a[1], b[1])
+    A.mul(v2, a[2], b[2])
+    A.mul(m0, add_lists(a[1], a[2]), add_lists(b[1], b[2]))
+    A.mul(m1, add_lists(a[0], a[1]), add_lists(b[0], b[1]))
+    A.mul(m2, add_lists(a[0], a[2]), add_lists(b[0], b[2]))
+    return [Lx({v0: 1}, {m0: 1, v1: -1, v2: -1}), Lx({m1: 1, v0: -1, v1: -1}, {v2: 1}), Lx({m2: 1, v0: -1, v2: -1, v1: 1})]
+
+
+def times_v(c):
+    """v * (c0, c1, c2) = (xi c2, c0, c1)"""
+    return [c[2].times_xi(), c[0], c[1]]
+
+
+def w_fp12_sqr(A, f):
+    """f <- f^2 (complex squaring): twelve independent products, then six linear steps straight into f"""
+    a, b = f[0:3], f[3:6]
+    ab = w_fp6(A, [[T(x)] for x in a], [[T(x)] for x in b])
+    s = [[T(a[i]), T(b[i])] for i in range(3)]
+    t = [[T(a[0]), T(b[2]).x()], [T(a[1]), T(b[0])], [T(a[2]), T(b[1])]]
+    st = w_fp6(A, s, t)
+    vab = times_v(ab)
+    for i in range(3):
+        A.linx(a[i], st[i] - ab[i] - vab[i])
+        A.linx(b[i], ab[i], dbl=1)
+
+
+def w_fp12_mul_by_034(A, f, l0, l3, l4):
+    """f <- f * (l0 + l3 w + l4 w^3): thirteen independent products, six linear steps"""
+    a, b = f[0:3], f[3:6]
+    A0 = A.tmp(3)
+    for i in range(3):
+        A.mul(A0[i], a[i], l0)
+    B = w_fp6(A, [[T(x)] for x in b], [[T(l3)], [T(l4)], None], sparse01=True)
+    C = w_fp6(A, [[T(a[i]), T(b[i])] for i in range(3)], [[T(l0), T(l3)], [T(l4)], None], sparse01=True)
+    vB = times_v(B)
+    for i in range(3):
+        A.linx(b[i], C[i] - Lx.of(A0[i]) - B[i])
+    for i in range(3):
+        A.linx(a[i], Lx.of(A0[i]) + vB[i])
+
+
+def w_fp12_mul(A, x, y):
+    """x <- x * y: eighteen independent products, six linear steps"""
+    a, b, c, d = x[0:3], x[3:6], y[0:3], y[3:6]
+    aa = w_fp6(A, [[T(i)] for i in a], [[T(i)] for i in c])
+    bb = w_fp6(A, [[T(i)] for i in b], [[T(i)] for i in d])
+    ss = w_fp6(A, [[T(a[i]), T(b[i])] for i in range(3)], [[T(c[i]), T(d[i])] for i in range(3)])
+    vbb = times_v(bb)
+    for i in range(3):
+        A.linx(b[i], ss[i] - aa[i] - bb[i])
+    for i in range(3):
+        A.linx(a[i], aa[i] + vbb[i])
+
+
+def w_cyclotomic_square(A, f):
+    """Granger-Scott squaring: nine independent squarings, six linear steps (pairings.rs:68-115)"""
+    z0, z4, z3, z2, z1, z5 = f
+    t0, t1, c1, u0, u1, d1, t2, t3, c3 = A.tmp(9)
+    A.sqr(t0, z0)
+    A.sqr(t1, z1)
+    A.sqr(c1, [T(z0), T(z1)])
+    A.sqr(u0, z2)
+    A.sqr(u1, z3)
+    A.sqr(d1, [T(z2), T(z3)])
+    A.sqr(t2, z4)
+    A.sqr(t3, z5)
+    A.sqr(c3, [T(z4), T(z5)])
+    A.linx(z0, Lx({t0: 3, z0: -2}, {t1: 3}))
+    A.linx(z1, Lx({c1: 3, t0: -3, t1: -3, z1: 2}))
+    A.linx(z4, Lx({u0: 3, z4: -2}, {u1: 3}))
+    A.linx(z5, Lx({d1: 3, u0: -3, u1: -3, z5: 2}))
+    A.linx(z2, Lx({z2: 2}, {c3: 3, t2: -3, t3: -3}))
+    A.linx(z3, Lx({t2: 3, z3: -2}, {t3: 3}))
+
+
+def w_doubling_step(A, Tp, line, sc_px, sc_py):
+    """pairings.rs:901-930 with the dependent chain cut to three product levels: every product is written over values that are
+    already there (X, Y, Z and products of earlier levels), the glue is linear steps"""
+    X, Y, Z = Tp
+    t0, t1, zs, zy, t2, t3p, t5, t6p, w3, w0, u, yp = A.tmp(12)
+    A.sqr(t0, X)
+    A.sqr(t1, Y)
+    A.sqr(zs, Z)
+    A.sqr(zy, [T(Z), T(Y)])
+    A.sqr(t2, t1)
+    A.sqr(t3p, [T(t1), T(X)])
+    A.sqr(t5, [3 * T(t0)])
+    A.sqr(t6p, [T(X), 3 * T(t0)])
+    A.mul(w3, t0, zs)                                                   # tmp3 = -6 t0 zs
+    A.mul(w0, [T(zy), -T(t1), -T(zs)], zs)                              # Z' zs
+    A.linx(u, Lx({t3p: 1, t0: -1, t2: -1}))                             # t3 = 2 u
+    A.mul(yp, [6 * T(u), -T(t5)], [3 * T(t0)])                          # (t3 - X') t4
+    A.mulfp(line[0], [2 * T(w0)], sc_py)
+    A.mulfp(line[1], [-6 * T(w3)], sc_px)
+    A.linx(line[2], Lx({t6p: 1, t0: -1, t5: -1, t1: -4}))
+    A.linx(X, Lx({t5: 1, u: -4}))
+    A.linx(Z, Lx({zy: 1, t1: -1, zs: -1}))
+    A.linx(Y, Lx({yp: 1, t2: -8}))
+
+
+def w_addition_step(A, Tp, qx, qy, line, sc_px, sc_py):
+    """pairings.rs:932-962, five product levels; qx, qy are TERMS"""
+    X, Y, Z = Tp
+    qx, qy = terms(qx)[0], terms(qy)[0]
+    zs, ys, bp, a, b, a3, b9, fp, zcp, e, g, zt, t10p, ye, yp = A.tmp(15)
+    A.sqr(zs, Z)
+    A.sqr(ys, qy)
+    A.sqr(bp, [qy, T(Z)])
+    A.mul(a, zs, qx)                                                    # t0
+    A.mul(b, [T(bp), -T(ys), -T(zs)], zs)                               # t1
+    c = [T(a), -T(X)]                                                   # t2
+    f = [T(b), -2 * T(Y)]                                               # t6
+    A.sqr(a3, c)                                                        # t3
+    A.mul(b9, f, qx)                                                    # t9
+    A.sqr(fp, f)
+    A.sqr(zcp, [T(Z)] + c)                                              # (Z + t2)^2
+    A.mul(e, [4 * T(a3)], c)                                            # t5
+    A.mul(g, [4 * T(a3)], X)                                            # t7
+    zn = [T(zcp), -T(zs), -T(a3)]                                       # Z'
+    A.sqr(zt, zn)
+    A.sqr(t10p, [qy] + zn)
+    A.mulfp(line[0], [2 * t for t in zn], sc_py)
+    A.mulfp(line[1], [-2 * T(b), 4 * T(Y)], sc_px)
+    A.mul(ye, Y, e)
+    A.mul(yp, [3 * T(g), T(e), -T(fp)], f)                              # (t7 - X') t6
+    A.linx(line[2], Lx({b9: 2, t10p: -1, ys: 1, zt: 1}))
+    A.linx(X, Lx({fp: 1, e: -1, g: -2}))
+    A.linx(Z, Lx({zcp: 1, zs: -1, a3: -1}))
+    A.linx(Y, Lx({yp: 1, ye: -2}))
+
+
 class WSim(Sim):
     """bundle-level simulator of the wide machine: all units read, then all units write"""
 
@@ -1005,6 +1210,9 @@ class WSim(Sim):
     def result(self, ins):
         if ins.op == W_LIN:
             res = self.total(ins.xs)
+            if ins.xi:
+                res = self.xi(res)
+            res = self.add(res, self.total(ins.ys))
             for _ in range(ins.dbl):
                 res = self.add(res, res)
             return self.conj(res) if ins.conjx else res

@@ -8,7 +8,7 @@ sys.path.insert(0, os.getcwd())
 import bls_bn254_b200 as b
 from bls_bn254_b200 import scheme
 ctx = b.Context([0])
-for n in (1, 256, 512, 768, 1024, 1536):
+for n in (1, 256, 1024, 2048, 3072):
     pks, msgs, sigs, expect = scheme.synth_batch(ctx, n, variant=0, n_keys=min(n, 64), seed=3)
     row = []
     for lanes in (2, 4):
