@@ -619,7 +619,7 @@ def main():
         hpk5, hm5 = torch.from_numpy(pk5.reshape(-1)).pin_memory(), torch.from_numpy(m5.reshape(-1)).pin_memory()
         hof5, hsg5 = torch.from_numpy(of5.view(np.int64)).pin_memory(), torch.from_numpy(sg5.reshape(-1)).pin_memory()
         hok5 = torch.zeros(n5, dtype=torch.uint8).pin_memory()
-        wn = min(n5, 1 << 18)   # warm-up: one chunk (allocates the staging buffers)
+        wn = min(n5, 3 << 18)   # warm-up: three chunks, so that both staging sets (and the overlapped-tail buffers) exist at their final sizes
         ctx.raw("bn254_verify_batch", 0, hpk5.data_ptr(), hm5.data_ptr(), hof5.data_ptr(), hsg5.data_ptr(), wn, b.DST_MIN_SIG, len(b.DST_MIN_SIG), 0, hok5.data_ptr())
         barrier()
         t0 = time.perf_counter()
