@@ -797,7 +797,7 @@ def test_verify_with_prepared_keys(ctx, orc, B, shape):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_fast_aggregate_verify_batch(ctx, orc, B, variant):
+def test_fast_aggregate_verify_batch(ctx, orc, B, variant, shape):
     """bn254_fast_aggregate_verify_batch (FastAggregateVerify of the IETF draft: many signers, one message per group): verdicts
     equal the oracle's -- valid committees accept; an empty key set, an identity key, an undecodable key, a missing signer, a
     tampered message and two keys that cancel reject."""
@@ -835,3 +835,30 @@ def test_fast_aggregate_verify_batch(ctx, orc, B, variant):
         assert got == orc.fast_aggregate_verify_batch(variant, keys, sizes, msgs, sigs, dst, flags=flags), flags
         assert got == bytes([1, 1, 1, 0, 0, 0, 1, 0, 0, 0])
     assert ctx.fast_aggregate_verify_batch(variant, b"", [], [], b"", dst) == b""
+
+
+def test_wide_shape_boundary(ctx, orc, B):
+    """Shape 0 picks the wide (one warp per pairing) kernels for launches of at most "wide_max" pairings and the lane-pair
+    kernels above: both sides of the boundary against the oracle, min-sig and min-pk, standalone pairings and a lone final
+    exponentiation included, and the profiler confirms which kernels ran."""
+    ctx.set_option("wide_max", 40)
+    try:
+        for variant, dst in ((0, B.DST_MIN_SIG), (1, B.DST_MIN_PK)):
+            for n, wide in ((40, True), (41, False)):
+                pks, msgs, sigs, exp = B.scheme.synth_batch(ctx, n, variant=variant, corrupt_every=7)
+                got, names = launched(ctx, lambda: ctx.verify_batch(variant, pks, msgs, sigs, dst))
+                assert got == exp == orc.verify_batch(variant, pks, msgs, sigs, dst, nthreads=8)
+                assert any(x.startswith("k_w_") for x in names) == wide, (variant, n, names)
+                assert any(x.endswith("_l2") for x in names) == (not wide), (variant, n, names)
+        g1, g2 = _points(ctx, orc, 41, 41)
+        gt_w, names = launched(ctx, lambda: ctx.pairing(g1[:64 * 40], g2[:128 * 40]))
+        assert {"k_w_miller1", "k_w_final_exp"} <= names
+        gt_l, names = launched(ctx, lambda: ctx.pairing(g1, g2))
+        assert {"k_miller1_l2", "k_final_exp_l2"} <= names
+        ref = orc.pairing_batch(g1, g2, nthreads=8)
+        assert gt_l == ref and gt_w == ref[:384 * 40]
+        ml = orc.miller_loop_batch(g1[:64], g2[:128])
+        fe, names = launched(ctx, lambda: ctx.final_exponentiation(ml))
+        assert fe == orc.final_exponentiation(ml) and "k_w_final_exp" in names
+    finally:
+        ctx.set_option("wide_max", 1536)
