@@ -341,3 +341,41 @@ def test_pairing_as_written_audit(orc, kats):
     assert g2 != aw.f12_mul(g, g)                                       # e(2P, Q) != e(P, Q)^2
     # the intended function, by contrast, meets the KAT (both oracles)
     assert [c for h in pm.pairing(pm.G1_GEN, pm.G2_GEN) for f2 in h for c in f2] == kat
+
+
+def test_fast_aggregate_verify_in_the_oracle(orc):
+    """orc_fast_aggregate_verify_batch (the checker of bn254_fast_aggregate_verify_batch): a committee on ONE message with the
+    sum of its signatures verifies exactly when the ordinary aggregate predicate does on the repeated message (bilinearity:
+    e(H(m), sum pk) = prod e(H(m), pk_i)), and the KeyValidate cases reject: an empty committee, an identity key, an
+    undecodable key, keys that cancel."""
+    sizes = [1, 4, 0, 3, 2, 2]
+    G = len(sizes)
+    rng = random.Random(17)
+    msgs = [rng.randbytes(rng.choice((0, 9, 32))) for _ in range(G)]
+    keys, sigs = b"", b""
+    id1 = (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+    id2 = bytes(64) + bytes(63) + b"\x01"
+    per_group = []
+    for g, k in enumerate(sizes):
+        sks = [rng.randrange(1, pm.R_ORDER) for _ in range(k)]
+        if g == 5:
+            sks[1] = pm.R_ORDER - sks[0]                 # the aggregate key is the identity
+        sk_b = b"".join(s.to_bytes(32, "big") for s in sks)
+        pk = bytearray(orc.g2_mul(orc.g2_generator() * k, sk_b)) if k else bytearray()
+        agg = orc.g1_sum(orc.g1_mul(orc.hash_to_g1([msgs[g]] * k, DST_SIG), sk_b)) if k else id1
+        if g == 3:
+            pk[128:256] = id2                            # an identity key inside the committee
+        if g == 4:
+            pk[0:128] = b"\xff" * 128                    # an undecodable key
+        per_group.append((bytes(pk), agg))
+        keys += bytes(pk)
+        sigs += agg
+    got = orc.fast_aggregate_verify_batch(0, keys, sizes, msgs, sigs, DST_SIG)
+    assert got == bytes([1, 1, 0, 0, 0, 0])
+    for g in (0, 1):
+        pk, agg = per_group[g]
+        assert orc.aggregate_verify(0, pk, [msgs[g]] * sizes[g], agg, DST_SIG) == 1
+    wrong = list(msgs)
+    wrong[1] = wrong[1] + b"?"
+    assert orc.fast_aggregate_verify_batch(0, keys, sizes, wrong, sigs, DST_SIG) == bytes([1, 0, 0, 0, 0, 0])
+    assert orc.fast_aggregate_verify_batch(0, keys, sizes, msgs, sigs, DST_SIG, flags=3) == got
