@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -118,7 +119,7 @@ struct bn254_ctx {
 struct bn254_g2_prepared {
     bn254_ctx *ctx = nullptr;
     size_t n = 0;
-    std::vector<void *> tab, fl;
+    std::vector<void *> tab, fl, pts;    // per device: line tables, key flags, the decoded keys themselves (g2m)
 };
 
 namespace {
@@ -244,14 +245,12 @@ int launch_check(Dev &d, const char *kernel) {
 // shared memory of a wide-machine CTA running routines [r_lo, r_hi] (host copy of the generated tables)
 inline size_t wide_smem(int r_lo, int r_hi) {
     static uint16_t dir[vm::R_COUNT][2];
-    static std::vector<uint16_t> boff;
-    static bool have = false;
-    if (!have) {
+    static uint16_t boff[sizeof(vm::W_BOFF) / 2];
+    static std::once_flag once;      // a multi-device ctx launches from one host thread per device
+    std::call_once(once, [] {
         cudaMemcpyFromSymbol(dir, vm::W_DIR, sizeof dir);
-        boff.resize(sizeof(vm::W_BOFF) / 2);
-        cudaMemcpyFromSymbol(boff.data(), vm::W_BOFF, sizeof(vm::W_BOFF));
-        have = true;
-    }
+        cudaMemcpyFromSymbol(boff, vm::W_BOFF, sizeof boff);
+    });
     const int i_lo = boff[dir[r_lo][0]], i_hi = boff[dir[r_hi][0] + dir[r_hi][1]];
     return vm::wide_smem_bytes(r_lo, r_hi, BN_W_WARPS, i_lo, i_hi);
 }
@@ -532,7 +531,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
 
 // min-sig verification of one chunk against PREPARED public keys (G2Prepared): decode the signatures, hash, the two-pair loop
 // with both line sequences precomputed (no twist-point arithmetic), final exponentiation, compare
-int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, const uint32_t *key_index, const uint8_t *msgs, const uint64_t *off,
+int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, const g2m *pts, const uint32_t *key_index, const uint8_t *msgs, const uint64_t *off,
                         uint64_t base, const uint8_t *sigs, size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
     const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
     fp12 *F; uint8_t *flf, *flp0, *flp1; g1m *P0, *P1;
@@ -544,7 +543,17 @@ int dev_verify_prepared(Dev &d, const line_t<fp2> *tab, const uint8_t *flk, cons
     if (int rc = ensure_t(d, S_FLP1, n, &flp1)) return rc;
     LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, P0, flp0, sigs, n, check);
     if (int rc = dev_hash_g1(d, P1, flp1, msgs, off, base, n, dst, dst_len, 2)) return rc;
-    LAUNCH_PAIR(d, k_miller2_prep, k_miller2_prep_l2, n, F, flf, P0, flp0, P1, flp1, tab, flk, key_index, n);
+    if (use_wide(d, n)) {
+        // A batch this small is latency bound: the line tables save work, not time.  Fetch the keys of the tuples and run the
+        // ordinary two-pair loop in its wide shape (the same bytes: the table holds exactly the lines that loop computes).
+        g2m *Q1; uint8_t *flq1;
+        if (int rc = ensure_t(d, S_Q1, n, &Q1)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, n, &flq1)) return rc;
+        LAUNCH(d, k_g2_fetch, n, BN_TPB_LIGHT, Q1, flq1, pts, flk, key_index, n);
+        if (int rc = launch_miller2_fixed(d, n, F, flf, P0, flp0, P1, flp1, Q1, flq1)) return rc;
+    } else {
+        LAUNCH_PAIR(d, k_miller2_prep, k_miller2_prep_l2, n, F, flf, P0, flp0, P1, flp1, tab, flk, key_index, n);
+    }
     if (int rc = launch_final_exp(d, F, n)) return rc;
     LAUNCH(d, k_fp12_is_one, n, BN_TPB_LIGHT, ok, F, flf, n);
     return 0;
@@ -1616,8 +1625,11 @@ int bn254_g2_prepare(bn254_ctx *ctx, const uint8_t *pks, size_t n, uint32_t flag
             CK(d, cudaMalloc(&fl, std::max<size_t>(16, n)));
             pr->fl.push_back(fl);
             uint8_t *din; g2m *Q;
+            void *pts = nullptr;
+            CK(d, cudaMalloc(&pts, std::max<size_t>(1, n) * sizeof(g2m)));   // kept: small batches run the ordinary (wide) loop on them
+            pr->pts.push_back(pts);
+            Q = (g2m *)pts;
             if (int r = ensure_t(d, S_IN_A, n * 128 + 16, &din)) return r;
-            if (int r = ensure_t(d, S_Q0, n + 1, &Q)) return r;
             if (n) CK(d, cudaMemcpyAsync(din, pks, n * 128, cudaMemcpyHostToDevice, d.st));
             LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, Q, (uint8_t *)fl, din, n, check);
             if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, (uint8_t *)fl, Q, n);
@@ -1643,6 +1655,7 @@ void bn254_g2_prepared_free(bn254_g2_prepared *pr) {
         cudaSetDevice(pr->ctx->devs[g].id);
         if (pr->tab[g]) cudaFree(pr->tab[g]);
         if (g < pr->fl.size() && pr->fl[g]) cudaFree(pr->fl[g]);
+        if (g < pr->pts.size() && pr->pts[g]) cudaFree(pr->pts[g]);
     }
     delete pr;
 }
@@ -1701,7 +1714,7 @@ int bn254_verify_batch_prepared(bn254_ctx *ctx, const bn254_g2_prepared *pr, con
             if (int rc = pipe.h2d(dki, key_index + c, m * sizeof(uint32_t))) return rc;
             if (int rc = pipe.h2d(dsig, sigs + c * 64, m * 64)) return rc;
             if (int rc = pipe.inputs_ready()) return rc;
-            if (int rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[g], (const uint8_t *)pr->fl[g], dki, dm, dof, base, dsig, m, ddst, dlen, flags, dok))
+            if (int rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[g], (const uint8_t *)pr->fl[g], (const g2m *)pr->pts[g], dki, dm, dof, base, dsig, m, ddst, dlen, flags, dok))
                 return rc;
             if (int rc = pipe.d2h(ok + c, pin_ok, dok, m)) return rc;
             if (int rc = pipe.end()) return rc;
@@ -2126,7 +2139,7 @@ int bn254_verify_batch_prepared_dev(bn254_ctx *ctx, const bn254_g2_prepared *pr,
     if (!pr || pr->ctx != ctx) return fail_arg(ctx, "prepared keys belong to another ctx");
     const uint8_t *ddst; uint32_t dlen;
     int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
-    if (!rc) rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[0], (const uint8_t *)pr->fl[0], key_index, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
+    if (!rc) rc = dev_verify_prepared(d, (const line_t<fp2> *)pr->tab[0], (const uint8_t *)pr->fl[0], (const g2m *)pr->pts[0], key_index, msgs, offsets, 0, sigs, n, ddst, dlen, flags, ok);
     DEV_EPILOGUE(rc);
 }
 int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets,

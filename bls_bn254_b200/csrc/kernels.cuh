@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_prepared_encode(uint8_t *out, 
     fp_to_be(out + 64 * i + 32, c->c1);
 }
 
+// tuple i gets a copy of its prepared key's point and flag (small batches verify through the ordinary loop)
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_g2_fetch(g2m *Q, uint8_t *fl, const g2m *keys, const uint8_t *flk, const uint32_t *key_index, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key_index[i];
+    copy_rec(Q[i], keys[k]);
+    fl[i] = flk[k];
+}
+
 // ---- the slot machine (vm.cuh): a lane pair per pairing, every live value in a shared-memory slot, the tower algebra as
 //      constant-memory programs.  Thread t works on item t / 2 exactly as in the lane-pair kernels above (BN_L2_PROLOGUE).
 //      These kernels assume LIVE pairs (no identity input): an item with a dead pair is recomputed afterwards by the fix-up
