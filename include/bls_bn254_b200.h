@@ -27,8 +27,9 @@
  * (cudaHostAlloc / cudaHostRegister / bn254_host_register) make every copy asynchronous; pageable
  * buffers work and are staged.  "_dev" entry points take device pointers resident on the ctx's FIRST device.
  *
- * Latency note: a lone verification through this library takes ~9 ms (a single pairing is a latency-
- * bound chain of ~17 000 dependent field multiplications; a CPU core does it in ~2 ms).  The library
+ * Latency note: a lone verification through this library takes ~4 ms (a single pairing is a latency-
+ * bound chain of ~17 000 dependent field multiplications; launches of at most "wide_max" = 1536 pairings
+ * give each pairing a whole warp, which cuts the chain 2-3 x; a CPU core does it in ~2 ms).  The library
  * is for batches: throughput saturates from ~2^14 tuples per call.
  *
  * Identity policy of the verification predicates: a public key or (per-tuple) signature that decodes
