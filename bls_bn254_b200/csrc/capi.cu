@@ -108,10 +108,9 @@ struct bn254_ctx {
     std::string err;
     size_t chunk = (size_t)1 << 18;  // items staged per host<->device round
     bool chunk_is_default = true;    // not set through BN254_CHUNK / bn254_ctx_set_option
-    // Exact per-tuple verification streams chunks of exactly one wave of the lane-pair kernels (66 304 tuples on 148 SMs):
-    // that shape is the faster one (+4 % over one thread per pairing at 2^18), and with the double-buffered pipeline the
-    // chunk size no longer matters for the copies.  The randomised path keeps 2^18 (its twin kernels want big batches).
-    size_t verify_chunk(const Dev &d) const { return chunk_is_default && d.shape == 0 ? std::min(chunk, d.lane_wave_threads / 2) : chunk; }
+    // Chunks of the verification entry points: 2^18 tuples, i.e. four waves of the lane-pair kernels (several waves per launch
+    // backfill the SMs as early warps finish: 2.23 M verifications/s against 2.17 M for one-wave chunks).
+    size_t verify_chunk(const Dev &) const { return chunk; }
 };
 
 // G2Prepared for a set of public keys: per device of the ctx the 88 line triples of every key (16 896 bytes per key) and one
@@ -199,14 +198,15 @@ int launch_check(Dev &d, const char *kernel) {
         }                                                                        \
     } while (0)
 
-// Pairing kernels come in two bit-identical shapes: one thread per pairing, and two lanes per pairing
-// (lane-split Fp2, tower.cuh: half the per-thread state, twice the warps).  Measured on B200: the lane
-// pair wins while the batch does not fill the machine with one thread per item (2^14: +10 %, 2^16:
-// +4 %), the two are level beyond.  d.shape = 0 (default) picks per launch: lanes while 2n threads fit
-// one wave of the lane kernels; 1 / 2 force a shape (BN254_LANES, bn254_ctx_set_option).
+// Pairing kernels come in bit-identical shapes: one thread per pairing, and two lanes per pairing (lane-split Fp2, tower.cuh:
+// half the per-thread state, twice the warps).  d.shape = 0 (default) runs the lane pair at every size: it wins below one
+// wave because one thread per item leaves the machine under-occupied (2^14: +19 %, 2^16: +8 %) and, measured on the final
+// build, also beyond (2^18 items per launch: two-pair loop +5 %, one-pair loop +10 %, final exponentiation +5 %, twin loop
+// +4 %; 2^20: verification +5.5 %).  1 / 2 force a shape (BN254_LANES, bn254_ctx_set_option) so that the parity suite meets
+// the one-thread kernels too.
 #define LAUNCH_PAIR(d, kscalar, klane, n, ...)                                              \
     do {                                                                                    \
-        if ((d).shape == 2 || ((d).shape == 0 && 2 * (size_t)(n) <= (d).lane_wave_threads))   \
+        if ((d).shape != 1)                                                                 \
             LAUNCH(d, klane, 2 * (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                   \
         else                                                                                \
             LAUNCH(d, kscalar, (size_t)(n), BN_TPB_HEAVY, __VA_ARGS__);                     \

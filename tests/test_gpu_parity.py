@@ -438,9 +438,18 @@ def test_randomized_batch_verify_full_size(ctx, orc, B):
     assert ctx.verify_batch_randomized(0, pks, msgs, tail, B.DST_MIN_SIG, bytes(32), group=g)[i // g] == 0
 
 
-def test_randomized_and_aggregate_beyond_one_lane_wave(ctx, B):
-    """140 001 tuples: more than the lane-pair kernels hold in one wave, so the randomised and aggregate paths run the
-    one-thread shape of the twin kernel (two tuples per thread, odd tail).  Valid groups accept, the groups of two
+@pytest.fixture(params=[0, 1], ids=["default-shape", "one-thread"])
+def big_shape(request, ctx):
+    """Big batches run several waves of the lane-pair kernels by default; "lanes" = 1 forces the one-thread kernels
+    (k_miller2_fixed, k_miller2, k_miller1, k_miller_twin, k_final_exp) so that they meet the oracle at these sizes too."""
+    ctx.set_option("lanes", request.param)
+    yield request.param
+    ctx.set_option("lanes", 0)
+
+
+def test_randomized_and_aggregate_beyond_one_lane_wave(ctx, B, big_shape):
+    """140 001 tuples: more than the lane-pair kernels hold in one wave; the randomised and aggregate paths run the twin
+    kernel (two tuples per thread / lane pair, odd tail) in both shapes.  Valid groups accept, the groups of two
     corrupted tuples reject, and the aggregate product equals, byte for byte, the product of shards that take other kernels."""
     n = 140001
     pks, msgs, sigs, _ = B.scheme.synth_batch(ctx, n, variant=0, n_keys=128, corrupt_every=0)
@@ -625,11 +634,11 @@ def test_aggregate_verify_honours_the_validation_flags(ctx, orc, B):
 
 
 def test_verify_c5_shape(orc, B):
-    """The shapes BASELINE config 5 (2^24 tuples) runs through the double-buffered host pipeline.  By default exact
-    verification streams chunks of one wave of lane pairs (66 304 tuples: k_miller2_fixed_l2, k_final_exp_l2); with the chunk
-    set to 2^18 every full chunk runs one thread per pairing (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097: accept bytes
-    equal the construction in both, a 512-tuple slice straddling a chunk boundary equals the oracle, and the profiler confirms
-    which kernels launched.  Pageable and pinned result buffers take different copy paths."""
+    """The shapes BASELINE config 5 (2^24 tuples) runs through the double-buffered host pipeline: chunks of 2^18 tuples, by
+    default four waves of the lane-pair kernels (k_miller2_fixed_l2, k_final_exp_l2); with "lanes" = 1 one thread per pairing
+    (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097: accept bytes equal the construction in both, a 512-tuple slice
+    straddling the chunk boundary equals the oracle, and the profiler confirms which kernels launched.  Pageable and pinned
+    result buffers take different copy paths."""
     import numpy as np
     import torch
     c = B.Context([0])
@@ -639,11 +648,11 @@ def test_verify_c5_shape(orc, B):
         (got), names = launched(c, lambda: c.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG))
         assert got == exp
         assert {"k_miller2_fixed_l2", "k_final_exp_l2", "k_hash_g1"} <= names and "k_miller2_fixed" not in names
-        c.set_option("chunk", 1 << 18)
+        c.set_option("lanes", 1)
         (got), names = launched(c, lambda: c.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG))
+        c.set_option("lanes", 0)
         assert got == exp
-        # the full chunk runs one thread per pairing; the 4097-tuple tail fits one wave of lane pairs and takes that shape
-        assert {"k_miller2_fixed", "k_final_exp", "k_hash_g1", "k_miller2_fixed_l2", "k_final_exp_l2"} <= names
+        assert {"k_miller2_fixed", "k_final_exp", "k_hash_g1"} <= names and not any(x.endswith("_l2") for x in names)
         lo = (1 << 18) - 256
         ref = orc.verify_batch(0, pks[128 * lo:128 * (lo + 512)], msgs[lo:lo + 512], sigs[64 * lo:64 * (lo + 512)], B.DST_MIN_SIG, nthreads=orc.ncpu())
         assert got[lo:lo + 512] == ref
@@ -667,7 +676,7 @@ def test_verify_c5_shape(orc, B):
         c.close()
 
 
-def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B):
+def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B, big_shape):
     """70 001 pairings: more than one wave of lane pairs, so pairing_batch / miller_loop_batch / final_exponentiation run
     k_miller1 and k_final_exp (one thread per item).  Samples from the head, the middle and the ragged tail against the
     oracle; the profiler confirms which kernels ran."""
@@ -681,7 +690,10 @@ def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B):
     g1 = b"".join(b1[64 * k:64 * k + 64] for k in idx)
     g2 = b"".join(b2[128 * k:128 * k + 128] for k in jdx)
     (gt, st), names = launched(ctx, lambda: ctx.pairing(g1, g2, want_status=True))
-    assert {"k_miller1", "k_final_exp"} <= names and not any(x.endswith("_l2") for x in names)
+    if big_shape == 1:
+        assert {"k_miller1", "k_final_exp"} <= names and not any(x.endswith("_l2") for x in names)
+    else:
+        assert {"k_miller1_l2", "k_final_exp_l2"} <= names and "k_miller1" not in names
     assert st == b"\x01" * n
     for lo in (0, 35000, n - 40):
         sl = slice(lo, lo + 40)
@@ -691,16 +703,16 @@ def test_pairing_and_final_exp_beyond_one_wave(ctx, orc, B):
     lo = n - 33
     assert ml[384 * lo:] == orc.miller_loop_batch(g1[64 * lo:], g2[128 * lo:], nthreads=8)
     fe, names = launched(ctx, lambda: ctx.final_exponentiation(ml))
-    assert "k_final_exp" in names
+    assert ("k_final_exp" if big_shape == 1 else "k_final_exp_l2") in names
     assert fe == gt
-    # min-pk verification in one chunk of this size: k_miller2 (both pairs variable, one thread per item)
+    # min-pk verification in one chunk of this size: k_miller2 / k_miller2_l2 (both pairs variable)
     m = 66400
     c = B.Context([0])
     try:
-        c.set_option("chunk", 1 << 18)
+        c.set_option("lanes", big_shape)
         pks, vm, sigs, exp = B.scheme.synth_batch(c, m, variant=1, n_keys=32)
         got, names = launched(c, lambda: c.verify_batch(1, pks, vm, sigs, B.DST_MIN_PK))
-        assert got == exp and "k_miller2" in names and "k_hash_g2" in names
+        assert got == exp and ("k_miller2" if big_shape == 1 else "k_miller2_l2") in names and "k_hash_g2" in names
         lo = m - 48
         assert got[lo:] == orc.verify_batch(1, pks[64 * lo:], vm[lo:], sigs[128 * lo:], B.DST_MIN_PK, nthreads=8)
     finally:
