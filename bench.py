@@ -647,7 +647,7 @@ def main():
             assert ref == bytes(hok5[lo:lo + k5].numpy()), "c5: accept bits differ from the oracle"
             check = "all accept bytes equal the construction; %d tuples straddling the first chunk boundary byte-equal to the oracle" % k5
         sub["c5"] = {"config": "batch verify 2^%d independent (pk, msg, sig) tuples in total (min-sig, %d keys, 1/%d corrupted) sharded over %d rank(s), "
-                               "through bn254_verify_batch[_randomized] on pinned host buffers: chunks of 2^18 tuples (four waves of the lane-pair kernels), "
+                               "through bn254_verify_batch[_randomized] on pinned host buffers: chunks of one lane-pair wave (66 304 tuples = one 896-thread CTA per SM; randomised: 2^18), "
                                "upload / kernels / download overlapped on two staging sets" %
                                (args.c5_log2n, N_KEYS, CORRUPT_EVERY, world),
                      "tuples_total": n5_total, "tuples_per_rank": n5, "scaling": "strong",

@@ -119,7 +119,13 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_g2_require_subg
 #ifndef BN_MINB_HASH1
 #define BN_MINB_HASH1 16
 #endif
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HASH1) k_hash_g1(g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
+#ifndef BN_TPB_HASH1
+#define BN_TPB_HASH1 BN_TPB_HEAVY
+#endif
+#ifndef BN_TPB_HASH2
+#define BN_TPB_HASH2 BN_TPB_HEAVY
+#endif
+__global__ void __launch_bounds__(BN_TPB_HASH1, BN_MINB_HASH1) k_hash_g1(g1m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                                                            size_t n, const uint8_t *dst, uint32_t dst_len, int count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HASH1) k_hash_g1(g1m *ou
 #ifndef BN_MINB_HASH2
 #define BN_MINB_HASH2 BN_MINB_HEAVY
 #endif
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HASH2) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
+__global__ void __launch_bounds__(BN_TPB_HASH2, BN_MINB_HASH2) k_hash_g2(g2m *out, uint8_t *fl, const uint8_t *msgs, const uint64_t *off, uint64_t base,
                                                            size_t n, const uint8_t *dst, uint32_t dst_len, int count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -210,15 +216,22 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_FEXP) k_final_exp(fp12 *
 // ---- two lanes per pairing (lane-split Fp2): thread t works on item t/2, lane parity t&1.  A warp
 //      whose 16 items are all out of range exits as a whole; in the last partial warp the idle pairs
 //      recompute the last item (identical bytes are stored) so that every pair stays convergent.
+// Lane-pair pairing kernels: 72 registers, 896 resident threads per SM (2 x 2^16 threads are one wave on 148 SMs).  They are
+// compiled for CTAs of UP TO 896 threads and launched with ONE CTA per SM wherever the batch allows (capi.cu: lane_tpb): the 28
+// warps of such a CTA land 7 on every scheduler, while fourteen 64-thread CTAs per SM are spread unevenly -- measured per 2^16
+// verifications: 64 x 14 CTAs 30.25 ms, 224 x 4 30.44, 448 x 2 29.26, 896 x 1 28.18 ms.
+#ifndef BN_TPB_L2
+#define BN_TPB_L2 896
+#endif
 #ifndef BN_MINB_L2
-#define BN_MINB_L2 14   // 72 registers: 2 x 2^16 threads are exactly one wave on 148 SMs
+#define BN_MINB_L2 1
 #endif
 #define BN_L2_PROLOGUE()                                                 \
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;            \
     if (((t & ~(size_t)31) >> 1) >= n) return;                           \
     size_t i = t >> 1;                                                   \
     if (i >= n) i = n - 1;
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller1_l2(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_miller1_l2(fp12 *F, uint8_t *flF, const g1m *P, const uint8_t *flP, const g2m *Q,
                                                                            const uint8_t *flQ, size_t n, int *bad) {
     BN_L2_PROLOGUE();
     uint8_t fl;
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller1_l2(fp12 *F
     if (flF) flF[i] = fl;
     if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_fixed_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0,
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_miller2_fixed_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0,
                                                                                  const g1m *P1, const uint8_t *flP1, const g2m *Q1,
                                                                                  const uint8_t *flQ1, size_t n) {
     BN_L2_PROLOGUE();
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_fixed_l2(f
     item_miller2_l2<true>(F[i], fl, P0[i], flP0[i], nullptr, 0, P1[i], flP1[i], Q1[i], flQ1[i]);
     flF[i] = fl;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride,
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_miller2_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, size_t p0_stride,
                                                                            const g2m *Q0, const uint8_t *flQ0, const g1m *P1, const uint8_t *flP1,
                                                                            const g2m *Q1, const uint8_t *flQ1, size_t n) {
     BN_L2_PROLOGUE();
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_l2(fp12 *F
     item_miller2_l2<false>(F[i], fl, P0[i * p0_stride], flP0[i * p0_stride], &Q0[i], flQ0[i], P1[i], flP1[i], Q1[i], flQ1[i]);
     flF[i] = fl;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_final_exp_l2(fp12 *F, size_t n) {
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_final_exp_l2(fp12 *F, size_t n) {
     BN_L2_PROLOGUE();
     item_final_exp_l2(F[i]);
 }
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller2_prep(fp
     copy_rec(F[i], f);
     flF[i] = fl;
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller2_prep_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_miller2_prep_l2(fp12 *F, uint8_t *flF, const g1m *P0, const uint8_t *flP0, const g1m *P1,
                                                                                 const uint8_t *flP1, const line_t<fp2> *tab, const uint8_t *flK,
                                                                                 const uint32_t *key_index, size_t n) {
     BN_L2_PROLOGUE();
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_miller_twin(fp1
     copy_rec(F[t], f);
     if (bad && (fl & FL_BAD)) atomicOr(bad, 1);
 }
-__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_L2) k_miller_twin_l2(fp12 *F, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
+__global__ void __launch_bounds__(BN_TPB_L2, BN_MINB_L2) k_miller_twin_l2(fp12 *F, const g1m *P, const uint8_t *flP, const g2m *Q, const uint8_t *flQ,
                                                                                size_t n, int *bad) {
     size_t th = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t m = (n + 1) / 2;                       // records written

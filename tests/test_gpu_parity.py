@@ -634,9 +634,9 @@ def test_aggregate_verify_honours_the_validation_flags(ctx, orc, B):
 
 
 def test_verify_c5_shape(orc, B):
-    """The shapes BASELINE config 5 (2^24 tuples) runs through the double-buffered host pipeline: chunks of 2^18 tuples, by
-    default four waves of the lane-pair kernels (k_miller2_fixed_l2, k_final_exp_l2); with "lanes" = 1 one thread per pairing
-    (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097: accept bytes equal the construction in both, a 512-tuple slice
+    """The shapes BASELINE config 5 (2^24 tuples) runs through the double-buffered host pipeline: by default chunks of one wave
+    of the lane-pair kernels (66 304 tuples: k_miller2_fixed_l2, k_final_exp_l2, one 896-thread CTA per SM); with "lanes" = 1
+    chunks of 2^18 tuples, one thread per pairing (k_miller2_fixed, k_final_exp).  n = 2^18 + 4097: accept bytes equal the construction in both, a 512-tuple slice
     straddling the chunk boundary equals the oracle, and the profiler confirms which kernels launched.  Pageable and pinned
     result buffers take different copy paths."""
     import numpy as np
