@@ -80,6 +80,8 @@ def lib():
             getattr(L, name).argtypes = [vp, C.c_int, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp, C.c_int, sz, vp]
         L.bn254_aggregate_partial.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, sz, C.c_uint32, vp, vp]
         L.bn254_fast_aggregate_verify_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, sz, vp, sz, C.c_uint32, vp]
+        for name in ("bn254_verify_same_key_randomized", "bn254_verify_same_key_randomized_dev"):
+            getattr(L, name).argtypes = [vp, C.c_int, vp, vp, sz, vp, vp, vp, vp, sz, C.c_uint32, vp, C.c_int, vp]
         L.bn254_g2_prepare.argtypes = [vp, vp, sz, C.c_uint32, C.POINTER(vp)]
         L.bn254_g2_prepared_free.argtypes = [vp]
         L.bn254_g2_prepared_free.restype = None
@@ -113,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "bn254_device_count", "bn254_ctx_create", "bn254_ctx_destroy", "bn254_last_error", "bn254_launch_count", "bn254_stream", "bn254_sync", "bn254_profile_enable", "bn254_profile_drain",
     "bn254_ctx_set_option", "bn254_host_register", "bn254_host_unregister", "bn254_comm_unique_id", "bn254_comm_init_rank", "bn254_comm_nranks",
     "bn254_aggregate_verify_dist", "bn254_aggregate_verify_dist_dev",
-    "bn254_fast_aggregate_verify_batch",
+    "bn254_fast_aggregate_verify_batch", "bn254_verify_same_key_randomized", "bn254_verify_same_key_randomized_dev",
     "bn254_g2_prepare", "bn254_g2_prepared_free", "bn254_g2_prepared_count", "bn254_g2_prepared_export", "bn254_verify_batch_prepared", "bn254_verify_batch_prepared_dev",
     "bn254_hash_to_g1", "bn254_encode_to_g1", "bn254_hash_to_g2", "bn254_encode_to_g2",
     "bn254_pairing_batch", "bn254_miller_loop_batch", "bn254_multi_miller_loop", "bn254_final_exponentiation", "bn254_fp12_product",

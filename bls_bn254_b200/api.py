@@ -269,6 +269,31 @@ class Context:
                                                            len(dst), flags, _ptr(ok)))
         return ok.raw[:n]
 
+    def verify_same_key_randomized(self, variant, pks, msg_counts, msgs, sigs, dst, seed, rand_bits=64, flags=0):
+        """Same-key randomised verification: key k owns the next msg_counts[k] (message, signature) tuples and gets ONE accept
+        byte (one Miller loop and one final exponentiation per KEY; per tuple a hash and two short scalar multiplications).
+        `seed` = 32 bytes the signers cannot predict."""
+        blob, off, n = _msgs(msgs)
+        rpk, rsig = self._recs(variant)
+        nk = len(msg_counts)
+        if len(pks) != rpk * nk:
+            raise Bn254Error(-3 if variant == MIN_SIG else -2, "public-key buffer length")
+        if sum(msg_counts) != n or len(sigs) != rsig * n:
+            raise Bn254Error(-10, "msg_counts must add up to the number of messages, one signature per message")
+        if len(seed) != 32:
+            raise Bn254Error(-10, "seed must be 32 bytes")
+        koff = (C.c_uint64 * (nk + 1))()
+        for i, k in enumerate(msg_counts):
+            koff[i + 1] = koff[i] + k
+        ok = C.create_string_buffer(max(1, nk))
+        self._ck(self._L.bn254_verify_same_key_randomized(self._h, variant, _ptr(pks), _ptr(koff), nk, _ptr(blob), _ptr(off), _ptr(sigs), _ptr(dst),
+                                                          len(dst), flags, _ptr(seed), rand_bits, _ptr(ok)))
+        return ok.raw[:nk]
+
+    def verify_same_key_randomized_dev(self, variant, pks, key_offsets_host, n_keys, msgs, offsets, sigs, dst, dst_len, flags, seed, rand_bits, ok):
+        self._ck(self._L.bn254_verify_same_key_randomized_dev(self._h, variant, pks, key_offsets_host, n_keys, msgs, offsets, sigs, dst, dst_len, flags,
+                                                              seed, rand_bits, ok))
+
     def g2_prepare(self, pks, flags=0):
         """G2Prepared::from for n min-sig public keys (n x 128 bytes): prepare once, verify many (verify_batch_prepared).
         `flags` = validation of the keys (CHECK_ON_CURVE / CHECK_SUBGROUP); identity keys are unusable either way."""

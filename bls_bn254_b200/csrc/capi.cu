@@ -769,6 +769,133 @@ int dev_verify_rand(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs
     return 0;
 }
 
+// ---- same-key randomised verification ("same-key grouping") ------------------------------------------
+// Reduction plan of one chunk, computed on the host from the key offsets: a blob of u64 arrays -- the nk + 1 key offsets relative
+// to the chunk, then per level the nb + 1 bounds of its blocks (fan-in BN_SEG_FAN, a block never straddles two keys, a key
+// without tuples has no block), last the nk + 1 offsets of the keys' final records.
+struct SkPlan {
+    struct Level { size_t pos, nb; };
+    std::vector<uint64_t> blob;
+    std::vector<Level> levels;
+    size_t kfin_pos = 0, nfin = 0, nb_max[2] = {0, 0};   // nb_max[j]: most blocks among the levels written to ping-pong buffer j
+};
+void sk_plan(SkPlan &p, const uint64_t *koff, size_t nk) {
+    const uint64_t t0 = koff[0];
+    std::vector<uint64_t> cur(nk + 1), nxt(nk + 1);
+    for (size_t k = 0; k <= nk; k++) cur[k] = koff[k] - t0;
+    p.blob.assign(cur.begin(), cur.end());
+    for (;;) {
+        uint64_t longest = 0;
+        for (size_t k = 0; k < nk; k++) longest = std::max(longest, cur[k + 1] - cur[k]);
+        if (longest <= 1) break;
+        SkPlan::Level L;
+        L.pos = p.blob.size();
+        nxt[0] = 0;
+        for (size_t k = 0; k < nk; k++) {
+            for (uint64_t s = cur[k]; s < cur[k + 1]; s += BN_SEG_FAN) p.blob.push_back(s);
+            nxt[k + 1] = nxt[k] + (cur[k + 1] - cur[k] + BN_SEG_FAN - 1) / BN_SEG_FAN;
+        }
+        p.blob.push_back(cur[nk]);
+        L.nb = (size_t)nxt[nk];
+        size_t &m = p.nb_max[p.levels.size() & 1];
+        m = std::max(m, L.nb);
+        p.levels.push_back(L);
+        cur.swap(nxt);
+    }
+    p.kfin_pos = p.blob.size();
+    p.blob.insert(p.blob.end(), cur.begin(), cur.end());
+    p.nfin = (size_t)cur[nk];
+}
+// One chunk of whole keys (device pointers; `plan` = the uploaded blob of `hp`): nk keys, their n tuples -> nk accept bytes.
+//   min-sig: e(sum r_i sig_i, -g2) * e(sum r_i H(m_i), pk_k) == 1        min-pk: e(-g1, sum r_i sig_i) * e(pk_k, sum r_i H(m_i)) == 1
+// Per tuple: decode, hash, two GLV scalings; per key: the two sums, ONE two-pair Miller loop and ONE final exponentiation --
+// the exact predicate's own kernels on (pk_k, sum r_i H(m_i), sum r_i sig_i).  idx0 = index of the chunk's first tuple in the call.
+int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, const uint64_t *plan, const SkPlan &hp, const uint8_t *msgs,
+                        const uint64_t *off, uint64_t base, const uint8_t *sigs, size_t n, const uint8_t *seed, uint64_t idx0, int nbits,
+                        const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+    const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
+    const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
+    fp12 *F; uint8_t *flf, *fla, *flb, *flka, *flkb, *flpk;
+    int *kbad;
+    if (int rc = ensure_t(d, S_F, nk, &F)) return rc;
+    if (int rc = ensure_t(d, S_FLF, nk, &flf)) return rc;
+    if (int rc = ensure_t(d, S_RB_BAD, nk, &kbad)) return rc;
+    if (int rc = ensure_t(d, S_RB_FLP, nk, &flka)) return rc;
+    if (int rc = ensure_t(d, S_FLTMP, nk + 1, &flkb)) return rc;
+    CK(d, cudaMemsetAsync(kbad, 0, nk * sizeof(int), d.cur));
+    const uint64_t *ko = plan, *kfin = plan + hp.kfin_pos;
+    if (variant == BN254_MIN_SIG) {
+        g1m *A, *B, *KA, *KB; g2m *PK; g1p *S, *SA, *SB;
+        if (int rc = ensure_t(d, S_P0, n, &A)) return rc;
+        if (int rc = ensure_t(d, S_FLP0, n, &fla)) return rc;
+        if (int rc = ensure_t(d, S_P1, n, &B)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, n, &flb)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
+        if (int rc = ensure_t(d, S_RB_GP, nk, &KA)) return rc;
+        if (int rc = ensure_t(d, S_TMP, (nk + 1) * sizeof(g1m), (uint8_t **)&KB)) return rc;
+        if (int rc = ensure_t(d, S_Q1, nk, &PK)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, nk, &flpk)) return rc;
+        LAUNCH(d, k_g2_decode, nk, BN_TPB_LIGHT, PK, flpk, pks, nk, check);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, nk, BN_TPB_HEAVY, flpk, PK, nk);
+        const g1p *src = S;
+        if (n) {
+            LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, A, fla, sigs, n, check);
+            if (int rc = dev_hash_g1(d, B, flb, msgs, off, base, n, dst, dst_len, 2)) return rc;
+            LAUNCH(d, k_sk_key_flags, n, BN_TPB_LIGHT, kbad, fla, flb, ko, nk, n);
+            LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
+            LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
+            size_t n_in = n;
+            for (size_t l = 0; l < hp.levels.size(); l++) {
+                g1p *out = (l & 1) ? SB : SA;
+                LAUNCH(d, k_sk_sum_g1p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
+                src = out;
+                n_in = hp.levels[l].nb;
+            }
+        }
+        LAUNCH(d, k_sk_finish_g1, nk, BN_TPB_HEAVY, KA, flka, KB, flkb, src, kfin, kbad, nk);
+        if (int rc = launch_miller2_fixed(d, nk, F, flf, KA, flka, KB, flkb, PK, flpk)) return rc;
+    } else {
+        g2m *A, *B, *KA, *KB; g1m *PK; g2p *S, *SA, *SB;
+        const g1m *ng1; const uint8_t *flc;
+        if (int rc = ensure_t(d, S_Q0, n, &A)) return rc;
+        if (int rc = ensure_t(d, S_FLQ0, n, &fla)) return rc;
+        if (int rc = ensure_t(d, S_Q1, n, &B)) return rc;
+        if (int rc = ensure_t(d, S_FLQ1, n, &flb)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
+        if (int rc = ensure_t(d, S_RB_GQ, nk, &KA)) return rc;
+        if (int rc = ensure_t(d, S_TMP, (nk + 1) * sizeof(g2m), (uint8_t **)&KB)) return rc;
+        if (int rc = ensure_t(d, S_P1, nk, &PK)) return rc;
+        if (int rc = ensure_t(d, S_FLP1, nk, &flpk)) return rc;
+        if (int rc = neg_g1_const(d, &ng1, &flc)) return rc;
+        LAUNCH(d, k_g1_decode, nk, BN_TPB_LIGHT, PK, flpk, pks, nk, check);
+        const g2p *src = S;
+        if (n) {
+            LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, A, fla, sigs, n, check);
+            if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, fla, A, n);
+            if (int rc = dev_hash_g2(d, B, flb, msgs, off, base, n, dst, dst_len, 2)) return rc;
+            LAUNCH(d, k_sk_key_flags, n, BN_TPB_LIGHT, kbad, fla, flb, ko, nk, n);
+            LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
+            LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
+            size_t n_in = n;
+            for (size_t l = 0; l < hp.levels.size(); l++) {
+                g2p *out = (l & 1) ? SB : SA;
+                LAUNCH(d, k_sk_sum_g2p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
+                src = out;
+                n_in = hp.levels[l].nb;
+            }
+        }
+        LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, KA, flka, KB, flkb, src, kfin, kbad, nk);
+        if (int rc = launch_miller2(d, nk, F, flf, ng1, flc, (size_t)0, KA, flka, PK, flpk, KB, flkb)) return rc;
+    }
+    if (int rc = launch_final_exp(d, F, nk)) return rc;
+    LAUNCH(d, k_fp12_is_one, nk, BN_TPB_LIGHT, ok, F, flf, nk);
+    return 0;
+}
+
 // One shard of an aggregate verification (device pointers): rec->f = prod_i ML(H(m_i), pk_i) [* ML(aggsig, -g2) when
 // agg_sig != NULL] in internal form, rec->bad = a key was undecodable / the identity / failed the requested checks, or a
 // message hit the SvdW exception.  The last pass of the product tree writes rec->f in place (rec may be the NCCL send
@@ -1573,6 +1700,63 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
     });
 }
 
+// Same-key randomised verification: key k owns the tuples [key_offsets[k], key_offsets[k+1]) of msgs / sigs and gets one accept
+// byte.  Keys (with their tuples) are what the devices share out and what the chunk pipeline streams; a key is never split, so
+// the scratch grows to the largest key (~0.5 KB of device memory per tuple).
+int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets, size_t n_keys,
+                                     const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs, const uint8_t *dst, size_t dst_len,
+                                     uint32_t flags, const uint8_t *seed, int rand_bits, uint8_t *ok_keys) {
+    if (!ctx) return BN254_ERR_ARG;
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (rand_bits != 64 && rand_bits != 128) return fail_arg(ctx, "rand_bits must be 64 or 128");
+    if (n_keys == 0) return 0;
+    if (!pks || !key_offsets || !seed || !ok_keys) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, key_offsets, n_keys)) return rc;
+    const size_t n_tuples = (size_t)key_offsets[n_keys];
+    if (n_tuples && (!offsets || !sigs)) return fail_arg(ctx, "null pointer");
+    if (n_tuples)
+        if (int rc = check_offsets(ctx, offsets, n_tuples)) return rc;
+    const size_t rpk = variant == BN254_MIN_SIG ? 128 : 64, rsig = variant == BN254_MIN_SIG ? 64 : 128;
+    const bool pin_ok = host_ptr_is_pinned(ok_keys);
+    return run_sharded(ctx, n_keys, [=](Dev &d, size_t lo, size_t hi) -> int {
+        const uint8_t *ddst; uint32_t dlen;
+        if (int rc = stage_dst(d, dst, dst_len, true, &ddst, &dlen)) return rc;
+        uint8_t *dseed;
+        if (int rc = ensure_t(d, S_RB_SEED, 32, &dseed)) return rc;
+        CK(d, cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, d.st));
+        Pipe pipe(d);
+        SkPlan plan;
+        for (size_t c = lo; c < hi;) {
+            size_t e = c + 1;
+            while (e < hi && e - c < ctx->chunk && key_offsets[e + 1] - key_offsets[c] <= ctx->chunk) e++;
+            const size_t nk = e - c, t0 = (size_t)key_offsets[c], m = (size_t)key_offsets[e] - t0;
+            plan = SkPlan();
+            sk_plan(plan, key_offsets + c, nk);
+            if (int rc = pipe.begin(pin_ok ? 0 : pad64(nk))) return rc;
+            const uint8_t *dm = nullptr; const uint64_t *dof = nullptr; uint64_t base = 0;
+            if (m)
+                if (int rc = stage_msgs(d, &pipe, msgs, offsets, t0, t0 + m, &dm, &dof, &base)) return rc;
+            uint8_t *dpk, *dsig, *dok; uint64_t *dplan;
+            if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), nk * rpk, &dpk)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rsig + 16, &dsig)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_IN_C, pipe.set()), plan.blob.size(), &dplan)) return rc;
+            if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), nk, &dok)) return rc;
+            if (int rc = pipe.h2d(dpk, pks + c * rpk, nk * rpk)) return rc;
+            if (int rc = pipe.h2d(dsig, sigs + t0 * rsig, m * rsig)) return rc;
+            // pageable source: the runtime stages it before the call returns, so the plan may be rebuilt for the next chunk
+            if (int rc = pipe.h2d(dplan, plan.blob.data(), plan.blob.size() * sizeof(uint64_t))) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;
+            if (int rc = dev_verify_same_key(d, variant, dpk, nk, dplan, plan, dm, dof, base, dsig, m, dseed, (uint64_t)t0, rand_bits, ddst, dlen,
+                                             flags, dok))
+                return rc;
+            if (int rc = pipe.d2h(ok_keys + c, pin_ok, dok, nk)) return rc;
+            if (int rc = pipe.end()) return rc;
+            c = e;
+        }
+        return pipe.finish();
+    });
+}
+
 // FastAggregateVerify of the IETF BLS draft for G groups: group g = the public keys [key_offsets[g], key_offsets[g+1]) of `pks`,
 // message g, aggregate signature g.  Groups (with their keys) are what the devices share out and what the chunk pipeline streams.
 int bn254_fast_aggregate_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets, const uint8_t *msgs,
@@ -2164,6 +2348,33 @@ int bn254_verify_batch_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t
     const uint8_t *ddst; uint32_t dlen;
     int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
     if (!rc) rc = dev_verify_rand(d, variant, pks, msgs, offsets, 0, sigs, n, group, seed, 0, rand_bits, ddst, dlen, flags, ok_groups);
+    DEV_EPILOGUE(rc);
+}
+// device pointers (device 0 of the ctx) for everything but key_offsets, which stays a HOST array: the reduction plan is built
+// from it.  One chunk: every scratch array is sized for all n tuples.
+int bn254_verify_same_key_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets, size_t n_keys,
+                                         const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs, const uint8_t *dst, size_t dst_len,
+                                         uint32_t flags, const uint8_t *seed, int rand_bits, uint8_t *ok_keys) {
+    DEV_PROLOGUE();
+    if (variant != BN254_MIN_SIG && variant != BN254_MIN_PK) return fail_arg(ctx, "variant must be 0 (min-sig) or 1 (min-pk)");
+    if (rand_bits != 64 && rand_bits != 128) return fail_arg(ctx, "rand_bits must be 64 or 128");
+    if (n_keys == 0) return 0;
+    if (!pks || !key_offsets || !seed || !ok_keys) return fail_arg(ctx, "null pointer");
+    if (int rc = check_offsets(ctx, key_offsets, n_keys)) return rc;
+    if (key_offsets[0] != 0) return fail_arg(ctx, "key_offsets[0] must be 0 for device buffers");
+    const size_t n = (size_t)key_offsets[n_keys];
+    if (n && (!offsets || !sigs)) return fail_arg(ctx, "null pointer");
+    const uint8_t *ddst; uint32_t dlen;
+    uint64_t *dplan = nullptr;
+    SkPlan plan;
+    sk_plan(plan, key_offsets, n_keys);
+    int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
+    if (!rc) rc = ensure_t(d, S_IN_C, plan.blob.size(), &dplan);
+    if (!rc && cudaMemcpyAsync(dplan, plan.blob.data(), plan.blob.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st) != cudaSuccess) {
+        d.err = "cudaMemcpyAsync of the reduction plan failed";
+        rc = BN254_ERR_CUDA_BASE;
+    }
+    if (!rc) rc = dev_verify_same_key(d, variant, pks, n_keys, dplan, plan, msgs, offsets, 0, sigs, n, seed, 0, rand_bits, ddst, dlen, flags, ok_keys);
     DEV_EPILOGUE(rc);
 }
 int bn254_aggregate_partial_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *offsets, size_t n,

@@ -858,6 +858,81 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_rbv_ok(uint8_t *ok, const fp12
     ok[i] = (!gbad[i] && fp12_is_one(F[i])) ? 1 : 0;
 }
 
+// ---- same-key randomised verification (SURVEY.md 8(f)-1 "same-key grouping"): key k owns a variable number of tuples; the scaled
+// signatures and the scaled message points of every key are summed by levels of a variable-length segmented reduction whose
+// block bounds the host computes from the key offsets (capi.cu: sk_plan).  The buffer of a level holds TWO arrays of n_in
+// records, w = 0 the signature side and w = 1 the hash side; block b covers records [sub[b], sub[b+1]) of one key, never empty.
+template <class PT>
+__device__ __forceinline__ void sk_sum_blocks(PT *out, const PT *in, const uint64_t *sub, size_t nb, size_t n_in) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * nb) return;
+    const size_t w = t >= nb ? 1 : 0, b = t - w * nb;
+    const PT *src = in + w * n_in;
+    const uint64_t lo = sub[b], hi = sub[b + 1];
+    PT acc, x;
+    copy_rec(acc, src[lo]);
+#pragma unroll 1
+    for (uint64_t j = lo + 1; j < hi; j++) {
+        copy_rec(x, src[j]);
+        pt_add(acc, acc, x);
+    }
+    copy_rec(out[w * nb + b], acc);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_sum_g1p(g1p *out, const g1p *in, const uint64_t *sub, size_t nb, size_t n_in) {
+    sk_sum_blocks(out, in, sub, nb, n_in);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_sum_g2p(g2p *out, const g2p *in, const uint64_t *sub, size_t nb, size_t n_in) {
+    sk_sum_blocks(out, in, sub, nb, n_in);
+}
+// kbad[key of tuple i] |= tuple i is unusable (undecodable / identity / invalid signature, SvdW exception of its message).
+// ko = the nk + 1 key offsets relative to the chunk; only an unusable tuple searches for its key.
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_sk_key_flags(int *kbad, const uint8_t *fa, const uint8_t *fb, const uint64_t *ko, size_t nk, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!((fa[i] | fb[i]) & FL_BAD)) return;
+    size_t lo = 0, hi = nk;                 // largest k with ko[k] <= i (keys without tuples repeat an offset: take the last)
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) >> 1;
+        if (ko[mid] <= i) lo = mid; else hi = mid;
+    }
+    atomicOr(&kbad[lo], 1);
+}
+// The two sums of key k (record kfin[k] of either array of the last level; a key without tuples has none) -> affine points with
+// flags: FL_BAD for a key without tuples or with an unusable tuple, FL_INF for a sum that is the identity (factor 1 in the loop).
+template <class F, class M>
+__device__ __forceinline__ void sk_finish(M *A, uint8_t *flA, M *B, uint8_t *flB, const point<F> *S, const uint64_t *kfin, const int *kbad, size_t nk) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    const uint64_t r = kfin[k], nfin = kfin[nk];
+    M ra, rb;
+    uint8_t fa = FL_BAD, fb = FL_BAD;
+    if (kfin[k + 1] > r) {
+        point<F> a;
+        bool inf;
+        copy_rec(a, S[r]);
+        pt_to_affine(ra.x, ra.y, inf, a);
+        fa = (kbad[k] ? FL_BAD : 0) | (inf ? FL_INF : 0);
+        copy_rec(a, S[nfin + r]);
+        pt_to_affine(rb.x, rb.y, inf, a);
+        fb = (kbad[k] ? FL_BAD : 0) | (inf ? FL_INF : 0);
+    } else {
+        F::set_zero(ra.x); F::set_zero(ra.y);
+        F::set_zero(rb.x); F::set_zero(rb.y);
+    }
+    copy_rec(A[k], ra);
+    copy_rec(B[k], rb);
+    flA[k] = fa;
+    flB[k] = fb;
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_finish_g1(g1m *A, uint8_t *flA, g1m *B, uint8_t *flB, const g1p *S, const uint64_t *kfin,
+                                                                const int *kbad, size_t nk) {
+    sk_finish<F1, g1m>(A, flA, B, flB, S, kfin, kbad, nk);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_finish_g2(g2m *A, uint8_t *flA, g2m *B, uint8_t *flB, const g2p *S, const uint64_t *kfin,
+                                                                const int *kbad, size_t nk) {
+    sk_finish<F2, g2m>(A, flA, B, flB, S, kfin, kbad, nk);
+}
+
 // compressed codecs
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_compress(uint8_t *out, const g1m *P, const uint8_t *fl, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

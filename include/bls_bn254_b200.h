@@ -142,6 +142,26 @@ int bn254_verify_batch_randomized(bn254_ctx *ctx, int variant, const uint8_t *pk
                                   const uint8_t *sigs, size_t n, const uint8_t *dst, size_t dst_len, uint32_t flags,
                                   const uint8_t *seed /* 32 B */, int rand_bits, size_t group,
                                   uint8_t *ok_groups /* ceil(n/group) bytes 0/1 */);
+/* Same-key randomised verification ("same-key grouping"; no counterpart in the reference): many messages
+ * signed under FEW keys (a validator that signs a stream of messages).  Key k owns the tuples [key_offsets[k], key_offsets[k+1])
+ * of `msgs` / `sigs` (the caller sorts its tuples by key) and gets ONE accept byte:
+ *     min-sig: e(sum_i r_i sig_i, -g2) * e(sum_i r_i H_G1(m_i), pk_k) == 1     min-pk: e(-g1, sum_i r_i sig_i) * e(pk_k, sum_i r_i H_G2(m_i)) == 1
+ * (bilinearity: prod_i e(r_i H(m_i), pk_k) = e(sum_i r_i H(m_i), pk_k)).  Per tuple that is one hash to the curve and two short
+ * scalar multiplications; the pairing work -- one two-pair Miller loop and one final exponentiation -- is per KEY.  r_i is the
+ * scalar of bn254_verify_batch_randomized for tuple index i, the error bound and its preconditions (unpredictable seed, inputs in
+ * the order-r subgroups) are the same.  A key without tuples, an unusable key (undecodable / identity / failing the checks of
+ * `flags`) or an unusable signature rejects that key.  On a rejected key the caller falls back to bn254_verify_batch on the key's
+ * tuples.  A key is never split over chunks: device scratch grows to ~0.5 KB per tuple of the largest key.
+ * `_dev`: device pointers on device 0 for everything except key_offsets (host; key_offsets[0] must be 0). */
+int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t *pks /* n_keys records */,
+                                     const uint64_t *key_offsets /* n_keys+1, in tuples */, size_t n_keys, const uint8_t *msgs,
+                                     const uint64_t *offsets /* key_offsets[n_keys]+1 */, const uint8_t *sigs, const uint8_t *dst,
+                                     size_t dst_len, uint32_t flags, const uint8_t *seed /* 32 B */, int rand_bits,
+                                     uint8_t *ok_keys /* n_keys bytes 0/1 */);
+int bn254_verify_same_key_randomized_dev(bn254_ctx *ctx, int variant, const uint8_t *pks, const uint64_t *key_offsets /* HOST */,
+                                         size_t n_keys, const uint8_t *msgs, const uint64_t *offsets, const uint8_t *sigs,
+                                         const uint8_t *dst, size_t dst_len, uint32_t flags, const uint8_t *seed, int rand_bits,
+                                         uint8_t *ok_keys);
 /* FastAggregateVerify of the IETF BLS draft (many signers, ONE message per group), n_groups groups at once: group g = the public
  * keys [key_offsets[g], key_offsets[g+1]) of `pks`, message g, aggregate signature g:
  *     min-sig: e(aggsig_g, -g2) * e(H_G1(m_g), sum pk) == 1          min-pk: e(-g1, aggsig_g) * e(sum pk, H_G2(m_g)) == 1

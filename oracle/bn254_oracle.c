@@ -1325,6 +1325,102 @@ EXPORT int orc_fast_aggregate_verify_batch(int variant, const uint8_t *pks, cons
     return 0;
 }
 
+/* Same-key randomised verification (SURVEY.md 8(f)-1 "same-key grouping"; defined by include/bls_bn254_b200.h, absent in the
+ * reference): key k owns the tuples [koff[k], koff[k+1]) -- its messages and signatures -- and gets ONE accept byte from
+ *   min-sig: e(sum r_i sig_i, -g2) * e(sum r_i H(m_i), pk_k) == 1;   min-pk: e(-g1, sum r_i sig_i) * e(pk_k, sum r_i H(m_i)) == 1
+ * with the scalars r_i of orc_verify_batch_randomized (i = index of the tuple in the call, i.e. its position in sigs / msgs).
+ * The key is validated like a verification key, every signature like a signature; a key without tuples, an unusable key or
+ * an unusable tuple rejects the key.  A sum that happens to be the identity contributes the factor 1, as in multi_miller. */
+typedef struct {
+    verify_args v; const uint8_t *seed; int rand_bits; const uint64_t *koff; size_t nkeys;
+    g1p *a1, *b1; g2p *a2, *b2; uint8_t *bad; uint8_t *okk;
+} sk_args;
+static void sk_item_range(void *p, size_t lo, size_t hi) {
+    sk_args *r = (sk_args *)p; const verify_args *a = &r->v;
+    const uint64_t t0 = r->koff[0];
+    for (size_t j = lo; j < hi; j++) {
+        const size_t i = (size_t)t0 + j;
+        const uint8_t *msg = a->msgs + a->off[i];
+        size_t mlen = a->off[i + 1] - a->off[i];
+        uint64_t ka, kb;
+        rbv_scalar(&ka, &kb, r->seed, (uint64_t)i, r->rand_bits);
+        const int hb = r->rand_bits / 2;
+        r->bad[j] = 1;
+        if (a->variant == 0) {
+            g1a sig, h; g1p t;
+            if (!g1a_from_bytes(&sig, a->sigs + 64 * i) || sig.inf) continue;
+            if ((a->flags & 3) && !g1a_on_curve(&sig)) continue;
+            if ((a->flags & 2) && !g1a_torsion_free(&sig)) continue;
+            if (!hash_to_g1_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
+            g1_from_affine(&t, &sig.x, &sig.y, 0); g1_mul_glv(&r->a1[j], &t, ka, kb, hb);
+            g1_from_affine(&t, &h.x, &h.y, h.inf); g1_mul_glv(&r->b1[j], &t, ka, kb, hb);
+        } else {
+            g2a sig, h; g2p t;
+            if (!g2a_from_bytes(&sig, a->sigs + 128 * i) || sig.inf) continue;
+            if ((a->flags & 3) && !g2a_on_curve(&sig)) continue;
+            if ((a->flags & 2) && !g2a_torsion_free(&sig)) continue;
+            if (!hash_to_g2_one(&h, msg, mlen, a->dst, a->dst_len, 2)) continue;
+            g2_from_affine(&t, &sig.x, &sig.y, 0); g2_mul_glv(&r->a2[j], &t, ka, kb, hb);
+            g2_from_affine(&t, &h.x, &h.y, h.inf); g2_mul_glv(&r->b2[j], &t, ka, kb, hb);
+        }
+        r->bad[j] = 0;
+    }
+}
+static void sk_key_range(void *p, size_t lo, size_t hi) {
+    sk_args *r = (sk_args *)p; const verify_args *a = &r->v;
+    const uint64_t t0 = r->koff[0];
+    for (size_t k = lo; k < hi; k++) {
+        const size_t s = (size_t)(r->koff[k] - t0), e = (size_t)(r->koff[k + 1] - t0);
+        int good = e > s;
+        for (size_t j = s; j < e && good; j++) good = !r->bad[j];
+        g1a ps[2]; g2a qs[2];
+        if (a->variant == 0) {
+            g2a pk;
+            if (!g2a_from_bytes(&pk, a->pks + 128 * k) || pk.inf) good = 0;
+            if (good && (a->flags & 3) && !g2a_on_curve(&pk)) good = 0;
+            if (good && (a->flags & 2) && !g2a_torsion_free(&pk)) good = 0;
+            if (!good) { r->okk[k] = 0; continue; }
+            g1p sa, sb; g1_set_identity(&sa); g1_set_identity(&sb);
+            for (size_t j = s; j < e; j++) { g1_add(&sa, &sa, &r->a1[j]); g1_add(&sb, &sb, &r->b1[j]); }
+            g1_to_affine(&ps[0].x, &ps[0].y, &ps[0].inf, &sa); qs[0] = NEG_G2_GEN_A;
+            g1_to_affine(&ps[1].x, &ps[1].y, &ps[1].inf, &sb); qs[1] = pk;
+        } else {
+            g1a pk;
+            if (!g1a_from_bytes(&pk, a->pks + 64 * k) || pk.inf) good = 0;
+            if (good && (a->flags & 3) && !g1a_on_curve(&pk)) good = 0;
+            if (good && (a->flags & 2) && !g1a_torsion_free(&pk)) good = 0;
+            if (!good) { r->okk[k] = 0; continue; }
+            g2p sa, sb; g2_set_identity(&sa); g2_set_identity(&sb);
+            for (size_t j = s; j < e; j++) { g2_add(&sa, &sa, &r->a2[j]); g2_add(&sb, &sb, &r->b2[j]); }
+            ps[0] = NEG_G1_GEN_A; g2_to_affine(&qs[0].x, &qs[0].y, &qs[0].inf, &sa);
+            ps[1] = pk;           g2_to_affine(&qs[1].x, &qs[1].y, &qs[1].inf, &sb);
+        }
+        fp12 f;
+        multi_miller(&f, ps, qs, 2);
+        final_exponentiation(&f, &f);
+        r->okk[k] = (uint8_t)fp12_eq(&f, &F12_ONE);
+    }
+}
+EXPORT int orc_verify_same_key_randomized(int variant, const uint8_t *pks, const uint64_t *koff, size_t nkeys, const uint8_t *msgs,
+                                          const uint64_t *off, const uint8_t *sigs, const uint8_t *dst, size_t dst_len, uint32_t flags,
+                                          const uint8_t *seed, int rand_bits, uint8_t *ok_keys, int nthreads) {
+    orc_init();
+    if (rand_bits != 64 && rand_bits != 128) return -10;
+    if (nkeys == 0) return 0;
+    const size_t n = (size_t)(koff[nkeys] - koff[0]);
+    sk_args r;
+    memset(&r, 0, sizeof r);
+    verify_args v = {variant, pks, msgs, off, sigs, dst, dst_len, flags, NULL};
+    r.v = v; r.seed = seed; r.rand_bits = rand_bits; r.koff = koff; r.nkeys = nkeys; r.okk = ok_keys;
+    r.bad = (uint8_t *)calloc(n + 1, 1);
+    if (variant == 0) { r.a1 = (g1p *)calloc(n + 1, sizeof(g1p)); r.b1 = (g1p *)calloc(n + 1, sizeof(g1p)); }
+    else { r.a2 = (g2p *)calloc(n + 1, sizeof(g2p)); r.b2 = (g2p *)calloc(n + 1, sizeof(g2p)); }
+    parallel_for(n, nthreads, sk_item_range, &r);
+    parallel_for(nkeys, nthreads, sk_key_range, &r);
+    free(r.bad); free(r.a1); free(r.b1); free(r.a2); free(r.b2);
+    return 0;
+}
+
 /* ---- test-data generators: scalar multiplication (g1.rs:821-841, g2.rs:866-886), sums */
 typedef struct { const uint8_t *pts; const uint8_t *sc; uint8_t *out; } mul_args;
 static void scalar_limbs(uint64_t k[4], const uint8_t be[32]) {

@@ -188,6 +188,21 @@ def fast_aggregate_verify_batch(variant, pks, key_counts, msgs, sigs, dst, flags
     return ok.raw[:len(msgs)]
 
 
+def verify_same_key_randomized(variant, pks, msg_counts, msgs, sigs, dst, seed, rand_bits=64, flags=0, nthreads=1):
+    """one accept byte per KEY: key k owns the next msg_counts[k] (message, signature) tuples"""
+    blob, off = pack_msgs(msgs)
+    nk = len(msg_counts)
+    koff = (C.c_uint64 * (nk + 1))()
+    for i, k in enumerate(msg_counts):
+        koff[i + 1] = koff[i] + k
+    assert koff[nk] == len(msgs)
+    ok = _buf(max(1, nk))
+    rc = lib().orc_verify_same_key_randomized(variant, pks, koff, C.c_size_t(nk), blob, off, sigs, dst, C.c_size_t(len(dst)), C.c_uint32(flags),
+                                              seed, rand_bits, ok, nthreads)
+    assert rc == 0, rc
+    return ok.raw[:nk]
+
+
 def g2_sum(pts):
     out = _buf(128)
     assert lib().orc_g2_sum(pts, C.c_size_t(len(pts) // 128), out) == 0

@@ -852,6 +852,97 @@ def test_fast_aggregate_verify_batch(ctx, orc, B, variant, shape):
     assert ctx.fast_aggregate_verify_batch(variant, b"", [], [], b"", dst) == b""
 
 
+def _same_key_batch(ctx, B, rng, variant, counts, msg_len=(0, 7, 32, 100)):
+    """keys, messages and signatures of a same-key batch: key k signs the next counts[k] messages"""
+    R = B.R_ORDER
+    nk = len(counts)
+    sks = [B.scheme.SecretKey(rng.randrange(1, R)) for _ in range(nk)]
+    key_of = [k for k, c in enumerate(counts) for _ in range(c)]
+    msgs = [i.to_bytes(4, "little") + rng.randbytes(rng.choice(msg_len)) for i in range(len(key_of))]
+    pks = B.scheme.public_keys(ctx, sks, variant)
+    sigs = B.scheme.sign(ctx, [sks[k] for k in key_of], msgs, variant) if key_of else b""
+    return sks, key_of, msgs, bytearray(pks), bytearray(sigs)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_same_key_randomized_vs_oracle(ctx, orc, B, variant, shape):
+    """bn254_verify_same_key_randomized (many messages under few keys: ONE Miller loop and ONE final exponentiation per key over
+    the randomised sums of that key's signatures and message points): verdicts equal the oracle's -- clean keys accept; a key
+    without tuples, a tampered message, a signature under another key, an identity signature, an identity key and an
+    undecodable key reject exactly their key -- with both scalar widths and with validation on."""
+    rng = random.Random(71 + variant)
+    dst = B.DST_MIN_SIG if variant == 0 else B.DST_MIN_PK
+    rpk, rsig = (128, 64) if variant == 0 else (64, 128)
+    counts = [1, 5, 0, 37, 4, 2, 16, 3, 3, 9, 1]
+    sks, key_of, msgs, pks, sigs = _same_key_batch(ctx, B, rng, variant, counts)
+    start = [sum(counts[:k]) for k in range(len(counts))]
+    ident_pk = (bytes(64) + bytes(63) + b"\x01") if variant == 0 else ((0).to_bytes(32, "big") + (1).to_bytes(32, "big"))
+    ident_sig = ((0).to_bytes(32, "big") + (1).to_bytes(32, "big")) if variant == 0 else (bytes(64) + bytes(63) + b"\x01")
+    seed = rng.randbytes(32)
+    clean = bytes(int(c > 0) for c in counts)
+    assert ctx.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed) == clean
+    msgs[start[3] + 20] += b"?"                                                         # key 3: tampered message
+    t4 = start[4] + 1                                                                   # key 4: a signature made by key 5
+    sigs[t4 * rsig:(t4 + 1) * rsig] = B.scheme.sign(ctx, [sks[5]], [msgs[t4]], variant)
+    t6 = start[6] + 15                                                                  # key 6: identity signature (last tuple)
+    sigs[t6 * rsig:(t6 + 1) * rsig] = ident_sig
+    pks[7 * rpk:8 * rpk] = ident_pk                                                     # key 7: identity key
+    pks[8 * rpk:9 * rpk] = b"\xff" * rpk                                                # key 8: undecodable key
+    want = bytes([1, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1])
+    for flags, bits in ((0, 64), (3, 64), (1, 128)):
+        got = ctx.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed, rand_bits=bits, flags=flags)
+        ref = orc.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed, rand_bits=bits, flags=flags, nthreads=orc.ncpu())
+        assert got == ref == want, (flags, bits)
+    assert ctx.verify_same_key_randomized(variant, b"", [], [], b"", dst, seed) == b""
+    assert ctx.verify_same_key_randomized(variant, bytes(pks[:2 * rpk]), [0, 0], [], b"", dst, seed) == b"\x00\x00"
+    with pytest.raises(B.Bn254Error):
+        ctx.verify_same_key_randomized(variant, bytes(pks), counts[:-1], msgs, bytes(sigs), dst, seed)
+
+
+def test_same_key_randomized_multi_chunk_and_predicted_scalars(ctx, orc, B):
+    """The host pipeline of the same-key path: with a small chunk the keys stream through several staging rounds (a key is never
+    split: the 600-tuple key exceeds the chunk and goes alone) and the verdicts equal the one-chunk call and the construction.
+    Soundness depends on the seed being unpredictable: a forger who KNOWS the seed cancels two errors (sig_a + D, sig_b - (r_a /
+    r_b) D) and is accepted under that seed, rejected under any other -- the oracle agrees on both."""
+    from rbv_util import _rbv_scalar
+    rng = random.Random(83)
+    counts = [600, 3, 0, 250, 40, 7, 130, 1]
+    sks, key_of, msgs, pks, sigs = _same_key_batch(ctx, B, rng, 0, counts, msg_len=(28,))
+    start = [sum(counts[:k]) for k in range(len(counts))]
+    bad = start[3] + 101
+    sigs[64 * bad:64 * bad + 64] = sigs[64 * (bad + 1):64 * (bad + 2)]
+    want = bytes([1, 1, 0, 0, 1, 1, 1, 1])
+    seed = rng.randbytes(32)
+    one = ctx.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed)
+    assert one == want
+    c = B.Context([0])
+    try:
+        c.set_option("chunk", 256)
+        many, names = launched(c, lambda: c.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed))
+    finally:
+        c.close()
+    assert many == want
+    assert {"k_sk_sum_g1p", "k_sk_finish_g1", "k_sk_key_flags", "k_rbv_scale_g1p"} <= names, names
+    # predicted scalars: key 4's tuples a, b get sig_a + D and sig_b - [r_a / r_b] D
+    R = B.R_ORDER
+    a, b = start[4] + 2, start[4] + 9
+    ra, rb = _rbv_scalar(seed, a, 64), _rbv_scalar(seed, b, 64)
+    D = B.scheme.sign(ctx, [B.scheme.SecretKey(12345)], [b"delta"], 0)
+    c = (R - ra * pow(rb, -1, R)) % R
+    cD = ctx.g1_mul(D, c.to_bytes(32, "big"))
+    forged = bytearray(sigs)
+    forged[64 * bad:64 * bad + 64] = B.scheme.sign(ctx, [sks[3]], [msgs[bad]], 0)        # repair key 3
+    forged[64 * a:64 * a + 64] = ctx.g1_sum(bytes(forged[64 * a:64 * a + 64]) + D)
+    forged[64 * b:64 * b + 64] = ctx.g1_sum(bytes(forged[64 * b:64 * b + 64]) + cD)
+    got = ctx.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(forged), B.DST_MIN_SIG, seed)
+    assert got == bytes([1, 1, 0, 1, 1, 1, 1, 1])                                        # accepted under the KNOWN seed ...
+    assert got == orc.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(forged), B.DST_MIN_SIG, seed, nthreads=orc.ncpu())
+    other = ctx.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(forged), B.DST_MIN_SIG, bytes(32))
+    assert other == bytes([1, 1, 0, 1, 0, 1, 1, 1])                                      # ... and caught under any other
+    exact = ctx.verify_batch(0, b"".join(bytes(pks[128 * k:128 * k + 128]) for k in key_of), msgs, bytes(forged), B.DST_MIN_SIG)
+    assert exact[a] == 0 and exact[b] == 0 and sum(exact) == len(key_of) - 2
+
+
 def test_wide_shape_boundary(ctx, orc, B):
     """Shape 0 picks the wide (one warp per pairing) kernels for launches of at most "wide_max" pairings and the lane-pair
     kernels above: both sides of the boundary against the oracle, min-sig and min-pk, standalone pairings and a lone final

@@ -379,3 +379,52 @@ def test_fast_aggregate_verify_in_the_oracle(orc):
     wrong[1] = wrong[1] + b"?"
     assert orc.fast_aggregate_verify_batch(0, keys, sizes, wrong, sigs, DST_SIG) == bytes([1, 0, 0, 0, 0, 0])
     assert orc.fast_aggregate_verify_batch(0, keys, sizes, msgs, sigs, DST_SIG, flags=3) == got
+
+
+def test_same_key_randomized_in_the_oracle(orc):
+    """orc_verify_same_key_randomized (the checker of bn254_verify_same_key_randomized): one accept byte per KEY over all of that
+    key's (message, signature) tuples.  A key whose tuples all verify is accepted whatever the seed; one bad tuple, an identity
+    or undecodable key, an identity signature or a key without tuples rejects exactly that key; the verdicts agree with the
+    exact per-tuple predicate folded per key, in both variants and with 128-bit scalars."""
+    rng = random.Random(23)
+    for variant, dst in ((0, DST_SIG), (1, DST_PK)):
+        counts = [3, 1, 0, 4, 2, 2, 1]
+        nk, n = len(counts), sum(counts)
+        sks = [rng.randrange(1, pm.R_ORDER) for _ in range(nk)]
+        msgs = [rng.randbytes(rng.choice((0, 7, 32, 70))) for _ in range(n)]
+        key_of = [k for k, c in enumerate(counts) for _ in range(c)]
+        sk_t = b"".join(sks[k].to_bytes(32, "big") for k in key_of)
+        sk_k = b"".join(s.to_bytes(32, "big") for s in sks)
+        if variant == 0:
+            pks = bytearray(orc.g2_mul(orc.g2_generator() * nk, sk_k))
+            sigs = bytearray(orc.g1_mul(orc.hash_to_g1(msgs, dst), sk_t))
+            rpk, rsig = 128, 64
+            id_pk, id_sig = bytes(64) + bytes(63) + b"\x01", (0).to_bytes(32, "big") + (1).to_bytes(32, "big")
+        else:
+            pks = bytearray(orc.g1_mul(orc.g1_generator() * nk, sk_k))
+            sigs = bytearray(orc.g2_mul(orc.hash_to_g2(msgs, dst), sk_t))
+            rpk, rsig = 64, 128
+            id_pk, id_sig = (0).to_bytes(32, "big") + (1).to_bytes(32, "big"), bytes(64) + bytes(63) + b"\x01"
+        seed = bytes(range(32))
+        good = bytes([1, 1, 0, 1, 1, 1, 1])                                  # the key without tuples rejects
+        assert orc.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed) == good
+        assert orc.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed[::-1], rand_bits=128, flags=3) == good
+        # tuple 5 (key 3) signs another message; key 4 is the identity; key 5's first signature is the identity; key 6 undecodable
+        bad_msgs = list(msgs)
+        bad_msgs[5] = bad_msgs[5] + b"!"
+        pks[4 * rpk:5 * rpk] = id_pk
+        t5 = sum(counts[:5])
+        sigs[t5 * rsig:(t5 + 1) * rsig] = id_sig
+        pks[6 * rpk:7 * rpk] = b"\xff" * rpk
+        want = bytes([1, 1, 0, 0, 0, 0, 0])
+        assert orc.verify_same_key_randomized(variant, bytes(pks), counts, bad_msgs, bytes(sigs), dst, seed, nthreads=2) == want
+        # the exact predicate, folded per key, says the same
+        pk_t = b"".join(bytes(pks[k * rpk:(k + 1) * rpk]) for k in key_of)
+        exact = orc.verify_batch(variant, pk_t, bad_msgs, bytes(sigs), dst)
+        fold = [int(counts[k] > 0 and all(exact[i] for i in range(n) if key_of[i] == k)) for k in range(nk)]
+        assert bytes(fold) == want
+        # two signatures of one key swapped: each tuple fails on its own and the randomised sum catches it as well
+        if variant == 0:
+            s = bytearray(orc.g1_mul(orc.hash_to_g1(msgs, dst), sk_t))
+            s[0:64], s[64:128] = s[64:128], s[0:64]
+            assert orc.verify_same_key_randomized(0, orc.g2_mul(orc.g2_generator() * nk, sk_k), counts, msgs, bytes(s), dst, seed)[0] == 0
