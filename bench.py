@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=65536, help="tuples of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-subgroup", action="store_true", help="verify workloads: also validate inputs (on-curve + order-r subgroup)")
+    ap.add_argument("--same-key-keys", type=int, default=64, help="distinct keys of the same_key sub-record")
+    ap.add_argument("--same-key-stream-log2n", type=int, default=22, help="log2 of the tuples per GPU of the streamed same_key figure")
     ap.add_argument("--sub", default=None, help="sub-records of the other BASELINE configs: all | none | comma list of c1,c3,c4,c5,pairing,prepared "
                                                 "(default: all for the verify workload, none otherwise)")
     ap.add_argument("--c5-log2n", type=int, default=24, help="log2 of the TOTAL tuples of the c5 sub-record (sharded over the ranks)")
@@ -249,7 +251,7 @@ def main():
 
     w = args.workload
     subs = args.sub if args.sub is not None else ("all" if w == "verify" else "none")
-    subs = {"all": {"c1", "c3", "c4", "c5", "pairing", "prepared"}, "none": set()}.get(subs, set(subs.split(",")))
+    subs = {"all": {"c1", "c3", "c4", "c5", "pairing", "prepared", "same_key"}, "none": set()}.get(subs, set(subs.split(",")))
     variant = b.MIN_PK if w == "verify_pk" else b.MIN_SIG
     vflags = b.CHECK_SUBGROUP if args.check_subgroup else 0
     n = 1 << args.log2n
@@ -521,6 +523,76 @@ def main():
                           "e2e_pairings_per_sec": n * world * ssteps / (ems * 1e-3), "checked": check}
         del dp1, dp2, dgt
         torch.cuda.empty_cache()
+
+    if "same_key" in subs:
+        # SURVEY 8(f)-1 "same-key grouping": the batch size of the primary workload, signed under FEW keys (tuples sorted by key);
+        # bn254_verify_same_key_randomized gives one verdict per key from one Miller loop + one final exponentiation per KEY
+        nks = args.same_key_keys
+        bad_keys = (1, nks // 2) if nks > 2 else ()
+        kp, kko, km, kof, ksg, kexp = b.scheme.synth_same_key_np(ctx, n, nks, 0, first=first + (1 << 43), bad_keys=bad_keys)
+        kseed = bytes((7 * i + 1) & 255 for i in range(32))
+        dkp, dkm, dks = dev_bytes(kp.reshape(-1)), dev_bytes(km.reshape(-1)), dev_bytes(ksg.reshape(-1))
+        dkof = torch.from_numpy(kof.view(np.int64)).to(dev)
+        dkseed, dkdst = dev_bytes(kseed), dev_bytes(b.DST_MIN_SIG)
+        dkok = torch.zeros(nks, dtype=torch.uint8, device=dev)
+        hkp, hkm, hks = pinned(kp.reshape(-1)), pinned(km.reshape(-1)), pinned(ksg.reshape(-1))
+        hkof = torch.from_numpy(kof.view(np.int64)).pin_memory()
+        hkok = torch.zeros(nks, dtype=torch.uint8).pin_memory()
+        run = lambda: ctx.verify_same_key_randomized_dev(0, dkp.data_ptr(), kko.ctypes.data, nks, dkm.data_ptr(), dkof.data_ptr(), dks.data_ptr(),
+                                                         dkdst.data_ptr(), len(b.DST_MIN_SIG), vflags, dkseed.data_ptr(), 64, dkok.data_ptr())
+        run(); ctx.sync()
+        assert bytes(dkok.cpu().numpy()) == kexp.tobytes(), "same-key verdicts differ from the construction"
+        barrier()
+        ms, _ = timed_dev(run, args.steps)
+        ms = max_over_ranks(ms)
+        erun = lambda: ctx.raw("bn254_verify_same_key_randomized", 0, hkp.data_ptr(), kko.ctypes.data, nks, hkm.data_ptr(), hkof.data_ptr(), hks.data_ptr(),
+                               b.DST_MIN_SIG, len(b.DST_MIN_SIG), vflags, kseed, 64, hkok.data_ptr())
+        erun()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            erun()
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert bytes(hkok.numpy()) == kexp.tobytes(), "same-key verdicts (host-buffer call) differ from the construction"
+        check = None
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import orc
+            kk = min(nks, 4)                       # the first keys (a broken one among them) against the oracle
+            tk = int(kko[kk])
+            cnt = [int(kko[i + 1] - kko[i]) for i in range(kk)]
+            sub_ok = ctx.verify_same_key_randomized(0, kp[:kk].tobytes(), cnt, (km[:tk].tobytes(), kof[:tk + 1]), ksg[:tk].tobytes(), b.DST_MIN_SIG, kseed, flags=vflags)
+            ref = orc.verify_same_key_randomized(0, kp[:kk].tobytes(), cnt, [bytes(r) for r in km[:tk]], ksg[:tk].tobytes(), b.DST_MIN_SIG, kseed, flags=vflags,
+                                                 nthreads=orc.ncpu())
+            assert sub_ok == ref == kexp[:kk].tobytes(), "same-key verdicts differ from the oracle"
+            check = "verdicts equal the construction; the first %d keys (%d tuples, one broken key) equal the oracle" % (kk, tk)
+        sub["same_key"] = {"config": "2^%d (msg, sig) tuples per GPU under %d keys, sorted by key (min-sig, %d keys with one broken tuple); "
+                                     "bn254_verify_same_key_randomized: per tuple a hash to G1 and two 64-bit GLV scalar multiplications, per KEY the two "
+                                     "sums, one two-pair Miller loop and one final exponentiation; one accept byte per key" % (args.log2n, nks, len(bad_keys)),
+                           "verifications_per_sec": n * world * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                           "e2e_verifications_per_sec": n * world * args.steps / (ems * 1e-3), "keys": nks, "rand_bits": 64, "checked": check}
+        del dkp, dkm, dks, dkof, dkok
+        torch.cuda.empty_cache()
+        # streamed: 2^22 tuples per GPU under 16 x as many keys through the host call on pinned buffers -- chunks of 2^18 tuples, the
+        # per-key tail of a chunk (a latency-bound chain on a few keys) overlaps the per-tuple kernels of the next
+        n_st, nk_st = (1 << args.same_key_stream_log2n) if args.same_key_stream_log2n else 0, 16 * nks
+        if n_st:
+            sp, sko, sm, sof, ssg, sexp = b.scheme.synth_same_key_np(ctx, n_st, nk_st, 0, first=first + (1 << 44), bad_keys=(3, nk_st - 2))
+            hsp, hsm, hss = pinned(sp.reshape(-1)), pinned(sm.reshape(-1)), pinned(ssg.reshape(-1))
+            hsof = torch.from_numpy(sof.view(np.int64)).pin_memory()
+            hsok = torch.zeros(nk_st, dtype=torch.uint8).pin_memory()
+            srun = lambda: ctx.raw("bn254_verify_same_key_randomized", 0, hsp.data_ptr(), sko.ctypes.data, nk_st, hsm.data_ptr(), hsof.data_ptr(), hss.data_ptr(),
+                                   b.DST_MIN_SIG, len(b.DST_MIN_SIG), vflags, kseed, 64, hsok.data_ptr())
+            srun()
+            assert bytes(hsok.numpy()) == sexp.tobytes(), "same-key verdicts (streamed) differ from the construction"
+            barrier()
+            t0 = time.perf_counter()
+            srun()
+            torch.cuda.synchronize()
+            st_s = max_over_ranks(time.perf_counter() - t0)
+            sub["same_key"]["streamed"] = {"tuples_per_gpu": n_st, "keys_per_gpu": nk_st, "seconds": st_s, "verifications_per_sec": n_st * world / st_s,
+                                           "h2d_bytes_per_gpu": int(hsp.numel() + hsm.numel() + hss.numel() + 8 * (n_st + 1)), "d2h_bytes_per_gpu": nk_st,
+                                           "note": "host-buffer call, copies inside the timed region; verdicts equal the construction"}
+            del hsp, hsm, hss, hsof
 
     if "c3" in subs:
         n3 = 1 << args.c3_log2n

@@ -810,22 +810,33 @@ void sk_plan(SkPlan &p, const uint64_t *koff, size_t nk) {
 //   min-sig: e(sum r_i sig_i, -g2) * e(sum r_i H(m_i), pk_k) == 1        min-pk: e(-g1, sum r_i sig_i) * e(pk_k, sum r_i H(m_i)) == 1
 // Per tuple: decode, hash, two GLV scalings; per key: the two sums, ONE two-pair Miller loop and ONE final exponentiation --
 // the exact predicate's own kernels on (pk_k, sum r_i H(m_i), sum r_i sig_i).  idx0 = index of the chunk's first tuple in the call.
+// `tail_set` >= 0 (the host pipeline): the per-key tail -- Miller loop, final exponentiation, verdict: a latency-bound chain on
+// a few keys -- runs on d.tail over buffers of that staging set and overlaps the per-tuple kernels of the next chunk; the caller
+// collects `ok` on d.tail.
 int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, const uint64_t *plan, const SkPlan &hp, const uint8_t *msgs,
                         const uint64_t *off, uint64_t base, const uint8_t *sigs, size_t n, const uint8_t *seed, uint64_t idx0, int nbits,
-                        const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+                        const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok, int tail_set = -1, bool tail_hidden = false) {
     const int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? DEC_ON_CURVE : 0) | DEC_NO_IDENTITY;
     const bool subgroup = (flags & BN254_FLAG_CHECK_SUBGROUP) != 0;
-    fp12 *F; uint8_t *flf, *fla, *flb, *flka, *flkb, *flpk;
+    const bool sig_g1 = variant == BN254_MIN_SIG;
+    if (tail_set >= 0 && (d.prof || d.shape == 3 || d.cur != d.st)) tail_set = -1;   // per-kernel timing / shared scratch want it serial
+    // everything the tail reads lives in ONE per-staging-set allocation: F | sums of the signature side | sums of the hash side |
+    // decoded keys | four flag arrays
+    const size_t nkp = (nk + 15) & ~(size_t)15;
+    const size_t rec_sum = sig_g1 ? sizeof(g1m) : sizeof(g2m), rec_pk = sig_g1 ? sizeof(g2m) : sizeof(g1m);
+    uint8_t *tb;
+    if (int rc = ensure_t(d, stage_buf(S_RB_T, tail_set > 0 ? 1 : 0), nkp * (sizeof(fp12) + 2 * rec_sum + rec_pk + 4), &tb)) return rc;
+    fp12 *F = (fp12 *)tb;
+    uint8_t *ka = tb + nkp * sizeof(fp12), *kb = ka + nkp * rec_sum, *pk = kb + nkp * rec_sum;
+    uint8_t *flf = pk + nkp * rec_pk, *flka = flf + nkp, *flkb = flka + nkp, *flpk = flkb + nkp;
+    uint8_t *fla, *flb;
     int *kbad;
-    if (int rc = ensure_t(d, S_F, nk, &F)) return rc;
-    if (int rc = ensure_t(d, S_FLF, nk, &flf)) return rc;
     if (int rc = ensure_t(d, S_RB_BAD, nk, &kbad)) return rc;
-    if (int rc = ensure_t(d, S_RB_FLP, nk, &flka)) return rc;
-    if (int rc = ensure_t(d, S_FLTMP, nk + 1, &flkb)) return rc;
     CK(d, cudaMemsetAsync(kbad, 0, nk * sizeof(int), d.cur));
     const uint64_t *ko = plan, *kfin = plan + hp.kfin_pos;
-    if (variant == BN254_MIN_SIG) {
-        g1m *A, *B, *KA, *KB; g2m *PK; g1p *S, *SA, *SB;
+    const g1m *ng1 = nullptr; const uint8_t *flc = nullptr;
+    if (sig_g1) {
+        g1m *A, *B; g1p *S, *SA, *SB;
         if (int rc = ensure_t(d, S_P0, n, &A)) return rc;
         if (int rc = ensure_t(d, S_FLP0, n, &fla)) return rc;
         if (int rc = ensure_t(d, S_P1, n, &B)) return rc;
@@ -833,12 +844,8 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
         if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
         if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
         if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
-        if (int rc = ensure_t(d, S_RB_GP, nk, &KA)) return rc;
-        if (int rc = ensure_t(d, S_TMP, (nk + 1) * sizeof(g1m), (uint8_t **)&KB)) return rc;
-        if (int rc = ensure_t(d, S_Q1, nk, &PK)) return rc;
-        if (int rc = ensure_t(d, S_FLQ1, nk, &flpk)) return rc;
-        LAUNCH(d, k_g2_decode, nk, BN_TPB_LIGHT, PK, flpk, pks, nk, check);
-        if (subgroup) LAUNCH(d, k_g2_require_subgroup, nk, BN_TPB_HEAVY, flpk, PK, nk);
+        LAUNCH(d, k_g2_decode, nk, BN_TPB_LIGHT, (g2m *)pk, flpk, pks, nk, check);
+        if (subgroup) LAUNCH(d, k_g2_require_subgroup, nk, BN_TPB_HEAVY, flpk, (g2m *)pk, nk);
         const g1p *src = S;
         if (n) {
             LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, A, fla, sigs, n, check);
@@ -854,11 +861,9 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
                 n_in = hp.levels[l].nb;
             }
         }
-        LAUNCH(d, k_sk_finish_g1, nk, BN_TPB_HEAVY, KA, flka, KB, flkb, src, kfin, kbad, nk);
-        if (int rc = launch_miller2_fixed(d, nk, F, flf, KA, flka, KB, flkb, PK, flpk)) return rc;
+        LAUNCH(d, k_sk_finish_g1, nk, BN_TPB_HEAVY, (g1m *)ka, flka, (g1m *)kb, flkb, src, kfin, kbad, nk);
     } else {
-        g2m *A, *B, *KA, *KB; g1m *PK; g2p *S, *SA, *SB;
-        const g1m *ng1; const uint8_t *flc;
+        g2m *A, *B; g2p *S, *SA, *SB;
         if (int rc = ensure_t(d, S_Q0, n, &A)) return rc;
         if (int rc = ensure_t(d, S_FLQ0, n, &fla)) return rc;
         if (int rc = ensure_t(d, S_Q1, n, &B)) return rc;
@@ -866,12 +871,8 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
         if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
         if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
         if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
-        if (int rc = ensure_t(d, S_RB_GQ, nk, &KA)) return rc;
-        if (int rc = ensure_t(d, S_TMP, (nk + 1) * sizeof(g2m), (uint8_t **)&KB)) return rc;
-        if (int rc = ensure_t(d, S_P1, nk, &PK)) return rc;
-        if (int rc = ensure_t(d, S_FLP1, nk, &flpk)) return rc;
         if (int rc = neg_g1_const(d, &ng1, &flc)) return rc;
-        LAUNCH(d, k_g1_decode, nk, BN_TPB_LIGHT, PK, flpk, pks, nk, check);
+        LAUNCH(d, k_g1_decode, nk, BN_TPB_LIGHT, (g1m *)pk, flpk, pks, nk, check);
         const g2p *src = S;
         if (n) {
             LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, A, fla, sigs, n, check);
@@ -888,8 +889,29 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
                 n_in = hp.levels[l].nb;
             }
         }
-        LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, KA, flka, KB, flkb, src, kfin, kbad, nk);
-        if (int rc = launch_miller2(d, nk, F, flf, ng1, flc, (size_t)0, KA, flka, PK, flpk, KB, flkb)) return rc;
+        LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, (g2m *)ka, flka, (g2m *)kb, flkb, src, kfin, kbad, nk);
+    }
+    // ---- the per-key tail: on the launch stream, or on d.tail beside the next chunk (then in the throughput shape: a hidden tail
+    //      must not take the shared memory and registers the overlapped kernels want) ----
+    struct WideOff {
+        Dev &d; size_t keep;
+        WideOff(Dev &dd, bool off) : d(dd), keep(dd.wide_max) { if (off) d.wide_max = 0; }
+        ~WideOff() { d.wide_max = keep; }
+    } wide_off(d, tail_set >= 0 && tail_hidden);
+    struct Cur {   // LAUNCH goes to d.cur; always put the main stream back
+        Dev &d; cudaStream_t keep;
+        Cur(Dev &dd, bool tail) : d(dd), keep(dd.cur) { if (tail) dd.cur = dd.tail; }
+        ~Cur() { d.cur = keep; }
+    };
+    if (tail_set >= 0) {
+        CK(d, cudaEventRecord(d.ev_tail[tail_set], d.st));
+        CK(d, cudaStreamWaitEvent(d.tail, d.ev_tail[tail_set], 0));
+    }
+    Cur guard(d, tail_set >= 0);
+    if (sig_g1) {
+        if (int rc = launch_miller2_fixed(d, nk, F, flf, (const g1m *)ka, flka, (const g1m *)kb, flkb, (const g2m *)pk, flpk)) return rc;
+    } else {
+        if (int rc = launch_miller2(d, nk, F, flf, ng1, flc, (size_t)0, (const g2m *)ka, flka, (const g1m *)pk, flpk, (const g2m *)kb, flkb)) return rc;
     }
     if (int rc = launch_final_exp(d, F, nk)) return rc;
     LAUNCH(d, k_fp12_is_one, nk, BN_TPB_LIGHT, ok, F, flf, nk);
@@ -1725,6 +1747,8 @@ int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t 
         if (int rc = ensure_t(d, S_RB_SEED, 32, &dseed)) return rc;
         CK(d, cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, d.st));
         Pipe pipe(d);
+        const bool overlap_tail = !d.prof && d.shape != 3;
+        if (overlap_tail) pipe.rs = d.tail;
         SkPlan plan;
         for (size_t c = lo; c < hi;) {
             size_t e = c + 1;
@@ -1747,7 +1771,7 @@ int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t 
             if (int rc = pipe.h2d(dplan, plan.blob.data(), plan.blob.size() * sizeof(uint64_t))) return rc;
             if (int rc = pipe.inputs_ready()) return rc;
             if (int rc = dev_verify_same_key(d, variant, dpk, nk, dplan, plan, dm, dof, base, dsig, m, dseed, (uint64_t)t0, rand_bits, ddst, dlen,
-                                             flags, dok))
+                                             flags, dok, overlap_tail ? pipe.set() : -1, e < hi /* another chunk follows and hides this tail */))
                 return rc;
             if (int rc = pipe.d2h(ok_keys + c, pin_ok, dok, nk)) return rc;
             if (int rc = pipe.end()) return rc;

@@ -219,3 +219,33 @@ def synth_batch_np(ctx, n, variant=MIN_SIG, seed=SEED, first=0, n_keys=4096, cor
         sigs[j[m2]] = sigs[o[m2]]                           # a valid signature of another tuple
         expected[j] = 0
     return pks, msgs, off, sigs, expected
+
+
+def synth_same_key_np(ctx, n, n_keys=64, variant=MIN_SIG, seed=SEED, first=0, bad_keys=()):
+    """Workload of the same-key path: n_keys keys, key k owns the next n // n_keys (+1 for the first n % n_keys keys) tuples --
+    distinct 32-byte messages, signatures made on the GPU; every key listed in bad_keys gets ONE broken tuple (a valid signature
+    of its neighbour).  Returns numpy arrays (pks [n_keys, rpk], key_offsets [n_keys + 1] u64, msgs [n, 32], offsets [n + 1] u64,
+    sigs [n, rsig], expected [n_keys])."""
+    import numpy as np
+    rpk, rsig = (128, 64) if variant == MIN_SIG else (64, 128)
+    uniq = [SecretKey(scalar_from_seed(seed, (1 << 20) + i)) for i in range(n_keys)]
+    upk = np.frombuffer(public_keys(ctx, uniq, variant), dtype=np.uint8).reshape(n_keys, rpk).copy()
+    usc = np.frombuffer(b"".join(s.to_bytes() for s in uniq), dtype=np.uint8).reshape(n_keys, 32)
+    counts = np.full(n_keys, n // n_keys, dtype=np.uint64)
+    counts[:n % n_keys] += np.uint64(1)
+    koff = np.zeros(n_keys + 1, dtype=np.uint64)
+    koff[1:] = np.cumsum(counts)
+    key_of = np.repeat(np.arange(n_keys, dtype=np.int64), counts.astype(np.int64))
+    msgs = synth_messages_np(n, first, seed)
+    off = np.arange(0, 32 * (n + 1), 32, dtype=np.uint64)
+    sc = np.ascontiguousarray(usc[key_of]).reshape(-1)
+    dst = _dst(variant)
+    hashed = (ctx.hash_to_g1 if variant == MIN_SIG else ctx.hash_to_g2)((msgs.reshape(-1), off), dst)
+    sigs = np.frombuffer((ctx.g1_mul if variant == MIN_SIG else ctx.g2_mul)(hashed, sc), dtype=np.uint8).reshape(n, rsig).copy()
+    expected = (counts > 0).astype(np.uint8)
+    for k in bad_keys:
+        if counts[k] >= 2:
+            j = int(koff[k]) + int(counts[k]) // 2
+            sigs[j] = sigs[j - 1]
+            expected[k] = 0
+    return upk, koff, msgs, off, sigs, expected

@@ -919,8 +919,11 @@ def test_same_key_randomized_multi_chunk_and_predicted_scalars(ctx, orc, B):
     try:
         c.set_option("chunk", 256)
         many, names = launched(c, lambda: c.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed))
+        # without the profiler the per-key tail of a chunk runs on its own stream beside the next chunk
+        overlapped = [c.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed) for _ in range(3)]
     finally:
         c.close()
+    assert overlapped == [want] * 3
     assert many == want
     assert {"k_sk_sum_g1p", "k_sk_finish_g1", "k_sk_key_flags", "k_rbv_scale_g1p"} <= names, names
     # predicted scalars: key 4's tuples a, b get sig_a + D and sig_b - [r_a / r_b] D
