@@ -144,7 +144,7 @@ class Context:
         self._ck(self._L.bn254_sync(self._h))
 
     def set_option(self, name, value):
-        """"lanes" (0 per launch / 1 one thread per pairing / 2 lane pair / 3 slot machine / 4 wide slot machine), "wide_max", "chunk", "split":
+        """"lanes" (0 per launch / 1 one thread per pairing / 2 lane pair / 3 slot machine / 4 wide slot machine), "wide_max", "chunk", "split", "sk_msm_min":
         include/bls_bn254_b200.h"""
         self._ck(self._L.bn254_ctx_set_option(self._h, name.encode(), int(value)))
 

@@ -83,6 +83,8 @@ struct Dev {
     int nsub = 1;
     size_t lane_wave_threads = 0;   // threads of one full wave of the lane-pair kernels on this device
     size_t sms = 1;
+    size_t sk_msm_slices = 0;       // tuning: slices per segment of the bucket kernels (0 = chosen per chunk)
+    size_t sk_msm_min = 128;        // same-key path: average tuples per key from which the sums run as bucket-method MSMs
     // Shape of the pairing kernels: 0 = picked per launch (lane pairs while 2n threads fit one wave), 1 = one thread per
     // pairing, 2 = two lanes per pairing.  BN254_LANES / bn254_ctx_set_option("lanes") force a shape so that the parity
     // suite meets BOTH shapes at every size (the big-batch shape is what a 2^24-tuple job runs).
@@ -835,15 +837,31 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
     CK(d, cudaMemsetAsync(kbad, 0, nk * sizeof(int), d.cur));
     const uint64_t *ko = plan, *kfin = plan + hp.kfin_pos;
     const g1m *ng1 = nullptr; const uint8_t *flc = nullptr;
+    // Long segments: the two sums of a key as bucket-method multi-scalar multiplications (kernels.cuh: k_sk_bucket_*), ~4 x less
+    // per-tuple work than scaling every point; short segments: scale every point, then the planned segmented sums.
+    // "sk_msm_min" = smallest average segment length that takes the bucket path (0: never).
+    const int NW = nbits >> 3;                                     // radix-16 windows per scalar half
+    const bool msm = d.sk_msm_min && n >= d.sk_msm_min * nk;
+    const size_t nwin = 2 * nk * 2 * (size_t)NW;                   // (array, key, half, window)
+    int msm_S = 1;                                                 // slices per segment: enough bucket threads to fill the machine
+    if (msm) {
+        const size_t avg = n / nk, want = (d.sms * 1024 + nwin * 16 - 1) / (nwin * 16);
+        msm_S = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, avg / 64), 8));
+        if (d.sk_msm_slices) msm_S = (int)d.sk_msm_slices;
+    }
+    uint8_t *D = nullptr;                                          // digit bytes: 2 NW arrays of npad
+    const size_t npad = (n + 15) & ~(size_t)15;
+    if (msm)
+        if (int rc = ensure_t(d, S_F2, 2 * (size_t)NW * npad + 16, &D)) return rc;
     if (sig_g1) {
         g1m *A, *B; g1p *S, *SA, *SB;
         if (int rc = ensure_t(d, S_P0, n, &A)) return rc;
         if (int rc = ensure_t(d, S_FLP0, n, &fla)) return rc;
         if (int rc = ensure_t(d, S_P1, n, &B)) return rc;
         if (int rc = ensure_t(d, S_FLP1, n, &flb)) return rc;
-        if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
-        if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
-        if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, msm ? nwin * 16 * msm_S : 2 * n + 1, &S)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, msm ? nwin : 2 * hp.nb_max[0] + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, msm ? 2 * nk : 2 * hp.nb_max[1] + 1, &SB)) return rc;
         LAUNCH(d, k_g2_decode, nk, BN_TPB_LIGHT, (g2m *)pk, flpk, pks, nk, check);
         if (subgroup) LAUNCH(d, k_g2_require_subgroup, nk, BN_TPB_HEAVY, flpk, (g2m *)pk, nk);
         const g1p *src = S;
@@ -851,26 +869,34 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
             LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, A, fla, sigs, n, check);
             if (int rc = dev_hash_g1(d, B, flb, msgs, off, base, n, dst, dst_len, 2)) return rc;
             LAUNCH(d, k_sk_key_flags, n, BN_TPB_LIGHT, kbad, fla, flb, ko, nk, n);
-            LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
-            LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
-            size_t n_in = n;
-            for (size_t l = 0; l < hp.levels.size(); l++) {
-                g1p *out = (l & 1) ? SB : SA;
-                LAUNCH(d, k_sk_sum_g1p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
-                src = out;
-                n_in = hp.levels[l].nb;
+            if (msm) {
+                LAUNCH(d, k_sk_digits, n, BN_TPB_LIGHT, D, seed, idx0, nbits, n, npad);
+                LAUNCH(d, k_sk_bucket_g1, nwin * 16 * msm_S, BN_TPB_HEAVY, S, A, fla, B, flb, D, npad, ko, nk, NW, msm_S);
+                LAUNCH(d, k_sk_window_g1, (nwin * 16 + 31) & ~(size_t)31, BN_TPB_HEAVY, SA, S, nwin, msm_S);
+                LAUNCH(d, k_sk_combine_g1, 2 * nk, BN_TPB_HEAVY, SB, SA, nk, NW);
+                src = SB;
+            } else {
+                LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
+                LAUNCH(d, k_rbv_scale_g1p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
+                size_t n_in = n;
+                for (size_t l = 0; l < hp.levels.size(); l++) {
+                    g1p *out = (l & 1) ? SB : SA;
+                    LAUNCH(d, k_sk_sum_g1p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
+                    src = out;
+                    n_in = hp.levels[l].nb;
+                }
             }
         }
-        LAUNCH(d, k_sk_finish_g1, nk, BN_TPB_HEAVY, (g1m *)ka, flka, (g1m *)kb, flkb, src, kfin, kbad, nk);
+        LAUNCH(d, k_sk_finish_g1, nk, BN_TPB_HEAVY, (g1m *)ka, flka, (g1m *)kb, flkb, src, msm ? ko : kfin, kbad, nk, msm);
     } else {
         g2m *A, *B; g2p *S, *SA, *SB;
         if (int rc = ensure_t(d, S_Q0, n, &A)) return rc;
         if (int rc = ensure_t(d, S_FLQ0, n, &fla)) return rc;
         if (int rc = ensure_t(d, S_Q1, n, &B)) return rc;
         if (int rc = ensure_t(d, S_FLQ1, n, &flb)) return rc;
-        if (int rc = ensure_t(d, S_RB_S0, 2 * n + 1, &S)) return rc;
-        if (int rc = ensure_t(d, S_RB_S1, 2 * hp.nb_max[0] + 1, &SA)) return rc;
-        if (int rc = ensure_t(d, S_RB_S2, 2 * hp.nb_max[1] + 1, &SB)) return rc;
+        if (int rc = ensure_t(d, S_RB_S0, msm ? nwin * 16 * msm_S : 2 * n + 1, &S)) return rc;
+        if (int rc = ensure_t(d, S_RB_S1, msm ? nwin : 2 * hp.nb_max[0] + 1, &SA)) return rc;
+        if (int rc = ensure_t(d, S_RB_S2, msm ? 2 * nk : 2 * hp.nb_max[1] + 1, &SB)) return rc;
         if (int rc = neg_g1_const(d, &ng1, &flc)) return rc;
         LAUNCH(d, k_g1_decode, nk, BN_TPB_LIGHT, (g1m *)pk, flpk, pks, nk, check);
         const g2p *src = S;
@@ -879,17 +905,25 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
             if (subgroup) LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, fla, A, n);
             if (int rc = dev_hash_g2(d, B, flb, msgs, off, base, n, dst, dst_len, 2)) return rc;
             LAUNCH(d, k_sk_key_flags, n, BN_TPB_LIGHT, kbad, fla, flb, ko, nk, n);
-            LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
-            LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
-            size_t n_in = n;
-            for (size_t l = 0; l < hp.levels.size(); l++) {
-                g2p *out = (l & 1) ? SB : SA;
-                LAUNCH(d, k_sk_sum_g2p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
-                src = out;
-                n_in = hp.levels[l].nb;
+            if (msm) {
+                LAUNCH(d, k_sk_digits, n, BN_TPB_LIGHT, D, seed, idx0, nbits, n, npad);
+                LAUNCH(d, k_sk_bucket_g2, nwin * 16 * msm_S, BN_TPB_HEAVY, S, A, fla, B, flb, D, npad, ko, nk, NW, msm_S);
+                LAUNCH(d, k_sk_window_g2, (nwin * 16 + 31) & ~(size_t)31, BN_TPB_HEAVY, SA, S, nwin, msm_S);
+                LAUNCH(d, k_sk_combine_g2, 2 * nk, BN_TPB_HEAVY, SB, SA, nk, NW);
+                src = SB;
+            } else {
+                LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S, A, fla, seed, idx0, nbits, n);
+                LAUNCH(d, k_rbv_scale_g2p, n, BN_TPB_HEAVY, S + n, B, flb, seed, idx0, nbits, n);
+                size_t n_in = n;
+                for (size_t l = 0; l < hp.levels.size(); l++) {
+                    g2p *out = (l & 1) ? SB : SA;
+                    LAUNCH(d, k_sk_sum_g2p, 2 * hp.levels[l].nb, BN_TPB_HEAVY, out, src, plan + hp.levels[l].pos, hp.levels[l].nb, n_in);
+                    src = out;
+                    n_in = hp.levels[l].nb;
+                }
             }
         }
-        LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, (g2m *)ka, flka, (g2m *)kb, flkb, src, kfin, kbad, nk);
+        LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, (g2m *)ka, flka, (g2m *)kb, flkb, src, msm ? ko : kfin, kbad, nk, msm);
     }
     // ---- the per-key tail: on the launch stream, or on d.tail beside the next chunk (then in the throughput shape: a hidden tail
     //      must not take the shared memory and registers the overlapped kernels want) ----
@@ -1391,10 +1425,14 @@ int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value) {
     } else if (k == "chunk" && value > 0) {
         ctx->chunk = (size_t)value;
         ctx->chunk_is_default = false;
+    } else if (k == "sk_msm_slices" && value >= 0 && value <= 64) {
+        for (auto &d : ctx->devs) d.sk_msm_slices = (size_t)value;
+    } else if (k == "sk_msm_min" && value >= 0) {
+        for (auto &d : ctx->devs) d.sk_msm_min = (size_t)value;
     } else if (k == "split" && value >= 1 && value <= Dev::MAXSUB) {
         for (auto &d : ctx->devs) d.nsub = (int)value;
     } else {
-        return fail_arg(ctx, "unknown option or value out of range (lanes 0..4, wide_max >= 0, chunk > 0, split 1..8)");
+        return fail_arg(ctx, "unknown option or value out of range (lanes 0..4, wide_max >= 0, chunk > 0, split 1..8, sk_msm_min >= 0)");
     }
     return 0;
 }

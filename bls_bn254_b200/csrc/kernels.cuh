@@ -899,14 +899,16 @@ __global__ void __launch_bounds__(BN_TPB_LIGHT) k_sk_key_flags(int *kbad, const 
 }
 // The two sums of key k (record kfin[k] of either array of the last level; a key without tuples has none) -> affine points with
 // flags: FL_BAD for a key without tuples or with an unusable tuple, FL_INF for a sum that is the identity (factor 1 in the loop).
+// dense (the bucket path): kfin = the key offsets themselves, the records are S[k] and S[nk + k].
 template <class F, class M>
-__device__ __forceinline__ void sk_finish(M *A, uint8_t *flA, M *B, uint8_t *flB, const point<F> *S, const uint64_t *kfin, const int *kbad, size_t nk) {
+__device__ __forceinline__ void sk_finish(M *A, uint8_t *flA, M *B, uint8_t *flB, const point<F> *S, const uint64_t *kfin, const int *kbad, size_t nk,
+                                          bool dense) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nk) return;
-    const uint64_t r = kfin[k], nfin = kfin[nk];
+    const uint64_t r = dense ? k : kfin[k], nfin = dense ? nk : kfin[nk];
     M ra, rb;
     uint8_t fa = FL_BAD, fb = FL_BAD;
-    if (kfin[k + 1] > r) {
+    if (kfin[k + 1] > kfin[k]) {
         point<F> a;
         bool inf;
         copy_rec(a, S[r]);
@@ -925,13 +927,167 @@ __device__ __forceinline__ void sk_finish(M *A, uint8_t *flA, M *B, uint8_t *flB
     flB[k] = fb;
 }
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_finish_g1(g1m *A, uint8_t *flA, g1m *B, uint8_t *flB, const g1p *S, const uint64_t *kfin,
-                                                                const int *kbad, size_t nk) {
-    sk_finish<F1, g1m>(A, flA, B, flB, S, kfin, kbad, nk);
+                                                                const int *kbad, size_t nk, bool dense) {
+    sk_finish<F1, g1m>(A, flA, B, flB, S, kfin, kbad, nk, dense);
 }
 __global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_finish_g2(g2m *A, uint8_t *flA, g2m *B, uint8_t *flB, const g2p *S, const uint64_t *kfin,
-                                                                const int *kbad, size_t nk) {
-    sk_finish<F2, g2m>(A, flA, B, flB, S, kfin, kbad, nk);
+                                                                const int *kbad, size_t nk, bool dense) {
+    sk_finish<F2, g2m>(A, flA, B, flB, S, kfin, kbad, nk, dense);
 }
+
+// ---- same-key path, long segments: the two sums of a key as multi-scalar multiplications by the bucket method ---------------
+// r_i = a_i + b_i lambda, so  sum_i r_i P_i = A + phi(B),  A = sum_i a_i P_i,  B = sum_i b_i P_i  (phi linear).  Each half h is cut
+// into NW radix-16 windows: W_(h,w) = sum_v v * (sum of the P_i whose digit is v).  A per-tuple scaling costs nbits/2 doublings +
+// ~3/8 nbits additions (889 M for G1 at 64 bits); here a point enters ONE bucket per window: nbits/4 additions (~220 M), plus a
+// per-key epilogue that does not grow with the segment.  Used when a key's segment is long enough to amortise it (capi.cu).
+// Dn = the radix-16 digits as bytes, one array of npad bytes (npad = n rounded up to 16, + 16 readable) per (half, window):
+// Dn[(h * NW + w) * npad + i] = digit w of half h of tuple i's scalar.
+__global__ void __launch_bounds__(BN_TPB_LIGHT) k_sk_digits(uint8_t *Dn, const uint8_t *seed, uint64_t base, int nbits, size_t n, size_t npad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rbv_k kw;
+    rbv_scalar(kw, seed, base + i, nbits);
+    const int NW = nbits >> 3;
+    for (int w = 0; w < NW; w++) {
+        Dn[(size_t)w * npad + i] = (uint8_t)((kw.a[w >> 3] >> ((w & 7) * 4)) & 15u);
+        Dn[(size_t)(NW + w) * npad + i] = (uint8_t)((kw.b[w >> 3] >> ((w & 7) * 4)) & 15u);
+    }
+}
+// Thread (array ar, key k, half h, window w, slice s, bucket v): the sum of the points of slice s of key k's segment whose digit
+// is v.  A warp holds two slices x 16 bucket values of ONE (ar, k, h, w): every lane walks its own slice to its next match --
+// sixteen digits per step: one 128-bit load, a byte-wise compare -- then all lanes add together.  v = 0 lanes idle.  Unusable
+// or identity points are skipped, as in item_rbv_scale_proj.  out[((((ar * nk + k) * 2 + h) * NW + w) * 16 + v) * S + s].
+template <class F, class M>
+__device__ __forceinline__ void sk_bucket(point<F> *out, const M *P0, const uint8_t *fl0, const M *P1, const uint8_t *fl1, const uint8_t *Dn,
+                                          size_t npad, const uint64_t *ko, size_t nk, int NW, int S) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t v = (uint32_t)(t & 15);
+    size_t rest = t >> 4;
+    const int s = (int)(rest % (size_t)S); rest /= (size_t)S;
+    const int w = (int)(rest % (size_t)NW); rest /= (size_t)NW;
+    const int h = (int)(rest & 1); rest >>= 1;
+    const int ar = (int)(rest & 1);
+    const size_t k = rest >> 1;
+    const bool owner = k < nk && v != 0;         // whole warps stay in the loop: the additions run convergent
+    const M *P = ar ? P1 : P0;
+    const uint8_t *fl = ar ? fl1 : fl0;
+    uint64_t j = 0, end = 0;
+    if (owner) {
+        const uint64_t lo0 = ko[k], len = ko[k + 1] - lo0;
+        j = lo0 + len * (uint64_t)s / (uint64_t)S;
+        end = lo0 + len * (uint64_t)(s + 1) / (uint64_t)S;
+    }
+    const uint8_t *dn = Dn + (size_t)(h * NW + w) * npad;
+    const uint32_t vv = v * 0x01010101u;
+    point<F> acc, x;
+    pt_set_identity(acc);
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, j < end)) {
+        // every lane walks to its next match (or to the end of its slice) ...
+        bool found = false;
+#pragma unroll 1
+        while (j < end) {
+            const uint64_t jb = j & ~(uint64_t)15;
+            const uint4 q = *reinterpret_cast<const uint4 *>(dn + jb);
+            // bit i of m = digit of tuple jb + i equals v  (__vcmpeq4: 0xff per equal byte; the multiply gathers one bit per byte)
+            uint32_t m = (((__vcmpeq4(q.x, vv) & 0x01010101u) * 0x01020408u) >> 24) | ((((__vcmpeq4(q.y, vv) & 0x01010101u) * 0x01020408u) >> 24) << 4) |
+                         ((((__vcmpeq4(q.z, vv) & 0x01010101u) * 0x01020408u) >> 24) << 8) | ((((__vcmpeq4(q.w, vv) & 0x01010101u) * 0x01020408u) >> 24) << 12);
+            m &= ~((1u << (uint32_t)(j - jb)) - 1u);
+            if (end - jb < 16) m &= (1u << (uint32_t)(end - jb)) - 1u;
+            if (m) {
+                j = jb + (uint64_t)(__ffs(m) - 1);
+                found = !(fl[j] & (FL_BAD | FL_INF));
+                if (found) break;
+                j++;
+            } else {
+                j = jb + 16;
+            }
+        }
+        __syncwarp();
+        // ... then all lanes that found one add together
+        if (found) {
+            M p;
+            copy_rec(p, P[j]);
+            pt_from_affine(x, p.x, p.y, false);
+            pt_add(acc, acc, x);
+            j++;
+        }
+    }
+    if (!owner) return;
+    copy_rec(out[((((size_t)ar * nk + k) * 2 + h) * NW + w) * 16 * S + (size_t)v * S + s], acc);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_bucket_g1(g1p *out, const g1m *P0, const uint8_t *fl0, const g1m *P1, const uint8_t *fl1,
+                                                                const uint8_t *Dn, size_t npad, const uint64_t *ko, size_t nk, int NW, int S) {
+    sk_bucket<F1, g1m>(out, P0, fl0, P1, fl1, Dn, npad, ko, nk, NW, S);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_bucket_g2(g2p *out, const g2m *P0, const uint8_t *fl0, const g2m *P1, const uint8_t *fl1,
+                                                                const uint8_t *Dn, size_t npad, const uint64_t *ko, size_t nk, int NW, int S) {
+    sk_bucket<F2, g2m>(out, P0, fl0, P1, fl1, Dn, npad, ko, nk, NW, S);
+}
+// Sixteen lanes per (ar, k, h, w): W = sum_v v * bucket_v.  Lane v first sums the slices of its bucket, then a suffix scan over the
+// sixteen lanes (run_v = sum_(u >= v) bucket_u, four shuffle-and-add steps) and a tree sum of run_1 .. run_15 (four more):
+// S + 7 dependent additions instead of the 15 (S + 1) of the sequential running-sum rule.  out[((ar * nk + k) * 2 + h) * NW + w].
+template <class F>
+__device__ __forceinline__ void pt_shfl_down16(point<F> &r, const point<F> &a, int delta) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&a);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(point<F>) / 4); i++) dst[i] = __shfl_down_sync(0xffffffffu, src[i], delta, 16);
+}
+template <class F>
+__device__ __forceinline__ void sk_window(point<F> *out, const point<F> *B, size_t nwin, int S) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t win = t >> 4;
+    const int v = (int)(t & 15);
+    const bool live = win < nwin;              // the grid is padded to whole warps: dead lanes shuffle along
+    if (!live) win = nwin - 1;
+    const point<F> *b = B + win * 16 * (size_t)S + (size_t)v * S;
+    point<F> x, y;
+    pt_set_identity(x);
+    if (v)
+#pragma unroll 1
+        for (int s = 0; s < S; s++) {
+            copy_rec(y, b[s]);
+            pt_add(x, x, y);
+        }
+#pragma unroll 1
+    for (int delta = 1; delta < 16; delta <<= 1) {       // suffix scan
+        pt_shfl_down16(y, x, delta);
+        if (v + delta < 16) pt_add(x, x, y);
+    }
+    if (v == 0) pt_set_identity(x);                      // run_0 is not a term
+#pragma unroll 1
+    for (int delta = 8; delta >= 1; delta >>= 1) {       // tree sum
+        pt_shfl_down16(y, x, delta);
+        if (v < delta) pt_add(x, x, y);
+    }
+    if (live && v == 0) copy_rec(out[win], x);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_window_g1(g1p *out, const g1p *B, size_t nwin, int S) { sk_window(out, B, nwin, S); }
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_window_g2(g2p *out, const g2p *B, size_t nwin, int S) { sk_window(out, B, nwin, S); }
+// Thread (ar, k): sum_w 16^w (W_(0,w) + phi(W_(1,w))) by Horner's rule -> out[ar * nk + k], the layout k_sk_finish reads with
+// dense = true (record k of either array; a key without tuples is told from its offsets).
+template <class F>
+__device__ __forceinline__ void sk_combine(point<F> *out, const point<F> *W, size_t nk, int NW) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * nk) return;
+    const point<F> *w0 = W + t * 2 * (size_t)NW, *w1 = w0 + NW;
+    point<F> acc, x, y;
+    pt_set_identity(acc);
+#pragma unroll 1
+    for (int w = NW - 1; w >= 0; w--) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) pt_dbl(acc, acc);
+        copy_rec(x, w0[w]);
+        copy_rec(y, w1[w]);
+        F::glv_beta(y.x, y.x);
+        pt_add(x, x, y);
+        pt_add(acc, acc, x);
+    }
+    copy_rec(out[t], acc);
+}
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_combine_g1(g1p *out, const g1p *W, size_t nk, int NW) { sk_combine(out, W, nk, NW); }
+__global__ void __launch_bounds__(BN_TPB_HEAVY, BN_MINB_HEAVY) k_sk_combine_g2(g2p *out, const g2p *W, size_t nk, int NW) { sk_combine(out, W, nk, NW); }
 
 // compressed codecs
 __global__ void __launch_bounds__(BN_TPB_LIGHT) k_g1_compress(uint8_t *out, const g1m *P, const uint8_t *fl, size_t n) {

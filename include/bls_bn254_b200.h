@@ -75,7 +75,9 @@ const char *bn254_last_error(const bn254_ctx *ctx);
  * 2 two lanes per pairing, 3 the slot machine (two lanes, operands in shared memory), 4 the wide slot machine (one WARP per
  * pairing: the latency shape); results are bit-identical in every shape (the parity suite runs all of them); "wide_max" =
  * with "lanes" 0, launches of at most this many pairings use the wide shape; "chunk" = items staged per host<->device round
- * (default 2^18); "split" = concurrent slices per verification batch (default 1). */
+ * (default 2^18); "split" = concurrent slices per verification batch (default 1); "sk_msm_min" = average tuples per key from
+ * which the same-key path sums by bucket-method multi-scalar multiplications instead of scaling every point (default 128,
+ * 0 = never; same verdicts either way). */
 int bn254_ctx_set_option(bn254_ctx *ctx, const char *name, long value);
 /* Pin / unpin caller memory (cudaHostRegister) so that the chunk pipeline copies it asynchronously. */
 int bn254_host_register(void *p, size_t bytes);

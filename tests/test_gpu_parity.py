@@ -864,8 +864,17 @@ def _same_key_batch(ctx, B, rng, variant, counts, msg_len=(0, 7, 32, 100)):
     return sks, key_of, msgs, bytearray(pks), bytearray(sigs)
 
 
+@pytest.fixture(params=[0, 1], ids=["scaled-points", "bucket-msm"])
+def sk_sums(request, ctx):
+    """Both ways the same-key path forms a key's two sums: every point scaled, then segmented sums (sk_msm_min = 0: never the
+    bucket path) / bucket-method multi-scalar multiplications (sk_msm_min = 1: always)."""
+    ctx.set_option("sk_msm_min", request.param)
+    yield request.param
+    ctx.set_option("sk_msm_min", 128)
+
+
 @pytest.mark.parametrize("variant", [0, 1])
-def test_same_key_randomized_vs_oracle(ctx, orc, B, variant, shape):
+def test_same_key_randomized_vs_oracle(ctx, orc, B, variant, shape, sk_sums):
     """bn254_verify_same_key_randomized (many messages under few keys: ONE Miller loop and ONE final exponentiation per key over
     the randomised sums of that key's signatures and message points): verdicts equal the oracle's -- clean keys accept; a key
     without tuples, a tampered message, a signature under another key, an identity signature, an identity key and an
@@ -918,6 +927,7 @@ def test_same_key_randomized_multi_chunk_and_predicted_scalars(ctx, orc, B):
     c = B.Context([0])
     try:
         c.set_option("chunk", 256)
+        c.set_option("sk_msm_min", 0)
         many, names = launched(c, lambda: c.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed))
         # without the profiler the per-key tail of a chunk runs on its own stream beside the next chunk
         overlapped = [c.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed) for _ in range(3)]
@@ -926,6 +936,13 @@ def test_same_key_randomized_multi_chunk_and_predicted_scalars(ctx, orc, B):
     assert overlapped == [want] * 3
     assert many == want
     assert {"k_sk_sum_g1p", "k_sk_finish_g1", "k_sk_key_flags", "k_rbv_scale_g1p"} <= names, names
+    # the same job with the sums as bucket-method multi-scalar multiplications (default for segments this long), 128-bit scalars too
+    msm, names = launched(ctx, lambda: ctx.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed))
+    assert msm == want and {"k_sk_digits", "k_sk_bucket_g1", "k_sk_window_g1", "k_sk_combine_g1"} <= names, names
+    for bits in (64, 128):
+        got = ctx.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed[::-1], rand_bits=bits, flags=3)
+        assert got == want == orc.verify_same_key_randomized(0, bytes(pks), counts, msgs, bytes(sigs), B.DST_MIN_SIG, seed[::-1], rand_bits=bits, flags=3,
+                                                             nthreads=orc.ncpu())
     # predicted scalars: key 4's tuples a, b get sig_a + D and sig_b - [r_a / r_b] D
     R = B.R_ORDER
     a, b = start[4] + 2, start[4] + 9

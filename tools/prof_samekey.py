@@ -4,7 +4,11 @@ import numpy as np
 import bls_bn254_b200 as b
 
 ctx = b.Context([0])
-for log2n, nk in ((16, 64), (18, 64), (16, 4096)):
+import os
+SL = [int(x) for x in os.environ.get("SK_SLICES", "0").split(",")]
+for log2n, nk, sl in [(16, 64, x) for x in SL] + [(18, 64, x) for x in SL] + [(16, 4096, 0)]:
+    ctx.set_option("sk_msm_slices", sl)
+    print("slices option", sl)
     n = 1 << log2n
     kp, kko, km, kof, ksg, kexp = b.scheme.synth_same_key_np(ctx, n, nk, 0, bad_keys=(1,))
     seed = bytes(range(32))
@@ -27,6 +31,7 @@ for log2n, nk in ((16, 64), (18, 64), (16, 4096)):
         agg[r[0]][1] += r[2]
     for k, v in agg.items():
         print("   %-28s x%-3d %8.3f ms" % (k, v[0], v[1]))
+ctx.set_option("sk_msm_slices", 0)
 # streaming: 2^22 tuples under 64 keys through the host call (chunks of 2^18 tuples, tails overlapped)
 n = 1 << 22
 kp, kko, km, kof, ksg, kexp = b.scheme.synth_same_key_np(ctx, n, 1024, 0, bad_keys=(1, 700))
