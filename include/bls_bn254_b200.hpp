@@ -339,6 +339,23 @@ inline std::vector<uint8_t> verify_batch_randomized(const Context &ctx, const st
                                                 dst.data(), dst.size(), flags, seed.data(), rand_bits, group, ok.data()));
     return ok;
 }
+// Same-key randomised verification (bn254_verify_same_key_randomized): key k signed the next msg_counts[k] messages; one accept
+// flag per KEY from one Miller loop and one final exponentiation over the randomised sums of its signatures and message points.
+inline std::vector<uint8_t> verify_same_key_randomized(const Context &ctx, const std::vector<PublicKey> &pks, const std::vector<size_t> &msg_counts,
+                                                       const Messages &msgs, const std::vector<Signature> &sigs, const std::array<uint8_t, 32> &seed,
+                                                       int rand_bits = 64, uint32_t flags = 0) {
+    const size_t nk = pks.size(), n = msgs.size();
+    std::vector<uint64_t> koff(nk + 1, 0);
+    if (msg_counts.size() != nk || sigs.size() != n) throw Bn254Error(BN254_ERR_ARG, "length mismatch");
+    for (size_t k = 0; k < nk; k++) koff[k + 1] = koff[k] + msg_counts[k];
+    if (koff[nk] != n) throw Bn254Error(BN254_ERR_ARG, "msg_counts must add up to the number of messages");
+    std::vector<uint8_t> ok(nk);
+    Bytes dst = dst_of(MinSig);
+    if (nk)
+        ctx.check(bn254_verify_same_key_randomized(ctx.raw(), BN254_MIN_SIG, pks[0].bytes.data(), koff.data(), nk, msgs.data(), msgs.offsets.data(),
+                                                   n ? sigs[0].bytes.data() : nullptr, dst.data(), dst.size(), flags, seed.data(), rand_bits, ok.data()));
+    return ok;
+}
 // G2Prepared (pairings.rs:609-660) for a set of public keys: prepare once, verify many.  Tuple i of verify_batch names key
 // key_index[i]; the accept flags equal verify_batch's on the expanded key array.
 class G2Prepared {

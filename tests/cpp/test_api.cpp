@@ -140,6 +140,28 @@ int main(int argc, char **argv) {
         CHECK(prep.verify_batch(ctx, idx, msgs, sigs) == verify_batch(ctx, pks, msgs, sigs));
         CHECK(prep.verify_batch(ctx, idx, msgs, bad) == verify_batch(ctx, pks, msgs, bad));
     }
+    {   // same-key grouping: key j signs messages 3j .. 3j+2; one flag per key; one wrong signature rejects only its key
+        std::vector<PublicKey> kpk;
+        std::vector<Signature> ksig;
+        Messages kmsg;
+        std::vector<size_t> counts;
+        for (size_t j = 0; j < 4; j++) {
+            SecretKey sk;
+            sk.be.fill(0);
+            sk.be[31] = static_cast<uint8_t>(j + 9);
+            kpk.push_back(sk.public_key(ctx));
+            counts.push_back(3);
+            for (size_t q = 0; q < 3; q++) {
+                Bytes m = str("stream " + std::to_string(3 * j + q));
+                ksig.push_back(sk.sign(ctx, m));
+                kmsg.push(m);
+            }
+        }
+        CHECK(verify_same_key_randomized(ctx, kpk, counts, kmsg, ksig, seed) == std::vector<uint8_t>(4, 1));
+        std::swap(ksig[7], ksig[8]);   // both under key 2
+        std::vector<uint8_t> kk = verify_same_key_randomized(ctx, kpk, counts, kmsg, ksig, seed, 128, BN254_FLAG_CHECK_SUBGROUP);
+        CHECK(kk.size() == 4 && kk[0] == 1 && kk[1] == 1 && kk[2] == 0 && kk[3] == 1);
+    }
     Signature agg = aggregate(ctx, sigs);
     CHECK(aggregate_verify(ctx, pks, msgs, agg));
     CHECK(!aggregate_verify(ctx, pks, msgs, sigs[0]));
