@@ -96,7 +96,7 @@ struct Dev {
     size_t wide_max = 1536;
     // Chunk pipeline of the host-buffer entry points: copies run on `cp`, kernels on `st`; two staging sets.
     cudaStream_t cp = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_out[2] = {};
+    cudaEvent_t ev_in[2] = {}, ev_in2[2] = {}, ev_out[2] = {};   // ev_in2: the keys / signatures of a chunk have arrived (hashing only waits for ev_in: the messages)
     void *pin[2] = {};              // pinned result staging (used when the caller's result buffer is pageable)
     size_t pin_cap[2] = {};
     // NCCL communicator of the aggregate path (one rank per device; null on a lone device without bn254_comm_init_rank)
@@ -472,12 +472,17 @@ struct VerifyBufs {
     const g1m *ng1; const uint8_t *flc;
 };
 // pks == nullptr: the public keys are already decoded and validated in b.Q1 / b.flq1 (min-sig) or b.P1 / b.flp1 (min-pk)
+// `keys_sigs_ready`: the messages are on the device, the keys and signatures may still be on their way (host pipeline): hash
+// first, wait for the event, then decode -- the upload of 192 of a tuple's 224 bytes hides under the hash kernel
 int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base,
-                     const uint8_t *sigs, size_t lo, size_t hi, const uint8_t *dst, uint32_t dst_len, int check, uint8_t *ok) {
+                     const uint8_t *sigs, size_t lo, size_t hi, const uint8_t *dst, uint32_t dst_len, int check, uint8_t *ok,
+                     cudaEvent_t keys_sigs_ready = nullptr) {
     size_t n = hi - lo;
     const bool subgroup = (check & 2) != 0;
     check = (check & 1) | DEC_NO_IDENTITY;   // an identity key or signature never verifies (items.cuh: DEC_NO_IDENTITY)
     if (variant == BN254_MIN_SIG) {
+        if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
+        if (keys_sigs_ready) CK(d, cudaStreamWaitEvent(d.cur, keys_sigs_ready, 0));
         LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P0 + lo, b.flp0 + lo, sigs + 64 * lo, n, check);
         if (pks) {
             LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q1 + lo, b.flq1 + lo, pks + 128 * lo, n, check);
@@ -485,15 +490,15 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
                 LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq1 + lo, b.Q1 + lo, n);
             }
         }
-        if (int rc = dev_hash_g1(d, b.P1 + lo, b.flp1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         if (int rc = launch_miller2_fixed(d, n, b.F + lo, b.flf + lo, b.P0 + lo, b.flp0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo, b.flq1 + lo)) return rc;
     } else {
+        if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
+        if (keys_sigs_ready) CK(d, cudaStreamWaitEvent(d.cur, keys_sigs_ready, 0));
         LAUNCH(d, k_g2_decode, n, BN_TPB_LIGHT, b.Q0 + lo, b.flq0 + lo, sigs + 128 * lo, n, check);
         if (pks) LAUNCH(d, k_g1_decode, n, BN_TPB_LIGHT, b.P1 + lo, b.flp1 + lo, pks + 64 * lo, n, check);
         if (subgroup) {
             LAUNCH(d, k_g2_require_subgroup, n, BN_TPB_HEAVY, b.flq0 + lo, b.Q0 + lo, n);
         }
-        if (int rc = dev_hash_g2(d, b.Q1 + lo, b.flq1 + lo, msgs, off + lo, base, n, dst, dst_len, 2)) return rc;
         if (int rc = launch_miller2(d, n, b.F + lo, b.flf + lo, b.ng1, b.flc, (size_t)0, b.Q0 + lo, b.flq0 + lo, b.P1 + lo, b.flp1 + lo, b.Q1 + lo,
                                     b.flq1 + lo))
             return rc;
@@ -504,7 +509,7 @@ int dev_verify_slice(Dev &d, const VerifyBufs &b, int variant, const uint8_t *pk
 }
 // verification of one chunk, device pointers in / out
 int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint8_t *sigs,
-               size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok) {
+               size_t n, const uint8_t *dst, uint32_t dst_len, uint32_t flags, uint8_t *ok, cudaEvent_t keys_sigs_ready = nullptr) {
     int check = ((flags & (BN254_FLAG_CHECK_ON_CURVE | BN254_FLAG_CHECK_SUBGROUP)) ? 1 : 0) | ((flags & BN254_FLAG_CHECK_SUBGROUP) ? 2 : 0);
     VerifyBufs b = {};
     if (int rc = ensure_t(d, S_F, n, &b.F)) return rc;
@@ -523,7 +528,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
     }
     int S = d.nsub;
     if (d.prof || n < (size_t)2048 * (size_t)S) S = 1;   // per-kernel timing wants the kernels serial
-    if (S <= 1) return dev_verify_slice(d, b, variant, pks, msgs, off, base, sigs, 0, n, dst, dst_len, check, ok);
+    if (S <= 1) return dev_verify_slice(d, b, variant, pks, msgs, off, base, sigs, 0, n, dst, dst_len, check, ok, keys_sigs_ready);
     // fork: every slice waits for what is already queued on the main stream, then runs its own pipeline
     CK(d, cudaEventRecord(d.ev_fork, d.st));
     int rc = 0;
@@ -532,7 +537,7 @@ int dev_verify(Dev &d, int variant, const uint8_t *pks, const uint8_t *msgs, con
         d.cur = d.sub[k];
         cudaError_t e = cudaStreamWaitEvent(d.cur, d.ev_fork, 0);
         if (e != cudaSuccess) { d.cur = d.st; CK(d, e); }
-        rc = dev_verify_slice(d, b, variant, pks, msgs, off, base, sigs, lo, hi, dst, dst_len, check, ok);
+        rc = dev_verify_slice(d, b, variant, pks, msgs, off, base, sigs, lo, hi, dst, dst_len, check, ok, keys_sigs_ready);
         if (!rc && cudaEventRecord(d.ev_join[k], d.cur) != cudaSuccess) rc = BN254_ERR_CUDA_BASE;
     }
     d.cur = d.st;
@@ -1161,6 +1166,13 @@ struct Pipe {
         CK(d, cudaStreamWaitEvent(d.st, d.ev_in[s], 0));
         return 0;
     }
+    // what has been copied since inputs_ready(): recorded, NOT yet waited for -- the consumer waits right before it needs it
+    int more_inputs(cudaEvent_t *ev) {
+        int s = set();
+        CK(d, cudaEventRecord(d.ev_in2[s], d.cp));
+        *ev = d.ev_in2[s];
+        return 0;
+    }
     int d2h(uint8_t *host, bool pinned, const uint8_t *dev, size_t bytes) {
         if (!bytes) return 0;
         if (pinned) {
@@ -1339,6 +1351,7 @@ int bn254_ctx_create(bn254_ctx **out, const int *device_ids, int n_dev) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking);
         for (int k = 0; k < 2 && e == cudaSuccess; k++) {
             e = cudaEventCreateWithFlags(&d.ev_in[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_in2[k], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_out[k], cudaEventDisableTiming);
         }
         if (e != cudaSuccess) {
@@ -1511,6 +1524,7 @@ void bn254_ctx_destroy(bn254_ctx *ctx) {
             if (d.ev_tail[k]) cudaEventDestroy(d.ev_tail[k]);
         for (int k = 0; k < 2; k++) {
             if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
+            if (d.ev_in2[k]) cudaEventDestroy(d.ev_in2[k]);
             if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
             if (d.pin[k]) cudaFreeHost(d.pin[k]);
         }
@@ -1702,10 +1716,12 @@ int bn254_verify_batch(bn254_ctx *ctx, int variant, const uint8_t *pks, const ui
             if (int rc = ensure_t(d, stage_buf(S_IN_A, pipe.set()), m * rpk, &dpk)) return rc;
             if (int rc = ensure_t(d, stage_buf(S_IN_B, pipe.set()), m * rsig, &dsig)) return rc;
             if (int rc = ensure_t(d, stage_buf(S_OUT, pipe.set()), m, &dok)) return rc;
+            if (int rc = pipe.inputs_ready()) return rc;       // the messages: all the hash kernel needs
             if (int rc = pipe.h2d(dpk, pks + c * rpk, m * rpk)) return rc;
             if (int rc = pipe.h2d(dsig, sigs + c * rsig, m * rsig)) return rc;
-            if (int rc = pipe.inputs_ready()) return rc;
-            if (int rc = dev_verify(d, variant, dpk, dm, dof, base, dsig, m, ddst, dlen, flags, dok)) return rc;
+            cudaEvent_t rest;
+            if (int rc = pipe.more_inputs(&rest)) return rc;
+            if (int rc = dev_verify(d, variant, dpk, dm, dof, base, dsig, m, ddst, dlen, flags, dok, rest)) return rc;
             if (int rc = pipe.d2h(ok + c, pin_ok, dok, m)) return rc;
             if (int rc = pipe.end()) return rc;
         }
