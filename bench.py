@@ -566,8 +566,8 @@ def main():
             assert sub_ok == ref == kexp[:kk].tobytes(), "same-key verdicts differ from the oracle"
             check = "verdicts equal the construction; the first %d keys (%d tuples, one broken key) equal the oracle" % (kk, tk)
         sub["same_key"] = {"config": "2^%d (msg, sig) tuples per GPU under %d keys, sorted by key (min-sig, %d keys with one broken tuple); "
-                                     "bn254_verify_same_key_randomized: per tuple a hash to G1 and two 64-bit GLV scalar multiplications, per KEY the two "
-                                     "sums, one two-pair Miller loop and one final exponentiation; one accept byte per key" % (args.log2n, nks, len(bad_keys)),
+                                     "bn254_verify_same_key_randomized: per tuple a hash to G1 and a share of the key's two sums (bucket-method "
+                                     "multi-scalar multiplications over 64-bit GLV scalars), per KEY one two-pair Miller loop and one final exponentiation; one accept byte per key" % (args.log2n, nks, len(bad_keys)),
                            "verifications_per_sec": n * world * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
                            "e2e_verifications_per_sec": n * world * args.steps / (ems * 1e-3), "keys": nks, "rand_bits": 64, "checked": check}
         del dkp, dkm, dks, dkof, dkok

@@ -786,12 +786,14 @@ struct SkPlan {
     std::vector<Level> levels;
     size_t kfin_pos = 0, nfin = 0, nb_max[2] = {0, 0};   // nb_max[j]: most blocks among the levels written to ping-pong buffer j
 };
-void sk_plan(SkPlan &p, const uint64_t *koff, size_t nk) {
+// a chunk of n tuples under nk keys takes the bucket path (no levels needed: the bucket kernels read the key offsets)
+inline bool sk_use_msm(const Dev &d, size_t n, size_t nk) { return d.sk_msm_min && n >= d.sk_msm_min * nk; }
+void sk_plan(SkPlan &p, const uint64_t *koff, size_t nk, bool with_levels) {
     const uint64_t t0 = koff[0];
     std::vector<uint64_t> cur(nk + 1), nxt(nk + 1);
     for (size_t k = 0; k <= nk; k++) cur[k] = koff[k] - t0;
     p.blob.assign(cur.begin(), cur.end());
-    for (;;) {
+    while (with_levels) {
         uint64_t longest = 0;
         for (size_t k = 0; k < nk; k++) longest = std::max(longest, cur[k + 1] - cur[k]);
         if (longest <= 1) break;
@@ -846,7 +848,7 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
     // per-tuple work than scaling every point; short segments: scale every point, then the planned segmented sums.
     // "sk_msm_min" = smallest average segment length that takes the bucket path (0: never).
     const int NW = nbits >> 3;                                     // radix-16 windows per scalar half
-    const bool msm = d.sk_msm_min && n >= d.sk_msm_min * nk;
+    const bool msm = sk_use_msm(d, n, nk);
     const size_t nwin = 2 * nk * 2 * (size_t)NW;                   // (array, key, half, window)
     int msm_S = 1;                                                 // slices per segment: enough bucket threads to fill the machine
     if (msm) {
@@ -930,8 +932,10 @@ int dev_verify_same_key(Dev &d, int variant, const uint8_t *pks, size_t nk, cons
         }
         LAUNCH(d, k_sk_finish_g2, nk, BN_TPB_HEAVY, (g2m *)ka, flka, (g2m *)kb, flkb, src, msm ? ko : kfin, kbad, nk, msm);
     }
-    // ---- the per-key tail: on the launch stream, or on d.tail beside the next chunk (then in the throughput shape: a hidden tail
-    //      must not take the shared memory and registers the overlapped kernels want) ----
+    // ---- the per-key tail: on the launch stream, or on d.tail beside the next chunk.  tail_hidden would put a hidden tail into
+    //      the throughput shape (as the randomised path does for its per-group tail); here the host entry leaves it off: a few
+    //      dozen keys per chunk are a few dozen warps in the wide shape, and its 3.3 ms latency (lane pairs: 8 ms, as long as a
+    //      whole chunk) lets staging set k be handed back before chunk k + 1 ends, so the host can queue chunk k + 2 in time ----
     struct WideOff {
         Dev &d; size_t keep;
         WideOff(Dev &dd, bool off) : d(dd), keep(dd.wide_max) { if (off) d.wide_max = 0; }
@@ -1809,7 +1813,7 @@ int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t 
             while (e < hi && e - c < ctx->chunk && key_offsets[e + 1] - key_offsets[c] <= ctx->chunk) e++;
             const size_t nk = e - c, t0 = (size_t)key_offsets[c], m = (size_t)key_offsets[e] - t0;
             plan = SkPlan();
-            sk_plan(plan, key_offsets + c, nk);
+            sk_plan(plan, key_offsets + c, nk, !sk_use_msm(d, m, nk));
             if (int rc = pipe.begin(pin_ok ? 0 : pad64(nk))) return rc;
             const uint8_t *dm = nullptr; const uint64_t *dof = nullptr; uint64_t base = 0;
             if (m)
@@ -1825,7 +1829,7 @@ int bn254_verify_same_key_randomized(bn254_ctx *ctx, int variant, const uint8_t 
             if (int rc = pipe.h2d(dplan, plan.blob.data(), plan.blob.size() * sizeof(uint64_t))) return rc;
             if (int rc = pipe.inputs_ready()) return rc;
             if (int rc = dev_verify_same_key(d, variant, dpk, nk, dplan, plan, dm, dof, base, dsig, m, dseed, (uint64_t)t0, rand_bits, ddst, dlen,
-                                             flags, dok, overlap_tail ? pipe.set() : -1, e < hi /* another chunk follows and hides this tail */))
+                                             flags, dok, overlap_tail ? pipe.set() : -1, false /* the tail keeps the latency shape: see dev_verify_same_key */))
                 return rc;
             if (int rc = pipe.d2h(ok_keys + c, pin_ok, dok, nk)) return rc;
             if (int rc = pipe.end()) return rc;
@@ -2445,7 +2449,7 @@ int bn254_verify_same_key_randomized_dev(bn254_ctx *ctx, int variant, const uint
     const uint8_t *ddst; uint32_t dlen;
     uint64_t *dplan = nullptr;
     SkPlan plan;
-    sk_plan(plan, key_offsets, n_keys);
+    sk_plan(plan, key_offsets, n_keys, !sk_use_msm(d, (size_t)key_offsets[n_keys], n_keys));
     int rc = stage_dst(d, dst, dst_len, false, &ddst, &dlen);
     if (!rc) rc = ensure_t(d, S_IN_C, plan.blob.size(), &dplan);
     if (!rc && cudaMemcpyAsync(dplan, plan.blob.data(), plan.blob.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st) != cudaSuccess) {

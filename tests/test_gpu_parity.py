@@ -529,6 +529,14 @@ def test_multi_device_ctx(orc, B):
         seed = b"\x77" * 32
         want = bytes(int(all(exp[g:g + 32])) for g in range(0, 700, 32))
         assert c2.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=32) == want == c1.verify_batch_randomized(0, pks, msgs, sigs, B.DST_MIN_SIG, seed, group=32)
+        # same-key grouping shares out whole keys; the scalars follow the tuple's index in the CALL, whichever device takes it
+        counts = [40, 0, 300, 7, 160, 90, 1, 33]
+        _, _, kmsgs, kpks, ksigs = _same_key_batch(c1, B, random.Random(5), 0, counts, msg_len=(24,))
+        t = sum(counts[:5]) + 17
+        ksigs[64 * t:64 * t + 64] = ksigs[64 * (t + 1):64 * (t + 2)]              # key 5 (device 1's share)
+        got = c2.verify_same_key_randomized(0, bytes(kpks), counts, kmsgs, bytes(ksigs), B.DST_MIN_SIG, seed)
+        assert got == bytes([1, 0, 1, 1, 1, 0, 1, 1]) == c1.verify_same_key_randomized(0, bytes(kpks), counts, kmsgs, bytes(ksigs), B.DST_MIN_SIG, seed)
+        assert got == orc.verify_same_key_randomized(0, bytes(kpks), counts, kmsgs, bytes(ksigs), B.DST_MIN_SIG, seed, nthreads=orc.ncpu())
     finally:
         c1.close()
         c2.close()
@@ -586,13 +594,14 @@ def test_profile_and_launch_count(ctx, orc, B):
     names = [r[0] for r in recs]
     # a batch this small runs the latency shape of the two pairing kernels (one warp per pairing, k_w_*) plus the fix-up pass
     # for dead pairs; "wide_max" = 0 sends it to the lane-pair shape
-    assert names == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_w_miller2_fixed", "k_vm_fixup_miller2_fixed", "k_w_final_exp", "k_fp12_is_one"]
+    # (hashing first: in the host pipeline it only waits for the messages, the keys and signatures arrive under it)
+    assert names == ["k_hash_g1", "k_g1_decode", "k_g2_decode", "k_w_miller2_fixed", "k_vm_fixup_miller2_fixed", "k_w_final_exp", "k_fp12_is_one"]
     ctx.set_option("wide_max", 0)
     ctx.profile(True)
     try:
         assert ctx.verify_batch(0, pks, msgs, sigs, B.DST_MIN_SIG) == exp
         names = [r[0] for r in ctx.profile_drain()]
-        assert names == ["k_g1_decode", "k_g2_decode", "k_hash_g1", "k_miller2_fixed_l2", "k_final_exp_l2", "k_fp12_is_one"]
+        assert names == ["k_hash_g1", "k_g1_decode", "k_g2_decode", "k_miller2_fixed_l2", "k_final_exp_l2", "k_fp12_is_one"]
     finally:
         ctx.profile(False)
         ctx.set_option("wide_max", 1536)
