@@ -593,11 +593,11 @@ BN_INL uint32_t ctz32(uint32_t x) {  // x != 0
     return (uint32_t)__builtin_ctz(x);
 #endif
 }
-BN_INL uint32_t shr_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [z, z + 32) of hi:lo, 0 < z < 32
+BN_INL uint32_t shr_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [z, z + 32) of hi:lo, 0 <= z < 32
 #if BN_PTX
     return __funnelshift_r(lo, hi, z);
 #else
-    return (lo >> z) | (hi << (32 - z));
+    return z ? (lo >> z) | (hi << (32 - z)) : lo;
 #endif
 }
 BN_NOINL bool fp_is_square_jacobi(const fp &x) {
@@ -615,32 +615,32 @@ BN_NOINL bool fp_is_square_jacobi(const fp &x) {
     // guarantees termination should a caller ever hand in a value that is not a residue below p
 #pragma unroll 1
     for (int pass = 0; pass < 2048; pass++) {
-        // a != 0.  Strip the factors of two: (2 / n) = -1 iff n = 3, 5 mod 8.
-        uint32_t lo = a[0];
-        if (lo == 0) {  // 32 of them at once (an even count: no sign change)
+        // a != 0.  Strip the factors of two: (2 / n) = -1 iff n = 3, 5 mod 8.  Whole zero words (32 factors: an even count, no
+        // sign change) go in a loop of their own -- as a `continue` branch of this loop its register rotation was merged into
+        // the common loop tail and every pass paid for it.  z = 0 only before the first subtraction; the shifts take it.
+#pragma unroll 1
+        while (a[0] == 0) {
 #pragma unroll
             for (int i = 0; i < 7; i++) a[i] = a[i + 1];
             a[7] = 0;
-            continue;
         }
-        uint32_t z = ctz32(lo);
-        if (z) {
+        const uint32_t z = ctz32(a[0]);
 #pragma unroll
-            for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
-            a[7] >>= z;
-            uint32_t n8 = n[0] & 7u;
-            neg ^= (z & 1u) & (uint32_t)((n8 == 3u) | (n8 == 5u));
-        }
+        for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
+        a[7] >>= z;
+        const uint32_t n8 = n[0] & 7u;
+        neg ^= (z & 1u) & (uint32_t)((n8 == 3u) | (n8 == 5u));
         // a odd.  d = a - n; when a < n the roles swap (reciprocity: sign flips iff both are 3 mod 4) and a - n becomes n - a.
+        // (both differences as borrow chains and a select: cheaper than negating d limb by limb)
+        uint32_t e[8];
         uint32_t lt = sub_n(d, a, n);
+        (void)sub_n(e, n, a);
         neg ^= ((a[0] & n[0]) >> 1) & lt & 1u;
-        uint32_t carry = lt & 1u, zero = 0;
+        uint32_t zero = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             n[i] = lt ? a[i] : n[i];
-            uint32_t t = d[i] ^ lt;  // two's complement negation of d when lt
-            uint32_t s = t + carry;
-            carry = (uint32_t)(s < t);
+            uint32_t s = lt ? e[i] : d[i];
             a[i] = s;
             zero |= s;
         }
@@ -648,11 +648,11 @@ BN_NOINL bool fp_is_square_jacobi(const fp &x) {
     }
     return neg == 0;
 }
-BN_INL uint32_t shl_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [32 - z, 64 - z) of hi:lo, 0 < z < 32
+BN_INL uint32_t shl_pair(uint32_t lo, uint32_t hi, uint32_t z) {  // bits [32 - z, 64 - z) of hi:lo, 0 <= z < 32
 #if BN_PTX
     return __funnelshift_l(lo, hi, z);
 #else
-    return (hi << z) | (lo >> (32 - z));
+    return z ? (hi << z) | (lo >> (32 - z)) : hi;
 #endif
 }
 // fp.rs:207-210 (the crate calls crypto-bigint's inv_odd_mod): a^-1, 0 -> 0.  Same value as a^(p-2), computed by a
@@ -683,8 +683,9 @@ BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
     // guarantees termination should a caller ever hand in a value that is not a residue below p
 #pragma unroll 1
     for (int pass = 0; pass < 2048; pass++) {
-        uint32_t lo = a[0];
-        if (lo == 0) {  // 32 trailing zeros at once
+        // 32 trailing zeros at once, in a loop of their own (see fp_is_square_jacobi); z = 0 only before the first subtraction
+#pragma unroll 1
+        while (a[0] == 0) {
 #pragma unroll
             for (int i = 0; i < 7; i++) a[i] = a[i + 1];
             a[7] = 0;
@@ -692,32 +693,28 @@ BN_NOINL void fp_inv_bingcd(fp &r, const fp &x) {
             for (int i = 7; i > 0; i--) N[i] = N[i - 1];
             N[0] = 0;
             kk += 32;
-            continue;
         }
-        uint32_t z = ctz32(lo);
-        if (z) {
+        const uint32_t z = ctz32(a[0]);
 #pragma unroll
-            for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
-            a[7] >>= z;
+        for (int i = 0; i < 7; i++) a[i] = shr_pair(a[i], a[i + 1], z);
+        a[7] >>= z;
 #pragma unroll
-            for (int i = 7; i > 0; i--) N[i] = shl_pair(N[i - 1], N[i], z);
-            N[0] <<= z;
-            kk += z;
-        }
+        for (int i = 7; i > 0; i--) N[i] = shl_pair(N[i - 1], N[i], z);
+        N[0] <<= z;
+        kk += z;
         // a, n odd.  d = a - n; a < n swaps the roles: (a, A) <- (n - a, A + N), (n, N) <- (a, A), sigma <- -sigma
         uint32_t lt = sub_n(d, a, n);
-        uint32_t S[8];
+        uint32_t e[8], S[8];
+        (void)sub_n(e, n, a);
         (void)add_n(S, A, N);
         sigma_neg ^= lt & 1u;
-        uint32_t carry = lt & 1u, zero = 0;
+        uint32_t zero = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             n[i] = lt ? a[i] : n[i];
             N[i] = lt ? A[i] : N[i];
             A[i] = S[i];
-            uint32_t t = d[i] ^ lt;
-            uint32_t s2 = t + carry;
-            carry = (uint32_t)(s2 < t);
+            uint32_t s2 = lt ? e[i] : d[i];
             a[i] = s2;
             zero |= s2;
         }
