@@ -349,6 +349,20 @@ BN_INL void fp_sub(fp &r, const fp &a, const fp &b) {  // fp.rs:396-398
     r = s;
 }
 BN_INL void fp_dbl(fp &r, const fp &a) { fp_add(r, a, a); }
+// Unreduced sum / difference for values that go straight into ONE product as its two factors: a + b in [0, 2p) and
+// a - b + p in (0, 2p).  fp_mul of two values below 2p stays inside its frame (rows < 2p 2^32, as in fp_dot2) and ends below
+// (4p^2 + R p) / R < 1.76 p, so its single conditional subtraction still returns the canonical residue.
+BN_INL void fp_add_nr(fp &r, const fp &a, const fp &b) {
+    fp s;
+    (void)add_n(s.v, a.v, b.v);
+    r = s;
+}
+BN_INL void fp_sub_nr(fp &r, const fp &a, const fp &b) {
+    fp s;
+    (void)sub_n(s.v, a.v, b.v);
+    add_p_masked(s.v, 0xffffffffu);
+    r = s;
+}
 BN_INL bool fp_is_zero(const fp &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) == 0; }
 BN_INL bool fp_eq(const fp &a, const fp &b) {
     uint32_t d = 0;
@@ -364,6 +378,15 @@ BN_INL void fp_neg(fp &r, const fp &a) {  // fp.rs:400-402
     fp z;
     fp_set_zero(z);
     fp_sub(r, z, a);
+}
+// r = p - a, in (0, p]: the negation WITHOUT the a == 0 fix-up (p instead of 0), one borrow chain against immediates instead of
+// fp_neg's three.  Only for a value that goes straight into a product as the ROW-SCANNED operand (b of fp_mul, b / d of
+// fp_dot2), which may be any 256-bit value congruent to what is meant: p there multiplies to 0 mod p like 0 does.
+BN_INL void fp_neg_rs(fp &r, const fp &a) {
+    const uint32_t pl[8] = {p_limb(0), p_limb(1), p_limb(2), p_limb(3), p_limb(4), p_limb(5), p_limb(6), p_limb(7)};
+    fp s;
+    (void)sub_n(s.v, pl, a.v);
+    r = s;
 }
 BN_INL void fp_select(fp &r, bool c, const fp &a, const fp &b) {  // r = c ? a : b
 #pragma unroll
@@ -416,6 +439,10 @@ BN_INL void fp_mul_inl(fp &r, const fp &a, const fp &b) {  // fp.rs:404-407
 // T + 3p*2^32 < 2^288 so the 9-word frame holds, and two conditional subtractions finish.
 // This is how Fp2 products are formed: c0 = a0 b0 + a1 (-b1), c1 = a0 b1 + a1 b0 -- 2 x 200 wide
 // IMADs and one negation instead of Karatsuba's 3 x 136 and five additions.
+// FACTORS_LE_P = true: the caller guarantees b, d <= p as well (a, c < p always).  The closing value is exactly
+// (a b + c d + M p) / R with M < R, i.e. below p (1 + 2p/R) < 1.38 p then, and ONE conditional subtraction finishes; with
+// arbitrary 256-bit row-scanned operands it is below 3p and takes two.
+template <bool FACTORS_LE_P = false>
 BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &d) {
     BN_COUNT_OPS(392);   // two product rows (2 x 128) + one reduction (128) + 8 quotient digits
     uint32_t E[8], O[8], m;
@@ -446,7 +473,7 @@ BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &
     uint32_t hi[8] = {E[1], E[2], E[3], E[4], E[5], E[6], E[7], 0u};
     (void)add_n(s.v, O, hi);  // < 3p + 1 < 2^256
     fp_reduce_once(s);
-    fp_reduce_once(s);
+    if (!FACTORS_LE_P) fp_reduce_once(s);
     r = s;
 }
 
@@ -455,6 +482,7 @@ BN_INL void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &
 // One warp alone reaches only ~64 % of the IMAD pipe on a single dot product (dependent carry chains,
 // measured with k_fp_peak); two interleaved instruction streams give the scheduler what a second warp
 // would.  Same frame and bounds as fp_dot2_inl.
+template <bool FACTORS_LE_P = false>
 BN_INL void fp_dot2x2_inl(fp &r0, fp &r1, const fp &a, const fp &c, const fp &b0, const fp &d0, const fp &b1, const fp &d1) {
     BN_COUNT_OPS(784);
     uint32_t E0[8], O0[8], E1[8], O1[8], m0, m1;
@@ -503,8 +531,10 @@ BN_INL void fp_dot2x2_inl(fp &r0, fp &r1, const fp &a, const fp &c, const fp &b0
     (void)add_n(s1.v, O1, h1);
     fp_reduce_once(s0);
     fp_reduce_once(s1);
-    fp_reduce_once(s0);
-    fp_reduce_once(s1);
+    if (!FACTORS_LE_P) {
+        fp_reduce_once(s0);
+        fp_reduce_once(s1);
+    }
     r0 = s0;
     r1 = s1;
 }

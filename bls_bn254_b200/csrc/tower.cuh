@@ -99,16 +99,16 @@ BN_INL void fp2_tadd(fp2 &z, const fp2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp
 BN_FP2MUL void fp2_mul(fp2 &r, const fp2 &a, const fp2 &b) {
     fp2 x = a, y = b, z;
     fp nb1;
-    fp_neg(nb1, y.c1);
-    fp_dot2x2_inl(z.c0, z.c1, x.c0, x.c1, y.c0, nb1, y.c1, y.c0);
+    fp_neg_rs(nb1, y.c1);   // row-scanned operand of the dot product: p - b1 will do
+    fp_dot2x2_inl<true>(z.c0, z.c1, x.c0, x.c1, y.c0, nb1, y.c1, y.c0);   // every factor <= p: one closing subtraction
     r = z;
 }
 // fp2.rs:392-402
 BN_FP2MUL void fp2_sqr(fp2 &r, const fp2 &a) {
     fp2 x = a, z;
     fp s, d, m;
-    fp_add(s, x.c0, x.c1);
-    fp_sub(d, x.c0, x.c1);
+    fp_add_nr(s, x.c0, x.c1);   // both below 2p and used once, as the factors of the next product
+    fp_sub_nr(d, x.c0, x.c1);
     fp_mul(m, x.c0, x.c1);
     fp_mul(z.c0, s, d);
     fp_dbl(z.c1, m);
@@ -305,10 +305,10 @@ BN_NOINL void fp2_mul(fp2l &r, const fp2l &a, const fp2l &b) {
     bool odd = lane_par() != 0;
     lane_xchg(pa, x0);
     lane_xchg(pb, y0);
-    fp_neg(npb, pb);
+    fp_neg_rs(npb, pb);     // row-scanned operand of the dot product: p - b1 will do
     fp_select(u, odd, pb, y0);
     fp_select(w, odd, y0, npb);
-    fp_dot2_inl(o, x0, u, pa, w);
+    fp_dot2_inl<true>(o, x0, u, pa, w);   // every factor <= p: one closing subtraction
     r.v = o;
 }
 BN_NOINL void fp2_sqr(fp2l &r, const fp2l &a) {
@@ -316,8 +316,8 @@ BN_NOINL void fp2_sqr(fp2l &r, const fp2l &a) {
     bool odd = lane_par() != 0;
     lane_xchg(pa, x0);
     fp_select(s, odd, pa, x0);  // a0
-    fp_add(x, s, pa);           // even: a0 + a1, odd: a0 + a0
-    fp_sub(d, x0, pa);
+    fp_add_nr(x, s, pa);        // even: a0 + a1, odd: a0 + a0     (below 2p, not reduced: the factors of ONE product)
+    fp_sub_nr(d, x0, pa);       // a0 - a1 + p
     fp_select(y, odd, x0, d);   // even: a0 - a1, odd: a1
     fp_mul(o, x, y);
     r.v = o;
@@ -330,7 +330,7 @@ BN_NOINL void fp2_mul_fp(fp2l &r, const fp2l &a, const fp &s) {
 BN_NOINL void fp2_mul_xi(fp2l &r, const fp2l &a) {
     fp x0 = a.v, pa, n, t, u, o;
     lane_xchg(pa, x0);
-    fp_neg(n, pa);
+    fp_neg_rs(n, pa);   // p - a1 in (0, p]: t + n < 2p, the one conditional subtraction of fp_add still lands in [0, p)
     fp_mul9(t, x0);
     fp_select(u, lane_par() != 0, pa, n);
     fp_add(o, t, u);
@@ -339,7 +339,7 @@ BN_NOINL void fp2_mul_xi(fp2l &r, const fp2l &a) {
 BN_NOINL void fp2_xi_add(fp2l &r, const fp2l &a, const fp2l &b) {  // xi a + b in one call
     fp x0 = a.v, y = b.v, pa, n, t, u, o;
     lane_xchg(pa, x0);
-    fp_neg(n, pa);
+    fp_neg_rs(n, pa);   // as in fp2_mul_xi
     fp_mul9(t, x0);
     fp_select(u, lane_par() != 0, pa, n);
     fp_add(o, t, u);
