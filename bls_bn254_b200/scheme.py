@@ -116,6 +116,39 @@ def verify_randomized(ctx, pks, msgs, sigs, variant=MIN_SIG, dst=None, flags=VAL
     return bytes(out)
 
 
+def verify_same_key(ctx, pks, msg_counts, msgs, sigs, variant=MIN_SIG, dst=None, flags=VALIDATE, rand_bits=64, seed=None):
+    """Many messages under few keys: key k signed the next msg_counts[k] messages (tuples sorted by key).  Returns n accept
+    bytes like verify(): every key first gets ONE randomised pairing check over all its tuples
+    (bn254_verify_same_key_randomized: error probability <= 2^-rand_bits per key); the tuples of a key that passes are accepted
+    wholesale, those of a rejected key are re-verified one by one with the exact predicate.  `seed` and `flags` as in
+    verify_randomized()."""
+    dst = _dst(variant) if dst is None else dst
+    seed = os.urandom(32) if seed is None else seed
+    blob, off = pack_msgs(msgs) if not isinstance(msgs, tuple) else msgs
+    n = len(off) - 1
+    if n == 0:
+        return b""
+    keys_ok = ctx.verify_same_key_randomized(variant, pks, msg_counts, (blob, off), sigs, dst, seed, rand_bits=rand_bits, flags=flags)
+    out = bytearray(n)
+    rpk, rsig = (128, 64) if variant == MIN_SIG else (64, 128)
+    redo, redo_key, lo = [], [], 0
+    for k, c in enumerate(msg_counts):
+        if keys_ok[k]:
+            out[lo:lo + c] = b"\x01" * c
+        else:
+            redo.extend(range(lo, lo + c))
+            redo_key.extend([k] * c)
+        lo += c
+    if redo:
+        blob_b = bytes(blob)
+        sub_msgs = [blob_b[off[i]:off[i + 1]] for i in redo]
+        sub_pks = b"".join(pks[k * rpk:(k + 1) * rpk] for k in redo_key)
+        sub_sigs = b"".join(sigs[i * rsig:(i + 1) * rsig] for i in redo)
+        for i, v in zip(redo, ctx.verify_batch(variant, sub_pks, sub_msgs, sub_sigs, dst, flags)):
+            out[i] = v
+    return bytes(out)
+
+
 def aggregate(ctx, sigs, variant=MIN_SIG):
     """Sum of signatures (one wire-format point)."""
     return ctx.g1_sum(sigs) if variant == MIN_SIG else ctx.g2_sum(sigs)

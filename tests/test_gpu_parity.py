@@ -911,6 +911,11 @@ def test_same_key_randomized_vs_oracle(ctx, orc, B, variant, shape, sk_sums):
         got = ctx.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed, rand_bits=bits, flags=flags)
         ref = orc.verify_same_key_randomized(variant, bytes(pks), counts, msgs, bytes(sigs), dst, seed, rand_bits=bits, flags=flags, nthreads=orc.ncpu())
         assert got == ref == want, (flags, bits)
+    # the scheme layer turns per-key verdicts into per-tuple ones: rejected keys are re-verified exactly
+    per_tuple = B.scheme.verify_same_key(ctx, bytes(pks), counts, msgs, bytes(sigs), variant, flags=0, seed=seed)
+    key_of = [k for k, c in enumerate(counts) for _ in range(c)]
+    exact = ctx.verify_batch(variant, b"".join(bytes(pks[k * rpk:(k + 1) * rpk]) for k in key_of), msgs, bytes(sigs), dst)
+    assert per_tuple == exact and 0 < sum(exact) < len(exact)
     assert ctx.verify_same_key_randomized(variant, b"", [], [], b"", dst, seed) == b""
     assert ctx.verify_same_key_randomized(variant, bytes(pks[:2 * rpk]), [0, 0], [], b"", dst, seed) == b"\x00\x00"
     with pytest.raises(B.Bn254Error):
