@@ -98,6 +98,29 @@ BN_INL void ell_sel(fp12_t<T2> &f, const line_t<T2> &l, const fp &px, const fp &
     fp2_select(c2, live, l.c, zero);
     fp12_mul_by_034(f, c0, c1, c2);
 }
+// The evaluated line alone, (a yP, b xP, c), neutralised to 1 + 0 w + 0 w^3 for a dead pair when `sel`: what the two-pair loops
+// hand to fp12_mul_by_034_034.
+template <class T2>
+BN_INL void line_eval(T2 &c0, T2 &c3, T2 &c4, const line_t<T2> &l, const fp &px, const fp &py, bool sel, bool live) {
+    fp2_mul_fp(c0, l.a, py);
+    fp2_mul_fp(c3, l.b, px);
+    c4 = l.c;
+    if (sel) {
+        T2 one, zero;
+        fp2_set_one(one);
+        fp2_sub(zero, one, one);
+        fp2_select(c0, live, c0, one);
+        fp2_select(c3, live, c3, zero);
+        fp2_select(c4, live, c4, zero);
+    }
+}
+BN_INL void line_fixed(line_t<fp2> &l, int idx) { l = *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]); }
+BN_INL void line_fixed(line_t<fp2l> &l, int idx) {
+    const line_t<fp2> &m = *reinterpret_cast<const line_t<fp2> *>(&k::NEG_G2_LINES[idx][0][0][0]);
+    fp2_load(l.a, m.a);
+    fp2_load(l.b, m.b);
+    fp2_load(l.c, m.c);
+}
 // does this Fp2 representation branch around dead pairs (one thread per item) or neutralise them (lane pairs)?
 template <class T2> struct skips_dead { static const bool value = true; };
 #if BN_LANES_CONVERGENT
@@ -118,6 +141,9 @@ BN_INL void ell_fixed(fp12_t<fp2l> &f, int idx, const fp &px, const fp &py, bool
     else ell_sel(f, l, px, py, live);
 }
 
+#ifndef BN_PAIR_LINES
+#define BN_PAIR_LINES 1
+#endif
 // Product of NP Miller loops with one shared squaring per step (multi_miller_loop,
 // pairings.rs:808-857).  Pair i is skipped when live[i] is false (identity inputs contribute 1,
 // pairings.rs:820-835).  When FIXED0, pair 0 is (P0, -g2) and its 88 lines come from the
@@ -143,6 +169,30 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
     for (int s = 0; s < BN254_ATE_NAF_LEN; s++) {
         int d = k::ATE_NAF[s];
         if (s) fp12_sqr(f, f);  // f = 1 on the first step
+#if BN_PAIR_LINES
+        // Two pairs: the two lines of a step are multiplied with each other first and f once with their product (23 Fp2
+        // products instead of 26).  One thread per item keeps the per-pair path when a pair is dead (it branches around it).
+        if (NP == 2 && (!skip || (live[0] && live[1]))) {
+            T2 a0, b0, c0, a1, b1, c1;
+            if (FIXED0) line_fixed(l, idx);
+            else doubling_step(l, r[0]);
+            line_eval(a0, b0, c0, l, *px[0], *py[0], !skip, live[0]);
+            doubling_step(l, r[1]);
+            line_eval(a1, b1, c1, l, *px[1], *py[1], !skip, live[1]);
+            fp12_mul_by_034_034(f, a0, b0, c0, a1, b1, c1);
+            idx++;
+            if (d) {
+                if (FIXED0) line_fixed(l, idx);
+                else addition_step(l, r[0], *qx[0], d > 0 ? *qy[0] : nqy[0]);
+                line_eval(a0, b0, c0, l, *px[0], *py[0], !skip, live[0]);
+                addition_step(l, r[1], *qx[1], d > 0 ? *qy[1] : nqy[1]);
+                line_eval(a1, b1, c1, l, *px[1], *py[1], !skip, live[1]);
+                fp12_mul_by_034_034(f, a0, b0, c0, a1, b1, c1);
+                idx++;
+            }
+            continue;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (skip && !live[i]) continue;

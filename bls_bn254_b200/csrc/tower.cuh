@@ -518,6 +518,38 @@ BN_NOINL void fp12_mul_by_034(fp12_t<T2> &f, const T2 &c0, const T2 &c3, const T
     fp6_sub(f.c1, t1, s);
     fp6_add_mulv(f.c0, t0, s);
 }
+// f <- f * l * l' for TWO sparse elements l = a + (b + c v) w, l' = a' + (b' + c' v) w (the lines of the two pairs of one Miller
+// step).  The sparse-by-sparse product first,
+//     l l' = (a a' + xi c c') + b b' v + (b c' + c b') v^2  +  ((a b' + a' b) + (a c' + a' c) v) w
+// (six Fp2 products with Karatsuba on the three cross terms), then f times that -- one coefficient of its w part is zero:
+// 6 + 5 + 6 products.  23 Fp2 products instead of the 2 x 13 of two fp12_mul_by_034.
+template <class T2>
+BN_NOINL void fp12_mul_by_034_034(fp12_t<T2> &f, const T2 &a, const T2 &b, const T2 &c, const T2 &a2, const T2 &b2, const T2 &c2) {
+    fp6_t<T2> g0, t1, s;
+    T2 g10, g11;
+    {
+        T2 aa, bb, cc, t;
+        fp2_mul(aa, a, a2);
+        fp2_mul(bb, b, b2);
+        fp2_mul(cc, c, c2);
+        fp2_mul_sums(t, b, c, b2, c2); fp2_sub2(g0.c2, t, bb, cc);
+        fp2_mul_sums(t, a, b, a2, b2); fp2_sub2(g10, t, aa, bb);
+        fp2_mul_sums(t, a, c, a2, c2); fp2_sub2(g11, t, aa, cc);
+        fp2_xi_add(g0.c0, cc, aa);
+        g0.c1 = bb;
+    }
+    // f's own halves serve as temporaries as soon as they are consumed (the stack of the Miller kernels is what they run on)
+    fp6_add(s, f.c0, f.c1);                  // f0 + f1
+    fp6_mul_by_01(t1, f.c1, g10, g11);       // t1 = f1 g1            (f.c1 is free now)
+    fp6_mul(f.c1, f.c0, g0);                 // t0 = f0 g0 in f.c1    (f.c0 is free now)
+    fp2_add(g0.c0, g0.c0, g10);              // g0 + g1
+    fp2_add(g0.c1, g0.c1, g11);
+    fp6_mul(f.c0, s, g0);                    // (f0 + f1)(g0 + g1) in f.c0
+    fp6_sub(s, f.c0, f.c1);
+    fp6_sub(s, s, t1);                       // the new f1
+    fp6_add_mulv(f.c0, f.c1, t1);            // the new f0 = t0 + v t1
+    f.c1 = s;
+}
 // coefficient of w^i: i even -> c0.c(i/2), i odd -> c1.c((i-1)/2)
 template <class T2>
 BN_INL T2 &fp12_coeff(fp12_t<T2> &a, int i) {
