@@ -306,6 +306,18 @@ BN_INL void miller_loop_prepared(fp12_t<T2> &f, const fp &p0x, const fp &p0y, bo
         if (s && s < BN254_ATE_NAF_LEN) fp12_sqr(f, f);
 #pragma unroll 1
         for (int j = 0; j < nlines; j++) {
+#if BN_PAIR_LINES
+            if (!skip || (live0 && live1)) {   // both lines of the step first, then f once (fp12_mul_by_034_034)
+                T2 a0, b0, c0, a1, b1, c1;
+                line_fixed(l, idx);
+                line_eval(a0, b0, c0, l, p0x, p0y, !skip, live0);
+                line_load(l, tab1[idx]);
+                line_eval(a1, b1, c1, l, p1x, p1y, !skip, live1);
+                fp12_mul_by_034_034(f, a0, b0, c0, a1, b1, c1);
+                idx++;
+                continue;
+            }
+#endif
             if (!skip || live0) ell_fixed(f, idx, p0x, p0y, live0);
             if (!skip || live1) {
                 line_load(l, tab1[idx]);
