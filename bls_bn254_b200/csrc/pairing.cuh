@@ -169,10 +169,10 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
     for (int s = 0; s < BN254_ATE_NAF_LEN; s++) {
         int d = k::ATE_NAF[s];
         if (s) fp12_sqr(f, f);  // f = 1 on the first step
-#if BN_PAIR_LINES
         // Two pairs: the two lines of a step are multiplied with each other first and f once with their product (23 Fp2
         // products instead of 26).  One thread per item keeps the per-pair path when a pair is dead (it branches around it).
-        if (NP == 2 && (!skip || (live[0] && live[1]))) {
+        const bool paired = BN_PAIR_LINES && NP == 2 && (!skip || (live[0] && live[NP - 1]));
+        if (paired) {
             T2 a0, b0, c0, a1, b1, c1;
             if (FIXED0) line_fixed(l, idx);
             else doubling_step(l, r[0]);
@@ -190,34 +190,33 @@ BN_INL void miller_loop(fp12_t<T2> &f, const fp *const *px, const fp *const *py,
                 fp12_mul_by_034_034(f, a0, b0, c0, a1, b1, c1);
                 idx++;
             }
-            continue;
-        }
-#endif
-#pragma unroll
-        for (int i = 0; i < NP; i++) {
-            if (skip && !live[i]) continue;
-            if (FIXED0 && i == 0) {
-                ell_fixed(f, idx, *px[0], *py[0], live[0]);
-            } else {
-                doubling_step(l, r[i]);
-                if (skip) ell(f, l, *px[i], *py[i]);
-                else ell_sel(f, l, *px[i], *py[i], live[i]);
-            }
-        }
-        idx++;
-        if (d) {
+        } else {
 #pragma unroll
             for (int i = 0; i < NP; i++) {
                 if (skip && !live[i]) continue;
                 if (FIXED0 && i == 0) {
                     ell_fixed(f, idx, *px[0], *py[0], live[0]);
                 } else {
-                    addition_step(l, r[i], *qx[i], d > 0 ? *qy[i] : nqy[i]);
+                    doubling_step(l, r[i]);
                     if (skip) ell(f, l, *px[i], *py[i]);
                     else ell_sel(f, l, *px[i], *py[i], live[i]);
                 }
             }
             idx++;
+            if (d) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    if (skip && !live[i]) continue;
+                    if (FIXED0 && i == 0) {
+                        ell_fixed(f, idx, *px[0], *py[0], live[0]);
+                    } else {
+                        addition_step(l, r[i], *qx[i], d > 0 ? *qy[i] : nqy[i]);
+                        if (skip) ell(f, l, *px[i], *py[i]);
+                        else ell_sel(f, l, *px[i], *py[i], live[i]);
+                    }
+                }
+                idx++;
+            }
         }
     }
     // two Frobenius additions: Q1 = psi(Q), Q2 = -psi^2(Q)
