@@ -102,3 +102,42 @@ def verify_randomized_sharded(ctx, variant, pks_shard, msgs_shard, sigs_shard, d
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
         ok = int(t.item())
     return local, ok
+
+
+def shard_keys(msg_counts, world, rank):
+    """Same-key jobs shard by KEY: rank r owns the contiguous keys [nk r / world, nk (r + 1) / world) and with them the tuples
+    [sum(counts[:k_lo]), sum(counts[:k_hi])).  Returns (k_lo, k_hi, t_lo, t_hi)."""
+    k_lo, k_hi = shard_range(len(msg_counts), world, rank)
+    t_lo = sum(msg_counts[:k_lo])
+    return k_lo, k_hi, t_lo, t_lo + sum(msg_counts[k_lo:k_hi])
+
+
+def verify_same_key_sharded(ctx, variant, pks_shard, msg_counts_shard, msgs_shard, sigs_shard, dst, seed, rand_bits=64, flags=VALIDATE,
+                            gather=False, device=None, group=None):
+    """Same-key randomised verification of a sharded job: every rank checks ITS keys (a key and all its tuples live on one
+    rank, so there is no data-path collective) with a per-rank seed derived from the common `seed`; one all-reduce (MIN) of a
+    single byte tells every rank whether the whole job was accepted, and gather=True additionally all-gathers the per-key
+    verdicts (padded to the longest shard) so that every rank holds all of them in key order.
+    Returns (this rank's per-key verdicts or, with gather, the whole job's; whole-job verdict 0/1)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank_seed = hashlib.sha256(bytes(seed) + struct.pack("<I", rank)).digest()
+    local = ctx.verify_same_key_randomized(variant, pks_shard, msg_counts_shard, msgs_shard, sigs_shard, dst, rank_seed, rand_bits=rand_bits, flags=flags)
+    ok = int(all(local)) if len(local) else 1
+    if world == 1:
+        return local, ok
+    t = torch.tensor([ok], dtype=torch.uint8, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    ok = int(t.item())
+    if not gather:
+        return local, ok
+    n = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    lens = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(lens, n, group=group)
+    longest = max(int(x.item()) for x in lens)
+    pad = torch.zeros(max(1, longest), dtype=torch.uint8, device=device)
+    if len(local):
+        pad[:len(local)] = torch.tensor(list(local), dtype=torch.uint8, device=device)
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return b"".join(bytes(o.cpu().numpy())[:int(l.item())] for o, l in zip(outs, lens)), ok

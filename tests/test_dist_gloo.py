@@ -1,6 +1,6 @@
 """world_size-2 gloo test of the N>1 host path (bls_bn254_b200/dist.py): shard ranges, the single
 all-gather of Fp12 partials for aggregate verification, gathered accept bytes, the all-reduced verdict of the
-randomised batch verification.  No GPU here, so the
+randomised batch verification, and the same-key path sharded by key.  No GPU here, so the
 per-rank compute is a stand-in built on the CPU oracle (tests may use it); the plumbing under test
 (sharding, record layout, collective, finish) is the code the GPU ranks run."""
 import os
@@ -63,6 +63,9 @@ class OracleCtx:
     def verify_batch_randomized(self, variant, pks, msgs, sigs, dst, seed, group=256, rand_bits=64, flags=0):
         return self.o.verify_batch_randomized(variant, pks, msgs, sigs, dst, seed, group=group, rand_bits=rand_bits, flags=flags)
 
+    def verify_same_key_randomized(self, variant, pks, msg_counts, msgs, sigs, dst, seed, rand_bits=64, flags=0):
+        return self.o.verify_same_key_randomized(variant, pks, msg_counts, msgs, sigs, dst, seed, rand_bits=rand_bits, flags=flags)
+
 
 def _make(n):
     import hashlib
@@ -79,6 +82,7 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, str(ROOT))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    import hashlib
     import torch.distributed as dist
     from bls_bn254_b200 import dist as bd
     from oracle import orc
@@ -110,7 +114,19 @@ def _worker(rank, world, port, q):
         seed = bytes(range(32))
         rnd_good = bd.verify_randomized_sharded(ctx, 0, p, m, s, DST, seed, group_size=3)
         rnd_bad = bd.verify_randomized_sharded(ctx, 0, p, bad_msgs, s, DST, seed, group_size=3)
-        q.put((rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad))
+        # same-key grouping: 5 keys with 3, 0, 2, 4, 1 messages; keys (with their tuples) are what the ranks share out
+        counts = [3, 0, 2, 4, 1]
+        nk, nt = len(counts), sum(counts)
+        key_of = [k for k, c in enumerate(counts) for _ in range(c)]
+        kmsgs = [b"stream %d" % i for i in range(nt)]
+        ksc = b"".join(hashlib.sha256(b"k%d" % key_of[i]).digest() for i in range(nt))
+        ksc = b"".join((int.from_bytes(ksc[32 * i:32 * i + 32], "big") % R).to_bytes(32, "big") for i in range(nt))
+        ksigs = bytearray(orc.g1_mul(orc.hash_to_g1(kmsgs, DST), ksc))
+        ksigs[64 * 6:64 * 7] = ksigs[64 * 7:64 * 8]                      # key 3's second tuple carries its third signature
+        k_lo, k_hi, t_lo, t_hi = bd.shard_keys(counts, world, rank)
+        sk = bd.verify_same_key_sharded(ctx, 0, pks[128 * k_lo:128 * k_hi], counts[k_lo:k_hi], kmsgs[t_lo:t_hi], bytes(ksigs[64 * t_lo:64 * t_hi]), DST,
+                                        seed, flags=0, gather=True)
+        q.put((rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad, sk))
     finally:
         dist.destroy_process_group()
 
@@ -129,7 +145,9 @@ def test_world_size_2_gloo():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad in res:
+    for rank, ok, ok_bad, ok_badkey, got, rnd_good, rnd_bad, sk in res:
+        # keys 0, 1 on rank 0 and 2, 3, 4 on rank 1: the key without tuples and the key with a swapped signature reject
+        assert sk == (b"\x01\x00\x01\x00\x01", 0)
         assert ok == 1 and ok_bad == 0 and ok_badkey == 0
         assert got == b"\x01\x01\x01\x01\x01\x00\x01\x01"
         # 11 tuples over 2 ranks = 5 + 6: two groups of <= 3 per rank; rank 1's first message was tampered with
