@@ -168,6 +168,26 @@ impl Context {
         self.ck(rc)?;
         Ok(ok)
     }
+    /// Same-key randomised verification: key k owns tuples `key_offsets[k] .. key_offsets[k + 1]` of `blob` / `sigs` (tuples
+    /// sorted by key); one accept byte per KEY from one pairing check over the randomised sums of its signatures and message
+    /// points (`seed` = 32 fresh CSPRNG bytes per call).
+    #[allow(clippy::too_many_arguments)]
+    pub fn verify_same_key_randomized(&mut self, variant: i32, pks: &[u8], key_offsets: &[u64], blob: &[u8], offsets: &[u64], sigs: &[u8],
+                                      dst: &[u8], flags: u32, seed: &[u8; 32], rand_bits: i32) -> Result<Vec<u8>, Bn254Error> {
+        let nk = key_offsets.len().saturating_sub(1);
+        let n = offsets.len().saturating_sub(1);
+        let (rpk, rsig) = Self::recs(variant);
+        if pks.len() != rpk * nk || sigs.len() != rsig * n || key_offsets.first() != Some(&0) || key_offsets.last() != Some(&(n as u64)) {
+            return Err(Bn254Error::BadArgument("buffer lengths / key offsets".into()));
+        }
+        let mut ok = vec![0u8; nk];
+        let rc = unsafe {
+            ffi::bn254_verify_same_key_randomized(self.h, variant, pks.as_ptr(), key_offsets.as_ptr(), nk, blob.as_ptr(), offsets.as_ptr(), sigs.as_ptr(),
+                                                  dst.as_ptr(), dst.len(), flags, seed.as_ptr(), rand_bits, ok.as_mut_ptr())
+        };
+        self.ck(rc)?;
+        Ok(ok)
+    }
     /// Distinct-message aggregate verification: one multi-Miller product, one final exponentiation.
     pub fn aggregate_verify(&mut self, variant: i32, pks: &[u8], blob: &[u8], offsets: &[u64], agg_sig: &[u8], dst: &[u8], flags: u32)
                             -> Result<bool, Bn254Error> {
