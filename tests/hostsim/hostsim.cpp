@@ -135,7 +135,8 @@ EXPORT void sim_g2_mul(const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t 
 }
 // Fp12 tower operations of tower.cuh one at a time (384-byte wire elements, pairings.rs:499-514), for both Fp2 representations
 // where that applies.  op: 0 mul, 1 sqr, 2 inv, 3 conj, 4/5/6 frobenius p^1 / p^2 / p^3, 7 cyclotomic square (a must be in the
-// cyclotomic subgroup), 8 sparse product a * (c0 + c3 w + c4 w^3) with (c0, c3, c4) = the first three Fp2 of b
+// cyclotomic subgroup), 8 sparse product a * (c0 + c3 w + c4 w^3) with (c0, c3, c4) = the first three Fp2 of b, 9 the paired
+// sparse product a * l * l' of the two-pair Miller loops with l from the first and l' from the last three Fp2 of b
 EXPORT int sim_fp12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
     fp12 x, y, r;
     if (!fp12_from_bytes(x, a)) return -1;
@@ -148,6 +149,7 @@ EXPORT int sim_fp12_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out)
         case 4: case 5: case 6: fp12_frob(r, x, op - 3); break;
         case 7: cyclotomic_square(r, x); break;
         case 8: r = x; fp12_mul_by_034(r, y.c0.c0, y.c0.c1, y.c0.c2); break;
+        case 9: r = x; fp12_mul_by_034_034(r, y.c0.c0, y.c0.c1, y.c0.c2, y.c1.c0, y.c1.c1, y.c1.c2); break;
         default: return -2;
     }
     fp12_to_bytes(out, r);
@@ -375,6 +377,7 @@ static void l2_op_body(void *vp) {
         case 3: fp12_conj(r, x); break;
         case 4: case 5: case 6: fp12_frob(r, x, a->op - 3); break;
         case 7: cyclotomic_square(r, x); break;
+        case 9: r = x; fp12_mul_by_034_034(r, y.c0.c0, y.c0.c1, y.c0.c2, y.c1.c0, y.c1.c1, y.c1.c2); break;
         default: r = x; fp12_mul_by_034(r, y.c0.c0, y.c0.c1, y.c0.c2); break;
     }
     fp12_store(a->r, r);

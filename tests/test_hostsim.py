@@ -156,7 +156,7 @@ def test_scalar_mul_and_codecs(sim, orc):
 
 def test_fp12_tower_operations_one_by_one(sim, orc):
     """Fp6 / Fp12 product, square, inverse, conjugate, the three Frobenius maps, the Granger-Scott cyclotomic square and the
-    sparse 0/3/4 line product of the device code against the big-integer model (oracle/pymodel.py) -- the operations no
+    sparse 0/3/4 line product (single and paired) of the device code against the big-integer model (oracle/pymodel.py) -- the operations no
     reference test pins individually -- plus the identities x * x^-1 = 1 and frob_k(x) = x^(p^k)"""
     from oracle import pymodel as pm
     rng = random.Random(31)
@@ -185,6 +185,12 @@ def test_fp12_tower_operations_one_by_one(sim, orc):
             assert call(3 + k, x) == pm.gt_to_repr(pm.f12_frob(x, k))
         c0, c3, c4 = y[0]
         assert call(8, x, y) == pm.gt_to_repr(pm.f12_mul(x, pm.f12_sparse034(c0, c3, c4)))
+        # the paired product of the two-pair Miller loops: x * l * l' (sparse by sparse first), also with a neutral / a zero line
+        d0, d3, d4 = y[1]
+        assert call(9, x, y) == pm.gt_to_repr(pm.f12_mul(pm.f12_mul(x, pm.f12_sparse034(c0, c3, c4)), pm.f12_sparse034(d0, d3, d4)))
+        neutral = (y[0], ((1, 0), (0, 0), (0, 0)))
+        assert call(9, x, neutral) == call(8, x, y)
+        assert call(9, x, (y[0], ((0, 0), (0, 0), (0, 0)))) == pm.gt_to_repr(tuple(tuple((0, 0) for _ in range(3)) for _ in range(2)))
     x = rnd12()
     assert call(4, x) == pm.gt_to_repr(pm.f12_pow(x, P))          # Frobenius really is the p-th power
     # cyclotomic subgroup: x^((p^6 - 1)(p^2 + 1)); there squaring has the compressed Granger-Scott form and conj = inverse
